@@ -1,0 +1,339 @@
+"""duckdb-cubit_b200 — B200-native CUBIT bitmap-index scan (merge → decode → probe).
+
+This package is a thin ctypes binding over the C-ABI in include/cubit_gpu.h
+(libcubit_gpu.so: hand-written sm_100a kernels + C++ host code).  It exists for the
+tests and bench.py; the product is the shared library, and DuckDB binds to it from C++
+(INTEGRATION.md).  There is no CPU fallback: loading fails loudly if the library has
+not been built, and every compute call fails if no B200 is present.
+
+The directory name has a hyphen, so import it with
+    importlib.import_module("duckdb-cubit_b200")      (tests/conftest.py does this)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcubit_gpu.so")
+HOST_LIB_PATH = os.path.join(_HERE, "libcubit_host.so")
+
+# ---- mirror of include/cubit_gpu.h -------------------------------------------------
+ABI_VERSION = 1
+OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5
+MAX_STREAMS = 64
+MAX_PROBE_COLS = 8
+Q_ROWIDS, Q_BITVECTOR, Q_VALUES, Q_TIMING, Q_UNFUSED, Q_ASYNC = 1, 2, 4, 8, 16, 32
+AGG_NONE, AGG_SUM, AGG_SUM_PROD = 0, 1, 2
+
+# every symbol include/cubit_gpu.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "cubit_gpu_abi_version", "cubit_gpu_last_error", "cubit_gpu_device_count", "cubit_gpu_create",
+    "cubit_gpu_destroy", "cubit_gpu_set_stream", "cubit_gpu_words_per_bitvector", "cubit_gpu_launch_count",
+    "cubit_gpu_index_create", "cubit_gpu_upload_bitvector", "cubit_gpu_download_bitvector", "cubit_gpu_index_build",
+    "cubit_gpu_bitvector_count", "cubit_gpu_set_delta", "cubit_gpu_merge_deltas", "cubit_gpu_upload_column",
+    "cubit_gpu_download_column", "cubit_gpu_synth_column", "cubit_gpu_drop_column", "cubit_gpu_query",
+    "cubit_gpu_result_wait", "cubit_gpu_result_get", "cubit_gpu_fetch", "cubit_gpu_fetch_bitvector",
+    "cubit_gpu_free_result", "cubit_gpu_probe",
+]
+
+
+class BvRef(C.Structure):
+    _fields_ = [("index_id", C.c_int32), ("value_id", C.c_uint32)]
+
+
+class PredGroup(C.Structure):
+    _fields_ = [("n_refs", C.c_uint32), ("refs", C.POINTER(BvRef))]
+
+
+class Query(C.Structure):
+    _fields_ = [("n_groups", C.c_uint32), ("groups", C.POINTER(PredGroup)), ("flags", C.c_uint32),
+                ("n_cols", C.c_uint32), ("cols", C.POINTER(C.c_int32)), ("agg_kind", C.c_int32),
+                ("agg_col_a", C.c_int32), ("agg_col_b", C.c_int32)]
+
+
+class ResultInfo(C.Structure):
+    _fields_ = [("count", C.c_uint64), ("sum_lo", C.c_uint64), ("sum_hi", C.c_int64), ("capacity", C.c_uint64),
+                ("n_streams", C.c_uint32), ("n_launches", C.c_uint32), ("delta_entries", C.c_uint64),
+                ("algo_bytes_scan", C.c_uint64), ("algo_bytes_probe", C.c_uint64), ("ms_scan", C.c_float),
+                ("ms_probe", C.c_float), ("ms_total", C.c_float), ("fused", C.c_uint32),
+                ("d_rowids", C.c_void_p), ("d_bitvector", C.c_void_p), ("d_values", C.c_void_p * MAX_PROBE_COLS)]
+
+
+class CubitError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("cubit_gpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libcubit_gpu.so.  Raises (never falls back) if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s not built — run `python duckdb-cubit_b200/build.py` "
+                          "(there is no CPU fallback for the CUBIT GPU path)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u64, i64, u32, i32 = C.c_void_p, C.c_uint64, C.c_int64, C.c_uint32, C.c_int32
+    P = C.POINTER
+    sig = {
+        "cubit_gpu_abi_version": ([], C.c_int),
+        "cubit_gpu_last_error": ([], C.c_char_p),
+        "cubit_gpu_device_count": ([P(C.c_int)], C.c_int),
+        "cubit_gpu_create": ([C.c_int, u64, i64, u32, P(vp)], C.c_int),
+        "cubit_gpu_destroy": ([vp], C.c_int),
+        "cubit_gpu_set_stream": ([vp, vp], C.c_int),
+        "cubit_gpu_words_per_bitvector": ([vp, P(u64)], C.c_int),
+        "cubit_gpu_launch_count": ([vp, P(u64)], C.c_int),
+        "cubit_gpu_index_create": ([vp, u32, P(i32)], C.c_int),
+        "cubit_gpu_upload_bitvector": ([vp, i32, u32, vp, u64], C.c_int),
+        "cubit_gpu_download_bitvector": ([vp, i32, u32, vp, u64], C.c_int),
+        "cubit_gpu_index_build": ([vp, i32, i32, i64], C.c_int),
+        "cubit_gpu_bitvector_count": ([vp, i32, u32, P(u64)], C.c_int),
+        "cubit_gpu_set_delta": ([vp, i32, u32, vp, u64], C.c_int),
+        "cubit_gpu_merge_deltas": ([vp, i32], C.c_int),
+        "cubit_gpu_upload_column": ([vp, i32, vp, u32, u64], C.c_int),
+        "cubit_gpu_download_column": ([vp, i32, vp, u32, u64], C.c_int),
+        "cubit_gpu_synth_column": ([vp, i32, i32, u64, u64, u32, u32, u32], C.c_int),
+        "cubit_gpu_drop_column": ([vp, i32], C.c_int),
+        "cubit_gpu_query": ([vp, P(Query), P(vp)], C.c_int),
+        "cubit_gpu_result_wait": ([vp], C.c_int),
+        "cubit_gpu_result_get": ([vp, P(ResultInfo)], C.c_int),
+        "cubit_gpu_fetch": ([vp, u64, u64, vp, u32, P(vp)], C.c_int),
+        "cubit_gpu_fetch_bitvector": ([vp, vp, u64], C.c_int),
+        "cubit_gpu_free_result": ([vp], C.c_int),
+        "cubit_gpu_probe": ([vp, i32, vp, u64, vp, P(u64), P(i64)], C.c_int),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = res
+    if L.cubit_gpu_abi_version() != ABI_VERSION:
+        raise ImportError("libcubit_gpu.so ABI %d != binding %d" % (L.cubit_gpu_abi_version(), ABI_VERSION))
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != OK:
+        raise CubitError(rc, load_library().cubit_gpu_last_error().decode())
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = load_library().cubit_gpu_device_count(C.byref(n))
+    return n.value if rc == OK else 0
+
+
+def int128(lo, hi):
+    return (int(hi) << 64) + int(lo)
+
+
+class QueryPlan:
+    """A cubit_query kept alive on the host side (ctypes arrays) so it can be re-issued cheaply."""
+
+    def __init__(self, groups, flags=Q_ROWIDS, cols=(), agg=AGG_NONE, agg_a=-1, agg_b=-1):
+        self._ref_arrays = []
+        self._groups = (PredGroup * len(groups))()
+        for g, grp in enumerate(groups):
+            arr = (BvRef * len(grp))()
+            for i, (ix, v) in enumerate(grp):
+                arr[i].index_id, arr[i].value_id = ix, v
+            self._ref_arrays.append(arr)
+            self._groups[g].n_refs = len(grp)
+            self._groups[g].refs = arr
+        self._cols = (C.c_int32 * max(1, len(cols)))(*cols)
+        self.q = Query(len(groups), self._groups, flags, len(cols), self._cols, agg, agg_a, agg_b)
+
+
+class Result:
+    """One query's result set (cubit_gpu_result)."""
+
+    def __init__(self, table, handle, col_dtypes):
+        self._t, self._h, self._dtypes = table, handle, col_dtypes
+        self._info = None
+
+    def wait(self):
+        _check(self._t._L.cubit_gpu_result_wait(self._h))
+        return self
+
+    @property
+    def info(self):
+        if self._info is None:
+            inf = ResultInfo()
+            _check(self._t._L.cubit_gpu_result_get(self._h, C.byref(inf)))
+            self._info = inf
+        return self._info
+
+    @property
+    def count(self):
+        return int(self.info.count)
+
+    @property
+    def sum(self):
+        return int128(self.info.sum_lo, self.info.sum_hi)
+
+    def fetch(self, offset=0, n=None, rowids=True, out_ids=None, out_cols=None):
+        """→ (row_ids or None, [column arrays]) for result rows [offset, offset+n)"""
+        if n is None:
+            n = self.count - offset
+        ids = None
+        if rowids:
+            ids = out_ids[:n] if out_ids is not None else np.empty(n, dtype=np.int64)
+        cols = []
+        ptrs = (C.c_void_p * max(1, len(self._dtypes)))()
+        for c, dt in enumerate(self._dtypes):
+            a = out_cols[c][:n] if out_cols is not None else np.empty(n, dtype=dt)
+            cols.append(a)
+            ptrs[c] = a.ctypes.data
+        _check(self._t._L.cubit_gpu_fetch(self._h, offset, n, ids.ctypes.data if ids is not None else None,
+                                          len(self._dtypes), ptrs))
+        return ids, cols
+
+    def bitvector(self):
+        q = np.empty(self._t.n_words, dtype=np.uint64)
+        _check(self._t._L.cubit_gpu_fetch_bitvector(self._h, q.ctypes.data, len(q)))
+        return q
+
+    def free(self):
+        if self._h is not None:
+            self._t._L.cubit_gpu_free_result(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.free()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class CubitTable:
+    """One table shard resident on one B200 (cubit_gpu_table)."""
+
+    def __init__(self, n_rows, row_base=0, seg_bits=65536, device=0):
+        self._L = load_library()
+        h = C.c_void_p()
+        _check(self._L.cubit_gpu_create(device, n_rows, row_base, seg_bits, C.byref(h)))
+        self._h = h
+        self.n_rows, self.row_base, self.seg_bits, self.device = n_rows, row_base, seg_bits, device
+        self.n_words = (n_rows + 63) // 64
+        self._col_dtype = {}
+
+    def close(self):
+        if self._h is not None:
+            self._L.cubit_gpu_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(self._L.cubit_gpu_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    @property
+    def launch_count(self):
+        n = C.c_uint64(0)
+        _check(self._L.cubit_gpu_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    # ---- index
+    def create_index(self, cardinality):
+        ix = C.c_int32(-1)
+        _check(self._L.cubit_gpu_index_create(self._h, cardinality, C.byref(ix)))
+        return ix.value
+
+    def upload_bitvector(self, index_id, value_id, words):
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        _check(self._L.cubit_gpu_upload_bitvector(self._h, index_id, value_id, words.ctypes.data, len(words)))
+
+    def upload_index(self, bitvectors):
+        """bitvectors: [card, n_words] uint64 → new index id"""
+        ix = self.create_index(len(bitvectors))
+        for v, w in enumerate(bitvectors):
+            self.upload_bitvector(ix, v, w)
+        return ix
+
+    def download_bitvector(self, index_id, value_id):
+        out = np.empty(self.n_words, dtype=np.uint64)
+        _check(self._L.cubit_gpu_download_bitvector(self._h, index_id, value_id, out.ctypes.data, len(out)))
+        return out
+
+    def build_index(self, index_id, col_id, base_value=0):
+        _check(self._L.cubit_gpu_index_build(self._h, index_id, col_id, base_value))
+
+    def bitvector_count(self, index_id, value_id):
+        n = C.c_uint64(0)
+        _check(self._L.cubit_gpu_bitvector_count(self._h, index_id, value_id, C.byref(n)))
+        return n.value
+
+    def set_delta(self, index_id, value_id, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        _check(self._L.cubit_gpu_set_delta(self._h, index_id, value_id, rows.ctypes.data if len(rows) else None,
+                                           len(rows)))
+
+    def merge_deltas(self, index_id):
+        _check(self._L.cubit_gpu_merge_deltas(self._h, index_id))
+
+    # ---- columns
+    def upload_column(self, col_id, data):
+        data = np.ascontiguousarray(data)
+        if data.dtype.itemsize not in (4, 8):
+            raise ValueError("columns are 4 or 8 bytes wide")
+        _check(self._L.cubit_gpu_upload_column(self._h, col_id, data.ctypes.data, data.dtype.itemsize, len(data)))
+        self._col_dtype[col_id] = data.dtype
+
+    def download_column(self, col_id):
+        dt = self._col_dtype[col_id]
+        out = np.empty(self.n_rows, dtype=dt)
+        _check(self._L.cubit_gpu_download_column(self._h, col_id, out.ctypes.data, dt.itemsize, len(out)))
+        return out
+
+    def synth_column(self, col_id, kind, seed=0, threshold=0, card=100, hot_lo=10, hot_n=10):
+        _check(self._L.cubit_gpu_synth_column(self._h, col_id, kind, seed, threshold, card, hot_lo, hot_n))
+        self._col_dtype[col_id] = np.dtype(np.int64 if kind == 0 else np.int32)
+
+    def drop_column(self, col_id):
+        _check(self._L.cubit_gpu_drop_column(self._h, col_id))
+        self._col_dtype.pop(col_id, None)
+
+    # ---- query
+    def execute(self, plan):
+        """issue a prepared QueryPlan → Result"""
+        h = C.c_void_p()
+        _check(self._L.cubit_gpu_query(self._h, C.byref(plan.q), C.byref(h)))
+        ncols = plan.q.n_cols if (plan.q.flags & Q_VALUES) else 0
+        return Result(self, h, [self._col_dtype[plan._cols[c]] for c in range(ncols)])
+
+    def query(self, groups, flags=Q_ROWIDS, cols=(), agg=AGG_NONE, agg_a=-1, agg_b=-1):
+        """groups: [[(index_id, value_id), ...], ...]  — OR inside a group, AND across groups"""
+        return self.execute(QueryPlan(groups, flags, cols, agg, agg_a, agg_b))
+
+    def probe(self, col_id, row_ids, want_sum=False):
+        """gather col[row_ids] (the DataTable::Fetch analog) → (values, sum or None)"""
+        row_ids = np.ascontiguousarray(row_ids, dtype=np.int64)
+        dt = self._col_dtype[col_id]
+        out = np.empty(len(row_ids), dtype=dt)
+        lo, hi = C.c_uint64(0), C.c_int64(0)
+        _check(self._L.cubit_gpu_probe(self._h, col_id, row_ids.ctypes.data if len(row_ids) else None, len(row_ids),
+                                       out.ctypes.data, C.byref(lo) if want_sum else None,
+                                       C.byref(hi) if want_sum else None))
+        return out, (int128(lo.value, hi.value) if want_sum else None)

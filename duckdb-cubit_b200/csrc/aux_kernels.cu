@@ -1,0 +1,397 @@
+// aux_kernels.cu — the kernels either side of the fused scan:
+//   * cubit_probe_kernel      column probe at sorted row IDs (+ SUM / SUM(a*b))
+//                             — the DataTable::Fetch analog
+//                             (reference: src/storage/data_table.cpp:373-377 →
+//                              row_group_collection.cpp:264-288 → FixedSizeFetchRow
+//                              fixed_size_uncompressed.cpp:169-178)
+//   * cubit_index_build_kernel  per-value bitvectors from a column scan
+//                             (CREATE INDEX analog, plan_create_index.cpp:16-130)
+//   * popcount / delta merge-back / synthetic column generators
+#include "kernels.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cubit {
+
+__device__ __forceinline__ void add128(unsigned long long &lo, long long &hi, long long v) {
+	unsigned long long uv = (unsigned long long)v;
+	lo += uv;
+	hi += (long long)(lo < uv) + (v >> 63);
+}
+__device__ __forceinline__ void add128(unsigned long long &lo, long long &hi, unsigned long long lo2, long long hi2) {
+	lo += lo2;
+	hi += hi2 + (long long)(lo < lo2);
+}
+
+// ------------------------------------------------------------------- probe
+constexpr int kProbeThreads = 256;
+constexpr int kProbePairs = 4; // row-ID pairs per thread per iteration (8 independent gathers in flight)
+
+__device__ __forceinline__ void agg_row(const ProbeArgs &a, int64_t local, unsigned long long &lo, long long &hi,
+                                        unsigned int &ovf) {
+	if (a.agg_kind == 1) {
+		add128(lo, hi, __ldg(a.agg_a + local));
+	} else if (a.agg_kind == 2) {
+		const long long x = __ldg(a.agg_a + local);
+		const long long y = __ldg(a.agg_b + local);
+		const long long pr = x * y;
+		if (__mul64hi(x, y) != (pr >> 63)) {
+			ovf = 1;
+		}
+		add128(lo, hi, pr);
+	}
+}
+
+__global__ void __launch_bounds__(kProbeThreads) cubit_probe_kernel(const __grid_constant__ ProbeArgs a) {
+	const unsigned long long n = a.count_ptr ? *a.count_ptr : a.n;
+	const unsigned long long n_pairs = n >> 1;
+	unsigned long long lo = 0;
+	long long hi = 0;
+	unsigned int ovf = 0;
+
+	const unsigned long long stride = (unsigned long long)gridDim.x * kProbeThreads * kProbePairs;
+	for (unsigned long long base = (unsigned long long)blockIdx.x * kProbeThreads * kProbePairs; base < n_pairs;
+	     base += stride) {
+		longlong2 id[kProbePairs];
+		bool ok[kProbePairs];
+#pragma unroll
+		for (int u = 0; u < kProbePairs; u++) {
+			const unsigned long long p = base + (unsigned long long)u * kProbeThreads + threadIdx.x;
+			ok[u] = p < n_pairs;
+			id[u] = ok[u] ? __ldg(reinterpret_cast<const longlong2 *>(a.ids) + p) : make_longlong2(0, 0);
+		}
+		for (int c = 0; c < a.n_cols; c++) {
+			if (a.elem_bytes[c] == 8) {
+				const long long *col = static_cast<const long long *>(a.col[c]);
+				longlong2 v[kProbePairs];
+#pragma unroll
+				for (int u = 0; u < kProbePairs; u++) {
+					if (ok[u]) {
+						const int64_t l0 = id[u].x - a.row_base, l1 = id[u].y - a.row_base;
+						if (l1 == l0 + 1 && (l0 & 1) == 0) { // dense aligned run: one 128-bit load
+							v[u] = __ldg(reinterpret_cast<const longlong2 *>(col + l0));
+						} else {
+							v[u].x = __ldg(col + l0);
+							v[u].y = __ldg(col + l1);
+						}
+					}
+				}
+#pragma unroll
+				for (int u = 0; u < kProbePairs; u++) {
+					if (ok[u]) {
+						const unsigned long long p = base + (unsigned long long)u * kProbeThreads + threadIdx.x;
+						__stcs(reinterpret_cast<longlong2 *>(a.out[c]) + p, v[u]);
+					}
+				}
+			} else {
+				const int *col = static_cast<const int *>(a.col[c]);
+				int2 v[kProbePairs];
+#pragma unroll
+				for (int u = 0; u < kProbePairs; u++) {
+					if (ok[u]) {
+						v[u].x = __ldg(col + (id[u].x - a.row_base));
+						v[u].y = __ldg(col + (id[u].y - a.row_base));
+					}
+				}
+#pragma unroll
+				for (int u = 0; u < kProbePairs; u++) {
+					if (ok[u]) {
+						const unsigned long long p = base + (unsigned long long)u * kProbeThreads + threadIdx.x;
+						__stcs(reinterpret_cast<int2 *>(a.out[c]) + p, v[u]);
+					}
+				}
+			}
+		}
+		if (a.agg_kind) {
+#pragma unroll
+			for (int u = 0; u < kProbePairs; u++) {
+				if (ok[u]) {
+					agg_row(a, id[u].x - a.row_base, lo, hi, ovf);
+					agg_row(a, id[u].y - a.row_base, lo, hi, ovf);
+				}
+			}
+		}
+	}
+	// odd tail element
+	if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+		const int64_t l = a.ids[n - 1] - a.row_base;
+		for (int c = 0; c < a.n_cols; c++) {
+			if (a.elem_bytes[c] == 8) {
+				static_cast<long long *>(a.out[c])[n - 1] = static_cast<const long long *>(a.col[c])[l];
+			} else {
+				static_cast<int *>(a.out[c])[n - 1] = static_cast<const int *>(a.col[c])[l];
+			}
+		}
+		if (a.agg_kind) {
+			agg_row(a, l, lo, hi, ovf);
+		}
+	}
+	if (!a.agg_kind) {
+		return;
+	}
+	__shared__ BlockPartial red[kProbeThreads / 32];
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		const unsigned long long olo = __shfl_xor_sync(0xffffffffu, lo, d);
+		const long long ohi = __shfl_xor_sync(0xffffffffu, hi, d);
+		add128(lo, hi, olo, ohi);
+		ovf |= __shfl_xor_sync(0xffffffffu, ovf, d);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		red[threadIdx.x >> 5].sum_lo = lo;
+		red[threadIdx.x >> 5].sum_hi = hi;
+		red[threadIdx.x >> 5].pad = ovf;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned long long tlo = 0, tov = 0;
+		long long thi = 0;
+		for (int w = 0; w < kProbeThreads / 32; w++) {
+			add128(tlo, thi, red[w].sum_lo, red[w].sum_hi);
+			tov |= red[w].pad;
+		}
+		volatile BlockPartial *dst = a.partials + blockIdx.x;
+		dst->sum_lo = tlo;
+		dst->sum_hi = thi;
+		dst->pad = tov;
+		__threadfence();
+		if (atomicAdd(a.done, 1u) == gridDim.x - 1) {
+			__threadfence();
+			unsigned long long flo = 0, fov = 0;
+			long long fhi = 0;
+			for (unsigned b = 0; b < gridDim.x; b++) {
+				const volatile BlockPartial *p = a.partials + b;
+				add128(flo, fhi, p->sum_lo, p->sum_hi);
+				fov |= p->pad;
+			}
+			a.hdr->sum_lo = flo;
+			a.hdr->sum_hi = fhi;
+			a.hdr->overflow = (unsigned int)fov;
+		}
+	}
+}
+
+cudaError_t launch_probe(const ProbeArgs &args, int sm_count, cudaStream_t stream) {
+	const int grid = sm_count * 8;
+	cubit_probe_kernel<<<grid, kProbeThreads, 0, stream>>>(args);
+	return cudaGetLastError();
+}
+int probe_grid(int sm_count) {
+	return sm_count * 8;
+}
+
+// ------------------------------------------------------------- index build
+// One CTA converts kBuildRows consecutive rows per iteration.  Each warp reads
+// 32 consecutive rows (coalesced); __match_any_sync gives every lane the mask
+// of lanes holding the same value, which IS the 32-bit slice of that value's
+// bitvector for these rows.  Slices are collected in a shared-memory tile
+// [value][kBuildRows/32] (each slot written by exactly one lane) and flushed as
+// contiguous runs of kBuildRows/8 bytes per value.
+constexpr int kBuildThreads = 256;
+constexpr int kBuildRows = 4096;
+constexpr int kBuildSlots = kBuildRows / 32; // u32 slots per value per tile
+
+template <typename T>
+__global__ void __launch_bounds__(kBuildThreads)
+    cubit_index_build_kernel(const T *__restrict__ col, uint64_t n_rows, int64_t base_value, uint32_t v_lo,
+                             uint32_t v_n, uint64_t *__restrict__ bitvectors, uint64_t words_per_bv) {
+	extern __shared__ uint32_t tile[]; // [v_n][kBuildSlots]
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint64_t n_tiles = (n_rows + kBuildRows - 1) / kBuildRows;
+	for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+		for (uint32_t i = threadIdx.x; i < v_n * kBuildSlots; i += kBuildThreads) {
+			tile[i] = 0;
+		}
+		__syncthreads();
+		const uint64_t row0 = t * kBuildRows;
+#pragma unroll 4
+		for (int it = 0; it < kBuildSlots / (kBuildThreads / 32); it++) {
+			const int slot = it * (kBuildThreads / 32) + warp;
+			const uint64_t r = row0 + (uint64_t)slot * 32 + lane;
+			long long rel = -1;
+			if (r < n_rows) {
+				rel = (long long)col[r] - base_value - (long long)v_lo;
+			}
+			const bool in = rel >= 0 && rel < (long long)v_n;
+			const unsigned key = in ? (unsigned)rel : 0xffffffffu;
+			const unsigned same = __match_any_sync(0xffffffffu, key);
+			if (in && (__ffs(same) - 1) == lane) {
+				tile[(uint32_t)rel * kBuildSlots + slot] = same;
+			}
+		}
+		__syncthreads();
+		// flush: per value kBuildSlots u32 = kBuildRows/64 u64 words, contiguous in B_v
+		const uint64_t word0 = row0 / 64;
+		constexpr int kWordsPerVal = kBuildRows / 64;
+		for (uint32_t i = threadIdx.x; i < v_n * kWordsPerVal; i += kBuildThreads) {
+			const uint32_t v = i / kWordsPerVal, w = i % kWordsPerVal;
+			if (word0 + w < words_per_bv) {
+				const uint64_t val = (uint64_t)tile[v * kBuildSlots + 2 * w] |
+				                     ((uint64_t)tile[v * kBuildSlots + 2 * w + 1] << 32);
+				bitvectors[(uint64_t)(v_lo + v) * words_per_bv + word0 + w] = val;
+			}
+		}
+		__syncthreads();
+	}
+}
+
+cudaError_t launch_index_build(const void *col, uint32_t elem_bytes, uint64_t n_rows, int64_t base_value,
+                               uint32_t cardinality, uint64_t *bitvectors, uint64_t words_per_bv, int sm_count,
+                               cudaStream_t stream, int *n_launches) {
+	// values per pass bounded by shared memory (≤ 200 KiB tile)
+	const uint32_t max_v = (200u * 1024u) / (kBuildSlots * 4u);
+	int launches = 0;
+	static bool configured = false;
+	if (!configured) {
+		cudaFuncSetAttribute(cubit_index_build_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+		cudaFuncSetAttribute(cubit_index_build_kernel<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                     200 * 1024);
+		configured = true;
+	}
+	const uint64_t n_tiles = (n_rows + kBuildRows - 1) / kBuildRows;
+	for (uint32_t v_lo = 0; v_lo < cardinality; v_lo += max_v) {
+		const uint32_t v_n = (cardinality - v_lo) < max_v ? (cardinality - v_lo) : max_v;
+		const size_t smem = (size_t)v_n * kBuildSlots * 4;
+		int per_sm = (int)((220u * 1024u) / (smem + 1024));
+		if (per_sm < 1) {
+			per_sm = 1;
+		}
+		if (per_sm > 8) {
+			per_sm = 8;
+		}
+		uint64_t grid = (uint64_t)sm_count * per_sm;
+		if (grid > n_tiles) {
+			grid = n_tiles;
+		}
+		if (grid < 1) {
+			grid = 1;
+		}
+		if (elem_bytes == 4) {
+			cubit_index_build_kernel<int><<<(unsigned)grid, kBuildThreads, smem, stream>>>(
+			    static_cast<const int *>(col), n_rows, base_value, v_lo, v_n, bitvectors, words_per_bv);
+		} else {
+			cubit_index_build_kernel<long long><<<(unsigned)grid, kBuildThreads, smem, stream>>>(
+			    static_cast<const long long *>(col), n_rows, base_value, v_lo, v_n, bitvectors, words_per_bv);
+		}
+		launches++;
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) {
+			return e;
+		}
+	}
+	if (n_launches) {
+		*n_launches = launches;
+	}
+	return cudaSuccess;
+}
+
+// ---------------------------------------------------------------- popcount
+__global__ void cubit_popcount_many_kernel(const uint64_t *__restrict__ bitvectors, uint64_t words_per_bv,
+                                           unsigned long long *__restrict__ out) {
+	// grid = (blocks_per_bv, n_bv)
+	const uint64_t *bv = bitvectors + (uint64_t)blockIdx.y * words_per_bv;
+	unsigned long long c = 0;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words_per_bv;
+	     i += (uint64_t)gridDim.x * blockDim.x) {
+		c += __popcll(bv[i]);
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		c += __shfl_xor_sync(0xffffffffu, c, d);
+	}
+	if ((threadIdx.x & 31) == 0 && c) {
+		atomicAdd(out + blockIdx.y, c);
+	}
+}
+
+cudaError_t launch_popcount_many(const uint64_t *bitvectors, uint64_t words_per_bv, uint32_t n_bv,
+                                 unsigned long long *out, cudaStream_t stream) {
+	cudaError_t e = cudaMemsetAsync(out, 0, sizeof(unsigned long long) * n_bv, stream);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	uint64_t bx = (words_per_bv + 256 * 8 - 1) / (256 * 8);
+	if (bx > 1024) {
+		bx = 1024;
+	}
+	if (bx < 1) {
+		bx = 1;
+	}
+	for (uint32_t v0 = 0; v0 < n_bv; v0 += 32768) {
+		const uint32_t nv = (n_bv - v0) < 32768u ? (n_bv - v0) : 32768u;
+		dim3 grid((unsigned)bx, nv);
+		cubit_popcount_many_kernel<<<grid, 256, 0, stream>>>(bitvectors + (uint64_t)v0 * words_per_bv, words_per_bv,
+		                                                      out + v0);
+	}
+	return cudaGetLastError();
+}
+
+cudaError_t launch_popcount(const uint64_t *words, uint64_t n_words, unsigned long long *out, int sm_count,
+                            cudaStream_t stream) {
+	(void)sm_count;
+	return launch_popcount_many(words, n_words, 1, out, stream);
+}
+
+// ------------------------------------------------------- delta merge-back
+__global__ void cubit_apply_delta_kernel(uint64_t *__restrict__ bv, const uint32_t *__restrict__ doff,
+                                         const DeltaEnt *__restrict__ dent, uint32_t n_seg, uint32_t seg_words) {
+	for (uint32_t seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
+		const uint32_t d0 = doff[seg], d1 = doff[seg + 1];
+		for (uint32_t e = d0 + threadIdx.x; e < d1; e += blockDim.x) {
+			bv[(uint64_t)seg * seg_words + dent[e].word] ^= dent[e].mask;
+		}
+	}
+}
+
+cudaError_t launch_apply_delta(uint64_t *bv, const uint32_t *doff, const DeltaEnt *dent, uint32_t n_seg,
+                               uint32_t seg_words, cudaStream_t stream) {
+	unsigned grid = n_seg < 4096u ? n_seg : 4096u;
+	if (grid < 1) {
+		grid = 1;
+	}
+	cubit_apply_delta_kernel<<<grid, 64, 0, stream>>>(bv, doff, dent, n_seg, seg_words);
+	return cudaGetLastError();
+}
+
+// ------------------------------------------------------ synthetic columns
+// restated in oracle/cubit_oracle.c (oracle_synth_value)
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+	x += 0x9E3779B97F4A7C15ull;
+	x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+	x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+	return x ^ (x >> 31);
+}
+
+__global__ void cubit_synth_kernel(void *col, int kind, uint64_t n_rows, int64_t row_base, uint64_t seed,
+                                   uint64_t threshold, uint32_t card, uint32_t hot_lo, uint32_t hot_n) {
+	for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows;
+	     r += (uint64_t)gridDim.x * blockDim.x) {
+		if (kind == 0) {
+			static_cast<long long *>(col)[r] = row_base + (long long)r;
+		} else {
+			const uint64_t z = splitmix64(seed + (uint64_t)row_base + r);
+			const uint64_t y = z >> 7;
+			uint32_t v;
+			if (z < threshold) {
+				v = hot_lo + (uint32_t)(y % hot_n);
+			} else {
+				v = (uint32_t)(y % (card - hot_n));
+				if (v >= hot_lo) {
+					v += hot_n;
+				}
+			}
+			static_cast<int *>(col)[r] = (int)v;
+		}
+	}
+}
+
+cudaError_t launch_synth_column(void *col, int kind, uint64_t n_rows, int64_t row_base, uint64_t seed,
+                                uint64_t threshold, uint32_t card, uint32_t hot_lo, uint32_t hot_n, int sm_count,
+                                cudaStream_t stream) {
+	cubit_synth_kernel<<<sm_count * 16, 256, 0, stream>>>(col, kind, n_rows, row_base, seed, threshold, card, hot_lo,
+	                                                      hot_n);
+	return cudaGetLastError();
+}
+
+} // namespace cubit

@@ -1,0 +1,1201 @@
+// cubit_gpu.cu — host side of the C-ABI declared in include/cubit_gpu.h.
+//
+// Owns the HBM-resident state of one table shard (value bitvectors padded to
+// whole segments, pending-delta CSR lists, decoded column slices), plans a query
+// (flattens the AND-of-ORs predicate into an ordered stream list, bounds the
+// result size from per-bitvector cardinalities) and launches the kernels in
+// scan_kernel.cu / aux_kernels.cu on the table's stream.  There is no CPU
+// fallback anywhere in this file: every compute entry point launches CUDA work
+// or fails.
+#include "../../include/cubit_gpu.h"
+#include "kernels.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace cubit;
+
+// ------------------------------------------------------------------- errors
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	g_last_error = buf;
+	return code;
+}
+
+#define CU_TRY(expr)                                                                                                   \
+	do {                                                                                                               \
+		cudaError_t _e = (expr);                                                                                       \
+		if (_e != cudaSuccess) {                                                                                       \
+			return fail(_e == cudaErrorMemoryAllocation ? CUBIT_ENOMEM : CUBIT_ECUDA, "%s: %s (%s:%d)", #expr,         \
+			            cudaGetErrorString(_e), __FILE__, __LINE__);                                                   \
+		}                                                                                                              \
+	} while (0)
+
+// ------------------------------------------------------------------ objects
+struct Delta {
+	uint32_t *d_off = nullptr; // [n_seg + 1]
+	DeltaEnt *d_ent = nullptr;
+	uint64_t n_ent = 0;  // delta words
+	uint64_t n_rows = 0; // flipped rows (after cancellation)
+};
+
+struct Index {
+	uint32_t card = 0;
+	uint64_t *d_bits = nullptr;   // [card][words_per_bv]
+	std::vector<uint64_t> counts; // popcount of every B_v as stored
+	bool counts_valid = false;
+	std::vector<Delta> deltas; // [card]
+};
+
+struct Column {
+	void *d = nullptr;
+	uint32_t elem = 0;
+	uint64_t n = 0;
+};
+
+struct cubit_gpu_table {
+	int device = 0;
+	int sm_count = 0;
+	uint64_t n_rows = 0;
+	int64_t row_base = 0;
+	uint32_t seg_bits = 0, seg_words = 0, n_seg = 0;
+	uint64_t n_words = 0;      // ceil(n_rows / 64)
+	uint64_t words_per_bv = 0; // n_seg * seg_words
+	cudaStream_t own_stream = nullptr;
+	cudaStream_t stream = nullptr;
+	std::vector<Index *> indexes;
+	std::map<int32_t, Column> columns;
+	std::mutex mu;
+	uint64_t launches = 0;
+	unsigned long long *d_scratch = nullptr; // popcount scratch
+	uint64_t scratch_n = 0;
+	std::vector<ResultHeader *> hdr_pool; // pinned result headers, recycled across queries
+};
+
+struct cubit_gpu_result {
+	cubit_gpu_table *t = nullptr;
+	cudaStream_t stream = nullptr;
+	unsigned char *d_block = nullptr; // hdr | ctrl | partials | probe done ctr
+	ResultHeader *d_hdr = nullptr;
+	ResultHeader *h_hdr = nullptr; // pinned
+	long long *d_ids = nullptr;
+	uint64_t *d_q = nullptr;
+	uint64_t *d_q_tmp = nullptr;
+	void *d_vals[CUBIT_MAX_PROBE_COLS] = {};
+	uint32_t val_elem[CUBIT_MAX_PROBE_COLS] = {};
+	uint32_t n_cols = 0;
+	uint32_t flags = 0;
+	int agg_kind = 0;
+	cudaEvent_t ev[4] = {};
+	cudaEvent_t ev_done = nullptr;
+	bool timing = false, probe_timed = false;
+	uint64_t probe_widths = 0; // bytes per selected row the probe needs (distinct columns, + row-ID re-read)
+	bool finished = false;
+	cubit_result_info info = {};
+};
+
+static int use_device(const cubit_gpu_table *t) {
+	CU_TRY(cudaSetDevice(t->device));
+	return CUBIT_OK;
+}
+
+// ------------------------------------------------------------------ library
+extern "C" int cubit_gpu_abi_version(void) {
+	return CUBIT_GPU_ABI_VERSION;
+}
+
+extern "C" const char *cubit_gpu_last_error(void) {
+	return g_last_error.c_str();
+}
+
+extern "C" int cubit_gpu_device_count(int *count) {
+	if (!count) {
+		return fail(CUBIT_EINVAL, "count is NULL");
+	}
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) {
+		*count = 0;
+		return fail(CUBIT_ENODEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+	}
+	*count = n;
+	return CUBIT_OK;
+}
+
+// -------------------------------------------------------------------- table
+extern "C" int cubit_gpu_create(int device, uint64_t n_rows, int64_t row_base, uint32_t seg_bits,
+                                cubit_gpu_table **out) {
+	if (!out) {
+		return fail(CUBIT_EINVAL, "out is NULL");
+	}
+	*out = nullptr;
+	if (seg_bits != 32768 && seg_bits != 65536 && seg_bits != 131072) {
+		return fail(CUBIT_EINVAL, "seg_bits must be 32768, 65536 or 131072 (got %u)", seg_bits);
+	}
+	if (n_rows == 0) {
+		return fail(CUBIT_EINVAL, "n_rows must be > 0");
+	}
+	if (row_base < 0 || (uint64_t)row_base % 64 != 0) {
+		return fail(CUBIT_EINVAL, "row_base must be a non-negative multiple of 64");
+	}
+	if ((n_rows + seg_bits - 1) / seg_bits > 0x7fffffffull) {
+		return fail(CUBIT_EINVAL, "too many segments");
+	}
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0) {
+		return fail(CUBIT_ENODEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+	}
+	if (device < 0 || device >= ndev) {
+		return fail(CUBIT_EINVAL, "device %d out of range (have %d)", device, ndev);
+	}
+	CU_TRY(cudaSetDevice(device));
+	cubit_gpu_table *t = new (std::nothrow) cubit_gpu_table();
+	if (!t) {
+		return fail(CUBIT_ENOMEM, "host allocation failed");
+	}
+	t->device = device;
+	t->n_rows = n_rows;
+	t->row_base = row_base;
+	t->seg_bits = seg_bits;
+	t->seg_words = seg_bits / 64;
+	t->n_seg = (uint32_t)((n_rows + seg_bits - 1) / seg_bits);
+	t->n_words = (n_rows + 63) / 64;
+	t->words_per_bv = (uint64_t)t->n_seg * t->seg_words;
+	cudaDeviceProp prop;
+	e = cudaGetDeviceProperties(&prop, device);
+	if (e != cudaSuccess) {
+		delete t;
+		return fail(CUBIT_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+	}
+	if (prop.major < 10) {
+		delete t;
+		return fail(CUBIT_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+		            prop.major, prop.minor);
+	}
+	t->sm_count = prop.multiProcessorCount;
+	e = cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking);
+	if (e != cudaSuccess) {
+		delete t;
+		return fail(CUBIT_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+	}
+	t->stream = t->own_stream;
+	// keep freed result buffers in the stream-ordered pool (no cudaMalloc per query)
+	cudaMemPool_t pool;
+	if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+		uint64_t thresh = UINT64_MAX;
+		cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+	}
+	*out = t;
+	return CUBIT_OK;
+}
+
+static void free_delta(Delta &d) {
+	if (d.d_off) {
+		cudaFree(d.d_off);
+	}
+	if (d.d_ent) {
+		cudaFree(d.d_ent);
+	}
+	d = Delta();
+}
+
+extern "C" int cubit_gpu_destroy(cubit_gpu_table *t) {
+	if (!t) {
+		return CUBIT_OK;
+	}
+	cudaSetDevice(t->device);
+	cudaStreamSynchronize(t->stream);
+	for (Index *ix : t->indexes) {
+		if (!ix) {
+			continue;
+		}
+		for (Delta &d : ix->deltas) {
+			free_delta(d);
+		}
+		if (ix->d_bits) {
+			cudaFree(ix->d_bits);
+		}
+		delete ix;
+	}
+	for (auto &kv : t->columns) {
+		if (kv.second.d) {
+			cudaFree(kv.second.d);
+		}
+	}
+	if (t->d_scratch) {
+		cudaFree(t->d_scratch);
+	}
+	for (ResultHeader *h : t->hdr_pool) {
+		cudaFreeHost(h);
+	}
+	if (t->own_stream) {
+		cudaStreamDestroy(t->own_stream);
+	}
+	delete t;
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_set_stream(cubit_gpu_table *t, void *cuda_stream) {
+	if (!t) {
+		return fail(CUBIT_EINVAL, "table is NULL");
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	CU_TRY(cudaStreamSynchronize(t->stream));
+	t->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : t->own_stream;
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_words_per_bitvector(const cubit_gpu_table *t, uint64_t *n_words) {
+	if (!t || !n_words) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	*n_words = t->n_words;
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_launch_count(const cubit_gpu_table *t, uint64_t *n) {
+	if (!t || !n) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	*n = t->launches;
+	return CUBIT_OK;
+}
+
+// -------------------------------------------------------------------- index
+static Index *get_index(cubit_gpu_table *t, int32_t index_id) {
+	if (index_id < 0 || (size_t)index_id >= t->indexes.size()) {
+		return nullptr;
+	}
+	return t->indexes[index_id];
+}
+
+extern "C" int cubit_gpu_index_create(cubit_gpu_table *t, uint32_t cardinality, int32_t *index_id) {
+	if (!t || !index_id) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	if (cardinality == 0 || cardinality > (1u << 20)) {
+		return fail(CUBIT_EINVAL, "cardinality %u out of range", cardinality);
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	Index *ix = new (std::nothrow) Index();
+	if (!ix) {
+		return fail(CUBIT_ENOMEM, "host allocation failed");
+	}
+	ix->card = cardinality;
+	const size_t bytes = (size_t)cardinality * t->words_per_bv * 8;
+	cudaError_t e = cudaMalloc(&ix->d_bits, bytes);
+	if (e != cudaSuccess) {
+		delete ix;
+		return fail(CUBIT_ENOMEM, "cudaMalloc(%zu bytes) for index: %s", bytes, cudaGetErrorString(e));
+	}
+	e = cudaMemsetAsync(ix->d_bits, 0, bytes, t->stream);
+	if (e != cudaSuccess) {
+		cudaFree(ix->d_bits);
+		delete ix;
+		return fail(CUBIT_ECUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+	}
+	ix->counts.assign(cardinality, 0);
+	ix->counts_valid = true; // all zero
+	ix->deltas.resize(cardinality);
+	t->indexes.push_back(ix);
+	*index_id = (int32_t)t->indexes.size() - 1;
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_upload_bitvector(cubit_gpu_table *t, int32_t index_id, uint32_t value_id,
+                                          const uint64_t *words, uint64_t n_words) {
+	if (!t || !words) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	Index *ix = get_index(t, index_id);
+	if (!ix || value_id >= ix->card) {
+		return fail(CUBIT_EINVAL, "bad (index %d, value %u)", index_id, value_id);
+	}
+	if (n_words != t->n_words) {
+		return fail(CUBIT_EINVAL, "n_words %llu != ceil(n_rows/64) = %llu", (unsigned long long)n_words,
+		            (unsigned long long)t->n_words);
+	}
+	const unsigned tail = (unsigned)(t->n_rows % 64);
+	if (tail && (words[n_words - 1] >> tail) != 0) {
+		return fail(CUBIT_EINVAL, "bits at positions >= n_rows must be zero");
+	}
+	uint64_t *dst = ix->d_bits + (uint64_t)value_id * t->words_per_bv;
+	CU_TRY(cudaMemcpyAsync(dst, words, n_words * 8, cudaMemcpyHostToDevice, t->stream));
+	CU_TRY(cudaStreamSynchronize(t->stream));
+	ix->counts_valid = false;
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_download_bitvector(cubit_gpu_table *t, int32_t index_id, uint32_t value_id, uint64_t *words,
+                                            uint64_t n_words) {
+	if (!t || !words) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	Index *ix = get_index(t, index_id);
+	if (!ix || value_id >= ix->card) {
+		return fail(CUBIT_EINVAL, "bad (index %d, value %u)", index_id, value_id);
+	}
+	if (n_words != t->n_words) {
+		return fail(CUBIT_EINVAL, "n_words mismatch");
+	}
+	const uint64_t *src = ix->d_bits + (uint64_t)value_id * t->words_per_bv;
+	CU_TRY(cudaMemcpyAsync(words, src, n_words * 8, cudaMemcpyDeviceToHost, t->stream));
+	CU_TRY(cudaStreamSynchronize(t->stream));
+	return CUBIT_OK;
+}
+
+static int refresh_counts(cubit_gpu_table *t, Index *ix) {
+	if (ix->counts_valid) {
+		return CUBIT_OK;
+	}
+	if (t->scratch_n < ix->card) {
+		if (t->d_scratch) {
+			cudaFree(t->d_scratch);
+			t->d_scratch = nullptr;
+		}
+		CU_TRY(cudaMalloc(&t->d_scratch, sizeof(unsigned long long) * ix->card));
+		t->scratch_n = ix->card;
+	}
+	CU_TRY(launch_popcount_many(ix->d_bits, t->words_per_bv, ix->card, t->d_scratch, t->stream));
+	t->launches += (ix->card + 32767) / 32768;
+	static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "u64");
+	CU_TRY(cudaMemcpyAsync(ix->counts.data(), t->d_scratch, sizeof(uint64_t) * ix->card, cudaMemcpyDeviceToHost,
+	                       t->stream));
+	CU_TRY(cudaStreamSynchronize(t->stream));
+	ix->counts_valid = true;
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_bitvector_count(cubit_gpu_table *t, int32_t index_id, uint32_t value_id, uint64_t *count) {
+	if (!t || !count) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	Index *ix = get_index(t, index_id);
+	if (!ix || value_id >= ix->card) {
+		return fail(CUBIT_EINVAL, "bad (index %d, value %u)", index_id, value_id);
+	}
+	int rc = refresh_counts(t, ix);
+	if (rc) {
+		return rc;
+	}
+	*count = ix->counts[value_id];
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_index_build(cubit_gpu_table *t, int32_t index_id, int32_t col_id, int64_t base_value) {
+	if (!t) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	Index *ix = get_index(t, index_id);
+	if (!ix) {
+		return fail(CUBIT_EINVAL, "bad index %d", index_id);
+	}
+	auto it = t->columns.find(col_id);
+	if (it == t->columns.end()) {
+		return fail(CUBIT_EINVAL, "no column %d", col_id);
+	}
+	const Column &c = it->second;
+	if (c.n != t->n_rows) {
+		return fail(CUBIT_EINVAL, "column %d has %llu rows, table has %llu", col_id, (unsigned long long)c.n,
+		            (unsigned long long)t->n_rows);
+	}
+	for (Delta &d : ix->deltas) {
+		if (d.n_ent) {
+			return fail(CUBIT_ESTATE, "index %d has pending deltas; merge them before a rebuild", index_id);
+		}
+	}
+	int launches = 0;
+	CU_TRY(launch_index_build(c.d, c.elem, t->n_rows, base_value, ix->card, ix->d_bits, t->words_per_bv, t->sm_count,
+	                          t->stream, &launches));
+	t->launches += launches;
+	CU_TRY(cudaStreamSynchronize(t->stream));
+	ix->counts_valid = false;
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_set_delta(cubit_gpu_table *t, int32_t index_id, uint32_t value_id, const int64_t *rows,
+                                   uint64_t n) {
+	if (!t || (n && !rows)) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	Index *ix = get_index(t, index_id);
+	if (!ix || value_id >= ix->card) {
+		return fail(CUBIT_EINVAL, "bad (index %d, value %u)", index_id, value_id);
+	}
+	std::vector<int64_t> sorted(rows, rows + n);
+	std::sort(sorted.begin(), sorted.end());
+	if (n && (sorted.front() < 0 || (uint64_t)sorted.back() >= t->n_rows)) {
+		return fail(CUBIT_EINVAL, "delta row out of range [0, %llu)", (unsigned long long)t->n_rows);
+	}
+	// CSR per segment of (word-in-segment, mask); a row listed twice cancels
+	std::vector<uint32_t> off((size_t)t->n_seg + 1, 0);
+	std::vector<DeltaEnt> ent;
+	ent.reserve(n);
+	uint64_t flipped = 0;
+	size_t i = 0;
+	while (i < sorted.size()) {
+		const uint64_t gw = (uint64_t)sorted[i] / 64; // global word
+		uint64_t mask = 0;
+		while (i < sorted.size() && (uint64_t)sorted[i] / 64 == gw) {
+			mask ^= 1ull << ((uint64_t)sorted[i] % 64);
+			i++;
+		}
+		if (mask) {
+			DeltaEnt e;
+			e.word = (uint32_t)(gw % t->seg_words);
+			e.pad = 0;
+			e.mask = mask;
+			ent.push_back(e);
+			off[gw / t->seg_words + 1]++;
+			flipped += (uint64_t)__builtin_popcountll(mask);
+		}
+	}
+	for (size_t s = 0; s < t->n_seg; s++) {
+		off[s + 1] += off[s];
+	}
+	if (ent.size() > 0xfffffff0ull) {
+		return fail(CUBIT_EINVAL, "too many delta words");
+	}
+	CU_TRY(cudaStreamSynchronize(t->stream)); // no query may still read the old lists
+	Delta &d = ix->deltas[value_id];
+	free_delta(d);
+	if (ent.empty()) {
+		return CUBIT_OK;
+	}
+	CU_TRY(cudaMalloc(&d.d_off, off.size() * sizeof(uint32_t)));
+	CU_TRY(cudaMalloc(&d.d_ent, ent.size() * sizeof(DeltaEnt)));
+	CU_TRY(cudaMemcpyAsync(d.d_off, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, t->stream));
+	CU_TRY(cudaMemcpyAsync(d.d_ent, ent.data(), ent.size() * sizeof(DeltaEnt), cudaMemcpyHostToDevice, t->stream));
+	CU_TRY(cudaStreamSynchronize(t->stream));
+	d.n_ent = ent.size();
+	d.n_rows = flipped;
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_merge_deltas(cubit_gpu_table *t, int32_t index_id) {
+	if (!t) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	Index *ix = get_index(t, index_id);
+	if (!ix) {
+		return fail(CUBIT_EINVAL, "bad index %d", index_id);
+	}
+	bool any = false;
+	for (uint32_t v = 0; v < ix->card; v++) {
+		Delta &d = ix->deltas[v];
+		if (!d.n_ent) {
+			continue;
+		}
+		CU_TRY(launch_apply_delta(ix->d_bits + (uint64_t)v * t->words_per_bv, d.d_off, d.d_ent, t->n_seg,
+		                          t->seg_words, t->stream));
+		t->launches++;
+		any = true;
+	}
+	CU_TRY(cudaStreamSynchronize(t->stream));
+	if (any) {
+		for (Delta &d : ix->deltas) {
+			free_delta(d);
+		}
+		ix->counts_valid = false;
+	}
+	return CUBIT_OK;
+}
+
+// ------------------------------------------------------------------ columns
+extern "C" int cubit_gpu_upload_column(cubit_gpu_table *t, int32_t col_id, const void *data, uint32_t elem_bytes,
+                                       uint64_t n) {
+	if (!t || !data) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	if (elem_bytes != 4 && elem_bytes != 8) {
+		return fail(CUBIT_EINVAL, "elem_bytes must be 4 or 8");
+	}
+	if (n != t->n_rows) {
+		return fail(CUBIT_EINVAL, "column has %llu rows, table has %llu", (unsigned long long)n,
+		            (unsigned long long)t->n_rows);
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	Column &c = t->columns[col_id];
+	if (c.d && (c.elem != elem_bytes || c.n != n)) {
+		CU_TRY(cudaStreamSynchronize(t->stream));
+		cudaFree(c.d);
+		c.d = nullptr;
+	}
+	if (!c.d) {
+		// + 16 bytes so a 128-bit load of the last aligned pair never leaves the allocation
+		CU_TRY(cudaMalloc(&c.d, (size_t)n * elem_bytes + 16));
+	}
+	c.elem = elem_bytes;
+	c.n = n;
+	CU_TRY(cudaMemcpyAsync(c.d, data, (size_t)n * elem_bytes, cudaMemcpyHostToDevice, t->stream));
+	CU_TRY(cudaStreamSynchronize(t->stream));
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_download_column(cubit_gpu_table *t, int32_t col_id, void *data, uint32_t elem_bytes,
+                                         uint64_t n) {
+	if (!t || !data) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	auto it = t->columns.find(col_id);
+	if (it == t->columns.end()) {
+		return fail(CUBIT_EINVAL, "no column %d", col_id);
+	}
+	if (it->second.elem != elem_bytes || n > it->second.n) {
+		return fail(CUBIT_EINVAL, "column %d shape mismatch", col_id);
+	}
+	CU_TRY(cudaMemcpyAsync(data, it->second.d, (size_t)n * elem_bytes, cudaMemcpyDeviceToHost, t->stream));
+	CU_TRY(cudaStreamSynchronize(t->stream));
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_synth_column(cubit_gpu_table *t, int32_t col_id, int32_t kind, uint64_t seed,
+                                      uint64_t threshold, uint32_t card, uint32_t hot_lo, uint32_t hot_n) {
+	if (!t) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	if (kind != 0 && kind != 1) {
+		return fail(CUBIT_EINVAL, "kind must be 0 or 1");
+	}
+	if (kind == 1 && (hot_n == 0 || hot_n >= card || hot_lo + hot_n > card)) {
+		return fail(CUBIT_EINVAL, "bad hot range");
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	const uint32_t elem = kind == 0 ? 8 : 4;
+	Column &c = t->columns[col_id];
+	if (c.d && (c.elem != elem || c.n != t->n_rows)) {
+		CU_TRY(cudaStreamSynchronize(t->stream));
+		cudaFree(c.d);
+		c.d = nullptr;
+	}
+	if (!c.d) {
+		CU_TRY(cudaMalloc(&c.d, (size_t)t->n_rows * elem + 16));
+	}
+	c.elem = elem;
+	c.n = t->n_rows;
+	CU_TRY(launch_synth_column(c.d, kind, t->n_rows, t->row_base, seed, threshold, card, hot_lo, hot_n, t->sm_count,
+	                           t->stream));
+	t->launches++;
+	CU_TRY(cudaStreamSynchronize(t->stream));
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_drop_column(cubit_gpu_table *t, int32_t col_id) {
+	if (!t) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	auto it = t->columns.find(col_id);
+	if (it == t->columns.end()) {
+		return fail(CUBIT_EINVAL, "no column %d", col_id);
+	}
+	CU_TRY(cudaStreamSynchronize(t->stream));
+	cudaFree(it->second.d);
+	t->columns.erase(it);
+	return CUBIT_OK;
+}
+
+// -------------------------------------------------------------------- query
+static void release_result(cubit_gpu_result *r) {
+	cudaStream_t s = r->stream;
+	if (r->d_block) {
+		cudaFreeAsync(r->d_block, s);
+	}
+	if (r->d_ids) {
+		cudaFreeAsync(r->d_ids, s);
+	}
+	if (r->d_q) {
+		cudaFreeAsync(r->d_q, s);
+	}
+	if (r->d_q_tmp) {
+		cudaFreeAsync(r->d_q_tmp, s);
+	}
+	for (auto &p : r->d_vals) {
+		if (p) {
+			cudaFreeAsync(p, s);
+		}
+	}
+	if (r->h_hdr) {
+		r->t->hdr_pool.push_back(r->h_hdr); // caller holds t->mu
+	}
+	for (auto &e : r->ev) {
+		if (e) {
+			cudaEventDestroy(e);
+		}
+	}
+	if (r->ev_done) {
+		cudaEventDestroy(r->ev_done);
+	}
+	delete r;
+}
+
+static int finish_result(cubit_gpu_result *r) {
+	if (r->finished) {
+		return CUBIT_OK;
+	}
+	CU_TRY(cudaEventSynchronize(r->ev_done));
+	r->info.count = r->h_hdr->count;
+	r->info.sum_lo = r->h_hdr->sum_lo;
+	r->info.sum_hi = r->h_hdr->sum_hi;
+	r->info.algo_bytes_scan += 8ull * ((r->flags & CUBIT_Q_ROWIDS) ? r->info.count : 0);
+	// P of SURVEY §8d: M * Σ width over the distinct columns whose values are needed
+	// (+ 8*M when a separate probe kernel re-reads the row IDs)
+	r->info.algo_bytes_probe = r->info.count * r->probe_widths;
+	if (r->timing) {
+		float ms = 0;
+		cudaEventElapsedTime(&ms, r->ev[0], r->ev[1]);
+		r->info.ms_scan = ms;
+		if (r->probe_timed) {
+			cudaEventElapsedTime(&ms, r->ev[1], r->ev[2]);
+			r->info.ms_probe = ms;
+			cudaEventElapsedTime(&ms, r->ev[0], r->ev[2]);
+			r->info.ms_total = ms;
+		} else {
+			r->info.ms_total = r->info.ms_scan;
+		}
+	}
+	r->finished = true;
+	if (r->h_hdr->overflow) {
+		return fail(CUBIT_EINVAL, "Overflow in multiplication of INT64 in SUM(a*b)");
+	}
+	if ((r->flags & (CUBIT_Q_ROWIDS | CUBIT_Q_VALUES)) && r->info.count > r->info.capacity) {
+		return fail(CUBIT_ESTATE, "internal: result %llu exceeds capacity bound %llu",
+		            (unsigned long long)r->info.count, (unsigned long long)r->info.capacity);
+	}
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_result **out) {
+	if (!t || !q || !out) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	*out = nullptr;
+	if (q->n_groups == 0 || !q->groups) {
+		return fail(CUBIT_EINVAL, "query has no predicate groups");
+	}
+	if (q->n_cols > CUBIT_MAX_PROBE_COLS || (q->n_cols && !q->cols)) {
+		return fail(CUBIT_EINVAL, "bad projected column list");
+	}
+	if (q->agg_kind < CUBIT_AGG_NONE || q->agg_kind > CUBIT_AGG_SUM_PROD) {
+		return fail(CUBIT_EINVAL, "bad agg_kind %d", q->agg_kind);
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+
+	// ---- flatten predicate into the ordered stream list
+	ScanArgs sa;
+	memset(&sa, 0, sizeof(sa));
+	uint32_t k = 0;
+	bool has_delta = false;
+	uint64_t delta_entries = 0;
+	uint64_t cap = t->n_rows;
+	for (uint32_t g = 0; g < q->n_groups; g++) {
+		const cubit_pred_group &grp = q->groups[g];
+		if (grp.n_refs == 0 || !grp.refs) {
+			return fail(CUBIT_EINVAL, "predicate group %u is empty", g);
+		}
+		uint64_t group_bound = 0;
+		for (uint32_t i = 0; i < grp.n_refs; i++) {
+			if (k >= (uint32_t)kMaxStreams) {
+				return fail(CUBIT_EINVAL, "query reads more than %d bitvectors", kMaxStreams);
+			}
+			Index *ix = get_index(t, grp.refs[i].index_id);
+			if (!ix || grp.refs[i].value_id >= ix->card) {
+				return fail(CUBIT_EINVAL, "group %u ref %u: bad (index %d, value %u)", g, i, grp.refs[i].index_id,
+				            grp.refs[i].value_id);
+			}
+			int rc = refresh_counts(t, ix);
+			if (rc) {
+				return rc;
+			}
+			const uint32_t v = grp.refs[i].value_id;
+			sa.bv[k] = ix->d_bits + (uint64_t)v * t->words_per_bv;
+			const Delta &d = ix->deltas[v];
+			if (d.n_ent) {
+				sa.doff[k] = d.d_off;
+				sa.dent[k] = d.d_ent;
+				has_delta = true;
+				delta_entries += d.n_ent;
+			}
+			group_bound += ix->counts[v] + d.n_rows;
+			k++;
+		}
+		sa.group_end |= 1ull << (k - 1);
+		cap = std::min(cap, group_bound);
+	}
+	sa.k = k;
+	sa.n_seg = t->n_seg;
+	sa.row_base = t->row_base;
+
+	// ---- projected / aggregate columns
+	const bool want_ids = (q->flags & CUBIT_Q_ROWIDS) != 0;
+	const bool want_vals = (q->flags & CUBIT_Q_VALUES) != 0 && q->n_cols > 0;
+	const bool want_q = (q->flags & CUBIT_Q_BITVECTOR) != 0;
+	const bool unfused = (q->flags & CUBIT_Q_UNFUSED) != 0;
+	const Column *vcols[CUBIT_MAX_PROBE_COLS] = {};
+	bool fusable = !unfused;
+	if (want_vals) {
+		for (uint32_t c = 0; c < q->n_cols; c++) {
+			auto it = t->columns.find(q->cols[c]);
+			if (it == t->columns.end()) {
+				return fail(CUBIT_EINVAL, "no column %d", q->cols[c]);
+			}
+			vcols[c] = &it->second;
+			if (it->second.elem != 8) {
+				fusable = false;
+			}
+		}
+		if (q->n_cols > (uint32_t)kMaxFusedCols) {
+			fusable = false;
+		}
+	}
+	const Column *agg_a = nullptr, *agg_b = nullptr;
+	if (q->agg_kind != CUBIT_AGG_NONE) {
+		auto it = t->columns.find(q->agg_col_a);
+		if (it == t->columns.end() || it->second.elem != 8) {
+			return fail(CUBIT_EINVAL, "aggregate column %d missing or not 8 bytes wide", q->agg_col_a);
+		}
+		agg_a = &it->second;
+		if (q->agg_kind == CUBIT_AGG_SUM_PROD) {
+			it = t->columns.find(q->agg_col_b);
+			if (it == t->columns.end() || it->second.elem != 8) {
+				return fail(CUBIT_EINVAL, "aggregate column %d missing or not 8 bytes wide", q->agg_col_b);
+			}
+			agg_b = &it->second;
+		}
+	}
+	const bool need_probe = want_vals || q->agg_kind != CUBIT_AGG_NONE;
+	const bool separate_probe = need_probe && !fusable;
+	const bool need_ids_buf = want_ids || separate_probe;
+	if (!need_ids_buf && !want_vals) {
+		cap = 0;
+	}
+	cap = (cap + 1) & ~1ull; // even: the probe kernel moves row IDs in pairs
+
+	// ---- result object
+	cubit_gpu_result *r = new (std::nothrow) cubit_gpu_result();
+	if (!r) {
+		return fail(CUBIT_ENOMEM, "host allocation failed");
+	}
+	r->t = t;
+	r->stream = t->stream;
+	r->flags = q->flags;
+	r->agg_kind = q->agg_kind;
+	r->n_cols = want_vals ? q->n_cols : 0;
+	r->timing = (q->flags & CUBIT_Q_TIMING) != 0;
+	cudaStream_t st = t->stream;
+	int rc = CUBIT_OK;
+#define Q_TRY(expr)                                                                                                    \
+	do {                                                                                                               \
+		cudaError_t _e = (expr);                                                                                       \
+		if (_e != cudaSuccess) {                                                                                       \
+			rc = fail(_e == cudaErrorMemoryAllocation ? CUBIT_ENOMEM : CUBIT_ECUDA, "%s: %s (%s:%d)", #expr,           \
+			          cudaGetErrorString(_e), __FILE__, __LINE__);                                                     \
+			release_result(r);                                                                                         \
+			return rc;                                                                                                 \
+		}                                                                                                              \
+	} while (0)
+
+	const int max_grid = std::max(scan_max_grid(t->seg_words, t->sm_count), probe_grid(t->sm_count));
+	const size_t hdr_bytes = 64;
+	const size_t ctrl_bytes = ((size_t)t->n_seg + 1) * 8;
+	const size_t ctrl_pad = (ctrl_bytes + 63) & ~(size_t)63;
+	const size_t part_bytes = (size_t)max_grid * sizeof(BlockPartial);
+	// layout: hdr | ctrl A | ctrl B (decode pass of the unfused path) | partials | probe done
+	const size_t block_bytes = hdr_bytes + 2 * ctrl_pad + part_bytes + 64;
+	Q_TRY(cudaMallocAsync((void **)&r->d_block, block_bytes, st));
+	r->d_hdr = reinterpret_cast<ResultHeader *>(r->d_block);
+	unsigned long long *ctrl_a = reinterpret_cast<unsigned long long *>(r->d_block + hdr_bytes);
+	unsigned long long *ctrl_b = reinterpret_cast<unsigned long long *>(r->d_block + hdr_bytes + ctrl_pad);
+	BlockPartial *partials = reinterpret_cast<BlockPartial *>(r->d_block + hdr_bytes + 2 * ctrl_pad);
+	unsigned int *probe_done = reinterpret_cast<unsigned int *>(r->d_block + hdr_bytes + 2 * ctrl_pad + part_bytes);
+	if (!t->hdr_pool.empty()) {
+		r->h_hdr = t->hdr_pool.back();
+		t->hdr_pool.pop_back();
+	} else {
+		Q_TRY(cudaHostAlloc((void **)&r->h_hdr, sizeof(ResultHeader), cudaHostAllocDefault));
+	}
+	memset(r->h_hdr, 0, sizeof(ResultHeader));
+	if (need_ids_buf && cap) {
+		Q_TRY(cudaMallocAsync((void **)&r->d_ids, cap * 8, st));
+	}
+	if (want_vals && cap) {
+		for (uint32_t c = 0; c < q->n_cols; c++) {
+			r->val_elem[c] = vcols[c]->elem;
+			Q_TRY(cudaMallocAsync(&r->d_vals[c], cap * vcols[c]->elem, st));
+		}
+	}
+	if (want_q) {
+		Q_TRY(cudaMallocAsync((void **)&r->d_q, t->words_per_bv * 8, st));
+	}
+	if (unfused && !want_q) {
+		Q_TRY(cudaMallocAsync((void **)&r->d_q_tmp, t->words_per_bv * 8, st));
+	}
+	Q_TRY(cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming));
+	if (r->timing) {
+		for (auto &e : r->ev) {
+			Q_TRY(cudaEventCreate(&e));
+		}
+	}
+
+	// zero hdr + both control blocks (+ probe done counter lives at the end)
+	Q_TRY(cudaMemsetAsync(r->d_block, 0, hdr_bytes + 2 * ctrl_pad, st));
+	Q_TRY(cudaMemsetAsync(probe_done, 0, 64, st));
+
+	sa.partials = partials;
+	sa.hdr = r->d_hdr;
+	sa.ids_cap = cap;
+	uint32_t n_launch = 0;
+	if (r->timing) {
+		Q_TRY(cudaEventRecord(r->ev[0], st));
+	}
+	if (!unfused) {
+		// one pass: merge (+delta XOR) + decode (+ fused probe / aggregate when eligible)
+		sa.ctrl = ctrl_a;
+		sa.q_out = r->d_q;
+		sa.ids_out = need_ids_buf ? r->d_ids : nullptr;
+		if (fusable) {
+			if (want_vals && cap) {
+				sa.n_vcols = (int)q->n_cols;
+				for (uint32_t c = 0; c < q->n_cols; c++) {
+					sa.vcol[c] = static_cast<const long long *>(vcols[c]->d);
+					sa.vout[c] = static_cast<long long *>(r->d_vals[c]);
+				}
+			}
+			sa.agg_kind = q->agg_kind;
+			sa.agg_a = agg_a ? static_cast<const long long *>(agg_a->d) : nullptr;
+			sa.agg_b = agg_b ? static_cast<const long long *>(agg_b->d) : nullptr;
+		}
+		Q_TRY(launch_scan(sa, t->seg_words, has_delta, t->sm_count, st, nullptr));
+		n_launch++;
+		r->info.fused = 1;
+	} else {
+		// three separate kernels: K1 merge → Q, K2 decode Q → row IDs, K3 probe
+		uint64_t *qbuf = want_q ? r->d_q : r->d_q_tmp;
+		sa.ctrl = ctrl_a;
+		sa.q_out = qbuf;
+		sa.ids_out = nullptr;
+		Q_TRY(launch_scan(sa, t->seg_words, has_delta, t->sm_count, st, nullptr));
+		n_launch++;
+		if (need_ids_buf) {
+			ScanArgs sd;
+			memset(&sd, 0, sizeof(sd));
+			sd.bv[0] = qbuf;
+			sd.group_end = 1;
+			sd.k = 1;
+			sd.n_seg = t->n_seg;
+			sd.row_base = t->row_base;
+			sd.ctrl = ctrl_b;
+			sd.ids_out = r->d_ids;
+			sd.ids_cap = cap;
+			sd.partials = partials;
+			sd.hdr = r->d_hdr;
+			Q_TRY(launch_scan(sd, t->seg_words, false, t->sm_count, st, nullptr));
+			n_launch++;
+		}
+		r->info.fused = 0;
+	}
+	if (r->timing) {
+		Q_TRY(cudaEventRecord(r->ev[1], st));
+	}
+	if (separate_probe) {
+		ProbeArgs pa;
+		memset(&pa, 0, sizeof(pa));
+		pa.ids = r->d_ids;
+		pa.count_ptr = &r->d_hdr->count;
+		pa.row_base = t->row_base;
+		pa.n_cols = want_vals && cap ? (int)q->n_cols : 0;
+		for (int c = 0; c < pa.n_cols; c++) {
+			pa.col[c] = vcols[c]->d;
+			pa.out[c] = r->d_vals[c];
+			pa.elem_bytes[c] = vcols[c]->elem;
+		}
+		pa.agg_kind = q->agg_kind;
+		pa.agg_a = agg_a ? static_cast<const long long *>(agg_a->d) : nullptr;
+		pa.agg_b = agg_b ? static_cast<const long long *>(agg_b->d) : nullptr;
+		pa.partials = partials;
+		pa.done = probe_done;
+		pa.hdr = r->d_hdr;
+		Q_TRY(launch_probe(pa, t->sm_count, st));
+		n_launch++;
+		if (r->timing) {
+			Q_TRY(cudaEventRecord(r->ev[2], st));
+			r->probe_timed = true;
+		}
+	}
+	Q_TRY(cudaMemcpyAsync(r->h_hdr, r->d_hdr, sizeof(ResultHeader), cudaMemcpyDeviceToHost, st));
+	Q_TRY(cudaEventRecord(r->ev_done, st));
+#undef Q_TRY
+	t->launches += n_launch;
+
+	{
+		std::vector<int32_t> seen;
+		auto add_col = [&](int32_t id, uint32_t w) {
+			if (std::find(seen.begin(), seen.end(), id) == seen.end()) {
+				seen.push_back(id);
+				r->probe_widths += w;
+			}
+		};
+		for (uint32_t c = 0; c < r->n_cols; c++) {
+			add_col(q->cols[c], vcols[c]->elem);
+		}
+		if (q->agg_kind != CUBIT_AGG_NONE) {
+			add_col(q->agg_col_a, 8);
+		}
+		if (q->agg_kind == CUBIT_AGG_SUM_PROD) {
+			add_col(q->agg_col_b, 8);
+		}
+		if (separate_probe) {
+			r->probe_widths += 8;
+		}
+	}
+	r->info.capacity = cap;
+	r->info.n_streams = k;
+	r->info.n_launches = n_launch;
+	r->info.delta_entries = delta_entries;
+	r->info.algo_bytes_scan = (uint64_t)k * t->n_words * 8 + delta_entries * sizeof(DeltaEnt);
+	r->info.d_rowids = want_ids ? reinterpret_cast<const int64_t *>(r->d_ids) : nullptr;
+	r->info.d_bitvector = r->d_q;
+	for (uint32_t c = 0; c < r->n_cols; c++) {
+		r->info.d_values[c] = r->d_vals[c];
+	}
+	if (!(q->flags & CUBIT_Q_ASYNC)) {
+		rc = finish_result(r);
+		if (rc) {
+			release_result(r);
+			return rc;
+		}
+	}
+	*out = r;
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_result_wait(cubit_gpu_result *r) {
+	if (!r) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	cudaSetDevice(r->t->device);
+	return finish_result(r);
+}
+
+extern "C" int cubit_gpu_result_get(cubit_gpu_result *r, cubit_result_info *info) {
+	if (!r || !info) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	cudaSetDevice(r->t->device);
+	int rc = finish_result(r);
+	if (rc) {
+		return rc;
+	}
+	*info = r->info;
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_fetch(cubit_gpu_result *r, uint64_t offset, uint64_t n, int64_t *host_rowids,
+                               uint32_t n_cols, void *const *host_cols) {
+	if (!r) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	cudaSetDevice(r->t->device);
+	int rc = finish_result(r);
+	if (rc) {
+		return rc;
+	}
+	if (offset > r->info.count || n > r->info.count - offset) {
+		return fail(CUBIT_EINVAL, "fetch range [%llu, +%llu) outside result of %llu rows", (unsigned long long)offset,
+		            (unsigned long long)n, (unsigned long long)r->info.count);
+	}
+	if (n_cols > r->n_cols) {
+		return fail(CUBIT_EINVAL, "result has %u projected columns, %u requested", r->n_cols, n_cols);
+	}
+	if (host_rowids && !(r->flags & CUBIT_Q_ROWIDS)) {
+		return fail(CUBIT_ESTATE, "query did not materialise row IDs (CUBIT_Q_ROWIDS)");
+	}
+	if (n == 0) {
+		return CUBIT_OK;
+	}
+	std::lock_guard<std::mutex> lk(r->t->mu);
+	cudaStream_t st = r->stream;
+	if (host_rowids) {
+		CU_TRY(cudaMemcpyAsync(host_rowids, r->d_ids + offset, n * 8, cudaMemcpyDeviceToHost, st));
+	}
+	for (uint32_t c = 0; c < n_cols; c++) {
+		if (host_cols && host_cols[c]) {
+			const size_t w = r->val_elem[c];
+			CU_TRY(cudaMemcpyAsync(host_cols[c], static_cast<const char *>(r->d_vals[c]) + offset * w, n * w,
+			                       cudaMemcpyDeviceToHost, st));
+		}
+	}
+	CU_TRY(cudaStreamSynchronize(st));
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_fetch_bitvector(cubit_gpu_result *r, uint64_t *host_words, uint64_t n_words) {
+	if (!r || !host_words) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	cudaSetDevice(r->t->device);
+	int rc = finish_result(r);
+	if (rc) {
+		return rc;
+	}
+	if (!r->d_q) {
+		return fail(CUBIT_ESTATE, "query did not materialise the bitvector (CUBIT_Q_BITVECTOR)");
+	}
+	if (n_words != r->t->n_words) {
+		return fail(CUBIT_EINVAL, "n_words mismatch");
+	}
+	std::lock_guard<std::mutex> lk(r->t->mu);
+	CU_TRY(cudaMemcpyAsync(host_words, r->d_q, n_words * 8, cudaMemcpyDeviceToHost, r->stream));
+	CU_TRY(cudaStreamSynchronize(r->stream));
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_free_result(cubit_gpu_result *r) {
+	if (!r) {
+		return CUBIT_OK;
+	}
+	cudaSetDevice(r->t->device);
+	std::lock_guard<std::mutex> lk(r->t->mu);
+	release_result(r);
+	return CUBIT_OK;
+}
+
+// -------------------------------------------------------------------- probe
+extern "C" int cubit_gpu_probe(cubit_gpu_table *t, int32_t col_id, const int64_t *host_rowids, uint64_t n,
+                               void *host_out, uint64_t *sum_lo, int64_t *sum_hi) {
+	if (!t || (n && !host_rowids)) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	auto it = t->columns.find(col_id);
+	if (it == t->columns.end()) {
+		return fail(CUBIT_EINVAL, "no column %d", col_id);
+	}
+	const Column &c = it->second;
+	const bool want_sum = sum_lo || sum_hi;
+	if (want_sum && c.elem != 8) {
+		return fail(CUBIT_EINVAL, "SUM needs an 8-byte column");
+	}
+	for (uint64_t i = 0; i < n; i++) {
+		const int64_t l = host_rowids[i] - t->row_base;
+		if (l < 0 || (uint64_t)l >= t->n_rows) {
+			return fail(CUBIT_EINVAL, "row id %lld outside this shard", (long long)host_rowids[i]);
+		}
+	}
+	if (sum_lo) {
+		*sum_lo = 0;
+	}
+	if (sum_hi) {
+		*sum_hi = 0;
+	}
+	if (n == 0) {
+		return CUBIT_OK;
+	}
+	cudaStream_t st = t->stream;
+	const uint64_t cap = (n + 1) & ~1ull;
+	long long *d_ids = nullptr;
+	void *d_out = nullptr;
+	unsigned char *d_blk = nullptr;
+	const int grid = probe_grid(t->sm_count);
+	const size_t blk_bytes = 64 + 64 + (size_t)grid * sizeof(BlockPartial);
+	CU_TRY(cudaMallocAsync((void **)&d_ids, cap * 8, st));
+	CU_TRY(cudaMallocAsync(&d_out, cap * c.elem, st));
+	CU_TRY(cudaMallocAsync((void **)&d_blk, blk_bytes, st));
+	CU_TRY(cudaMemsetAsync(d_blk, 0, 128, st));
+	CU_TRY(cudaMemcpyAsync(d_ids, host_rowids, n * 8, cudaMemcpyHostToDevice, st));
+	ProbeArgs pa;
+	memset(&pa, 0, sizeof(pa));
+	pa.ids = d_ids;
+	pa.n = n;
+	pa.row_base = t->row_base;
+	pa.n_cols = host_out ? 1 : 0;
+	pa.col[0] = c.d;
+	pa.out[0] = d_out;
+	pa.elem_bytes[0] = c.elem;
+	pa.agg_kind = want_sum ? CUBIT_AGG_SUM : CUBIT_AGG_NONE;
+	pa.agg_a = static_cast<const long long *>(c.d);
+	pa.hdr = reinterpret_cast<ResultHeader *>(d_blk);
+	pa.done = reinterpret_cast<unsigned int *>(d_blk + 64);
+	pa.partials = reinterpret_cast<BlockPartial *>(d_blk + 128);
+	CU_TRY(launch_probe(pa, t->sm_count, st));
+	t->launches++;
+	ResultHeader h;
+	if (host_out) {
+		CU_TRY(cudaMemcpyAsync(host_out, d_out, n * c.elem, cudaMemcpyDeviceToHost, st));
+	}
+	CU_TRY(cudaMemcpyAsync(&h, d_blk, sizeof(h), cudaMemcpyDeviceToHost, st));
+	CU_TRY(cudaStreamSynchronize(st));
+	cudaFreeAsync(d_ids, st);
+	cudaFreeAsync(d_out, st);
+	cudaFreeAsync(d_blk, st);
+	if (sum_lo) {
+		*sum_lo = h.sum_lo;
+	}
+	if (sum_hi) {
+		*sum_hi = h.sum_hi;
+	}
+	return CUBIT_OK;
+}

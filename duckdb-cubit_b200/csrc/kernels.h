@@ -1,0 +1,105 @@
+// kernels.h — internal launch interface between the C-ABI host code
+// (cubit_gpu.cu) and the sm_100a kernels.  Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cubit {
+
+constexpr int kMaxStreams = 64;       // == CUBIT_MAX_STREAMS
+constexpr int kMaxFusedCols = 2;      // value columns the fused scan kernel can probe (int64 only)
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kScanThreads = kConsumerThreads + 32; // + one producer warp
+constexpr int kScanStages = 8;                      // bulk-copy ring depth (stages of one segment each)
+
+// One pending-delta word of one (bitvector, segment): XOR `mask` into word
+// `word` of the staged segment.  Words are unique within a (bitvector, segment).
+struct DeltaEnt {
+	uint32_t word;
+	uint32_t pad;
+	uint64_t mask;
+};
+
+// Device-side result header (one per query).
+struct ResultHeader {
+	unsigned long long count;
+	unsigned long long sum_lo;
+	long long sum_hi;
+	unsigned int overflow; // int64 product overflow seen (CUBIT_AGG_SUM_PROD)
+	unsigned int pad;
+};
+
+struct BlockPartial {
+	unsigned long long count;
+	unsigned long long sum_lo;
+	long long sum_hi;
+	unsigned long long pad;
+};
+
+// Per-query control block, zeroed (cudaMemsetAsync) before every scan launch.
+//   [0]            ticket counter (u32) | blocks-done counter (u32)
+//   [1 .. n_seg]   decoupled look-back status word of every segment
+struct ScanArgs {
+	const uint64_t *bv[kMaxStreams];    // value bitvector B_i (padded to whole segments)
+	const uint32_t *doff[kMaxStreams];  // delta CSR offsets [n_seg+1] of D_i, or nullptr
+	const DeltaEnt *dent[kMaxStreams];  // delta entries of D_i
+	uint64_t group_end;                 // bit i: stream i closes its OR group (then Q &= group)
+	uint32_t k;                         // streams
+	uint32_t n_seg;                     // segments (tiles)
+	int64_t row_base;                   // global row ID of local row 0
+	unsigned long long *ctrl;           // control block (see above)
+	uint64_t *q_out;                    // merged bitvector out, or nullptr
+	long long *ids_out;                 // sorted row IDs out, or nullptr
+	unsigned long long ids_cap;         // capacity of ids_out / vals_out in rows
+	const long long *vcol[kMaxFusedCols]; // fused probe: int64 columns (local row indexed)
+	long long *vout[kMaxFusedCols];       // gathered values out (same positions as ids_out), or nullptr
+	int n_vcols;
+	int agg_kind;                       // CUBIT_AGG_*
+	const long long *agg_a;
+	const long long *agg_b;
+	BlockPartial *partials;             // [gridDim.x]
+	ResultHeader *hdr;
+};
+
+struct ProbeArgs {
+	const long long *ids;               // sorted global row IDs
+	const unsigned long long *count_ptr; // device count (hdr->count) or nullptr
+	unsigned long long n;               // used when count_ptr == nullptr
+	int64_t row_base;
+	int n_cols;
+	const void *col[8];
+	void *out[8];
+	uint32_t elem_bytes[8];
+	int agg_kind;
+	const long long *agg_a;
+	const long long *agg_b;
+	BlockPartial *partials;
+	unsigned int *done;                 // blocks-done counter (zeroed)
+	ResultHeader *hdr;                  // count is left untouched; sums written
+};
+
+// ---- launchers (all asynchronous on `stream`; return cudaGetLastError()) ----
+// seg_words ∈ {512, 1024, 2048}.  has_delta: any doff[i] != nullptr.
+cudaError_t launch_scan(const ScanArgs &args, uint32_t seg_words, bool has_delta, int sm_count, cudaStream_t stream,
+                        int *grid_out);
+int scan_max_grid(uint32_t seg_words, int sm_count);
+
+cudaError_t launch_probe(const ProbeArgs &args, int sm_count, cudaStream_t stream);
+int probe_grid(int sm_count);
+
+// index build: B_(col[r]-base) |= bit r, for values in [v_lo, v_lo+v_n)
+cudaError_t launch_index_build(const void *col, uint32_t elem_bytes, uint64_t n_rows, int64_t base_value,
+                               uint32_t cardinality, uint64_t *bitvectors, uint64_t words_per_bv, int sm_count,
+                               cudaStream_t stream, int *n_launches);
+cudaError_t launch_popcount(const uint64_t *words, uint64_t n_words, unsigned long long *out, int sm_count,
+                            cudaStream_t stream);
+cudaError_t launch_popcount_many(const uint64_t *bitvectors, uint64_t words_per_bv, uint32_t n_bv,
+                                 unsigned long long *out, cudaStream_t stream);
+cudaError_t launch_apply_delta(uint64_t *bv, const uint32_t *doff, const DeltaEnt *dent, uint32_t n_seg,
+                               uint32_t seg_words, cudaStream_t stream);
+cudaError_t launch_synth_column(void *col, int kind, uint64_t n_rows, int64_t row_base, uint64_t seed,
+                                uint64_t threshold, uint32_t card, uint32_t hot_lo, uint32_t hot_n, int sm_count,
+                                cudaStream_t stream);
+
+} // namespace cubit

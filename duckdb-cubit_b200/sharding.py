@@ -1,0 +1,49 @@
+"""Row-range sharding of a table over the GPUs of one box.
+
+Bit r of every bitvector and row r of every column depend only on r, so the table is cut
+into contiguous row ranges aligned to the CUBIT segment size; rank g owns rows
+[lo_g, hi_g) of every bitvector, delta list and column.  The scan itself needs no
+collective.  Afterwards:
+  * COUNT / SUM  → one all-reduce of a few int64 limbs (exact: 128-bit sums are split into
+    32-bit limbs so the int64 all-reduce cannot overflow),
+  * row-ID lists → already global (row_base = lo_g) and globally sorted in rank order.
+The reference's own parallel unit is the 122,880-row row group handed out by
+RowGroupCollection::NextParallelScan (src/storage/table/row_group_collection.cpp:174-224).
+"""
+
+N_LIMBS = 5  # 4 x 32-bit limbs of the 128-bit sum + 1 limb for the count
+
+
+def shard_ranges(n_rows, world_size, seg_bits):
+    """→ [(lo, hi)] per rank; every lo is a multiple of seg_bits; ranges tile [0, n_rows)."""
+    n_seg = (n_rows + seg_bits - 1) // seg_bits
+    out = []
+    for g in range(world_size):
+        s0 = n_seg * g // world_size
+        s1 = n_seg * (g + 1) // world_size
+        out.append((min(s0 * seg_bits, n_rows), min(s1 * seg_bits, n_rows)))
+    return out
+
+
+def to_limbs(count, total):
+    """(count, signed 128-bit sum) → N_LIMBS python ints, each < 2^32 (sum as two's complement)"""
+    u = total & ((1 << 128) - 1)
+    return [(u >> (32 * i)) & 0xFFFFFFFF for i in range(4)] + [count]
+
+
+def from_limbs(limbs):
+    """inverse of to_limbs after an element-wise SUM over ranks (limbs may exceed 2^32)"""
+    u = sum(int(limbs[i]) << (32 * i) for i in range(4)) & ((1 << 128) - 1)
+    if u >= 1 << 127:
+        u -= 1 << 128
+    return int(limbs[4]), u
+
+
+def allreduce_aggregate(count, total, dist=None, device=None):
+    """exact global (COUNT, SUM) over all ranks; torch.distributed does the plumbing"""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return count, total
+    import torch
+    t = torch.tensor(to_limbs(count, total), dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return from_limbs(t.tolist())

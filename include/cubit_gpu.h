@@ -1,0 +1,190 @@
+/*
+ * cubit_gpu.h — C-ABI of the B200-native CUBIT bitmap-index scan path.
+ *
+ * This is the drop-in boundary: the only symbols the
+ * reference's C++ operator code binds to.  Everything is `extern "C"`, plain
+ * pointers and sizes; no C++ / torch types cross it.  The reference-side
+ * caller is the table function that PhysicalTableScan::GetData dispatches to
+ * (reference: src/execution/operator/scan/physical_table_scan.cpp:82-103 →
+ * TableFunction::function, src/include/duckdb/function/table_function.hpp:194)
+ * and the index object that would sit beside ART as a BoundIndex
+ * (src/include/duckdb/execution/index/bound_index.hpp:67-126).  INTEGRATION.md
+ * shows the binding a DuckDB maintainer adds.
+ *
+ * Conventions
+ *   - every function returns CUBIT_OK (0) or a negative CUBIT_E* code; the
+ *     message is available from cubit_gpu_last_error() (thread-local).  No
+ *     exception ever crosses the ABI (reference errors are C++ exceptions that
+ *     the table function re-throws: table_function-c.cpp:203-212).
+ *   - bit order is DuckDB's ValidityMask order: row r is bit (r % 64) of
+ *     64-bit word r / 64 (src/include/duckdb/common/types/validity_mask.hpp:163-168).
+ *   - row IDs are row_t = int64_t (src/include/duckdb/common/typedefs.hpp:19),
+ *     ascending and duplicate free, the contract of ART::Scan
+ *     (src/execution/index/art/art.cpp:974-985).  A shard created with
+ *     row_base = B reports global row IDs B + local position.
+ *   - there is NO CPU fallback.  If no CUDA device is usable every entry point
+ *     that needs one fails with CUBIT_ENODEVICE.
+ */
+#ifndef CUBIT_GPU_H
+#define CUBIT_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUBIT_GPU_ABI_VERSION 1
+
+/* error codes */
+#define CUBIT_OK 0
+#define CUBIT_EINVAL (-1)    /* bad argument / out of range id            */
+#define CUBIT_ENODEVICE (-2) /* no usable CUDA device                      */
+#define CUBIT_ECUDA (-3)     /* CUDA runtime error (message has the text)  */
+#define CUBIT_ENOMEM (-4)    /* host or device allocation failed           */
+#define CUBIT_ESTATE (-5)    /* call not valid in the object's state       */
+
+/* limits */
+#define CUBIT_MAX_STREAMS 64 /* bitvectors read by one query (Σ group sizes) */
+#define CUBIT_MAX_PROBE_COLS 8
+
+typedef struct cubit_gpu_table cubit_gpu_table;   /* one table shard on one GPU */
+typedef struct cubit_gpu_result cubit_gpu_result; /* one query's result set     */
+
+/* (index, value) names one value bitvector B_v of one CUBIT index. */
+typedef struct cubit_bv_ref {
+	int32_t index_id;
+	uint32_t value_id;
+} cubit_bv_ref;
+
+/* One OR group: OR over refs[0..n_refs).  A range predicate lo<=x<=hi on an
+ * indexed column is the OR over the value bitvectors in [lo,hi]. */
+typedef struct cubit_pred_group {
+	uint32_t n_refs;
+	const cubit_bv_ref *refs;
+} cubit_pred_group;
+
+/* what the query materialises */
+#define CUBIT_Q_ROWIDS (1u << 0)    /* sorted int64 row IDs (device resident, fetchable)      */
+#define CUBIT_Q_BITVECTOR (1u << 1) /* the merged query bitvector Q (device resident)          */
+#define CUBIT_Q_VALUES (1u << 2)    /* probe cols[] at the selected rows (device, fetchable)   */
+#define CUBIT_Q_TIMING (1u << 3)    /* record per-kernel CUDA-event times in cubit_result_info */
+#define CUBIT_Q_UNFUSED (1u << 4)   /* force merge → decode → probe as three separate kernels  */
+#define CUBIT_Q_ASYNC (1u << 5)     /* enqueue only; cubit_gpu_result_wait() completes it      */
+
+/* fused aggregate over the selected rows (SUM semantics of the reference:
+ * int64 input, 128-bit accumulator — sum.cpp:172-178, sum_helpers.hpp:92-113) */
+#define CUBIT_AGG_NONE 0
+#define CUBIT_AGG_SUM 1      /* SUM(col a)            */
+#define CUBIT_AGG_SUM_PROD 2 /* SUM(col a * col b), int64 product (arithmetic.cpp:766-795) */
+
+/* Q = AND_j ( OR_{i in groups[j]} ( B_i XOR D_i ) ) */
+typedef struct cubit_query {
+	uint32_t n_groups;
+	const cubit_pred_group *groups;
+	uint32_t flags;       /* CUBIT_Q_*                                         */
+	uint32_t n_cols;      /* projected columns to probe (CUBIT_Q_VALUES)        */
+	const int32_t *cols;  /* column ids, as given to cubit_gpu_upload_column    */
+	int32_t agg_kind;     /* CUBIT_AGG_*                                        */
+	int32_t agg_col_a;
+	int32_t agg_col_b;
+} cubit_query;
+
+typedef struct cubit_result_info {
+	uint64_t count;         /* rows selected = popcount(Q)                        */
+	uint64_t sum_lo;        /* 128-bit two's complement aggregate, low limb      */
+	int64_t sum_hi;         /*                                        high limb  */
+	uint64_t capacity;      /* rows the row-ID / value buffers were sized for    */
+	uint32_t n_streams;     /* k: value bitvectors read                          */
+	uint32_t n_launches;    /* kernels launched for this query                   */
+	uint64_t delta_entries; /* pending-delta words XOR-ed at query time          */
+	uint64_t algo_bytes_scan;  /* k*ceil(N/64)*8 + delta + 8*count   */
+	uint64_t algo_bytes_probe; /* count*(8 + Σ col widths) for a separate probe  */
+	float ms_scan;          /* merge+decode kernel(s), CUDA events (CUBIT_Q_TIMING) */
+	float ms_probe;         /* probe kernel                                      */
+	float ms_total;         /* first launch → last launch of the query           */
+	uint32_t fused;         /* 1 if merge+decode(+probe) ran as one kernel       */
+	const int64_t *d_rowids;   /* device pointers (valid until free_result)     */
+	const uint64_t *d_bitvector;
+	const void *d_values[CUBIT_MAX_PROBE_COLS];
+} cubit_result_info;
+
+/* ---- library ---------------------------------------------------------- */
+int cubit_gpu_abi_version(void);
+const char *cubit_gpu_last_error(void);
+int cubit_gpu_device_count(int *count);
+
+/* ---- table shard -------------------------------------------------------
+ * n_rows    rows held by this shard (row-range sharding)
+ * row_base  global row ID of local row 0 (multiple of seg_bits)
+ * seg_bits  CUBIT segment size in rows: 32768, 65536 or 131072.  One segment
+ *           is the unit of the merge kernel and of the pending-delta lists.  */
+int cubit_gpu_create(int device, uint64_t n_rows, int64_t row_base, uint32_t seg_bits, cubit_gpu_table **out);
+int cubit_gpu_destroy(cubit_gpu_table *t);
+/* run this table's kernels on a caller-owned cudaStream_t (NULL = own stream) */
+int cubit_gpu_set_stream(cubit_gpu_table *t, void *cuda_stream);
+int cubit_gpu_words_per_bitvector(const cubit_gpu_table *t, uint64_t *n_words);
+/* kernels launched by this table since creation (bench.py: gpu_launches) */
+int cubit_gpu_launch_count(const cubit_gpu_table *t, uint64_t *n);
+
+/* ---- CUBIT index: `cardinality` value bitvectors over the shard's rows -- */
+int cubit_gpu_index_create(cubit_gpu_table *t, uint32_t cardinality, int32_t *index_id);
+/* words: ceil(n_rows/64) host words, bits >= n_rows must be 0 */
+int cubit_gpu_upload_bitvector(cubit_gpu_table *t, int32_t index_id, uint32_t value_id, const uint64_t *words,
+                               uint64_t n_words);
+int cubit_gpu_download_bitvector(cubit_gpu_table *t, int32_t index_id, uint32_t value_id, uint64_t *words,
+                                 uint64_t n_words);
+/* build every bitvector of the index on the GPU from a resident integer
+ * column: row r sets bit r of B_(col[r]-base_value); values outside
+ * [base_value, base_value+cardinality) are not indexed (NULL keys are not
+ * indexed in the reference either: plan_create_index.cpp:60-78). */
+int cubit_gpu_index_build(cubit_gpu_table *t, int32_t index_id, int32_t col_id, int64_t base_value);
+/* popcount of B_v as stored (pending deltas not applied) */
+int cubit_gpu_bitvector_count(cubit_gpu_table *t, int32_t index_id, uint32_t value_id, uint64_t *count);
+
+/* Pending update/delete delta D_v of one bitvector: the set of LOCAL row
+ * positions whose bit is flipped at query time (B_v XOR D_v).  Replaces any
+ * previous pending delta of that bitvector; a row listed twice cancels.
+ * UPDATE v→w of row r contributes r to D_v and D_w, DELETE of a row whose
+ * value is v contributes r to D_v. */
+int cubit_gpu_set_delta(cubit_gpu_table *t, int32_t index_id, uint32_t value_id, const int64_t *rows, uint64_t n);
+/* merge-back: B_v ^= D_v for every bitvector of the index, deltas cleared */
+int cubit_gpu_merge_deltas(cubit_gpu_table *t, int32_t index_id);
+
+/* ---- columns (decoded, fixed width 4 or 8 bytes, HBM resident) ---------- */
+int cubit_gpu_upload_column(cubit_gpu_table *t, int32_t col_id, const void *data, uint32_t elem_bytes, uint64_t n);
+int cubit_gpu_download_column(cubit_gpu_table *t, int32_t col_id, void *data, uint32_t elem_bytes, uint64_t n);
+/* Synthetic columns generated on the device (bench / parity-test support;
+ * the generators are restated in oracle/cubit_oracle.c):
+ *   kind 0: int64 payload, value = row_base + r
+ *   kind 1: int32 value column of SURVEY §8d config 2: z = splitmix64(seed + row_base + r);
+ *           z < threshold ? hot_lo + (z>>7) % hot_n : the (z>>7) % (card-hot_n)-th value outside the hot range */
+int cubit_gpu_synth_column(cubit_gpu_table *t, int32_t col_id, int32_t kind, uint64_t seed, uint64_t threshold,
+                           uint32_t card, uint32_t hot_lo, uint32_t hot_n);
+int cubit_gpu_drop_column(cubit_gpu_table *t, int32_t col_id);
+
+/* ---- query --------------------------------------------------------------
+ * Synchronous unless CUBIT_Q_ASYNC: on return info fields are final.
+ * Thread-safe per table (calls are serialised on the table's stream).      */
+int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_result **out);
+int cubit_gpu_result_wait(cubit_gpu_result *r);
+int cubit_gpu_result_get(cubit_gpu_result *r, cubit_result_info *info);
+/* copy result rows [offset, offset+n) to host: row IDs and/or the which-th
+ * projected column (pass NULL to skip one).  This is what fills a DataChunk
+ * (≤ 2048 rows per GetData call: table_scan.cpp:258-268). */
+int cubit_gpu_fetch(cubit_gpu_result *r, uint64_t offset, uint64_t n, int64_t *host_rowids, uint32_t n_cols,
+                    void *const *host_cols);
+int cubit_gpu_fetch_bitvector(cubit_gpu_result *r, uint64_t *host_words, uint64_t n_words);
+int cubit_gpu_free_result(cubit_gpu_result *r);
+
+/* Probe a resident column at caller-supplied sorted row IDs (the
+ * DataTable::Fetch analog, src/storage/data_table.cpp:373-377): gathers
+ * col[row_ids[i] - row_base] into host_out and optionally sums it. */
+int cubit_gpu_probe(cubit_gpu_table *t, int32_t col_id, const int64_t *host_rowids, uint64_t n, void *host_out,
+                    uint64_t *sum_lo, int64_t *sum_hi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUBIT_GPU_H */

@@ -1,0 +1,251 @@
+"""CPU oracle of the CUBIT bitmap-index scan path — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference`
+legs may import this package.  The product path (duckdb-cubit_b200/) never does.
+
+Two independent restatements live here:
+  * cubit_oracle.c  (C, via ctypes)  — also the multi-threaded CPU baseline
+  * np_*            (numpy)          — a second implementation used to cross-check the C one
+Parity status and reference citations: see the header of cubit_oracle.c.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libcubit_oracle.so")
+_lib = None
+
+_u64p = C.POINTER(C.c_uint64)
+_i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int32)
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "cubit_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        flags = ["-O3", "-fPIC", "-Wall", "-Wextra", "-fvisibility=hidden"]
+        # -march=native is only valid for the machine that compiles; the library may have been
+        # built in another container, so rebuild here if it was not produced on this host.
+        subprocess.check_call(["gcc"] + flags + ["-march=native", "-shared", "-o", _LIB_PATH, src, "-lpthread"])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        try:
+            _lib = C.CDLL(_LIB_PATH)
+        except OSError:
+            build(force=True)
+            _lib = C.CDLL(_LIB_PATH)
+        L = _lib
+        L.oracle_merge.argtypes = [C.POINTER(_u64p), C.POINTER(_u64p), _i32p, C.c_int, C.c_uint64, _u64p]
+        L.oracle_merge.restype = None
+        L.oracle_merge_segmented.argtypes = [C.POINTER(_u64p), C.POINTER(_u64p), _i32p, C.c_int, C.c_uint64,
+                                             C.c_uint64, _u64p]
+        L.oracle_merge_segmented.restype = None
+        L.oracle_decode.argtypes = [_u64p, C.c_uint64, C.c_int64, _i64p]
+        L.oracle_decode.restype = C.c_uint64
+        L.oracle_popcount.argtypes = [_u64p, C.c_uint64]
+        L.oracle_popcount.restype = C.c_uint64
+        L.oracle_probe.argtypes = [_i64p, C.c_uint64, C.c_int64, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.oracle_probe.restype = None
+        L.oracle_sum_i64.argtypes = [_i64p, C.c_uint64, _u64p, _i64p]
+        L.oracle_sum_i64.restype = None
+        L.oracle_sum_prod_i64.argtypes = [_i64p, _i64p, C.c_uint64, _u64p, _i64p]
+        L.oracle_sum_prod_i64.restype = C.c_int
+        L.oracle_build_index.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_int64, C.c_uint32, _u64p,
+                                         C.c_uint64]
+        L.oracle_build_index.restype = None
+        L.oracle_delta_from_rows.argtypes = [_i64p, C.c_uint64, _u64p]
+        L.oracle_delta_from_rows.restype = None
+        L.oracle_synth_column.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_uint64, C.c_uint64,
+                                          C.c_uint32, C.c_uint32, C.c_uint32]
+        L.oracle_synth_column.restype = None
+        L.oracle_synth_bitvectors.argtypes = [_u64p, C.c_uint64, C.c_int64, C.c_uint64, C.c_uint64, C.c_uint32,
+                                              C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+        L.oracle_synth_bitvectors.restype = None
+        L.oracle_scan_mt.argtypes = [C.POINTER(_u64p), C.POINTER(_u64p), _i32p, C.c_int, C.c_uint64, C.c_int64,
+                                     _u64p, _i64p, _i64p, _i64p, _u64p, _i64p, C.c_int]
+        L.oracle_scan_mt.restype = C.c_uint64
+    return _lib
+
+
+def _p(a, typ):
+    return a.ctypes.data_as(typ)
+
+
+def _stream_ptrs(arrs):
+    """arrs: list of 1-D uint64 arrays (or None) -> (ctypes array of pointers, keepalive)"""
+    ptrs = (_u64p * len(arrs))()
+    for i, a in enumerate(arrs):
+        ptrs[i] = _p(a, _u64p) if a is not None else _u64p()
+    return ptrs
+
+
+def int128(lo, hi):
+    """(uint64 lo, int64 hi) two's complement limbs -> python int"""
+    return (int(hi) << 64) + int(lo)
+
+
+# ------------------------------------------------------------------ C oracle
+def merge(groups, deltas=None, seg_words=None):
+    """groups: list of lists of uint64 arrays (OR inside a group, AND across).
+    deltas: same shape, dense uint64 delta bitvectors or None entries."""
+    streams, dl, gof = [], [], []
+    for g, grp in enumerate(groups):
+        for i, b in enumerate(grp):
+            b = np.ascontiguousarray(b, dtype=np.uint64)
+            streams.append(b)
+            d = None
+            if deltas is not None and deltas[g][i] is not None:
+                d = np.ascontiguousarray(deltas[g][i], dtype=np.uint64)
+            dl.append(d)
+            gof.append(g)
+    n_words = len(streams[0])
+    q = np.empty(n_words, dtype=np.uint64)
+    gof = np.asarray(gof, dtype=np.int32)
+    sp = _stream_ptrs(streams)
+    dp = _stream_ptrs(dl)
+    dpp = dp if any(d is not None for d in dl) else C.POINTER(_u64p)()
+    if seg_words:
+        lib().oracle_merge_segmented(sp, dpp, _p(gof, _i32p), len(streams), n_words, seg_words, _p(q, _u64p))
+    else:
+        lib().oracle_merge(sp, dpp, _p(gof, _i32p), len(streams), n_words, _p(q, _u64p))
+    return q
+
+
+def decode(q, row_base=0):
+    q = np.ascontiguousarray(q, dtype=np.uint64)
+    n = lib().oracle_popcount(_p(q, _u64p), len(q))
+    out = np.empty(n, dtype=np.int64)
+    got = lib().oracle_decode(_p(q, _u64p), len(q), row_base, _p(out, _i64p))
+    assert got == n
+    return out
+
+
+def popcount(q):
+    q = np.ascontiguousarray(q, dtype=np.uint64)
+    return int(lib().oracle_popcount(_p(q, _u64p), len(q)))
+
+
+def probe(ids, col, row_base=0):
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    col = np.ascontiguousarray(col)
+    out = np.empty(len(ids), dtype=col.dtype)
+    lib().oracle_probe(_p(ids, _i64p), len(ids), row_base, col.ctypes.data, col.dtype.itemsize, out.ctypes.data)
+    return out
+
+
+def sum_i64(vals):
+    vals = np.ascontiguousarray(vals, dtype=np.int64)
+    lo, hi = C.c_uint64(0), C.c_int64(0)
+    lib().oracle_sum_i64(_p(vals, _i64p), len(vals), C.byref(lo), C.byref(hi))
+    return int128(lo.value, hi.value)
+
+
+def sum_prod_i64(a, b):
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    b = np.ascontiguousarray(b, dtype=np.int64)
+    lo, hi = C.c_uint64(0), C.c_int64(0)
+    ovf = lib().oracle_sum_prod_i64(_p(a, _i64p), _p(b, _i64p), len(a), C.byref(lo), C.byref(hi))
+    return int128(lo.value, hi.value), bool(ovf)
+
+
+def build_index(col, base_value, card):
+    col = np.ascontiguousarray(col)
+    assert col.dtype.itemsize in (4, 8)
+    n = len(col)
+    n_words = (n + 63) // 64
+    bv = np.zeros((card, n_words), dtype=np.uint64)
+    lib().oracle_build_index(col.ctypes.data, col.dtype.itemsize, n, base_value, card, _p(bv, _u64p), n_words)
+    return bv
+
+
+def delta_from_rows(rows, n_rows):
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    d = np.zeros((n_rows + 63) // 64, dtype=np.uint64)
+    lib().oracle_delta_from_rows(_p(rows, _i64p), len(rows), _p(d, _u64p))
+    return d
+
+
+def synth_column(kind, n_rows, row_base=0, seed=0, threshold=0, card=100, hot_lo=10, hot_n=10):
+    col = np.empty(n_rows, dtype=np.int64 if kind == 0 else np.int32)
+    lib().oracle_synth_column(col.ctypes.data, kind, n_rows, row_base, seed, threshold, card, hot_lo, hot_n)
+    return col
+
+
+def synth_bitvectors(n_rows, row_base, seed, threshold, card, hot_lo, hot_n, v0, nv, n_threads=1):
+    n_words = (n_rows + 63) // 64
+    out = np.empty((nv, n_words), dtype=np.uint64)
+    lib().oracle_synth_bitvectors(_p(out, _u64p), n_rows, row_base, seed, threshold, card, hot_lo, hot_n, v0, nv,
+                                  n_threads)
+    return out
+
+
+def scan_mt(groups, payload=None, row_base=0, n_threads=1, want_ids=True, deltas=None, bufs=None):
+    """The whole path, multi-threaded: merge -> decode -> probe payload -> SUM.
+    Returns (count, ids, vals, sum).  `bufs` = (q, ids, vals) preallocated arrays to reuse."""
+    streams, dl, gof = [], [], []
+    for g, grp in enumerate(groups):
+        for i, b in enumerate(grp):
+            streams.append(b)
+            dl.append(deltas[g][i] if deltas is not None else None)
+            gof.append(g)
+    n_words = len(streams[0])
+    gof = np.asarray(gof, dtype=np.int32)
+    if bufs is None:
+        cap = n_words * 64
+        q = np.empty(n_words, dtype=np.uint64)
+        ids = np.empty(cap, dtype=np.int64) if want_ids else None
+        vals = np.empty(cap, dtype=np.int64) if payload is not None and want_ids else None
+    else:
+        q, ids, vals = bufs
+    sp = _stream_ptrs(streams)
+    dp = _stream_ptrs(dl)
+    dpp = dp if any(d is not None for d in dl) else C.POINTER(_u64p)()
+    lo, hi = C.c_uint64(0), C.c_int64(0)
+    n = lib().oracle_scan_mt(sp, dpp, _p(gof, _i32p), len(streams), n_words, row_base, _p(q, _u64p),
+                             _p(ids, _i64p) if ids is not None else _i64p(),
+                             _p(payload, _i64p) if payload is not None else _i64p(),
+                             _p(vals, _i64p) if vals is not None else _i64p(), C.byref(lo), C.byref(hi), n_threads)
+    return int(n), ids, vals, int128(lo.value, hi.value)
+
+
+# --------------------------------------------------------------- numpy oracle
+def np_merge(groups, deltas=None):
+    acc = None
+    for g, grp in enumerate(groups):
+        o = np.zeros_like(np.asarray(grp[0], dtype=np.uint64))
+        for i, b in enumerate(grp):
+            v = np.asarray(b, dtype=np.uint64)
+            if deltas is not None and deltas[g][i] is not None:
+                v = v ^ np.asarray(deltas[g][i], dtype=np.uint64)
+            o = o | v
+        acc = o if acc is None else (acc & o)
+    return acc
+
+
+def np_decode(q, row_base=0):
+    bits = np.unpackbits(np.ascontiguousarray(q, dtype="<u8").view(np.uint8), bitorder="little")
+    return np.flatnonzero(bits).astype(np.int64) + row_base
+
+
+def np_build_index(col, base_value, card):
+    col = np.asarray(col).astype(np.int64)
+    n = len(col)
+    n_words = (n + 63) // 64
+    out = np.zeros((card, n_words), dtype=np.uint64)
+    for v in range(card):
+        m = np.zeros(n_words * 64, dtype=np.uint8)
+        m[:n] = col == (base_value + v)
+        out[v] = np.packbits(m, bitorder="little").view("<u8")
+    return out
+
+
+def np_sum(vals):
+    return int(sum(int(x) for x in np.asarray(vals, dtype=np.int64).tolist()))

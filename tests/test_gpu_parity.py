@@ -1,0 +1,302 @@
+"""GPU: the CUDA path, called through the C-ABI, against the oracle and the reference goldens.
+
+Bit-exact everywhere (row IDs, values, integer aggregates); there is no float on this path.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+INDEX_BASE = {"quantity": 1, "discount": 0, "month": 0}
+INDEX_CARD = {"quantity": 50, "discount": 11, "month": 84}
+COL_PRICE, COL_DISC, COL_SHIP, COL_QTY = 0, 1, 2, 3
+
+
+def digest(ids):
+    return hashlib.sha256(np.ascontiguousarray(ids, dtype="<i8").tobytes()).hexdigest()
+
+
+def make_lineitem_table(cubit, lineitem, seg_bits=65536, build_on_gpu=False):
+    n = len(lineitem["price"])
+    t = cubit.CubitTable(n, seg_bits=seg_bits)
+    t.upload_column(COL_PRICE, lineitem["price"])
+    t.upload_column(COL_DISC, lineitem["discount"])
+    t.upload_column(COL_SHIP, lineitem["shipdate"])  # int32
+    ix = {}
+    for slot, c in enumerate(("quantity", "discount", "month")):
+        if build_on_gpu:
+            t.upload_column(10 + slot, lineitem[c])
+            ix[c] = t.create_index(INDEX_CARD[c])
+            t.build_index(ix[c], 10 + slot, INDEX_BASE[c])
+        else:
+            ix[c] = t.upload_index(oracle.build_index(lineitem[c], INDEX_BASE[c], INDEX_CARD[c]))
+    return t, ix
+
+
+def refs(ent, ix):
+    return [[(ix[c], v - INDEX_BASE[c]) for (c, v) in grp] for grp in ent["groups"]]
+
+
+@pytest.mark.parametrize("seg_bits", [32768, 65536, 131072])
+@pytest.mark.parametrize("unfused", [False, True])
+def test_tpch_sf001_against_reference_goldens(cubit, golden, lineitem, seg_bits, unfused):
+    g, gids = golden
+    t, ix = make_lineitem_table(cubit, lineitem, seg_bits, build_on_gpu=(seg_bits == 65536))
+    extra = cubit.Q_UNFUSED if unfused else 0
+    for name, ent in g["tpch_sf001"]["answers"].items():
+        want = gids["tpch_sf001/%s/ids" % name]
+        with t.query(refs(ent, ix), flags=cubit.Q_ROWIDS | cubit.Q_VALUES | cubit.Q_BITVECTOR | extra,
+                     cols=[COL_PRICE, COL_DISC], agg=cubit.AGG_SUM_PROD, agg_a=COL_PRICE, agg_b=COL_DISC) as r:
+            assert r.count == ent["count"], name
+            assert r.sum == ent["sum_price_x_discount_e4"], name
+            ids, (price, disc) = r.fetch()
+            assert np.array_equal(ids, want), name
+            assert np.array_equal(price, lineitem["price"][want])
+            assert np.array_equal(disc, lineitem["discount"][want])
+            assert np.array_equal(oracle.decode(r.bitvector()), want)
+            assert r.info.fused == (0 if unfused else 1)
+        # SUM(price) with an int32 projected column → separate probe kernel
+        with t.query(refs(ent, ix), flags=cubit.Q_ROWIDS | cubit.Q_VALUES | extra, cols=[COL_SHIP],
+                     agg=cubit.AGG_SUM, agg_a=COL_PRICE) as r:
+            assert r.count == ent["count"] and r.sum == ent["sum_price_cents"], name
+            ids, (ship,) = r.fetch()
+            assert np.array_equal(ids, want) and np.array_equal(ship, lineitem["shipdate"][want])
+        # aggregate only (no row IDs materialised)
+        with t.query(refs(ent, ix), flags=extra, agg=cubit.AGG_SUM, agg_a=COL_PRICE) as r:
+            assert r.count == ent["count"] and r.sum == ent["sum_price_cents"], name
+    t.close()
+
+
+def test_q6_answer_file(cubit, golden, lineitem):
+    """extension/tpch/dbgen/answers/sf0.01/q06.csv = 1193053.2253"""
+    g, _ = golden
+    t, ix = make_lineitem_table(cubit, lineitem)
+    ent = g["tpch_sf001"]["answers"]["q6"]
+    with t.query(refs(ent, ix), flags=0, agg=cubit.AGG_SUM_PROD, agg_a=COL_PRICE, agg_b=COL_DISC) as r:
+        assert r.sum == 11930532253 and r.info.n_streams == 38
+    t.close()
+
+
+def delta_lists(gids, lineitem):
+    upd = gids["tpch_sf001_delta/updated_rows"]
+    newq = gids["tpch_sf001_delta/new_quantity"]
+    dele = gids["tpch_sf001_delta/deleted_rows"]
+    flips = {}
+    for r, a, b in zip(upd.tolist(), lineitem["quantity"][upd].tolist(), newq.tolist()):
+        flips.setdefault(("quantity", a), []).append(r)
+        flips.setdefault(("quantity", b), []).append(r)
+    for c in ("quantity", "discount", "month"):
+        for r, v in zip(dele.tolist(), lineitem[c][dele].tolist()):
+            flips.setdefault((c, v), []).append(r)
+    return flips
+
+
+@pytest.mark.parametrize("seg_bits", [32768, 131072])
+def test_pending_deltas_match_sql_update_delete(cubit, golden, lineitem, seg_bits):
+    g, gids = golden
+    t, ix = make_lineitem_table(cubit, lineitem, seg_bits)
+    for (c, v), rows in delta_lists(gids, lineitem).items():
+        t.set_delta(ix[c], v - INDEX_BASE[c], np.asarray(rows))
+    answers = g["tpch_sf001_delta"]["answers"]
+
+    def check():
+        for name, ent in answers.items():
+            want = gids["tpch_sf001_delta/%s/ids" % name]
+            for extra in (0, cubit.Q_UNFUSED):
+                with t.query(refs(ent, ix), flags=cubit.Q_ROWIDS | extra, agg=cubit.AGG_SUM, agg_a=COL_PRICE) as r:
+                    ids, _ = r.fetch()
+                    assert np.array_equal(ids, want), name
+                    assert r.count == ent["count"] and r.sum == ent["sum_price_cents"]
+    check()                      # deltas XOR-ed at query time
+    some = t.query(refs(answers["q_10_19"], ix), flags=0)
+    assert some.info.delta_entries > 0
+    some.free()
+    for c in ix:
+        t.merge_deltas(ix[c])    # merge-back: B ^= D
+    check()
+    some = t.query(refs(answers["q_10_19"], ix), flags=0)
+    assert some.info.delta_entries == 0
+    some.free()
+    t.close()
+
+
+def random_case(rng, n, card):
+    col = rng.integers(0, card, n).astype(np.int32)
+    pay = rng.integers(-2**62, 2**62, n).astype(np.int64)
+    return col, pay
+
+
+@pytest.mark.parametrize("n,seg_bits,row_base", [
+    (1, 32768, 0), (63, 65536, 64), (64, 65536, 0), (65, 131072, 128), (32768, 32768, 0), (32769, 32768, 32768 * 3),
+    (65536 * 3 + 5, 65536, 65536), (1_000_003, 65536, 0), (5_000_011, 131072, 131072 * 7), (3_333_333, 32768, 0)])
+def test_random_tables_all_paths(cubit, n, seg_bits, row_base):
+    rng = np.random.default_rng(n)
+    card = 16
+    col, pay = random_case(rng, n, card)
+    bv = oracle.build_index(col, 0, card)
+    t = cubit.CubitTable(n, row_base=row_base, seg_bits=seg_bits)
+    t.upload_column(0, pay)
+    t.upload_column(1, col)
+    ix = t.create_index(card)
+    t.build_index(ix, 1, 0)
+    for v in range(card):
+        assert np.array_equal(t.download_bitvector(ix, v), bv[v])
+        assert t.bitvector_count(ix, v) == oracle.popcount(bv[v])
+    # pending deltas on two bitvectors (with a duplicate row that must cancel)
+    d3 = rng.integers(0, n, max(1, n // 50))
+    d7 = np.concatenate([rng.integers(0, n, max(1, n // 80)), d3[:1], d3[:1]])
+    t.set_delta(ix, 3, d3)
+    t.set_delta(ix, 7, d7)
+    dl = [None] * card
+    dl[3] = oracle.delta_from_rows(d3, n)
+    dl[7] = oracle.delta_from_rows(d7, n)
+    cases = [
+        [[0]], [[3]], [list(range(card))], [[1, 3, 5, 7]], [[1, 3, 5, 7], [3, 7, 9]], [[2], [2]], [[2], [4]],
+        [[0, 1, 2, 3], [3, 4, 5], [3, 7]],
+    ]
+    for groups in cases:
+        og = [[bv[v] for v in grp] for grp in groups]
+        od = [[dl[v] for v in grp] for grp in groups]
+        q = oracle.merge(og, od)
+        want = oracle.decode(q, row_base)
+        wv = oracle.probe(want, pay, row_base)
+        for extra in (0, cubit.Q_UNFUSED):
+            with t.query([[(ix, v) for v in grp] for grp in groups],
+                         flags=cubit.Q_ROWIDS | cubit.Q_VALUES | cubit.Q_BITVECTOR | extra, cols=[0, 1],
+                         agg=cubit.AGG_SUM, agg_a=0) as r:
+                assert r.count == len(want), (groups, extra)
+                ids, (vals, cv) = r.fetch()
+                assert np.array_equal(ids, want)
+                assert np.array_equal(vals, wv)
+                assert np.array_equal(cv, col[want - row_base])
+                assert r.sum == oracle.sum_i64(wv)
+                assert np.array_equal(r.bitvector(), q)
+                if len(want) > 5:  # windowed fetch, the DataChunk hand-off (≤2048 rows per call)
+                    i2, (v2, _) = r.fetch(offset=3, n=min(2048, len(want) - 3))
+                    assert np.array_equal(i2, want[3:3 + len(i2)]) and np.array_equal(v2, wv[3:3 + len(i2)])
+    # stand-alone probe (DataTable::Fetch analog)
+    some = np.sort(rng.choice(n, size=min(n, 1001), replace=False)) + row_base
+    vals, s = t.probe(0, some, want_sum=True)
+    assert np.array_equal(vals, pay[some - row_base]) and s == oracle.sum_i64(vals)
+    cvals, _ = t.probe(1, some)
+    assert np.array_equal(cvals, col[some - row_base])
+    t.close()
+
+
+def test_edge_bitvectors(cubit):
+    n = 200_000
+    t = cubit.CubitTable(n)
+    zeros = np.zeros(t.n_words, dtype=np.uint64)
+    ones = np.full(t.n_words, ~np.uint64(0), dtype=np.uint64)
+    ones[-1] = np.uint64((1 << (n % 64)) - 1)
+    ix = t.upload_index(np.stack([zeros, ones]))
+    t.synth_column(0, 0)
+    with t.query([[(ix, 0)]], flags=cubit.Q_ROWIDS, agg=cubit.AGG_SUM, agg_a=0) as r:
+        assert r.count == 0 and r.sum == 0 and len(r.fetch()[0]) == 0
+    with t.query([[(ix, 1)]], flags=cubit.Q_ROWIDS | cubit.Q_VALUES, cols=[0], agg=cubit.AGG_SUM, agg_a=0) as r:
+        ids, (v,) = r.fetch()
+        assert np.array_equal(ids, np.arange(n)) and np.array_equal(v, ids) and r.sum == n * (n - 1) // 2
+    with t.query([[(ix, 1)], [(ix, 0)]], flags=cubit.Q_ROWIDS) as r:
+        assert r.count == 0
+    with pytest.raises(cubit.CubitError):   # bits beyond n_rows are rejected
+        bad = ones.copy()
+        bad[-1] = ~np.uint64(0)
+        t.upload_bitvector(ix, 0, bad)
+    with pytest.raises(cubit.CubitError):
+        t.query([[(ix, 5)]])
+    with pytest.raises(cubit.CubitError):
+        t.query([])
+    with pytest.raises(cubit.CubitError):
+        t.set_delta(ix, 0, np.array([n]))
+    t.close()
+
+
+def test_sum_prod_overflow_is_an_error(cubit):
+    n = 1000
+    t = cubit.CubitTable(n)
+    t.upload_column(0, np.full(n, 2**40, dtype=np.int64))
+    ones = np.zeros(t.n_words, dtype=np.uint64)
+    ones[0] = 1
+    ix = t.upload_index(ones[None, :])
+    with pytest.raises(cubit.CubitError) as e:
+        t.query([[(ix, 0)]], flags=0, agg=cubit.AGG_SUM_PROD, agg_a=0, agg_b=0)
+    assert "Overflow" in str(e.value)
+    t.close()
+
+
+def test_synth_generator_and_gpu_index_build_match_reference_sql(cubit, golden):
+    g, _ = golden
+    for tag, ent in g["synthetic"].items():
+        n = ent["n_rows"]
+        t = cubit.CubitTable(n)
+        t.synth_column(1, 1, seed=ent["seed"], threshold=int(ent["threshold"]), card=ent["card"], hot_lo=10, hot_n=10)
+        t.synth_column(0, 0)
+        assert np.array_equal(t.download_column(1),
+                              oracle.synth_column(1, n, 0, ent["seed"], int(ent["threshold"]), ent["card"], 10, 10))
+        ix = t.create_index(ent["card"])
+        t.build_index(ix, 1, 0)
+        with t.query([[(ix, v) for v in range(10, 20)]], flags=cubit.Q_ROWIDS, agg=cubit.AGG_SUM, agg_a=0) as r:
+            ids, _ = r.fetch()
+            assert r.count == ent["count"] and r.sum == ent["sum_rowid"] and digest(ids) == ent["ids_sha256"]
+        t.close()
+
+
+def test_sf1_shape_config1(cubit):
+    """config 1 shape: 6,001,215 rows, 50-value index, equality predicate + SUM (data synthetic:
+    the SF1 table itself cannot travel; its reference answers are pinned on the CPU side)"""
+    n = 6_001_215
+    rng = np.random.default_rng(1)
+    qty = rng.integers(1, 51, n).astype(np.int32)
+    price = rng.integers(90_000, 10_500_000, n).astype(np.int64)
+    t = cubit.CubitTable(n)
+    t.upload_column(0, price)
+    t.upload_column(1, qty)
+    ix = t.create_index(50)
+    t.build_index(ix, 1, 1)
+    want = np.flatnonzero(qty == 24)
+    with t.query([[(ix, 23)]], flags=cubit.Q_ROWIDS, agg=cubit.AGG_SUM, agg_a=0) as r:
+        ids, _ = r.fetch()
+        assert np.array_equal(ids, want) and r.sum == int(price[want].sum())
+    t.close()
+
+
+@pytest.mark.parametrize("sel", ["1e-4", "0.5"])
+def test_full_size_properties_1b_rows(cubit, sel):
+    """BASELINE config 2 at full size (10^9 rows): size-independent properties.
+    payload = row id, so SUM(payload) == SUM(row ids); the OR of disjoint value bitvectors
+    must select exactly Σ popcount(B_v) rows; row IDs strictly ascending; every returned
+    row's value lies in the predicate range."""
+    from fractions import Fraction
+    n = 1_000_000_000
+    thr = int(Fraction(sel) * (1 << 64))
+    t = cubit.CubitTable(n)
+    t.synth_column(1, 1, seed=0xC0B17, threshold=thr, card=100, hot_lo=10, hot_n=10)
+    ix = t.create_index(100)
+    t.build_index(ix, 1, 0)
+    t.synth_column(0, 0)
+    total = sum(t.bitvector_count(ix, v) for v in range(100))
+    assert total == n
+    expect = sum(t.bitvector_count(ix, v) for v in range(10, 20))
+    assert abs(expect / n - float(Fraction(sel))) < 0.01 * float(Fraction(sel)) + 1e-6
+    with t.query([[(ix, v) for v in range(10, 20)]], flags=cubit.Q_ROWIDS | cubit.Q_VALUES, cols=[1],
+                 agg=cubit.AGG_SUM, agg_a=0) as r:
+        assert r.count == expect
+        fused_sum = r.sum
+        chunk = 1 << 25
+        prev, acc = -1, 0
+        for off in range(0, r.count, chunk):
+            ids, (vals,) = r.fetch(off, min(chunk, r.count - off))
+            assert ids[0] > prev and (np.diff(ids) > 0).all()
+            assert vals.min() >= 10 and vals.max() <= 19
+            prev = int(ids[-1])
+            acc += int(ids.sum(dtype=np.uint64)) if ids[-1] < 2**32 else sum(int(x) for x in ids)
+        assert prev < n and acc == fused_sum
+    # the three-kernel path agrees with the fused one
+    with t.query([[(ix, v) for v in range(10, 20)]], flags=cubit.Q_ROWIDS | cubit.Q_UNFUSED, agg=cubit.AGG_SUM,
+                 agg_a=0) as r2:
+        assert r2.count == expect and r2.sum == fused_sum
+    t.close()

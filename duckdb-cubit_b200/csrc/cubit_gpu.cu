@@ -824,6 +824,49 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 		}
 	}
 	const bool need_probe = want_vals || q->agg_kind != CUBIT_AGG_NONE;
+	// Fusing the probe into the scan kernel pays when the selection is sparse (saves a launch
+	// and the row-ID re-read) or when no row IDs are materialised at all (bit-driven aggregate).
+	// For dense materialising queries the gathers need more loads in flight than the scan
+	// kernel's 8 consumer warps can hold, so the dedicated probe kernel runs instead.
+	if ((want_ids || want_vals) && cap > t->n_rows / 64) {
+		fusable = false;
+	}
+	// the fused kernel gathers at most kMaxFusedCols DISTINCT int64 columns per selected row
+	const Column *dist_cols[kMaxFusedCols] = {};
+	int dist_out[kMaxFusedCols] = {-1, -1}; // which projected column each distinct column feeds
+	int n_dist = 0, agg_ia = 0, agg_ib = 0;
+	if (fusable && need_probe) {
+		auto slot_of = [&](const Column *c) -> int {
+			for (int d = 0; d < n_dist; d++) {
+				if (dist_cols[d] == c) {
+					return d;
+				}
+			}
+			if (n_dist == kMaxFusedCols) {
+				return -1;
+			}
+			dist_cols[n_dist] = c;
+			return n_dist++;
+		};
+		if (want_vals) {
+			for (uint32_t c = 0; c < q->n_cols && fusable; c++) {
+				const int d = slot_of(vcols[c]);
+				if (d < 0 || dist_out[d] >= 0) {
+					fusable = false; // too many columns, or one column projected twice
+				} else {
+					dist_out[d] = (int)c;
+				}
+			}
+		}
+		if (fusable && agg_a) {
+			agg_ia = slot_of(agg_a);
+			fusable = agg_ia >= 0;
+		}
+		if (fusable && agg_b) {
+			agg_ib = slot_of(agg_b);
+			fusable = agg_ib >= 0;
+		}
+	}
 	const bool separate_probe = need_probe && !fusable;
 	const bool need_ids_buf = want_ids || separate_probe;
 	if (!need_ids_buf && !want_vals) {
@@ -914,16 +957,14 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 		sa.q_out = r->d_q;
 		sa.ids_out = need_ids_buf ? r->d_ids : nullptr;
 		if (fusable) {
-			if (want_vals && cap) {
-				sa.n_vcols = (int)q->n_cols;
-				for (uint32_t c = 0; c < q->n_cols; c++) {
-					sa.vcol[c] = static_cast<const long long *>(vcols[c]->d);
-					sa.vout[c] = static_cast<long long *>(r->d_vals[c]);
-				}
+			sa.n_load = n_dist;
+			for (int d = 0; d < n_dist; d++) {
+				sa.lcol[d] = static_cast<const long long *>(dist_cols[d]->d);
+				sa.lout[d] = dist_out[d] >= 0 && cap ? static_cast<long long *>(r->d_vals[dist_out[d]]) : nullptr;
 			}
 			sa.agg_kind = q->agg_kind;
-			sa.agg_a = agg_a ? static_cast<const long long *>(agg_a->d) : nullptr;
-			sa.agg_b = agg_b ? static_cast<const long long *>(agg_b->d) : nullptr;
+			sa.agg_ia = agg_ia;
+			sa.agg_ib = agg_ib;
 		}
 		Q_TRY(launch_scan(sa, t->seg_words, has_delta, t->sm_count, st, nullptr));
 		n_launch++;

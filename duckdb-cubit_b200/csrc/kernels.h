@@ -10,8 +10,8 @@ constexpr int kMaxStreams = 64;       // == CUBIT_MAX_STREAMS
 constexpr int kMaxFusedCols = 2;      // value columns the fused scan kernel can probe (int64 only)
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kScanThreads = kConsumerThreads + 32; // + one producer warp
-constexpr int kScanStages = 8;                      // bulk-copy ring depth (stages of one segment each)
+constexpr int kScanThreads = kConsumerThreads + 64; // + one producer warp + one prefix (look-back) warp
+constexpr int kScanRingBytes = 72 * 1024;           // bulk-copy ring per CTA (stages of one segment each); 2 CTAs / SM
 
 // One pending-delta word of one (bitvector, segment): XOR `mask` into word
 // `word` of the staged segment.  Words are unique within a (bitvector, segment).
@@ -52,12 +52,13 @@ struct ScanArgs {
 	uint64_t *q_out;                    // merged bitvector out, or nullptr
 	long long *ids_out;                 // sorted row IDs out, or nullptr
 	unsigned long long ids_cap;         // capacity of ids_out / vals_out in rows
-	const long long *vcol[kMaxFusedCols]; // fused probe: int64 columns (local row indexed)
-	long long *vout[kMaxFusedCols];       // gathered values out (same positions as ids_out), or nullptr
-	int n_vcols;
-	int agg_kind;                       // CUBIT_AGG_*
-	const long long *agg_a;
-	const long long *agg_b;
+	// fused probe: the distinct int64 columns read at every selected row
+	int n_load;                           // 0..kMaxFusedCols
+	const long long *lcol[kMaxFusedCols]; // column base (local row indexed)
+	long long *lout[kMaxFusedCols];       // gathered values out (same positions as ids_out), or nullptr
+	int agg_kind;                         // CUBIT_AGG_*: SUM(lcol[agg_ia]) / SUM(lcol[agg_ia]*lcol[agg_ib])
+	int agg_ia;
+	int agg_ib;
 	BlockPartial *partials;             // [gridDim.x]
 	ResultHeader *hdr;
 };
@@ -80,7 +81,7 @@ struct ProbeArgs {
 };
 
 // ---- launchers (all asynchronous on `stream`; return cudaGetLastError()) ----
-// seg_words ∈ {512, 1024, 2048}.  has_delta: any doff[i] != nullptr.
+// seg_words ∈ {512, 1024, 2048} (= 256 consumer threads × 2/4/8 words).  has_delta: any doff[i] != nullptr.
 cudaError_t launch_scan(const ScanArgs &args, uint32_t seg_words, bool has_delta, int sm_count, cudaStream_t stream,
                         int *grid_out);
 int scan_max_grid(uint32_t seg_words, int sm_count);

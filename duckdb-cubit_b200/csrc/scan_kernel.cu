@@ -11,22 +11,35 @@
 //   SUM carry      src/include/duckdb/core_functions/aggregate/sum_helpers.hpp:92-113
 //
 // Shape of the kernel (B200-first, HBM-bound integer work, no tensor cores):
-//   * persistent CTAs (SM count × occupancy), segments handed out by a ticket
-//     counter, so every predecessor of a segment is already owned by a running
-//     CTA — the decoupled look-back below can never wait on unscheduled work.
-//   * one producer warp streams whole segments of every queried bitvector with
+//   * TWO persistent CTAs per SM (8 consumer warps + 1 producer warp + 1 prefix
+//     warp each); segments are handed out by a ticket counter, so every
+//     predecessor of a segment is already owned by a running CTA.
+//   * the producer warp streams whole segments of every queried bitvector with
 //     1-D bulk async copies (cp.async.bulk → SASS UBLKCP, the TMA engine) into a
-//     kScanStages-deep shared-memory ring guarded by mbarriers; it runs ahead
-//     of the consumers by the ring depth, which is what keeps ≥64 KiB per SM in
-//     flight while consumers are busy decoding or waiting in the look-back.
-//   * 8 consumer warps: apply the (sparse) pending-delta words of the staged
+//     72 KiB shared-memory ring guarded by mbarriers; it runs ahead of the
+//     consumers by the ring depth, which keeps the HBM pipe full (≥ 64 KiB in
+//     flight per SM) while consumers decode and emit.  Consumers wait for up to
+//     four ring stages with ONE SIMT try_wait (lane u polls stage u), so the
+//     mbarrier round trip is paid once per four streams, not once per stream.
+//   * consumer warps: apply the (sparse) pending-delta words of the staged
 //     segment (XOR), fold the segment into registers (OR within a group, AND
-//     across groups), 128-bit ld.shared per lane, conflict free.
-//   * decode: __popcll per word, warp __shfl_up scan, block scan over 8 warp
-//     totals, single-pass inter-segment prefix by decoupled look-back (one
-//     64-bit status word per segment, no atomics on the data path), then every
-//     set bit is written by "lane = bit" so each store instruction writes one
-//     contiguous run of row IDs (coalesced, sorted, no atomics).
+//     across groups) with conflict-free ld.shared.
+//   * decode: __popcll, warp __shfl_up scan, block scan over 16 warp totals; the
+//     segment's aggregate is published at once.  The inter-segment prefix is a
+//     single-pass decoupled look-back done by the PREFIX WARP, asynchronously (it
+//     sums the published aggregates between this CTA's previous segment and the
+//     new one — no chains through other CTAs' look-backs):
+//     consumers hand it (segment, count) through shared memory + mbarrier and
+//     pick the answer up two segments later (the emission of a segment is
+//     deferred behind the merge of the next two), so neither the look-back's L2
+//     round trips nor its waits are ever on the consumers' critical path and no
+//     CTA publishes an aggregate late because it is waiting for somebody else.
+//   * emit: every warp compacts the set bits of 2048 consecutive rows into a
+//     private shared-memory staging buffer (16-bit local row numbers; each lane
+//     walks the two 32-bit halves of its word as two independent ctz chains, no
+//     atomics) and then writes row IDs (and gathers/stores column values,
+//     accumulates SUMs) in position order: four consecutive results per lane,
+//     128-bit stores aligned to the 32-byte sector.
 #include "kernels.h"
 
 #include <cuda_runtime.h>
@@ -81,22 +94,14 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
 	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void st_stream_s64(long long *p, long long v) {
-	asm volatile("st.global.cs.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ long long ld_nc_s64(const long long *p) {
-	long long v;
-	asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
-	return v;
-}
 
-// look-back status word: [63:62] flag, [61:0] value
-constexpr unsigned long long kFlagAgg = 1ull << 62;    // value = popcount of this segment
-constexpr unsigned long long kFlagPrefix = 2ull << 62; // value = popcount of segments [0, this]
+// look-back status word: [63:62] flag (0 = not published yet), [61:0] popcount of the segment
+constexpr unsigned long long kFlagAgg = 1ull << 62;
 constexpr unsigned long long kValMask = (1ull << 62) - 1;
+constexpr uint32_t kNoTile = 0xffffffffu;
 
 struct StageMeta {
-	uint32_t tile; // 0xffffffff = no more work
+	uint32_t tile; // kNoTile = no more work
 	uint32_t d0;   // first delta entry of (stream, segment)
 	uint32_t dcnt; // number of delta entries
 	uint32_t pad;
@@ -113,27 +118,219 @@ __device__ __forceinline__ void add128(unsigned long long &lo, long long &hi, un
 	hi += hi2 + (long long)(lo < lo2);
 }
 
+constexpr int kReqSlots = 4;       // look-back requests in flight per CTA (> emission deferral depth)
+constexpr int kDefer = 2;          // segments merged between a segment's merge and its emission
+constexpr int kWaitBatch = 4;      // ring stages consumed per mbarrier round trip
+constexpr int kSlotRows = 32 * 64; // rows one warp compacts at a time (32 lanes × one 64-bit word)
+
 template <int WPT>
 struct ScanSmem {
 	static constexpr int kTileWords = kConsumerThreads * WPT;
 	static constexpr int kTileBytes = kTileWords * 8;
-	alignas(128) uint64_t stage[kScanStages][kTileWords];
-	alignas(8) uint64_t full[kScanStages];
-	uint64_t empty[kScanStages];
-	StageMeta meta[kScanStages];
+	static constexpr int kStages = kScanRingBytes / kTileBytes;
+	alignas(128) uint64_t stage[kStages][kTileWords];
+	alignas(16) uint16_t compact[kConsumerWarps][kSlotRows + 8]; // per-warp staging of local row numbers
+	alignas(8) uint64_t full[kStages];
+	uint64_t empty[kStages];
+	uint64_t req_full[kReqSlots];  // consumers → prefix warp
+	uint64_t resp_full[kReqSlots]; // prefix warp → consumers
+	unsigned long long resp_excl[kReqSlots];
+	uint32_t req_tile[kReqSlots];
+	uint32_t req_total[kReqSlots];
+	StageMeta meta[kStages];
 	uint32_t warp_tot[2][kConsumerWarps];
-	unsigned long long tile_base[2];
 	BlockPartial red[kConsumerWarps];
 };
 
+constexpr int kLookSlots = 16; // status words per prefix-warp lane per window → 512 segments per window
+
+// ---- the prefix warp's look-back, off the consumers' path.
+// status[t] = kFlagAgg | popcount(segment t), published once by the CTA that merged t.
+// The warp remembers the last segment this CTA handled (t0) and the inclusive prefix through
+// it (s0); the exclusive prefix of the next one is s0 + Σ status(t0+1 .. t-1).  It depends
+// only on those segments having been MERGED (inherent) — never on another CTA's look-back,
+// so there are no prefix chains, and the usual gap (≈ number of resident CTAs) is one window.
+__device__ __forceinline__ unsigned long long sum_aggregates(const unsigned long long *status, int64_t lo, int64_t hi,
+                                                             int lane) {
+	unsigned long long acc = 0; // per-lane partial
+	for (int64_t w0 = lo; w0 < hi; w0 += kLookSlots * 32) {
+		unsigned pending = 0; // bit j: slot j of this lane still unpublished
+#pragma unroll
+		for (int j = 0; j < kLookSlots; j++) {
+			if (w0 + j * 32 + lane < hi) {
+				pending |= 1u << j;
+			}
+		}
+		while (__any_sync(0xffffffffu, pending != 0)) {
+			unsigned long long sv[kLookSlots];
+#pragma unroll
+			for (int j = 0; j < kLookSlots; j++) {
+				sv[j] = (pending >> j) & 1u ? ld_relaxed_u64(&status[w0 + j * 32 + lane]) : 0ull;
+			}
+#pragma unroll
+			for (int j = 0; j < kLookSlots; j++) {
+				if (sv[j] >> 62) {
+					acc += sv[j] & kValMask;
+					pending &= ~(1u << j);
+				}
+			}
+			if (__any_sync(0xffffffffu, pending != 0)) {
+				__nanosleep(64); // some predecessor is still being merged: re-read only the holes
+			}
+		}
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		acc += __shfl_xor_sync(0xffffffffu, acc, d);
+	}
+	return acc;
+}
+
+// one selected row: store its id / gathered values at output position `pos`, accumulate
+template <int NL, bool POS>
+__device__ __forceinline__ void consume_row(const ScanArgs &a, unsigned long long pos, int64_t rid,
+                                            const long long (&v)[NL > 0 ? NL : 1], unsigned long long &sum_lo,
+                                            long long &sum_hi, unsigned int &overflow) {
+	if (POS) {
+		if (a.ids_out) {
+			__stcs(a.ids_out + pos, (long long)rid);
+		}
+#pragma unroll
+		for (int c = 0; c < NL; c++) {
+			if (a.lout[c]) {
+				__stcs(a.lout[c] + pos, v[c]);
+			}
+		}
+	}
+	if (NL > 0) {
+		const long long x = (NL > 1 && a.agg_ia == 1) ? v[NL - 1] : v[0];
+		if (a.agg_kind == 1) {
+			add128(sum_lo, sum_hi, x);
+		} else if (a.agg_kind == 2) {
+			const long long y = (NL > 1 && a.agg_ib == 1) ? v[NL - 1] : v[0];
+			const long long pr = x * y;
+			if (__mul64hi(x, y) != (pr >> 63)) {
+				overflow = 1;
+			}
+			add128(sum_lo, sum_hi, pr);
+		}
+	}
+}
+
+// ---- emission of one warp's span of a merged segment.
+// q[i] of lane l is word (i*32 + l) of the span, so slot i = 2048 consecutive rows.
+template <int WPT, int NL, bool POS>
+__device__ __forceinline__ void emit_span(const ScanArgs &a, const uint64_t (&q)[WPT], uint16_t *cbuf,
+                                          unsigned long long wbase, int64_t span_row0, int lane,
+                                          unsigned long long &sum_lo, long long &sum_hi, unsigned int &overflow) {
+	unsigned long long pos0 = wbase; // output position of the slot's first selected row
+#pragma unroll
+	for (int i = 0; i < WPT; i++) {
+		const uint32_t wlo = (uint32_t)q[i], whi = (uint32_t)(q[i] >> 32);
+		const uint32_t clo = __popc(wlo), c = clo + __popc(whi);
+		uint32_t incl = c;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+			if (lane >= d) {
+				incl += n;
+			}
+		}
+		const uint32_t slot_total = __shfl_sync(0xffffffffu, incl, 31);
+		if (slot_total == 0) {
+			continue;
+		}
+		// Staging index = (pos0 & 3) + rank, so staging index ≡ output position (mod 4) and a
+		// group of four staged rows maps onto one 32-byte-aligned run of output positions.
+		const uint32_t pad = (uint32_t)pos0 & 3u;
+		{
+			// lane-local compaction: the two halves of the word are two independent ctz chains
+			uint32_t p0 = pad + incl - c, p1 = p0 + clo;
+			uint32_t w0 = wlo, w1 = whi;
+			const uint32_t b0 = (uint32_t)lane * 64u, b1 = b0 + 32u;
+			while (w0 | w1) {
+				if (w0) {
+					cbuf[p0++] = (uint16_t)(b0 + (uint32_t)(__ffs(w0) - 1));
+					w0 &= w0 - 1;
+				}
+				if (w1) {
+					cbuf[p1++] = (uint16_t)(b1 + (uint32_t)(__ffs(w1) - 1));
+					w1 &= w1 - 1;
+				}
+			}
+		}
+		__syncwarp();
+		// position-ordered write-out: lane handles staged rows [4g, 4g+4)
+		const int64_t slot_row0 = span_row0 + (int64_t)i * kSlotRows;
+		const int64_t local0 = slot_row0 - a.row_base;
+		const unsigned long long obase = pos0 - pad; // output position of staging index 0 (multiple of 4)
+		const uint32_t end = pad + slot_total;
+		for (uint32_t g = lane; g * 4 < end; g += 32) {
+			const uint32_t e0 = g * 4;
+			const uint2 packed = *reinterpret_cast<const uint2 *>(cbuf + e0);
+			uint32_t r[4];
+			r[0] = packed.x & 0xffffu;
+			r[1] = packed.x >> 16;
+			r[2] = packed.y & 0xffffu;
+			r[3] = packed.y >> 16;
+			const bool full4 = e0 >= pad && e0 + 4 <= end;
+			long long v[4][NL > 0 ? NL : 1];
+			if (NL > 0) {
+#pragma unroll
+				for (int e = 0; e < 4; e++) {
+					if (full4 || (e0 + e >= pad && e0 + e < end)) {
+#pragma unroll
+						for (int cc = 0; cc < NL; cc++) {
+							v[e][cc] = __ldg(a.lcol[cc] + (local0 + r[e]));
+						}
+					}
+				}
+			}
+			if (POS && full4) {
+				if (a.ids_out) {
+					longlong2 *dst = reinterpret_cast<longlong2 *>(a.ids_out + obase + e0);
+					__stcs(dst, make_longlong2(slot_row0 + r[0], slot_row0 + r[1]));
+					__stcs(dst + 1, make_longlong2(slot_row0 + r[2], slot_row0 + r[3]));
+				}
+#pragma unroll
+				for (int cc = 0; cc < NL; cc++) {
+					if (a.lout[cc]) {
+						longlong2 *dst = reinterpret_cast<longlong2 *>(a.lout[cc] + obase + e0);
+						__stcs(dst, make_longlong2(v[0][cc], v[1][cc]));
+						__stcs(dst + 1, make_longlong2(v[2][cc], v[3][cc]));
+					}
+				}
+				if (NL > 0) {
+#pragma unroll
+					for (int e = 0; e < 4; e++) {
+						consume_row<NL, false>(a, 0, 0, v[e], sum_lo, sum_hi, overflow);
+					}
+				}
+			} else {
+#pragma unroll
+				for (int e = 0; e < 4; e++) {
+					if (e0 + e >= pad && e0 + e < end) {
+						consume_row<NL, POS>(a, obase + e0 + e, slot_row0 + r[e], v[e], sum_lo, sum_hi, overflow);
+					}
+				}
+			}
+		}
+		__syncwarp();
+		pos0 += slot_total;
+	}
+}
+
 // WPT: 64-bit words of Q each consumer thread holds → segment = 256*WPT words
 //      (WPT 2/4/8 ↔ 32768/65536/131072 rows per segment).
-template <int WPT, bool HAS_DELTA>
-__global__ void __launch_bounds__(kScanThreads) cubit_scan_kernel(const __grid_constant__ ScanArgs a) {
+// NL : distinct int64 columns gathered at every selected row (fused probe).
+template <int WPT, bool HAS_DELTA, int NL>
+__global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __grid_constant__ ScanArgs a) {
 	using Smem = ScanSmem<WPT>;
+	constexpr int kStages = Smem::kStages;
 	constexpr int kTileWords = Smem::kTileWords;
 	constexpr int kTileBytes = Smem::kTileBytes;
-	constexpr int NCH = WPT / 2; // 16-byte chunks per lane
+	constexpr int kSpanWords = WPT * 32; // words of one warp's span
+	constexpr int UB = WPT >= 8 ? 2 : (kWaitBatch < kStages ? kWaitBatch : kStages);
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	Smem &sm = *reinterpret_cast<Smem *>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
 
@@ -142,84 +339,108 @@ __global__ void __launch_bounds__(kScanThreads) cubit_scan_kernel(const __grid_c
 	unsigned int *ticket = reinterpret_cast<unsigned int *>(a.ctrl);
 	unsigned int *done_ctr = ticket + 1;
 	unsigned long long *status = a.ctrl + 1;
+	const bool need_pos =
+	    (a.ids_out != nullptr) || (NL > 0 && (a.lout[0] != nullptr || (NL > 1 && a.lout[NL - 1] != nullptr)));
+	const bool need_emit = need_pos || (NL > 0 && a.agg_kind != 0);
 
 	if (threadIdx.x == 0) {
-		for (int s = 0; s < kScanStages; s++) {
+		for (int s = 0; s < kStages; s++) {
 			mbar_init(&sm.full[s], 1);
 			mbar_init(&sm.empty[s], kConsumerWarps);
+		}
+		for (int s = 0; s < kReqSlots; s++) {
+			mbar_init(&sm.req_full[s], 1);
+			mbar_init(&sm.resp_full[s], 1);
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
 
 	if (warp == kConsumerWarps) {
-		// ------------------------------------------------------------ producer warp
-		uint32_t stage = 0, phase = 0;
-		uint32_t tile = 0;
-		if (lane == 0) {
-			tile = atomicAdd(ticket, 1u);
+		// ------------------------------------------------------------ producer warp (one lane)
+		if (lane != 0) {
+			return;
 		}
-		tile = __shfl_sync(0xffffffffu, tile, 0);
+		uint32_t stage = 0, phase = 0;
+		uint32_t tile = atomicAdd(ticket, 1u);
 		while (true) {
 			const bool valid = tile < a.n_seg;
 			uint32_t next = 0;
-			if (valid && lane == 0) {
+			if (valid) {
 				next = atomicAdd(ticket, 1u); // prefetched: consumed one segment later
 			}
-			if (!valid) {
-				if (lane == 0) {
-					mbar_wait(&sm.empty[stage], phase ^ 1);
-					sm.meta[stage].tile = 0xffffffffu;
-					mbar_arrive(&sm.full[stage]);
-				}
-				break;
-			}
-			// delta CSR offsets of this segment: lane i serves streams i and i+32
-			uint32_t dlo0 = 0, dhi0 = 0, dlo1 = 0, dhi1 = 0;
-			if (HAS_DELTA) {
-				if (lane < (int)a.k && a.doff[lane]) {
-					dlo0 = __ldg(a.doff[lane] + tile);
-					dhi0 = __ldg(a.doff[lane] + tile + 1);
-				}
-				if (lane + 32 < (int)a.k && a.doff[lane + 32]) {
-					dlo1 = __ldg(a.doff[lane + 32] + tile);
-					dhi1 = __ldg(a.doff[lane + 32] + tile + 1);
-				}
-			}
 			for (uint32_t s = 0; s < a.k; s++) {
-				uint32_t d0 = 0, d1 = 0;
-				if (HAS_DELTA) {
-					d0 = __shfl_sync(0xffffffffu, s < 32 ? dlo0 : dlo1, s & 31);
-					d1 = __shfl_sync(0xffffffffu, s < 32 ? dhi0 : dhi1, s & 31);
-				}
-				if (lane == 0) {
-					mbar_wait(&sm.empty[stage], phase ^ 1);
-					sm.meta[stage].tile = tile;
-					sm.meta[stage].d0 = d0;
-					sm.meta[stage].dcnt = d1 - d0;
+				mbar_wait(&sm.empty[stage], phase ^ 1);
+				sm.meta[stage].tile = valid ? tile : kNoTile;
+				if (!valid) {
+					mbar_arrive(&sm.full[stage]); // end marker: k empty stages, so batched waits stay uniform
+				} else {
+					if (HAS_DELTA) {
+						uint32_t d0 = 0, d1 = 0;
+						if (a.doff[s]) {
+							d0 = __ldg(a.doff[s] + tile);
+							d1 = __ldg(a.doff[s] + tile + 1);
+						}
+						sm.meta[stage].d0 = d0;
+						sm.meta[stage].dcnt = d1 - d0;
+					}
 					mbar_arrive_expect_tx(&sm.full[stage], kTileBytes);
 					bulk_g2s(&sm.stage[stage][0], a.bv[s] + (size_t)tile * kTileWords, kTileBytes, &sm.full[stage]);
 				}
 				stage++;
-				if (stage == kScanStages) {
+				if (stage == kStages) {
 					stage = 0;
 					phase ^= 1;
 				}
 			}
-			next = __shfl_sync(0xffffffffu, next, 0);
+			if (!valid) {
+				return;
+			}
 			tile = next;
 		}
-		return;
+	}
+
+	if (warp == kConsumerWarps + 1) {
+		// -------------------------------------------------------------- prefix warp
+		if (!need_pos) {
+			return;
+		}
+		int64_t t0 = -1;            // last segment handled by this CTA
+		unsigned long long s0 = 0; // popcount of segments [0, t0]
+		for (uint32_t n = 0;; n++) {
+			const uint32_t slot = n % kReqSlots, par = (n / kReqSlots) & 1;
+			mbar_wait(&sm.req_full[slot], par);
+			const uint32_t tile = sm.req_tile[slot];
+			if (tile == kNoTile) {
+				return;
+			}
+			const uint32_t total = sm.req_total[slot];
+			const unsigned long long excl = s0 + sum_aggregates(status, t0 + 1, (int64_t)tile, lane);
+			if (lane == 0) {
+				sm.resp_excl[slot] = excl;
+				mbar_arrive(&sm.resp_full[slot]);
+			}
+			t0 = tile;
+			s0 = excl + total;
+			__syncwarp();
+		}
 	}
 
 	// ---------------------------------------------------------------- consumer warps
-	const unsigned lanemask_lt = (1u << lane) - 1u;
 	uint32_t stage = 0, phase = 0;
 	unsigned long long blk_count = 0; // meaningful in thread 0
 	unsigned long long sum_lo = 0;
 	long long sum_hi = 0;
 	unsigned int overflow = 0;
 	uint32_t it = 0;
+
+	// The PENDING segments: merged and counted one and two iterations ago, aggregates
+	// published, look-back requests handed to the prefix warp.  A segment is emitted after
+	// the two following segments have been merged, by which time the prefix warp has its
+	// exclusive prefix ready (its predecessors' aggregates have had two segment-times to land).
+	uint64_t pq[kDefer][WPT];
+	uint32_t ptile[kDefer] = {}, ptotal[kDefer] = {}, pwexcl[kDefer] = {}, pit[kDefer] = {};
+	bool have_p[kDefer] = {};
 
 	while (true) {
 		uint64_t q[WPT], g[WPT];
@@ -229,234 +450,169 @@ __global__ void __launch_bounds__(kScanThreads) cubit_scan_kernel(const __grid_c
 			g[i] = 0;
 		}
 		uint32_t tile = 0;
-		bool finished = false;
-		for (uint32_t s = 0; s < a.k; s++) {
-			mbar_wait(&sm.full[stage], phase);
+		for (uint32_t s = 0; s < a.k; s += UB) {
+			const uint32_t nb = (a.k - s) < (uint32_t)UB ? (a.k - s) : (uint32_t)UB;
+			// lane u polls ring stage (stage + u): one mbarrier round trip per batch
+			if (lane < (int)nb) {
+				uint32_t st = stage + lane, ph = phase;
+				if (st >= kStages) {
+					st -= kStages;
+					ph ^= 1;
+				}
+				mbar_wait(&sm.full[st], ph);
+			}
+			__syncwarp();
 			if (s == 0) {
 				tile = sm.meta[stage].tile;
-				if (tile == 0xffffffffu) {
-					finished = true;
-					break;
-				}
 			}
-			if (HAS_DELTA) {
-				const uint32_t dcnt = sm.meta[stage].dcnt;
-				if (dcnt) { // uniform across the consumer warps
-					const DeltaEnt *ent = a.dent[s] + sm.meta[stage].d0;
-					for (uint32_t e = threadIdx.x; e < dcnt; e += kConsumerThreads) {
-						const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(ent + e));
-						const uint64_t mask = ((uint64_t)raw.w << 32) | raw.z;
-						sm.stage[stage][raw.x] ^= mask; // words are unique per (stream, segment)
+			if (HAS_DELTA && tile != kNoTile) {
+				bool any = false;
+				for (uint32_t u = 0; u < nb; u++) {
+					const uint32_t st = (stage + u) % kStages;
+					const uint32_t dcnt = sm.meta[st].dcnt;
+					if (dcnt) { // uniform across the consumer warps
+						any = true;
+						const DeltaEnt *ent = a.dent[s + u] + sm.meta[st].d0;
+						for (uint32_t e = threadIdx.x; e < dcnt; e += kConsumerThreads) {
+							const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(ent + e));
+							const uint64_t mask = ((uint64_t)raw.w << 32) | raw.z;
+							sm.stage[st][raw.x] ^= mask; // words are unique per (stream, segment)
+						}
 					}
+				}
+				if (any) {
 					fence_proxy_async_smem();
 					consumer_bar_sync();
 				}
 			}
-			const uint4 *src = reinterpret_cast<const uint4 *>(&sm.stage[stage][warp * (WPT * 32)]);
+			if (tile != kNoTile) {
 #pragma unroll
-			for (int j = 0; j < NCH; j++) {
-				const uint4 v = src[j * 32 + lane];
-				g[2 * j] |= ((uint64_t)v.y << 32) | v.x;
-				g[2 * j + 1] |= ((uint64_t)v.w << 32) | v.z;
-			}
-			if ((a.group_end >> s) & 1ull) {
+				for (int u = 0; u < UB; u++) {
+					if (u < (int)nb) {
+						const uint64_t *src = &sm.stage[(stage + u) % kStages][warp * kSpanWords];
 #pragma unroll
-				for (int i = 0; i < WPT; i++) {
-					q[i] &= g[i];
-					g[i] = 0;
+						for (int i = 0; i < WPT; i++) {
+							g[i] |= src[i * 32 + lane];
+						}
+						if ((a.group_end >> (s + u)) & 1ull) {
+#pragma unroll
+							for (int i = 0; i < WPT; i++) {
+								q[i] &= g[i];
+								g[i] = 0;
+							}
+						}
+					}
 				}
 			}
 			__syncwarp();
-			if (lane == 0) {
-				mbar_arrive(&sm.empty[stage]);
+			if (lane < (int)nb) {
+				mbar_arrive(&sm.empty[(stage + lane) % kStages]);
 			}
-			stage++;
-			if (stage == kScanStages) {
-				stage = 0;
+			stage += nb;
+			if (stage >= kStages) {
+				stage -= kStages;
 				phase ^= 1;
+			}
+		}
+		const bool finished = tile == kNoTile;
+
+		uint32_t tile_total = 0, warp_excl = 0;
+		if (!finished) {
+			// ---- merged bitvector out (optional)
+			if (a.q_out) {
+				uint64_t *dst = a.q_out + (size_t)tile * kTileWords + warp * kSpanWords;
+#pragma unroll
+				for (int i = 0; i < WPT; i++) {
+					dst[i * 32 + lane] = q[i];
+				}
+			}
+			// ---- decode, step 1: popcount, warp reduce, block scan over the warp totals
+			uint32_t cnt = 0;
+#pragma unroll
+			for (int i = 0; i < WPT; i++) {
+				cnt += __popcll(q[i]);
+			}
+#pragma unroll
+			for (int d = 16; d > 0; d >>= 1) {
+				cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+			}
+			const int buf = it & 1;
+			if (lane == 0) {
+				sm.warp_tot[buf][warp] = cnt;
+			}
+			consumer_bar_sync();
+#pragma unroll
+			for (int w = 0; w < kConsumerWarps; w++) {
+				const uint32_t t = sm.warp_tot[buf][w];
+				warp_excl += (w < warp) ? t : 0u;
+				tile_total += t;
+			}
+			if (threadIdx.x == 0) {
+				blk_count += tile_total;
+				if (need_pos) {
+					// publish this segment's aggregate NOW and hand the look-back to the prefix warp
+					st_relaxed_u64(&status[tile], kFlagAgg | (unsigned long long)tile_total);
+					sm.req_tile[it % kReqSlots] = tile;
+					sm.req_total[it % kReqSlots] = tile_total;
+					mbar_arrive(&sm.req_full[it % kReqSlots]);
+				}
+			}
+		} else if (need_pos && threadIdx.x == 0) {
+			sm.req_tile[it % kReqSlots] = kNoTile; // tell the prefix warp to exit
+			mbar_arrive(&sm.req_full[it % kReqSlots]);
+		}
+
+		// ---- emit the oldest pending segment (all of them once the input is exhausted)
+		for (int round = 0; round < (finished ? kDefer : 1); round++) {
+			if (have_p[kDefer - 1] && need_emit) {
+				unsigned long long excl = 0;
+				if (need_pos) {
+					const uint32_t slot = pit[kDefer - 1] % kReqSlots, par = (pit[kDefer - 1] / kReqSlots) & 1;
+					if (lane == 0) {
+						mbar_wait(&sm.resp_full[slot], par);
+					}
+					__syncwarp();
+					excl = sm.resp_excl[slot];
+				}
+				if (ptotal[kDefer - 1] > 0) {
+					const int64_t span_row0 =
+					    a.row_base + ((int64_t)ptile[kDefer - 1] * kTileWords + (int64_t)warp * kSpanWords) * 64;
+					if (need_pos) {
+						emit_span<WPT, NL, true>(a, pq[kDefer - 1], sm.compact[warp], excl + pwexcl[kDefer - 1], span_row0,
+						                         lane, sum_lo, sum_hi, overflow);
+					} else {
+						emit_span<WPT, NL, false>(a, pq[kDefer - 1], sm.compact[warp], 0, span_row0, lane, sum_lo, sum_hi,
+						                          overflow);
+					}
+				}
+			}
+			// shift the queue
+#pragma unroll
+			for (int d = kDefer - 1; d > 0; d--) {
+				have_p[d] = have_p[d - 1];
+				ptile[d] = ptile[d - 1];
+				ptotal[d] = ptotal[d - 1];
+				pwexcl[d] = pwexcl[d - 1];
+				pit[d] = pit[d - 1];
+#pragma unroll
+				for (int i = 0; i < WPT; i++) {
+					pq[d][i] = pq[d - 1][i];
+				}
+			}
+			have_p[0] = !finished;
+			if (!finished) {
+				ptile[0] = tile;
+				ptotal[0] = tile_total;
+				pwexcl[0] = warp_excl;
+				pit[0] = it;
+#pragma unroll
+				for (int i = 0; i < WPT; i++) {
+					pq[0][i] = q[i];
+				}
 			}
 		}
 		if (finished) {
 			break;
-		}
-
-		// ---- merged bitvector out (optional)
-		if (a.q_out) {
-			uint4 *dst = reinterpret_cast<uint4 *>(a.q_out + (size_t)tile * kTileWords + warp * (WPT * 32));
-#pragma unroll
-			for (int j = 0; j < NCH; j++) {
-				uint4 v;
-				v.x = (uint32_t)q[2 * j];
-				v.y = (uint32_t)(q[2 * j] >> 32);
-				v.z = (uint32_t)q[2 * j + 1];
-				v.w = (uint32_t)(q[2 * j + 1] >> 32);
-				dst[j * 32 + lane] = v;
-			}
-		}
-
-		// ---- decode: popcount, warp scan, block scan
-		uint32_t off[WPT]; // exclusive offset of every word inside this warp's span
-		uint32_t warp_total = 0;
-#pragma unroll
-		for (int j = 0; j < NCH; j++) {
-			const uint32_t c0 = __popcll(q[2 * j]);
-			const uint32_t c1 = __popcll(q[2 * j + 1]);
-			uint32_t incl = c0 + c1;
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
-				if (lane >= d) {
-					incl += n;
-				}
-			}
-			const uint32_t excl = incl - (c0 + c1) + warp_total;
-			off[2 * j] = excl;
-			off[2 * j + 1] = excl + c0;
-			warp_total += __shfl_sync(0xffffffffu, incl, 31);
-		}
-		const int buf = it & 1;
-		if (lane == 0) {
-			sm.warp_tot[buf][warp] = warp_total;
-		}
-		consumer_bar_sync();
-		uint32_t tile_total = 0, warp_excl = 0;
-#pragma unroll
-		for (int w = 0; w < kConsumerWarps; w++) {
-			const uint32_t t = sm.warp_tot[buf][w];
-			warp_excl += (w < warp) ? t : 0u;
-			tile_total += t;
-		}
-		if (threadIdx.x == 0) {
-			blk_count += tile_total;
-		}
-
-		const bool need_pos = (a.ids_out != nullptr) || (a.n_vcols > 0);
-		if (need_pos) {
-			// ---- single-pass inter-segment prefix: decoupled look-back by warp 0
-			if (warp == 0) {
-				unsigned long long excl = 0;
-				if (tile == 0) {
-					if (lane == 0) {
-						st_relaxed_u64(&status[0], kFlagPrefix | (unsigned long long)tile_total);
-					}
-				} else {
-					if (lane == 0) {
-						st_relaxed_u64(&status[tile], kFlagAgg | (unsigned long long)tile_total);
-					}
-					int64_t look = (int64_t)tile - 1; // window [look-31, look]
-					while (true) {
-						const int64_t idx = look - lane;
-						unsigned long long sv = kFlagPrefix; // out-of-range slots act as a zero prefix
-						if (idx >= 0) {
-							do {
-								sv = ld_relaxed_u64(&status[idx]);
-							} while ((sv >> 62) == 0);
-						}
-						const unsigned pmask = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
-						// lanes nearer than the first inclusive prefix contribute their aggregates
-						const int first = pmask ? (__ffs(pmask) - 1) : 32;
-						unsigned long long contrib = (lane <= first) ? (sv & kValMask) : 0ull;
-#pragma unroll
-						for (int d = 16; d > 0; d >>= 1) {
-							contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
-						}
-						excl += contrib;
-						if (pmask) {
-							break;
-						}
-						look -= 32;
-					}
-					if (lane == 0) {
-						st_relaxed_u64(&status[tile], kFlagPrefix | (excl + tile_total));
-					}
-				}
-				if (lane == 0) {
-					sm.tile_base[buf] = excl;
-				}
-			}
-			consumer_bar_sync();
-			const unsigned long long wbase = sm.tile_base[buf] + warp_excl;
-			const int64_t span_row0 =
-			    a.row_base + ((int64_t)tile * kTileWords + (int64_t)warp * (WPT * 32)) * 64; // global id of span bit 0
-			const int64_t local_adj = -a.row_base; // global id → local row for column probes
-
-			// ---- emit: lane = bit.  For each non-zero word the warp writes its set
-			// bits as one contiguous run of row IDs (two 32-bit halves).
-#pragma unroll
-			for (int i = 0; i < WPT; i++) {
-				const int j = i >> 1, h = i & 1;
-				unsigned nz = __ballot_sync(0xffffffffu, q[i] != 0);
-				while (nz) {
-					const int src = __ffs(nz) - 1;
-					nz &= nz - 1;
-					const uint32_t wlo = __shfl_sync(0xffffffffu, (uint32_t)q[i], src);
-					const uint32_t whi = __shfl_sync(0xffffffffu, (uint32_t)(q[i] >> 32), src);
-					const uint32_t o = __shfl_sync(0xffffffffu, off[i], src);
-					const int64_t row0 = span_row0 + (int64_t)(j * 64 + src * 2 + h) * 64;
-					const unsigned long long p0 = wbase + o;
-#pragma unroll
-					for (int half = 0; half < 2; half++) {
-						const uint32_t wv = half ? whi : wlo;
-						if ((wv >> lane) & 1u) {
-							const unsigned long long p =
-							    p0 + (half ? __popc(wlo) : 0) + __popc(wv & lanemask_lt);
-							const int64_t rid = row0 + half * 32 + lane;
-							if (p < a.ids_cap) {
-								if (a.ids_out) {
-									st_stream_s64(a.ids_out + p, rid);
-								}
-								for (int c = 0; c < a.n_vcols; c++) {
-									st_stream_s64(a.vout[c] + p, ld_nc_s64(a.vcol[c] + (rid + local_adj)));
-								}
-							}
-							if (a.agg_kind == 1) {
-								add128(sum_lo, sum_hi, ld_nc_s64(a.agg_a + (rid + local_adj)));
-							} else if (a.agg_kind == 2) {
-								const long long x = ld_nc_s64(a.agg_a + (rid + local_adj));
-								const long long y = ld_nc_s64(a.agg_b + (rid + local_adj));
-								const long long pr = x * y;
-								if (__mul64hi(x, y) != (pr >> 63)) {
-									overflow = 1;
-								}
-								add128(sum_lo, sum_hi, pr);
-							}
-						}
-					}
-				}
-			}
-		} else if (a.agg_kind != 0) {
-			// aggregate only: bit-driven masked probe, no row IDs materialised
-			const int64_t span_local0 = ((int64_t)tile * kTileWords + (int64_t)warp * (WPT * 32)) * 64;
-#pragma unroll
-			for (int i = 0; i < WPT; i++) {
-				const int j = i >> 1, h = i & 1;
-				unsigned nz = __ballot_sync(0xffffffffu, q[i] != 0);
-				while (nz) {
-					const int src = __ffs(nz) - 1;
-					nz &= nz - 1;
-					const uint32_t wlo = __shfl_sync(0xffffffffu, (uint32_t)q[i], src);
-					const uint32_t whi = __shfl_sync(0xffffffffu, (uint32_t)(q[i] >> 32), src);
-					const int64_t row0 = span_local0 + (int64_t)(j * 64 + src * 2 + h) * 64;
-#pragma unroll
-					for (int half = 0; half < 2; half++) {
-						const uint32_t wv = half ? whi : wlo;
-						if ((wv >> lane) & 1u) {
-							const int64_t r = row0 + half * 32 + lane;
-							if (a.agg_kind == 1) {
-								add128(sum_lo, sum_hi, ld_nc_s64(a.agg_a + r));
-							} else {
-								const long long x = ld_nc_s64(a.agg_a + r);
-								const long long y = ld_nc_s64(a.agg_b + r);
-								const long long pr = x * y;
-								if (__mul64hi(x, y) != (pr >> 63)) {
-									overflow = 1;
-								}
-								add128(sum_lo, sum_hi, pr);
-							}
-						}
-					}
-				}
-			}
 		}
 		it++;
 	}
@@ -483,16 +639,11 @@ __global__ void __launch_bounds__(kScanThreads) cubit_scan_kernel(const __grid_c
 			add128(lo, hi, sm.red[w].sum_lo, sm.red[w].sum_hi);
 			ovf |= sm.red[w].pad;
 		}
-		BlockPartial bp;
-		bp.count = blk_count;
-		bp.sum_lo = lo;
-		bp.sum_hi = hi;
-		bp.pad = ovf;
 		volatile BlockPartial *dst = a.partials + blockIdx.x;
-		dst->count = bp.count;
-		dst->sum_lo = bp.sum_lo;
-		dst->sum_hi = bp.sum_hi;
-		dst->pad = bp.pad;
+		dst->count = blk_count;
+		dst->sum_lo = lo;
+		dst->sum_hi = hi;
+		dst->pad = ovf;
 		__threadfence();
 		const unsigned int prev = atomicAdd(done_ctr, 1u);
 		if (prev == gridDim.x - 1) {
@@ -514,27 +665,32 @@ __global__ void __launch_bounds__(kScanThreads) cubit_scan_kernel(const __grid_c
 }
 
 // --------------------------------------------------------------------- launch
-template <int WPT, bool HAS_DELTA>
+template <int WPT, bool HAS_DELTA, int NL>
 static cudaError_t launch_scan_t(const ScanArgs &args, int sm_count, cudaStream_t stream, int *grid_out) {
-	auto kern = cubit_scan_kernel<WPT, HAS_DELTA>;
+	auto kern = cubit_scan_kernel<WPT, HAS_DELTA, NL>;
 	const size_t smem = sizeof(ScanSmem<WPT>) + 128;
 	static bool configured = false; // per template instance
-	static int blocks_per_sm = 1;
 	if (!configured) {
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) {
 			return e;
 		}
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kScanThreads, smem);
+		configured = true;
+	}
+	static int blocks_per_sm = 0;
+	if (blocks_per_sm == 0) {
+		cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kScanThreads, smem);
 		if (e != cudaSuccess) {
 			return e;
 		}
 		if (blocks_per_sm < 1) {
 			blocks_per_sm = 1;
 		}
-		configured = true;
+		if (blocks_per_sm > 2) {
+			blocks_per_sm = 2;
+		}
 	}
-	long long grid = (long long)sm_count * blocks_per_sm;
+	long long grid = (long long)sm_count * blocks_per_sm; // persistent CTAs, all co-resident
 	if (grid > (long long)args.n_seg) {
 		grid = args.n_seg;
 	}
@@ -548,28 +704,40 @@ static cudaError_t launch_scan_t(const ScanArgs &args, int sm_count, cudaStream_
 	return cudaGetLastError();
 }
 
+template <int WPT, bool HAS_DELTA>
+static cudaError_t launch_scan_nl(const ScanArgs &args, int sm_count, cudaStream_t stream, int *grid_out) {
+	switch (args.n_load) {
+	case 0:
+		return launch_scan_t<WPT, HAS_DELTA, 0>(args, sm_count, stream, grid_out);
+	case 1:
+		return launch_scan_t<WPT, HAS_DELTA, 1>(args, sm_count, stream, grid_out);
+	case 2:
+		return launch_scan_t<WPT, HAS_DELTA, 2>(args, sm_count, stream, grid_out);
+	default:
+		return cudaErrorInvalidValue;
+	}
+}
+
 cudaError_t launch_scan(const ScanArgs &args, uint32_t seg_words, bool has_delta, int sm_count, cudaStream_t stream,
                         int *grid_out) {
 	switch (seg_words) {
 	case 512:
-		return has_delta ? launch_scan_t<2, true>(args, sm_count, stream, grid_out)
-		                 : launch_scan_t<2, false>(args, sm_count, stream, grid_out);
+		return has_delta ? launch_scan_nl<2, true>(args, sm_count, stream, grid_out)
+		                 : launch_scan_nl<2, false>(args, sm_count, stream, grid_out);
 	case 1024:
-		return has_delta ? launch_scan_t<4, true>(args, sm_count, stream, grid_out)
-		                 : launch_scan_t<4, false>(args, sm_count, stream, grid_out);
+		return has_delta ? launch_scan_nl<4, true>(args, sm_count, stream, grid_out)
+		                 : launch_scan_nl<4, false>(args, sm_count, stream, grid_out);
 	case 2048:
-		return has_delta ? launch_scan_t<8, true>(args, sm_count, stream, grid_out)
-		                 : launch_scan_t<8, false>(args, sm_count, stream, grid_out);
+		return has_delta ? launch_scan_nl<8, true>(args, sm_count, stream, grid_out)
+		                 : launch_scan_nl<8, false>(args, sm_count, stream, grid_out);
 	default:
 		return cudaErrorInvalidValue;
 	}
 }
 
 int scan_max_grid(uint32_t seg_words, int sm_count) {
-	// upper bound used to size the per-block partial array: smallest stage
-	// footprint (WPT=2) allows the most CTAs per SM; 16 is a safe ceiling.
 	(void)seg_words;
-	return sm_count * 16;
+	return sm_count * 2; // two CTAs per SM
 }
 
 } // namespace cubit

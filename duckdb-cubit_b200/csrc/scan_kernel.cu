@@ -217,106 +217,154 @@ __device__ __forceinline__ void consume_row(const ScanArgs &a, unsigned long lon
 	}
 }
 
-// ---- emission of one warp's span of a merged segment.
-// q[i] of lane l is word (i*32 + l) of the span, so slot i = 2048 consecutive rows.
-template <int WPT, int NL, bool POS>
-__device__ __forceinline__ void emit_span(const ScanArgs &a, const uint64_t (&q)[WPT], uint16_t *cbuf,
-                                          unsigned long long wbase, int64_t span_row0, int lane,
+// Position-ordered write-out of `count` staged rows (16-bit row numbers relative to
+// row_origin, staged at cbuf[pad ..), pad = first output position & 1).  Per iteration the
+// warp writes 128 consecutive results as two fully contiguous 512-byte stores (lane l:
+// pairs l and l+32), gathers the fused-probe columns for them first (independent loads in
+// flight) and accumulates the aggregates.
+template <int NL, bool POS>
+__device__ __forceinline__ void write_out(const ScanArgs &a, const uint16_t *cbuf, uint32_t pad, uint32_t count,
+                                          unsigned long long pos0, int64_t row_origin, int lane,
                                           unsigned long long &sum_lo, long long &sum_hi, unsigned int &overflow) {
-	unsigned long long pos0 = wbase; // output position of the slot's first selected row
+	const int64_t local0 = row_origin - a.row_base;
+	const unsigned long long obase = pos0 - pad; // output position of staging index 0 (even)
+	const uint32_t end = pad + count;
+	const uint32_t *cb32 = reinterpret_cast<const uint32_t *>(cbuf);
+	for (uint32_t g0 = 0; g0 * 2 < end; g0 += 64) {
+		uint32_t r[2][2];
+		bool ok[2][2];
+		long long v[2][2][NL > 0 ? NL : 1];
 #pragma unroll
-	for (int i = 0; i < WPT; i++) {
-		const uint32_t wlo = (uint32_t)q[i], whi = (uint32_t)(q[i] >> 32);
-		const uint32_t clo = __popc(wlo), c = clo + __popc(whi);
-		uint32_t incl = c;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
-			if (lane >= d) {
-				incl += n;
-			}
-		}
-		const uint32_t slot_total = __shfl_sync(0xffffffffu, incl, 31);
-		if (slot_total == 0) {
-			continue;
-		}
-		// Staging index = (pos0 & 3) + rank, so staging index ≡ output position (mod 4) and a
-		// group of four staged rows maps onto one 32-byte-aligned run of output positions.
-		const uint32_t pad = (uint32_t)pos0 & 3u;
-		{
-			// lane-local compaction: the two halves of the word are two independent ctz chains
-			uint32_t p0 = pad + incl - c, p1 = p0 + clo;
-			uint32_t w0 = wlo, w1 = whi;
-			const uint32_t b0 = (uint32_t)lane * 64u, b1 = b0 + 32u;
-			while (w0 | w1) {
-				if (w0) {
-					cbuf[p0++] = (uint16_t)(b0 + (uint32_t)(__ffs(w0) - 1));
-					w0 &= w0 - 1;
-				}
-				if (w1) {
-					cbuf[p1++] = (uint16_t)(b1 + (uint32_t)(__ffs(w1) - 1));
-					w1 &= w1 - 1;
-				}
-			}
-		}
-		__syncwarp();
-		// position-ordered write-out: lane handles staged rows [4g, 4g+4)
-		const int64_t slot_row0 = span_row0 + (int64_t)i * kSlotRows;
-		const int64_t local0 = slot_row0 - a.row_base;
-		const unsigned long long obase = pos0 - pad; // output position of staging index 0 (multiple of 4)
-		const uint32_t end = pad + slot_total;
-		for (uint32_t g = lane; g * 4 < end; g += 32) {
-			const uint32_t e0 = g * 4;
-			const uint2 packed = *reinterpret_cast<const uint2 *>(cbuf + e0);
-			uint32_t r[4];
-			r[0] = packed.x & 0xffffu;
-			r[1] = packed.x >> 16;
-			r[2] = packed.y & 0xffffu;
-			r[3] = packed.y >> 16;
-			const bool full4 = e0 >= pad && e0 + 4 <= end;
-			long long v[4][NL > 0 ? NL : 1];
+		for (int h = 0; h < 2; h++) {
+			const uint32_t g = g0 + h * 32 + lane; // pair index
+			const uint32_t packed = g * 2 < end ? cb32[g] : 0u;
+			r[h][0] = packed & 0xffffu;
+			r[h][1] = packed >> 16;
+			ok[h][0] = g * 2 >= pad && g * 2 < end;
+			ok[h][1] = g * 2 + 1 < end;
 			if (NL > 0) {
 #pragma unroll
-				for (int e = 0; e < 4; e++) {
-					if (full4 || (e0 + e >= pad && e0 + e < end)) {
+				for (int e = 0; e < 2; e++) {
+					if (ok[h][e]) {
 #pragma unroll
 						for (int cc = 0; cc < NL; cc++) {
-							v[e][cc] = __ldg(a.lcol[cc] + (local0 + r[e]));
+							v[h][e][cc] = __ldg(a.lcol[cc] + (local0 + r[h][e]));
 						}
 					}
 				}
 			}
-			if (POS && full4) {
+		}
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const uint32_t g = g0 + h * 32 + lane;
+			if (POS && ok[h][0] && ok[h][1]) {
 				if (a.ids_out) {
-					longlong2 *dst = reinterpret_cast<longlong2 *>(a.ids_out + obase + e0);
-					__stcs(dst, make_longlong2(slot_row0 + r[0], slot_row0 + r[1]));
-					__stcs(dst + 1, make_longlong2(slot_row0 + r[2], slot_row0 + r[3]));
+					__stcs(reinterpret_cast<longlong2 *>(a.ids_out + obase + g * 2),
+					       make_longlong2(row_origin + r[h][0], row_origin + r[h][1]));
 				}
 #pragma unroll
 				for (int cc = 0; cc < NL; cc++) {
 					if (a.lout[cc]) {
-						longlong2 *dst = reinterpret_cast<longlong2 *>(a.lout[cc] + obase + e0);
-						__stcs(dst, make_longlong2(v[0][cc], v[1][cc]));
-						__stcs(dst + 1, make_longlong2(v[2][cc], v[3][cc]));
+						__stcs(reinterpret_cast<longlong2 *>(a.lout[cc] + obase + g * 2),
+						       make_longlong2(v[h][0][cc], v[h][1][cc]));
 					}
 				}
 				if (NL > 0) {
-#pragma unroll
-					for (int e = 0; e < 4; e++) {
-						consume_row<NL, false>(a, 0, 0, v[e], sum_lo, sum_hi, overflow);
-					}
+					consume_row<NL, false>(a, 0, 0, v[h][0], sum_lo, sum_hi, overflow);
+					consume_row<NL, false>(a, 0, 0, v[h][1], sum_lo, sum_hi, overflow);
 				}
 			} else {
 #pragma unroll
-				for (int e = 0; e < 4; e++) {
-					if (e0 + e >= pad && e0 + e < end) {
-						consume_row<NL, POS>(a, obase + e0 + e, slot_row0 + r[e], v[e], sum_lo, sum_hi, overflow);
+				for (int e = 0; e < 2; e++) {
+					if (ok[h][e]) {
+						consume_row<NL, POS>(a, obase + g * 2 + e, row_origin + r[h][e], v[h][e], sum_lo, sum_hi,
+						                     overflow);
 					}
 				}
 			}
 		}
+	}
+}
+
+// lane-local compaction of one 64-bit word: its two halves are two independent ctz chains
+__device__ __forceinline__ void stage_word(uint16_t *cbuf, uint32_t p0, uint32_t wlo, uint32_t whi, uint32_t bit0) {
+	uint32_t p1 = p0 + __popc(wlo);
+	uint32_t w0 = wlo, w1 = whi;
+	const uint32_t b1 = bit0 + 32u;
+	while (w0 | w1) {
+		if (w0) {
+			cbuf[p0++] = (uint16_t)(bit0 + (uint32_t)(__ffs(w0) - 1));
+			w0 &= w0 - 1;
+		}
+		if (w1) {
+			cbuf[p1++] = (uint16_t)(b1 + (uint32_t)(__ffs(w1) - 1));
+			w1 &= w1 - 1;
+		}
+	}
+}
+
+// ---- emission of one warp's span of a merged segment.
+// q[i] of lane l is word (i*32 + l) of the span, so slot i = 2048 consecutive rows and the
+// output order is (slot, lane, bit).
+template <int WPT, int NL, bool POS>
+__device__ __forceinline__ void emit_span(const ScanArgs &a, const uint64_t (&q)[WPT], uint16_t *cbuf,
+                                          unsigned long long wbase, int64_t span_row0, int lane,
+                                          unsigned long long &sum_lo, long long &sum_hi, unsigned int &overflow) {
+	// WPT independent warp scans, interleaved (one scan's latency for all slots)
+	uint32_t c[WPT], incl[WPT];
+#pragma unroll
+	for (int i = 0; i < WPT; i++) {
+		c[i] = __popcll(q[i]);
+		incl[i] = c[i];
+	}
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+		for (int i = 0; i < WPT; i++) {
+			const uint32_t n = __shfl_up_sync(0xffffffffu, incl[i], d);
+			if (lane >= d) {
+				incl[i] += n;
+			}
+		}
+	}
+	uint32_t slot_total[WPT], span_total = 0;
+#pragma unroll
+	for (int i = 0; i < WPT; i++) {
+		slot_total[i] = __shfl_sync(0xffffffffu, incl[i], 31);
+		span_total += slot_total[i];
+	}
+	if (span_total == 0) {
+		return;
+	}
+	if (span_total <= (uint32_t)kSlotRows && WPT * kSlotRows <= 65536) {
+		// sparse / medium span: stage ALL slots at once (row numbers relative to the span fit
+		// 16 bits), then one write-out — one synchronisation round instead of one per slot
+		const uint32_t pad = (uint32_t)wbase & 1u;
+		uint32_t base = pad;
+#pragma unroll
+		for (int i = 0; i < WPT; i++) {
+			stage_word(cbuf, base + incl[i] - c[i], (uint32_t)q[i], (uint32_t)(q[i] >> 32),
+			           (uint32_t)(i * kSlotRows + lane * 64));
+			base += slot_total[i];
+		}
 		__syncwarp();
-		pos0 += slot_total;
+		write_out<NL, POS>(a, cbuf, pad, span_total, wbase, span_row0, lane, sum_lo, sum_hi, overflow);
+		__syncwarp();
+		return;
+	}
+	unsigned long long pos0 = wbase; // output position of the slot's first selected row
+#pragma unroll
+	for (int i = 0; i < WPT; i++) {
+		if (slot_total[i] == 0) {
+			continue;
+		}
+		const uint32_t pad = (uint32_t)pos0 & 1u;
+		stage_word(cbuf, pad + incl[i] - c[i], (uint32_t)q[i], (uint32_t)(q[i] >> 32), (uint32_t)lane * 64u);
+		__syncwarp();
+		write_out<NL, POS>(a, cbuf, pad, slot_total[i], pos0, span_row0 + (int64_t)i * kSlotRows, lane, sum_lo, sum_hi,
+		                   overflow);
+		__syncwarp();
+		pos0 += slot_total[i];
 	}
 }
 

@@ -8,7 +8,8 @@ Workload (BASELINE.json configs[1]), per GPU:
 One STEP = the whole selectivity sweep: six queries
     OR over the 10 value bitvectors 10..19 → sorted int64 row IDs → probe payload at those
     rows (values materialised) → COUNT, SUM(payload)
-each as ONE fused sm_100a kernel (merge + decode + probe + aggregate).
+each as two sm_100a kernels: the single-pass fused merge+decode kernel, then the bit-driven probe
+kernel (gather + SUM).
     value  = table rows covered per second, inputs resident in HBM, device-timed (CUDA events)
     e2e    = the same sweep through the synchronous C-ABI call a DuckDB table function makes
              (host predicate structs in, aggregate row + first 2048-row DataChunk out)
@@ -218,8 +219,8 @@ def run_b200(args):
             dist.all_reduce(tt)
             fl = tt.tolist()
             agg = [sharding.from_limbs(fl[i * 5:(i + 1) * 5]) for i in range(len(res))]
-        infos = [(r.info.ms_scan, r.info.algo_bytes_scan + r.info.algo_bytes_probe, r.count, r.info.n_launches)
-                 for r in res]
+        infos = [(r.info.ms_scan, r.info.ms_probe, r.info.algo_bytes_scan, r.info.algo_bytes_probe, r.count,
+                  r.info.n_launches, r.info.fused) for r in res]
         for r in res:
             r.free()
         return agg, infos
@@ -234,8 +235,8 @@ def run_b200(args):
         agg, infos = step_device()
     # correctness of what is being timed: COUNT equals Σ popcount of the (disjoint) value
     # bitvectors and SUM(payload) equals the closed form only via the global check below
-    for (c, _), e in zip(([(i[2], 0) for i in infos]), expect):
-        assert c == e, "count %d != expected %d" % (c, e)
+    for inf, e in zip(infos, expect):
+        assert inf[4] == e, "count %d != expected %d" % (inf[4], e)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -246,15 +247,29 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.time()
     e0.record(stream)
-    kernel_ms, kernel_bytes, per_sel = 0.0, 0, [[0.0, 0, 0] for _ in SELECTIVITIES]
+    # per-kernel accumulators: [ms, algorithmic bytes, launches]
+    kscan, kprobe = [0.0, 0, 0], [0.0, 0, 0]
+    per_sel = [dict(ms_scan=0.0, ms_probe=0.0, by_scan=0, by_probe=0, cnt=0, fused=0) for _ in SELECTIVITIES]
     for _ in range(args.steps):
         agg, infos = step_device()
-        for i, (ms, by, cnt, _nl) in enumerate(infos):
-            kernel_ms += ms
-            kernel_bytes += by
-            per_sel[i][0] += ms
-            per_sel[i][1] += by
-            per_sel[i][2] = cnt
+        for i, (ms_s, ms_p, by_s, by_p, cnt, _nl, fused) in enumerate(infos):
+            ps = per_sel[i]
+            ps["cnt"], ps["fused"] = cnt, fused
+            ps["ms_scan"] += ms_s
+            ps["ms_probe"] += ms_p
+            ps["by_scan"] += by_s
+            ps["by_probe"] += by_p
+            if ms_p > 0:        # separate probe kernel ran
+                kscan[0] += ms_s
+                kscan[1] += by_s
+                kscan[2] += 1
+                kprobe[0] += ms_p
+                kprobe[1] += by_p
+                kprobe[2] += 1
+            else:               # probe fused into the scan kernel
+                kscan[0] += ms_s
+                kscan[1] += by_s + by_p
+                kscan[2] += 1
     e1.record(stream)
     barrier()
     wall1 = time.time()
@@ -346,31 +361,44 @@ def run_b200(args):
         return 0
 
     peak, peak_src = measured_peak()
-    achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
-    traffic = None
+    traffic = {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("cubit_scan_kernel_avg_dram_bytes_per_launch")
+            traffic = json.load(open(tp))
         except Exception:
-            traffic = None
+            traffic = {}
+
+    def roof(acc, kernel, tkey, formula):
+        ms, by, n = acc
+        ach = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "frac_of_nominal_8TBs": ach / 8000.0, "traffic": traffic.get(tkey), "peak_source": peak_src,
+                "launches": n, "bytes_per_launch_avg": by / n if n else 0, "ms_per_launch_avg": ms / n if n else 0,
+                "share_of_step": ms / (ms_per_step * args.steps) if ms_per_step > 0 else 0, "bytes_formula": formula}
+
+    roof_scan = roof(kscan, "cubit_scan_kernel<4,false,0> (segment merge + bit->row-ID decode, single pass)",
+                     "cubit_scan_kernel_dram_bytes_per_launch",
+                     "k*ceil(N/64)*8 + 8*M  [SURVEY 8d]")
+    roof_probe = roof(kprobe, "cubit_probe_bits_kernel<4,1,true> (bit-driven probe: gather payload + SUM)",
+                      "cubit_probe_bits_kernel_dram_bytes_per_launch",
+                      "8*M payload values read + ceil(N/64)*8 re-read of the merged bitvector  [SURVEY 8d: P]")
+    dominant = roof_probe if kprobe[0] > kscan[0] else roof_scan
     sweep = []
-    for s, (sms, sby, cnt) in zip(SELECTIVITIES, per_sel):
-        gbs = sby / (sms * 1e-3) / 1e9 if sms > 0 else 0.0
-        sweep.append({"selectivity": s, "rows_selected": cnt, "kernel_ms": sms / args.steps,
-                      "rows_per_s": rows / (sms / args.steps * 1e-3) if sms > 0 else 0.0, "algo_gbs": gbs,
-                      "frac_of_peak": gbs / peak})
+    for s, ps in zip(SELECTIVITIES, per_sel):
+        ms_tot = (ps["ms_scan"] + ps["ms_probe"]) / args.steps
+        g_scan = ps["by_scan"] / (ps["ms_scan"] * 1e-3) / 1e9 if ps["ms_scan"] > 0 else 0.0
+        sweep.append({"selectivity": s, "rows_selected": ps["cnt"], "probe_fused": bool(ps["fused"] and ps["ms_probe"] == 0),
+                      "scan_ms": ps["ms_scan"] / args.steps, "probe_ms": ps["ms_probe"] / args.steps,
+                      "rows_per_s": rows / (ms_tot * 1e-3) if ms_tot > 0 else 0.0,
+                      "scan_algo_gbs": g_scan, "scan_frac_of_peak": g_scan / peak})
+    kernel_bytes = kscan[1] + kprobe[1]
     line = {
         "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(rows, world),
         "hbm_gbs": world * (kernel_bytes / args.steps) / (ms_per_step * 1e-3) / 1e9,
-        "roofline": {"bound": "hbm", "kernel": "cubit_scan_kernel<4,false> (fused merge+decode+probe+SUM)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": traffic, "peak_source": peak_src,
-                     "bytes_per_launch_avg": kernel_bytes / (args.steps * n_q),
-                     "ms_per_launch_avg": kernel_ms / (args.steps * n_q),
-                     "bytes_formula": "k*ceil(N/64)*8 + 8*M + 8*M (row IDs out, payload read; SURVEY §8d)"},
+        "roofline": dominant, "roofline_merge_decode": roof_scan, "roofline_probe": roof_probe,
         "sweep": sweep,
         "e2e": {"value": e2e_value, "unit": "rows/s",
                 "h2d_bytes_per_step": n_q * scan_args_bytes,

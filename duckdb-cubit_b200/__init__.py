@@ -23,7 +23,7 @@ ABI_VERSION = 1
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5
 MAX_STREAMS = 64
 MAX_PROBE_COLS = 8
-Q_ROWIDS, Q_BITVECTOR, Q_VALUES, Q_TIMING, Q_UNFUSED, Q_ASYNC = 1, 2, 4, 8, 16, 32
+Q_ROWIDS, Q_BITVECTOR, Q_VALUES, Q_TIMING, Q_UNFUSED, Q_ASYNC, Q_FUSE_PROBE = 1, 2, 4, 8, 16, 32, 64
 AGG_NONE, AGG_SUM, AGG_SUM_PROD = 0, 1, 2
 
 # every symbol include/cubit_gpu.h declares (tests check the library exports all of them)

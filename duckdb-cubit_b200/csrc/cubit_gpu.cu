@@ -102,6 +102,7 @@ struct cubit_gpu_result {
 	cudaEvent_t ev[4] = {};
 	cudaEvent_t ev_done = nullptr;
 	bool timing = false, probe_timed = false;
+	uint64_t probe_fixed_bytes = 0;
 	uint64_t probe_widths = 0; // bytes per selected row the probe needs (distinct columns, + row-ID re-read)
 	bool finished = false;
 	cubit_result_info info = {};
@@ -697,7 +698,7 @@ static int finish_result(cubit_gpu_result *r) {
 	r->info.algo_bytes_scan += 8ull * ((r->flags & CUBIT_Q_ROWIDS) ? r->info.count : 0);
 	// P of SURVEY §8d: M * Σ width over the distinct columns whose values are needed
 	// (+ 8*M when a separate probe kernel re-reads the row IDs)
-	r->info.algo_bytes_probe = r->info.count * r->probe_widths;
+	r->info.algo_bytes_probe = r->info.count * r->probe_widths + r->probe_fixed_bytes;
 	if (r->timing) {
 		float ms = 0;
 		cudaEventElapsedTime(&ms, r->ev[0], r->ev[1]);
@@ -824,14 +825,7 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 		}
 	}
 	const bool need_probe = want_vals || q->agg_kind != CUBIT_AGG_NONE;
-	// Fusing the probe into the scan kernel pays when the selection is sparse (saves a launch
-	// and the row-ID re-read) or when no row IDs are materialised at all (bit-driven aggregate).
-	// For dense materialising queries the gathers need more loads in flight than the scan
-	// kernel's 8 consumer warps can hold, so the dedicated probe kernel runs instead.
-	if ((want_ids || want_vals) && cap > t->n_rows / 64) {
-		fusable = false;
-	}
-	// the fused kernel gathers at most kMaxFusedCols DISTINCT int64 columns per selected row
+	// The scan-side probe paths gather at most kMaxFusedCols DISTINCT int64 columns per row.
 	const Column *dist_cols[kMaxFusedCols] = {};
 	int dist_out[kMaxFusedCols] = {-1, -1}; // which projected column each distinct column feeds
 	int n_dist = 0, agg_ia = 0, agg_ib = 0;
@@ -867,8 +861,24 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 			fusable = agg_ib >= 0;
 		}
 	}
-	const bool separate_probe = need_probe && !fusable;
-	const bool need_ids_buf = want_ids || separate_probe;
+	// How the probe runs:
+	//   PROBE_BITS    (default) bit-driven probe kernel right after the scan kernel: re-decodes the
+	//                 merged bitvector (1 bit/row instead of 8 bytes/selected row) as a plain fully
+	//                 occupied grid — the gathers need far more loads in flight than the scan
+	//                 kernel's 8 consumer warps per CTA can hold, and inside the scan kernel their
+	//                 latency lands on the consumers' critical path (measured: profiles/)
+	//   PROBE_FUSED   inside the scan kernel (CUBIT_Q_FUSE_PROBE): one launch
+	//   PROBE_GATHER  gather kernel over the row-ID list — 4-byte columns, > 2 columns, UNFUSED
+	enum { PROBE_NONE, PROBE_FUSED, PROBE_BITS, PROBE_GATHER } probe_mode = PROBE_NONE;
+	if (need_probe) {
+		if (!fusable) {
+			probe_mode = PROBE_GATHER;
+		} else {
+			probe_mode = (q->flags & CUBIT_Q_FUSE_PROBE) ? PROBE_FUSED : PROBE_BITS;
+		}
+	}
+	const bool separate_probe = probe_mode == PROBE_GATHER;
+	const bool need_ids_buf = want_ids || separate_probe || (probe_mode == PROBE_BITS && want_vals);
 	if (!need_ids_buf && !want_vals) {
 		cap = 0;
 	}
@@ -903,14 +913,17 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 	const size_t ctrl_bytes = ((size_t)t->n_seg + 1) * 8;
 	const size_t ctrl_pad = (ctrl_bytes + 63) & ~(size_t)63;
 	const size_t part_bytes = (size_t)max_grid * sizeof(BlockPartial);
-	// layout: hdr | ctrl A | ctrl B (decode pass of the unfused path) | partials | probe done
-	const size_t block_bytes = hdr_bytes + 2 * ctrl_pad + part_bytes + 64;
+	// layout: hdr | ctrl A | ctrl B (decode pass of the unfused path) | partials | probe done | segment prefixes
+	const size_t excl_bytes = probe_mode == PROBE_BITS ? ctrl_pad : 0;
+	const size_t block_bytes = hdr_bytes + 2 * ctrl_pad + part_bytes + 64 + excl_bytes;
 	Q_TRY(cudaMallocAsync((void **)&r->d_block, block_bytes, st));
 	r->d_hdr = reinterpret_cast<ResultHeader *>(r->d_block);
 	unsigned long long *ctrl_a = reinterpret_cast<unsigned long long *>(r->d_block + hdr_bytes);
 	unsigned long long *ctrl_b = reinterpret_cast<unsigned long long *>(r->d_block + hdr_bytes + ctrl_pad);
 	BlockPartial *partials = reinterpret_cast<BlockPartial *>(r->d_block + hdr_bytes + 2 * ctrl_pad);
 	unsigned int *probe_done = reinterpret_cast<unsigned int *>(r->d_block + hdr_bytes + 2 * ctrl_pad + part_bytes);
+	unsigned long long *tile_excl =
+	    reinterpret_cast<unsigned long long *>(r->d_block + hdr_bytes + 2 * ctrl_pad + part_bytes + 64);
 	if (!t->hdr_pool.empty()) {
 		r->h_hdr = t->hdr_pool.back();
 		t->hdr_pool.pop_back();
@@ -930,7 +943,7 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 	if (want_q) {
 		Q_TRY(cudaMallocAsync((void **)&r->d_q, t->words_per_bv * 8, st));
 	}
-	if (unfused && !want_q) {
+	if ((unfused || probe_mode == PROBE_BITS) && !want_q) {
 		Q_TRY(cudaMallocAsync((void **)&r->d_q_tmp, t->words_per_bv * 8, st));
 	}
 	Q_TRY(cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming));
@@ -954,9 +967,10 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 	if (!unfused) {
 		// one pass: merge (+delta XOR) + decode (+ fused probe / aggregate when eligible)
 		sa.ctrl = ctrl_a;
-		sa.q_out = r->d_q;
+		sa.q_out = probe_mode == PROBE_BITS && !want_q ? r->d_q_tmp : r->d_q;
 		sa.ids_out = need_ids_buf ? r->d_ids : nullptr;
-		if (fusable) {
+		sa.tile_excl = probe_mode == PROBE_BITS && want_vals ? tile_excl : nullptr;
+		if (probe_mode == PROBE_FUSED) {
 			sa.n_load = n_dist;
 			for (int d = 0; d < n_dist; d++) {
 				sa.lcol[d] = static_cast<const long long *>(dist_cols[d]->d);
@@ -997,6 +1011,30 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 	}
 	if (r->timing) {
 		Q_TRY(cudaEventRecord(r->ev[1], st));
+	}
+	if (probe_mode == PROBE_BITS) {
+		ScanArgs pb;
+		memset(&pb, 0, sizeof(pb));
+		pb.q_out = sa.q_out; // input of the bit-driven probe
+		pb.tile_excl = sa.tile_excl;
+		pb.n_seg = t->n_seg;
+		pb.row_base = t->row_base;
+		pb.ids_cap = cap;
+		pb.n_load = n_dist;
+		for (int d = 0; d < n_dist; d++) {
+			pb.lcol[d] = static_cast<const long long *>(dist_cols[d]->d);
+			pb.lout[d] = dist_out[d] >= 0 && cap ? static_cast<long long *>(r->d_vals[dist_out[d]]) : nullptr;
+		}
+		pb.agg_kind = q->agg_kind;
+		pb.agg_ia = agg_ia;
+		pb.agg_ib = agg_ib;
+		pb.hdr = r->d_hdr;
+		Q_TRY(launch_probe_bits(pb, t->seg_words, want_vals && cap, t->sm_count, st));
+		n_launch++;
+		if (r->timing) {
+			Q_TRY(cudaEventRecord(r->ev[2], st));
+			r->probe_timed = true;
+		}
 	}
 	if (separate_probe) {
 		ProbeArgs pa;
@@ -1046,8 +1084,9 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 			add_col(q->agg_col_b, 8);
 		}
 		if (separate_probe) {
-			r->probe_widths += 8;
+			r->probe_widths += 8; // the gather kernel re-reads the 8-byte row IDs
 		}
+		r->probe_fixed_bytes = probe_mode == PROBE_BITS ? t->n_words * 8 : 0; // ... the bit-driven one re-reads Q
 	}
 	r->info.capacity = cap;
 	r->info.n_streams = k;

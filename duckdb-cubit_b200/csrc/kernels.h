@@ -50,6 +50,7 @@ struct ScanArgs {
 	int64_t row_base;                   // global row ID of local row 0
 	unsigned long long *ctrl;           // control block (see above)
 	uint64_t *q_out;                    // merged bitvector out, or nullptr
+	unsigned long long *tile_excl;      // per-segment exclusive prefix out (scan) / in (bit-driven probe), or nullptr
 	long long *ids_out;                 // sorted row IDs out, or nullptr
 	unsigned long long ids_cap;         // capacity of ids_out / vals_out in rows
 	// fused probe: the distinct int64 columns read at every selected row
@@ -85,6 +86,11 @@ struct ProbeArgs {
 cudaError_t launch_scan(const ScanArgs &args, uint32_t seg_words, bool has_delta, int sm_count, cudaStream_t stream,
                         int *grid_out);
 int scan_max_grid(uint32_t seg_words, int sm_count);
+// Bit-driven probe: re-decodes the merged bitvector args.q_out (input here) with the
+// per-segment prefixes args.tile_excl and gathers / sums the fused-probe columns at full
+// occupancy.  Sums are ADDED to args.hdr (which the scan kernel has already finalised).
+cudaError_t launch_probe_bits(const ScanArgs &args, uint32_t seg_words, bool positions, int sm_count,
+                              cudaStream_t stream);
 
 cudaError_t launch_probe(const ProbeArgs &args, int sm_count, cudaStream_t stream);
 int probe_grid(int sm_count);

@@ -467,6 +467,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 			if (lane == 0) {
 				sm.resp_excl[slot] = excl;
 				mbar_arrive(&sm.resp_full[slot]);
+				if (a.tile_excl) {
+					a.tile_excl[tile] = excl; // consumed by the bit-driven probe kernel
+				}
 			}
 			t0 = tile;
 			s0 = excl + total;
@@ -709,6 +712,137 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 			a.hdr->sum_hi = thi;
 			a.hdr->overflow = (unsigned int)tovf;
 		}
+	}
+}
+
+// ------------------------------------------------------------ bit-driven probe
+// The dense-selection probe (SURVEY §8a A3 "direct bit-driven masked streaming when density
+// is high"): instead of re-reading 8-byte row IDs it re-decodes the merged bitvector Q
+// (1 bit per row) with the per-segment prefixes left by the scan kernel, and gathers the
+// columns with the same staged, position-ordered write-out — but as a plain, fully
+// occupied grid (48 warps / SM), which is what the gathers need to keep HBM busy.
+constexpr int kProbeBitsThreads = 256;
+
+template <int WPT, int NL, bool POS>
+__global__ void __launch_bounds__(kProbeBitsThreads) cubit_probe_bits_kernel(const __grid_constant__ ScanArgs a) {
+	constexpr int kTileWords = kProbeBitsThreads * WPT;
+	constexpr int kSpanWords = WPT * 32;
+	__shared__ __align__(16) uint16_t compact[kProbeBitsThreads / 32][kSlotRows + 8];
+	__shared__ uint32_t warp_tot[2][kProbeBitsThreads / 32];
+	__shared__ BlockPartial red[kProbeBitsThreads / 32];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	unsigned long long sum_lo = 0;
+	long long sum_hi = 0;
+	unsigned int overflow = 0;
+	uint32_t it = 0;
+	for (uint32_t tile = blockIdx.x; tile < a.n_seg; tile += gridDim.x, it++) {
+		uint64_t q[WPT];
+		const uint64_t *src = a.q_out + (size_t)tile * kTileWords + warp * kSpanWords;
+		uint32_t cnt = 0;
+#pragma unroll
+		for (int i = 0; i < WPT; i++) {
+			q[i] = __ldg(src + i * 32 + lane);
+			cnt += __popcll(q[i]);
+		}
+		unsigned long long wbase = 0;
+		if (POS) {
+			cnt = __reduce_add_sync(0xffffffffu, cnt);
+			if (lane == 0) {
+				warp_tot[it & 1][warp] = cnt;
+			}
+			__syncthreads();
+			uint32_t warp_excl = 0;
+#pragma unroll
+			for (int w = 0; w < kProbeBitsThreads / 32; w++) {
+				warp_excl += (w < warp) ? warp_tot[it & 1][w] : 0u;
+			}
+			wbase = a.tile_excl[tile] + warp_excl;
+		}
+		const int64_t span_row0 = a.row_base + ((int64_t)tile * kTileWords + (int64_t)warp * kSpanWords) * 64;
+		emit_span<WPT, NL, POS>(a, q, compact[warp], wbase, span_row0, lane, sum_lo, sum_hi, overflow);
+	}
+	if (a.agg_kind == 0) {
+		return;
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		const unsigned long long olo = __shfl_xor_sync(0xffffffffu, sum_lo, d);
+		const long long ohi = __shfl_xor_sync(0xffffffffu, sum_hi, d);
+		add128(sum_lo, sum_hi, olo, ohi);
+		overflow |= __shfl_xor_sync(0xffffffffu, overflow, d);
+	}
+	if (lane == 0) {
+		red[warp].sum_lo = sum_lo;
+		red[warp].sum_hi = sum_hi;
+		red[warp].pad = overflow;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned long long lo = 0, ovf = 0;
+		long long hi = 0;
+		for (int w = 0; w < kProbeBitsThreads / 32; w++) {
+			add128(lo, hi, red[w].sum_lo, red[w].sum_hi);
+			ovf |= red[w].pad;
+		}
+		// exact 128-bit accumulate: the carry out of the low limb is recovered from the value
+		// the atomic returns, the high limbs simply add
+		const unsigned long long old = atomicAdd(&a.hdr->sum_lo, lo);
+		const long long carry = (old + lo) < old ? 1 : 0;
+		atomicAdd(reinterpret_cast<unsigned long long *>(&a.hdr->sum_hi), (unsigned long long)(hi + carry));
+		if (ovf) {
+			atomicOr(&a.hdr->overflow, 1u);
+		}
+	}
+}
+
+template <int WPT, int NL, bool POS>
+static cudaError_t launch_probe_bits_t(const ScanArgs &args, int sm_count, cudaStream_t stream) {
+	auto kern = cubit_probe_bits_kernel<WPT, NL, POS>;
+	static int blocks_per_sm = 0;
+	if (blocks_per_sm == 0) {
+		cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kProbeBitsThreads, 0);
+		if (e != cudaSuccess) {
+			return e;
+		}
+		if (blocks_per_sm < 1) {
+			blocks_per_sm = 1;
+		}
+	}
+	long long grid = (long long)sm_count * blocks_per_sm * 4; // short-lived CTAs, dynamic balance by the HW scheduler
+	if (grid > (long long)args.n_seg) {
+		grid = args.n_seg;
+	}
+	if (grid < 1) {
+		grid = 1;
+	}
+	kern<<<(unsigned)grid, kProbeBitsThreads, 0, stream>>>(args);
+	return cudaGetLastError();
+}
+
+template <int WPT>
+static cudaError_t launch_probe_bits_w(const ScanArgs &args, bool positions, int sm_count, cudaStream_t stream) {
+	if (args.n_load == 1) {
+		return positions ? launch_probe_bits_t<WPT, 1, true>(args, sm_count, stream)
+		                 : launch_probe_bits_t<WPT, 1, false>(args, sm_count, stream);
+	}
+	if (args.n_load == 2) {
+		return positions ? launch_probe_bits_t<WPT, 2, true>(args, sm_count, stream)
+		                 : launch_probe_bits_t<WPT, 2, false>(args, sm_count, stream);
+	}
+	return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_probe_bits(const ScanArgs &args, uint32_t seg_words, bool positions, int sm_count,
+                              cudaStream_t stream) {
+	switch (seg_words) {
+	case 512:
+		return launch_probe_bits_w<2>(args, positions, sm_count, stream);
+	case 1024:
+		return launch_probe_bits_w<4>(args, positions, sm_count, stream);
+	case 2048:
+		return launch_probe_bits_w<8>(args, positions, sm_count, stream);
+	default:
+		return cudaErrorInvalidValue;
 	}
 }
 

@@ -72,6 +72,8 @@ typedef struct cubit_pred_group {
 #define CUBIT_Q_TIMING (1u << 3)    /* record per-kernel CUDA-event times in cubit_result_info */
 #define CUBIT_Q_UNFUSED (1u << 4)   /* force merge → decode → probe as three separate kernels  */
 #define CUBIT_Q_ASYNC (1u << 5)     /* enqueue only; cubit_gpu_result_wait() completes it      */
+#define CUBIT_Q_FUSE_PROBE (1u << 6) /* probe inside the scan kernel (one launch) instead of the
+                                        bit-driven probe kernel that follows it by default      */
 
 /* fused aggregate over the selected rows (SUM semantics of the reference:
  * int64 input, 128-bit accumulator — sum.cpp:172-178, sum_helpers.hpp:92-113) */

@@ -1,0 +1,150 @@
+#include "cubit_index.hpp"
+
+#include "cubit_gpu.h"
+
+namespace cubit_host {
+
+void ThrowLastError(int rc) {
+	std::string msg = cubit_gpu_last_error();
+	if (rc == CUBIT_EINVAL) {
+		throw InvalidInputException(msg);
+	}
+	throw InternalException("cubit_gpu: " + msg);
+}
+
+static inline void Check(int rc) {
+	if (rc != CUBIT_OK) {
+		ThrowLastError(rc);
+	}
+}
+
+CubitTable::CubitTable(idx_t n_rows_p, row_t row_base_p, uint32_t seg_bits, int device)
+    : n_rows(n_rows_p), row_base(row_base_p) {
+	Check(cubit_gpu_create(device, n_rows, row_base, seg_bits, &handle));
+}
+
+CubitTable::~CubitTable() {
+	cubit_gpu_destroy(handle);
+}
+
+void CubitTable::AddColumn(column_t col, const int64_t *values) {
+	Check(cubit_gpu_upload_column(handle, (int32_t)col, values, 8, n_rows));
+	col_types[col] = LogicalTypeId::BIGINT;
+}
+
+void CubitTable::AddColumn(column_t col, const int32_t *values) {
+	Check(cubit_gpu_upload_column(handle, (int32_t)col, values, 4, n_rows));
+	col_types[col] = LogicalTypeId::INTEGER;
+}
+
+LogicalTypeId CubitTable::ColumnType(column_t col) const {
+	if (col == COLUMN_IDENTIFIER_ROW_ID) {
+		return LogicalTypeId::BIGINT;
+	}
+	auto it = col_types.find(col);
+	if (it == col_types.end()) {
+		throw InvalidInputException("Table does not have column " + std::to_string(col));
+	}
+	return it->second;
+}
+
+CubitIndex::CubitIndex(CubitTable &table_p, column_t column_p, int64_t base_value_p, uint32_t cardinality_p)
+    : table(table_p), column(column_p), base_value(base_value_p), cardinality(cardinality_p) {
+	Check(cubit_gpu_index_create(table.Handle(), cardinality, &index_id));
+}
+
+uint32_t CubitIndex::ValueId(int64_t v) const {
+	if (v < base_value || v >= base_value + (int64_t)cardinality) {
+		throw InvalidInputException("key " + std::to_string(v) + " outside the indexed domain");
+	}
+	return (uint32_t)(v - base_value);
+}
+
+void CubitIndex::Build() {
+	Check(cubit_gpu_index_build(table.Handle(), index_id, (int32_t)column, base_value));
+}
+
+void CubitIndex::Delete(row_t row_id, int64_t current_value) {
+	std::lock_guard<std::mutex> lk(mu);
+	const uint32_t v = ValueId(current_value);
+	pending[v].push_back(row_id - table.RowBase());
+	dirty[v] = true;
+}
+
+void CubitIndex::Update(row_t row_id, int64_t old_value, int64_t new_value) {
+	if (old_value == new_value) {
+		return;
+	}
+	std::lock_guard<std::mutex> lk(mu);
+	const uint32_t a = ValueId(old_value), b = ValueId(new_value);
+	pending[a].push_back(row_id - table.RowBase());
+	pending[b].push_back(row_id - table.RowBase());
+	dirty[a] = dirty[b] = true;
+}
+
+void CubitIndex::CommitDeltas() {
+	std::lock_guard<std::mutex> lk(mu);
+	for (auto &kv : dirty) {
+		if (!kv.second) {
+			continue;
+		}
+		auto &rows = pending[kv.first];
+		Check(cubit_gpu_set_delta(table.Handle(), index_id, kv.first, rows.data(), rows.size()));
+		kv.second = false;
+	}
+}
+
+void CubitIndex::MergeDeltas() {
+	CommitDeltas();
+	std::lock_guard<std::mutex> lk(mu);
+	Check(cubit_gpu_merge_deltas(table.Handle(), index_id));
+	pending.clear();
+	dirty.clear();
+}
+
+idx_t CubitIndex::PendingDeltaRows() const {
+	std::lock_guard<std::mutex> lk(mu);
+	idx_t n = 0;
+	for (auto &kv : pending) {
+		n += kv.second.size();
+	}
+	return n;
+}
+
+bool CubitIndex::Scan(int64_t lo, int64_t hi, idx_t max_count, std::vector<row_t> &row_ids) {
+	lo = lo < base_value ? base_value : lo;
+	hi = hi >= base_value + (int64_t)cardinality ? base_value + (int64_t)cardinality - 1 : hi;
+	if (lo > hi) {
+		row_ids.clear();
+		return true;
+	}
+	std::vector<cubit_bv_ref> refs;
+	for (int64_t v = lo; v <= hi; v++) {
+		refs.push_back(cubit_bv_ref {index_id, (uint32_t)(v - base_value)});
+	}
+	if (refs.size() > CUBIT_MAX_STREAMS) {
+		throw InvalidInputException("range spans more than CUBIT_MAX_STREAMS value bitvectors");
+	}
+	cubit_pred_group grp {(uint32_t)refs.size(), refs.data()};
+	cubit_query q {};
+	q.n_groups = 1;
+	q.groups = &grp;
+	q.flags = CUBIT_Q_ROWIDS;
+	cubit_gpu_result *res = nullptr;
+	Check(cubit_gpu_query(table.Handle(), &q, &res));
+	cubit_result_info info;
+	int rc = cubit_gpu_result_get(res, &info);
+	if (rc == CUBIT_OK && info.count > max_count) {
+		cubit_gpu_free_result(res);
+		return false; // ART::Scan gives up past max_count (art.cpp:955-972)
+	}
+	if (rc == CUBIT_OK) {
+		row_ids.resize(info.count);
+		rc = cubit_gpu_fetch(res, 0, info.count, row_ids.data(), 0, nullptr);
+	}
+	cubit_gpu_free_result(res);
+	Check(rc);
+	return true;
+}
+
+} // namespace cubit_host

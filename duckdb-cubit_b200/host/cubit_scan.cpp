@@ -1,0 +1,183 @@
+#include "cubit_scan.hpp"
+
+#include "cubit_gpu.h"
+
+#include <algorithm>
+
+namespace cubit_host {
+
+static constexpr idx_t kWindowRows = 128 * STANDARD_VECTOR_SIZE; // rows per device→host transfer
+
+static inline void Check(int rc) {
+	if (rc != CUBIT_OK) {
+		ThrowLastError(rc);
+	}
+}
+
+CubitScanGlobalState::~CubitScanGlobalState() {
+	if (result) {
+		cubit_gpu_free_result(result);
+	}
+}
+
+std::unique_ptr<CubitScanBindData> CubitScanBind(CubitTable &table, std::vector<CubitPredicate> predicates,
+                                                 CubitAggregate aggregate, column_t agg_a, column_t agg_b) {
+	if (predicates.empty()) {
+		throw InvalidInputException("cubit_scan needs at least one predicate on an indexed column");
+	}
+	for (auto &p : predicates) {
+		if (!p.index || &p.index->Table() != &table) {
+			throw InvalidInputException("cubit_scan predicate refers to an index of another table");
+		}
+	}
+	auto bind = std::make_unique<CubitScanBindData>();
+	bind->table = &table;
+	bind->predicates = std::move(predicates);
+	bind->aggregate = aggregate;
+	bind->agg_column_a = agg_a;
+	bind->agg_column_b = agg_b;
+	return bind;
+}
+
+std::vector<LogicalTypeId> CubitScanReturnTypes(const CubitScanBindData &bind, const std::vector<column_t> &column_ids) {
+	if (bind.aggregate != CubitAggregate::NONE) {
+		return {LogicalTypeId::BIGINT, LogicalTypeId::BIGINT, LogicalTypeId::BIGINT}; // COUNT, SUM lower, SUM upper
+	}
+	std::vector<LogicalTypeId> types;
+	for (auto c : column_ids) {
+		types.push_back(bind.table->ColumnType(c));
+	}
+	return types;
+}
+
+std::unique_ptr<CubitScanGlobalState> CubitScanInitGlobal(const CubitScanBindData &bind,
+                                                         const std::vector<column_t> &column_ids) {
+	auto state = std::make_unique<CubitScanGlobalState>();
+	state->column_ids = column_ids;
+	state->types = CubitScanReturnTypes(bind, column_ids);
+
+	// predicate → AND of OR groups over value bitvectors
+	std::vector<std::vector<cubit_bv_ref>> refs(bind.predicates.size());
+	std::vector<cubit_pred_group> groups;
+	bool empty_result = false;
+	for (size_t g = 0; g < bind.predicates.size(); g++) {
+		const auto &p = bind.predicates[g];
+		const int64_t base = p.index->BaseValue(), card = p.index->Cardinality();
+		const int64_t lo = std::max(p.lo, base), hi = std::min(p.hi, base + card - 1);
+		if (lo > hi) {
+			empty_result = true;
+			break;
+		}
+		for (int64_t v = lo; v <= hi; v++) {
+			refs[g].push_back(cubit_bv_ref {p.index->Id(), (uint32_t)(v - base)});
+		}
+		groups.push_back(cubit_pred_group {(uint32_t)refs[g].size(), refs[g].data()});
+	}
+	if (empty_result) {
+		state->row_count = 0;
+		return state;
+	}
+	std::vector<int32_t> cols;
+	bool want_rowid = false;
+	for (auto c : column_ids) {
+		if (c == COLUMN_IDENTIFIER_ROW_ID) {
+			want_rowid = true;
+		} else {
+			cols.push_back((int32_t)c);
+		}
+	}
+	cubit_query q {};
+	q.n_groups = (uint32_t)groups.size();
+	q.groups = groups.data();
+	if (bind.aggregate != CubitAggregate::NONE) {
+		q.flags = 0; // aggregate push-down: no row IDs are materialised at all
+		q.agg_kind = (int32_t)bind.aggregate;
+		q.agg_col_a = (int32_t)bind.agg_column_a;
+		q.agg_col_b = (int32_t)bind.agg_column_b;
+	} else {
+		q.flags = (want_rowid ? CUBIT_Q_ROWIDS : 0u) | (cols.empty() ? 0u : CUBIT_Q_VALUES);
+		q.n_cols = (uint32_t)cols.size();
+		q.cols = cols.data();
+	}
+	Check(cubit_gpu_query(bind.table->Handle(), &q, &state->result));
+	cubit_result_info info;
+	Check(cubit_gpu_result_get(state->result, &info));
+	state->row_count = info.count;
+	state->sum.lower = info.sum_lo;
+	state->sum.upper = info.sum_hi;
+	return state;
+}
+
+static void FillWindow(CubitScanGlobalState &st) {
+	const idx_t n = std::min(kWindowRows, st.row_count - st.offset);
+	st.win_begin = st.offset;
+	st.win_end = st.offset + n;
+	bool want_rowid = false;
+	std::vector<void *> ptrs;
+	st.win_cols.resize(st.column_ids.size());
+	for (size_t i = 0; i < st.column_ids.size(); i++) {
+		if (st.column_ids[i] == COLUMN_IDENTIFIER_ROW_ID) {
+			want_rowid = true;
+		} else {
+			st.win_cols[i].resize(n * (size_t)st.types[i]);
+			ptrs.push_back(st.win_cols[i].data());
+		}
+	}
+	if (want_rowid) {
+		st.win_rowids.resize(n);
+	}
+	Check(cubit_gpu_fetch(st.result, st.win_begin, n, want_rowid ? st.win_rowids.data() : nullptr, (uint32_t)ptrs.size(),
+	                      ptrs.data()));
+}
+
+void CubitScanFunction(const CubitScanBindData &bind, CubitScanGlobalState &st, DataChunk &output) {
+	output.Reset();
+	if (st.finished) {
+		return;
+	}
+	if (bind.aggregate != CubitAggregate::NONE) {
+		if (!st.aggregate_done) {
+			if (output.ColumnCount() != 3) {
+				throw InternalException("aggregate push-down returns (COUNT, SUM lower, SUM upper)");
+			}
+			output.data[0].GetData<int64_t>()[0] = (int64_t)st.row_count;
+			output.data[1].GetData<int64_t>()[0] = (int64_t)st.sum.lower;
+			output.data[2].GetData<int64_t>()[0] = st.sum.upper;
+			output.SetCardinality(1);
+			st.aggregate_done = true;
+		} else {
+			st.finished = true;
+		}
+		return;
+	}
+	if (st.offset >= st.row_count) {
+		st.finished = true;
+		return;
+	}
+	if (output.ColumnCount() != st.column_ids.size()) {
+		throw InternalException("output chunk does not match the projected column list");
+	}
+	if (st.offset >= st.win_end) {
+		FillWindow(st);
+	}
+	// IndexScanFunction: scan_count = min(STANDARD_VECTOR_SIZE, remaining)  (table_scan.cpp:258-261)
+	const idx_t scan_count = std::min<idx_t>(STANDARD_VECTOR_SIZE, st.win_end - st.offset);
+	const idx_t rel = st.offset - st.win_begin;
+	for (size_t i = 0; i < st.column_ids.size(); i++) {
+		if (st.column_ids[i] == COLUMN_IDENTIFIER_ROW_ID) {
+			memcpy(output.data[i].Raw(), st.win_rowids.data() + rel, scan_count * sizeof(row_t));
+		} else {
+			const size_t w = (size_t)st.types[i];
+			memcpy(output.data[i].Raw(), st.win_cols[i].data() + rel * w, scan_count * w);
+		}
+	}
+	output.SetCardinality(scan_count);
+	st.offset += scan_count;
+}
+
+SourceResultType CubitScanGetData(const CubitScanBindData &bind, CubitScanGlobalState &gstate, DataChunk &chunk) {
+	CubitScanFunction(bind, gstate, chunk);
+	return chunk.size() == 0 ? SourceResultType::FINISHED : SourceResultType::HAVE_MORE_OUTPUT;
+}
+
+} // namespace cubit_host

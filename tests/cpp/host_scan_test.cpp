@@ -1,0 +1,167 @@
+// host_scan_test.cpp — drives the C++ host layer the way PhysicalTableScan drives a table
+// function (bind → init_global → GetData until FINISHED) and checks every chunk against a
+// brute-force evaluation of the same predicate over the columns.  Mirrors the shape of the
+// reference's own scan tests (test/sql/index/art/scan/test_art_many_matches.test: exact
+// counts for =, <, <=, >, >= over duplicates; test/api/capi/capi_table_functions.cpp).
+// Exit code 0 = all checks passed.  Needs a B200 (no CPU fallback).
+#include "cubit_scan.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+
+using namespace cubit_host;
+
+#define REQUIRE(cond)                                                                                                  \
+	do {                                                                                                               \
+		if (!(cond)) {                                                                                                 \
+			fprintf(stderr, "REQUIRE failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__);                                 \
+			exit(1);                                                                                                   \
+		}                                                                                                              \
+	} while (0)
+
+static uint64_t rng_state = 0x1234567;
+static uint64_t Rng() {
+	rng_state += 0x9E3779B97F4A7C15ull;
+	uint64_t z = rng_state;
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+
+static void ArtManyMatches(idx_t reps) {
+	// [0,1,0,1,...]: i<1, i<=1, i=0, i=1, i>0, i>=0 (test_art_many_matches.test)
+	std::vector<int32_t> col(2 * reps);
+	for (idx_t r = 0; r < col.size(); r++) {
+		col[r] = (int32_t)(r & 1);
+	}
+	CubitTable table(col.size());
+	table.AddColumn(0, col.data());
+	CubitIndex index(table, 0, 0, 2);
+	index.Build();
+	std::vector<row_t> ids;
+	REQUIRE(index.Scan(0, 0, 1 << 30, ids) && ids.size() == reps);
+	REQUIRE(index.Scan(0, 1, 1 << 30, ids) && ids.size() == 2 * reps);
+	REQUIRE(index.Scan(1, 1, 1 << 30, ids) && ids.size() == reps);
+	for (idx_t i = 0; i < ids.size(); i++) {
+		REQUIRE(ids[i] == (row_t)(2 * i + 1)); // sorted, unique (art.cpp:974-985)
+	}
+	REQUIRE(index.Scan(1, 100, 1 << 30, ids) && ids.size() == reps);  // i > 0
+	REQUIRE(index.Scan(-5, 100, 1 << 30, ids) && ids.size() == 2 * reps); // i >= 0
+	REQUIRE(!index.Scan(0, 1, reps, ids));                                // more than max_count → false
+	REQUIRE(index.Scan(7, 9, 10, ids) && ids.empty());
+}
+
+int main() {
+	ArtManyMatches(1024);
+	ArtManyMatches(2048);
+
+	const idx_t n = 1000003;
+	const row_t row_base = 65536 * 4;
+	std::vector<int32_t> qty(n), disc(n);
+	std::vector<int64_t> price(n);
+	for (idx_t r = 0; r < n; r++) {
+		qty[r] = 1 + (int32_t)(Rng() % 50);
+		disc[r] = (int32_t)(Rng() % 11);
+		price[r] = 90000 + (int64_t)(Rng() % 10000000);
+	}
+	std::vector<int64_t> disc64(disc.begin(), disc.end());
+	CubitTable table(n, row_base);
+	table.AddColumn(0, qty.data());
+	table.AddColumn(1, disc.data());
+	table.AddColumn(2, price.data());
+	table.AddColumn(3, disc64.data());
+	CubitIndex iq(table, 0, 1, 50), id(table, 1, 0, 11);
+	iq.Build();
+	id.Build();
+
+	// pending deltas: updates and deletes, XOR-ed at query time
+	std::vector<bool> deleted(n, false);
+	for (int i = 0; i < 5000; i++) {
+		const idx_t r = Rng() % n;
+		if (deleted[r]) {
+			continue;
+		}
+		if (i & 1) {
+			const int32_t nv = 1 + (int32_t)(Rng() % 50);
+			iq.Update(row_base + (row_t)r, qty[r], nv);
+			qty[r] = nv;
+		} else {
+			iq.Delete(row_base + (row_t)r, qty[r]);
+			id.Delete(row_base + (row_t)r, disc[r]);
+			deleted[r] = true;
+		}
+	}
+	iq.CommitDeltas();
+	id.CommitDeltas();
+	REQUIRE(iq.PendingDeltaRows() > 0);
+
+	for (int round = 0; round < 2; round++) {
+		// WHERE qty BETWEEN 10 AND 19 AND disc BETWEEN 5 AND 7 → rowid, price, disc
+		auto bind = CubitScanBind(table, {{&iq, 10, 19}, {&id, 5, 7}});
+		std::vector<column_t> column_ids = {COLUMN_IDENTIFIER_ROW_ID, 2, 1};
+		auto gstate = CubitScanInitGlobal(*bind, column_ids);
+		REQUIRE(gstate->MaxThreads() == 1);
+		DataChunk chunk;
+		chunk.Initialize(CubitScanReturnTypes(*bind, column_ids));
+		idx_t r = 0, seen = 0, calls = 0;
+		__int128 expect_sum = 0;
+		idx_t expect_count = 0;
+		while (CubitScanGetData(*bind, *gstate, chunk) == SourceResultType::HAVE_MORE_OUTPUT) {
+			calls++;
+			REQUIRE(chunk.size() <= STANDARD_VECTOR_SIZE);
+			for (idx_t i = 0; i < chunk.size(); i++, seen++) {
+				while (r < n && (deleted[r] || qty[r] < 10 || qty[r] > 19 || disc[r] < 5 || disc[r] > 7)) {
+					r++;
+				}
+				REQUIRE(r < n);
+				REQUIRE(chunk.data[0].GetData<row_t>()[i] == row_base + (row_t)r);
+				REQUIRE(chunk.data[1].GetData<int64_t>()[i] == price[r]);
+				REQUIRE(chunk.data[2].GetData<int32_t>()[i] == disc[r]);
+				expect_sum += (__int128)price[r] * disc[r];
+				expect_count++;
+				r++;
+			}
+		}
+		while (r < n && (deleted[r] || qty[r] < 10 || qty[r] > 19 || disc[r] < 5 || disc[r] > 7)) {
+			r++;
+		}
+		REQUIRE(r == n && seen == gstate->row_count && seen > 0);
+		REQUIRE(calls >= (seen + STANDARD_VECTOR_SIZE - 1) / STANDARD_VECTOR_SIZE);
+
+		// aggregate push-down: SELECT count(*), sum(price * disc) → one row
+		auto abind = CubitScanBind(table, {{&iq, 10, 19}, {&id, 5, 7}}, CubitAggregate::SUM_PRODUCT, 2, 3);
+		auto astate = CubitScanInitGlobal(*abind, {});
+		DataChunk arow;
+		arow.Initialize(CubitScanReturnTypes(*abind, {}));
+		REQUIRE(CubitScanGetData(*abind, *astate, arow) == SourceResultType::HAVE_MORE_OUTPUT && arow.size() == 1);
+		REQUIRE((idx_t)arow.data[0].GetData<int64_t>()[0] == expect_count);
+		const __int128 got = ((__int128)arow.data[2].GetData<int64_t>()[0] << 64) |
+		                     (unsigned __int128)(uint64_t)arow.data[1].GetData<int64_t>()[0];
+		REQUIRE(got == expect_sum);
+		REQUIRE(CubitScanGetData(*abind, *astate, arow) == SourceResultType::FINISHED);
+
+		if (round == 0) { // merge-back must not change any answer
+			iq.MergeDeltas();
+			id.MergeDeltas();
+			REQUIRE(iq.PendingDeltaRows() == 0);
+		}
+	}
+
+	// errors are exceptions, as in the reference's table functions
+	bool threw = false;
+	try {
+		CubitScanBind(table, {});
+	} catch (const InvalidInputException &) {
+		threw = true;
+	}
+	REQUIRE(threw);
+	threw = false;
+	try {
+		iq.Delete(row_base, 77);
+	} catch (const InvalidInputException &) {
+		threw = true;
+	}
+	REQUIRE(threw);
+	printf("host_scan_test ok\n");
+	return 0;
+}

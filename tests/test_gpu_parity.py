@@ -42,11 +42,14 @@ def refs(ent, ix):
 
 
 @pytest.mark.parametrize("seg_bits", [32768, 65536, 131072])
-@pytest.mark.parametrize("unfused", [False, True])
-def test_tpch_sf001_against_reference_goldens(cubit, golden, lineitem, seg_bits, unfused):
+@pytest.mark.parametrize("mode", ["default", "unfused", "fuse_probe"])
+def test_tpch_sf001_against_reference_goldens(cubit, golden, lineitem, seg_bits, mode):
+    """default = fused merge+decode kernel then bit-driven probe kernel; unfused = three kernels
+    (merge, decode, gather probe); fuse_probe = everything in the scan kernel"""
     g, gids = golden
+    unfused = mode == "unfused"
     t, ix = make_lineitem_table(cubit, lineitem, seg_bits, build_on_gpu=(seg_bits == 65536))
-    extra = cubit.Q_UNFUSED if unfused else 0
+    extra = {"default": 0, "unfused": cubit.Q_UNFUSED, "fuse_probe": cubit.Q_FUSE_PROBE}[mode]
     for name, ent in g["tpch_sf001"]["answers"].items():
         want = gids["tpch_sf001/%s/ids" % name]
         with t.query(refs(ent, ix), flags=cubit.Q_ROWIDS | cubit.Q_VALUES | cubit.Q_BITVECTOR | extra,
@@ -106,7 +109,7 @@ def test_pending_deltas_match_sql_update_delete(cubit, golden, lineitem, seg_bit
     def check():
         for name, ent in answers.items():
             want = gids["tpch_sf001_delta/%s/ids" % name]
-            for extra in (0, cubit.Q_UNFUSED):
+            for extra in (0, cubit.Q_UNFUSED, cubit.Q_FUSE_PROBE):
                 with t.query(refs(ent, ix), flags=cubit.Q_ROWIDS | extra, agg=cubit.AGG_SUM, agg_a=COL_PRICE) as r:
                     ids, _ = r.fetch()
                     assert np.array_equal(ids, want), name
@@ -126,7 +129,7 @@ def test_pending_deltas_match_sql_update_delete(cubit, golden, lineitem, seg_bit
 
 def random_case(rng, n, card):
     col = rng.integers(0, card, n).astype(np.int32)
-    pay = rng.integers(-2**62, 2**62, n).astype(np.int64)
+    pay = rng.integers(-2**31, 2**31, n).astype(np.int64) * 3
     return col, pay
 
 
@@ -164,7 +167,7 @@ def test_random_tables_all_paths(cubit, n, seg_bits, row_base):
         q = oracle.merge(og, od)
         want = oracle.decode(q, row_base)
         wv = oracle.probe(want, pay, row_base)
-        for extra in (0, cubit.Q_UNFUSED):
+        for extra in (0, cubit.Q_UNFUSED, cubit.Q_FUSE_PROBE):
             with t.query([[(ix, v) for v in grp] for grp in groups],
                          flags=cubit.Q_ROWIDS | cubit.Q_VALUES | cubit.Q_BITVECTOR | extra, cols=[0, 1],
                          agg=cubit.AGG_SUM, agg_a=0) as r:
@@ -175,6 +178,14 @@ def test_random_tables_all_paths(cubit, n, seg_bits, row_base):
                 assert np.array_equal(cv, col[want - row_base])
                 assert r.sum == oracle.sum_i64(wv)
                 assert np.array_equal(r.bitvector(), q)
+                # int64-only projection → the bit-driven probe (default) / in-kernel probe paths
+                with t.query([[(ix, v) for v in grp] for grp in groups], flags=cubit.Q_VALUES | extra, cols=[0],
+                             agg=cubit.AGG_SUM_PROD, agg_a=0, agg_b=0) as r2:
+                    sp, ovf = oracle.sum_prod_i64(wv, wv)
+                    if ovf:
+                        pytest.fail("test data must not overflow")
+                    assert r2.count == len(want) and r2.sum == sp
+                    assert np.array_equal(r2.fetch(rowids=False)[1][0], wv)
                 if len(want) > 5:  # windowed fetch, the DataChunk hand-off (≤2048 rows per call)
                     i2, (v2, _) = r.fetch(offset=3, n=min(2048, len(want) - 3))
                     assert np.array_equal(i2, want[3:3 + len(i2)]) and np.array_equal(v2, wv[3:3 + len(i2)])

@@ -1,0 +1,118 @@
+/* cubit_gpu_mock.c — TEST INFRASTRUCTURE ONLY.
+ * A CPU stand-in for the subset of include/cubit_gpu.h that integration/duckdb_cubit_extension.cpp
+ * calls, implemented with the ORACLE (oracle/cubit_oracle.c).  It exists so that the DuckDB-side glue can
+ * be exercised end-to-end through real reference SQL in the GPU-less build container
+ * (tests/test_duckdb_integration.py).  It is never built into, linked with or loaded by the product. */
+#include "cubit_gpu.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+void oracle_merge(const uint64_t *const *streams, const uint64_t *const *deltas, const int32_t *group_of, int k,
+                  uint64_t n_words, uint64_t *q);
+uint64_t oracle_decode(const uint64_t *q, uint64_t n_words, int64_t row_base, int64_t *out);
+uint64_t oracle_popcount(const uint64_t *q, uint64_t n_words);
+void oracle_probe(const int64_t *ids, uint64_t n, int64_t row_base, const void *col, uint32_t elem_bytes, void *out);
+void oracle_sum_i64(const int64_t *vals, uint64_t n, uint64_t *sum_lo, int64_t *sum_hi);
+void oracle_build_index(const void *col, uint32_t elem_bytes, uint64_t n_rows, int64_t base_value, uint32_t card,
+                        uint64_t *bitvectors, uint64_t n_words);
+
+#define MAX_COLS 64
+struct cubit_gpu_table {
+	uint64_t n_rows, n_words;
+	int64_t row_base;
+	int64_t *cols[MAX_COLS];
+	uint64_t *bits; /* one index only */
+	uint32_t card;
+};
+struct cubit_gpu_result {
+	struct cubit_gpu_table *t;
+	uint64_t count;
+	int64_t *ids;
+	int64_t *vals[CUBIT_MAX_PROBE_COLS];
+	uint32_t n_cols;
+	uint64_t sum_lo;
+	int64_t sum_hi;
+};
+static char g_err[256] = "";
+
+int cubit_gpu_abi_version(void) { return CUBIT_GPU_ABI_VERSION; }
+const char *cubit_gpu_last_error(void) { return g_err; }
+int cubit_gpu_create(int device, uint64_t n_rows, int64_t row_base, uint32_t seg_bits, cubit_gpu_table **out) {
+	(void)device; (void)seg_bits;
+	struct cubit_gpu_table *t = calloc(1, sizeof(*t));
+	t->n_rows = n_rows; t->n_words = (n_rows + 63) / 64; t->row_base = row_base;
+	*out = t;
+	return CUBIT_OK;
+}
+int cubit_gpu_destroy(cubit_gpu_table *t) {
+	if (!t) return CUBIT_OK;
+	for (int i = 0; i < MAX_COLS; i++) free(t->cols[i]);
+	free(t->bits); free(t);
+	return CUBIT_OK;
+}
+int cubit_gpu_upload_column(cubit_gpu_table *t, int32_t col_id, const void *data, uint32_t elem_bytes, uint64_t n) {
+	if (elem_bytes != 8 || col_id < 0 || col_id >= MAX_COLS || n != t->n_rows) { snprintf(g_err, sizeof g_err, "mock: bad column"); return CUBIT_EINVAL; }
+	t->cols[col_id] = malloc(n * 8);
+	memcpy(t->cols[col_id], data, n * 8);
+	return CUBIT_OK;
+}
+int cubit_gpu_index_create(cubit_gpu_table *t, uint32_t cardinality, int32_t *index_id) {
+	t->card = cardinality; t->bits = calloc((size_t)cardinality * t->n_words, 8); *index_id = 0;
+	return CUBIT_OK;
+}
+int cubit_gpu_index_build(cubit_gpu_table *t, int32_t index_id, int32_t col_id, int64_t base_value) {
+	(void)index_id;
+	oracle_build_index(t->cols[col_id], 8, t->n_rows, base_value, t->card, t->bits, t->n_words);
+	return CUBIT_OK;
+}
+int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_result **out) {
+	const uint64_t *streams[CUBIT_MAX_STREAMS]; int32_t group_of[CUBIT_MAX_STREAMS]; int k = 0;
+	for (uint32_t g = 0; g < q->n_groups; g++)
+		for (uint32_t i = 0; i < q->groups[g].n_refs; i++) {
+			if (q->groups[g].refs[i].value_id >= t->card) { snprintf(g_err, sizeof g_err, "mock: bad value id"); return CUBIT_EINVAL; }
+			streams[k] = t->bits + (size_t)q->groups[g].refs[i].value_id * t->n_words; group_of[k++] = (int32_t)g;
+		}
+	uint64_t *qb = malloc(t->n_words * 8);
+	oracle_merge(streams, NULL, group_of, k, t->n_words, qb);
+	struct cubit_gpu_result *r = calloc(1, sizeof(*r));
+	r->t = t; r->count = oracle_popcount(qb, t->n_words);
+	r->ids = malloc((r->count + 1) * 8);
+	oracle_decode(qb, t->n_words, t->row_base, r->ids);
+	free(qb);
+	if (q->flags & CUBIT_Q_VALUES) {
+		r->n_cols = q->n_cols;
+		for (uint32_t c = 0; c < q->n_cols; c++) {
+			r->vals[c] = malloc((r->count + 1) * 8);
+			oracle_probe(r->ids, r->count, t->row_base, t->cols[q->cols[c]], 8, r->vals[c]);
+		}
+	}
+	if (q->agg_kind == CUBIT_AGG_SUM) {
+		int64_t *tmp = malloc((r->count + 1) * 8);
+		oracle_probe(r->ids, r->count, t->row_base, t->cols[q->agg_col_a], 8, tmp);
+		oracle_sum_i64(tmp, r->count, &r->sum_lo, &r->sum_hi);
+		free(tmp);
+	}
+	*out = r;
+	return CUBIT_OK;
+}
+int cubit_gpu_result_get(cubit_gpu_result *r, cubit_result_info *info) {
+	memset(info, 0, sizeof(*info));
+	info->count = r->count; info->sum_lo = r->sum_lo; info->sum_hi = r->sum_hi;
+	return CUBIT_OK;
+}
+int cubit_gpu_fetch(cubit_gpu_result *r, uint64_t offset, uint64_t n, int64_t *host_rowids, uint32_t n_cols,
+                    void *const *host_cols) {
+	if (offset + n > r->count || n_cols > r->n_cols) { snprintf(g_err, sizeof g_err, "mock: bad fetch"); return CUBIT_EINVAL; }
+	if (host_rowids) memcpy(host_rowids, r->ids + offset, n * 8);
+	for (uint32_t c = 0; c < n_cols; c++) memcpy(host_cols[c], r->vals[c] + offset, n * 8);
+	return CUBIT_OK;
+}
+int cubit_gpu_free_result(cubit_gpu_result *r) {
+	if (!r) return CUBIT_OK;
+	free(r->ids);
+	for (int c = 0; c < CUBIT_MAX_PROBE_COLS; c++) free(r->vals[c]);
+	free(r);
+	return CUBIT_OK;
+}

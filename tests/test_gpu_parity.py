@@ -129,7 +129,7 @@ def test_pending_deltas_match_sql_update_delete(cubit, golden, lineitem, seg_bit
 
 def random_case(rng, n, card):
     col = rng.integers(0, card, n).astype(np.int32)
-    pay = rng.integers(-2**31, 2**31, n).astype(np.int64) * 3
+    pay = rng.integers(-2**62, 2**62, n).astype(np.int64)
     return col, pay
 
 
@@ -142,8 +142,10 @@ def test_random_tables_all_paths(cubit, n, seg_bits, row_base):
     col, pay = random_case(rng, n, card)
     bv = oracle.build_index(col, 0, card)
     t = cubit.CubitTable(n, row_base=row_base, seg_bits=seg_bits)
+    small = pay >> 40
     t.upload_column(0, pay)
     t.upload_column(1, col)
+    t.upload_column(2, small)
     ix = t.create_index(card)
     t.build_index(ix, 1, 0)
     for v in range(card):
@@ -180,11 +182,10 @@ def test_random_tables_all_paths(cubit, n, seg_bits, row_base):
                 assert np.array_equal(r.bitvector(), q)
                 # int64-only projection → the bit-driven probe (default) / in-kernel probe paths
                 with t.query([[(ix, v) for v in grp] for grp in groups], flags=cubit.Q_VALUES | extra, cols=[0],
-                             agg=cubit.AGG_SUM_PROD, agg_a=0, agg_b=0) as r2:
-                    sp, ovf = oracle.sum_prod_i64(wv, wv)
-                    if ovf:
-                        pytest.fail("test data must not overflow")
-                    assert r2.count == len(want) and r2.sum == sp
+                             agg=cubit.AGG_SUM_PROD, agg_a=2, agg_b=2) as r2:
+                    ws = oracle.probe(want, small, row_base)
+                    sp, ovf = oracle.sum_prod_i64(ws, ws)
+                    assert not ovf and r2.count == len(want) and r2.sum == sp
                     assert np.array_equal(r2.fetch(rowids=False)[1][0], wv)
                 if len(want) > 5:  # windowed fetch, the DataChunk hand-off (≤2048 rows per call)
                     i2, (v2, _) = r.fetch(offset=3, n=min(2048, len(want) - 3))

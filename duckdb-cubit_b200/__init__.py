@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcubit_gpu.so")
+LIB_PATH = os.environ.get("CUBIT_GPU_LIB") or os.path.join(_HERE, "libcubit_gpu.so")  # override: kernel experiments
 HOST_LIB_PATH = os.path.join(_HERE, "libcubit_host.so")
 
 # ---- mirror of include/cubit_gpu.h -------------------------------------------------
@@ -309,7 +309,7 @@ class CubitTable:
 
     def synth_column(self, col_id, kind, seed=0, threshold=0, card=100, hot_lo=10, hot_n=10):
         _check(self._L.cubit_gpu_synth_column(self._h, col_id, kind, seed, threshold, card, hot_lo, hot_n))
-        self._col_dtype[col_id] = np.dtype(np.int64 if kind == 0 else np.int32)
+        self._col_dtype[col_id] = np.dtype(np.int64 if kind in (0, 3) else np.int32)
 
     def drop_column(self, col_id):
         _check(self._L.cubit_gpu_drop_column(self._h, col_id))

@@ -369,6 +369,12 @@ __global__ void cubit_synth_kernel(void *col, int kind, uint64_t n_rows, int64_t
 	     r += (uint64_t)gridDim.x * blockDim.x) {
 		if (kind == 0) {
 			static_cast<long long *>(col)[r] = row_base + (long long)r;
+		} else if (kind == 2) { // uniform int32 in [hot_lo, hot_lo + card)
+			const uint64_t z = splitmix64(seed + (uint64_t)row_base + r);
+			static_cast<int *>(col)[r] = (int)(hot_lo + (uint32_t)((z >> 7) % card));
+		} else if (kind == 3) { // uniform int64 in [hot_lo, hot_lo + threshold)
+			const uint64_t z = splitmix64(seed + (uint64_t)row_base + r);
+			static_cast<long long *>(col)[r] = (long long)hot_lo + (long long)((z >> 7) % threshold);
 		} else {
 			const uint64_t z = splitmix64(seed + (uint64_t)row_base + r);
 			const uint64_t y = z >> 7;

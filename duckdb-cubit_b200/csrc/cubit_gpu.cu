@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -159,6 +160,10 @@ extern "C" int cubit_gpu_create(int device, uint64_t n_rows, int64_t row_base, u
 	cudaError_t e = cudaGetDeviceCount(&ndev);
 	if (e != cudaSuccess || ndev == 0) {
 		return fail(CUBIT_ENODEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+	}
+	if (const char *g = getenv("CUBIT_L2_FETCH_BYTES")) { // experiment knob (profiles/): L2→DRAM fetch granularity
+		cudaSetDevice(device);
+		cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
 	}
 	if (device < 0 || device >= ndev) {
 		return fail(CUBIT_EINVAL, "device %d out of range (have %d)", device, ndev);
@@ -606,8 +611,11 @@ extern "C" int cubit_gpu_synth_column(cubit_gpu_table *t, int32_t col_id, int32_
 	if (!t) {
 		return fail(CUBIT_EINVAL, "NULL argument");
 	}
-	if (kind != 0 && kind != 1) {
-		return fail(CUBIT_EINVAL, "kind must be 0 or 1");
+	if (kind < 0 || kind > 3) {
+		return fail(CUBIT_EINVAL, "kind must be 0..3");
+	}
+	if ((kind == 2 && card == 0) || (kind == 3 && threshold == 0)) {
+		return fail(CUBIT_EINVAL, "empty value range");
 	}
 	if (kind == 1 && (hot_n == 0 || hot_n >= card || hot_lo + hot_n > card)) {
 		return fail(CUBIT_EINVAL, "bad hot range");
@@ -616,7 +624,7 @@ extern "C" int cubit_gpu_synth_column(cubit_gpu_table *t, int32_t col_id, int32_
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
-	const uint32_t elem = kind == 0 ? 8 : 4;
+	const uint32_t elem = (kind == 0 || kind == 3) ? 8 : 4;
 	Column &c = t->columns[col_id];
 	if (c.d && (c.elem != elem || c.n != t->n_rows)) {
 		CU_TRY(cudaStreamSynchronize(t->stream));

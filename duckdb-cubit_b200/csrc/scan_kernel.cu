@@ -118,6 +118,26 @@ __device__ __forceinline__ void add128(unsigned long long &lo, long long &hi, un
 	hi += hi2 + (long long)(lo < lo2);
 }
 
+// gather load used by the probe paths (experiment knob: -DCUBIT_GATHER_LD=n)
+#ifndef CUBIT_GATHER_LD
+#define CUBIT_GATHER_LD 0
+#endif
+__device__ __forceinline__ long long gather_ld(const long long *p) {
+#if CUBIT_GATHER_LD == 0
+	return __ldg(p);
+#elif CUBIT_GATHER_LD == 1
+	return __ldcg(p);
+#elif CUBIT_GATHER_LD == 2
+	return __ldcs(p);
+#elif CUBIT_GATHER_LD == 3
+	long long v;
+	asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
+	return v;
+#else
+	return *p;
+#endif
+}
+
 constexpr int kReqSlots = 4;       // look-back requests in flight per CTA (> emission deferral depth)
 constexpr int kDefer = 2;          // segments merged between a segment's merge and its emission
 constexpr int kWaitBatch = 4;      // ring stages consumed per mbarrier round trip
@@ -248,7 +268,7 @@ __device__ __forceinline__ void write_out(const ScanArgs &a, const uint16_t *cbu
 					if (ok[h][e]) {
 #pragma unroll
 						for (int cc = 0; cc < NL; cc++) {
-							v[h][e][cc] = __ldg(a.lcol[cc] + (local0 + r[h][e]));
+							v[h][e][cc] = gather_ld(a.lcol[cc] + (local0 + r[h][e]));
 						}
 					}
 				}

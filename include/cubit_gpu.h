@@ -161,7 +161,9 @@ int cubit_gpu_download_column(cubit_gpu_table *t, int32_t col_id, void *data, ui
  * the generators are restated in oracle/cubit_oracle.c):
  *   kind 0: int64 payload, value = row_base + r
  *   kind 1: int32 value column of SURVEY §8d config 2: z = splitmix64(seed + row_base + r);
- *           z < threshold ? hot_lo + (z>>7) % hot_n : the (z>>7) % (card-hot_n)-th value outside the hot range */
+ *           z < threshold ? hot_lo + (z>>7) % hot_n : the (z>>7) % (card-hot_n)-th value outside the hot range
+ *   kind 2: int32 uniform in [hot_lo, hot_lo+card):      hot_lo + (z>>7) % card
+ *   kind 3: int64 uniform in [hot_lo, hot_lo+threshold): hot_lo + (z>>7) % threshold */
 int cubit_gpu_synth_column(cubit_gpu_table *t, int32_t col_id, int32_t kind, uint64_t seed, uint64_t threshold,
                            uint32_t card, uint32_t hot_lo, uint32_t hot_n);
 int cubit_gpu_drop_column(cubit_gpu_table *t, int32_t col_id);

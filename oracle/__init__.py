@@ -174,7 +174,7 @@ def delta_from_rows(rows, n_rows):
 
 
 def synth_column(kind, n_rows, row_base=0, seed=0, threshold=0, card=100, hot_lo=10, hot_n=10):
-    col = np.empty(n_rows, dtype=np.int64 if kind == 0 else np.int32)
+    col = np.empty(n_rows, dtype=np.int64 if kind in (0, 3) else np.int32)
     lib().oracle_synth_column(col.ctypes.data, kind, n_rows, row_base, seed, threshold, card, hot_lo, hot_n)
     return col
 

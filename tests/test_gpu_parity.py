@@ -312,3 +312,74 @@ def test_full_size_properties_1b_rows(cubit, sel):
                  agg_a=0) as r2:
         assert r2.count == expect and r2.sum == fused_sum
     t.close()
+
+
+def test_q6_shape_three_indexes_k38_against_oracle(cubit):
+    """config 3 shape at a size the oracle finishes in seconds: three indexes (84 month bins, 11 discounts,
+    50 quantities), Q = (12 months) AND (3 discounts) AND (23 quantities), k = 38, probe price & discount,
+    SUM(price*discount); device generators vs their oracle restatement included."""
+    n = 3_000_017
+    t = cubit.CubitTable(n, row_base=131072, seg_bits=131072)
+    t.synth_column(0, 3, seed=21, threshold=10_410_000, hot_lo=90_000)
+    t.synth_column(1, 3, seed=22, threshold=11, hot_lo=0)
+    t.synth_column(2, 2, seed=23, card=50, hot_lo=1)
+    t.synth_column(3, 2, seed=24, card=84, hot_lo=0)
+    price = oracle.synth_column(3, n, 131072, 21, 10_410_000, 0, 90_000, 0)
+    disc = oracle.synth_column(3, n, 131072, 22, 11, 0, 0, 0)
+    qty = oracle.synth_column(2, n, 131072, 23, 0, 50, 1, 0)
+    month = oracle.synth_column(2, n, 131072, 24, 0, 84, 0, 0)
+    for cid, ref in ((0, price), (1, disc), (2, qty), (3, month)):
+        assert np.array_equal(t.download_column(cid), ref)
+    ixd, ixq, ixm = t.create_index(11), t.create_index(50), t.create_index(84)
+    t.build_index(ixd, 1, 0)
+    t.build_index(ixq, 2, 1)
+    t.build_index(ixm, 3, 0)
+    bd, bq, bm = oracle.build_index(disc, 0, 11), oracle.build_index(qty, 1, 50), oracle.build_index(month, 0, 84)
+    groups = [[(ixm, m) for m in range(24, 36)], [(ixd, v) for v in (5, 6, 7)], [(ixq, v) for v in range(23)]]
+    og = [[bm[m] for m in range(24, 36)], [bd[v] for v in (5, 6, 7)], [bq[v] for v in range(23)]]
+    want = oracle.decode(oracle.merge(og), 131072)
+    wp, wd = oracle.probe(want, price, 131072), oracle.probe(want, disc, 131072)
+    ws, ovf = oracle.sum_prod_i64(wp, wd)
+    assert not ovf and len(want) > 1000
+    for extra in (0, cubit.Q_UNFUSED, cubit.Q_FUSE_PROBE):
+        with t.query(groups, flags=cubit.Q_ROWIDS | cubit.Q_VALUES | extra, cols=[0, 1], agg=cubit.AGG_SUM_PROD,
+                     agg_a=0, agg_b=1) as r:
+            assert r.info.n_streams == 38 and r.count == len(want) and r.sum == ws
+            ids, (p, d) = r.fetch()
+            assert np.array_equal(ids, want) and np.array_equal(p, wp) and np.array_equal(d, wd)
+        with t.query(groups, flags=extra, agg=cubit.AGG_SUM_PROD, agg_a=0, agg_b=1) as r:
+            assert r.count == len(want) and r.sum == ws
+    t.close()
+
+
+def test_concurrent_queries_on_one_table(cubit):
+    """the table handle is thread-safe (calls serialise on its stream): 8 host threads, mixed predicates"""
+    import threading
+    n = 2_000_003
+    rng = np.random.default_rng(5)
+    col = rng.integers(0, 20, n).astype(np.int32)
+    pay = rng.integers(-10**9, 10**9, n).astype(np.int64)
+    bv = oracle.build_index(col, 0, 20)
+    t = cubit.CubitTable(n)
+    t.upload_column(0, pay)
+    t.upload_column(1, col)
+    ix = t.create_index(20)
+    t.build_index(ix, 1, 0)
+    errors = []
+
+    def work(k):
+        try:
+            for rep in range(6):
+                vals = [(k + rep + j) % 20 for j in range(1 + (k % 4))]
+                want = oracle.decode(oracle.merge([[bv[v] for v in vals]]))
+                with t.query([[(ix, v) for v in vals]], flags=cubit.Q_ROWIDS | cubit.Q_VALUES, cols=[0],
+                             agg=cubit.AGG_SUM, agg_a=0) as r:
+                    ids, (v,) = r.fetch()
+                    assert np.array_equal(ids, want) and np.array_equal(v, pay[want]) and r.sum == int(pay[want].sum())
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+    th = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errors, errors
+    t.close()

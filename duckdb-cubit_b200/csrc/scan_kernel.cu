@@ -141,6 +141,7 @@ __device__ __forceinline__ long long gather_ld(const long long *p) {
 constexpr int kReqSlots = 4;       // look-back requests in flight per CTA (> emission deferral depth)
 constexpr int kDefer = 2;          // segments merged between a segment's merge and its emission
 constexpr int kWaitBatch = 4;      // ring stages consumed per mbarrier round trip
+constexpr int kDeltaStage = 32;    // delta words staged in shared memory per ring stage (the rest is read from L2)
 constexpr int kSlotRows = 32 * 64; // rows one warp compacts at a time (32 lanes × one 64-bit word)
 
 template <int WPT>
@@ -150,6 +151,7 @@ struct ScanSmem {
 	static constexpr int kStages = kScanRingBytes / kTileBytes;
 	alignas(128) uint64_t stage[kStages][kTileWords];
 	alignas(16) uint16_t compact[kConsumerWarps][kSlotRows + 8]; // per-warp staging of local row numbers
+	alignas(16) DeltaEnt dbuf[kStages][kDeltaStage];              // pending-delta words staged beside each segment
 	alignas(8) uint64_t full[kStages];
 	uint64_t empty[kStages];
 	uint64_t req_full[kReqSlots];  // consumers → prefix warp
@@ -159,6 +161,7 @@ struct ScanSmem {
 	uint32_t req_total[kReqSlots];
 	StageMeta meta[kStages];
 	uint32_t warp_tot[2][kConsumerWarps];
+	uint32_t poff[2 * kMaxStreams]; // producer: delta CSR offsets of the current segment (lo | hi)
 	BlockPartial red[kConsumerWarps];
 };
 
@@ -425,42 +428,82 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 	__syncthreads();
 
 	if (warp == kConsumerWarps) {
-		// ------------------------------------------------------------ producer warp (one lane)
-		if (lane != 0) {
-			return;
-		}
+		// ------------------------------------------------------------ producer warp
+		// Lane 0 walks the ring and issues the bulk copies.  With pending deltas the other lanes
+		// fetch the delta CSR offsets of the NEXT segment (its ticket is known one segment ahead)
+		// while lane 0 is busy, so those dependent loads never sit in front of a bulk copy.
 		uint32_t stage = 0, phase = 0;
-		uint32_t tile = atomicAdd(ticket, 1u);
+		uint32_t tile = 0;
+		if (lane == 0) {
+			tile = atomicAdd(ticket, 1u);
+		}
+		tile = __shfl_sync(0xffffffffu, tile, 0);
+		uint32_t dlo[2] = {0, 0}, dhi[2] = {0, 0}; // CSR offsets of streams lane and lane+32 for `tile`
+		auto load_offsets = [&](uint32_t tl) {
+#pragma unroll
+			for (int h = 0; h < 2; h++) {
+				const uint32_t s = (uint32_t)lane + 32u * h;
+				dlo[h] = dhi[h] = 0;
+				if (s < a.k && a.doff[s] && tl < a.n_seg) {
+					dlo[h] = __ldg(a.doff[s] + tl);
+					dhi[h] = __ldg(a.doff[s] + tl + 1);
+				}
+			}
+		};
+		if (HAS_DELTA) {
+			load_offsets(tile);
+		}
 		while (true) {
 			const bool valid = tile < a.n_seg;
 			uint32_t next = 0;
-			if (valid) {
+			if (valid && lane == 0) {
 				next = atomicAdd(ticket, 1u); // prefetched: consumed one segment later
 			}
-			for (uint32_t s = 0; s < a.k; s++) {
-				mbar_wait(&sm.empty[stage], phase ^ 1);
-				sm.meta[stage].tile = valid ? tile : kNoTile;
-				if (!valid) {
-					mbar_arrive(&sm.full[stage]); // end marker: k empty stages, so batched waits stay uniform
-				} else {
-					if (HAS_DELTA) {
-						uint32_t d0 = 0, d1 = 0;
-						if (a.doff[s]) {
-							d0 = __ldg(a.doff[s] + tile);
-							d1 = __ldg(a.doff[s] + tile + 1);
-						}
-						sm.meta[stage].d0 = d0;
-						sm.meta[stage].dcnt = d1 - d0;
-					}
-					mbar_arrive_expect_tx(&sm.full[stage], kTileBytes);
-					bulk_g2s(&sm.stage[stage][0], a.bv[s] + (size_t)tile * kTileWords, kTileBytes, &sm.full[stage]);
+			next = __shfl_sync(0xffffffffu, next, 0);
+			if (HAS_DELTA) {
+#pragma unroll
+				for (int h = 0; h < 2; h++) {
+					sm.poff[lane + 32 * h] = dlo[h];
+					sm.poff[64 + lane + 32 * h] = dhi[h];
 				}
-				stage++;
-				if (stage == kStages) {
-					stage = 0;
-					phase ^= 1;
+				__syncwarp();
+				if (valid) {
+					load_offsets(next); // in flight while lane 0 issues this segment's copies
 				}
 			}
+			if (lane == 0) {
+				for (uint32_t s = 0; s < a.k; s++) {
+					mbar_wait(&sm.empty[stage], phase ^ 1);
+					sm.meta[stage].tile = valid ? tile : kNoTile;
+					if (!valid) {
+						mbar_arrive(&sm.full[stage]); // end marker: k empty stages, so batched waits stay uniform
+					} else {
+						uint32_t dbytes = 0;
+						const DeltaEnt *dsrc = nullptr;
+						if (HAS_DELTA) {
+							const uint32_t d0 = sm.poff[s], d1 = sm.poff[64 + s];
+							sm.meta[stage].d0 = d0;
+							sm.meta[stage].dcnt = d1 - d0;
+							if (d1 > d0) { // stage the first kDeltaStage delta words next to the segment
+								dbytes = ((d1 - d0) < (uint32_t)kDeltaStage ? (d1 - d0) : (uint32_t)kDeltaStage) *
+								         (uint32_t)sizeof(DeltaEnt);
+								dsrc = a.dent[s] + d0;
+							}
+						}
+						mbar_arrive_expect_tx(&sm.full[stage], kTileBytes + dbytes);
+						bulk_g2s(&sm.stage[stage][0], a.bv[s] + (size_t)tile * kTileWords, kTileBytes, &sm.full[stage]);
+						if (dbytes) {
+							bulk_g2s(&sm.dbuf[stage][0], dsrc, dbytes, &sm.full[stage]);
+						}
+					}
+					stage++;
+					if (stage == kStages) {
+						stage = 0;
+						phase ^= 1;
+					}
+				}
+			}
+			__syncwarp();
 			if (!valid) {
 				return;
 			}
@@ -537,24 +580,30 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 				tile = sm.meta[stage].tile;
 			}
 			if (HAS_DELTA && tile != kNoTile) {
-				bool any = false;
+				// Every warp applies the delta words that fall into ITS span of the staged segment
+				// (XOR in shared memory, then the fold below picks them up): no block-wide barrier.
+				bool wrote = false;
 				for (uint32_t u = 0; u < nb; u++) {
 					const uint32_t st = (stage + u) % kStages;
 					const uint32_t dcnt = sm.meta[st].dcnt;
-					if (dcnt) { // uniform across the consumer warps
-						any = true;
-						const DeltaEnt *ent = a.dent[s + u] + sm.meta[st].d0;
-						for (uint32_t e = threadIdx.x; e < dcnt; e += kConsumerThreads) {
-							const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(ent + e));
-							const uint64_t mask = ((uint64_t)raw.w << 32) | raw.z;
-							sm.stage[st][raw.x] ^= mask; // words are unique per (stream, segment)
+					for (uint32_t e = lane; e < dcnt; e += 32) {
+						uint4 raw;
+						if (e < (uint32_t)kDeltaStage) {
+							raw = *reinterpret_cast<const uint4 *>(&sm.dbuf[st][e]);
+						} else {
+							raw = __ldg(reinterpret_cast<const uint4 *>(a.dent[s + u] + sm.meta[st].d0 + e));
+						}
+						const uint32_t rel = raw.x - (uint32_t)(warp * kSpanWords);
+						if (rel < (uint32_t)kSpanWords) { // words are unique per (stream, segment)
+							sm.stage[st][raw.x] ^= ((uint64_t)raw.w << 32) | raw.z;
+							wrote = true;
 						}
 					}
 				}
-				if (any) {
-					fence_proxy_async_smem();
-					consumer_bar_sync();
+				if (wrote) {
+					fence_proxy_async_smem(); // generic-proxy writes before the stage is refilled by the async proxy
 				}
+				__syncwarp();
 			}
 			if (tile != kNoTile) {
 #pragma unroll

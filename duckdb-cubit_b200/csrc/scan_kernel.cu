@@ -150,7 +150,7 @@ struct ScanSmem {
 	static constexpr int kTileBytes = kTileWords * 8;
 	static constexpr int kStages = kScanRingBytes / kTileBytes;
 	alignas(128) uint64_t stage[kStages][kTileWords];
-	alignas(16) uint16_t compact[kConsumerWarps][kSlotRows + 8]; // per-warp staging of local row numbers
+	alignas(16) uint16_t compact[kConsumerWarps][kSlotRows + 8 + 32]; // per-warp staging of local row numbers (+ dummy slots)
 	alignas(16) DeltaEnt dbuf[kStages][kDeltaStage];              // pending-delta words staged beside each segment
 	alignas(8) uint64_t full[kStages];
 	uint64_t empty[kStages];
@@ -309,20 +309,22 @@ __device__ __forceinline__ void write_out(const ScanArgs &a, const uint16_t *cbu
 	}
 }
 
-// lane-local compaction of one 64-bit word: its two halves are two independent ctz chains
-__device__ __forceinline__ void stage_word(uint16_t *cbuf, uint32_t p0, uint32_t wlo, uint32_t whi, uint32_t bit0) {
+// lane-local compaction of one 64-bit word: its two halves are two independent ctz chains.
+// Branch-free: an exhausted chain keeps "storing" into a per-lane dummy slot behind the
+// staging area, so the loop body is straight-line code (no divergence regions).
+__device__ __forceinline__ void stage_word(uint16_t *cbuf, uint32_t p0, uint32_t wlo, uint32_t whi, uint32_t bit0,
+                                           uint32_t dummy) {
 	uint32_t p1 = p0 + __popc(wlo);
 	uint32_t w0 = wlo, w1 = whi;
 	const uint32_t b1 = bit0 + 32u;
 	while (w0 | w1) {
-		if (w0) {
-			cbuf[p0++] = (uint16_t)(bit0 + (uint32_t)(__ffs(w0) - 1));
-			w0 &= w0 - 1;
-		}
-		if (w1) {
-			cbuf[p1++] = (uint16_t)(b1 + (uint32_t)(__ffs(w1) - 1));
-			w1 &= w1 - 1;
-		}
+		const uint32_t i0 = w0 ? p0 : dummy, i1 = w1 ? p1 : dummy;
+		cbuf[i0] = (uint16_t)(bit0 + (uint32_t)(__ffs(w0) - 1));
+		cbuf[i1] = (uint16_t)(b1 + (uint32_t)(__ffs(w1) - 1));
+		p0 += w0 != 0;
+		p1 += w1 != 0;
+		w0 &= w0 - 1; // 0 stays 0
+		w1 &= w1 - 1;
 	}
 }
 
@@ -359,6 +361,7 @@ __device__ __forceinline__ void emit_span(const ScanArgs &a, const uint64_t (&q)
 	if (span_total == 0) {
 		return;
 	}
+	const uint32_t dummy = (uint32_t)(kSlotRows + 8 + lane); // per-lane scratch slot behind the staging area
 	if (span_total <= (uint32_t)kSlotRows && WPT * kSlotRows <= 65536) {
 		// sparse / medium span: stage ALL slots at once (row numbers relative to the span fit
 		// 16 bits), then one write-out — one synchronisation round instead of one per slot
@@ -367,7 +370,7 @@ __device__ __forceinline__ void emit_span(const ScanArgs &a, const uint64_t (&q)
 #pragma unroll
 		for (int i = 0; i < WPT; i++) {
 			stage_word(cbuf, base + incl[i] - c[i], (uint32_t)q[i], (uint32_t)(q[i] >> 32),
-			           (uint32_t)(i * kSlotRows + lane * 64));
+			           (uint32_t)(i * kSlotRows + lane * 64), dummy);
 			base += slot_total[i];
 		}
 		__syncwarp();
@@ -382,7 +385,7 @@ __device__ __forceinline__ void emit_span(const ScanArgs &a, const uint64_t (&q)
 			continue;
 		}
 		const uint32_t pad = (uint32_t)pos0 & 1u;
-		stage_word(cbuf, pad + incl[i] - c[i], (uint32_t)q[i], (uint32_t)(q[i] >> 32), (uint32_t)lane * 64u);
+		stage_word(cbuf, pad + incl[i] - c[i], (uint32_t)q[i], (uint32_t)(q[i] >> 32), (uint32_t)lane * 64u, dummy);
 		__syncwarp();
 		write_out<NL, POS>(a, cbuf, pad, slot_total[i], pos0, span_row0 + (int64_t)i * kSlotRows, lane, sum_lo, sum_hi,
 		                   overflow);
@@ -796,7 +799,7 @@ template <int WPT, int NL, bool POS>
 __global__ void __launch_bounds__(kProbeBitsThreads) cubit_probe_bits_kernel(const __grid_constant__ ScanArgs a) {
 	constexpr int kTileWords = kProbeBitsThreads * WPT;
 	constexpr int kSpanWords = WPT * 32;
-	__shared__ __align__(16) uint16_t compact[kProbeBitsThreads / 32][kSlotRows + 8];
+	__shared__ __align__(16) uint16_t compact[kProbeBitsThreads / 32][kSlotRows + 8 + 32];
 	__shared__ uint32_t warp_tot[2][kProbeBitsThreads / 32];
 	__shared__ BlockPartial red[kProbeBitsThreads / 32];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

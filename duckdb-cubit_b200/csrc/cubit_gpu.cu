@@ -792,6 +792,9 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 		cap = std::min(cap, group_bound);
 	}
 	sa.k = k;
+	if (const char *dbg = getenv("CUBIT_SCAN_DEBUG")) {
+		sa.debug = (unsigned)atoi(dbg); // kernel timing experiments: skips parts of the kernel, results invalid
+	}
 	sa.n_seg = t->n_seg;
 	sa.row_base = t->row_base;
 

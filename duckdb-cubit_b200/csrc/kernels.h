@@ -62,6 +62,7 @@ struct ScanArgs {
 	int agg_ib;
 	BlockPartial *partials;             // [gridDim.x]
 	ResultHeader *hdr;
+	unsigned int debug;                 // timing experiments only (CUBIT_SCAN_DEBUG): results are WRONG when != 0
 };
 
 struct ProbeArgs {

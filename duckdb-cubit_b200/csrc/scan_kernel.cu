@@ -335,13 +335,18 @@ template <int WPT, int NL, bool POS>
 __device__ __forceinline__ void emit_span(const ScanArgs &a, const uint64_t (&q)[WPT], uint16_t *cbuf,
                                           unsigned long long wbase, int64_t span_row0, int lane,
                                           unsigned long long &sum_lo, long long &sum_hi, unsigned int &overflow) {
-	// WPT independent warp scans, interleaved (one scan's latency for all slots)
-	uint32_t c[WPT], incl[WPT];
+	uint32_t c[WPT], incl[WPT], lane_total = 0;
 #pragma unroll
 	for (int i = 0; i < WPT; i++) {
 		c[i] = __popcll(q[i]);
 		incl[i] = c[i];
+		lane_total += c[i];
 	}
+	const uint32_t span_total = __reduce_add_sync(0xffffffffu, lane_total); // redux.sync: one instruction
+	if (span_total == 0) {
+		return; // sparse selections: most spans are empty
+	}
+	// WPT independent warp scans, interleaved (one scan's latency for all slots)
 #pragma unroll
 	for (int d = 1; d < 32; d <<= 1) {
 #pragma unroll
@@ -352,14 +357,10 @@ __device__ __forceinline__ void emit_span(const ScanArgs &a, const uint64_t (&q)
 			}
 		}
 	}
-	uint32_t slot_total[WPT], span_total = 0;
+	uint32_t slot_total[WPT];
 #pragma unroll
 	for (int i = 0; i < WPT; i++) {
 		slot_total[i] = __shfl_sync(0xffffffffu, incl[i], 31);
-		span_total += slot_total[i];
-	}
-	if (span_total == 0) {
-		return;
 	}
 	const uint32_t dummy = (uint32_t)(kSlotRows + 8 + lane); // per-lane scratch slot behind the staging area
 	if (span_total <= (uint32_t)kSlotRows && WPT * kSlotRows <= 65536) {
@@ -544,6 +545,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 	}
 
 	// ---------------------------------------------------------------- consumer warps
+	// timing experiments only (see kernels.h): 2 = skip emission, 7 = no look-back traffic at all; anything
+	// else could unbalance the request/response mbarriers, so it is ignored
+	const unsigned dbg = (a.debug == 2u || a.debug == 7u) ? a.debug : 0u;
 	uint32_t stage = 0, phase = 0;
 	unsigned long long blk_count = 0; // meaningful in thread 0
 	unsigned long long sum_lo = 0;
@@ -672,7 +676,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 			}
 			if (threadIdx.x == 0) {
 				blk_count += tile_total;
-				if (need_pos) {
+				if (need_pos && !(dbg & 4u)) {
 					// publish this segment's aggregate NOW and hand the look-back to the prefix warp
 					st_relaxed_u64(&status[tile], kFlagAgg | (unsigned long long)tile_total);
 					sm.req_tile[it % kReqSlots] = tile;
@@ -680,16 +684,17 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 					mbar_arrive(&sm.req_full[it % kReqSlots]);
 				}
 			}
-		} else if (need_pos && threadIdx.x == 0) {
-			sm.req_tile[it % kReqSlots] = kNoTile; // tell the prefix warp to exit
-			mbar_arrive(&sm.req_full[it % kReqSlots]);
+		} else if (need_pos && threadIdx.x == 0) { // (debug & 4: the prefix warp still gets its exit request)
+			const uint32_t eslot = (dbg & 4u) ? 0u : it % kReqSlots; // no requests were posted: it still waits on slot 0
+			sm.req_tile[eslot] = kNoTile; // tell the prefix warp to exit
+			mbar_arrive(&sm.req_full[eslot]);
 		}
 
 		// ---- emit the oldest pending segment (all of them once the input is exhausted)
 		for (int round = 0; round < (finished ? kDefer : 1); round++) {
 			if (have_p[kDefer - 1] && need_emit) {
 				unsigned long long excl = 0;
-				if (need_pos) {
+				if (need_pos && !(dbg & 1u)) {
 					const uint32_t slot = pit[kDefer - 1] % kReqSlots, par = (pit[kDefer - 1] / kReqSlots) & 1;
 					if (lane == 0) {
 						mbar_wait(&sm.resp_full[slot], par);
@@ -697,7 +702,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 					__syncwarp();
 					excl = sm.resp_excl[slot];
 				}
-				if (ptotal[kDefer - 1] > 0) {
+				if (ptotal[kDefer - 1] > 0 && !(dbg & 2u)) {
 					const int64_t span_row0 =
 					    a.row_base + ((int64_t)ptile[kDefer - 1] * kTileWords + (int64_t)warp * kSpanWords) * 64;
 					if (need_pos) {

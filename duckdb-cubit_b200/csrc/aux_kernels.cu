@@ -151,23 +151,13 @@ __global__ void __launch_bounds__(kProbeThreads) cubit_probe_kernel(const __grid
 			add128(tlo, thi, red[w].sum_lo, red[w].sum_hi);
 			tov |= red[w].pad;
 		}
-		volatile BlockPartial *dst = a.partials + blockIdx.x;
-		dst->sum_lo = tlo;
-		dst->sum_hi = thi;
-		dst->pad = tov;
-		__threadfence();
-		if (atomicAdd(a.done, 1u) == gridDim.x - 1) {
-			__threadfence();
-			unsigned long long flo = 0, fov = 0;
-			long long fhi = 0;
-			for (unsigned b = 0; b < gridDim.x; b++) {
-				const volatile BlockPartial *p = a.partials + b;
-				add128(flo, fhi, p->sum_lo, p->sum_hi);
-				fov |= p->pad;
-			}
-			a.hdr->sum_lo = flo;
-			a.hdr->sum_hi = fhi;
-			a.hdr->overflow = (unsigned int)fov;
+		if (tlo | (unsigned long long)thi) { // exact 128-bit accumulate (carry from the returned old value)
+			const unsigned long long old = atomicAdd(&a.hdr->sum_lo, tlo);
+			const long long carry = (old + tlo) < old ? 1 : 0;
+			atomicAdd(reinterpret_cast<unsigned long long *>(&a.hdr->sum_hi), (unsigned long long)(thi + carry));
+		}
+		if (tov) {
+			atomicOr(&a.hdr->overflow, 1u);
 		}
 	}
 }
@@ -242,12 +232,15 @@ cudaError_t launch_index_build(const void *col, uint32_t elem_bytes, uint64_t n_
 	// values per pass bounded by shared memory (≤ 200 KiB tile)
 	const uint32_t max_v = (200u * 1024u) / (kBuildSlots * 4u);
 	int launches = 0;
-	static bool configured = false;
-	if (!configured) {
+	static bool configured[64] = {}; // function attributes are per device
+	int dev = 0;
+	cudaGetDevice(&dev);
+	dev &= 63;
+	if (!configured[dev]) {
 		cudaFuncSetAttribute(cubit_index_build_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 		cudaFuncSetAttribute(cubit_index_build_kernel<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		                     200 * 1024);
-		configured = true;
+		configured[dev] = true;
 	}
 	const uint64_t n_tiles = (n_rows + kBuildRows - 1) / kBuildRows;
 	for (uint32_t v_lo = 0; v_lo < cardinality; v_lo += max_v) {

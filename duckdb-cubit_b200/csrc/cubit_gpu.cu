@@ -964,9 +964,8 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 		}
 	}
 
-	// zero hdr + both control blocks (+ probe done counter lives at the end)
+	// zero hdr + both control blocks (ticket counters and per-segment status words)
 	Q_TRY(cudaMemsetAsync(r->d_block, 0, hdr_bytes + 2 * ctrl_pad, st));
-	Q_TRY(cudaMemsetAsync(probe_done, 0, 64, st));
 
 	sa.partials = partials;
 	sa.hdr = r->d_hdr;
@@ -1015,6 +1014,7 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 			sd.ids_cap = cap;
 			sd.partials = partials;
 			sd.hdr = r->d_hdr;
+			sd.skip_count = 1; // K1 already counted the selection
 			Q_TRY(launch_scan(sd, t->seg_words, false, t->sm_count, st, nullptr));
 			n_launch++;
 		}

@@ -62,6 +62,7 @@ struct ScanArgs {
 	int agg_ib;
 	BlockPartial *partials;             // [gridDim.x]
 	ResultHeader *hdr;
+	int skip_count;                     // 1: do not add this launch's popcounts to hdr->count (decode pass of UNFUSED)
 	unsigned int debug;                 // timing experiments only (CUBIT_SCAN_DEBUG): results are WRONG when != 0
 };
 

@@ -412,7 +412,6 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 	const int warp = threadIdx.x >> 5;
 	const int lane = threadIdx.x & 31;
 	unsigned int *ticket = reinterpret_cast<unsigned int *>(a.ctrl);
-	unsigned int *done_ctr = ticket + 1;
 	unsigned long long *status = a.ctrl + 1;
 	const bool need_pos =
 	    (a.ids_out != nullptr) || (NL > 0 && (a.lout[0] != nullptr || (NL > 1 && a.lout[NL - 1] != nullptr)));
@@ -745,7 +744,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 		it++;
 	}
 
-	// ---- block reduction of count / 128-bit sum, then last-block finalisation
+	// ---- block reduction of count / 128-bit sum, then one exact atomic accumulate per CTA
+	// (hdr is zeroed before the launch; no serial last-block pass over per-CTA partials)
 #pragma unroll
 	for (int d = 16; d > 0; d >>= 1) {
 		const unsigned long long olo = __shfl_xor_sync(0xffffffffu, sum_lo, d);
@@ -767,27 +767,17 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 			add128(lo, hi, sm.red[w].sum_lo, sm.red[w].sum_hi);
 			ovf |= sm.red[w].pad;
 		}
-		volatile BlockPartial *dst = a.partials + blockIdx.x;
-		dst->count = blk_count;
-		dst->sum_lo = lo;
-		dst->sum_hi = hi;
-		dst->pad = ovf;
-		__threadfence();
-		const unsigned int prev = atomicAdd(done_ctr, 1u);
-		if (prev == gridDim.x - 1) {
-			__threadfence();
-			unsigned long long cnt = 0, tlo = 0, tovf = 0;
-			long long thi = 0;
-			for (unsigned b = 0; b < gridDim.x; b++) {
-				const volatile BlockPartial *p = a.partials + b;
-				cnt += p->count;
-				add128(tlo, thi, p->sum_lo, p->sum_hi);
-				tovf |= p->pad;
-			}
-			a.hdr->count = cnt;
-			a.hdr->sum_lo = tlo;
-			a.hdr->sum_hi = thi;
-			a.hdr->overflow = (unsigned int)tovf;
+		if (blk_count && !a.skip_count) {
+			atomicAdd(&a.hdr->count, blk_count);
+		}
+		if (lo | (unsigned long long)hi) {
+			// the carry out of the low limb is recovered from the value the atomic returns
+			const unsigned long long old = atomicAdd(&a.hdr->sum_lo, lo);
+			const long long carry = (old + lo) < old ? 1 : 0;
+			atomicAdd(reinterpret_cast<unsigned long long *>(&a.hdr->sum_hi), (unsigned long long)(hi + carry));
+		}
+		if (ovf) {
+			atomicOr(&a.hdr->overflow, 1u);
 		}
 	}
 }
@@ -875,15 +865,14 @@ __global__ void __launch_bounds__(kProbeBitsThreads) cubit_probe_bits_kernel(con
 template <int WPT, int NL, bool POS>
 static cudaError_t launch_probe_bits_t(const ScanArgs &args, int sm_count, cudaStream_t stream) {
 	auto kern = cubit_probe_bits_kernel<WPT, NL, POS>;
-	static int blocks_per_sm = 0;
+	static int blocks_per_sm = 0; // same for every B200
 	if (blocks_per_sm == 0) {
-		cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kProbeBitsThreads, 0);
+		int b = 0;
+		cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kProbeBitsThreads, 0);
 		if (e != cudaSuccess) {
 			return e;
 		}
-		if (blocks_per_sm < 1) {
-			blocks_per_sm = 1;
-		}
+		blocks_per_sm = b < 1 ? 1 : b;
 	}
 	long long grid = (long long)sm_count * blocks_per_sm * 4; // short-lived CTAs, dynamic balance by the HW scheduler
 	if (grid > (long long)args.n_seg) {
@@ -928,28 +917,24 @@ template <int WPT, bool HAS_DELTA, int NL>
 static cudaError_t launch_scan_t(const ScanArgs &args, int sm_count, cudaStream_t stream, int *grid_out) {
 	auto kern = cubit_scan_kernel<WPT, HAS_DELTA, NL>;
 	const size_t smem = sizeof(ScanSmem<WPT>) + 128;
-	static bool configured = false; // per template instance
-	if (!configured) {
+	// function attributes are per device: configure once per (template instance, device)
+	static int blocks_per_sm_dev[64] = {};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	dev &= 63;
+	if (blocks_per_sm_dev[dev] == 0) {
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) {
 			return e;
 		}
-		configured = true;
-	}
-	static int blocks_per_sm = 0;
-	if (blocks_per_sm == 0) {
-		cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kScanThreads, smem);
+		int b = 0;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kScanThreads, smem);
 		if (e != cudaSuccess) {
 			return e;
 		}
-		if (blocks_per_sm < 1) {
-			blocks_per_sm = 1;
-		}
-		if (blocks_per_sm > 2) {
-			blocks_per_sm = 2;
-		}
+		blocks_per_sm_dev[dev] = b < 1 ? 1 : (b > 2 ? 2 : b);
 	}
-	long long grid = (long long)sm_count * blocks_per_sm; // persistent CTAs, all co-resident
+	long long grid = (long long)sm_count * blocks_per_sm_dev[dev]; // persistent CTAs, all co-resident
 	if (grid > (long long)args.n_seg) {
 		grid = args.n_seg;
 	}

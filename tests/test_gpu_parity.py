@@ -383,3 +383,30 @@ def test_concurrent_queries_on_one_table(cubit):
     [x.join() for x in th]
     assert not errors, errors
     t.close()
+
+
+def test_maximum_stream_count(cubit):
+    """CUBIT_MAX_STREAMS = 64 bitvectors in one query (4 groups of 16); 65 is rejected"""
+    n = 700_001
+    rng = np.random.default_rng(9)
+    col = rng.integers(0, 80, n).astype(np.int32)
+    bv = oracle.build_index(col, 0, 80)
+    t = cubit.CubitTable(n, seg_bits=32768)
+    t.upload_column(1, col)
+    ix = t.create_index(80)
+    t.build_index(ix, 1, 0)
+    d = rng.integers(0, n, 3000)
+    t.set_delta(ix, 70, d)          # stream 62: exercises the second half of the delta offset table
+    groups = [list(range(g * 16, g * 16 + 16)) for g in range(4)]
+    groups[1] = list(range(0, 16))  # overlap so the AND is not empty: (0..15) AND (0..15) AND ...
+    groups[2] = list(range(8, 24))
+    groups[3] = [v for v in range(8, 16)] + [70, 71, 72, 73, 74, 75, 76, 77]
+    groups[3], groups[0] = groups[0], groups[3]
+    dl = [[oracle.delta_from_rows(d, n) if v == 70 else None for v in g] for g in groups]
+    want = oracle.decode(oracle.merge([[bv[v] for v in g] for g in groups], dl))
+    assert len(want) > 0
+    with t.query([[(ix, v) for v in g] for g in groups], flags=cubit.Q_ROWIDS) as r:
+        assert r.info.n_streams == 64 and np.array_equal(r.fetch()[0], want)
+    with pytest.raises(cubit.CubitError):
+        t.query([[(ix, v) for v in range(65)]])
+    t.close()

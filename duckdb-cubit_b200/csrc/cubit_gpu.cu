@@ -662,6 +662,23 @@ extern "C" int cubit_gpu_drop_column(cubit_gpu_table *t, int32_t col_id) {
 }
 
 // -------------------------------------------------------------------- query
+// which scan kernel: 1 = warp-specialised (fold / emit warps, scan_kernel_ws.cu), 0 = scan_kernel.cu
+static int scan_variant() {
+	static int v = -1;
+	if (v < 0) {
+		const char *e = getenv("CUBIT_SCAN_WS");
+		v = e ? atoi(e) : 0;
+	}
+	return v;
+}
+
+static cudaError_t run_scan(const ScanArgs &sa, uint32_t seg_words, bool has_delta, int sm_count, cudaStream_t st) {
+	if (scan_variant() == 1) {
+		return launch_scan_ws(sa, seg_words, has_delta, sm_count, st);
+	}
+	return launch_scan(sa, seg_words, has_delta, sm_count, st, nullptr);
+}
+
 static void release_result(cubit_gpu_result *r) {
 	cudaStream_t s = r->stream;
 	if (r->d_block) {
@@ -990,7 +1007,7 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 			sa.agg_ia = agg_ia;
 			sa.agg_ib = agg_ib;
 		}
-		Q_TRY(launch_scan(sa, t->seg_words, has_delta, t->sm_count, st, nullptr));
+		Q_TRY(run_scan(sa, t->seg_words, has_delta, t->sm_count, st));
 		n_launch++;
 		r->info.fused = 1;
 	} else {
@@ -999,7 +1016,7 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 		sa.ctrl = ctrl_a;
 		sa.q_out = qbuf;
 		sa.ids_out = nullptr;
-		Q_TRY(launch_scan(sa, t->seg_words, has_delta, t->sm_count, st, nullptr));
+		Q_TRY(run_scan(sa, t->seg_words, has_delta, t->sm_count, st));
 		n_launch++;
 		if (need_ids_buf) {
 			ScanArgs sd;
@@ -1015,7 +1032,7 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 			sd.partials = partials;
 			sd.hdr = r->d_hdr;
 			sd.skip_count = 1; // K1 already counted the selection
-			Q_TRY(launch_scan(sd, t->seg_words, false, t->sm_count, st, nullptr));
+			Q_TRY(run_scan(sd, t->seg_words, false, t->sm_count, st));
 			n_launch++;
 		}
 		r->info.fused = 0;

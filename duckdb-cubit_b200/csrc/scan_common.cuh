@@ -1,0 +1,344 @@
+// scan_common.cuh — device helpers shared by the scan kernels (scan_kernel.cu, scan_kernel_ws.cu):
+// PTX glue (mbarrier, bulk async copy, relaxed status words), 128-bit accumulation, the prefix
+// warp's chain-free look-back, and the staged, position-ordered emission (stage_word / write_out /
+// emit_span).  See scan_kernel.cu for the algorithm description and the reference citations.
+#pragma once
+#include "kernels.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cubit {
+
+
+// ------------------------------------------------------------------ PTX glue
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+	             : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+	uint32_t addr = smem_u32(bar);
+	uint32_t done;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\t"
+		             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		             "selp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(done)
+		             : "r"(addr), "r"(parity)
+		             : "memory");
+	} while (!done);
+}
+// 1-D bulk async copy global → shared, completion on an mbarrier (TMA engine; SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+	                 smem_u32(smem_dst)),
+	             "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+	             : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync() {
+	asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+	unsigned long long v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// look-back status word: [63:62] flag (0 = not published yet), [61:0] popcount of the segment
+constexpr unsigned long long kFlagAgg = 1ull << 62;
+constexpr unsigned long long kValMask = (1ull << 62) - 1;
+constexpr uint32_t kNoTile = 0xffffffffu;
+
+struct StageMeta {
+	uint32_t tile; // kNoTile = no more work
+	uint32_t d0;   // first delta entry of (stream, segment)
+	uint32_t dcnt; // number of delta entries
+	uint32_t pad;
+};
+
+// 128-bit signed accumulate of an int64 (AddToHugeint::AddValue, sum_helpers.hpp:92-113)
+__device__ __forceinline__ void add128(unsigned long long &lo, long long &hi, long long v) {
+	unsigned long long uv = (unsigned long long)v;
+	lo += uv;
+	hi += (long long)(lo < uv) + (v >> 63);
+}
+__device__ __forceinline__ void add128(unsigned long long &lo, long long &hi, unsigned long long lo2, long long hi2) {
+	lo += lo2;
+	hi += hi2 + (long long)(lo < lo2);
+}
+
+// gather load used by the probe paths (experiment knob: -DCUBIT_GATHER_LD=n)
+#ifndef CUBIT_GATHER_LD
+#define CUBIT_GATHER_LD 0
+#endif
+__device__ __forceinline__ long long gather_ld(const long long *p) {
+#if CUBIT_GATHER_LD == 0
+	return __ldg(p);
+#elif CUBIT_GATHER_LD == 1
+	return __ldcg(p);
+#elif CUBIT_GATHER_LD == 2
+	return __ldcs(p);
+#elif CUBIT_GATHER_LD == 3
+	long long v;
+	asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
+	return v;
+#else
+	return *p;
+#endif
+}
+
+constexpr int kReqSlots = 4;       // look-back requests in flight per CTA (> emission deferral depth)
+constexpr int kDefer = 2;          // segments merged between a segment's merge and its emission
+constexpr int kWaitBatch = 4;      // ring stages consumed per mbarrier round trip
+constexpr int kDeltaStage = 32;    // delta words staged in shared memory per ring stage (the rest is read from L2)
+constexpr int kSlotRows = 32 * 64; // rows one warp compacts at a time (32 lanes × one 64-bit word)
+
+constexpr int kLookSlots = 16; // status words per prefix-warp lane per window → 512 segments per window
+
+// ---- the prefix warp's look-back, off the consumers' path.
+// status[t] = kFlagAgg | popcount(segment t), published once by the CTA that merged t.
+// The warp remembers the last segment this CTA handled (t0) and the inclusive prefix through
+// it (s0); the exclusive prefix of the next one is s0 + Σ status(t0+1 .. t-1).  It depends
+// only on those segments having been MERGED (inherent) — never on another CTA's look-back,
+// so there are no prefix chains, and the usual gap (≈ number of resident CTAs) is one window.
+__device__ __forceinline__ unsigned long long sum_aggregates(const unsigned long long *status, int64_t lo, int64_t hi,
+                                                             int lane) {
+	unsigned long long acc = 0; // per-lane partial
+	for (int64_t w0 = lo; w0 < hi; w0 += kLookSlots * 32) {
+		unsigned pending = 0; // bit j: slot j of this lane still unpublished
+#pragma unroll
+		for (int j = 0; j < kLookSlots; j++) {
+			if (w0 + j * 32 + lane < hi) {
+				pending |= 1u << j;
+			}
+		}
+		while (__any_sync(0xffffffffu, pending != 0)) {
+			unsigned long long sv[kLookSlots];
+#pragma unroll
+			for (int j = 0; j < kLookSlots; j++) {
+				sv[j] = (pending >> j) & 1u ? ld_relaxed_u64(&status[w0 + j * 32 + lane]) : 0ull;
+			}
+#pragma unroll
+			for (int j = 0; j < kLookSlots; j++) {
+				if (sv[j] >> 62) {
+					acc += sv[j] & kValMask;
+					pending &= ~(1u << j);
+				}
+			}
+			if (__any_sync(0xffffffffu, pending != 0)) {
+				__nanosleep(64); // some predecessor is still being merged: re-read only the holes
+			}
+		}
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		acc += __shfl_xor_sync(0xffffffffu, acc, d);
+	}
+	return acc;
+}
+
+// one selected row: store its id / gathered values at output position `pos`, accumulate
+template <int NL, bool POS>
+__device__ __forceinline__ void consume_row(const ScanArgs &a, unsigned long long pos, int64_t rid,
+                                            const long long (&v)[NL > 0 ? NL : 1], unsigned long long &sum_lo,
+                                            long long &sum_hi, unsigned int &overflow) {
+	if (POS) {
+		if (a.ids_out) {
+			__stcs(a.ids_out + pos, (long long)rid);
+		}
+#pragma unroll
+		for (int c = 0; c < NL; c++) {
+			if (a.lout[c]) {
+				__stcs(a.lout[c] + pos, v[c]);
+			}
+		}
+	}
+	if (NL > 0) {
+		const long long x = (NL > 1 && a.agg_ia == 1) ? v[NL - 1] : v[0];
+		if (a.agg_kind == 1) {
+			add128(sum_lo, sum_hi, x);
+		} else if (a.agg_kind == 2) {
+			const long long y = (NL > 1 && a.agg_ib == 1) ? v[NL - 1] : v[0];
+			const long long pr = x * y;
+			if (__mul64hi(x, y) != (pr >> 63)) {
+				overflow = 1;
+			}
+			add128(sum_lo, sum_hi, pr);
+		}
+	}
+}
+
+// Position-ordered write-out of `count` staged rows (16-bit row numbers relative to
+// row_origin, staged at cbuf[pad ..), pad = first output position & 1).  Per iteration the
+// warp writes 128 consecutive results as two fully contiguous 512-byte stores (lane l:
+// pairs l and l+32), gathers the fused-probe columns for them first (independent loads in
+// flight) and accumulates the aggregates.
+template <int NL, bool POS>
+__device__ __forceinline__ void write_out(const ScanArgs &a, const uint16_t *cbuf, uint32_t pad, uint32_t count,
+                                          unsigned long long pos0, int64_t row_origin, int lane,
+                                          unsigned long long &sum_lo, long long &sum_hi, unsigned int &overflow) {
+	const int64_t local0 = row_origin - a.row_base;
+	const unsigned long long obase = pos0 - pad; // output position of staging index 0 (even)
+	const uint32_t end = pad + count;
+	const uint32_t *cb32 = reinterpret_cast<const uint32_t *>(cbuf);
+	for (uint32_t g0 = 0; g0 * 2 < end; g0 += 64) {
+		uint32_t r[2][2];
+		bool ok[2][2];
+		long long v[2][2][NL > 0 ? NL : 1];
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const uint32_t g = g0 + h * 32 + lane; // pair index
+			const uint32_t packed = g * 2 < end ? cb32[g] : 0u;
+			r[h][0] = packed & 0xffffu;
+			r[h][1] = packed >> 16;
+			ok[h][0] = g * 2 >= pad && g * 2 < end;
+			ok[h][1] = g * 2 + 1 < end;
+			if (NL > 0) {
+#pragma unroll
+				for (int e = 0; e < 2; e++) {
+					if (ok[h][e]) {
+#pragma unroll
+						for (int cc = 0; cc < NL; cc++) {
+							v[h][e][cc] = gather_ld(a.lcol[cc] + (local0 + r[h][e]));
+						}
+					}
+				}
+			}
+		}
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const uint32_t g = g0 + h * 32 + lane;
+			if (POS && ok[h][0] && ok[h][1]) {
+				if (a.ids_out) {
+					__stcs(reinterpret_cast<longlong2 *>(a.ids_out + obase + g * 2),
+					       make_longlong2(row_origin + r[h][0], row_origin + r[h][1]));
+				}
+#pragma unroll
+				for (int cc = 0; cc < NL; cc++) {
+					if (a.lout[cc]) {
+						__stcs(reinterpret_cast<longlong2 *>(a.lout[cc] + obase + g * 2),
+						       make_longlong2(v[h][0][cc], v[h][1][cc]));
+					}
+				}
+				if (NL > 0) {
+					consume_row<NL, false>(a, 0, 0, v[h][0], sum_lo, sum_hi, overflow);
+					consume_row<NL, false>(a, 0, 0, v[h][1], sum_lo, sum_hi, overflow);
+				}
+			} else {
+#pragma unroll
+				for (int e = 0; e < 2; e++) {
+					if (ok[h][e]) {
+						consume_row<NL, POS>(a, obase + g * 2 + e, row_origin + r[h][e], v[h][e], sum_lo, sum_hi,
+						                     overflow);
+					}
+				}
+			}
+		}
+	}
+}
+
+// lane-local compaction of one 64-bit word: its two halves are two independent ctz chains.
+// Branch-free: an exhausted chain keeps "storing" into a per-lane dummy slot behind the
+// staging area, so the loop body is straight-line code (no divergence regions).
+__device__ __forceinline__ void stage_word(uint16_t *cbuf, uint32_t p0, uint32_t wlo, uint32_t whi, uint32_t bit0,
+                                           uint32_t dummy) {
+	uint32_t p1 = p0 + __popc(wlo);
+	uint32_t w0 = wlo, w1 = whi;
+	const uint32_t b1 = bit0 + 32u;
+	while (w0 | w1) {
+		const uint32_t i0 = w0 ? p0 : dummy, i1 = w1 ? p1 : dummy;
+		cbuf[i0] = (uint16_t)(bit0 + (uint32_t)(__ffs(w0) - 1));
+		cbuf[i1] = (uint16_t)(b1 + (uint32_t)(__ffs(w1) - 1));
+		p0 += w0 != 0;
+		p1 += w1 != 0;
+		w0 &= w0 - 1; // 0 stays 0
+		w1 &= w1 - 1;
+	}
+}
+
+// ---- emission of one warp's span of a merged segment.
+// q[i] of lane l is word (i*32 + l) of the span, so slot i = 2048 consecutive rows and the
+// output order is (slot, lane, bit).
+template <int WPT, int NL, bool POS>
+__device__ __forceinline__ void emit_span(const ScanArgs &a, const uint64_t (&q)[WPT], uint16_t *cbuf,
+                                          unsigned long long wbase, int64_t span_row0, int lane,
+                                          unsigned long long &sum_lo, long long &sum_hi, unsigned int &overflow) {
+	uint32_t c[WPT], incl[WPT], lane_total = 0;
+#pragma unroll
+	for (int i = 0; i < WPT; i++) {
+		c[i] = __popcll(q[i]);
+		incl[i] = c[i];
+		lane_total += c[i];
+	}
+	const uint32_t span_total = __reduce_add_sync(0xffffffffu, lane_total); // redux.sync: one instruction
+	if (span_total == 0) {
+		return; // sparse selections: most spans are empty
+	}
+	// WPT independent warp scans, interleaved (one scan's latency for all slots)
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+		for (int i = 0; i < WPT; i++) {
+			const uint32_t n = __shfl_up_sync(0xffffffffu, incl[i], d);
+			if (lane >= d) {
+				incl[i] += n;
+			}
+		}
+	}
+	uint32_t slot_total[WPT];
+#pragma unroll
+	for (int i = 0; i < WPT; i++) {
+		slot_total[i] = __shfl_sync(0xffffffffu, incl[i], 31);
+	}
+	const uint32_t dummy = (uint32_t)(kSlotRows + 8 + lane); // per-lane scratch slot behind the staging area
+	if (span_total <= (uint32_t)kSlotRows && WPT * kSlotRows <= 65536) {
+		// sparse / medium span: stage ALL slots at once (row numbers relative to the span fit
+		// 16 bits), then one write-out — one synchronisation round instead of one per slot
+		const uint32_t pad = (uint32_t)wbase & 1u;
+		uint32_t base = pad;
+#pragma unroll
+		for (int i = 0; i < WPT; i++) {
+			stage_word(cbuf, base + incl[i] - c[i], (uint32_t)q[i], (uint32_t)(q[i] >> 32),
+			           (uint32_t)(i * kSlotRows + lane * 64), dummy);
+			base += slot_total[i];
+		}
+		__syncwarp();
+		write_out<NL, POS>(a, cbuf, pad, span_total, wbase, span_row0, lane, sum_lo, sum_hi, overflow);
+		__syncwarp();
+		return;
+	}
+	unsigned long long pos0 = wbase; // output position of the slot's first selected row
+#pragma unroll
+	for (int i = 0; i < WPT; i++) {
+		if (slot_total[i] == 0) {
+			continue;
+		}
+		const uint32_t pad = (uint32_t)pos0 & 1u;
+		stage_word(cbuf, pad + incl[i] - c[i], (uint32_t)q[i], (uint32_t)(q[i] >> 32), (uint32_t)lane * 64u, dummy);
+		__syncwarp();
+		write_out<NL, POS>(a, cbuf, pad, slot_total[i], pos0, span_row0 + (int64_t)i * kSlotRows, lane, sum_lo, sum_hi,
+		                   overflow);
+		__syncwarp();
+		pos0 += slot_total[i];
+	}
+}
+
+// WPT: 64-bit words of Q each consumer thread holds → segment = 256*WPT words
+//      (WPT 2/4/8 ↔ 32768/65536/131072 rows per segment).
+// NL : distinct int64 columns gathered at every selected row (fused probe).
+} // namespace cubit

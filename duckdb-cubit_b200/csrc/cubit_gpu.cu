@@ -662,20 +662,7 @@ extern "C" int cubit_gpu_drop_column(cubit_gpu_table *t, int32_t col_id) {
 }
 
 // -------------------------------------------------------------------- query
-// which scan kernel: 1 = warp-specialised (fold / emit warps, scan_kernel_ws.cu), 0 = scan_kernel.cu
-static int scan_variant() {
-	static int v = -1;
-	if (v < 0) {
-		const char *e = getenv("CUBIT_SCAN_WS");
-		v = e ? atoi(e) : 0;
-	}
-	return v;
-}
-
 static cudaError_t run_scan(const ScanArgs &sa, uint32_t seg_words, bool has_delta, int sm_count, cudaStream_t st) {
-	if (scan_variant() == 1) {
-		return launch_scan_ws(sa, seg_words, has_delta, sm_count, st);
-	}
 	return launch_scan(sa, seg_words, has_delta, sm_count, st, nullptr);
 }
 

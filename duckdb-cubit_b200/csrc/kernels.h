@@ -88,8 +88,6 @@ struct ProbeArgs {
 cudaError_t launch_scan(const ScanArgs &args, uint32_t seg_words, bool has_delta, int sm_count, cudaStream_t stream,
                         int *grid_out);
 int scan_max_grid(uint32_t seg_words, int sm_count);
-// warp-specialised variant (scan_kernel_ws.cu): fold warps and emit warps overlap inside one CTA per SM
-cudaError_t launch_scan_ws(const ScanArgs &args, uint32_t seg_words, bool has_delta, int sm_count, cudaStream_t stream);
 // Bit-driven probe: re-decodes the merged bitvector args.q_out (input here) with the
 // per-segment prefixes args.tile_excl and gathers / sums the fused-probe columns at full
 // occupancy.  Sums are ADDED to args.hdr (which the scan kernel has already finalised).

@@ -469,15 +469,32 @@ __global__ void __launch_bounds__(kProbeBitsThreads) cubit_probe_bits_kernel(con
 	long long sum_hi = 0;
 	unsigned int overflow = 0;
 	uint32_t it = 0;
+	// software pipeline: the next segment's words are in flight while this one is decoded
+	uint64_t qn[WPT];
+	unsigned long long excl_n = 0;
+	auto prefetch = [&](uint32_t tl) {
+		if (tl < a.n_seg) {
+			const uint64_t *src = a.q_out + (size_t)tl * kTileWords + warp * kSpanWords;
+#pragma unroll
+			for (int i = 0; i < WPT; i++) {
+				qn[i] = __ldg(src + i * 32 + lane);
+			}
+			if (POS) {
+				excl_n = __ldg(a.tile_excl + tl);
+			}
+		}
+	};
+	prefetch(blockIdx.x);
 	for (uint32_t tile = blockIdx.x; tile < a.n_seg; tile += gridDim.x, it++) {
 		uint64_t q[WPT];
-		const uint64_t *src = a.q_out + (size_t)tile * kTileWords + warp * kSpanWords;
 		uint32_t cnt = 0;
 #pragma unroll
 		for (int i = 0; i < WPT; i++) {
-			q[i] = __ldg(src + i * 32 + lane);
+			q[i] = qn[i];
 			cnt += __popcll(q[i]);
 		}
+		const unsigned long long tile_excl = excl_n;
+		prefetch(tile + gridDim.x);
 		unsigned long long wbase = 0;
 		if (POS) {
 			cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -490,7 +507,7 @@ __global__ void __launch_bounds__(kProbeBitsThreads) cubit_probe_bits_kernel(con
 			for (int w = 0; w < kProbeBitsThreads / 32; w++) {
 				warp_excl += (w < warp) ? warp_tot[it & 1][w] : 0u;
 			}
-			wbase = a.tile_excl[tile] + warp_excl;
+			wbase = tile_excl + warp_excl;
 		}
 		const int64_t span_row0 = a.row_base + ((int64_t)tile * kTileWords + (int64_t)warp * kSpanWords) * 64;
 		emit_span<WPT, NL, POS>(a, q, compact[warp], wbase, span_row0, lane, sum_lo, sum_hi, overflow);
@@ -541,7 +558,7 @@ static cudaError_t launch_probe_bits_t(const ScanArgs &args, int sm_count, cudaS
 		}
 		blocks_per_sm = b < 1 ? 1 : b;
 	}
-	long long grid = (long long)sm_count * blocks_per_sm * 4; // short-lived CTAs, dynamic balance by the HW scheduler
+	long long grid = (long long)sm_count * blocks_per_sm; // resident CTAs, segments strided, next segment prefetched
 	if (grid > (long long)args.n_seg) {
 		grid = args.n_seg;
 	}

@@ -380,7 +380,8 @@ def run_b200(args):
     roof_scan = roof(kscan, "cubit_scan_kernel<4,false,0> (segment merge + bit->row-ID decode, single pass)",
                      "cubit_scan_kernel_dram_bytes_per_launch",
                      "k*ceil(N/64)*8 + 8*M  [SURVEY 8d]")
-    roof_probe = roof(kprobe, "cubit_probe_bits_kernel<4,1,true> (bit-driven probe: gather payload + SUM)",
+    roof_probe = roof(kprobe, "cubit_probe_bits_kernel<4,1,true> (bit-driven probe: gather payload + SUM; "
+                      "cubit_probe_kernel over the row-ID list for the two sparsest points)",
                       "cubit_probe_bits_kernel_dram_bytes_per_launch",
                       "8*M payload values read + ceil(N/64)*8 re-read of the merged bitvector  [SURVEY 8d: P]")
     dominant = roof_probe if kprobe[0] > kscan[0] else roof_scan

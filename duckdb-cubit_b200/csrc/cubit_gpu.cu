@@ -883,13 +883,22 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 	//                 kernel's 8 consumer warps per CTA can hold, and inside the scan kernel their
 	//                 latency lands on the consumers' critical path (measured: profiles/)
 	//   PROBE_FUSED   inside the scan kernel (CUBIT_Q_FUSE_PROBE): one launch
-	//   PROBE_GATHER  gather kernel over the row-ID list — 4-byte columns, > 2 columns, UNFUSED
+	//   PROBE_GATHER  gather kernel over the row-ID list — sparse selections whose row IDs are
+	//                 materialised anyway (< 1/256 of the rows), 4-byte columns, > 2 columns, UNFUSED
 	enum { PROBE_NONE, PROBE_FUSED, PROBE_BITS, PROBE_GATHER } probe_mode = PROBE_NONE;
 	if (need_probe) {
 		if (!fusable) {
 			probe_mode = PROBE_GATHER;
 		} else {
-			probe_mode = (q->flags & CUBIT_Q_FUSE_PROBE) ? PROBE_FUSED : PROBE_BITS;
+			if (q->flags & CUBIT_Q_FUSE_PROBE) {
+				probe_mode = PROBE_FUSED;
+			} else if (want_ids && cap <= t->n_rows / 256) {
+				// sparse and the row IDs are materialised anyway: gathering over the short ID list
+				// beats writing + re-reading the N/8-byte bitvector (measured: profiles/)
+				probe_mode = PROBE_GATHER;
+			} else {
+				probe_mode = PROBE_BITS;
+			}
 		}
 	}
 	const bool separate_probe = probe_mode == PROBE_GATHER;

@@ -14,14 +14,27 @@
 //   CALL cubit_load('lineitem', 'l_quantity', 1, 50);      -- build the GPU index + upload BIGINT columns
 //   SELECT sum(l_extendedprice) FROM cubit_scan('lineitem', 24, 24);   -- rowid + the uploaded columns
 //   SELECT * FROM cubit_agg('lineitem', 24, 24, 'l_extendedprice');    -- aggregate push-down: one row
+// and, transparently (OptimizerExtension, src/include/duckdb/optimizer/optimizer_extension.hpp:31-43): a plain
+//   SELECT sum(l_extendedprice) FROM lineitem WHERE l_quantity BETWEEN 10 AND 19;
+// whose pushed-down filters touch only the indexed column is re-pointed at the GPU scan, the way
+// TableScanPushdownComplexFilter re-points a seq_scan at ART's index_scan (src/function/table/table_scan.cpp:296-370).
 #include "duckdb.hpp"
 #include "duckdb/function/table_function.hpp"
 #include "duckdb/main/extension_util.hpp"
 #include "duckdb/common/types/data_chunk.hpp"
 #include "duckdb/common/types/vector.hpp"
+#include "duckdb/catalog/catalog_entry/table_catalog_entry.hpp"
+#include "duckdb/main/config.hpp"
+#include "duckdb/optimizer/optimizer_extension.hpp"
+#include "duckdb/planner/filter/conjunction_filter.hpp"
+#include "duckdb/planner/filter/constant_filter.hpp"
+#include "duckdb/planner/operator/logical_get.hpp"
 
 #include "cubit_gpu.h"
 
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -34,6 +47,8 @@ struct CubitGpuTable {
 	int64_t base_value = 0;
 	uint32_t cardinality = 0;
 	vector<string> column_names; // uploaded BIGINT columns, column id = position
+	vector<idx_t> table_column;  // table column index of every uploaded column
+	idx_t key_table_column = 0;  // table column index of the indexed column
 	idx_t row_count = 0;
 	~CubitGpuTable() {
 		cubit_gpu_destroy(handle);
@@ -102,6 +117,7 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 			}
 			int_cols.push_back(c);
 			gpu->column_names.push_back(res->names[c]);
+			gpu->table_column.push_back(c);
 		}
 	}
 	if (key_col == DConstants::INVALID_INDEX) {
@@ -123,6 +139,7 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 			cols[k].insert(cols[k].end(), ptr, ptr + chunk.size());
 		}
 	}
+	gpu->key_table_column = int_cols[key_col];
 	gpu->row_count = cols.empty() ? 0 : cols[0].size();
 	gpu->base_value = bind.base;
 	gpu->cardinality = bind.cardinality;
@@ -147,11 +164,14 @@ struct CubitScanBindData : public TableFunctionData {
 	int64_t lo = 0, hi = 0;
 	// aggregate push-down (cubit_agg)
 	int32_t agg_col = -1;
+	// set by the optimizer rewrite: column_ids are TABLE column indexes and must be mapped to GPU column ids
+	bool table_column_ids = false;
 };
 
 struct CubitScanGlobalState : public GlobalTableFunctionState {
 	cubit_gpu_result *result = nullptr;
 	vector<column_t> column_ids;
+	vector<idx_t> out_slot; // which entry of column_ids every output vector shows (projection_ids applied)
 	idx_t row_count = 0, offset = 0;
 	uint64_t sum_lo = 0;
 	int64_t sum_hi = 0;
@@ -178,10 +198,27 @@ static unique_ptr<FunctionData> CubitScanBind(ClientContext &, TableFunctionBind
 }
 
 static unique_ptr<GlobalTableFunctionState> CubitRunQuery(const CubitScanBindData &bind,
-                                                          const vector<column_t> &column_ids) {
+                                                          const vector<column_t> &column_ids_p,
+                                                          const vector<idx_t> &projection_ids) {
 	auto state = make_uniq<CubitScanGlobalState>();
-	state->column_ids = column_ids;
 	auto &gpu = *bind.gpu;
+	// the columns that actually leave the scan (filter-only columns are pruned: projection_ids)
+	vector<column_t> column_ids;
+	for (idx_t i = 0; i < (projection_ids.empty() ? column_ids_p.size() : projection_ids.size()); i++) {
+		column_t c = column_ids_p[projection_ids.empty() ? i : projection_ids[i]];
+		if (bind.table_column_ids && c != COLUMN_IDENTIFIER_ROW_ID) {
+			idx_t g = 0;
+			while (g < gpu.table_column.size() && gpu.table_column[g] != c) {
+				g++;
+			}
+			if (g == gpu.table_column.size()) {
+				throw InternalException("cubit: column %llu is not resident on the GPU", c);
+			}
+			c = g;
+		}
+		column_ids.push_back(c);
+	}
+	state->column_ids = column_ids;
 	const int64_t lo = MaxValue<int64_t>(bind.lo, gpu.base_value);
 	const int64_t hi = MinValue<int64_t>(bind.hi, gpu.base_value + gpu.cardinality - 1);
 	if (lo > hi) {
@@ -222,7 +259,7 @@ static unique_ptr<GlobalTableFunctionState> CubitRunQuery(const CubitScanBindDat
 }
 
 static unique_ptr<GlobalTableFunctionState> CubitScanInitGlobal(ClientContext &, TableFunctionInitInput &input) {
-	return CubitRunQuery(input.bind_data->Cast<CubitScanBindData>(), input.column_ids);
+	return CubitRunQuery(input.bind_data->Cast<CubitScanBindData>(), input.column_ids, input.projection_ids);
 }
 
 static void CubitScanFunction(ClientContext &, TableFunctionInput &data_p, DataChunk &output) {
@@ -282,20 +319,164 @@ static void CubitAggFunction(ClientContext &, TableFunctionInput &data_p, DataCh
 	state.agg_emitted = true;
 }
 
+// ---------------------------------------------------------------- transparent rewrite of seq_scan → cubit_scan
+static std::atomic<idx_t> cubit_rewrite_count {0};
+idx_t CubitRewriteCount() {
+	return cubit_rewrite_count.load();
+}
+
+static TableFunction CubitScanTableFunction();
+
+// lo <= key <= hi from the pushed-down filter of ONE column; false if the shape is not supported
+static bool CubitBoundsFromFilter(const TableFilter &filter, int64_t &lo, int64_t &hi) {
+	switch (filter.filter_type) {
+	case TableFilterType::IS_NOT_NULL:
+		return true; // NULL keys are not indexed
+	case TableFilterType::CONJUNCTION_AND: {
+		for (auto &child : filter.Cast<ConjunctionAndFilter>().child_filters) {
+			if (!CubitBoundsFromFilter(*child, lo, hi)) {
+				return false;
+			}
+		}
+		return true;
+	}
+	case TableFilterType::CONSTANT_COMPARISON: {
+		auto &cf = filter.Cast<ConstantFilter>();
+		if (!cf.constant.type().IsIntegral() && cf.constant.type().id() != LogicalTypeId::DECIMAL) {
+			return false;
+		}
+		int64_t c;
+		if (!Hugeint::TryCast(IntegralValue::Get(cf.constant), c)) { // raw integer (DECIMAL: unscaled cents)
+			return false;
+		}
+		switch (cf.comparison_type) {
+		case ExpressionType::COMPARE_EQUAL:
+			lo = MaxValue(lo, c);
+			hi = MinValue(hi, c);
+			return true;
+		case ExpressionType::COMPARE_GREATERTHAN:
+			lo = MaxValue(lo, c + 1);
+			return true;
+		case ExpressionType::COMPARE_GREATERTHANOREQUALTO:
+			lo = MaxValue(lo, c);
+			return true;
+		case ExpressionType::COMPARE_LESSTHAN:
+			hi = MinValue(hi, c - 1);
+			return true;
+		case ExpressionType::COMPARE_LESSTHANOREQUALTO:
+			hi = MinValue(hi, c);
+			return true;
+		default:
+			return false;
+		}
+	}
+	default:
+		return false;
+	}
+}
+
+#define CUBIT_WHY(msg)                                                                                                  \
+	do {                                                                                                               \
+		if (getenv("CUBIT_DEBUG_REWRITE")) {                                                                           \
+			fprintf(stderr, "cubit rewrite skipped: %s\n", msg);                                                      \
+		}                                                                                                              \
+		return;                                                                                                        \
+	} while (0)
+
+static void CubitRewriteGet(LogicalGet &get) {
+	if (get.function.name != "seq_scan") {
+		CUBIT_WHY(get.function.name.c_str());
+	}
+	if (get.table_filters.filters.size() != 1) {
+		CUBIT_WHY("not exactly one filtered column");
+	}
+	auto table = get.GetTable();
+	if (!table) {
+		CUBIT_WHY("no table");
+	}
+	shared_ptr<CubitGpuTable> gpu;
+	{
+		std::lock_guard<std::mutex> lk(cubit_registry_lock);
+		auto it = cubit_registry.find(table->name);
+		if (it == cubit_registry.end()) {
+			CUBIT_WHY("table has no GPU index");
+		}
+		gpu = it->second;
+	}
+	// the only pushed-down filter must sit on the indexed column (keys of LogicalGet::table_filters are
+	// table column indexes: filter_combiner.cpp:438-480, plan_get.cpp:15-33)
+	auto &entry = *get.table_filters.filters.begin();
+	if (entry.first != gpu->key_table_column) {
+		CUBIT_WHY("filter is not on the indexed column");
+	}
+	int64_t lo = NumericLimits<int64_t>::Minimum() + 1, hi = NumericLimits<int64_t>::Maximum() - 1;
+	if (!CubitBoundsFromFilter(*entry.second, lo, hi)) {
+		CUBIT_WHY("unsupported filter shape");
+	}
+	// every column that leaves the scan must be GPU resident and physically int64 (BIGINT, DECIMAL(≤18))
+	for (idx_t i = 0; i < (get.projection_ids.empty() ? get.column_ids.size() : get.projection_ids.size()); i++) {
+		const column_t c = get.column_ids[get.projection_ids.empty() ? i : get.projection_ids[i]];
+		if (c == COLUMN_IDENTIFIER_ROW_ID) {
+			continue;
+		}
+		if (c >= get.returned_types.size() || get.returned_types[c].InternalType() != PhysicalType::INT64) {
+			CUBIT_WHY("projected column is not physically INT64");
+		}
+		bool resident = false;
+		for (auto tc : gpu->table_column) {
+			resident |= tc == c;
+		}
+		if (!resident) {
+			CUBIT_WHY("projected column is not GPU resident");
+		}
+	}
+	auto bind = make_uniq<CubitScanBindData>();
+	bind->gpu = gpu;
+	bind->lo = lo;
+	bind->hi = hi;
+	bind->table_column_ids = true;
+	get.function = CubitScanTableFunction();
+	get.bind_data = std::move(bind);
+	get.table_filters.filters.clear(); // applied exactly by the bitmap scan
+	cubit_rewrite_count++;
+}
+
+static void CubitRewritePlan(LogicalOperator &op) {
+	if (op.type == LogicalOperatorType::LOGICAL_GET) {
+		CubitRewriteGet(op.Cast<LogicalGet>());
+	}
+	for (auto &child : op.children) {
+		CubitRewritePlan(*child);
+	}
+}
+
+static void CubitOptimize(OptimizerExtensionInput &, unique_ptr<LogicalOperator> &plan) {
+	CubitRewritePlan(*plan);
+}
+
+static TableFunction CubitScanTableFunction() {
+	TableFunction scan("cubit_scan", {LogicalType::VARCHAR, LogicalType::BIGINT, LogicalType::BIGINT}, CubitScanFunction,
+	                   CubitScanBind, CubitScanInitGlobal);
+	scan.projection_pushdown = true; // column_ids tell the GPU which columns to probe
+	scan.filter_prune = true;        // columns used only by the (absorbed) filter are not produced
+	return scan;
+}
+
 // ---------------------------------------------------------------- registration
 void RegisterCubitGpuFunctions(DatabaseInstance &db) {
 	TableFunction load("cubit_load", {LogicalType::VARCHAR, LogicalType::VARCHAR, LogicalType::BIGINT, LogicalType::BIGINT},
 	                   CubitLoadFunction, CubitLoadBind);
 	ExtensionUtil::RegisterFunction(db, load);
 
-	TableFunction scan("cubit_scan", {LogicalType::VARCHAR, LogicalType::BIGINT, LogicalType::BIGINT}, CubitScanFunction,
-	                   CubitScanBind, CubitScanInitGlobal);
-	scan.projection_pushdown = true; // column_ids tell the GPU which columns to probe
-	ExtensionUtil::RegisterFunction(db, scan);
+	ExtensionUtil::RegisterFunction(db, CubitScanTableFunction());
 
 	TableFunction agg("cubit_agg", {LogicalType::VARCHAR, LogicalType::BIGINT, LogicalType::BIGINT, LogicalType::VARCHAR},
 	                  CubitAggFunction, CubitAggBind, CubitScanInitGlobal);
 	ExtensionUtil::RegisterFunction(db, agg);
+
+	OptimizerExtension rewrite;
+	rewrite.optimize_function = CubitOptimize;
+	DBConfig::GetConfig(db).optimizer_extensions.push_back(rewrite);
 }
 
 } // namespace duckdb

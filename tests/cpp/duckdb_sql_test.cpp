@@ -8,6 +8,7 @@
 
 namespace duckdb {
 void RegisterCubitGpuFunctions(DatabaseInstance &db);
+idx_t CubitRewriteCount();
 }
 using namespace duckdb;
 
@@ -67,6 +68,35 @@ int main(int argc, char **argv) {
 		if (b->GetValue(0, 0).GetValue<int64_t>() > 0) {
 			REQUIRE(g->GetValue(1, 0).ToString() == b->GetValue(1, 0).ToString());
 		}
+	}
+	// transparent rewrite: plain SQL on the indexed table is re-pointed at the GPU scan by the optimizer
+	// extension; t_plain holds the same rows but has no GPU index, so it takes the vanilla seq_scan
+	Run(con, "CREATE TABLE t_plain AS SELECT * FROM t");
+	const char *wheres[] = {"q BETWEEN 10 AND 19", "q = 24", "q < 4", "q >= 48 AND q <= 49", "q > 45", "q >= 7"};
+	for (auto w : wheres) {
+		const string where = w;
+		const idx_t before = CubitRewriteCount();
+		auto a = Run(con, "SELECT count(*), sum(price), sum(price * disc), min(rowid), max(rowid) FROM t WHERE " + where);
+		REQUIRE(CubitRewriteCount() == before + 1); // the scan really went through cubit_scan
+		auto b = Run(con, "SELECT count(*), sum(price), sum(price * disc), min(rowid), max(rowid) FROM t_plain WHERE " + where);
+		REQUIRE(CubitRewriteCount() == before + 1);
+		for (idx_t c = 0; c < 5; c++) {
+			REQUIRE(a->GetValue(c, 0).ToString() == b->GetValue(c, 0).ToString());
+		}
+		auto x = Run(con, "SELECT rowid, price FROM t WHERE " + where + " ORDER BY rowid");
+		auto y = Run(con, "SELECT rowid, price FROM t_plain WHERE " + where + " ORDER BY rowid");
+		REQUIRE(x->RowCount() == y->RowCount());
+		for (idx_t r = 0; r < x->RowCount(); r += 97) {
+			REQUIRE(x->GetValue(0, r) == y->GetValue(0, r) && x->GetValue(1, r) == y->GetValue(1, r));
+		}
+	}
+	{ // a filter on another column as well: not rewritten, still correct
+		const idx_t before = CubitRewriteCount();
+		auto a = Run(con, "SELECT count(*) FROM t WHERE q = 24 AND disc = 3");
+		auto b = Run(con, "SELECT count(*) FROM t_plain WHERE q = 24 AND disc = 3");
+		REQUIRE(CubitRewriteCount() == before && a->GetValue(0, 0) == b->GetValue(0, 0));
+		auto plan = Run(con, "EXPLAIN SELECT sum(price) FROM t WHERE q BETWEEN 10 AND 19");
+		REQUIRE(plan->GetValue(1, 0).ToString().find("CUBIT_SCAN") != string::npos);
 	}
 	auto err = con.Query("SELECT * FROM cubit_scan('nope', 1, 2)");
 	REQUIRE(err->HasError());

@@ -24,7 +24,7 @@ OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5
 MAX_STREAMS = 64
 MAX_PROBE_COLS = 8
 Q_ROWIDS, Q_BITVECTOR, Q_VALUES, Q_TIMING, Q_UNFUSED, Q_ASYNC, Q_FUSE_PROBE = 1, 2, 4, 8, 16, 32, 64
-AGG_NONE, AGG_SUM, AGG_SUM_PROD = 0, 1, 2
+AGG_NONE, AGG_SUM, AGG_SUM_PROD, AGG_SUM_F64 = 0, 1, 2, 3
 
 # every symbol include/cubit_gpu.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
@@ -57,7 +57,8 @@ class ResultInfo(C.Structure):
                 ("n_streams", C.c_uint32), ("n_launches", C.c_uint32), ("delta_entries", C.c_uint64),
                 ("algo_bytes_scan", C.c_uint64), ("algo_bytes_probe", C.c_uint64), ("ms_scan", C.c_float),
                 ("ms_probe", C.c_float), ("ms_total", C.c_float), ("fused", C.c_uint32),
-                ("d_rowids", C.c_void_p), ("d_bitvector", C.c_void_p), ("d_values", C.c_void_p * MAX_PROBE_COLS)]
+                ("d_rowids", C.c_void_p), ("d_bitvector", C.c_void_p), ("d_values", C.c_void_p * MAX_PROBE_COLS),
+                ("sum_f64", C.c_double)]
 
 
 class CubitError(RuntimeError):
@@ -176,6 +177,10 @@ class Result:
     @property
     def sum(self):
         return int128(self.info.sum_lo, self.info.sum_hi)
+
+    @property
+    def sum_f64(self):
+        return float(self.info.sum_f64)
 
     def fetch(self, offset=0, n=None, rowids=True, out_ids=None, out_cols=None):
         """→ (row_ids or None, [column arrays]) for result rows [offset, offset+n)"""

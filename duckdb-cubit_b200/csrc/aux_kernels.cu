@@ -29,8 +29,10 @@ constexpr int kProbeThreads = 256;
 constexpr int kProbePairs = 4; // row-ID pairs per thread per iteration (8 independent gathers in flight)
 
 __device__ __forceinline__ void agg_row(const ProbeArgs &a, int64_t local, unsigned long long &lo, long long &hi,
-                                        unsigned int &ovf) {
-	if (a.agg_kind == 1) {
+                                        unsigned int &ovf, double &fsum) {
+	if (a.agg_kind == 3) {
+		fsum += __longlong_as_double(__ldg(a.agg_a + local));
+	} else if (a.agg_kind == 1) {
 		add128(lo, hi, __ldg(a.agg_a + local));
 	} else if (a.agg_kind == 2) {
 		const long long x = __ldg(a.agg_a + local);
@@ -49,6 +51,7 @@ __global__ void __launch_bounds__(kProbeThreads) cubit_probe_kernel(const __grid
 	unsigned long long lo = 0;
 	long long hi = 0;
 	unsigned int ovf = 0;
+	double fsum = 0.0;
 
 	const unsigned long long stride = (unsigned long long)gridDim.x * kProbeThreads * kProbePairs;
 	for (unsigned long long base = (unsigned long long)blockIdx.x * kProbeThreads * kProbePairs; base < n_pairs;
@@ -107,8 +110,8 @@ __global__ void __launch_bounds__(kProbeThreads) cubit_probe_kernel(const __grid
 #pragma unroll
 			for (int u = 0; u < kProbePairs; u++) {
 				if (ok[u]) {
-					agg_row(a, id[u].x - a.row_base, lo, hi, ovf);
-					agg_row(a, id[u].y - a.row_base, lo, hi, ovf);
+					agg_row(a, id[u].x - a.row_base, lo, hi, ovf, fsum);
+					agg_row(a, id[u].y - a.row_base, lo, hi, ovf, fsum);
 				}
 			}
 		}
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(kProbeThreads) cubit_probe_kernel(const __grid
 			}
 		}
 		if (a.agg_kind) {
-			agg_row(a, l, lo, hi, ovf);
+			agg_row(a, l, lo, hi, ovf, fsum);
 		}
 	}
 	if (!a.agg_kind) {
@@ -137,6 +140,10 @@ __global__ void __launch_bounds__(kProbeThreads) cubit_probe_kernel(const __grid
 		const long long ohi = __shfl_xor_sync(0xffffffffu, hi, d);
 		add128(lo, hi, olo, ohi);
 		ovf |= __shfl_xor_sync(0xffffffffu, ovf, d);
+		fsum += __shfl_xor_sync(0xffffffffu, fsum, d);
+	}
+	if ((threadIdx.x & 31) == 0 && fsum != 0.0) {
+		atomicAdd(&a.hdr->sum_f64, fsum);
 	}
 	if ((threadIdx.x & 31) == 0) {
 		red[threadIdx.x >> 5].sum_lo = lo;

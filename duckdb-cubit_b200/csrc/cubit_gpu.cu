@@ -707,6 +707,7 @@ static int finish_result(cubit_gpu_result *r) {
 	r->info.count = r->h_hdr->count;
 	r->info.sum_lo = r->h_hdr->sum_lo;
 	r->info.sum_hi = r->h_hdr->sum_hi;
+	r->info.sum_f64 = r->h_hdr->sum_f64;
 	r->info.algo_bytes_scan += 8ull * ((r->flags & CUBIT_Q_ROWIDS) ? r->info.count : 0);
 	// P of SURVEY §8d: M * Σ width over the distinct columns whose values are needed
 	// (+ 8*M when a separate probe kernel re-reads the row IDs)
@@ -746,7 +747,7 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 	if (q->n_cols > CUBIT_MAX_PROBE_COLS || (q->n_cols && !q->cols)) {
 		return fail(CUBIT_EINVAL, "bad projected column list");
 	}
-	if (q->agg_kind < CUBIT_AGG_NONE || q->agg_kind > CUBIT_AGG_SUM_PROD) {
+	if (q->agg_kind < CUBIT_AGG_NONE || q->agg_kind > CUBIT_AGG_SUM_F64) {
 		return fail(CUBIT_EINVAL, "bad agg_kind %d", q->agg_kind);
 	}
 	std::lock_guard<std::mutex> lk(t->mu);

@@ -28,6 +28,7 @@ struct ResultHeader {
 	long long sum_hi;
 	unsigned int overflow; // int64 product overflow seen (CUBIT_AGG_SUM_PROD)
 	unsigned int pad;
+	double sum_f64;        // CUBIT_AGG_SUM_F64
 };
 
 struct BlockPartial {

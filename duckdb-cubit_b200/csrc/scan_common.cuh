@@ -152,11 +152,44 @@ __device__ __forceinline__ unsigned long long sum_aggregates(const unsigned long
 	return acc;
 }
 
+// per-lane aggregate state of the fused / bit-driven probe
+struct Agg {
+	unsigned long long lo = 0; // 128-bit integer SUM, low limb
+	long long hi = 0;          //                      high limb
+	double f = 0.0;            // SUM over a DOUBLE column (CUBIT_AGG_SUM_F64)
+	unsigned int overflow = 0;
+};
+
+// warp-reduce an Agg and add it to the result header: exact for the integer limbs (the carry out of the
+// low limb is recovered from the value the atomic returns), plain atomicAdd for the double
+__device__ __forceinline__ void agg_flush_warp(Agg &g, ResultHeader *hdr, int lane) {
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		const unsigned long long olo = __shfl_xor_sync(0xffffffffu, g.lo, d);
+		const long long ohi = __shfl_xor_sync(0xffffffffu, g.hi, d);
+		add128(g.lo, g.hi, olo, ohi);
+		g.f += __shfl_xor_sync(0xffffffffu, g.f, d);
+		g.overflow |= __shfl_xor_sync(0xffffffffu, g.overflow, d);
+	}
+	if (lane == 0) {
+		if (g.lo | (unsigned long long)g.hi) {
+			const unsigned long long old = atomicAdd(&hdr->sum_lo, g.lo);
+			const long long carry = (old + g.lo) < old ? 1 : 0;
+			atomicAdd(reinterpret_cast<unsigned long long *>(&hdr->sum_hi), (unsigned long long)(g.hi + carry));
+		}
+		if (g.f != 0.0) {
+			atomicAdd(&hdr->sum_f64, g.f);
+		}
+		if (g.overflow) {
+			atomicOr(&hdr->overflow, 1u);
+		}
+	}
+}
+
 // one selected row: store its id / gathered values at output position `pos`, accumulate
 template <int NL, bool POS>
 __device__ __forceinline__ void consume_row(const ScanArgs &a, unsigned long long pos, int64_t rid,
-                                            const long long (&v)[NL > 0 ? NL : 1], unsigned long long &sum_lo,
-                                            long long &sum_hi, unsigned int &overflow) {
+                                            const long long (&v)[NL > 0 ? NL : 1], Agg &agg) {
 	if (POS) {
 		if (a.ids_out) {
 			__stcs(a.ids_out + pos, (long long)rid);
@@ -171,14 +204,16 @@ __device__ __forceinline__ void consume_row(const ScanArgs &a, unsigned long lon
 	if (NL > 0) {
 		const long long x = (NL > 1 && a.agg_ia == 1) ? v[NL - 1] : v[0];
 		if (a.agg_kind == 1) {
-			add128(sum_lo, sum_hi, x);
+			add128(agg.lo, agg.hi, x);
 		} else if (a.agg_kind == 2) {
 			const long long y = (NL > 1 && a.agg_ib == 1) ? v[NL - 1] : v[0];
 			const long long pr = x * y;
 			if (__mul64hi(x, y) != (pr >> 63)) {
-				overflow = 1;
+				agg.overflow = 1;
 			}
-			add128(sum_lo, sum_hi, pr);
+			add128(agg.lo, agg.hi, pr);
+		} else if (a.agg_kind == 3) {
+			agg.f += __longlong_as_double(x);
 		}
 	}
 }
@@ -191,7 +226,7 @@ __device__ __forceinline__ void consume_row(const ScanArgs &a, unsigned long lon
 template <int NL, bool POS>
 __device__ __forceinline__ void write_out(const ScanArgs &a, const uint16_t *cbuf, uint32_t pad, uint32_t count,
                                           unsigned long long pos0, int64_t row_origin, int lane,
-                                          unsigned long long &sum_lo, long long &sum_hi, unsigned int &overflow) {
+                                          Agg &agg) {
 	const int64_t local0 = row_origin - a.row_base;
 	const unsigned long long obase = pos0 - pad; // output position of staging index 0 (even)
 	const uint32_t end = pad + count;
@@ -236,15 +271,14 @@ __device__ __forceinline__ void write_out(const ScanArgs &a, const uint16_t *cbu
 					}
 				}
 				if (NL > 0) {
-					consume_row<NL, false>(a, 0, 0, v[h][0], sum_lo, sum_hi, overflow);
-					consume_row<NL, false>(a, 0, 0, v[h][1], sum_lo, sum_hi, overflow);
+					consume_row<NL, false>(a, 0, 0, v[h][0], agg);
+					consume_row<NL, false>(a, 0, 0, v[h][1], agg);
 				}
 			} else {
 #pragma unroll
 				for (int e = 0; e < 2; e++) {
 					if (ok[h][e]) {
-						consume_row<NL, POS>(a, obase + g * 2 + e, row_origin + r[h][e], v[h][e], sum_lo, sum_hi,
-						                     overflow);
+						consume_row<NL, POS>(a, obase + g * 2 + e, row_origin + r[h][e], v[h][e], agg);
 					}
 				}
 			}
@@ -277,7 +311,7 @@ __device__ __forceinline__ void stage_word(uint16_t *cbuf, uint32_t p0, uint32_t
 template <int WPT, int NL, bool POS>
 __device__ __forceinline__ void emit_span(const ScanArgs &a, const uint64_t (&q)[WPT], uint16_t *cbuf,
                                           unsigned long long wbase, int64_t span_row0, int lane,
-                                          unsigned long long &sum_lo, long long &sum_hi, unsigned int &overflow) {
+                                          Agg &agg) {
 	uint32_t c[WPT], incl[WPT], lane_total = 0;
 #pragma unroll
 	for (int i = 0; i < WPT; i++) {
@@ -318,7 +352,7 @@ __device__ __forceinline__ void emit_span(const ScanArgs &a, const uint64_t (&q)
 			base += slot_total[i];
 		}
 		__syncwarp();
-		write_out<NL, POS>(a, cbuf, pad, span_total, wbase, span_row0, lane, sum_lo, sum_hi, overflow);
+		write_out<NL, POS>(a, cbuf, pad, span_total, wbase, span_row0, lane, agg);
 		__syncwarp();
 		return;
 	}
@@ -331,8 +365,7 @@ __device__ __forceinline__ void emit_span(const ScanArgs &a, const uint64_t (&q)
 		const uint32_t pad = (uint32_t)pos0 & 1u;
 		stage_word(cbuf, pad + incl[i] - c[i], (uint32_t)q[i], (uint32_t)(q[i] >> 32), (uint32_t)lane * 64u, dummy);
 		__syncwarp();
-		write_out<NL, POS>(a, cbuf, pad, slot_total[i], pos0, span_row0 + (int64_t)i * kSlotRows, lane, sum_lo, sum_hi,
-		                   overflow);
+		write_out<NL, POS>(a, cbuf, pad, slot_total[i], pos0, span_row0 + (int64_t)i * kSlotRows, lane, agg);
 		__syncwarp();
 		pos0 += slot_total[i];
 	}

@@ -216,9 +216,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 	const unsigned dbg = (a.debug == 2u || a.debug == 7u) ? a.debug : 0u;
 	uint32_t stage = 0, phase = 0;
 	unsigned long long blk_count = 0; // meaningful in thread 0
-	unsigned long long sum_lo = 0;
-	long long sum_hi = 0;
-	unsigned int overflow = 0;
+	Agg agg;
 	uint32_t it = 0;
 
 	// The PENDING segments: merged and counted one and two iterations ago, aggregates
@@ -373,10 +371,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 					    a.row_base + ((int64_t)ptile[kDefer - 1] * kTileWords + (int64_t)warp * kSpanWords) * 64;
 					if (need_pos) {
 						emit_span<WPT, NL, true>(a, pq[kDefer - 1], sm.compact[warp], excl + pwexcl[kDefer - 1], span_row0,
-						                         lane, sum_lo, sum_hi, overflow);
+						                         lane, agg);
 					} else {
-						emit_span<WPT, NL, false>(a, pq[kDefer - 1], sm.compact[warp], 0, span_row0, lane, sum_lo, sum_hi,
-						                          overflow);
+						emit_span<WPT, NL, false>(a, pq[kDefer - 1], sm.compact[warp], 0, span_row0, lane, agg);
 					}
 				}
 			}
@@ -411,41 +408,13 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 		it++;
 	}
 
-	// ---- block reduction of count / 128-bit sum, then one exact atomic accumulate per CTA
-	// (hdr is zeroed before the launch; no serial last-block pass over per-CTA partials)
-#pragma unroll
-	for (int d = 16; d > 0; d >>= 1) {
-		const unsigned long long olo = __shfl_xor_sync(0xffffffffu, sum_lo, d);
-		const long long ohi = __shfl_xor_sync(0xffffffffu, sum_hi, d);
-		add128(sum_lo, sum_hi, olo, ohi);
-		overflow |= __shfl_xor_sync(0xffffffffu, overflow, d);
+	// ---- one exact atomic accumulate per warp / CTA (hdr is zeroed before the launch; no serial
+	// last-block pass over per-CTA partials)
+	if (NL > 0 && a.agg_kind != 0) {
+		agg_flush_warp(agg, a.hdr, lane);
 	}
-	if (lane == 0) {
-		sm.red[warp].sum_lo = sum_lo;
-		sm.red[warp].sum_hi = sum_hi;
-		sm.red[warp].pad = overflow;
-	}
-	consumer_bar_sync();
-	if (threadIdx.x == 0) {
-		unsigned long long lo = 0;
-		long long hi = 0;
-		unsigned long long ovf = 0;
-		for (int w = 0; w < kConsumerWarps; w++) {
-			add128(lo, hi, sm.red[w].sum_lo, sm.red[w].sum_hi);
-			ovf |= sm.red[w].pad;
-		}
-		if (blk_count && !a.skip_count) {
-			atomicAdd(&a.hdr->count, blk_count);
-		}
-		if (lo | (unsigned long long)hi) {
-			// the carry out of the low limb is recovered from the value the atomic returns
-			const unsigned long long old = atomicAdd(&a.hdr->sum_lo, lo);
-			const long long carry = (old + lo) < old ? 1 : 0;
-			atomicAdd(reinterpret_cast<unsigned long long *>(&a.hdr->sum_hi), (unsigned long long)(hi + carry));
-		}
-		if (ovf) {
-			atomicOr(&a.hdr->overflow, 1u);
-		}
+	if (threadIdx.x == 0 && blk_count && !a.skip_count) {
+		atomicAdd(&a.hdr->count, blk_count);
 	}
 }
 
@@ -458,16 +427,13 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 constexpr int kProbeBitsThreads = 256;
 
 template <int WPT, int NL, bool POS>
-__global__ void __launch_bounds__(kProbeBitsThreads) cubit_probe_bits_kernel(const __grid_constant__ ScanArgs a) {
+__global__ void __launch_bounds__(kProbeBitsThreads, 3) cubit_probe_bits_kernel(const __grid_constant__ ScanArgs a) {
 	constexpr int kTileWords = kProbeBitsThreads * WPT;
 	constexpr int kSpanWords = WPT * 32;
 	__shared__ __align__(16) uint16_t compact[kProbeBitsThreads / 32][kSlotRows + 8 + 32];
 	__shared__ uint32_t warp_tot[2][kProbeBitsThreads / 32];
-	__shared__ BlockPartial red[kProbeBitsThreads / 32];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	unsigned long long sum_lo = 0;
-	long long sum_hi = 0;
-	unsigned int overflow = 0;
+	Agg agg;
 	uint32_t it = 0;
 	// software pipeline: the next segment's words are in flight while this one is decoded
 	uint64_t qn[WPT];
@@ -510,39 +476,10 @@ __global__ void __launch_bounds__(kProbeBitsThreads) cubit_probe_bits_kernel(con
 			wbase = tile_excl + warp_excl;
 		}
 		const int64_t span_row0 = a.row_base + ((int64_t)tile * kTileWords + (int64_t)warp * kSpanWords) * 64;
-		emit_span<WPT, NL, POS>(a, q, compact[warp], wbase, span_row0, lane, sum_lo, sum_hi, overflow);
+		emit_span<WPT, NL, POS>(a, q, compact[warp], wbase, span_row0, lane, agg);
 	}
-	if (a.agg_kind == 0) {
-		return;
-	}
-#pragma unroll
-	for (int d = 16; d > 0; d >>= 1) {
-		const unsigned long long olo = __shfl_xor_sync(0xffffffffu, sum_lo, d);
-		const long long ohi = __shfl_xor_sync(0xffffffffu, sum_hi, d);
-		add128(sum_lo, sum_hi, olo, ohi);
-		overflow |= __shfl_xor_sync(0xffffffffu, overflow, d);
-	}
-	if (lane == 0) {
-		red[warp].sum_lo = sum_lo;
-		red[warp].sum_hi = sum_hi;
-		red[warp].pad = overflow;
-	}
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		unsigned long long lo = 0, ovf = 0;
-		long long hi = 0;
-		for (int w = 0; w < kProbeBitsThreads / 32; w++) {
-			add128(lo, hi, red[w].sum_lo, red[w].sum_hi);
-			ovf |= red[w].pad;
-		}
-		// exact 128-bit accumulate: the carry out of the low limb is recovered from the value
-		// the atomic returns, the high limbs simply add
-		const unsigned long long old = atomicAdd(&a.hdr->sum_lo, lo);
-		const long long carry = (old + lo) < old ? 1 : 0;
-		atomicAdd(reinterpret_cast<unsigned long long *>(&a.hdr->sum_hi), (unsigned long long)(hi + carry));
-		if (ovf) {
-			atomicOr(&a.hdr->overflow, 1u);
-		}
+	if (a.agg_kind != 0) {
+		agg_flush_warp(agg, a.hdr, lane);
 	}
 }
 

@@ -80,6 +80,8 @@ typedef struct cubit_pred_group {
 #define CUBIT_AGG_NONE 0
 #define CUBIT_AGG_SUM 1      /* SUM(col a)            */
 #define CUBIT_AGG_SUM_PROD 2 /* SUM(col a * col b), int64 product (arithmetic.cpp:766-795) */
+#define CUBIT_AGG_SUM_F64 3  /* SUM(col a) over a DOUBLE column; order of additions is not fixed, so the result
+                               is reproducible to ~1e-15 relative and specified to 1e-12 (north_star) */
 
 /* Q = AND_j ( OR_{i in groups[j]} ( B_i XOR D_i ) ) */
 typedef struct cubit_query {
@@ -110,6 +112,7 @@ typedef struct cubit_result_info {
 	const int64_t *d_rowids;   /* device pointers (valid until free_result)     */
 	const uint64_t *d_bitvector;
 	const void *d_values[CUBIT_MAX_PROBE_COLS];
+	double sum_f64;         /* CUBIT_AGG_SUM_F64 */
 } cubit_result_info;
 
 /* ---- library ---------------------------------------------------------- */

@@ -58,6 +58,8 @@ def lib():
         L.oracle_sum_i64.restype = None
         L.oracle_sum_prod_i64.argtypes = [_i64p, _i64p, C.c_uint64, _u64p, _i64p]
         L.oracle_sum_prod_i64.restype = C.c_int
+        L.oracle_sum_f64.argtypes = [C.POINTER(C.c_double), C.c_uint64, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.oracle_sum_f64.restype = None
         L.oracle_build_index.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_int64, C.c_uint32, _u64p,
                                          C.c_uint64]
         L.oracle_build_index.restype = None
@@ -154,6 +156,14 @@ def sum_prod_i64(a, b):
     lo, hi = C.c_uint64(0), C.c_int64(0)
     ovf = lib().oracle_sum_prod_i64(_p(a, _i64p), _p(b, _i64p), len(a), C.byref(lo), C.byref(hi))
     return int128(lo.value, hi.value), bool(ovf)
+
+
+def sum_f64(vals):
+    """→ (scan-order double sum, compensated sum)"""
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    a, b = C.c_double(0), C.c_double(0)
+    lib().oracle_sum_f64(vals.ctypes.data_as(C.POINTER(C.c_double)), len(vals), C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 def build_index(col, base_value, card):

@@ -410,3 +410,35 @@ def test_maximum_stream_count(cubit):
     with pytest.raises(cubit.CubitError):
         t.query([[(ix, v) for v in range(65)]])
     t.close()
+
+
+@pytest.mark.parametrize("extra_name", ["default", "unfused", "fuse_probe"])
+def test_double_sum_within_1e12(cubit, extra_name):
+    """SUM over a DOUBLE column (north_star: float aggregates within 1e-12 relative of the reference order sum)"""
+    import math
+    extra = {"default": 0, "unfused": cubit.Q_UNFUSED, "fuse_probe": cubit.Q_FUSE_PROBE}[extra_name]
+    n = 4_000_037
+    rng = np.random.default_rng(17)
+    col = rng.integers(0, 10, n).astype(np.int32)
+    val = rng.normal(0.0, 1e6, n) + 1e9          # float64, large common offset: cancellation-free but long sum
+    bv = oracle.build_index(col, 0, 10)
+    t = cubit.CubitTable(n)
+    t.upload_column(0, val)
+    t.upload_column(1, col)
+    ix = t.create_index(10)
+    t.build_index(ix, 1, 0)
+    TOL = 1e-12  # relative tolerance stated by north_star
+    for vals_sel in ([3], [0, 1, 2, 3, 4, 5, 6], list(range(10))):
+        want = oracle.decode(oracle.merge([[bv[v] for v in vals_sel]]))
+        ref_plain, ref_comp = oracle.sum_f64(val[want])      # DuckDB order (plain) and compensated
+        exact = math.fsum(val[want].tolist())
+        for flags in (extra, cubit.Q_ROWIDS | cubit.Q_VALUES | extra):
+            with t.query([[(ix, v) for v in vals_sel]], flags=flags, cols=[0] if flags & cubit.Q_VALUES else (),
+                         agg=cubit.AGG_SUM_F64, agg_a=0) as r:
+                assert r.count == len(want)
+                assert abs(r.sum_f64 - ref_plain) <= TOL * abs(ref_plain)
+                assert abs(r.sum_f64 - exact) <= TOL * abs(exact)
+                if flags & cubit.Q_VALUES:
+                    ids, (got,) = r.fetch()
+                    assert np.array_equal(ids, want) and np.array_equal(got, val[want])   # values are bit-exact
+    t.close()

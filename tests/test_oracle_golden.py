@@ -149,3 +149,13 @@ def test_empty_and_full():
     f = oracle.build_index(np.zeros(n, dtype=np.int32), 0, 1)[0]
     assert np.array_equal(oracle.decode(f), np.arange(n))
     assert len(oracle.decode(oracle.merge([[f], [z]]))) == 0
+
+
+def test_double_sum_oracle():
+    import math
+    rng = np.random.default_rng(3)
+    v = rng.normal(0, 1e6, 200_000) + 1e9
+    plain, comp = oracle.sum_f64(v)
+    exact = math.fsum(v.tolist())
+    assert abs(comp - exact) <= 1e-15 * abs(exact)
+    assert abs(plain - exact) <= 1e-12 * abs(exact)

@@ -442,3 +442,72 @@ def test_double_sum_within_1e12(cubit, extra_name):
                     ids, (got,) = r.fetch()
                     assert np.array_equal(ids, want) and np.array_equal(got, val[want])   # values are bit-exact
     t.close()
+
+
+def test_scan_while_deltas_change(cubit):
+    """concurrentloop-style stress (test/sql/parallelism/interquery/*): one thread keeps replacing /
+    clearing / merging pending deltas while others scan; every scan must see exactly one of the consistent states"""
+    import threading
+    n = 1_500_007
+    rng = np.random.default_rng(23)
+    col = rng.integers(0, 8, n).astype(np.int32)
+    bv = oracle.build_index(col, 0, 8)
+    t = cubit.CubitTable(n, seg_bits=32768)
+    t.upload_column(1, col)
+    ix = t.create_index(8)
+    t.build_index(ix, 1, 0)
+    d = np.unique(rng.integers(0, n, 20_000))
+    base = oracle.decode(oracle.merge([[bv[2], bv[5]]]))
+    flipped = oracle.decode(oracle.merge([[bv[2], bv[5]]], [[oracle.delta_from_rows(d, n), None]]))
+    assert len(base) != len(flipped)
+    states = {digest(base), digest(flipped)}
+    stop = threading.Event()
+    errors = []
+
+    def writer():
+        try:
+            i = 0
+            while not stop.is_set():
+                t.set_delta(ix, 2, d if i % 2 == 0 else np.zeros(0, dtype=np.int64))
+                i += 1
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    def reader():
+        try:
+            for _ in range(40):
+                with t.query([[(ix, 2), (ix, 5)]], flags=cubit.Q_ROWIDS) as r:
+                    ids, _ = r.fetch()
+                    if digest(ids) not in states:
+                        errors.append("scan saw a state that never existed (%d rows)" % len(ids))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+    w = threading.Thread(target=writer)
+    rs = [threading.Thread(target=reader) for _ in range(3)]
+    w.start()
+    [x.start() for x in rs]
+    [x.join() for x in rs]
+    stop.set()
+    w.join()
+    assert not errors, errors[:3]
+    t.close()
+
+
+def test_high_cardinality_index_build(cubit):
+    """cardinality above one shared-memory tile (400 values per pass) → multi-pass GPU index build;
+    values outside the indexed domain are ignored (NULL-like)"""
+    n, card = 300_011, 1000
+    rng = np.random.default_rng(31)
+    col = rng.integers(-50, card + 50, n).astype(np.int64)
+    bv = oracle.build_index(col, 0, card)
+    t = cubit.CubitTable(n, seg_bits=32768)
+    t.upload_column(0, col)
+    ix = t.create_index(card)
+    t.build_index(ix, 0, 0)
+    for v in (0, 1, 399, 400, 401, 799, 800, 999):
+        assert np.array_equal(t.download_bitvector(ix, v), bv[v]), v
+    assert sum(t.bitvector_count(ix, v) for v in range(card)) == int(((col >= 0) & (col < card)).sum())
+    want = oracle.decode(oracle.merge([[bv[v] for v in range(380, 420)]]))
+    with t.query([[(ix, v) for v in range(380, 420)]], flags=cubit.Q_ROWIDS) as r:
+        assert np.array_equal(r.fetch()[0], want)
+    t.close()

@@ -196,37 +196,40 @@ __global__ void __launch_bounds__(kBuildThreads)
 	extern __shared__ uint32_t tile[]; // [v_n][kBuildSlots]
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint64_t n_tiles = (n_rows + kBuildRows - 1) / kBuildRows;
+	constexpr int kIters = kBuildSlots / (kBuildThreads / 32); // 32-row slots per warp per tile
 	for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-		for (uint32_t i = threadIdx.x; i < v_n * kBuildSlots; i += kBuildThreads) {
-			tile[i] = 0;
+		const uint64_t row0 = t * kBuildRows;
+		// all of this warp's column loads first (kIters independent 128-byte requests in flight),
+		// overlapped with zeroing the tile
+		long long rel[kIters];
+#pragma unroll
+		for (int it = 0; it < kIters; it++) {
+			const uint64_t r = row0 + (uint64_t)(it * (kBuildThreads / 32) + warp) * 32 + lane;
+			rel[it] = r < n_rows ? (long long)__ldcs(col + r) - base_value - (long long)v_lo : -1;
+		}
+		for (uint32_t i = threadIdx.x; i < v_n * (kBuildSlots / 4); i += kBuildThreads) {
+			reinterpret_cast<uint4 *>(tile)[i] = make_uint4(0, 0, 0, 0);
 		}
 		__syncthreads();
-		const uint64_t row0 = t * kBuildRows;
-#pragma unroll 4
-		for (int it = 0; it < kBuildSlots / (kBuildThreads / 32); it++) {
+#pragma unroll
+		for (int it = 0; it < kIters; it++) {
 			const int slot = it * (kBuildThreads / 32) + warp;
-			const uint64_t r = row0 + (uint64_t)slot * 32 + lane;
-			long long rel = -1;
-			if (r < n_rows) {
-				rel = (long long)col[r] - base_value - (long long)v_lo;
-			}
-			const bool in = rel >= 0 && rel < (long long)v_n;
-			const unsigned key = in ? (unsigned)rel : 0xffffffffu;
+			const bool in = rel[it] >= 0 && rel[it] < (long long)v_n;
+			const unsigned key = in ? (unsigned)rel[it] : 0xffffffffu;
 			const unsigned same = __match_any_sync(0xffffffffu, key);
 			if (in && (__ffs(same) - 1) == lane) {
-				tile[(uint32_t)rel * kBuildSlots + slot] = same;
+				tile[(uint32_t)rel[it] * kBuildSlots + slot] = same;
 			}
 		}
 		__syncthreads();
 		// flush: per value kBuildSlots u32 = kBuildRows/64 u64 words, contiguous in B_v
 		const uint64_t word0 = row0 / 64;
-		constexpr int kWordsPerVal = kBuildRows / 64;
-		for (uint32_t i = threadIdx.x; i < v_n * kWordsPerVal; i += kBuildThreads) {
-			const uint32_t v = i / kWordsPerVal, w = i % kWordsPerVal;
-			if (word0 + w < words_per_bv) {
-				const uint64_t val = (uint64_t)tile[v * kBuildSlots + 2 * w] |
-				                     ((uint64_t)tile[v * kBuildSlots + 2 * w + 1] << 32);
-				bitvectors[(uint64_t)(v_lo + v) * words_per_bv + word0 + w] = val;
+		constexpr int kPairsPerVal = kBuildRows / 128; // 16-byte (two-word) pieces per value
+		for (uint32_t i = threadIdx.x; i < v_n * kPairsPerVal; i += kBuildThreads) {
+			const uint32_t v = i / kPairsPerVal, p = i % kPairsPerVal;
+			if (word0 + 2 * p < words_per_bv) {
+				const uint4 x = reinterpret_cast<const uint4 *>(tile)[v * (kBuildSlots / 4) + p];
+				__stcs(reinterpret_cast<uint4 *>(bitvectors + (uint64_t)(v_lo + v) * words_per_bv + word0 + 2 * p), x);
 			}
 		}
 		__syncthreads();

@@ -47,3 +47,51 @@ def allreduce_aggregate(count, total, dist=None, device=None):
     t = torch.tensor(to_limbs(count, total), dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return from_limbs(t.tolist())
+
+
+class _DeviceArray:
+    """zero-copy view of a device buffer owned by the library (CUDA array interface v2)"""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def result_rowids_tensor(result, device):
+    """the result's row-ID list as a torch tensor on `device` WITHOUT a copy (valid until result.free())"""
+    import torch
+    n = result.count
+    ptr = result.info.d_rowids
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype=torch.int64, device=device)
+    return torch.as_tensor(_DeviceArray(ptr, n, "<i8"), device=device)
+
+
+def gather_sorted(local, dist, dst=0):
+    """Gather every rank's sorted row-ID tensor on rank `dst` (north_star: "per-shard row-ID lists are
+    concatenated with shard offsets"; NCCL point-to-point over NVLink when the tensors are on GPUs).
+    Shards are contiguous row ranges in rank order and their row IDs are already global, so plain
+    concatenation in rank order IS the globally sorted list.  Returns the full tensor on dst, None elsewhere."""
+    import torch
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    counts = torch.zeros(world, dtype=torch.int64, device=local.device)
+    counts[rank] = local.numel()
+    dist.all_reduce(counts)  # an all-gather of the per-shard counts
+    counts = counts.tolist()
+    if rank == dst:
+        out = torch.empty(sum(counts), dtype=local.dtype, device=local.device)
+        off = [0]
+        for c in counts:
+            off.append(off[-1] + c)
+        out[off[rank]:off[rank + 1]] = local
+        ops = [dist.P2POp(dist.irecv, out[off[r]:off[r + 1]], r) for r in range(world) if r != dst and counts[r]]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return out
+    if local.numel():
+        for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, local.contiguous(), dst)]):
+            req.wait()
+    return None

@@ -511,3 +511,25 @@ def test_high_cardinality_index_build(cubit):
     with t.query([[(ix, v) for v in range(380, 420)]], flags=cubit.Q_ROWIDS) as r:
         assert np.array_equal(r.fetch()[0], want)
     t.close()
+
+
+def test_zero_copy_rowid_tensor(cubit):
+    """sharding.result_rowids_tensor: the device-resident row-ID list as a torch tensor without a copy
+    (what the multi-GPU result gather sends over NCCL)"""
+    import importlib
+    import torch
+    sharding = importlib.import_module("duckdb-cubit_b200.sharding")
+    n = 500_003
+    rng = np.random.default_rng(41)
+    col = rng.integers(0, 6, n).astype(np.int32)
+    t = cubit.CubitTable(n, row_base=65536)
+    t.upload_column(1, col)
+    ix = t.create_index(6)
+    t.build_index(ix, 1, 0)
+    with t.query([[(ix, 2), (ix, 4)]], flags=cubit.Q_ROWIDS) as r:
+        ids, _ = r.fetch()
+        ten = sharding.result_rowids_tensor(r, torch.device("cuda", 0))
+        assert ten.data_ptr() == r.info.d_rowids and ten.numel() == r.count
+        assert np.array_equal(ten.cpu().numpy(), ids)
+        assert sharding.gather_sorted(ten, None) is ten
+    t.close()

@@ -30,6 +30,12 @@ def _worker(rank, world, port, n_rows, seg_bits, out_dir):
     vals = oracle.probe(ids, pay, row_base=lo)
     cnt, tot = sharding.allreduce_aggregate(len(ids), oracle.sum_i64(vals), dist)
     np.save(os.path.join(out_dir, "ids_%d.npy" % rank), ids)
+    import torch
+    full = sharding.gather_sorted(torch.from_numpy(ids), dist, dst=0)   # result gather (send/recv)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "gathered.npy"), full.numpy())
+    else:
+        assert full is None
     if rank == 0:
         np.save(os.path.join(out_dir, "agg.npy"), np.array([cnt, tot >> 64, tot & ((1 << 64) - 1)], dtype=object),
                 allow_pickle=True)
@@ -52,6 +58,7 @@ def test_two_rank_shards_equal_single_table(tmp_path, n_rows, seg_bits):
     want = oracle.decode(oracle.merge([[bv[v] for v in range(10, 20)]]))
     got = np.concatenate([np.load(os.path.join(tmp_path, "ids_%d.npy" % r)) for r in range(world)])
     assert np.array_equal(got, want)  # concatenation in rank order is globally sorted
+    assert np.array_equal(np.load(os.path.join(tmp_path, "gathered.npy")), want)  # gathered over the process group
     agg = np.load(os.path.join(tmp_path, "agg.npy"), allow_pickle=True)
     total = (int(agg[1]) << 64) + int(agg[2])
     assert int(agg[0]) == len(want) and total == oracle.sum_i64(pay[want])

@@ -32,7 +32,8 @@ ABI_SYMBOLS = [
     "cubit_gpu_destroy", "cubit_gpu_set_stream", "cubit_gpu_words_per_bitvector", "cubit_gpu_launch_count",
     "cubit_gpu_index_create", "cubit_gpu_upload_bitvector", "cubit_gpu_download_bitvector", "cubit_gpu_index_build",
     "cubit_gpu_bitvector_count", "cubit_gpu_set_delta", "cubit_gpu_merge_deltas", "cubit_gpu_upload_column",
-    "cubit_gpu_download_column", "cubit_gpu_synth_column", "cubit_gpu_drop_column", "cubit_gpu_query",
+    "cubit_gpu_download_column", "cubit_gpu_synth_column", "cubit_gpu_drop_column", "cubit_gpu_pack_column",
+    "cubit_gpu_query",
     "cubit_gpu_result_wait", "cubit_gpu_result_get", "cubit_gpu_fetch", "cubit_gpu_fetch_bitvector",
     "cubit_gpu_free_result", "cubit_gpu_probe",
 ]
@@ -101,6 +102,7 @@ def load_library():
         "cubit_gpu_download_column": ([vp, i32, vp, u32, u64], C.c_int),
         "cubit_gpu_synth_column": ([vp, i32, i32, u64, u64, u32, u32, u32], C.c_int),
         "cubit_gpu_drop_column": ([vp, i32], C.c_int),
+        "cubit_gpu_pack_column": ([vp, i32, C.c_int, P(u64)], C.c_int),
         "cubit_gpu_query": ([vp, P(Query), P(vp)], C.c_int),
         "cubit_gpu_result_wait": ([vp], C.c_int),
         "cubit_gpu_result_get": ([vp, P(ResultInfo)], C.c_int),
@@ -315,6 +317,12 @@ class CubitTable:
     def synth_column(self, col_id, kind, seed=0, threshold=0, card=100, hot_lo=10, hot_n=10):
         _check(self._L.cubit_gpu_synth_column(self._h, col_id, kind, seed, threshold, card, hot_lo, hot_n))
         self._col_dtype[col_id] = np.dtype(np.int64 if kind in (0, 3) else np.int32)
+
+    def pack_column(self, col_id, keep_raw=False):
+        """store an int64 column FOR-bit-packed in HBM (lossless) → resident bytes"""
+        b = C.c_uint64(0)
+        _check(self._L.cubit_gpu_pack_column(self._h, col_id, 1 if keep_raw else 0, C.byref(b)))
+        return b.value
 
     def drop_column(self, col_id):
         _check(self._L.cubit_gpu_drop_column(self._h, col_id))

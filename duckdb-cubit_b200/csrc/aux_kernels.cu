@@ -7,9 +7,11 @@
 //   * cubit_index_build_kernel  per-value bitvectors from a column scan
 //                             (CREATE INDEX analog, plan_create_index.cpp:16-130)
 //   * popcount / delta merge-back / synthetic column generators
+#include "col_ref.cuh"
 #include "kernels.h"
 
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 
 namespace cubit {
@@ -31,12 +33,12 @@ constexpr int kProbePairs = 4; // row-ID pairs per thread per iteration (8 indep
 __device__ __forceinline__ void agg_row(const ProbeArgs &a, int64_t local, unsigned long long &lo, long long &hi,
                                         unsigned int &ovf, double &fsum) {
 	if (a.agg_kind == 3) {
-		fsum += __longlong_as_double(__ldg(a.agg_a + local));
+		fsum += __longlong_as_double(load_col(a.agg_a, local));
 	} else if (a.agg_kind == 1) {
-		add128(lo, hi, __ldg(a.agg_a + local));
+		add128(lo, hi, load_col(a.agg_a, local));
 	} else if (a.agg_kind == 2) {
-		const long long x = __ldg(a.agg_a + local);
-		const long long y = __ldg(a.agg_b + local);
+		const long long x = load_col(a.agg_a, local);
+		const long long y = load_col(a.agg_b, local);
 		const long long pr = x * y;
 		if (__mul64hi(x, y) != (pr >> 63)) {
 			ovf = 1;
@@ -72,7 +74,10 @@ __global__ void __launch_bounds__(kProbeThreads) cubit_probe_kernel(const __grid
 				for (int u = 0; u < kProbePairs; u++) {
 					if (ok[u]) {
 						const int64_t l0 = id[u].x - a.row_base, l1 = id[u].y - a.row_base;
-						if (l1 == l0 + 1 && (l0 & 1) == 0) { // dense aligned run: one 128-bit load
+						if (!col) { // bit-packed column
+							v[u].x = load_col(a.packed[c], l0);
+							v[u].y = load_col(a.packed[c], l1);
+						} else if (l1 == l0 + 1 && (l0 & 1) == 0) { // dense aligned run: one 128-bit load
 							v[u] = __ldg(reinterpret_cast<const longlong2 *>(col + l0));
 						} else {
 							v[u].x = __ldg(col + l0);
@@ -121,7 +126,8 @@ __global__ void __launch_bounds__(kProbeThreads) cubit_probe_kernel(const __grid
 		const int64_t l = a.ids[n - 1] - a.row_base;
 		for (int c = 0; c < a.n_cols; c++) {
 			if (a.elem_bytes[c] == 8) {
-				static_cast<long long *>(a.out[c])[n - 1] = static_cast<const long long *>(a.col[c])[l];
+				static_cast<long long *>(a.out[c])[n - 1] =
+				    a.col[c] ? static_cast<const long long *>(a.col[c])[l] : load_col(a.packed[c], l);
 			} else {
 				static_cast<int *>(a.out[c])[n - 1] = static_cast<const int *>(a.col[c])[l];
 			}
@@ -354,6 +360,85 @@ cudaError_t launch_apply_delta(uint64_t *bv, const uint32_t *doff, const DeltaEn
 		grid = 1;
 	}
 	cubit_apply_delta_kernel<<<grid, 64, 0, stream>>>(bv, doff, dent, n_seg, seg_words);
+	return cudaGetLastError();
+}
+
+// ------------------------------------------------------- FOR bit-packing
+// pass 1: per block of kPackBlock rows, min and the bit width of (max - min)
+__global__ void __launch_bounds__(256) cubit_pack_widths_kernel(const long long *__restrict__ col, uint64_t n_rows,
+                                                                long long *__restrict__ base_out,
+                                                                uint32_t *__restrict__ width_out) {
+	__shared__ long long smin[8], smax[8];
+	const uint64_t blk = blockIdx.x;
+	long long mn = LLONG_MAX, mx = LLONG_MIN;
+	for (int i = threadIdx.x; i < kPackBlock; i += 256) {
+		const uint64_t r = blk * kPackBlock + i;
+		if (r < n_rows) {
+			const long long v = col[r];
+			mn = v < mn ? v : mn;
+			mx = v > mx ? v : mx;
+		}
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		const long long a = __shfl_xor_sync(0xffffffffu, mn, d), b = __shfl_xor_sync(0xffffffffu, mx, d);
+		mn = a < mn ? a : mn;
+		mx = b > mx ? b : mx;
+	}
+	if ((threadIdx.x & 31) == 0) {
+		smin[threadIdx.x >> 5] = mn;
+		smax[threadIdx.x >> 5] = mx;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int w = 1; w < 8; w++) {
+			mn = smin[w] < mn ? smin[w] : mn;
+			mx = smax[w] > mx ? smax[w] : mx;
+		}
+		const unsigned long long range = (unsigned long long)mx - (unsigned long long)mn; // exact in 64 bits
+		base_out[blk] = mn;
+		width_out[blk] = range ? 64u - (uint32_t)__clzll((long long)range) : 0u;
+	}
+}
+
+// pass 2: one CTA packs one block; thread w assembles payload word w from the staged (value - base)
+__global__ void __launch_bounds__(256) cubit_pack_blocks_kernel(const long long *__restrict__ col, uint64_t n_rows,
+                                                                const PackHdr *__restrict__ hdr,
+                                                                unsigned long long *__restrict__ words) {
+	__shared__ unsigned long long rel[kPackBlock];
+	const uint64_t blk = blockIdx.x;
+	const PackHdr h = hdr[blk];
+	for (int i = threadIdx.x; i < kPackBlock; i += 256) {
+		const uint64_t r = blk * kPackBlock + i;
+		rel[i] = r < n_rows ? (unsigned long long)col[r] - (unsigned long long)h.base : 0ull;
+	}
+	__syncthreads();
+	const uint32_t width = h.width, n_words = 16u * width; // 1024 * width / 64
+	for (uint32_t w = threadIdx.x; w < n_words; w += 256) {
+		unsigned long long out = 0;
+		const uint32_t bit0 = w * 64u;
+		uint32_t i = bit0 / width; // first value overlapping this word
+		while (i < (uint32_t)kPackBlock && i * width < bit0 + 64u) {
+			const uint32_t vb = i * width;
+			const unsigned long long v = rel[i];
+			out |= vb >= bit0 ? v << (vb - bit0) : v >> (bit0 - vb);
+			i++;
+		}
+		words[h.word_off + w] = out;
+	}
+}
+
+cudaError_t launch_pack_widths(const long long *col, uint64_t n_rows, long long *base_out, uint32_t *width_out,
+                               cudaStream_t stream) {
+	const uint64_t blocks = (n_rows + kPackBlock - 1) / kPackBlock;
+	cubit_pack_widths_kernel<<<(unsigned)blocks, 256, 0, stream>>>(col, n_rows, base_out, width_out);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_pack_blocks(const long long *col, uint64_t n_rows, const PackHdr *hdr, unsigned long long *words,
+                               cudaStream_t stream) {
+	const uint64_t blocks = (n_rows + kPackBlock - 1) / kPackBlock;
+	cubit_pack_blocks_kernel<<<(unsigned)blocks, 256, 0, stream>>>(col, n_rows, hdr, words);
 	return cudaGetLastError();
 }
 

@@ -62,10 +62,49 @@ struct Index {
 };
 
 struct Column {
-	void *d = nullptr;
+	void *d = nullptr; // raw array (may be dropped once packed)
 	uint32_t elem = 0;
 	uint64_t n = 0;
+	// FOR-bit-packed form of an 8-byte column (kernels.h: ColRef)
+	unsigned long long *d_words = nullptr;
+	PackHdr *d_hdr = nullptr;
+	uint64_t packed_bytes = 0;
+	bool packed() const {
+		return d_words != nullptr;
+	}
 };
+
+// Which form of the column a probe reads.  Packed costs fewer bytes but ~2x the instructions per value:
+// measured (profiles/r1_experiment_packed_payload.log) it wins while the selection is sparse enough for the
+// probe to be DRAM-bound (< ~1/6 of the rows) and loses when dense, where the decode becomes issue-bound.
+static ColRef col_ref(const Column *c, bool dense = false) {
+	ColRef r;
+	r.raw = nullptr;
+	r.words = nullptr;
+	r.hdr = nullptr;
+	if (c) {
+		if (c->packed() && !(dense && c->d)) {
+			r.words = c->d_words;
+			r.hdr = c->d_hdr;
+		} else {
+			r.raw = static_cast<const long long *>(c->d);
+		}
+	}
+	return r;
+}
+
+static void free_column(Column &c) {
+	if (c.d) {
+		cudaFree(c.d);
+	}
+	if (c.d_words) {
+		cudaFree(c.d_words);
+	}
+	if (c.d_hdr) {
+		cudaFree(c.d_hdr);
+	}
+	c = Column();
+}
 
 struct cubit_gpu_table {
 	int device = 0;
@@ -238,9 +277,7 @@ extern "C" int cubit_gpu_destroy(cubit_gpu_table *t) {
 		delete ix;
 	}
 	for (auto &kv : t->columns) {
-		if (kv.second.d) {
-			cudaFree(kv.second.d);
-		}
+		free_column(kv.second);
 	}
 	if (t->d_scratch) {
 		cudaFree(t->d_scratch);
@@ -437,6 +474,9 @@ extern "C" int cubit_gpu_index_build(cubit_gpu_table *t, int32_t index_id, int32
 		return fail(CUBIT_EINVAL, "no column %d", col_id);
 	}
 	const Column &c = it->second;
+	if (!c.d) {
+		return fail(CUBIT_ESTATE, "column %d is resident only in packed form; build the index before packing", col_id);
+	}
 	if (c.n != t->n_rows) {
 		return fail(CUBIT_EINVAL, "column %d has %llu rows, table has %llu", col_id, (unsigned long long)c.n,
 		            (unsigned long long)t->n_rows);
@@ -569,10 +609,9 @@ extern "C" int cubit_gpu_upload_column(cubit_gpu_table *t, int32_t col_id, const
 		return CUBIT_ECUDA;
 	}
 	Column &c = t->columns[col_id];
-	if (c.d && (c.elem != elem_bytes || c.n != n)) {
+	if (c.packed() || (c.d && (c.elem != elem_bytes || c.n != n))) {
 		CU_TRY(cudaStreamSynchronize(t->stream));
-		cudaFree(c.d);
-		c.d = nullptr;
+		free_column(c);
 	}
 	if (!c.d) {
 		// + 16 bytes so a 128-bit load of the last aligned pair never leaves the allocation
@@ -601,8 +640,36 @@ extern "C" int cubit_gpu_download_column(cubit_gpu_table *t, int32_t col_id, voi
 	if (it->second.elem != elem_bytes || n > it->second.n) {
 		return fail(CUBIT_EINVAL, "column %d shape mismatch", col_id);
 	}
-	CU_TRY(cudaMemcpyAsync(data, it->second.d, (size_t)n * elem_bytes, cudaMemcpyDeviceToHost, t->stream));
+	const Column &c = it->second;
+	if (c.d) {
+		CU_TRY(cudaMemcpyAsync(data, c.d, (size_t)n * elem_bytes, cudaMemcpyDeviceToHost, t->stream));
+		CU_TRY(cudaStreamSynchronize(t->stream));
+		return CUBIT_OK;
+	}
+	// only the packed form is resident: fetch it and decode on the host (diagnostic path)
+	const uint64_t n_blk = (c.n + kPackBlock - 1) / kPackBlock;
+	std::vector<PackHdr> hdr(n_blk);
+	std::vector<unsigned long long> words(c.packed_bytes / 8);
+	CU_TRY(cudaMemcpyAsync(hdr.data(), c.d_hdr, n_blk * sizeof(PackHdr), cudaMemcpyDeviceToHost, t->stream));
+	CU_TRY(cudaMemcpyAsync(words.data(), c.d_words, c.packed_bytes, cudaMemcpyDeviceToHost, t->stream));
 	CU_TRY(cudaStreamSynchronize(t->stream));
+	long long *out = static_cast<long long *>(data);
+	for (uint64_t r = 0; r < n; r++) {
+		const PackHdr &h = hdr[r / kPackBlock];
+		unsigned long long v = 0;
+		if (h.width) {
+			const uint64_t bit = (r % kPackBlock) * h.width;
+			const unsigned sh = (unsigned)(bit & 63);
+			v = words[h.word_off + (bit >> 6)] >> sh;
+			if (sh + h.width > 64) {
+				v |= words[h.word_off + (bit >> 6) + 1] << (64 - sh);
+			}
+			if (h.width < 64) {
+				v &= (1ull << h.width) - 1;
+			}
+		}
+		out[r] = h.base + (long long)v;
+	}
 	return CUBIT_OK;
 }
 
@@ -626,10 +693,9 @@ extern "C" int cubit_gpu_synth_column(cubit_gpu_table *t, int32_t col_id, int32_
 	}
 	const uint32_t elem = (kind == 0 || kind == 3) ? 8 : 4;
 	Column &c = t->columns[col_id];
-	if (c.d && (c.elem != elem || c.n != t->n_rows)) {
+	if (c.packed() || (c.d && (c.elem != elem || c.n != t->n_rows))) {
 		CU_TRY(cudaStreamSynchronize(t->stream));
-		cudaFree(c.d);
-		c.d = nullptr;
+		free_column(c);
 	}
 	if (!c.d) {
 		CU_TRY(cudaMalloc(&c.d, (size_t)t->n_rows * elem + 16));
@@ -640,6 +706,73 @@ extern "C" int cubit_gpu_synth_column(cubit_gpu_table *t, int32_t col_id, int32_
 	                           t->stream));
 	t->launches++;
 	CU_TRY(cudaStreamSynchronize(t->stream));
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_pack_column(cubit_gpu_table *t, int32_t col_id, int keep_raw, uint64_t *packed_bytes) {
+	if (!t) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	auto it = t->columns.find(col_id);
+	if (it == t->columns.end()) {
+		return fail(CUBIT_EINVAL, "no column %d", col_id);
+	}
+	Column &c = it->second;
+	if (c.elem != 8) {
+		return fail(CUBIT_EINVAL, "only 8-byte columns can be bit-packed");
+	}
+	if (c.packed()) {
+		if (packed_bytes) {
+			*packed_bytes = c.packed_bytes;
+		}
+		return CUBIT_OK;
+	}
+	const uint64_t n_blk = (c.n + kPackBlock - 1) / kPackBlock;
+	long long *d_base = nullptr;
+	uint32_t *d_width = nullptr;
+	CU_TRY(cudaMalloc(&d_base, n_blk * sizeof(long long)));
+	CU_TRY(cudaMalloc(&d_width, n_blk * sizeof(uint32_t)));
+	CU_TRY(launch_pack_widths(static_cast<const long long *>(c.d), c.n, d_base, d_width, t->stream));
+	t->launches++;
+	std::vector<long long> base(n_blk);
+	std::vector<uint32_t> width(n_blk);
+	CU_TRY(cudaMemcpyAsync(base.data(), d_base, n_blk * sizeof(long long), cudaMemcpyDeviceToHost, t->stream));
+	CU_TRY(cudaMemcpyAsync(width.data(), d_width, n_blk * sizeof(uint32_t), cudaMemcpyDeviceToHost, t->stream));
+	CU_TRY(cudaStreamSynchronize(t->stream));
+	cudaFree(d_base);
+	cudaFree(d_width);
+	std::vector<PackHdr> hdr(n_blk);
+	uint64_t off = 0;
+	for (uint64_t b = 0; b < n_blk; b++) {
+		hdr[b].base = base[b];
+		hdr[b].width = width[b];
+		if (off > 0xffffffffull) {
+			return fail(CUBIT_EINVAL, "packed column exceeds 32 GiB");
+		}
+		hdr[b].word_off = (uint32_t)off;
+		off += 16ull * width[b];
+	}
+	const uint64_t bytes = (off + 2) * 8; // + spare words: the decoder may read one word past a value
+	CU_TRY(cudaMalloc(&c.d_hdr, (n_blk + 16) * sizeof(PackHdr))); // + 16: load_hdrs reads a whole span's headers
+	CU_TRY(cudaMemsetAsync(c.d_hdr + n_blk, 0, 16 * sizeof(PackHdr), t->stream));
+	CU_TRY(cudaMalloc(&c.d_words, bytes));
+	CU_TRY(cudaMemsetAsync(c.d_words + off, 0, 16, t->stream));
+	CU_TRY(cudaMemcpyAsync(c.d_hdr, hdr.data(), n_blk * sizeof(PackHdr), cudaMemcpyHostToDevice, t->stream));
+	CU_TRY(launch_pack_blocks(static_cast<const long long *>(c.d), c.n, c.d_hdr, c.d_words, t->stream));
+	t->launches++;
+	CU_TRY(cudaStreamSynchronize(t->stream));
+	c.packed_bytes = bytes;
+	if (!keep_raw) {
+		cudaFree(c.d);
+		c.d = nullptr;
+	}
+	if (packed_bytes) {
+		*packed_bytes = bytes + n_blk * sizeof(PackHdr);
+	}
 	return CUBIT_OK;
 }
 
@@ -656,7 +789,7 @@ extern "C" int cubit_gpu_drop_column(cubit_gpu_table *t, int32_t col_id) {
 		return fail(CUBIT_EINVAL, "no column %d", col_id);
 	}
 	CU_TRY(cudaStreamSynchronize(t->stream));
-	cudaFree(it->second.d);
+	free_column(it->second);
 	t->columns.erase(it);
 	return CUBIT_OK;
 }
@@ -886,6 +1019,7 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 	//   PROBE_FUSED   inside the scan kernel (CUBIT_Q_FUSE_PROBE): one launch
 	//   PROBE_GATHER  gather kernel over the row-ID list — sparse selections whose row IDs are
 	//                 materialised anyway (< 1/256 of the rows), 4-byte columns, > 2 columns, UNFUSED
+	const bool dense_sel = cap > t->n_rows / 6; // upper bound of the selection (exact for disjoint ORs)
 	enum { PROBE_NONE, PROBE_FUSED, PROBE_BITS, PROBE_GATHER } probe_mode = PROBE_NONE;
 	if (need_probe) {
 		if (!fusable) {
@@ -997,7 +1131,7 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 		if (probe_mode == PROBE_FUSED) {
 			sa.n_load = n_dist;
 			for (int d = 0; d < n_dist; d++) {
-				sa.lcol[d] = static_cast<const long long *>(dist_cols[d]->d);
+				sa.lcol[d] = col_ref(dist_cols[d], dense_sel);
 				sa.lout[d] = dist_out[d] >= 0 && cap ? static_cast<long long *>(r->d_vals[dist_out[d]]) : nullptr;
 			}
 			sa.agg_kind = q->agg_kind;
@@ -1047,7 +1181,7 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 		pb.ids_cap = cap;
 		pb.n_load = n_dist;
 		for (int d = 0; d < n_dist; d++) {
-			pb.lcol[d] = static_cast<const long long *>(dist_cols[d]->d);
+			pb.lcol[d] = col_ref(dist_cols[d], dense_sel);
 			pb.lout[d] = dist_out[d] >= 0 && cap ? static_cast<long long *>(r->d_vals[dist_out[d]]) : nullptr;
 		}
 		pb.agg_kind = q->agg_kind;
@@ -1069,13 +1203,14 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 		pa.row_base = t->row_base;
 		pa.n_cols = want_vals && cap ? (int)q->n_cols : 0;
 		for (int c = 0; c < pa.n_cols; c++) {
-			pa.col[c] = vcols[c]->d;
+			pa.col[c] = vcols[c]->packed() ? nullptr : vcols[c]->d;
+			pa.packed[c] = col_ref(vcols[c]);
 			pa.out[c] = r->d_vals[c];
 			pa.elem_bytes[c] = vcols[c]->elem;
 		}
 		pa.agg_kind = q->agg_kind;
-		pa.agg_a = agg_a ? static_cast<const long long *>(agg_a->d) : nullptr;
-		pa.agg_b = agg_b ? static_cast<const long long *>(agg_b->d) : nullptr;
+		pa.agg_a = col_ref(agg_a);
+		pa.agg_b = col_ref(agg_b);
 		pa.partials = partials;
 		pa.done = probe_done;
 		pa.hdr = r->d_hdr;
@@ -1277,11 +1412,12 @@ extern "C" int cubit_gpu_probe(cubit_gpu_table *t, int32_t col_id, const int64_t
 	pa.n = n;
 	pa.row_base = t->row_base;
 	pa.n_cols = host_out ? 1 : 0;
-	pa.col[0] = c.d;
+	pa.col[0] = c.packed() ? nullptr : c.d;
+	pa.packed[0] = col_ref(&c);
 	pa.out[0] = d_out;
 	pa.elem_bytes[0] = c.elem;
 	pa.agg_kind = want_sum ? CUBIT_AGG_SUM : CUBIT_AGG_NONE;
-	pa.agg_a = static_cast<const long long *>(c.d);
+	pa.agg_a = col_ref(&c);
 	pa.hdr = reinterpret_cast<ResultHeader *>(d_blk);
 	pa.done = reinterpret_cast<unsigned int *>(d_blk + 64);
 	pa.partials = reinterpret_cast<BlockPartial *>(d_blk + 128);

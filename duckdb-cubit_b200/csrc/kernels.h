@@ -21,6 +21,25 @@ struct DeltaEnt {
 	uint64_t mask;
 };
 
+// ---- column storage -----------------------------------------------------------------------------
+// An 8-byte column lives in HBM either raw (int64 per row) or FOR-bit-packed: blocks of kPackBlock rows,
+// each with a 16-byte header {base = min of the block, width = bits of (max - min), word_off = first
+// 64-bit word of the block's payload}.  Value i of a block sits at bit i*width of that payload (exactly
+// 16*width words per block).  Lossless; the probe decodes in registers, so a dense probe reads width/8
+// bytes per row instead of 8 (the on-disk BitPacking idea of the reference, src/storage/compression/
+// bitpacking.cpp:22-75, restated with a GPU-friendly fixed block size — not its on-disk layout).
+constexpr int kPackBlock = 1024;
+struct PackHdr {
+	long long base;
+	uint32_t word_off;
+	uint32_t width;
+};
+struct ColRef {
+	const long long *raw;              // raw int64 column, or nullptr when packed
+	const unsigned long long *words;   // packed payload (one spare word at the end)
+	const PackHdr *hdr;                // one header per kPackBlock rows
+};
+
 // Device-side result header (one per query).
 struct ResultHeader {
 	unsigned long long count;
@@ -56,7 +75,7 @@ struct ScanArgs {
 	unsigned long long ids_cap;         // capacity of ids_out / vals_out in rows
 	// fused probe: the distinct int64 columns read at every selected row
 	int n_load;                           // 0..kMaxFusedCols
-	const long long *lcol[kMaxFusedCols]; // column base (local row indexed)
+	ColRef lcol[kMaxFusedCols];           // the columns (local row indexed; raw or bit-packed)
 	long long *lout[kMaxFusedCols];       // gathered values out (same positions as ids_out), or nullptr
 	int agg_kind;                         // CUBIT_AGG_*: SUM(lcol[agg_ia]) / SUM(lcol[agg_ia]*lcol[agg_ib])
 	int agg_ia;
@@ -73,12 +92,13 @@ struct ProbeArgs {
 	unsigned long long n;               // used when count_ptr == nullptr
 	int64_t row_base;
 	int n_cols;
-	const void *col[8];
+	const void *col[8];                 // raw column (4- or 8-byte), or nullptr when packed[c] is used
+	ColRef packed[8];                   // 8-byte columns stored bit-packed
 	void *out[8];
 	uint32_t elem_bytes[8];
 	int agg_kind;
-	const long long *agg_a;
-	const long long *agg_b;
+	ColRef agg_a;
+	ColRef agg_b;
 	BlockPartial *partials;
 	unsigned int *done;                 // blocks-done counter (zeroed)
 	ResultHeader *hdr;                  // count is left untouched; sums written
@@ -108,6 +128,11 @@ cudaError_t launch_popcount_many(const uint64_t *bitvectors, uint64_t words_per_
                                  unsigned long long *out, cudaStream_t stream);
 cudaError_t launch_apply_delta(uint64_t *bv, const uint32_t *doff, const DeltaEnt *dent, uint32_t n_seg,
                                uint32_t seg_words, cudaStream_t stream);
+// FOR-bit-packing of an int64 column (see ColRef): pass 1 per-block min/width, pass 2 pack
+cudaError_t launch_pack_widths(const long long *col, uint64_t n_rows, long long *base_out, uint32_t *width_out,
+                               cudaStream_t stream);
+cudaError_t launch_pack_blocks(const long long *col, uint64_t n_rows, const PackHdr *hdr, unsigned long long *words,
+                               cudaStream_t stream);
 cudaError_t launch_synth_column(void *col, int kind, uint64_t n_rows, int64_t row_base, uint64_t seed,
                                 uint64_t threshold, uint32_t card, uint32_t hot_lo, uint32_t hot_n, int sm_count,
                                 cudaStream_t stream);

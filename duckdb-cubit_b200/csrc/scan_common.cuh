@@ -3,6 +3,7 @@
 // warp's chain-free look-back, and the staged, position-ordered emission (stage_word / write_out /
 // emit_span).  See scan_kernel.cu for the algorithm description and the reference citations.
 #pragma once
+#include "col_ref.cuh"
 #include "kernels.h"
 
 #include <cuda_runtime.h>
@@ -80,26 +81,6 @@ __device__ __forceinline__ void add128(unsigned long long &lo, long long &hi, lo
 __device__ __forceinline__ void add128(unsigned long long &lo, long long &hi, unsigned long long lo2, long long hi2) {
 	lo += lo2;
 	hi += hi2 + (long long)(lo < lo2);
-}
-
-// gather load used by the probe paths (experiment knob: -DCUBIT_GATHER_LD=n)
-#ifndef CUBIT_GATHER_LD
-#define CUBIT_GATHER_LD 0
-#endif
-__device__ __forceinline__ long long gather_ld(const long long *p) {
-#if CUBIT_GATHER_LD == 0
-	return __ldg(p);
-#elif CUBIT_GATHER_LD == 1
-	return __ldcg(p);
-#elif CUBIT_GATHER_LD == 2
-	return __ldcs(p);
-#elif CUBIT_GATHER_LD == 3
-	long long v;
-	asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
-	return v;
-#else
-	return *p;
-#endif
 }
 
 constexpr int kReqSlots = 4;       // look-back requests in flight per CTA (> emission deferral depth)
@@ -231,6 +212,13 @@ __device__ __forceinline__ void write_out(const ScanArgs &a, const uint16_t *cbu
 	const unsigned long long obase = pos0 - pad; // output position of staging index 0 (even)
 	const uint32_t end = pad + count;
 	const uint32_t *cb32 = reinterpret_cast<const uint32_t *>(cbuf);
+	HdrRegs hdrs[NL > 0 ? NL : 1];
+	if (NL > 0) {
+#pragma unroll
+		for (int cc = 0; cc < NL; cc++) {
+			hdrs[cc] = load_hdrs(a.lcol[cc], local0, lane);
+		}
+	}
 	for (uint32_t g0 = 0; g0 * 2 < end; g0 += 64) {
 		uint32_t r[2][2];
 		bool ok[2][2];
@@ -246,11 +234,9 @@ __device__ __forceinline__ void write_out(const ScanArgs &a, const uint16_t *cbu
 			if (NL > 0) {
 #pragma unroll
 				for (int e = 0; e < 2; e++) {
-					if (ok[h][e]) {
 #pragma unroll
-						for (int cc = 0; cc < NL; cc++) {
-							v[h][e][cc] = gather_ld(a.lcol[cc] + (local0 + r[h][e]));
-						}
+					for (int cc = 0; cc < NL; cc++) {
+						v[h][e][cc] = load_col_hoisted(a.lcol[cc], hdrs[cc], local0, r[h][e], ok[h][e]);
 					}
 				}
 			}

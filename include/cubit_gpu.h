@@ -170,6 +170,10 @@ int cubit_gpu_download_column(cubit_gpu_table *t, int32_t col_id, void *data, ui
 int cubit_gpu_synth_column(cubit_gpu_table *t, int32_t col_id, int32_t kind, uint64_t seed, uint64_t threshold,
                            uint32_t card, uint32_t hot_lo, uint32_t hot_n);
 int cubit_gpu_drop_column(cubit_gpu_table *t, int32_t col_id);
+/* Store an 8-byte column FOR-bit-packed in HBM (lossless): blocks of 1024 rows, per block min + bit width of
+ * (max - min).  The probe kernels decode in registers, so a dense probe reads width/8 bytes per row instead of
+ * 8.  keep_raw = 0 frees the raw array (index builds need it: build first).  *packed_bytes = resident size. */
+int cubit_gpu_pack_column(cubit_gpu_table *t, int32_t col_id, int keep_raw, uint64_t *packed_bytes);
 
 /* ---- query --------------------------------------------------------------
  * Synchronous unless CUBIT_Q_ASYNC: on return info fields are final.

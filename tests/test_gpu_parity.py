@@ -533,3 +533,54 @@ def test_zero_copy_rowid_tensor(cubit):
         assert np.array_equal(ten.cpu().numpy(), ids)
         assert sharding.gather_sorted(ten, None) is ten
     t.close()
+
+
+@pytest.mark.parametrize("keep_raw,seg_bits", [(False, 65536), (True, 65536), (False, 131072), (False, 32768)])
+def test_bit_packed_columns_are_lossless_on_every_probe_path(cubit, keep_raw, seg_bits):
+    """cubit_gpu_pack_column: FOR-bit-packed int64 columns decode to exactly the raw values on every probe
+    path (bit-driven, gather over row IDs, in-scan fused, stand-alone probe) for every width 0..64"""
+    n = 1_200_011
+    rng = np.random.default_rng(77)
+    col = rng.integers(0, 12, n).astype(np.int32)
+    # blocks of 1024 rows get different ranges: constant, 1 bit, ..., 63 bits, full 64-bit range, negatives
+    blk = np.arange(n) // 1024
+    width = (blk % 66).astype(np.int64)                       # 0..65 (≥64 → full range)
+    lo = rng.integers(-2**40, 2**40, n // 1024 + 1)[blk]
+    span = np.where(width >= 63, 2**62, (1 << np.minimum(width, 62)))
+    a = lo + (rng.random(n) * span).astype(np.int64)
+    full = width >= 64
+    a[full] = rng.integers(-2**63, 2**63 - 1, int(full.sum()), dtype=np.int64)
+    b = rng.integers(0, 1000, n).astype(np.int64)             # small second column for SUM_PROD
+    b[: 5 * 1024] = 7                                         # constant blocks (width 0)
+    bv = oracle.build_index(col, 0, 12)
+    t = cubit.CubitTable(n, row_base=65536 * 2, seg_bits=seg_bits)
+    t.upload_column(0, a)
+    t.upload_column(1, col)
+    t.upload_column(2, b)
+    ix = t.create_index(12)
+    t.build_index(ix, 1, 0)
+    pa, pb = t.pack_column(0, keep_raw=keep_raw), t.pack_column(2, keep_raw=keep_raw)
+    assert pa < n * 8 and pb < n * 2                          # b needs ≤ 10 bits per value
+    assert np.array_equal(t.download_column(0), a) and np.array_equal(t.download_column(2), b)
+    for vals in ([3], [0, 1, 2, 3, 4, 5, 6, 7], list(range(12))):       # sparse-ish … all rows
+        want = oracle.decode(oracle.merge([[bv[v] for v in vals]]), 65536 * 2)
+        wa, wb = oracle.probe(want, a, 65536 * 2), oracle.probe(want, b, 65536 * 2)
+        for extra in (0, cubit.Q_UNFUSED, cubit.Q_FUSE_PROBE):
+            with t.query([[(ix, v) for v in vals]], flags=cubit.Q_ROWIDS | cubit.Q_VALUES | extra, cols=[0, 2],
+                         agg=cubit.AGG_SUM, agg_a=0) as r:
+                ids, (ga, gb) = r.fetch()
+                assert np.array_equal(ids, want) and np.array_equal(ga, wa) and np.array_equal(gb, wb)
+                assert r.sum == oracle.sum_i64(wa)
+            with t.query([[(ix, v) for v in vals]], flags=extra, agg=cubit.AGG_SUM_PROD, agg_a=2, agg_b=2) as r:
+                sp, ovf = oracle.sum_prod_i64(wb, wb)
+                assert not ovf and r.sum == sp
+    some = np.sort(rng.choice(n, 5001, replace=False)) + 65536 * 2
+    got, s = t.probe(0, some, want_sum=True)
+    assert np.array_equal(got, a[some - 65536 * 2]) and s == oracle.sum_i64(got)
+    with pytest.raises(cubit.CubitError):
+        t.pack_column(1)                                      # 4-byte columns are not packed
+    if not keep_raw:
+        with pytest.raises(cubit.CubitError):
+            ix2 = t.create_index(4)
+            t.build_index(ix2, 2, 0)                          # raw form gone: build first, then pack
+    t.close()

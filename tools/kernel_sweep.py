@@ -22,10 +22,14 @@ def main():
     ap.add_argument("--seg-bits", type=int, default=65536)
     ap.add_argument("--only", default="")
     ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--pack", action="store_true", help="store the payload column FOR-bit-packed")
+    ap.add_argument("--keep-raw", action="store_true", help="with --pack: keep the raw column too (hybrid)")
     args = ap.parse_args()
     cubit = importlib.import_module("duckdb-cubit_b200")
     t = cubit.CubitTable(args.rows, seg_bits=args.seg_bits)
     t.synth_column(0, 0)
+    if args.pack:
+        print(json.dumps({"packed_payload_bytes": t.pack_column(0, keep_raw=args.keep_raw)}), flush=True)
     variants = {
         "count": dict(flags=0),
         "bitvector": dict(flags=cubit.Q_BITVECTOR),

@@ -33,6 +33,7 @@ ABI_SYMBOLS = [
     "cubit_gpu_index_create", "cubit_gpu_upload_bitvector", "cubit_gpu_download_bitvector", "cubit_gpu_index_build",
     "cubit_gpu_bitvector_count", "cubit_gpu_set_delta", "cubit_gpu_merge_deltas", "cubit_gpu_upload_column",
     "cubit_gpu_download_column", "cubit_gpu_synth_column", "cubit_gpu_drop_column", "cubit_gpu_pack_column",
+    "cubit_gpu_upload_column_segments", "cubit_gpu_append_rows",
     "cubit_gpu_query",
     "cubit_gpu_result_wait", "cubit_gpu_result_get", "cubit_gpu_fetch", "cubit_gpu_fetch_bitvector",
     "cubit_gpu_free_result", "cubit_gpu_probe",
@@ -60,6 +61,23 @@ class ResultInfo(C.Structure):
                 ("ms_probe", C.c_float), ("ms_total", C.c_float), ("fused", C.c_uint32),
                 ("d_rowids", C.c_void_p), ("d_bitvector", C.c_void_p), ("d_values", C.c_void_p * MAX_PROBE_COLS),
                 ("sum_f64", C.c_double)]
+
+
+class ColumnSegment(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("reserved", C.c_uint32), ("row_start", C.c_uint64), ("count", C.c_uint64),
+                ("data", C.c_void_p), ("bytes", C.c_uint64)]
+
+
+class AppendColumn(C.Structure):
+    _fields_ = [("col_id", C.c_int32), ("elem_bytes", C.c_uint32), ("data", C.c_void_p)]
+
+
+class DecodeInfo(C.Structure):
+    _fields_ = [("h2d_bytes", C.c_uint64), ("n_groups", C.c_uint64), ("mode_groups", C.c_uint64 * 6),
+                ("n_launches", C.c_uint32), ("ms_decode", C.c_float)]
+
+
+SEG_UNCOMPRESSED, SEG_BITPACKING, SEG_CONSTANT = 0, 1, 2
 
 
 class CubitError(RuntimeError):
@@ -103,6 +121,8 @@ def load_library():
         "cubit_gpu_synth_column": ([vp, i32, i32, u64, u64, u32, u32, u32], C.c_int),
         "cubit_gpu_drop_column": ([vp, i32], C.c_int),
         "cubit_gpu_pack_column": ([vp, i32, C.c_int, P(u64)], C.c_int),
+        "cubit_gpu_append_rows": ([vp, u64, P(AppendColumn), u32], C.c_int),
+        "cubit_gpu_upload_column_segments": ([vp, i32, u32, P(ColumnSegment), u32, P(DecodeInfo)], C.c_int),
         "cubit_gpu_query": ([vp, P(Query), P(vp)], C.c_int),
         "cubit_gpu_result_wait": ([vp], C.c_int),
         "cubit_gpu_result_get": ([vp, P(ResultInfo)], C.c_int),
@@ -307,6 +327,35 @@ class CubitTable:
             raise ValueError("columns are 4 or 8 bytes wide")
         _check(self._L.cubit_gpu_upload_column(self._h, col_id, data.ctypes.data, data.dtype.itemsize, len(data)))
         self._col_dtype[col_id] = data.dtype
+
+    def upload_column_segments(self, col_id, elem_bytes, segments):
+        """upload a column as the reference's on-disk segments [(kind, row_start, count, uint8 array)] and decode
+        them on the GPU → DecodeInfo"""
+        arr = (ColumnSegment * max(1, len(segments)))()
+        keep = []
+        for i, (kind, start, count, data) in enumerate(segments):
+            data = np.ascontiguousarray(data).view(np.uint8)
+            keep.append(data)
+            arr[i] = ColumnSegment(kind, 0, start, count, data.ctypes.data, data.size)
+        info = DecodeInfo()
+        _check(self._L.cubit_gpu_upload_column_segments(self._h, col_id, elem_bytes, arr, len(segments), C.byref(info)))
+        self._col_dtype[col_id] = np.dtype(np.int64 if elem_bytes == 8 else np.int32)
+        return info
+
+    def append_rows(self, columns):
+        """INSERT: append rows at the end of the shard; columns = {col_id: array of the new rows' values}"""
+        arrs = {c: np.ascontiguousarray(a) for c, a in columns.items()}
+        n_new = len(next(iter(arrs.values()))) if arrs else 0
+        arr = (AppendColumn * max(1, len(arrs)))()
+        for i, (c, a) in enumerate(arrs.items()):
+            if len(a) != n_new:
+                raise ValueError("append columns differ in length")
+            arr[i] = AppendColumn(c, a.dtype.itemsize, a.ctypes.data)
+        _check(self._L.cubit_gpu_append_rows(self._h, n_new, arr, len(arrs)))
+        self.n_rows += n_new
+        n = C.c_uint64(0)
+        _check(self._L.cubit_gpu_words_per_bitvector(self._h, C.byref(n)))
+        self.n_words = n.value
 
     def download_column(self, col_id):
         dt = self._col_dtype[col_id]

@@ -197,13 +197,14 @@ constexpr int kBuildSlots = kBuildRows / 32; // u32 slots per value per tile
 
 template <typename T>
 __global__ void __launch_bounds__(kBuildThreads)
-    cubit_index_build_kernel(const T *__restrict__ col, uint64_t n_rows, int64_t base_value, uint32_t v_lo,
-                             uint32_t v_n, uint64_t *__restrict__ bitvectors, uint64_t words_per_bv) {
+    cubit_index_build_kernel(const T *__restrict__ col, uint64_t row_begin, uint64_t n_rows, int64_t base_value,
+                             uint32_t v_lo, uint32_t v_n, uint64_t *__restrict__ bitvectors, uint64_t words_per_bv) {
 	extern __shared__ uint32_t tile[]; // [v_n][kBuildSlots]
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint64_t n_tiles = (n_rows + kBuildRows - 1) / kBuildRows;
 	constexpr int kIters = kBuildSlots / (kBuildThreads / 32); // 32-row slots per warp per tile
-	for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+	// rows below row_begin are already indexed (append path): their bits are kept as they are
+	for (uint64_t t = row_begin / kBuildRows + blockIdx.x; t < n_tiles; t += gridDim.x) {
 		const uint64_t row0 = t * kBuildRows;
 		// all of this warp's column loads first (kIters independent 128-byte requests in flight),
 		// overlapped with zeroing the tile
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(kBuildThreads)
 #pragma unroll
 		for (int it = 0; it < kIters; it++) {
 			const uint64_t r = row0 + (uint64_t)(it * (kBuildThreads / 32) + warp) * 32 + lane;
-			rel[it] = r < n_rows ? (long long)__ldcs(col + r) - base_value - (long long)v_lo : -1;
+			rel[it] = (r >= row_begin && r < n_rows) ? (long long)__ldcs(col + r) - base_value - (long long)v_lo : -1;
 		}
 		for (uint32_t i = threadIdx.x; i < v_n * (kBuildSlots / 4); i += kBuildThreads) {
 			reinterpret_cast<uint4 *>(tile)[i] = make_uint4(0, 0, 0, 0);
@@ -234,15 +235,28 @@ __global__ void __launch_bounds__(kBuildThreads)
 		for (uint32_t i = threadIdx.x; i < v_n * kPairsPerVal; i += kBuildThreads) {
 			const uint32_t v = i / kPairsPerVal, p = i % kPairsPerVal;
 			if (word0 + 2 * p < words_per_bv) {
-				const uint4 x = reinterpret_cast<const uint4 *>(tile)[v * (kBuildSlots / 4) + p];
-				__stcs(reinterpret_cast<uint4 *>(bitvectors + (uint64_t)(v_lo + v) * words_per_bv + word0 + 2 * p), x);
+				uint4 x = reinterpret_cast<const uint4 *>(tile)[v * (kBuildSlots / 4) + p];
+				uint4 *dst = reinterpret_cast<uint4 *>(bitvectors + (uint64_t)(v_lo + v) * words_per_bv + word0 + 2 * p);
+				const uint64_t piece_row0 = (word0 + 2 * p) * 64;
+				if (piece_row0 + 128 <= row_begin) {
+					continue; // only rows indexed earlier
+				}
+				if (piece_row0 < row_begin) { // the boundary piece: old rows' bits stay (the tile holds zeros for them)
+					const uint4 old = *dst;
+					x.x |= old.x;
+					x.y |= old.y;
+					x.z |= old.z;
+					x.w |= old.w;
+				}
+				__stcs(dst, x);
 			}
 		}
 		__syncthreads();
 	}
 }
 
-cudaError_t launch_index_build(const void *col, uint32_t elem_bytes, uint64_t n_rows, int64_t base_value,
+cudaError_t launch_index_build(const void *col, uint32_t elem_bytes, uint64_t row_begin, uint64_t n_rows,
+                               int64_t base_value,
                                uint32_t cardinality, uint64_t *bitvectors, uint64_t words_per_bv, int sm_count,
                                cudaStream_t stream, int *n_launches) {
 	// values per pass bounded by shared memory (≤ 200 KiB tile)
@@ -258,7 +272,7 @@ cudaError_t launch_index_build(const void *col, uint32_t elem_bytes, uint64_t n_
 		                     200 * 1024);
 		configured[dev] = true;
 	}
-	const uint64_t n_tiles = (n_rows + kBuildRows - 1) / kBuildRows;
+	const uint64_t n_tiles = (n_rows + kBuildRows - 1) / kBuildRows - row_begin / kBuildRows;
 	for (uint32_t v_lo = 0; v_lo < cardinality; v_lo += max_v) {
 		const uint32_t v_n = (cardinality - v_lo) < max_v ? (cardinality - v_lo) : max_v;
 		const size_t smem = (size_t)v_n * kBuildSlots * 4;
@@ -278,10 +292,11 @@ cudaError_t launch_index_build(const void *col, uint32_t elem_bytes, uint64_t n_
 		}
 		if (elem_bytes == 4) {
 			cubit_index_build_kernel<int><<<(unsigned)grid, kBuildThreads, smem, stream>>>(
-			    static_cast<const int *>(col), n_rows, base_value, v_lo, v_n, bitvectors, words_per_bv);
+			    static_cast<const int *>(col), row_begin, n_rows, base_value, v_lo, v_n, bitvectors, words_per_bv);
 		} else {
 			cubit_index_build_kernel<long long><<<(unsigned)grid, kBuildThreads, smem, stream>>>(
-			    static_cast<const long long *>(col), n_rows, base_value, v_lo, v_n, bitvectors, words_per_bv);
+			    static_cast<const long long *>(col), row_begin, n_rows, base_value, v_lo, v_n, bitvectors,
+			    words_per_bv);
 		}
 		launches++;
 		cudaError_t e = cudaGetLastError();

@@ -58,6 +58,8 @@ struct Index {
 	uint64_t *d_bits = nullptr;   // [card][words_per_bv]
 	std::vector<uint64_t> counts; // popcount of every B_v as stored
 	bool counts_valid = false;
+	int32_t src_col = -1;         // column the index was built from (cubit_gpu_index_build), -1 = uploaded
+	int64_t src_base = 0;
 	std::vector<Delta> deltas; // [card]
 };
 
@@ -65,6 +67,7 @@ struct Column {
 	void *d = nullptr; // raw array (may be dropped once packed)
 	uint32_t elem = 0;
 	uint64_t n = 0;
+	uint64_t cap = 0; // rows allocated (>= n; grows on append)
 	// FOR-bit-packed form of an 8-byte column (kernels.h: ColRef)
 	unsigned long long *d_words = nullptr;
 	PackHdr *d_hdr = nullptr;
@@ -123,7 +126,10 @@ struct cubit_gpu_table {
 	unsigned long long *d_scratch = nullptr; // popcount scratch
 	uint64_t scratch_n = 0;
 	std::vector<ResultHeader *> hdr_pool; // pinned result headers, recycled across queries
+	uint8_t *h_stage[2] = {nullptr, nullptr}; // pinned staging chunks of the segment upload (lazy, kept)
+	cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 };
+constexpr uint64_t kStageChunk = 16ull << 20;
 
 struct cubit_gpu_result {
 	cubit_gpu_table *t = nullptr;
@@ -278,6 +284,14 @@ extern "C" int cubit_gpu_destroy(cubit_gpu_table *t) {
 	}
 	for (auto &kv : t->columns) {
 		free_column(kv.second);
+	}
+	for (int b = 0; b < 2; b++) {
+		if (t->h_stage[b]) {
+			cudaFreeHost(t->h_stage[b]);
+		}
+		if (t->stage_ev[b]) {
+			cudaEventDestroy(t->stage_ev[b]);
+		}
 	}
 	if (t->d_scratch) {
 		cudaFree(t->d_scratch);
@@ -487,11 +501,13 @@ extern "C" int cubit_gpu_index_build(cubit_gpu_table *t, int32_t index_id, int32
 		}
 	}
 	int launches = 0;
-	CU_TRY(launch_index_build(c.d, c.elem, t->n_rows, base_value, ix->card, ix->d_bits, t->words_per_bv, t->sm_count,
-	                          t->stream, &launches));
+	CU_TRY(launch_index_build(c.d, c.elem, 0, t->n_rows, base_value, ix->card, ix->d_bits, t->words_per_bv,
+	                          t->sm_count, t->stream, &launches));
 	t->launches += launches;
 	CU_TRY(cudaStreamSynchronize(t->stream));
 	ix->counts_valid = false;
+	ix->src_col = col_id;
+	ix->src_base = base_value;
 	return CUBIT_OK;
 }
 
@@ -616,11 +632,248 @@ extern "C" int cubit_gpu_upload_column(cubit_gpu_table *t, int32_t col_id, const
 	if (!c.d) {
 		// + 16 bytes so a 128-bit load of the last aligned pair never leaves the allocation
 		CU_TRY(cudaMalloc(&c.d, (size_t)n * elem_bytes + 16));
+		c.cap = n;
 	}
 	c.elem = elem_bytes;
 	c.n = n;
 	CU_TRY(cudaMemcpyAsync(c.d, data, (size_t)n * elem_bytes, cudaMemcpyHostToDevice, t->stream));
 	CU_TRY(cudaStreamSynchronize(t->stream));
+	return CUBIT_OK;
+}
+
+// Decode the reference's on-disk column segments on the GPU (column_decode.cu).  Everything the kernel will
+// dereference is bounds-checked here, on the host copy of the segment, so a malformed segment is an error
+// return and never an out-of-bounds device access.
+extern "C" int cubit_gpu_upload_column_segments(cubit_gpu_table *t, int32_t col_id, uint32_t elem_bytes,
+                                                const cubit_column_segment *segs, uint32_t n_segs,
+                                                cubit_decode_info *info) {
+	if (!t || (!segs && n_segs)) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	if (elem_bytes != 4 && elem_bytes != 8) {
+		return fail(CUBIT_EINVAL, "elem_bytes must be 4 or 8");
+	}
+	auto ld32 = [](const uint8_t *p) {
+		uint32_t v;
+		memcpy(&v, p, 4);
+		return v;
+	};
+	auto ld64 = [](const uint8_t *p) {
+		uint64_t v;
+		memcpy(&v, p, 8);
+		return v;
+	};
+	// ---- plan: validate, lay the segments out in one blob, build the group directory
+	std::vector<BpGroup> groups;
+	std::vector<uint64_t> seg_off(n_segs, 0);
+	cubit_decode_info di;
+	memset(&di, 0, sizeof(di));
+	uint64_t blob_bytes = 0, next_row = 0;
+	for (uint32_t si = 0; si < n_segs; si++) {
+		const cubit_column_segment &sg = segs[si];
+		if (sg.row_start != next_row || sg.count == 0 || !sg.data) {
+			return fail(CUBIT_EINVAL, "segment %u: segments must tile the rows in order (row_start %llu, expected %llu)", si,
+			            (unsigned long long)sg.row_start, (unsigned long long)next_row);
+		}
+		next_row += sg.count;
+		const uint8_t *p = static_cast<const uint8_t *>(sg.data);
+		if (sg.kind == CUBIT_SEG_UNCOMPRESSED) {
+			if (sg.bytes < sg.count * elem_bytes) {
+				return fail(CUBIT_EINVAL, "segment %u: %llu bytes for %llu uncompressed rows", si,
+				            (unsigned long long)sg.bytes, (unsigned long long)sg.count);
+			}
+			continue; // copied straight into the column
+		}
+		seg_off[si] = blob_bytes;
+		if (sg.kind == CUBIT_SEG_CONSTANT) {
+			if (sg.bytes < elem_bytes || sg.count > 0xffffffffull) {
+				return fail(CUBIT_EINVAL, "segment %u: bad constant segment", si);
+			}
+			groups.push_back(BpGroup {blob_bytes, sg.row_start, (uint32_t)sg.count, BP_CONSTANT});
+			di.mode_groups[BP_CONSTANT]++;
+			blob_bytes += 8;
+			continue;
+		}
+		if (sg.kind != CUBIT_SEG_BITPACKING) {
+			return fail(CUBIT_EINVAL, "segment %u: unknown kind %u", si, sg.kind);
+		}
+		const uint64_t n_grp = (sg.count + 2047) / 2048;
+		if (sg.bytes < 12 || (sg.bytes & 3)) {
+			return fail(CUBIT_EINVAL, "segment %u: bad size %llu", si, (unsigned long long)sg.bytes);
+		}
+		const uint64_t meta_end = ld64(p); // BitpackingScanState ctor, bitpacking.cpp:633-636
+		if (meta_end > sg.bytes || (meta_end & 3) || meta_end < 8 + 4 * n_grp) {
+			return fail(CUBIT_EINVAL, "segment %u: metadata end %llu outside the segment (%llu bytes, %llu groups)", si,
+			            (unsigned long long)meta_end, (unsigned long long)sg.bytes, (unsigned long long)n_grp);
+		}
+		const uint64_t data_end = meta_end - 4 * n_grp; // group data lives in [8, data_end)
+		for (uint64_t gi = 0; gi < n_grp; gi++) {
+			const uint32_t enc = ld32(p + meta_end - 4 * (gi + 1)); // DecodeMeta, bitpacking.cpp:68-73
+			const uint32_t mode = enc >> 24, off = enc & 0x00ffffffu;
+			const uint32_t n = (uint32_t)std::min<uint64_t>(2048, sg.count - gi * 2048);
+			uint64_t need; // bytes of the group at `off`
+			if (mode == BP_CONSTANT) {
+				need = elem_bytes;
+			} else if (mode == BP_CONSTANT_DELTA) {
+				need = 2 * elem_bytes;
+			} else if (mode == BP_FOR || mode == BP_DELTA_FOR) {
+				need = (mode == BP_FOR ? 2 : 3) * (uint64_t)elem_bytes;
+				if (off < 8 || (off & 3) || off + need > data_end) {
+					return fail(CUBIT_EINVAL, "segment %u group %llu: header outside the segment", si, (unsigned long long)gi);
+				}
+				const uint32_t width = (uint32_t)(elem_bytes == 8 ? ld64(p + off + 8) : ld32(p + off + 4)) & 0xffu;
+				if (width > elem_bytes * 8) {
+					return fail(CUBIT_EINVAL, "segment %u group %llu: bit width %u", si, (unsigned long long)gi, width);
+				}
+				need += (uint64_t)((n + 31) / 32) * width * 4; // GetRequiredSize, bitpacking.hpp:103-106
+			} else {
+				return fail(CUBIT_EINVAL, "segment %u group %llu: invalid bitpacking mode %u", si, (unsigned long long)gi, mode);
+			}
+			if (off < 8 || (off & 3) || off + need > data_end) {
+				return fail(CUBIT_EINVAL, "segment %u group %llu: data [%u, +%llu) outside the segment", si,
+				            (unsigned long long)gi, off, (unsigned long long)need);
+			}
+			groups.push_back(BpGroup {blob_bytes + off, sg.row_start + gi * 2048, n, mode});
+			di.mode_groups[mode]++;
+		}
+		blob_bytes += (sg.bytes + 7) & ~7ull;
+	}
+	if (next_row != t->n_rows) {
+		return fail(CUBIT_EINVAL, "segments cover %llu rows, table has %llu", (unsigned long long)next_row,
+		            (unsigned long long)t->n_rows);
+	}
+	if (groups.size() > 0x7fffffffull) {
+		return fail(CUBIT_EINVAL, "too many metadata groups");
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	Column &c = t->columns[col_id];
+	if (c.packed() || (c.d && (c.elem != elem_bytes || c.n != t->n_rows))) {
+		CU_TRY(cudaStreamSynchronize(t->stream));
+		free_column(c);
+	}
+	if (!c.d) {
+		CU_TRY(cudaMalloc(&c.d, (size_t)t->n_rows * elem_bytes + 16));
+		c.cap = t->n_rows;
+	}
+	c.elem = elem_bytes;
+	c.n = t->n_rows;
+	// ---- compressed bytes host → device as stored
+	uint8_t *d_blob = nullptr;
+	BpGroup *d_groups = nullptr;
+	auto cleanup = [&]() {
+		if (d_blob) {
+			cudaFree(d_blob);
+		}
+		if (d_groups) {
+			cudaFree(d_groups);
+		}
+	};
+#define CU_TRY_CLEAN(expr)                                                                                             \
+	do {                                                                                                               \
+		cudaError_t _e = (expr);                                                                                       \
+		if (_e != cudaSuccess) {                                                                                       \
+			cleanup();                                                                                                 \
+			return fail(_e == cudaErrorMemoryAllocation ? CUBIT_ENOMEM : CUBIT_ECUDA, "%s: %s (%s:%d)", #expr,         \
+			            cudaGetErrorString(_e), __FILE__, __LINE__);                                                   \
+		}                                                                                                              \
+	} while (0)
+	CU_TRY_CLEAN(cudaMalloc(&d_blob, blob_bytes + 16)); // + 16: the kernel never reads past a group, this is slack
+	CU_TRY_CLEAN(cudaMalloc(&d_groups, (groups.size() + 1) * sizeof(BpGroup)));
+	// Thousands of sub-megabyte segments: gather them into two pinned staging chunks on the host and move each
+	// chunk with ONE async copy (the next chunk is being filled while the previous one is on the wire).
+	const uint64_t chunk = kStageChunk;
+	cudaError_t pe = cudaSuccess;
+	for (int b = 0; b < 2 && pe == cudaSuccess; b++) {
+		if (!t->h_stage[b]) {
+			pe = cudaMallocHost(reinterpret_cast<void **>(&t->h_stage[b]), chunk);
+			if (pe == cudaSuccess) {
+				pe = cudaEventCreateWithFlags(&t->stage_ev[b], cudaEventDisableTiming);
+			}
+		}
+	}
+	CU_TRY_CLEAN(pe);
+	uint8_t *const *stage = t->h_stage;
+	cudaEvent_t *staged = t->stage_ev;
+	auto cleanup_stage = []() {};
+	uint64_t chunk_base = 0; // blob offset of the chunk being filled
+	int cur = 0;
+	bool used[2] = {false, false};
+	auto flush_chunk = [&](uint64_t upto) -> cudaError_t { // send blob bytes [chunk_base, upto)
+		cudaError_t e = cudaSuccess;
+		if (upto > chunk_base) {
+			e = cudaMemcpyAsync(d_blob + chunk_base, stage[cur], upto - chunk_base, cudaMemcpyHostToDevice, t->stream);
+			if (e == cudaSuccess) {
+				e = cudaEventRecord(staged[cur], t->stream);
+			}
+			used[cur] = true;
+			cur ^= 1;
+			if (e == cudaSuccess && used[cur]) {
+				e = cudaEventSynchronize(staged[cur]); // the other chunk must have left the host before it is refilled
+			}
+			chunk_base = upto;
+		}
+		return e;
+	};
+	for (uint32_t si = 0; si < n_segs && pe == cudaSuccess; si++) {
+		const cubit_column_segment &sg = segs[si];
+		if (sg.kind == CUBIT_SEG_UNCOMPRESSED) {
+			pe = cudaMemcpyAsync(static_cast<uint8_t *>(c.d) + sg.row_start * elem_bytes, sg.data, sg.count * elem_bytes,
+			                     cudaMemcpyHostToDevice, t->stream);
+			di.h2d_bytes += sg.count * elem_bytes;
+			continue;
+		}
+		const uint64_t nb = sg.kind == CUBIT_SEG_CONSTANT ? elem_bytes : sg.bytes;
+		const uint8_t *src = static_cast<const uint8_t *>(sg.data);
+		uint64_t done = 0;
+		while (done < nb && pe == cudaSuccess) { // a segment may straddle chunks
+			const uint64_t at = seg_off[si] + done;
+			if (at >= chunk_base + chunk) {
+				pe = flush_chunk(chunk_base + chunk);
+				continue;
+			}
+			const uint64_t take = std::min<uint64_t>(nb - done, chunk_base + chunk - at);
+			memcpy(stage[cur] + (at - chunk_base), src + done, take);
+			done += take;
+		}
+		di.h2d_bytes += nb;
+	}
+	if (pe == cudaSuccess) {
+		pe = flush_chunk(blob_bytes);
+	}
+	if (pe == cudaSuccess) {
+		pe = cudaStreamSynchronize(t->stream); // staging buffers are freed below
+	}
+	cleanup_stage();
+	CU_TRY_CLEAN(pe);
+	CU_TRY_CLEAN(cudaMemcpyAsync(d_groups, groups.data(), groups.size() * sizeof(BpGroup), cudaMemcpyHostToDevice,
+	                             t->stream));
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	CU_TRY_CLEAN(cudaEventCreate(&e0));
+	CU_TRY_CLEAN(cudaEventCreate(&e1));
+	cudaEventRecord(e0, t->stream);
+	cudaError_t le = launch_bp_decode(d_blob, d_groups, (uint32_t)groups.size(), c.d, elem_bytes, t->stream);
+	cudaEventRecord(e1, t->stream);
+	cudaError_t se = cudaStreamSynchronize(t->stream);
+	if (le == cudaSuccess && se == cudaSuccess) {
+		cudaEventElapsedTime(&di.ms_decode, e0, e1);
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	CU_TRY_CLEAN(le);
+	CU_TRY_CLEAN(se);
+#undef CU_TRY_CLEAN
+	cleanup();
+	if (!groups.empty()) {
+		t->launches++;
+		di.n_launches = 1;
+	}
+	di.n_groups = groups.size();
+	if (info) {
+		*info = di;
+	}
 	return CUBIT_OK;
 }
 
@@ -699,6 +952,7 @@ extern "C" int cubit_gpu_synth_column(cubit_gpu_table *t, int32_t col_id, int32_
 	}
 	if (!c.d) {
 		CU_TRY(cudaMalloc(&c.d, (size_t)t->n_rows * elem + 16));
+		c.cap = t->n_rows;
 	}
 	c.elem = elem;
 	c.n = t->n_rows;
@@ -773,6 +1027,132 @@ extern "C" int cubit_gpu_pack_column(cubit_gpu_table *t, int32_t col_id, int kee
 	if (packed_bytes) {
 		*packed_bytes = bytes + n_blk * sizeof(PackHdr);
 	}
+	return CUBIT_OK;
+}
+
+// Append path (INSERT: new rows take the next row ids — DataTable::Append / BoundIndex::Append,
+// src/include/duckdb/execution/index/bound_index.hpp:71-75; rowids are dense positions, row_group.cpp:511-514).
+// Bitvectors are padded to whole segments, so appending inside the last segment touches no allocation; past it
+// every index is re-strided once (capacity grows by half).  Indexes built from a column are extended on the GPU
+// by the index-build kernel over the new rows only.
+extern "C" int cubit_gpu_append_rows(cubit_gpu_table *t, uint64_t n_new, const cubit_append_column *cols,
+                                     uint32_t n_cols) {
+	if (!t || (!cols && n_cols)) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	if (n_new == 0) {
+		return fail(CUBIT_EINVAL, "n_new must be > 0");
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	const uint64_t old_n = t->n_rows, new_n = old_n + n_new;
+	const uint64_t new_n_seg = (new_n + t->seg_bits - 1) / t->seg_bits;
+	if (new_n_seg > 0x7fffffffull) {
+		return fail(CUBIT_EINVAL, "too many segments");
+	}
+	if (n_cols != t->columns.size()) {
+		return fail(CUBIT_EINVAL, "append must supply all %zu resident columns (got %u)", t->columns.size(), n_cols);
+	}
+	for (uint32_t i = 0; i < n_cols; i++) {
+		auto it = t->columns.find(cols[i].col_id);
+		if (it == t->columns.end() || !cols[i].data) {
+			return fail(CUBIT_EINVAL, "append: no resident column %d (or NULL data)", cols[i].col_id);
+		}
+		for (uint32_t j = 0; j < i; j++) {
+			if (cols[j].col_id == cols[i].col_id) {
+				return fail(CUBIT_EINVAL, "append: column %d listed twice", cols[i].col_id);
+			}
+		}
+		if (it->second.elem != cols[i].elem_bytes) {
+			return fail(CUBIT_EINVAL, "append: column %d is %u bytes wide", cols[i].col_id, it->second.elem);
+		}
+		if (it->second.packed()) {
+			return fail(CUBIT_ESTATE, "append: column %d is bit-packed; appends need the raw form", cols[i].col_id);
+		}
+	}
+	CU_TRY(cudaStreamSynchronize(t->stream)); // nothing in flight may still read the old allocations
+	// ---- value bitvectors: re-stride when the new rows leave the padded last segment
+	if (new_n_seg * t->seg_words > t->words_per_bv) {
+		const uint64_t cap_seg = std::max<uint64_t>(new_n_seg, (uint64_t)(t->words_per_bv / t->seg_words) * 3 / 2 + 1);
+		const uint64_t new_stride = cap_seg * t->seg_words;
+		for (Index *ix : t->indexes) {
+			uint64_t *nb = nullptr;
+			const size_t bytes = (size_t)ix->card * new_stride * 8;
+			CU_TRY(cudaMalloc(&nb, bytes));
+			cudaError_t e = cudaMemsetAsync(nb, 0, bytes, t->stream);
+			if (e == cudaSuccess) {
+				e = cudaMemcpy2DAsync(nb, new_stride * 8, ix->d_bits, t->words_per_bv * 8, t->words_per_bv * 8, ix->card,
+				                      cudaMemcpyDeviceToDevice, t->stream);
+			}
+			if (e == cudaSuccess) {
+				e = cudaStreamSynchronize(t->stream);
+			}
+			if (e != cudaSuccess) {
+				cudaFree(nb);
+				CU_TRY(e);
+			}
+			cudaFree(ix->d_bits);
+			ix->d_bits = nb;
+		}
+		t->words_per_bv = new_stride;
+	}
+	// ---- pending-delta CSR offsets cover [0, n_seg]: extend them with empty segments
+	if (new_n_seg > t->n_seg) {
+		for (Index *ix : t->indexes) {
+			for (Delta &d : ix->deltas) {
+				if (!d.d_off) {
+					continue;
+				}
+				std::vector<uint32_t> off((size_t)new_n_seg + 1);
+				CU_TRY(cudaMemcpy(off.data(), d.d_off, ((size_t)t->n_seg + 1) * 4, cudaMemcpyDeviceToHost));
+				for (size_t s = (size_t)t->n_seg + 1; s <= new_n_seg; s++) {
+					off[s] = off[t->n_seg];
+				}
+				uint32_t *no = nullptr;
+				CU_TRY(cudaMalloc(&no, off.size() * 4));
+				CU_TRY(cudaMemcpy(no, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+				cudaFree(d.d_off);
+				d.d_off = no;
+			}
+		}
+	}
+	// ---- columns: grow, then the new rows host → device behind the old ones
+	for (uint32_t i = 0; i < n_cols; i++) {
+		Column &c = t->columns[cols[i].col_id];
+		if (new_n > c.cap) {
+			const uint64_t cap = std::max<uint64_t>(new_n, c.cap + c.cap / 2);
+			void *nd = nullptr;
+			CU_TRY(cudaMalloc(&nd, (size_t)cap * c.elem + 16));
+			CU_TRY(cudaMemcpy(nd, c.d, (size_t)old_n * c.elem, cudaMemcpyDeviceToDevice));
+			cudaFree(c.d);
+			c.d = nd;
+			c.cap = cap;
+		}
+		CU_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(c.d) + (size_t)old_n * c.elem, cols[i].data, (size_t)n_new * c.elem,
+		                       cudaMemcpyHostToDevice, t->stream));
+		c.n = new_n;
+	}
+	t->n_rows = new_n;
+	t->n_seg = (uint32_t)new_n_seg;
+	t->n_words = (new_n + 63) / 64;
+	// ---- indexes built from a column: index the new rows on the GPU
+	for (Index *ix : t->indexes) {
+		ix->counts_valid = false;
+		if (ix->src_col < 0) {
+			continue; // uploaded bitvectors: the new rows' bits are 0 until the caller uploads them
+		}
+		auto it = t->columns.find(ix->src_col);
+		if (it == t->columns.end() || !it->second.d) {
+			continue;
+		}
+		int launches = 0;
+		CU_TRY(launch_index_build(it->second.d, it->second.elem, old_n, new_n, ix->src_base, ix->card, ix->d_bits,
+		                          t->words_per_bv, t->sm_count, t->stream, &launches));
+		t->launches += launches;
+	}
+	CU_TRY(cudaStreamSynchronize(t->stream));
 	return CUBIT_OK;
 }
 

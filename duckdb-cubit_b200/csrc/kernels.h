@@ -40,6 +40,17 @@ struct ColRef {
 	const PackHdr *hdr;                // one header per kPackBlock rows
 };
 
+// ---- decode of the reference's on-disk column segments (column_decode.cu) -------------------------
+// BitpackingMode, src/include/duckdb/storage/compression/bitpacking.hpp:15
+enum BpMode : uint32_t { BP_INVALID = 0, BP_AUTO = 1, BP_CONSTANT = 2, BP_CONSTANT_DELTA = 3, BP_DELTA_FOR = 4, BP_FOR = 5 };
+// one 2048-value metadata group of a BitPacking segment (or a whole Constant segment), validated on the host
+struct BpGroup {
+	uint64_t data_off; // byte offset in the staged blob of the group's header (4-byte aligned)
+	uint64_t row0;     // first local row the group decodes to
+	uint32_t n;        // values to produce (≤ 2048 except BP_CONSTANT)
+	uint32_t mode;     // BpMode
+};
+
 // Device-side result header (one per query).
 struct ResultHeader {
 	unsigned long long count;
@@ -118,8 +129,9 @@ cudaError_t launch_probe_bits(const ScanArgs &args, uint32_t seg_words, bool pos
 cudaError_t launch_probe(const ProbeArgs &args, int sm_count, cudaStream_t stream);
 int probe_grid(int sm_count);
 
-// index build: B_(col[r]-base) |= bit r, for values in [v_lo, v_lo+v_n)
-cudaError_t launch_index_build(const void *col, uint32_t elem_bytes, uint64_t n_rows, int64_t base_value,
+// index build: B_(col[r]-base) |= bit r for rows [row_begin, n_rows); bits of rows < row_begin are kept (append)
+cudaError_t launch_index_build(const void *col, uint32_t elem_bytes, uint64_t row_begin, uint64_t n_rows,
+                               int64_t base_value,
                                uint32_t cardinality, uint64_t *bitvectors, uint64_t words_per_bv, int sm_count,
                                cudaStream_t stream, int *n_launches);
 cudaError_t launch_popcount(const uint64_t *words, uint64_t n_words, unsigned long long *out, int sm_count,
@@ -133,6 +145,9 @@ cudaError_t launch_pack_widths(const long long *col, uint64_t n_rows, long long 
                                cudaStream_t stream);
 cudaError_t launch_pack_blocks(const long long *col, uint64_t n_rows, const PackHdr *hdr, unsigned long long *words,
                                cudaStream_t stream);
+// one CTA per BpGroup: packed words staged in shared memory, FOR / DELTA_FOR (block-wide running sum) decode
+cudaError_t launch_bp_decode(const uint8_t *blob, const BpGroup *groups, uint32_t n_groups, void *out,
+                             uint32_t elem_bytes, cudaStream_t stream);
 cudaError_t launch_synth_column(void *col, int kind, uint64_t n_rows, int64_t row_base, uint64_t seed,
                                 uint64_t threshold, uint32_t card, uint32_t hot_lo, uint32_t hot_n, int sm_count,
                                 cudaStream_t stream);

@@ -37,6 +37,19 @@ void CubitTable::AddColumn(column_t col, const int32_t *values) {
 	col_types[col] = LogicalTypeId::INTEGER;
 }
 
+void CubitTable::Append(idx_t n_new, const std::map<column_t, const void *> &values) {
+	std::vector<cubit_append_column> cols;
+	for (auto &kv : values) {
+		auto it = col_types.find(kv.first);
+		if (it == col_types.end()) {
+			throw InvalidInputException("Table does not have column " + std::to_string(kv.first));
+		}
+		cols.push_back(cubit_append_column {(int32_t)kv.first, it->second == LogicalTypeId::BIGINT ? 8u : 4u, kv.second});
+	}
+	Check(cubit_gpu_append_rows(handle, n_new, cols.data(), (uint32_t)cols.size()));
+	n_rows += n_new;
+}
+
 LogicalTypeId CubitTable::ColumnType(column_t col) const {
 	if (col == COLUMN_IDENTIFIER_ROW_ID) {
 		return LogicalTypeId::BIGINT;

@@ -30,6 +30,10 @@ public:
 
 	void AddColumn(column_t col, const int64_t *values);
 	void AddColumn(column_t col, const int32_t *values);
+	// INSERT: n_new rows appended at the end (they take the next row ids); `values` holds one array of n_new
+	// elements per resident column.  Indexes built from a column are extended on the GPU
+	// (BoundIndex::Append, bound_index.hpp:71-75).
+	void Append(idx_t n_new, const std::map<column_t, const void *> &values);
 	LogicalTypeId ColumnType(column_t col) const;
 	idx_t RowCount() const {
 		return n_rows;

@@ -175,6 +175,48 @@ int cubit_gpu_drop_column(cubit_gpu_table *t, int32_t col_id);
  * 8.  keep_raw = 0 frees the raw array (index builds need it: build first).  *packed_bytes = resident size. */
 int cubit_gpu_pack_column(cubit_gpu_table *t, int32_t col_id, int keep_raw, uint64_t *packed_bytes);
 
+/* Append n_new rows at the end of the shard (INSERT: the new rows take the next row ids — rowids are dense
+ * table positions, src/storage/table/row_group.cpp:511-514; index side BoundIndex::Append,
+ * src/include/duckdb/execution/index/bound_index.hpp:71-75).  Every resident column must be supplied (raw
+ * form; bit-packed columns are rejected with CUBIT_ESTATE).  Indexes built with cubit_gpu_index_build are
+ * extended from their source column on the GPU (only the new rows are scanned); bitvectors that were uploaded
+ * get zero bits for the new rows.  Pending deltas stay pending.  cubit_gpu_words_per_bitvector changes. */
+typedef struct cubit_append_column {
+	int32_t col_id;
+	uint32_t elem_bytes;
+	const void *data; /* n_new elements */
+} cubit_append_column;
+int cubit_gpu_append_rows(cubit_gpu_table *t, uint64_t n_new, const cubit_append_column *cols, uint32_t n_cols);
+
+/* Upload a column as the reference's ON-DISK column segments and decode them on the GPU:
+ * the compressed bytes cross PCIe as stored, one CTA decodes one 2048-value metadata group.  What each segment
+ * is — compression, first row, row count, bytes at (block_id, block_offset) — is what pragma_storage_info /
+ * ColumnSegment report (src/storage/table/column_segment.cpp, DataPointer in src/include/duckdb/storage/
+ * data_pointer.hpp); the layout decoded is src/storage/compression/bitpacking.cpp:22-75,524-544,660-860.
+ * Segments must be sorted by row_start and tile [0, n_rows) exactly.  Malformed segments are rejected on the
+ * host (CUBIT_EINVAL) before anything is launched.  The result is the same resident column
+ * cubit_gpu_upload_column produces. */
+#define CUBIT_SEG_UNCOMPRESSED 0 /* plain array of count elements (fixed_size_uncompressed.cpp)             */
+#define CUBIT_SEG_BITPACKING 1   /* BitPacking segment: u64 metadata-end offset, group data, metadata words */
+#define CUBIT_SEG_CONSTANT 2     /* Constant compression: data points to the one value of the segment       */
+typedef struct cubit_column_segment {
+	uint32_t kind;      /* CUBIT_SEG_*                                          */
+	uint32_t reserved;
+	uint64_t row_start; /* first row of the segment, local to this table shard  */
+	uint64_t count;     /* rows in the segment                                  */
+	const void *data;   /* the segment's bytes as stored in its block           */
+	uint64_t bytes;
+} cubit_column_segment;
+typedef struct cubit_decode_info {
+	uint64_t h2d_bytes;  /* compressed bytes copied host → device                */
+	uint64_t n_groups;   /* metadata groups decoded                               */
+	uint64_t mode_groups[6]; /* groups per BitpackingMode (bitpacking.hpp:15)     */
+	uint32_t n_launches;
+	float ms_decode;     /* decode kernel, CUDA events                            */
+} cubit_decode_info;
+int cubit_gpu_upload_column_segments(cubit_gpu_table *t, int32_t col_id, uint32_t elem_bytes,
+                                     const cubit_column_segment *segs, uint32_t n_segs, cubit_decode_info *info);
+
 /* ---- query --------------------------------------------------------------
  * Synchronous unless CUBIT_Q_ASYNC: on return info fields are final.
  * Thread-safe per table (calls are serialised on the table's stream).      */

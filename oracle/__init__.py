@@ -23,14 +23,57 @@ _i64p = C.POINTER(C.c_int64)
 _i32p = C.POINTER(C.c_int32)
 
 
+_SOURCES = ["cubit_oracle.c", "bitpacking_oracle.c"]
+_REF_DIR = os.path.join(_HERE, "_ref")
+_REF_FASTPFOR = os.path.join(_REF_DIR, "libfastpfor_ref.so")
+_REFERENCE_FASTPFOR_SRC = "/root/reference/third_party/fastpforlib"
+
+
 def build(force=False):
-    src = os.path.join(_HERE, "cubit_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, s) for s in _SOURCES]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
         flags = ["-O3", "-fPIC", "-Wall", "-Wextra", "-fvisibility=hidden"]
         # -march=native is only valid for the machine that compiles; the library may have been
         # built in another container, so rebuild here if it was not produced on this host.
-        subprocess.check_call(["gcc"] + flags + ["-march=native", "-shared", "-o", _LIB_PATH, src, "-lpthread"])
+        subprocess.check_call(["gcc"] + flags + ["-march=native", "-shared", "-o", _LIB_PATH] + srcs + ["-lpthread"])
     return _LIB_PATH
+
+
+def build_ref(force=False):
+    """oracle/_ref/libfastpfor_ref.so: the REFERENCE's own 32-value pack/unpack (third_party/fastpforlib,
+    the arithmetic under BitpackingPrimitives::PackGroup/UnPackGroup), compiled from the sources where they
+    lie under /root/reference plus a 20-line extern "C" shim of ours.  Only possible in the build container;
+    the built .so travels to the GPU box.  Returns the path, or None when neither sources nor a built .so exist."""
+    shim = os.path.join(_HERE, "ref_fastpfor_shim.cpp")
+    if os.path.isdir(_REFERENCE_FASTPFOR_SRC):
+        ref_src = os.path.join(_REFERENCE_FASTPFOR_SRC, "bitpacking.cpp")
+        if force or not os.path.exists(_REF_FASTPFOR) or os.path.getmtime(_REF_FASTPFOR) < os.path.getmtime(shim):
+            os.makedirs(_REF_DIR, exist_ok=True)
+            subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++11", "-I", _REFERENCE_FASTPFOR_SRC,
+                                   "-o", _REF_FASTPFOR, shim, ref_src])
+    return _REF_FASTPFOR if os.path.exists(_REF_FASTPFOR) else None
+
+
+_ref_fastpfor = None
+
+
+def ref_fastpfor():
+    """ctypes handle of oracle/_ref/libfastpfor_ref.so (None if it cannot be built or found)"""
+    global _ref_fastpfor
+    if _ref_fastpfor is None:
+        path = build_ref()
+        if path is None:
+            return None
+        L = C.CDLL(path)
+        u32p = C.POINTER(C.c_uint32)
+        L.ref_fastunpack64.argtypes = [u32p, _u64p, C.c_uint32]
+        L.ref_fastpack64.argtypes = [_u64p, u32p, C.c_uint32]
+        L.ref_fastunpack32.argtypes = [u32p, u32p, C.c_uint32]
+        L.ref_fastpack32.argtypes = [u32p, u32p, C.c_uint32]
+        for f in (L.ref_fastunpack64, L.ref_fastpack64, L.ref_fastunpack32, L.ref_fastpack32):
+            f.restype = None
+        _ref_fastpfor = L
+    return _ref_fastpfor
 
 
 def lib():
@@ -74,6 +117,15 @@ def lib():
         L.oracle_scan_mt.argtypes = [C.POINTER(_u64p), C.POINTER(_u64p), _i32p, C.c_int, C.c_uint64, C.c_int64,
                                      _u64p, _i64p, _i64p, _i64p, _u64p, _i64p, C.c_int]
         L.oracle_scan_mt.restype = C.c_uint64
+        u8p = C.POINTER(C.c_uint8)
+        L.oracle_bitpacking_decode.argtypes = [u8p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, _u64p]
+        L.oracle_bitpacking_decode.restype = C.c_int
+        L.oracle_bitpacking_encode.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, u8p, C.c_uint64]
+        L.oracle_bitpacking_encode.restype = C.c_int64
+        L.oracle_bp_unpack_group64.argtypes = [u8p, _u64p, C.c_uint32]
+        L.oracle_bp_unpack_group64.restype = None
+        L.oracle_bp_unpack_group32.argtypes = [u8p, C.POINTER(C.c_uint32), C.c_uint32]
+        L.oracle_bp_unpack_group32.restype = None
     return _lib
 
 
@@ -259,3 +311,63 @@ def np_build_index(col, base_value, card):
 
 def np_sum(vals):
     return int(sum(int(x) for x in np.asarray(vals, dtype=np.int64).tolist()))
+
+
+# ---------------------------------------------------------------- DuckDB BitPacking column segments
+BP_MODES = ["invalid", "auto", "constant", "constant_delta", "delta_for", "for"]
+
+
+def bitpacking_decode(seg, elem_bytes, count):
+    """decode one BitPacking segment (bytes as stored in the block) → (values, {mode: metadata groups})
+    restates BitpackingScanPartial, src/storage/compression/bitpacking.cpp:776-860"""
+    seg = np.ascontiguousarray(seg, dtype=np.uint8)
+    out = np.empty(count, dtype=np.int64 if elem_bytes == 8 else np.int32)
+    hist = np.zeros(6, dtype=np.uint64)
+    rc = lib().oracle_bitpacking_decode(_p(seg, C.POINTER(C.c_uint8)), seg.size, elem_bytes, count,
+                                        out.ctypes.data_as(C.c_void_p), _p(hist, _u64p))
+    if rc != 0:
+        raise ValueError("malformed BitPacking segment (oracle code %d)" % rc)
+    return out, {BP_MODES[i]: int(hist[i]) for i in range(6) if hist[i]}
+
+
+def decode_column_segments(blob, seg_meta, elem_bytes, n_rows):
+    """a whole column from its segment directory rows (kind, row_start, count, offset, bytes, elem):
+    kind 0 = Uncompressed (fixed_size_uncompressed.cpp), 1 = BitPacking, 2 = Constant (one value)"""
+    out = np.empty(n_rows, dtype=np.int64 if elem_bytes == 8 else np.int32)
+    modes = {}
+    for kind, start, count, off, nbytes, elem in seg_meta:
+        assert elem == elem_bytes
+        raw = blob[off:off + nbytes]
+        if kind == 0:
+            out[start:start + count] = np.frombuffer(raw.tobytes(), dtype=out.dtype)[:count]
+        elif kind == 2:
+            out[start:start + count] = np.frombuffer(raw.tobytes(), dtype=out.dtype)[0]
+        else:
+            vals, h = bitpacking_decode(raw, elem_bytes, count)
+            out[start:start + count] = vals
+            for k, v in h.items():
+                modes[k] = modes.get(k, 0) + v
+    return out, modes
+
+
+def bitpacking_encode(values, mode="auto"):
+    """one BitPacking segment (uint8 array) holding all of `values` (int64 or int32), written the way the
+    reference's BitpackingCompressState does (bitpacking.cpp:229-289,392-446,524-544)"""
+    values = np.ascontiguousarray(values)
+    assert values.dtype in (np.int64, np.int32)
+    n_grp = (len(values) + 2047) // 2048
+    out = np.empty(8 + n_grp * (24 + 2048 * 8 + 4) + 8, dtype=np.uint8)
+    n = lib().oracle_bitpacking_encode(values.ctypes.data_as(C.c_void_p), len(values), values.dtype.itemsize,
+                                       BP_MODES.index(mode), _p(out, C.POINTER(C.c_uint8)), out.size)
+    if n < 0:
+        raise ValueError("cannot encode (oracle code %d)" % n)
+    return out[:n].copy()
+
+
+def encode_column_segments(values, rows_per_segment=30720, mode="auto"):
+    """a whole column as BitPacking segments → [(kind=1, row_start, count, bytes)]"""
+    segs = []
+    for s in range(0, len(values), rows_per_segment):
+        part = values[s:s + rows_per_segment]
+        segs.append((1, s, len(part), bitpacking_encode(part, mode)))
+    return segs

@@ -584,3 +584,54 @@ def test_bit_packed_columns_are_lossless_on_every_probe_path(cubit, keep_raw, se
             ix2 = t.create_index(4)
             t.build_index(ix2, 2, 0)                          # raw form gone: build first, then pack
     t.close()
+
+
+@pytest.mark.parametrize("seg_bits", [32768, 65536])
+def test_append_rows_extends_columns_and_indexes(cubit, seg_bits):
+    """cubit_gpu_append_rows (INSERT): appended rows take the next row ids, built indexes are extended on the
+    GPU from the new rows only, uploaded bitvectors get zeros, pending deltas survive, and every query answer
+    equals the oracle's on the full arrays — across word, build-tile, segment and capacity boundaries"""
+    rng = np.random.default_rng(99)
+    base = seg_bits * 3
+    sizes = [50_001, 13, 4096 - 13, 70_000, 1, 300_000, 64]   # appended one after another
+    total = sum(sizes)
+    key = rng.integers(0, 9, total).astype(np.int32)
+    pay = rng.integers(-2**50, 2**50, total).astype(np.int64)
+    n = sizes[0]
+    t = cubit.CubitTable(n, row_base=base, seg_bits=seg_bits)
+    t.upload_column(0, pay[:n])
+    t.upload_column(1, key[:n])
+    ix = t.create_index(9)
+    t.build_index(ix, 1, 0)
+    up = t.create_index(2)                                       # an UPLOADED index (no source column)
+    manual = (np.arange(n) % 3 == 0)
+    t.upload_bitvector(up, 1, np.packbits(np.pad(manual, (0, -n % 64)), bitorder="little").view(np.uint64))
+    drows = np.array([5, 77, 40_000])
+    t.set_delta(ix, 4, drows)                                    # pending delete/update flips stay pending
+    for add in sizes[1:]:
+        t.append_rows({0: pay[n:n + add], 1: key[n:n + add]})
+        n += add
+        assert t.n_rows == n
+        assert np.array_equal(t.download_column(0), pay[:n]) and np.array_equal(t.download_column(1), key[:n])
+        bv = oracle.build_index(key[:n], 0, 9)
+        for v in (0, 4, 8):
+            assert np.array_equal(t.download_bitvector(ix, v), bv[v]), (n, v)
+        d4 = oracle.delta_from_rows(drows, n)
+        want = oracle.decode(oracle.merge([[bv[3], bv[4], bv[5]]], [[None, d4, None]]), base)
+        with t.query([[(ix, 3), (ix, 4), (ix, 5)]], flags=cubit.Q_ROWIDS | cubit.Q_VALUES, cols=[0],
+                     agg=cubit.AGG_SUM, agg_a=0) as r:
+            ids, (vals,) = r.fetch()
+            assert np.array_equal(ids, want) and np.array_equal(vals, oracle.probe(want, pay[:n], base))
+            assert r.sum == oracle.sum_i64(vals)
+        m = np.zeros(n, dtype=bool)
+        m[:sizes[0]] = manual
+        with t.query([[(up, 1)]], flags=cubit.Q_ROWIDS) as r:   # new rows of an uploaded bitvector are 0
+            assert np.array_equal(r.fetch()[0], np.nonzero(m)[0] + base)
+    t.merge_deltas(ix)
+    bv = oracle.build_index(key, 0, 9)
+    assert np.array_equal(t.download_bitvector(ix, 4), bv[4] ^ oracle.delta_from_rows(drows, total))
+    with pytest.raises(cubit.CubitError):
+        t.append_rows({0: pay[:10]})                             # every resident column must be supplied
+    with pytest.raises(cubit.CubitError):
+        t.append_rows({0: pay[:10], 1: key[:10].astype(np.int64)})  # wrong width
+    t.close()

@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "cubit_gpu_index_create", "cubit_gpu_upload_bitvector", "cubit_gpu_download_bitvector", "cubit_gpu_index_build",
     "cubit_gpu_bitvector_count", "cubit_gpu_set_delta", "cubit_gpu_merge_deltas", "cubit_gpu_upload_column",
     "cubit_gpu_download_column", "cubit_gpu_synth_column", "cubit_gpu_drop_column", "cubit_gpu_pack_column",
-    "cubit_gpu_upload_column_segments", "cubit_gpu_append_rows",
+    "cubit_gpu_upload_column_segments", "cubit_gpu_append_rows", "cubit_gpu_upload_bitvector_wah",
     "cubit_gpu_query",
     "cubit_gpu_result_wait", "cubit_gpu_result_get", "cubit_gpu_fetch", "cubit_gpu_fetch_bitvector",
     "cubit_gpu_free_result", "cubit_gpu_probe",
@@ -66,6 +66,10 @@ class ResultInfo(C.Structure):
 class ColumnSegment(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("reserved", C.c_uint32), ("row_start", C.c_uint64), ("count", C.c_uint64),
                 ("data", C.c_void_p), ("bytes", C.c_uint64)]
+
+
+class WahBitvector(C.Structure):
+    _fields_ = [("words", C.c_void_p), ("n_words", C.c_uint64), ("active_val", C.c_uint32), ("active_nbits", C.c_uint32)]
 
 
 class AppendColumn(C.Structure):
@@ -121,6 +125,7 @@ def load_library():
         "cubit_gpu_synth_column": ([vp, i32, i32, u64, u64, u32, u32, u32], C.c_int),
         "cubit_gpu_drop_column": ([vp, i32], C.c_int),
         "cubit_gpu_pack_column": ([vp, i32, C.c_int, P(u64)], C.c_int),
+        "cubit_gpu_upload_bitvector_wah": ([vp, i32, u32, P(WahBitvector)], C.c_int),
         "cubit_gpu_append_rows": ([vp, u64, P(AppendColumn), u32], C.c_int),
         "cubit_gpu_upload_column_segments": ([vp, i32, u32, P(ColumnSegment), u32, P(DecodeInfo)], C.c_int),
         "cubit_gpu_query": ([vp, P(Query), P(vp)], C.c_int),
@@ -291,6 +296,12 @@ class CubitTable:
     def upload_bitvector(self, index_id, value_id, words):
         words = np.ascontiguousarray(words, dtype=np.uint64)
         _check(self._L.cubit_gpu_upload_bitvector(self._h, index_id, value_id, words.ctypes.data, len(words)))
+
+    def upload_bitvector_wah(self, index_id, value_id, wah_words, active_val=0, active_nbits=0):
+        """upload a WAH-compressed (FastBit ibis::bitvector) value bitvector; expanded on the GPU"""
+        w = np.ascontiguousarray(wah_words, dtype=np.uint32)
+        bv = WahBitvector(w.ctypes.data if len(w) else None, len(w), active_val, active_nbits)
+        _check(self._L.cubit_gpu_upload_bitvector_wah(self._h, index_id, value_id, C.byref(bv)))
 
     def upload_index(self, bitvectors):
         """bitvectors: [card, n_words] uint64 → new index id"""

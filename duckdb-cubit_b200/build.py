@@ -46,7 +46,7 @@ def _run(cmd, verbose):
 def build_gpu(verbose=False, ptxas_info=False):
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, "kernels.h"), os.path.join(CSRC, "scan_common.cuh"), os.path.join(CSRC, "col_ref.cuh"), os.path.join(ROOT, "include", "cubit_gpu.h")]
-    units = ["scan_kernel.cu", "aux_kernels.cu", "column_decode.cu", "cubit_gpu.cu"]
+    units = ["scan_kernel.cu", "aux_kernels.cu", "column_decode.cu", "wah_decode.cu", "cubit_gpu.cu"]
     objs = []
     jobs = []
     for u in units:

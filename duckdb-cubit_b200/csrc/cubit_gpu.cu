@@ -407,6 +407,78 @@ extern "C" int cubit_gpu_upload_bitvector(cubit_gpu_table *t, int32_t index_id, 
 	return CUBIT_OK;
 }
 
+extern "C" int cubit_gpu_upload_bitvector_wah(cubit_gpu_table *t, int32_t index_id, uint32_t value_id,
+                                              const cubit_wah_bitvector *bv) {
+	if (!t || !bv || (!bv->words && bv->n_words)) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	if (bv->active_nbits > 30 || (bv->active_nbits < 32 && (bv->active_val >> bv->active_nbits) != 0)) {
+		return fail(CUBIT_EINVAL, "bad active word (nbits %u)", bv->active_nbits);
+	}
+	// one pass over the compressed words: validate, and the 31-bit-group prefix per block of kWahBlockWords
+	const uint64_t n_blocks = std::max<uint64_t>(1, (bv->n_words + kWahBlockWords - 1) / kWahBlockWords);
+	std::vector<unsigned long long> block_group0(n_blocks, 0);
+	unsigned long long groups = 0;
+	for (uint64_t i = 0; i < bv->n_words; i++) {
+		if (i % kWahBlockWords == 0) {
+			block_group0[i / kWahBlockWords] = groups;
+		}
+		const uint32_t w = bv->words[i];
+		if (w & 0x80000000u) {
+			if ((w & 0x3fffffffu) == 0) {
+				return fail(CUBIT_EINVAL, "WAH word %llu: zero-length fill", (unsigned long long)i);
+			}
+			groups += w & 0x3fffffffu;
+		} else {
+			groups++;
+		}
+		if (groups * 31ull > t->n_rows) {
+			return fail(CUBIT_EINVAL, "WAH bitvector is longer than the table (%llu rows)", (unsigned long long)t->n_rows);
+		}
+	}
+	if (groups * 31ull + bv->active_nbits > t->n_rows) {
+		return fail(CUBIT_EINVAL, "WAH bitvector describes %llu bits, table has %llu rows",
+		            (unsigned long long)(groups * 31ull + bv->active_nbits), (unsigned long long)t->n_rows);
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	Index *ix = get_index(t, index_id);
+	if (!ix || value_id >= ix->card) {
+		return fail(CUBIT_EINVAL, "bad index/value (%d, %u)", index_id, value_id);
+	}
+	uint32_t *d_wah = nullptr;
+	unsigned long long *d_blk = nullptr;
+	CU_TRY(cudaMalloc(&d_wah, (bv->n_words + 4) * 4));
+	cudaError_t e = cudaMalloc(&d_blk, n_blocks * 8);
+	unsigned long long *dst =
+	    reinterpret_cast<unsigned long long *>(ix->d_bits + (uint64_t)value_id * t->words_per_bv);
+	if (e == cudaSuccess) {
+		e = cudaMemcpyAsync(d_wah, bv->words, bv->n_words * 4, cudaMemcpyHostToDevice, t->stream);
+	}
+	if (e == cudaSuccess) {
+		e = cudaMemcpyAsync(d_blk, block_group0.data(), n_blocks * 8, cudaMemcpyHostToDevice, t->stream);
+	}
+	if (e == cudaSuccess) {
+		e = cudaMemsetAsync(dst, 0, t->words_per_bv * 8, t->stream);
+	}
+	if (e == cudaSuccess) {
+		e = launch_wah_expand(d_wah, bv->n_words, d_blk, groups, bv->active_val, bv->active_nbits, dst, t->stream);
+	}
+	if (e == cudaSuccess) {
+		e = cudaStreamSynchronize(t->stream);
+	}
+	cudaFree(d_wah);
+	if (d_blk) {
+		cudaFree(d_blk);
+	}
+	CU_TRY(e);
+	t->launches++;
+	ix->counts_valid = false;
+	return CUBIT_OK;
+}
+
 extern "C" int cubit_gpu_download_bitvector(cubit_gpu_table *t, int32_t index_id, uint32_t value_id, uint64_t *words,
                                             uint64_t n_words) {
 	if (!t || !words) {

@@ -148,6 +148,12 @@ cudaError_t launch_pack_blocks(const long long *col, uint64_t n_rows, const Pack
 // one CTA per BpGroup: packed words staged in shared memory, FOR / DELTA_FOR (block-wide running sum) decode
 cudaError_t launch_bp_decode(const uint8_t *blob, const BpGroup *groups, uint32_t n_groups, void *out,
                              uint32_t elem_bytes, cudaStream_t stream);
+// WAH (FastBit ibis::bitvector) → verbatim bitvector; `out` must be zeroed; block_group0[b] = number of 31-bit
+// groups before WAH word b * kWahBlockWords (host-computed while validating)
+constexpr int kWahBlockWords = 1024;
+cudaError_t launch_wah_expand(const uint32_t *wah, uint64_t n_wah, const unsigned long long *block_group0,
+                              unsigned long long total_groups, uint32_t active_val, uint32_t active_nbits,
+                              unsigned long long *out, cudaStream_t stream);
 cudaError_t launch_synth_column(void *col, int kind, uint64_t n_rows, int64_t row_base, uint64_t seed,
                                 uint64_t threshold, uint32_t card, uint32_t hot_lo, uint32_t hot_n, int sm_count,
                                 cudaStream_t stream);

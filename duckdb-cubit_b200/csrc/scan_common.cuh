@@ -88,6 +88,9 @@ constexpr int kDefer = 2;          // segments merged between a segment's merge 
 constexpr int kWaitBatch = 4;      // ring stages consumed per mbarrier round trip
 constexpr int kDeltaStage = 32;    // delta words staged in shared memory per ring stage (the rest is read from L2)
 constexpr int kSlotRows = 32 * 64; // rows one warp compacts at a time (32 lanes × one 64-bit word)
+// per-warp staging buffer (uint16 units): [0, kSlotRows + 8) row numbers, + 32 per-lane dummy slots, then the
+// pack-block headers of up to kMaxFusedCols bit-packed columns (16 × 16 bytes each, 16-byte aligned)
+constexpr int kCompactHdrOff = kSlotRows + 8 + 32;
 
 constexpr int kLookSlots = 16; // status words per prefix-warp lane per window → 512 segments per window
 
@@ -212,12 +215,14 @@ __device__ __forceinline__ void write_out(const ScanArgs &a, const uint16_t *cbu
 	const unsigned long long obase = pos0 - pad; // output position of staging index 0 (even)
 	const uint32_t end = pad + count;
 	const uint32_t *cb32 = reinterpret_cast<const uint32_t *>(cbuf);
-	HdrRegs hdrs[NL > 0 ? NL : 1];
+	// pack-block headers of the probed columns, parked behind the staging area (kCompactHdrOff)
+	uint4 *hs = reinterpret_cast<uint4 *>(const_cast<uint16_t *>(cbuf) + kCompactHdrOff);
 	if (NL > 0) {
 #pragma unroll
 		for (int cc = 0; cc < NL; cc++) {
-			hdrs[cc] = load_hdrs(a.lcol[cc], local0, lane);
+			stage_hdrs(a.lcol[cc], local0, lane, hs + cc * kHdrSlots);
 		}
+		__syncwarp();
 	}
 	for (uint32_t g0 = 0; g0 * 2 < end; g0 += 64) {
 		uint32_t r[2][2];
@@ -236,7 +241,7 @@ __device__ __forceinline__ void write_out(const ScanArgs &a, const uint16_t *cbu
 				for (int e = 0; e < 2; e++) {
 #pragma unroll
 					for (int cc = 0; cc < NL; cc++) {
-						v[h][e][cc] = load_col_hoisted(a.lcol[cc], hdrs[cc], local0, r[h][e], ok[h][e]);
+						v[h][e][cc] = load_col_staged(a.lcol[cc], hs + cc * kHdrSlots, local0, r[h][e], ok[h][e]);
 					}
 				}
 			}

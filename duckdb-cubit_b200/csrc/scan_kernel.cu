@@ -44,13 +44,16 @@
 
 namespace cubit {
 
-template <int WPT>
+// NL > 0 (probe fused into the scan, not the default path): the per-warp staging rows also hold the pack-block
+// headers of the probed columns; the ring gives up 8 KiB so that two CTAs still fit one SM.
+template <int WPT, int NL>
 struct ScanSmem {
 	static constexpr int kTileWords = kConsumerThreads * WPT;
 	static constexpr int kTileBytes = kTileWords * 8;
-	static constexpr int kStages = kScanRingBytes / kTileBytes;
+	static constexpr int kStages = (kScanRingBytes - (NL > 0 ? 8192 : 0)) / kTileBytes;
+	static constexpr int kCompactRow = kCompactHdrOff + NL * kHdrSlots * 8;
 	alignas(128) uint64_t stage[kStages][kTileWords];
-	alignas(16) uint16_t compact[kConsumerWarps][kSlotRows + 8 + 32]; // per-warp staging of local row numbers (+ dummy slots)
+	alignas(16) uint16_t compact[kConsumerWarps][kCompactRow]; // per-warp staging of local row numbers (+ dummy slots)
 	alignas(16) DeltaEnt dbuf[kStages][kDeltaStage];              // pending-delta words staged beside each segment
 	alignas(8) uint64_t full[kStages];
 	uint64_t empty[kStages];
@@ -67,7 +70,7 @@ struct ScanSmem {
 
 template <int WPT, bool HAS_DELTA, int NL>
 __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __grid_constant__ ScanArgs a) {
-	using Smem = ScanSmem<WPT>;
+	using Smem = ScanSmem<WPT, NL>;
 	constexpr int kStages = Smem::kStages;
 	constexpr int kTileWords = Smem::kTileWords;
 	constexpr int kTileBytes = Smem::kTileBytes;
@@ -430,7 +433,7 @@ template <int WPT, int NL, bool POS>
 __global__ void __launch_bounds__(kProbeBitsThreads, 3) cubit_probe_bits_kernel(const __grid_constant__ ScanArgs a) {
 	constexpr int kTileWords = kProbeBitsThreads * WPT;
 	constexpr int kSpanWords = WPT * 32;
-	__shared__ __align__(16) uint16_t compact[kProbeBitsThreads / 32][kSlotRows + 8 + 32];
+	__shared__ __align__(16) uint16_t compact[kProbeBitsThreads / 32][kCompactHdrOff + NL * kHdrSlots * 8];
 	__shared__ uint32_t warp_tot[2][kProbeBitsThreads / 32];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	Agg agg;
@@ -537,7 +540,7 @@ cudaError_t launch_probe_bits(const ScanArgs &args, uint32_t seg_words, bool pos
 template <int WPT, bool HAS_DELTA, int NL>
 static cudaError_t launch_scan_t(const ScanArgs &args, int sm_count, cudaStream_t stream, int *grid_out) {
 	auto kern = cubit_scan_kernel<WPT, HAS_DELTA, NL>;
-	const size_t smem = sizeof(ScanSmem<WPT>) + 128;
+	const size_t smem = sizeof(ScanSmem<WPT, NL>) + 128;
 	// function attributes are per device: configure once per (template instance, device)
 	static int blocks_per_sm_dev[64] = {};
 	int dev = 0;

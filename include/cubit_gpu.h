@@ -140,6 +140,20 @@ int cubit_gpu_upload_bitvector(cubit_gpu_table *t, int32_t index_id, uint32_t va
                                uint64_t n_words);
 int cubit_gpu_download_bitvector(cubit_gpu_table *t, int32_t index_id, uint32_t value_id, uint64_t *words,
                                  uint64_t n_words);
+/* Upload a value bitvector in the WAH-compressed form of FastBit's ibis::bitvector — what the upstream CUBIT
+ * library keeps per value (32-bit words; literal: MSB 0 + 31 bits, first bit most significant; fill: MSB 1,
+ * bit 30 = fill bit, low 30 bits = number of 31-bit groups; `active` = the trailing < 31 bits).  The compressed
+ * words cross PCIe as they are and are expanded on the GPU.  The vector may describe fewer than n_rows bits
+ * (the rest is 0, as ibis::bitvector::adjustSize would pad) but not more.  Malformed input (zero-length fill,
+ * active_nbits > 30, too long) is rejected on the host. */
+typedef struct cubit_wah_bitvector {
+	const uint32_t *words;
+	uint64_t n_words;
+	uint32_t active_val;   /* trailing bits, first bit most significant of the low active_nbits bits */
+	uint32_t active_nbits; /* 0..30 */
+} cubit_wah_bitvector;
+int cubit_gpu_upload_bitvector_wah(cubit_gpu_table *t, int32_t index_id, uint32_t value_id,
+                                   const cubit_wah_bitvector *bv);
 /* build every bitvector of the index on the GPU from a resident integer
  * column: row r sets bit r of B_(col[r]-base_value); values outside
  * [base_value, base_value+cardinality) are not indexed (NULL keys are not

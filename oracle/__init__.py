@@ -23,7 +23,7 @@ _i64p = C.POINTER(C.c_int64)
 _i32p = C.POINTER(C.c_int32)
 
 
-_SOURCES = ["cubit_oracle.c", "bitpacking_oracle.c"]
+_SOURCES = ["cubit_oracle.c", "bitpacking_oracle.c", "wah_oracle.c"]
 _REF_DIR = os.path.join(_HERE, "_ref")
 _REF_FASTPFOR = os.path.join(_REF_DIR, "libfastpfor_ref.so")
 _REFERENCE_FASTPFOR_SRC = "/root/reference/third_party/fastpforlib"
@@ -122,6 +122,13 @@ def lib():
         L.oracle_bitpacking_decode.restype = C.c_int
         L.oracle_bitpacking_encode.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, u8p, C.c_uint64]
         L.oracle_bitpacking_encode.restype = C.c_int64
+        u32p = C.POINTER(C.c_uint32)
+        L.oracle_wah_encode.argtypes = [_u64p, C.c_uint64, u32p, C.c_uint64, u32p, u32p]
+        L.oracle_wah_encode.restype = C.c_int64
+        L.oracle_wah_bits.argtypes = [u32p, C.c_uint64, C.c_uint32]
+        L.oracle_wah_bits.restype = C.c_int64
+        L.oracle_wah_decode.argtypes = [u32p, C.c_uint64, C.c_uint32, C.c_uint32, _u64p, C.c_uint64]
+        L.oracle_wah_decode.restype = C.c_int64
         L.oracle_bp_unpack_group64.argtypes = [u8p, _u64p, C.c_uint32]
         L.oracle_bp_unpack_group64.restype = None
         L.oracle_bp_unpack_group32.argtypes = [u8p, C.POINTER(C.c_uint32), C.c_uint32]
@@ -371,3 +378,26 @@ def encode_column_segments(values, rows_per_segment=30720, mode="auto"):
         part = values[s:s + rows_per_segment]
         segs.append((1, s, len(part), bitpacking_encode(part, mode)))
     return segs
+
+
+# ---------------------------------------------------------------- WAH (FastBit ibis::bitvector) bitvectors
+def wah_encode(words, n_bits):
+    """verbatim bitvector (uint64 words, DuckDB bit order) → (wah uint32 words, active_val, active_nbits)"""
+    words = np.ascontiguousarray(words, dtype=np.uint64)
+    out = np.empty(n_bits // 31 + 1, dtype=np.uint32)
+    av, an = C.c_uint32(0), C.c_uint32(0)
+    n = lib().oracle_wah_encode(_p(words, _u64p), n_bits, _p(out, C.POINTER(C.c_uint32)), out.size, C.byref(av),
+                                C.byref(an))
+    assert n >= 0
+    return out[:n].copy(), av.value, an.value
+
+
+def wah_decode(wah, active_val, active_nbits, n_words):
+    """→ (verbatim uint64 words, bits described); raises on malformed input"""
+    wah = np.ascontiguousarray(wah, dtype=np.uint32)
+    out = np.empty(n_words, dtype=np.uint64)
+    n = lib().oracle_wah_decode(_p(wah, C.POINTER(C.c_uint32)), wah.size, active_val, active_nbits, _p(out, _u64p),
+                                n_words)
+    if n < 0:
+        raise ValueError("malformed WAH bitvector")
+    return out, int(n)

@@ -77,16 +77,18 @@ struct Column {
 	}
 };
 
-// Which form of the column a probe reads.  Packed costs fewer bytes but ~2x the instructions per value:
-// measured (profiles/r1_experiment_packed_payload.log) it wins while the selection is sparse enough for the
-// probe to be DRAM-bound (< ~1/6 of the rows) and loses when dense, where the decode becomes issue-bound.
-static ColRef col_ref(const Column *c, bool dense = false) {
+// Which form of the column a probe reads when both are resident (cubit_gpu_pack_column keep_raw = 1).  Packed
+// moves fewer bytes but costs more instructions and one more dependent load per value: measured
+// (profiles/r1_experiment_packed_payload.log) it wins in the middle band — bit-driven probe, 1/256 .. 1/6 of the
+// rows selected, where the raw gather is DRAM-bound on 128-byte fetches — and loses for dense selections (the
+// decode becomes issue-bound) and for the sparse gather over row IDs (latency-bound).  prefer_raw = those two.
+static ColRef col_ref(const Column *c, bool prefer_raw = false) {
 	ColRef r;
 	r.raw = nullptr;
 	r.words = nullptr;
 	r.hdr = nullptr;
 	if (c) {
-		if (c->packed() && !(dense && c->d)) {
+		if (c->packed() && !(prefer_raw && c->d)) {
 			r.words = c->d_words;
 			r.hdr = c->d_hdr;
 		} else {
@@ -1655,14 +1657,14 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 		pa.row_base = t->row_base;
 		pa.n_cols = want_vals && cap ? (int)q->n_cols : 0;
 		for (int c = 0; c < pa.n_cols; c++) {
-			pa.col[c] = vcols[c]->packed() ? nullptr : vcols[c]->d;
-			pa.packed[c] = col_ref(vcols[c]);
+			pa.col[c] = vcols[c]->d; // the gather over row IDs prefers the raw form when it is resident: one
+			pa.packed[c] = col_ref(vcols[c], true); // dependent load per value instead of header + payload
 			pa.out[c] = r->d_vals[c];
 			pa.elem_bytes[c] = vcols[c]->elem;
 		}
 		pa.agg_kind = q->agg_kind;
-		pa.agg_a = col_ref(agg_a);
-		pa.agg_b = col_ref(agg_b);
+		pa.agg_a = col_ref(agg_a, true);
+		pa.agg_b = col_ref(agg_b, true);
 		pa.partials = partials;
 		pa.done = probe_done;
 		pa.hdr = r->d_hdr;
@@ -1864,12 +1866,12 @@ extern "C" int cubit_gpu_probe(cubit_gpu_table *t, int32_t col_id, const int64_t
 	pa.n = n;
 	pa.row_base = t->row_base;
 	pa.n_cols = host_out ? 1 : 0;
-	pa.col[0] = c.packed() ? nullptr : c.d;
-	pa.packed[0] = col_ref(&c);
+	pa.col[0] = c.d;
+	pa.packed[0] = col_ref(&c, true);
 	pa.out[0] = d_out;
 	pa.elem_bytes[0] = c.elem;
 	pa.agg_kind = want_sum ? CUBIT_AGG_SUM : CUBIT_AGG_NONE;
-	pa.agg_a = col_ref(&c);
+	pa.agg_a = col_ref(&c, true);
 	pa.hdr = reinterpret_cast<ResultHeader *>(d_blk);
 	pa.done = reinterpret_cast<unsigned int *>(d_blk + 64);
 	pa.partials = reinterpret_cast<BlockPartial *>(d_blk + 128);

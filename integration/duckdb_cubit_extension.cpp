@@ -28,7 +28,15 @@
 #include "duckdb/optimizer/optimizer_extension.hpp"
 #include "duckdb/planner/filter/conjunction_filter.hpp"
 #include "duckdb/planner/filter/constant_filter.hpp"
+#include "duckdb/planner/operator/logical_delete.hpp"
 #include "duckdb/planner/operator/logical_get.hpp"
+#include "duckdb/planner/operator/logical_insert.hpp"
+#include "duckdb/planner/operator/logical_update.hpp"
+#include "duckdb/storage/block_manager.hpp"
+#include "duckdb/storage/buffer_manager.hpp"
+#include "duckdb/storage/data_table.hpp"
+#include "duckdb/storage/table_io_manager.hpp"
+#include "duckdb/storage/table_storage_info.hpp"
 
 #include "cubit_gpu.h"
 
@@ -94,6 +102,88 @@ static unique_ptr<FunctionData> CubitLoadBind(ClientContext &, TableFunctionBind
 	return std::move(bind);
 }
 
+// ---- storage route: hand a column's ON-DISK segments to the GPU as they are.
+// GetColumnSegmentInfo is what pragma_storage_info shows (src/function/table/system/pragma_storage_info.cpp):
+// per segment its first row, row count, compression, and where its bytes live (block_id, block_offset).  The
+// block is pinned through the buffer manager exactly as BitpackingScanState does (bitpacking.cpp:627-636) and
+// the bytes go to cubit_gpu_upload_column_segments untouched; the GPU decodes them.  Returns false (and the
+// caller falls back to pulling decoded rows through a query) unless EVERY segment of the column is a
+// persistent, un-updated BitPacking or Uncompressed INT64 segment without NULLs.
+static std::atomic<idx_t> cubit_segment_columns {0};
+idx_t CubitSegmentRouteCount() {
+	return cubit_segment_columns.load();
+}
+
+static bool CubitUploadColumnSegments(ClientContext &context, const string &table, idx_t table_column,
+                                      const LogicalType &type, cubit_gpu_table *handle, int32_t gpu_col, idx_t row_count) {
+	if (type.InternalType() != PhysicalType::INT64) {
+		return false;
+	}
+	auto &entry = Catalog::GetEntry<TableCatalogEntry>(context, INVALID_CATALOG, DEFAULT_SCHEMA, table);
+	if (!entry.IsDuckTable()) {
+		return false;
+	}
+	auto &storage = entry.GetStorage();
+	auto &block_manager = TableIOManager::Get(storage).GetBlockManagerForRowData();
+	if (block_manager.InMemory()) {
+		return false;
+	}
+	vector<ColumnSegmentInfo> mine;
+	for (auto &info : entry.GetColumnSegmentInfo()) {
+		if (info.column_id != table_column) {
+			continue;
+		}
+		if (info.segment_type == "VALIDITY") {
+			if (info.segment_stats.find("Has Null: false") == string::npos) {
+				return false; // NULL keys/values are not handled on this route
+			}
+			continue;
+		}
+		if (!info.persistent || info.has_updates || info.block_id < 0 ||
+		    (info.compression_type != "BitPacking" && info.compression_type != "Uncompressed")) {
+			return false;
+		}
+		mine.push_back(info);
+	}
+	std::sort(mine.begin(), mine.end(),
+	          [](const ColumnSegmentInfo &a, const ColumnSegmentInfo &b) { return a.segment_start < b.segment_start; });
+	vector<BufferHandle> pins; // keep every block resident until the upload returns
+	vector<cubit_column_segment> segs;
+	idx_t next_row = 0;
+	for (auto &info : mine) {
+		if (info.segment_start != next_row) {
+			return false;
+		}
+		next_row += info.segment_count;
+		auto block = block_manager.RegisterBlock(info.block_id);
+		pins.push_back(block_manager.buffer_manager.Pin(block));
+		auto ptr = pins.back().Ptr() + info.block_offset;
+		cubit_column_segment seg;
+		seg.reserved = 0;
+		seg.row_start = info.segment_start;
+		seg.count = info.segment_count;
+		seg.data = ptr;
+		if (info.compression_type == "BitPacking") {
+			seg.kind = CUBIT_SEG_BITPACKING;
+			seg.bytes = Load<idx_t>(ptr); // offset of the end of the metadata = segment size (bitpacking.cpp:524-544)
+			if (info.block_offset + seg.bytes > block_manager.GetBlockSize()) {
+				return false;
+			}
+		} else {
+			seg.kind = CUBIT_SEG_UNCOMPRESSED;
+			seg.bytes = info.segment_count * sizeof(int64_t);
+		}
+		segs.push_back(seg);
+	}
+	if (next_row != row_count || segs.empty()) {
+		return false;
+	}
+	cubit_decode_info dinfo;
+	CubitCheck(cubit_gpu_upload_column_segments(handle, gpu_col, 8, segs.data(), NumericCast<uint32_t>(segs.size()), &dinfo));
+	cubit_segment_columns++;
+	return true;
+}
+
 static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p, DataChunk &output) {
 	auto &bind = data_p.bind_data->CastNoConst<CubitLoadBindData>();
 	if (bind.done) {
@@ -145,7 +235,11 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 	gpu->cardinality = bind.cardinality;
 	CubitCheck(cubit_gpu_create(0, gpu->row_count, 0, 65536, &gpu->handle));
 	for (idx_t k = 0; k < cols.size(); k++) {
-		CubitCheck(cubit_gpu_upload_column(gpu->handle, NumericCast<int32_t>(k), cols[k].data(), 8, gpu->row_count));
+		// compressed segments straight from the buffer manager when the column qualifies, decoded rows otherwise
+		if (!CubitUploadColumnSegments(context, bind.table, int_cols[k], res->types[int_cols[k]], gpu->handle,
+		                               NumericCast<int32_t>(k), gpu->row_count)) {
+			CubitCheck(cubit_gpu_upload_column(gpu->handle, NumericCast<int32_t>(k), cols[k].data(), 8, gpu->row_count));
+		}
 	}
 	CubitCheck(cubit_gpu_index_create(gpu->handle, gpu->cardinality, &gpu->index_id));
 	CubitCheck(cubit_gpu_index_build(gpu->handle, gpu->index_id, NumericCast<int32_t>(key_col), gpu->base_value));
@@ -450,7 +544,41 @@ static void CubitRewritePlan(LogicalOperator &op) {
 	}
 }
 
+// DML on an indexed table: this glue does not sit in the index-maintenance path (that needs a registered index
+// type, bound_index.hpp:71-97 → cubit_gpu_set_delta / cubit_gpu_append_rows), so the GPU copy would go stale.
+// The statement itself keeps the vanilla scan, and the table's GPU index is dropped: later scans fall back to
+// the vanilla path until cubit_load is called again.
+static bool CubitInvalidateOnDml(LogicalOperator &op) {
+	bool dml = false;
+	const TableCatalogEntry *target = nullptr;
+	switch (op.type) {
+	case LogicalOperatorType::LOGICAL_UPDATE:
+		target = &op.Cast<LogicalUpdate>().table;
+		break;
+	case LogicalOperatorType::LOGICAL_DELETE:
+		target = &op.Cast<LogicalDelete>().table;
+		break;
+	case LogicalOperatorType::LOGICAL_INSERT:
+		target = &op.Cast<LogicalInsert>().table;
+		break;
+	default:
+		break;
+	}
+	if (target) {
+		dml = true;
+		std::lock_guard<std::mutex> lk(cubit_registry_lock);
+		cubit_registry.erase(target->name);
+	}
+	for (auto &child : op.children) {
+		dml |= CubitInvalidateOnDml(*child);
+	}
+	return dml;
+}
+
 static void CubitOptimize(OptimizerExtensionInput &, unique_ptr<LogicalOperator> &plan) {
+	if (CubitInvalidateOnDml(*plan)) {
+		return;
+	}
 	CubitRewritePlan(*plan);
 }
 

@@ -58,6 +58,28 @@ int cubit_gpu_upload_column(cubit_gpu_table *t, int32_t col_id, const void *data
 	memcpy(t->cols[col_id], data, n * 8);
 	return CUBIT_OK;
 }
+int oracle_bitpacking_decode(const uint8_t *seg, uint64_t seg_bytes, uint32_t elem_bytes, uint64_t count, void *out,
+                             uint64_t *mode_hist);
+int cubit_gpu_upload_column_segments(cubit_gpu_table *t, int32_t col_id, uint32_t elem_bytes,
+                                     const cubit_column_segment *segs, uint32_t n_segs, cubit_decode_info *info) {
+	if (elem_bytes != 8 || col_id < 0 || col_id >= MAX_COLS) { snprintf(g_err, sizeof g_err, "mock: bad column"); return CUBIT_EINVAL; }
+	int64_t *col = malloc(t->n_rows * 8);
+	uint64_t next = 0, hist[6] = {0};
+	for (uint32_t i = 0; i < n_segs; i++) {
+		const cubit_column_segment *s = &segs[i];
+		if (s->row_start != next || next + s->count > t->n_rows) { free(col); snprintf(g_err, sizeof g_err, "mock: segments do not tile"); return CUBIT_EINVAL; }
+		if (s->kind == CUBIT_SEG_UNCOMPRESSED) memcpy(col + next, s->data, s->count * 8);
+		else if (s->kind == CUBIT_SEG_BITPACKING) {
+			if (oracle_bitpacking_decode(s->data, s->bytes, 8, s->count, col + next, hist) != 0) { free(col); snprintf(g_err, sizeof g_err, "mock: malformed segment"); return CUBIT_EINVAL; }
+		} else { free(col); snprintf(g_err, sizeof g_err, "mock: kind"); return CUBIT_EINVAL; }
+		next += s->count;
+	}
+	if (next != t->n_rows) { free(col); snprintf(g_err, sizeof g_err, "mock: rows"); return CUBIT_EINVAL; }
+	free(t->cols[col_id]);
+	t->cols[col_id] = col;
+	if (info) { memset(info, 0, sizeof(*info)); info->n_groups = hist[2] + hist[3] + hist[4] + hist[5]; }
+	return CUBIT_OK;
+}
 int cubit_gpu_index_create(cubit_gpu_table *t, uint32_t cardinality, int32_t *index_id) {
 	t->card = cardinality; t->bits = calloc((size_t)cardinality * t->n_words, 8); *index_id = 0;
 	return CUBIT_OK;

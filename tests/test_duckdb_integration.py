@@ -46,6 +46,9 @@ def test_glue_sql_equals_vanilla_scan_with_oracle_mock(tmp_path):
                            os.path.join(mock_dir, "libcubit_gpu_mock.so"), "-L", os.path.join(ROOT, "oracle"),
                            "-lcubit_oracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
     exe = _build(mock_dir, "sql_mock", mock_dir, "cubit_gpu_mock")
-    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    r = subprocess.run([exe, "--db", os.path.join(mock_dir, "storage_route.db")], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True)
     assert r.returncode == 0, r.stderr
     assert "duckdb_sql_test ok" in r.stdout
+    # columns of a checkpointed, file-backed table reached the C-ABI as the reference's compressed segments
+    assert "storage route ok" in r.stdout

@@ -83,8 +83,25 @@ __device__ __forceinline__ void add128(unsigned long long &lo, long long &hi, un
 	hi += hi2 + (long long)(lo < lo2);
 }
 
-constexpr int kReqSlots = 4;       // look-back requests in flight per CTA (> emission deferral depth)
-constexpr int kDefer = 2;          // segments merged between a segment's merge and its emission
+#ifndef CUBIT_PREFIX_DELAY_NS
+#define CUBIT_PREFIX_DELAY_NS 0
+#endif
+#ifndef CUBIT_PREFIX_RETRY_NS
+#define CUBIT_PREFIX_RETRY_NS 64
+#endif
+#ifndef CUBIT_DEFER
+#define CUBIT_DEFER 2
+#endif
+#ifndef CUBIT_REQ_SLOTS
+#define CUBIT_REQ_SLOTS 4
+#endif
+constexpr int kReqSlots = CUBIT_REQ_SLOTS; // look-back requests in flight per CTA (> emission deferral depth)
+constexpr int kDefer = CUBIT_DEFER;        // segments merged between a segment's merge and its emission
+#ifndef CUBIT_PREFIX_LAG
+#define CUBIT_PREFIX_LAG (CUBIT_DEFER - 1)
+#endif
+constexpr int kPrefixLag = CUBIT_PREFIX_LAG; // requests posted after request n before the prefix warp serves n
+static_assert(kPrefixLag >= 0 && kPrefixLag < kDefer && kReqSlots > kDefer, "look-back pipeline depth");
 constexpr int kWaitBatch = 4;      // ring stages consumed per mbarrier round trip
 constexpr int kDeltaStage = 32;    // delta words staged in shared memory per ring stage (the rest is read from L2)
 constexpr int kSlotRows = 32 * 64; // rows one warp compacts at a time (32 lanes × one 64-bit word)
@@ -125,7 +142,7 @@ __device__ __forceinline__ unsigned long long sum_aggregates(const unsigned long
 				}
 			}
 			if (__any_sync(0xffffffffu, pending != 0)) {
-				__nanosleep(64); // some predecessor is still being merged: re-read only the holes
+				__nanosleep(CUBIT_PREFIX_RETRY_NS); // some predecessor is still being merged: re-read only the holes
 			}
 		}
 	}

@@ -191,15 +191,31 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 		}
 		int64_t t0 = -1;            // last segment handled by this CTA
 		unsigned long long s0 = 0; // popcount of segments [0, t0]
+		// Request n is served once request n + kPrefixLag has been posted (the end marker counts), i.e.
+		// kPrefixLag segment-times after it was posted and still a segment-time before its answer is
+		// needed: by then its predecessors' aggregates have (almost always) landed, so the look-back is
+		// ONE round of status loads.  Polling at once instead re-reads the holes for microseconds from
+		// every CTA, and that L2 traffic costs the bulk-copy stream 10-15 % (profiles/r1_sweep_v13_prefix_lag.log).
+		uint32_t seen = 0, exit_at = kNoTile;
 		for (uint32_t n = 0;; n++) {
-			const uint32_t slot = n % kReqSlots, par = (n / kReqSlots) & 1;
-			mbar_wait(&sm.req_full[slot], par);
-			const uint32_t tile = sm.req_tile[slot];
-			if (tile == kNoTile) {
+			while (seen <= n + (uint32_t)kPrefixLag && exit_at == kNoTile) {
+				mbar_wait(&sm.req_full[seen % kReqSlots], (seen / kReqSlots) & 1);
+				if (sm.req_tile[seen % kReqSlots] == kNoTile) {
+					exit_at = seen;
+				}
+				seen++;
+			}
+			if (n == exit_at) {
 				return;
 			}
+			const uint32_t slot = n % kReqSlots;
+			const uint32_t tile = sm.req_tile[slot];
 			const uint32_t total = sm.req_total[slot];
-			const unsigned long long excl = s0 + sum_aggregates(status, t0 + 1, (int64_t)tile, lane);
+#if CUBIT_PREFIX_DELAY_NS
+			__nanosleep(CUBIT_PREFIX_DELAY_NS);
+#endif
+			const unsigned long long excl =
+			    s0 + ((a.debug & 8u) ? 0ull : sum_aggregates(status, t0 + 1, (int64_t)tile, lane));
 			if (lane == 0) {
 				sm.resp_excl[slot] = excl;
 				mbar_arrive(&sm.resp_full[slot]);
@@ -216,7 +232,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 	// ---------------------------------------------------------------- consumer warps
 	// timing experiments only (see kernels.h): 2 = skip emission, 7 = no look-back traffic at all; anything
 	// else could unbalance the request/response mbarriers, so it is ignored
-	const unsigned dbg = (a.debug == 2u || a.debug == 7u) ? a.debug : 0u;
+	const unsigned dbg = (a.debug == 2u || a.debug == 7u || a.debug == 10u) ? a.debug : 0u;
 	uint32_t stage = 0, phase = 0;
 	unsigned long long blk_count = 0; // meaningful in thread 0
 	Agg agg;

@@ -105,12 +105,20 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 		// Lane 0 walks the ring and issues the bulk copies.  With pending deltas the other lanes
 		// fetch the delta CSR offsets of the NEXT segment (its ticket is known one segment ahead)
 		// while lane 0 is busy, so those dependent loads never sit in front of a bulk copy.
+		// Tickets (one segment each, so segments are merged in roughly global order, which the look-back
+		// relies on) are drawn `a.ticket_depth` segments ahead: lane j of this warp holds the ticket of
+		// iteration i ≡ j (mod depth) and re-draws right after it was consumed, so the atomic's round trip
+		// to L2 (≈ 1 µs under load) overlaps `depth` segments of bulk copies instead of gating each one —
+		// with few bitvectors per query a segment is only one or two 8 KiB copies.
 		uint32_t stage = 0, phase = 0;
-		uint32_t tile = 0;
-		if (lane == 0) {
-			tile = atomicAdd(ticket, 1u);
-		}
-		tile = __shfl_sync(0xffffffffu, tile, 0);
+		const uint32_t td = a.ticket_depth; // 2..8
+		// the first `depth` rounds are assigned statically (round j: segment j·grid + CTA) — drawing them
+		// with one warp-wide atomic would hand each CTA `depth` CONSECUTIVE segments, which serialises the
+		// look-back; the counter then continues from depth·grid
+		const uint32_t tbase = td * gridDim.x;
+		uint32_t my_ticket = (uint32_t)lane * gridDim.x + blockIdx.x;
+		uint32_t tslot = 0; // lane holding the current iteration's ticket
+		uint32_t tile = __shfl_sync(0xffffffffu, my_ticket, 0);
 		uint32_t dlo[2] = {0, 0}, dhi[2] = {0, 0}; // CSR offsets of streams lane and lane+32 for `tile`
 		auto load_offsets = [&](uint32_t tl) {
 #pragma unroll
@@ -128,11 +136,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 		}
 		while (true) {
 			const bool valid = tile < a.n_seg;
-			uint32_t next = 0;
-			if (valid && lane == 0) {
-				next = atomicAdd(ticket, 1u); // prefetched: consumed one segment later
+			if (valid && lane == (int)tslot) {
+				my_ticket = tbase + atomicAdd(ticket, 1u); // consumed `depth` iterations from now
 			}
-			next = __shfl_sync(0xffffffffu, next, 0);
+			tslot = tslot + 1 == td ? 0 : tslot + 1;
+			const uint32_t next = __shfl_sync(0xffffffffu, my_ticket, tslot); // drawn depth-1 iterations ago
 			if (HAS_DELTA) {
 #pragma unroll
 				for (int h = 0; h < 2; h++) {
@@ -584,7 +592,11 @@ static cudaError_t launch_scan_t(const ScanArgs &args, int sm_count, cudaStream_
 	if (grid_out) {
 		*grid_out = (int)grid;
 	}
-	kern<<<(unsigned)grid, kScanThreads, smem, stream>>>(args);
+	// tickets in flight per CTA: ≈ 16 bulk copies' worth, 2..8 (see the producer warp)
+	ScanArgs largs = args;
+	const uint32_t td = 16u / (args.k ? args.k : 1u);
+	largs.ticket_depth = td < 2u ? 2u : (td > 8u ? 8u : td);
+	kern<<<(unsigned)grid, kScanThreads, smem, stream>>>(largs);
 	return cudaGetLastError();
 }
 

@@ -379,6 +379,93 @@ __device__ __forceinline__ void emit_span(const ScanArgs &a, const uint64_t (&q)
 	}
 }
 
+// ---- the same emission cut into steps, so that the scan kernel can interleave the write-out of a pending
+// segment with the fold of the next one (the ring keeps draining while a dense segment is written out).
+// sparse / medium span: step 0 stages every slot, step 1 writes out; dense span: one step per slot.
+constexpr uint32_t kEmitDone = 0xffu;
+struct EmitState {
+	uint32_t step = kEmitDone; // next step, kEmitDone = nothing (left) to do
+	uint32_t span_total = 0;   // selected rows of the span
+	unsigned long long pos0 = 0; // output position of the next row to emit
+};
+
+template <int WPT>
+__device__ __forceinline__ void emit_begin(const uint64_t (&q)[WPT], unsigned long long wbase, EmitState &es) {
+	uint32_t lane_total = 0;
+#pragma unroll
+	for (int i = 0; i < WPT; i++) {
+		lane_total += __popcll(q[i]);
+	}
+	es.span_total = __reduce_add_sync(0xffffffffu, lane_total);
+	es.pos0 = wbase;
+	es.step = es.span_total ? 0u : kEmitDone;
+}
+
+template <int WPT, int NL, bool POS>
+__device__ __forceinline__ void emit_step(const ScanArgs &a, const uint64_t (&q)[WPT], uint16_t *cbuf,
+                                          int64_t span_row0, int lane, Agg &agg, EmitState &es) {
+	const uint32_t dummy = (uint32_t)(kSlotRows + 8 + lane);
+	if (es.span_total <= (uint32_t)kSlotRows && WPT * kSlotRows <= 65536) {
+		const uint32_t pad = (uint32_t)es.pos0 & 1u;
+		if (es.step == 0) {
+			uint32_t c[WPT], incl[WPT];
+#pragma unroll
+			for (int i = 0; i < WPT; i++) {
+				c[i] = __popcll(q[i]);
+				incl[i] = c[i];
+			}
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+				for (int i = 0; i < WPT; i++) {
+					const uint32_t n = __shfl_up_sync(0xffffffffu, incl[i], d);
+					if (lane >= d) {
+						incl[i] += n;
+					}
+				}
+			}
+			uint32_t base = pad;
+#pragma unroll
+			for (int i = 0; i < WPT; i++) {
+				stage_word(cbuf, base + incl[i] - c[i], (uint32_t)q[i], (uint32_t)(q[i] >> 32),
+				           (uint32_t)(i * kSlotRows + lane * 64), dummy);
+				base += __shfl_sync(0xffffffffu, incl[i], 31);
+			}
+			__syncwarp();
+			es.step = 1;
+		} else {
+			write_out<NL, POS>(a, cbuf, pad, es.span_total, es.pos0, span_row0, lane, agg);
+			__syncwarp();
+			es.step = kEmitDone;
+		}
+		return;
+	}
+#pragma unroll
+	for (int i = 0; i < WPT; i++) {
+		if (es.step == (uint32_t)i) {
+			const uint32_t c = __popcll(q[i]);
+			uint32_t incl = c;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+				if (lane >= d) {
+					incl += n;
+				}
+			}
+			const uint32_t slot_total = __shfl_sync(0xffffffffu, incl, 31);
+			if (slot_total) {
+				const uint32_t pad = (uint32_t)es.pos0 & 1u;
+				stage_word(cbuf, pad + incl - c, (uint32_t)q[i], (uint32_t)(q[i] >> 32), (uint32_t)lane * 64u, dummy);
+				__syncwarp();
+				write_out<NL, POS>(a, cbuf, pad, slot_total, es.pos0, span_row0 + (int64_t)i * kSlotRows, lane, agg);
+				__syncwarp();
+				es.pos0 += slot_total;
+			}
+		}
+	}
+	es.step = es.step + 1 == (uint32_t)WPT ? kEmitDone : es.step + 1;
+}
+
 // WPT: 64-bit words of Q each consumer thread holds → segment = 256*WPT words
 //      (WPT 2/4/8 ↔ 32768/65536/131072 rows per segment).
 // NL : distinct int64 columns gathered at every selected row (fused probe).

@@ -246,13 +246,16 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 	Agg agg;
 	uint32_t it = 0;
 
-	// The PENDING segments: merged and counted one and two iterations ago, aggregates
-	// published, look-back requests handed to the prefix warp.  A segment is emitted after
-	// the two following segments have been merged, by which time the prefix warp has its
-	// exclusive prefix ready (its predecessors' aggregates have had two segment-times to land).
+	// The PENDING segments: merged and counted up to kDefer iterations ago, aggregates published,
+	// look-back requests handed to the prefix warp.  The oldest one is emitted WHILE the current
+	// segment is merged, one emission step after every batch of ring stages (so the ring keeps
+	// draining during a dense write-out) and the rest after the current aggregate is published;
+	// by then the prefix warp has had its exclusive prefix ready for a whole segment-time.
 	uint64_t pq[kDefer][WPT];
 	uint32_t ptile[kDefer] = {}, ptotal[kDefer] = {}, pwexcl[kDefer] = {}, pit[kDefer] = {};
 	bool have_p[kDefer] = {};
+	const uint32_t n_batches = (a.k + (uint32_t)UB - 1) / (uint32_t)UB;
+	bool draining = false; // input exhausted: only pending segments are left
 
 	while (true) {
 		uint64_t q[WPT], g[WPT];
@@ -261,178 +264,194 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 			q[i] = ~0ull;
 			g[i] = 0;
 		}
-		uint32_t tile = 0;
-		for (uint32_t s = 0; s < a.k; s += UB) {
-			const uint32_t nb = (a.k - s) < (uint32_t)UB ? (a.k - s) : (uint32_t)UB;
-			// lane u polls ring stage (stage + u): one mbarrier round trip per batch
-			if (lane < (int)nb) {
-				uint32_t st = stage + lane, ph = phase;
-				if (st >= kStages) {
-					st -= kStages;
-					ph ^= 1;
-				}
-				mbar_wait(&sm.full[st], ph);
-			}
-			__syncwarp();
-			if (s == 0) {
-				tile = sm.meta[stage].tile;
-			}
-			if (HAS_DELTA && tile != kNoTile) {
-				// Every warp applies the delta words that fall into ITS span of the staged segment
-				// (XOR in shared memory, then the fold below picks them up): no block-wide barrier.
-				bool wrote = false;
-				for (uint32_t u = 0; u < nb; u++) {
-					const uint32_t st = (stage + u) % kStages;
-					const uint32_t dcnt = sm.meta[st].dcnt;
-					for (uint32_t e = lane; e < dcnt; e += 32) {
-						uint4 raw;
-						if (e < (uint32_t)kDeltaStage) {
-							raw = *reinterpret_cast<const uint4 *>(&sm.dbuf[st][e]);
-						} else {
-							raw = __ldg(reinterpret_cast<const uint4 *>(a.dent[s + u] + sm.meta[st].d0 + e));
-						}
-						const uint32_t rel = raw.x - (uint32_t)(warp * kSpanWords);
-						if (rel < (uint32_t)kSpanWords) { // words are unique per (stream, segment)
-							sm.stage[st][raw.x] ^= ((uint64_t)raw.w << 32) | raw.z;
-							wrote = true;
-						}
+		uint32_t tile = kNoTile;
+		uint32_t tile_total = 0, warp_excl = 0;
+		bool e_todo = have_p[kDefer - 1] && need_emit; // the oldest pending segment is still to be emitted
+		bool e_open = false;
+		EmitState es;
+		const uint32_t nb_iter = draining ? 0u : n_batches;
+		for (uint32_t b = 0;; b++) {
+			if (b < nb_iter) {
+				// ---- fold one batch of ring stages
+				const uint32_t s = b * (uint32_t)UB;
+				const uint32_t nb = (a.k - s) < (uint32_t)UB ? (a.k - s) : (uint32_t)UB;
+				// lane u polls ring stage (stage + u): one mbarrier round trip per batch
+				if (lane < (int)nb) {
+					uint32_t st = stage + lane, ph = phase;
+					if (st >= kStages) {
+						st -= kStages;
+						ph ^= 1;
 					}
-				}
-				if (wrote) {
-					fence_proxy_async_smem(); // generic-proxy writes before the stage is refilled by the async proxy
+					mbar_wait(&sm.full[st], ph);
 				}
 				__syncwarp();
-			}
-			if (tile != kNoTile) {
-#pragma unroll
-				for (int u = 0; u < UB; u++) {
-					if (u < (int)nb) {
-						const uint64_t *src = &sm.stage[(stage + u) % kStages][warp * kSpanWords];
-#pragma unroll
-						for (int i = 0; i < WPT; i++) {
-							g[i] |= src[i * 32 + lane];
+				if (s == 0) {
+					tile = sm.meta[stage].tile;
+				}
+				if (HAS_DELTA && tile != kNoTile) {
+					// Every warp applies the delta words that fall into ITS span of the staged segment
+					// (XOR in shared memory, then the fold below picks them up): no block-wide barrier.
+					bool wrote = false;
+					for (uint32_t u = 0; u < nb; u++) {
+						const uint32_t st = (stage + u) % kStages;
+						const uint32_t dcnt = sm.meta[st].dcnt;
+						for (uint32_t e = lane; e < dcnt; e += 32) {
+							uint4 raw;
+							if (e < (uint32_t)kDeltaStage) {
+								raw = *reinterpret_cast<const uint4 *>(&sm.dbuf[st][e]);
+							} else {
+								raw = __ldg(reinterpret_cast<const uint4 *>(a.dent[s + u] + sm.meta[st].d0 + e));
+							}
+							const uint32_t rel = raw.x - (uint32_t)(warp * kSpanWords);
+							if (rel < (uint32_t)kSpanWords) { // words are unique per (stream, segment)
+								sm.stage[st][raw.x] ^= ((uint64_t)raw.w << 32) | raw.z;
+								wrote = true;
+							}
 						}
-						if ((a.group_end >> (s + u)) & 1ull) {
+					}
+					if (wrote) {
+						fence_proxy_async_smem(); // generic-proxy writes before the stage is refilled by the async proxy
+					}
+					__syncwarp();
+				}
+				if (tile != kNoTile) {
+#pragma unroll
+					for (int u = 0; u < UB; u++) {
+						if (u < (int)nb) {
+							const uint64_t *src = &sm.stage[(stage + u) % kStages][warp * kSpanWords];
 #pragma unroll
 							for (int i = 0; i < WPT; i++) {
-								q[i] &= g[i];
-								g[i] = 0;
+								g[i] |= src[i * 32 + lane];
+							}
+							if ((a.group_end >> (s + u)) & 1ull) {
+#pragma unroll
+								for (int i = 0; i < WPT; i++) {
+									q[i] &= g[i];
+									g[i] = 0;
+								}
 							}
 						}
 					}
 				}
-			}
-			__syncwarp();
-			if (lane < (int)nb) {
-				mbar_arrive(&sm.empty[(stage + lane) % kStages]);
-			}
-			stage += nb;
-			if (stage >= kStages) {
-				stage -= kStages;
-				phase ^= 1;
-			}
-		}
-		const bool finished = tile == kNoTile;
-
-		uint32_t tile_total = 0, warp_excl = 0;
-		if (!finished) {
-			// ---- merged bitvector out (optional)
-			if (a.q_out) {
-				uint64_t *dst = a.q_out + (size_t)tile * kTileWords + warp * kSpanWords;
-#pragma unroll
-				for (int i = 0; i < WPT; i++) {
-					dst[i * 32 + lane] = q[i];
+				__syncwarp();
+				if (lane < (int)nb) {
+					mbar_arrive(&sm.empty[(stage + lane) % kStages]);
 				}
-			}
-			// ---- decode, step 1: popcount, warp reduce, block scan over the warp totals
-			uint32_t cnt = 0;
-#pragma unroll
-			for (int i = 0; i < WPT; i++) {
-				cnt += __popcll(q[i]);
-			}
-#pragma unroll
-			for (int d = 16; d > 0; d >>= 1) {
-				cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-			}
-			const int buf = it & 1;
-			if (lane == 0) {
-				sm.warp_tot[buf][warp] = cnt;
-			}
-			consumer_bar_sync();
-#pragma unroll
-			for (int w = 0; w < kConsumerWarps; w++) {
-				const uint32_t t = sm.warp_tot[buf][w];
-				warp_excl += (w < warp) ? t : 0u;
-				tile_total += t;
-			}
-			if (threadIdx.x == 0) {
-				blk_count += tile_total;
-				if (need_pos && !(dbg & 4u)) {
-					// publish this segment's aggregate NOW and hand the look-back to the prefix warp
-					st_relaxed_u64(&status[tile], kFlagAgg | (unsigned long long)tile_total);
-					sm.req_tile[it % kReqSlots] = tile;
-					sm.req_total[it % kReqSlots] = tile_total;
-					mbar_arrive(&sm.req_full[it % kReqSlots]);
+				stage += nb;
+				if (stage >= kStages) {
+					stage -= kStages;
+					phase ^= 1;
 				}
-			}
-		} else if (need_pos && threadIdx.x == 0) { // (debug & 4: the prefix warp still gets its exit request)
-			const uint32_t eslot = (dbg & 4u) ? 0u : it % kReqSlots; // no requests were posted: it still waits on slot 0
-			sm.req_tile[eslot] = kNoTile; // tell the prefix warp to exit
-			mbar_arrive(&sm.req_full[eslot]);
-		}
-
-		// ---- emit the oldest pending segment (all of them once the input is exhausted)
-		for (int round = 0; round < (finished ? kDefer : 1); round++) {
-			if (have_p[kDefer - 1] && need_emit) {
-				unsigned long long excl = 0;
-				if (need_pos && !(dbg & 1u)) {
-					const uint32_t slot = pit[kDefer - 1] % kReqSlots, par = (pit[kDefer - 1] / kReqSlots) & 1;
-					if (lane == 0) {
-						mbar_wait(&sm.resp_full[slot], par);
+			} else if (b == nb_iter && !draining) {
+				if (tile != kNoTile) {
+					// ---- merged bitvector out (optional)
+					if (a.q_out) {
+						uint64_t *dst = a.q_out + (size_t)tile * kTileWords + warp * kSpanWords;
+#pragma unroll
+						for (int i = 0; i < WPT; i++) {
+							dst[i * 32 + lane] = q[i];
+						}
 					}
-					__syncwarp();
-					excl = sm.resp_excl[slot];
+					// ---- decode, step 1: popcount, warp reduce, block scan over the warp totals
+					uint32_t cnt = 0;
+#pragma unroll
+					for (int i = 0; i < WPT; i++) {
+						cnt += __popcll(q[i]);
+					}
+					cnt = __reduce_add_sync(0xffffffffu, cnt);
+					const int buf = it & 1;
+					if (lane == 0) {
+						sm.warp_tot[buf][warp] = cnt;
+					}
+					consumer_bar_sync();
+#pragma unroll
+					for (int w = 0; w < kConsumerWarps; w++) {
+						const uint32_t t = sm.warp_tot[buf][w];
+						warp_excl += (w < warp) ? t : 0u;
+						tile_total += t;
+					}
+					if (threadIdx.x == 0) {
+						blk_count += tile_total;
+						if (need_pos && !(dbg & 4u)) {
+							// publish this segment's aggregate NOW and hand the look-back to the prefix warp
+							st_relaxed_u64(&status[tile], kFlagAgg | (unsigned long long)tile_total);
+							sm.req_tile[it % kReqSlots] = tile;
+							sm.req_total[it % kReqSlots] = tile_total;
+							mbar_arrive(&sm.req_full[it % kReqSlots]);
+						}
+					}
+				} else if (need_pos && threadIdx.x == 0) { // (debug & 4: the prefix warp still gets its exit request)
+					const uint32_t eslot = (dbg & 4u) ? 0u : it % kReqSlots; // no requests were posted: it still waits on slot 0
+					sm.req_tile[eslot] = kNoTile; // tell the prefix warp to exit
+					mbar_arrive(&sm.req_full[eslot]);
 				}
-				if (ptotal[kDefer - 1] > 0 && !(dbg & 2u)) {
+			}
+			// ---- one emission step of the oldest pending segment
+			if (e_todo) {
+				if (!e_open) {
+					e_open = true;
+					unsigned long long excl = 0;
+					if (need_pos && !(dbg & 1u)) {
+						const uint32_t slot = pit[kDefer - 1] % kReqSlots, par = (pit[kDefer - 1] / kReqSlots) & 1;
+						if (lane == 0) {
+							mbar_wait(&sm.resp_full[slot], par);
+						}
+						__syncwarp();
+						excl = sm.resp_excl[slot];
+					}
+					if (ptotal[kDefer - 1] > 0 && !(dbg & 2u)) {
+						emit_begin<WPT>(pq[kDefer - 1], excl + pwexcl[kDefer - 1], es);
+					}
+				}
+				if (es.step != kEmitDone) {
 					const int64_t span_row0 =
 					    a.row_base + ((int64_t)ptile[kDefer - 1] * kTileWords + (int64_t)warp * kSpanWords) * 64;
 					if (need_pos) {
-						emit_span<WPT, NL, true>(a, pq[kDefer - 1], sm.compact[warp], excl + pwexcl[kDefer - 1], span_row0,
-						                         lane, agg);
+						emit_step<WPT, NL, true>(a, pq[kDefer - 1], sm.compact[warp], span_row0, lane, agg, es);
 					} else {
-						emit_span<WPT, NL, false>(a, pq[kDefer - 1], sm.compact[warp], 0, span_row0, lane, agg);
+						emit_step<WPT, NL, false>(a, pq[kDefer - 1], sm.compact[warp], span_row0, lane, agg, es);
 					}
 				}
+				e_todo = es.step != kEmitDone;
 			}
-			// shift the queue
-#pragma unroll
-			for (int d = kDefer - 1; d > 0; d--) {
-				have_p[d] = have_p[d - 1];
-				ptile[d] = ptile[d - 1];
-				ptotal[d] = ptotal[d - 1];
-				pwexcl[d] = pwexcl[d - 1];
-				pit[d] = pit[d - 1];
-#pragma unroll
-				for (int i = 0; i < WPT; i++) {
-					pq[d][i] = pq[d - 1][i];
-				}
-			}
-			have_p[0] = !finished;
-			if (!finished) {
-				ptile[0] = tile;
-				ptotal[0] = tile_total;
-				pwexcl[0] = warp_excl;
-				pit[0] = it;
-#pragma unroll
-				for (int i = 0; i < WPT; i++) {
-					pq[0][i] = q[i];
-				}
+			if (b >= nb_iter && !e_todo) {
+				break;
 			}
 		}
-		if (finished) {
-			break;
+		const bool finished = draining || tile == kNoTile;
+
+		// shift the queue
+		bool any_pending = false;
+#pragma unroll
+		for (int d = kDefer - 1; d > 0; d--) {
+			have_p[d] = have_p[d - 1];
+			any_pending |= have_p[d];
+			ptile[d] = ptile[d - 1];
+			ptotal[d] = ptotal[d - 1];
+			pwexcl[d] = pwexcl[d - 1];
+			pit[d] = pit[d - 1];
+#pragma unroll
+			for (int i = 0; i < WPT; i++) {
+				pq[d][i] = pq[d - 1][i];
+			}
 		}
-		it++;
+		have_p[0] = !finished;
+		if (!finished) {
+			ptile[0] = tile;
+			ptotal[0] = tile_total;
+			pwexcl[0] = warp_excl;
+			pit[0] = it;
+#pragma unroll
+			for (int i = 0; i < WPT; i++) {
+				pq[0][i] = q[i];
+			}
+			it++;
+		} else {
+			draining = true;
+			if (!any_pending) {
+				break;
+			}
+		}
 	}
 
 	// ---- one exact atomic accumulate per warp / CTA (hdr is zeroed before the launch; no serial

@@ -38,6 +38,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 		             : "memory");
 	} while (!done);
 }
+// the same for the producer and prefix warps, whose waits are long and not latency-critical: a bare try_wait
+// loop re-issues every few cycles and takes issue slots from the consumer warps of the same scheduler
+// (16 % of all issued instructions at s = 0.1, profiles/r1_ncu_scan_s01.md)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, unsigned ns) {
+	uint32_t addr = smem_u32(bar);
+	uint32_t done;
+	while (true) {
+		asm volatile("{\n\t.reg .pred p;\n\t"
+		             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		             "selp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(done)
+		             : "r"(addr), "r"(parity)
+		             : "memory");
+		if (done) {
+			return;
+		}
+		__nanosleep(ns);
+	}
+}
 // 1-D bulk async copy global → shared, completion on an mbarrier (TMA engine; SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -299,17 +318,37 @@ __device__ __forceinline__ void write_out(const ScanArgs &a, const uint16_t *cbu
 // staging area, so the loop body is straight-line code (no divergence regions).
 __device__ __forceinline__ void stage_word(uint16_t *cbuf, uint32_t p0, uint32_t wlo, uint32_t whi, uint32_t bit0,
                                            uint32_t dummy) {
-	uint32_t p1 = p0 + __popc(wlo);
+	(void)dummy;
+	// running shared-memory byte addresses of the two chains; one step = ctz, predicated 16-bit store,
+	// predicated address bump, clear the lowest set bit (8 SASS instructions per chain, no select / re-derived
+	// address as the compiler generates for the C form)
+	uint32_t a0 = smem_u32(cbuf + p0);
+	uint32_t a1 = a0 + 2u * (uint32_t)__popc(wlo);
 	uint32_t w0 = wlo, w1 = whi;
 	const uint32_t b1 = bit0 + 32u;
 	while (w0 | w1) {
-		const uint32_t i0 = w0 ? p0 : dummy, i1 = w1 ? p1 : dummy;
-		cbuf[i0] = (uint16_t)(bit0 + (uint32_t)(__ffs(w0) - 1));
-		cbuf[i1] = (uint16_t)(b1 + (uint32_t)(__ffs(w1) - 1));
-		p0 += w0 != 0;
-		p1 += w1 != 0;
-		w0 &= w0 - 1; // 0 stays 0
-		w1 &= w1 - 1;
+		asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b32 f, g, t;\n\t.reg .b16 h;\n\t"
+		             "setp.ne.u32 p, %2, 0;\n\t"
+		             "setp.ne.u32 q, %3, 0;\n\t"
+		             "brev.b32 f, %2;\n\t"
+		             "brev.b32 g, %3;\n\t"
+		             "clz.b32 f, f;\n\t"
+		             "clz.b32 g, g;\n\t"
+		             "add.u32 f, f, %4;\n\t"
+		             "add.u32 g, g, %5;\n\t"
+		             "cvt.u16.u32 h, f;\n\t"
+		             "@p st.shared.u16 [%0], h;\n\t"
+		             "cvt.u16.u32 h, g;\n\t"
+		             "@q st.shared.u16 [%1], h;\n\t"
+		             "@p add.u32 %0, %0, 2;\n\t"
+		             "@q add.u32 %1, %1, 2;\n\t"
+		             "add.u32 t, %2, -1;\n\t"
+		             "and.b32 %2, %2, t;\n\t"
+		             "add.u32 t, %3, -1;\n\t"
+		             "and.b32 %3, %3, t;\n\t}"
+		             : "+r"(a0), "+r"(a1), "+r"(w0), "+r"(w1)
+		             : "r"(bit0), "r"(b1)
+		             : "memory");
 	}
 }
 

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 			}
 			if (lane == 0) {
 				for (uint32_t s = 0; s < a.k; s++) {
-					mbar_wait(&sm.empty[stage], phase ^ 1);
+					mbar_wait_sleep(&sm.empty[stage], phase ^ 1, 32);
 					sm.meta[stage].tile = valid ? tile : kNoTile;
 					if (!valid) {
 						mbar_arrive(&sm.full[stage]); // end marker: k empty stages, so batched waits stay uniform
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 		uint32_t seen = 0, exit_at = kNoTile;
 		for (uint32_t n = 0;; n++) {
 			while (seen <= n + (uint32_t)kPrefixLag && exit_at == kNoTile) {
-				mbar_wait(&sm.req_full[seen % kReqSlots], (seen / kReqSlots) & 1);
+				mbar_wait_sleep(&sm.req_full[seen % kReqSlots], (seen / kReqSlots) & 1, 200);
 				if (sm.req_tile[seen % kReqSlots] == kNoTile) {
 					exit_at = seen;
 				}

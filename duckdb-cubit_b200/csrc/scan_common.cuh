@@ -105,6 +105,12 @@ __device__ __forceinline__ void add128(unsigned long long &lo, long long &hi, un
 #ifndef CUBIT_PREFIX_DELAY_NS
 #define CUBIT_PREFIX_DELAY_NS 0
 #endif
+#ifndef CUBIT_STAGE_ASM
+#define CUBIT_STAGE_ASM 1
+#endif
+#ifndef CUBIT_PRODUCER_SLEEP_NS
+#define CUBIT_PRODUCER_SLEEP_NS 0
+#endif
 #ifndef CUBIT_PREFIX_RETRY_NS
 #define CUBIT_PREFIX_RETRY_NS 64
 #endif
@@ -243,7 +249,7 @@ __device__ __forceinline__ void consume_row(const ScanArgs &a, unsigned long lon
 // warp writes 128 consecutive results as two fully contiguous 512-byte stores (lane l:
 // pairs l and l+32), gathers the fused-probe columns for them first (independent loads in
 // flight) and accumulates the aggregates.
-template <int NL, bool POS>
+template <int NL, bool POS, bool PK = true>
 __device__ __forceinline__ void write_out(const ScanArgs &a, const uint16_t *cbuf, uint32_t pad, uint32_t count,
                                           unsigned long long pos0, int64_t row_origin, int lane,
                                           Agg &agg) {
@@ -253,7 +259,7 @@ __device__ __forceinline__ void write_out(const ScanArgs &a, const uint16_t *cbu
 	const uint32_t *cb32 = reinterpret_cast<const uint32_t *>(cbuf);
 	// pack-block headers of the probed columns, parked behind the staging area (kCompactHdrOff)
 	uint4 *hs = reinterpret_cast<uint4 *>(const_cast<uint16_t *>(cbuf) + kCompactHdrOff);
-	if (NL > 0) {
+	if (NL > 0 && PK) { // PK = false: every probed column is a raw array, nothing to stage
 #pragma unroll
 		for (int cc = 0; cc < NL; cc++) {
 			stage_hdrs(a.lcol[cc], local0, lane, hs + cc * kHdrSlots);
@@ -277,7 +283,11 @@ __device__ __forceinline__ void write_out(const ScanArgs &a, const uint16_t *cbu
 				for (int e = 0; e < 2; e++) {
 #pragma unroll
 					for (int cc = 0; cc < NL; cc++) {
-						v[h][e][cc] = load_col_staged(a.lcol[cc], hs + cc * kHdrSlots, local0, r[h][e], ok[h][e]);
+						if (PK) {
+							v[h][e][cc] = load_col_staged(a.lcol[cc], hs + cc * kHdrSlots, local0, r[h][e], ok[h][e]);
+						} else {
+							v[h][e][cc] = ok[h][e] ? __ldg(a.lcol[cc].raw + local0 + r[h][e]) : 0;
+						}
 					}
 				}
 			}
@@ -318,6 +328,20 @@ __device__ __forceinline__ void write_out(const ScanArgs &a, const uint16_t *cbu
 // staging area, so the loop body is straight-line code (no divergence regions).
 __device__ __forceinline__ void stage_word(uint16_t *cbuf, uint32_t p0, uint32_t wlo, uint32_t whi, uint32_t bit0,
                                            uint32_t dummy) {
+#if !CUBIT_STAGE_ASM
+	uint32_t p1 = p0 + __popc(wlo);
+	uint32_t w0 = wlo, w1 = whi;
+	const uint32_t b1 = bit0 + 32u;
+	while (w0 | w1) {
+		const uint32_t i0 = w0 ? p0 : dummy, i1 = w1 ? p1 : dummy;
+		cbuf[i0] = (uint16_t)(bit0 + (uint32_t)(__ffs(w0) - 1));
+		cbuf[i1] = (uint16_t)(b1 + (uint32_t)(__ffs(w1) - 1));
+		p0 += w0 != 0;
+		p1 += w1 != 0;
+		w0 &= w0 - 1; // 0 stays 0
+		w1 &= w1 - 1;
+	}
+#else
 	(void)dummy;
 	// running shared-memory byte addresses of the two chains; one step = ctz, predicated 16-bit store,
 	// predicated address bump, clear the lowest set bit (8 SASS instructions per chain, no select / re-derived
@@ -350,12 +374,13 @@ __device__ __forceinline__ void stage_word(uint16_t *cbuf, uint32_t p0, uint32_t
 		             : "r"(bit0), "r"(b1)
 		             : "memory");
 	}
+#endif
 }
 
 // ---- emission of one warp's span of a merged segment.
 // q[i] of lane l is word (i*32 + l) of the span, so slot i = 2048 consecutive rows and the
 // output order is (slot, lane, bit).
-template <int WPT, int NL, bool POS>
+template <int WPT, int NL, bool POS, bool PK = true>
 __device__ __forceinline__ void emit_span(const ScanArgs &a, const uint64_t (&q)[WPT], uint16_t *cbuf,
                                           unsigned long long wbase, int64_t span_row0, int lane,
                                           Agg &agg) {
@@ -399,7 +424,7 @@ __device__ __forceinline__ void emit_span(const ScanArgs &a, const uint64_t (&q)
 			base += slot_total[i];
 		}
 		__syncwarp();
-		write_out<NL, POS>(a, cbuf, pad, span_total, wbase, span_row0, lane, agg);
+		write_out<NL, POS, PK>(a, cbuf, pad, span_total, wbase, span_row0, lane, agg);
 		__syncwarp();
 		return;
 	}
@@ -412,7 +437,7 @@ __device__ __forceinline__ void emit_span(const ScanArgs &a, const uint64_t (&q)
 		const uint32_t pad = (uint32_t)pos0 & 1u;
 		stage_word(cbuf, pad + incl[i] - c[i], (uint32_t)q[i], (uint32_t)(q[i] >> 32), (uint32_t)lane * 64u, dummy);
 		__syncwarp();
-		write_out<NL, POS>(a, cbuf, pad, slot_total[i], pos0, span_row0 + (int64_t)i * kSlotRows, lane, agg);
+		write_out<NL, POS, PK>(a, cbuf, pad, slot_total[i], pos0, span_row0 + (int64_t)i * kSlotRows, lane, agg);
 		__syncwarp();
 		pos0 += slot_total[i];
 	}

@@ -154,7 +154,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 			}
 			if (lane == 0) {
 				for (uint32_t s = 0; s < a.k; s++) {
-					mbar_wait_sleep(&sm.empty[stage], phase ^ 1, 32);
+#if CUBIT_PRODUCER_SLEEP_NS
+					mbar_wait_sleep(&sm.empty[stage], phase ^ 1, CUBIT_PRODUCER_SLEEP_NS);
+#else
+					mbar_wait(&sm.empty[stage], phase ^ 1);
+#endif
 					sm.meta[stage].tile = valid ? tile : kNoTile;
 					if (!valid) {
 						mbar_arrive(&sm.full[stage]); // end marker: k empty stages, so batched waits stay uniform
@@ -472,11 +476,13 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 // occupied grid (48 warps / SM), which is what the gathers need to keep HBM busy.
 constexpr int kProbeBitsThreads = 256;
 
-template <int WPT, int NL, bool POS>
+// PK: some probed column is FOR-bit-packed (its pack-block headers are staged per warp); PK = false is the
+// all-raw instance, with a smaller staging row and a plain gather.
+template <int WPT, int NL, bool POS, bool PK>
 __global__ void __launch_bounds__(kProbeBitsThreads, 3) cubit_probe_bits_kernel(const __grid_constant__ ScanArgs a) {
 	constexpr int kTileWords = kProbeBitsThreads * WPT;
 	constexpr int kSpanWords = WPT * 32;
-	__shared__ __align__(16) uint16_t compact[kProbeBitsThreads / 32][kCompactHdrOff + NL * kHdrSlots * 8];
+	__shared__ __align__(16) uint16_t compact[kProbeBitsThreads / 32][kCompactHdrOff + (PK ? NL * kHdrSlots * 8 : 0)];
 	__shared__ uint32_t warp_tot[2][kProbeBitsThreads / 32];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	Agg agg;
@@ -522,16 +528,16 @@ __global__ void __launch_bounds__(kProbeBitsThreads, 3) cubit_probe_bits_kernel(
 			wbase = tile_excl + warp_excl;
 		}
 		const int64_t span_row0 = a.row_base + ((int64_t)tile * kTileWords + (int64_t)warp * kSpanWords) * 64;
-		emit_span<WPT, NL, POS>(a, q, compact[warp], wbase, span_row0, lane, agg);
+		emit_span<WPT, NL, POS, PK>(a, q, compact[warp], wbase, span_row0, lane, agg);
 	}
 	if (a.agg_kind != 0) {
 		agg_flush_warp(agg, a.hdr, lane);
 	}
 }
 
-template <int WPT, int NL, bool POS>
-static cudaError_t launch_probe_bits_t(const ScanArgs &args, int sm_count, cudaStream_t stream) {
-	auto kern = cubit_probe_bits_kernel<WPT, NL, POS>;
+template <int WPT, int NL, bool POS, bool PK>
+static cudaError_t launch_probe_bits_p(const ScanArgs &args, int sm_count, cudaStream_t stream) {
+	auto kern = cubit_probe_bits_kernel<WPT, NL, POS, PK>;
 	static int blocks_per_sm = 0; // same for every B200
 	if (blocks_per_sm == 0) {
 		int b = 0;
@@ -550,6 +556,16 @@ static cudaError_t launch_probe_bits_t(const ScanArgs &args, int sm_count, cudaS
 	}
 	kern<<<(unsigned)grid, kProbeBitsThreads, 0, stream>>>(args);
 	return cudaGetLastError();
+}
+
+template <int WPT, int NL, bool POS>
+static cudaError_t launch_probe_bits_t(const ScanArgs &args, int sm_count, cudaStream_t stream) {
+	bool packed = false;
+	for (int c = 0; c < NL; c++) {
+		packed |= args.lcol[c].raw == nullptr;
+	}
+	return packed ? launch_probe_bits_p<WPT, NL, POS, true>(args, sm_count, stream)
+	              : launch_probe_bits_p<WPT, NL, POS, false>(args, sm_count, stream);
 }
 
 template <int WPT>

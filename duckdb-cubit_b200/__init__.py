@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("CUBIT_GPU_LIB") or os.path.join(_HERE, "libcubit_gpu.
 HOST_LIB_PATH = os.path.join(_HERE, "libcubit_host.so")
 
 # ---- mirror of include/cubit_gpu.h -------------------------------------------------
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5
 MAX_STREAMS = 64
 MAX_PROBE_COLS = 8
@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "cubit_gpu_upload_column_segments", "cubit_gpu_append_rows", "cubit_gpu_upload_bitvector_wah",
     "cubit_gpu_query",
     "cubit_gpu_result_wait", "cubit_gpu_result_get", "cubit_gpu_fetch", "cubit_gpu_fetch_bitvector",
-    "cubit_gpu_free_result", "cubit_gpu_probe",
+    "cubit_gpu_free_result", "cubit_gpu_probe", "cubit_gpu_upload_column_validity", "cubit_gpu_fetch_validity",
 ]
 
 
@@ -60,7 +60,7 @@ class ResultInfo(C.Structure):
                 ("algo_bytes_scan", C.c_uint64), ("algo_bytes_probe", C.c_uint64), ("ms_scan", C.c_float),
                 ("ms_probe", C.c_float), ("ms_total", C.c_float), ("fused", C.c_uint32),
                 ("d_rowids", C.c_void_p), ("d_bitvector", C.c_void_p), ("d_values", C.c_void_p * MAX_PROBE_COLS),
-                ("sum_f64", C.c_double)]
+                ("sum_f64", C.c_double), ("agg_rows", C.c_uint64), ("d_validity", C.c_void_p * MAX_PROBE_COLS)]
 
 
 class ColumnSegment(C.Structure):
@@ -135,6 +135,8 @@ def load_library():
         "cubit_gpu_fetch_bitvector": ([vp, vp, u64], C.c_int),
         "cubit_gpu_free_result": ([vp], C.c_int),
         "cubit_gpu_probe": ([vp, i32, vp, u64, vp, P(u64), P(i64)], C.c_int),
+        "cubit_gpu_upload_column_validity": ([vp, i32, vp, u64], C.c_int),
+        "cubit_gpu_fetch_validity": ([vp, u32, u64, u64, vp, P(C.c_int)], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -225,6 +227,19 @@ class Result:
         _check(self._t._L.cubit_gpu_fetch(self._h, offset, n, ids.ctypes.data if ids is not None else None,
                                           len(self._dtypes), ptrs))
         return ids, cols
+
+    def fetch_validity(self, col, offset=0, n=None):
+        """→ (uint64 mask words with bit j = result row offset+j valid, all_valid) for projected column `col`"""
+        if n is None:
+            n = self.count - offset
+        words = np.zeros(max(1, (n + 63) // 64), dtype=np.uint64)
+        allv = C.c_int(0)
+        _check(self._t._L.cubit_gpu_fetch_validity(self._h, col, offset, n, words.ctypes.data, C.byref(allv)))
+        return words[:(n + 63) // 64], bool(allv.value)
+
+    @property
+    def agg_rows(self):
+        return int(self.info.agg_rows)
 
     def bitvector(self):
         q = np.empty(self._t.n_words, dtype=np.uint64)
@@ -338,6 +353,14 @@ class CubitTable:
             raise ValueError("columns are 4 or 8 bytes wide")
         _check(self._L.cubit_gpu_upload_column(self._h, col_id, data.ctypes.data, data.dtype.itemsize, len(data)))
         self._col_dtype[col_id] = data.dtype
+
+    def upload_validity(self, col_id, words):
+        """validity mask of a column (DuckDB ValidityMask words, bit = 1: valid); None drops it"""
+        if words is None:
+            _check(self._L.cubit_gpu_upload_column_validity(self._h, col_id, None, 0))
+            return
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        _check(self._L.cubit_gpu_upload_column_validity(self._h, col_id, words.ctypes.data, len(words)))
 
     def upload_column_segments(self, col_id, elem_bytes, segments):
         """upload a column as the reference's on-disk segments [(kind, row_start, count, uint8 array)] and decode

@@ -30,8 +30,16 @@ __device__ __forceinline__ void add128(unsigned long long &lo, long long &hi, un
 constexpr int kProbeThreads = 256;
 constexpr int kProbePairs = 4; // row-ID pairs per thread per iteration (8 independent gathers in flight)
 
+__device__ __forceinline__ bool row_valid(const unsigned long long *valid, int64_t local) {
+	return !valid || ((__ldg(valid + (local >> 6)) >> (local & 63)) & 1ull);
+}
+
 __device__ __forceinline__ void agg_row(const ProbeArgs &a, int64_t local, unsigned long long &lo, long long &hi,
-                                        unsigned int &ovf, double &fsum) {
+                                        unsigned int &ovf, double &fsum, unsigned long long &nn) {
+	if (!row_valid(a.agg_valid_a, local) || (a.agg_kind == 2 && !row_valid(a.agg_valid_b, local))) {
+		return; // NULL input: not aggregated
+	}
+	nn++;
 	if (a.agg_kind == 3) {
 		fsum += __longlong_as_double(load_col(a.agg_a, local));
 	} else if (a.agg_kind == 1) {
@@ -54,6 +62,7 @@ __global__ void __launch_bounds__(kProbeThreads) cubit_probe_kernel(const __grid
 	long long hi = 0;
 	unsigned int ovf = 0;
 	double fsum = 0.0;
+	unsigned long long nn = 0; // non-NULL aggregate inputs
 
 	const unsigned long long stride = (unsigned long long)gridDim.x * kProbeThreads * kProbePairs;
 	for (unsigned long long base = (unsigned long long)blockIdx.x * kProbeThreads * kProbePairs; base < n_pairs;
@@ -115,8 +124,8 @@ __global__ void __launch_bounds__(kProbeThreads) cubit_probe_kernel(const __grid
 #pragma unroll
 			for (int u = 0; u < kProbePairs; u++) {
 				if (ok[u]) {
-					agg_row(a, id[u].x - a.row_base, lo, hi, ovf, fsum);
-					agg_row(a, id[u].y - a.row_base, lo, hi, ovf, fsum);
+					agg_row(a, id[u].x - a.row_base, lo, hi, ovf, fsum, nn);
+					agg_row(a, id[u].y - a.row_base, lo, hi, ovf, fsum, nn);
 				}
 			}
 		}
@@ -133,7 +142,7 @@ __global__ void __launch_bounds__(kProbeThreads) cubit_probe_kernel(const __grid
 			}
 		}
 		if (a.agg_kind) {
-			agg_row(a, l, lo, hi, ovf, fsum);
+			agg_row(a, l, lo, hi, ovf, fsum, nn);
 		}
 	}
 	if (!a.agg_kind) {
@@ -150,6 +159,12 @@ __global__ void __launch_bounds__(kProbeThreads) cubit_probe_kernel(const __grid
 	}
 	if ((threadIdx.x & 31) == 0 && fsum != 0.0) {
 		atomicAdd(&a.hdr->sum_f64, fsum);
+	}
+	if (a.agg_valid_a || a.agg_valid_b) {
+		nn = __reduce_add_sync(0xffffffffu, (unsigned)nn); // per-warp total stays far below 2^32 (rows / resident threads)
+		if ((threadIdx.x & 31) == 0 && nn) {
+			atomicAdd(&a.hdr->agg_rows, nn);
+		}
 	}
 	if ((threadIdx.x & 31) == 0) {
 		red[threadIdx.x >> 5].sum_lo = lo;
@@ -182,6 +197,35 @@ cudaError_t launch_probe(const ProbeArgs &args, int sm_count, cudaStream_t strea
 }
 int probe_grid(int sm_count) {
 	return sm_count * 8;
+}
+
+// ------------------------------------------------------- validity at row IDs
+__global__ void __launch_bounds__(256) cubit_validity_gather_kernel(const long long *__restrict__ ids,
+                                                                    const unsigned long long *__restrict__ count_ptr,
+                                                                    int64_t row_base,
+                                                                    const unsigned long long *__restrict__ valid,
+                                                                    uint32_t *__restrict__ out32) {
+	const unsigned long long n = *count_ptr;
+	const unsigned long long n32 = (n + 31) & ~31ull;
+	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+	for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += stride) {
+		bool bit = false;
+		if (i < n) {
+			const int64_t local = __ldg(ids + i) - row_base;
+			bit = (__ldg(valid + (local >> 6)) >> (local & 63)) & 1ull;
+		}
+		const unsigned m = __ballot_sync(0xffffffffu, bit);
+		if ((threadIdx.x & 31) == 0) {
+			out32[i >> 5] = m;
+		}
+	}
+}
+
+cudaError_t launch_validity_gather(const long long *ids, const unsigned long long *count_ptr, int64_t row_base,
+                                   const unsigned long long *valid, uint32_t *out32, int sm_count,
+                                   cudaStream_t stream) {
+	cubit_validity_gather_kernel<<<sm_count * 8, 256, 0, stream>>>(ids, count_ptr, row_base, valid, out32);
+	return cudaGetLastError();
 }
 
 // ------------------------------------------------------------- index build

@@ -72,6 +72,9 @@ struct Column {
 	unsigned long long *d_words = nullptr;
 	PackHdr *d_hdr = nullptr;
 	uint64_t packed_bytes = 0;
+	// validity mask (ValidityMask layout, bit = 1: valid), nullptr = the column holds no NULLs
+	unsigned long long *d_valid = nullptr;
+	uint64_t valid_cap_words = 0;
 	bool packed() const {
 		return d_words != nullptr;
 	}
@@ -108,6 +111,9 @@ static void free_column(Column &c) {
 	if (c.d_hdr) {
 		cudaFree(c.d_hdr);
 	}
+	if (c.d_valid) {
+		cudaFree(c.d_valid);
+	}
 	c = Column();
 }
 
@@ -143,6 +149,8 @@ struct cubit_gpu_result {
 	uint64_t *d_q = nullptr;
 	uint64_t *d_q_tmp = nullptr;
 	void *d_vals[CUBIT_MAX_PROBE_COLS] = {};
+	uint32_t *d_valid[CUBIT_MAX_PROBE_COLS] = {}; // validity of the projected values (bit j = result row j), or nullptr
+	bool agg_nulls = false;                       // an aggregate input has a validity mask
 	uint32_t val_elem[CUBIT_MAX_PROBE_COLS] = {};
 	uint32_t n_cols = 0;
 	uint32_t flags = 0;
@@ -712,6 +720,54 @@ extern "C" int cubit_gpu_upload_column(cubit_gpu_table *t, int32_t col_id, const
 	c.n = n;
 	CU_TRY(cudaMemcpyAsync(c.d, data, (size_t)n * elem_bytes, cudaMemcpyHostToDevice, t->stream));
 	CU_TRY(cudaStreamSynchronize(t->stream));
+	if (c.d_valid) { // new contents: all valid until a mask is uploaded again
+		cudaFree(c.d_valid);
+		c.d_valid = nullptr;
+		c.valid_cap_words = 0;
+	}
+	return CUBIT_OK;
+}
+
+// NULLs of a column: its validity mask in the reference's layout (ValidityMask, validity_mask.hpp:50,163-168 —
+// what a validity_uncompressed segment stores, validity_uncompressed.cpp:381).  The probe reports the validity
+// of every projected value (cubit_gpu_fetch_validity) and aggregates skip NULL inputs.
+extern "C" int cubit_gpu_upload_column_validity(cubit_gpu_table *t, int32_t col_id, const uint64_t *words,
+                                                uint64_t n_words) {
+	if (!t) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	std::lock_guard<std::mutex> lk(t->mu);
+	if (use_device(t)) {
+		return CUBIT_ECUDA;
+	}
+	auto it = t->columns.find(col_id);
+	if (it == t->columns.end()) {
+		return fail(CUBIT_EINVAL, "no column %d", col_id);
+	}
+	Column &c = it->second;
+	CU_TRY(cudaStreamSynchronize(t->stream));
+	if (!words) { // drop the mask: every row valid
+		if (c.d_valid) {
+			cudaFree(c.d_valid);
+		}
+		c.d_valid = nullptr;
+		c.valid_cap_words = 0;
+		return CUBIT_OK;
+	}
+	if (n_words != t->n_words) {
+		return fail(CUBIT_EINVAL, "validity mask has %llu words, table needs %llu", (unsigned long long)n_words,
+		            (unsigned long long)t->n_words);
+	}
+	if (c.valid_cap_words < n_words) {
+		if (c.d_valid) {
+			cudaFree(c.d_valid);
+			c.d_valid = nullptr;
+		}
+		CU_TRY(cudaMalloc((void **)&c.d_valid, (n_words + 2) * 8));
+		c.valid_cap_words = n_words;
+	}
+	CU_TRY(cudaMemcpyAsync(c.d_valid, words, n_words * 8, cudaMemcpyHostToDevice, t->stream));
+	CU_TRY(cudaStreamSynchronize(t->stream));
 	return CUBIT_OK;
 }
 
@@ -1207,6 +1263,27 @@ extern "C" int cubit_gpu_append_rows(cubit_gpu_table *t, uint64_t n_new, const c
 		CU_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(c.d) + (size_t)old_n * c.elem, cols[i].data, (size_t)n_new * c.elem,
 		                       cudaMemcpyHostToDevice, t->stream));
 		c.n = new_n;
+		if (c.d_valid) { // appended rows are valid until a new mask is uploaded
+			const uint64_t old_w = (old_n + 63) / 64, new_w = (new_n + 63) / 64;
+			if (new_w > c.valid_cap_words) {
+				const uint64_t capw = std::max<uint64_t>(new_w, c.valid_cap_words + c.valid_cap_words / 2);
+				unsigned long long *nv = nullptr;
+				CU_TRY(cudaMalloc((void **)&nv, (capw + 2) * 8));
+				CU_TRY(cudaMemcpy(nv, c.d_valid, old_w * 8, cudaMemcpyDeviceToDevice));
+				cudaFree(c.d_valid);
+				c.d_valid = nv;
+				c.valid_cap_words = capw;
+			}
+			if (old_n & 63) {
+				unsigned long long last = 0;
+				CU_TRY(cudaMemcpy(&last, c.d_valid + old_w - 1, 8, cudaMemcpyDeviceToHost));
+				last |= ~0ull << (old_n & 63);
+				CU_TRY(cudaMemcpy(c.d_valid + old_w - 1, &last, 8, cudaMemcpyHostToDevice));
+			}
+			if (new_w > old_w) {
+				CU_TRY(cudaMemset(c.d_valid + old_w, 0xff, (new_w - old_w) * 8));
+			}
+		}
 	}
 	t->n_rows = new_n;
 	t->n_seg = (uint32_t)new_n_seg;
@@ -1272,6 +1349,11 @@ static void release_result(cubit_gpu_result *r) {
 			cudaFreeAsync(p, s);
 		}
 	}
+	for (auto &p : r->d_valid) {
+		if (p) {
+			cudaFreeAsync(p, s);
+		}
+	}
 	if (r->h_hdr) {
 		r->t->hdr_pool.push_back(r->h_hdr); // caller holds t->mu
 	}
@@ -1295,6 +1377,7 @@ static int finish_result(cubit_gpu_result *r) {
 	r->info.sum_lo = r->h_hdr->sum_lo;
 	r->info.sum_hi = r->h_hdr->sum_hi;
 	r->info.sum_f64 = r->h_hdr->sum_f64;
+	r->info.agg_rows = r->agg_kind == CUBIT_AGG_NONE ? 0 : (r->agg_nulls ? r->h_hdr->agg_rows : r->h_hdr->count);
 	r->info.algo_bytes_scan += 8ull * ((r->flags & CUBIT_Q_ROWIDS) ? r->info.count : 0);
 	// P of SURVEY §8d: M * Σ width over the distinct columns whose values are needed
 	// (+ 8*M when a separate probe kernel re-reads the row IDs)
@@ -1426,6 +1509,15 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 			}
 			agg_b = &it->second;
 		}
+	}
+	// NULL-bearing columns are probed by the gather kernel over the row-ID list (validity gathered per
+	// projected column, NULL inputs skipped by the aggregate); the bit-driven / fused paths assume no NULLs
+	bool any_nulls = (agg_a && agg_a->d_valid) || (agg_b && agg_b->d_valid);
+	for (uint32_t c = 0; want_vals && c < q->n_cols; c++) {
+		any_nulls |= vcols[c]->d_valid != nullptr;
+	}
+	if (any_nulls) {
+		fusable = false;
 	}
 	const bool need_probe = want_vals || q->agg_kind != CUBIT_AGG_NONE;
 	// The scan-side probe paths gather at most kMaxFusedCols DISTINCT int64 columns per row.
@@ -1665,11 +1757,25 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 		pa.agg_kind = q->agg_kind;
 		pa.agg_a = col_ref(agg_a, true);
 		pa.agg_b = col_ref(agg_b, true);
+		pa.agg_valid_a = agg_a ? agg_a->d_valid : nullptr;
+		pa.agg_valid_b = agg_b ? agg_b->d_valid : nullptr;
+		r->agg_nulls = pa.agg_valid_a || pa.agg_valid_b;
 		pa.partials = partials;
 		pa.done = probe_done;
 		pa.hdr = r->d_hdr;
 		Q_TRY(launch_probe(pa, t->sm_count, st));
 		n_launch++;
+		for (int c = 0; c < pa.n_cols; c++) {
+			if (!vcols[c]->d_valid) {
+				continue;
+			}
+			const size_t vbytes = ((size_t)(cap + 31) / 32 + 2) * 4;
+			Q_TRY(cudaMallocAsync((void **)&r->d_valid[c], vbytes, st));
+			Q_TRY(cudaMemsetAsync(r->d_valid[c], 0, vbytes, st));
+			Q_TRY(launch_validity_gather(r->d_ids, &r->d_hdr->count, t->row_base, vcols[c]->d_valid, r->d_valid[c],
+			                             t->sm_count, st));
+			n_launch++;
+		}
 		if (r->timing) {
 			Q_TRY(cudaEventRecord(r->ev[2], st));
 			r->probe_timed = true;
@@ -1711,6 +1817,7 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 	r->info.d_bitvector = r->d_q;
 	for (uint32_t c = 0; c < r->n_cols; c++) {
 		r->info.d_values[c] = r->d_vals[c];
+		r->info.d_validity[c] = r->d_valid[c];
 	}
 	if (!(q->flags & CUBIT_Q_ASYNC)) {
 		rc = finish_result(r);
@@ -1780,6 +1887,77 @@ extern "C" int cubit_gpu_fetch(cubit_gpu_result *r, uint64_t offset, uint64_t n,
 		}
 	}
 	CU_TRY(cudaStreamSynchronize(st));
+	return CUBIT_OK;
+}
+
+// Validity of projected column `col` for result rows [offset, offset + n): bit j of host_words = row offset + j
+// (1 = valid), ceil(n / 64) words, bits past n zero — the mask a DataChunk vector carries (vector.hpp:242-256).
+extern "C" int cubit_gpu_fetch_validity(cubit_gpu_result *r, uint32_t col, uint64_t offset, uint64_t n,
+                                        uint64_t *host_words, int *all_valid) {
+	if (!r || (!host_words && !all_valid)) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	cudaSetDevice(r->t->device);
+	int rc = finish_result(r);
+	if (rc) {
+		return rc;
+	}
+	if (col >= r->n_cols) {
+		return fail(CUBIT_EINVAL, "result has %u projected columns, column %u requested", r->n_cols, col);
+	}
+	if (offset > r->info.count || n > r->info.count - offset) {
+		return fail(CUBIT_EINVAL, "fetch range [%llu, +%llu) outside result of %llu rows", (unsigned long long)offset,
+		            (unsigned long long)n, (unsigned long long)r->info.count);
+	}
+	const uint64_t out_words = (n + 63) / 64;
+	if (!r->d_valid[col]) { // the column holds no NULLs
+		if (all_valid) {
+			*all_valid = 1;
+		}
+		for (uint64_t w = 0; host_words && w < out_words; w++) {
+			const uint64_t left = n - w * 64;
+			host_words[w] = left >= 64 ? ~0ull : ((1ull << left) - 1);
+		}
+		return CUBIT_OK;
+	}
+	if (n == 0) {
+		if (all_valid) {
+			*all_valid = 1;
+		}
+		return CUBIT_OK;
+	}
+	// device mask is 32-bit words over result positions (zero past count, 2 spare words): copy the covering
+	// 64-bit words and shift so that bit 0 = row `offset`
+	const uint64_t w0 = offset / 64, sh = offset % 64;
+	const uint64_t src_words = (sh + n + 63) / 64;
+	std::vector<uint64_t> tmp(src_words + 1, 0);
+	{
+		std::lock_guard<std::mutex> lk(r->t->mu);
+		const uint64_t avail32 = (r->info.capacity + 31) / 32 + 2; // words allocated
+		uint64_t copy32 = src_words * 2;
+		if (w0 * 2 + copy32 > avail32) {
+			copy32 = avail32 - w0 * 2;
+		}
+		CU_TRY(cudaMemcpyAsync(tmp.data(), r->d_valid[col] + w0 * 2, copy32 * 4, cudaMemcpyDeviceToHost, r->stream));
+		CU_TRY(cudaStreamSynchronize(r->stream));
+	}
+	bool all = true;
+	for (uint64_t w = 0; w < out_words; w++) {
+		uint64_t v = tmp[w] >> sh;
+		if (sh) {
+			v |= tmp[w + 1] << (64 - sh);
+		}
+		const uint64_t left = n - w * 64;
+		const uint64_t mask = left >= 64 ? ~0ull : ((1ull << left) - 1);
+		v &= mask;
+		all &= v == mask;
+		if (host_words) {
+			host_words[w] = v;
+		}
+	}
+	if (all_valid) {
+		*all_valid = all ? 1 : 0;
+	}
 	return CUBIT_OK;
 }
 

@@ -59,6 +59,7 @@ struct ResultHeader {
 	unsigned int overflow; // int64 product overflow seen (CUBIT_AGG_SUM_PROD)
 	unsigned int pad;
 	double sum_f64;        // CUBIT_AGG_SUM_F64
+	unsigned long long agg_rows; // non-NULL inputs of the aggregate (written only when a validity mask is involved)
 };
 
 struct BlockPartial {
@@ -111,6 +112,10 @@ struct ProbeArgs {
 	int agg_kind;
 	ColRef agg_a;
 	ColRef agg_b;
+	// validity masks (DuckDB ValidityMask layout, bit = 1: valid) of the aggregate inputs, or nullptr = no NULLs;
+	// rows whose input is NULL are skipped (SUM ignores NULLs; a product with a NULL factor is NULL)
+	const unsigned long long *agg_valid_a;
+	const unsigned long long *agg_valid_b;
 	BlockPartial *partials;
 	unsigned int *done;                 // blocks-done counter (zeroed)
 	ResultHeader *hdr;                  // count is left untouched; sums written
@@ -128,6 +133,11 @@ cudaError_t launch_probe_bits(const ScanArgs &args, uint32_t seg_words, bool pos
                               cudaStream_t stream);
 
 cudaError_t launch_probe(const ProbeArgs &args, int sm_count, cudaStream_t stream);
+// validity of a probed column at the selected rows (ValidityFetchRow analog, validity_uncompressed.cpp:381):
+// bit j of out32 = valid[ids[j] - row_base] for j < *count_ptr (out32 zeroed beforehand, ceil(cap/32) words)
+cudaError_t launch_validity_gather(const long long *ids, const unsigned long long *count_ptr, int64_t row_base,
+                                   const unsigned long long *valid, uint32_t *out32, int sm_count,
+                                   cudaStream_t stream);
 int probe_grid(int sm_count);
 
 // index build: B_(col[r]-base) |= bit r for rows [row_begin, n_rows); bits of rows < row_begin are kept (append)

@@ -37,6 +37,13 @@ void CubitTable::AddColumn(column_t col, const int32_t *values) {
 	col_types[col] = LogicalTypeId::INTEGER;
 }
 
+void CubitTable::SetValidity(column_t col, const uint64_t *words) {
+	if (!col_types.count(col)) {
+		throw InvalidInputException("Table does not have column " + std::to_string(col));
+	}
+	Check(cubit_gpu_upload_column_validity(handle, (int32_t)col, words, words ? (n_rows + 63) / 64 : 0));
+}
+
 void CubitTable::Append(idx_t n_new, const std::map<column_t, const void *> &values) {
 	std::vector<cubit_append_column> cols;
 	for (auto &kv : values) {

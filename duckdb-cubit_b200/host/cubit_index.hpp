@@ -30,6 +30,8 @@ public:
 
 	void AddColumn(column_t col, const int64_t *values);
 	void AddColumn(column_t col, const int32_t *values);
+	// NULLs of a resident column: its ValidityMask words (ceil(rows / 64); nullptr = no NULLs)
+	void SetValidity(column_t col, const uint64_t *words);
 	// INSERT: n_new rows appended at the end (they take the next row ids); `values` holds one array of n_new
 	// elements per resident column.  Indexes built from a column are extended on the GPU
 	// (BoundIndex::Append, bound_index.hpp:71-75).

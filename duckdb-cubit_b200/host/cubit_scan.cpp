@@ -163,12 +163,18 @@ void CubitScanFunction(const CubitScanBindData &bind, CubitScanGlobalState &st, 
 	// IndexScanFunction: scan_count = min(STANDARD_VECTOR_SIZE, remaining)  (table_scan.cpp:258-261)
 	const idx_t scan_count = std::min<idx_t>(STANDARD_VECTOR_SIZE, st.win_end - st.offset);
 	const idx_t rel = st.offset - st.win_begin;
+	uint32_t value_col = 0;
 	for (size_t i = 0; i < st.column_ids.size(); i++) {
+		output.data[i].all_valid = true;
 		if (st.column_ids[i] == COLUMN_IDENTIFIER_ROW_ID) {
 			memcpy(output.data[i].Raw(), st.win_rowids.data() + rel, scan_count * sizeof(row_t));
 		} else {
 			const size_t w = (size_t)st.types[i];
 			memcpy(output.data[i].Raw(), st.win_cols[i].data() + rel * w, scan_count * w);
+			// validity of the probed values (StandardColumnData::FetchRow: validity.FetchRow + data)
+			int all = 1;
+			Check(cubit_gpu_fetch_validity(st.result, value_col++, st.offset, scan_count, output.data[i].validity, &all));
+			output.data[i].all_valid = all != 0;
 		}
 	}
 	output.SetCardinality(scan_count);

@@ -32,14 +32,20 @@ struct InternalException : std::runtime_error {
 	using std::runtime_error::runtime_error;
 };
 
-// FLAT vector: a typed array of up to STANDARD_VECTOR_SIZE values (no validity mask on this
-// path: NULL keys are not indexed and projected columns here are NOT NULL)
+// FLAT vector: a typed array of up to STANDARD_VECTOR_SIZE values plus the ValidityMask (vector.hpp:242-256,
+// validity_mask.hpp:50: u64 words, bit r%64 of word r/64 = 1 when row r is valid; "all valid" = no mask)
 struct Vector {
 	LogicalTypeId type = LogicalTypeId::BIGINT;
 	std::vector<uint8_t> buffer;
+	uint64_t validity[STANDARD_VECTOR_SIZE / 64];
+	bool all_valid = true;
 	void Initialize(LogicalTypeId t) {
 		type = t;
 		buffer.assign((size_t)t * STANDARD_VECTOR_SIZE, 0);
+		all_valid = true;
+	}
+	bool RowIsValid(idx_t i) const { // ValidityMask::RowIsValid (validity_mask.hpp:163-168)
+		return all_valid || ((validity[i / 64] >> (i % 64)) & 1);
 	}
 	template <class T>
 	T *GetData() {

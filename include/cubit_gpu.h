@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CUBIT_GPU_ABI_VERSION 1
+#define CUBIT_GPU_ABI_VERSION 2
 
 /* error codes */
 #define CUBIT_OK 0
@@ -113,6 +113,10 @@ typedef struct cubit_result_info {
 	const uint64_t *d_bitvector;
 	const void *d_values[CUBIT_MAX_PROBE_COLS];
 	double sum_f64;         /* CUBIT_AGG_SUM_F64 */
+	uint64_t agg_rows;      /* non-NULL inputs of the aggregate (= count when the aggregate columns hold no
+	                           NULLs); 0 means the SQL SUM is NULL                                          */
+	const uint32_t *d_validity[CUBIT_MAX_PROBE_COLS]; /* device validity bits of the projected values (bit j of
+	                           32-bit word j/32 = result row j), NULL = that column holds no NULLs          */
 } cubit_result_info;
 
 /* ---- library ---------------------------------------------------------- */
@@ -174,6 +178,16 @@ int cubit_gpu_merge_deltas(cubit_gpu_table *t, int32_t index_id);
 /* ---- columns (decoded, fixed width 4 or 8 bytes, HBM resident) ---------- */
 int cubit_gpu_upload_column(cubit_gpu_table *t, int32_t col_id, const void *data, uint32_t elem_bytes, uint64_t n);
 int cubit_gpu_download_column(cubit_gpu_table *t, int32_t col_id, void *data, uint32_t elem_bytes, uint64_t n);
+/* NULLs: the column's validity mask in the reference's layout (ValidityMask: 64-bit words, bit r%64 of word r/64
+ * = 1 when row r is valid, src/include/duckdb/common/types/validity_mask.hpp:50,163-168 — also what a
+ * validity_uncompressed segment stores, src/storage/compression/validity_uncompressed.cpp:381).  n_words must be
+ * ceil(n_rows / 64); words = NULL drops the mask.
+ * Upload it after the column data (cubit_gpu_upload_column resets a column to all-valid).  Probes report the
+ * validity of every projected value (cubit_gpu_fetch_validity, StandardColumnData::FetchRow =
+ * validity.FetchRow + data, standard_column_data.cpp:169-178); SUM skips NULL inputs, SUM(a*b) skips rows where
+ * either factor is NULL, `count` stays COUNT(*) and cubit_result_info.agg_rows counts the non-NULL inputs.
+ * Appended rows are valid. */
+int cubit_gpu_upload_column_validity(cubit_gpu_table *t, int32_t col_id, const uint64_t *words, uint64_t n_words);
 /* Synthetic columns generated on the device (bench / parity-test support;
  * the generators are restated in oracle/cubit_oracle.c):
  *   kind 0: int64 payload, value = row_base + r
@@ -242,6 +256,12 @@ int cubit_gpu_result_get(cubit_gpu_result *r, cubit_result_info *info);
  * (≤ 2048 rows per GetData call: table_scan.cpp:258-268). */
 int cubit_gpu_fetch(cubit_gpu_result *r, uint64_t offset, uint64_t n, int64_t *host_rowids, uint32_t n_cols,
                     void *const *host_cols);
+/* Validity mask of projected column `col` (index into the query's cols[]) for result rows [offset, offset+n):
+ * bit j of host_words = row offset+j, ceil(n/64) words, bits past n zero — the mask the DataChunk vector gets
+ * (FlatVector::Validity).  *all_valid (optional) = 1 when no NULL falls into the range, so the caller can skip
+ * installing a mask; host_words may be NULL when only that flag is wanted. */
+int cubit_gpu_fetch_validity(cubit_gpu_result *r, uint32_t col, uint64_t offset, uint64_t n, uint64_t *host_words,
+                             int *all_valid);
 int cubit_gpu_fetch_bitvector(cubit_gpu_result *r, uint64_t *host_words, uint64_t n_words);
 int cubit_gpu_free_result(cubit_gpu_result *r);
 

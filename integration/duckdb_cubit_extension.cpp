@@ -214,6 +214,10 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 		throw InvalidInputException("cubit_load: key column \"%s\" not found or not integral", bind.key);
 	}
 	vector<vector<int64_t>> cols(int_cols.size());
+	// NULLs: one validity mask per column in the reference's own layout (ValidityMask words), built only for
+	// columns that hold a NULL; NULL keys are not indexed (plan_create_index.cpp:60-78 filters them out)
+	vector<vector<uint64_t>> valid(int_cols.size());
+	idx_t rows_seen = 0;
 	for (auto &chunk : res->Collection().Chunks()) {
 		for (idx_t k = 0; k < int_cols.size(); k++) {
 			auto &vec = chunk.data[int_cols[k]];
@@ -227,7 +231,24 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 			as_bigint.Flatten(chunk.size());
 			auto ptr = FlatVector::GetData<int64_t>(as_bigint);
 			cols[k].insert(cols[k].end(), ptr, ptr + chunk.size());
+			auto &mask = FlatVector::Validity(as_bigint);
+			if (!mask.AllValid()) {
+				for (idx_t r = 0; r < chunk.size(); r++) {
+					if (mask.RowIsValid(r)) {
+						continue;
+					}
+					if (valid[k].empty()) {
+						valid[k].assign((res->RowCount() + 63) / 64, ~uint64_t(0));
+					}
+					const idx_t row = rows_seen + r;
+					valid[k][row / 64] &= ~(uint64_t(1) << (row % 64));
+					if (k == key_col) {
+						cols[k][row] = NumericLimits<int64_t>::Minimum(); // outside every indexed domain
+					}
+				}
+			}
 		}
+		rows_seen += chunk.size();
 	}
 	gpu->key_table_column = int_cols[key_col];
 	gpu->row_count = cols.empty() ? 0 : cols[0].size();
@@ -236,9 +257,15 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 	CubitCheck(cubit_gpu_create(0, gpu->row_count, 0, 65536, &gpu->handle));
 	for (idx_t k = 0; k < cols.size(); k++) {
 		// compressed segments straight from the buffer manager when the column qualifies, decoded rows otherwise
-		if (!CubitUploadColumnSegments(context, bind.table, int_cols[k], res->types[int_cols[k]], gpu->handle,
-		                               NumericCast<int32_t>(k), gpu->row_count)) {
+		// (a key column with NULLs goes the decoded way: its NULL rows must carry an out-of-domain value)
+		const bool null_keys = k == key_col && !valid[k].empty();
+		if (null_keys || !CubitUploadColumnSegments(context, bind.table, int_cols[k], res->types[int_cols[k]],
+		                                            gpu->handle, NumericCast<int32_t>(k), gpu->row_count)) {
 			CubitCheck(cubit_gpu_upload_column(gpu->handle, NumericCast<int32_t>(k), cols[k].data(), 8, gpu->row_count));
+		}
+		if (!valid[k].empty()) {
+			CubitCheck(cubit_gpu_upload_column_validity(gpu->handle, NumericCast<int32_t>(k), valid[k].data(),
+			                                            valid[k].size()));
 		}
 	}
 	CubitCheck(cubit_gpu_index_create(gpu->handle, gpu->cardinality, &gpu->index_id));
@@ -269,6 +296,7 @@ struct CubitScanGlobalState : public GlobalTableFunctionState {
 	idx_t row_count = 0, offset = 0;
 	uint64_t sum_lo = 0;
 	int64_t sum_hi = 0;
+	uint64_t agg_rows = 0; // non-NULL inputs of the pushed-down SUM
 	bool agg_emitted = false;
 	~CubitScanGlobalState() override {
 		cubit_gpu_free_result(result);
@@ -349,6 +377,7 @@ static unique_ptr<GlobalTableFunctionState> CubitRunQuery(const CubitScanBindDat
 	state->row_count = info.count;
 	state->sum_lo = info.sum_lo;
 	state->sum_hi = info.sum_hi;
+	state->agg_rows = info.agg_rows;
 	return std::move(state);
 }
 
@@ -374,6 +403,24 @@ static void CubitScanFunction(ClientContext &, TableFunctionInput &data_p, DataC
 	}
 	CubitCheck(cubit_gpu_fetch(state.result, state.offset, scan_count, rowids, NumericCast<uint32_t>(col_ptrs.size()),
 	                           col_ptrs.data()));
+	// NULLs: the validity mask of every projected value (StandardColumnData::FetchRow = validity + data)
+	uint32_t value_col = 0;
+	for (idx_t i = 0; i < state.column_ids.size(); i++) {
+		if (state.column_ids[i] == COLUMN_IDENTIFIER_ROW_ID) {
+			continue;
+		}
+		uint64_t words[STANDARD_VECTOR_SIZE / 64];
+		int all_valid = 1;
+		CubitCheck(cubit_gpu_fetch_validity(state.result, value_col++, state.offset, scan_count, words, &all_valid));
+		if (!all_valid) {
+			auto &mask = FlatVector::Validity(output.data[i]);
+			for (idx_t r = 0; r < scan_count; r++) {
+				if (!((words[r / 64] >> (r % 64)) & 1)) {
+					mask.SetInvalid(r);
+				}
+			}
+		}
+	}
 	output.SetCardinality(scan_count);
 	state.offset += scan_count;
 }
@@ -408,7 +455,8 @@ static void CubitAggFunction(ClientContext &, TableFunctionInput &data_p, DataCh
 	hugeint_t sum;
 	sum.lower = state.sum_lo;
 	sum.upper = state.sum_hi;
-	output.SetValue(1, 0, Value::HUGEINT(sum));
+	// SUM over no non-NULL input is NULL (sum.cpp: the state is only "set" by a valid row)
+	output.SetValue(1, 0, state.agg_rows ? Value::HUGEINT(sum) : Value(LogicalType::HUGEINT));
 	output.SetCardinality(1);
 	state.agg_emitted = true;
 }

@@ -103,6 +103,11 @@ def lib():
         L.oracle_sum_prod_i64.restype = C.c_int
         L.oracle_sum_f64.argtypes = [C.POINTER(C.c_double), C.c_uint64, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.oracle_sum_f64.restype = None
+        L.oracle_probe_validity.argtypes = [_i64p, C.c_uint64, C.c_int64, _u64p, _u64p]
+        L.oracle_probe_validity.restype = C.c_uint64
+        L.oracle_sum_nulls.argtypes = [_i64p, C.c_uint64, C.c_int64, _i64p, _u64p, _i64p, _u64p, _u64p, _i64p,
+                                       C.POINTER(C.c_int)]
+        L.oracle_sum_nulls.restype = C.c_uint64
         L.oracle_build_index.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_int64, C.c_uint32, _u64p,
                                          C.c_uint64]
         L.oracle_build_index.restype = None
@@ -200,6 +205,30 @@ def probe(ids, col, row_base=0):
     out = np.empty(len(ids), dtype=col.dtype)
     lib().oracle_probe(_p(ids, _i64p), len(ids), row_base, col.ctypes.data, col.dtype.itemsize, out.ctypes.data)
     return out
+
+
+def probe_validity(ids, valid, row_base=0):
+    """validity bits of a probed column at the row ids → (uint64 mask words over result positions, n valid)"""
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    out = np.zeros((len(ids) + 63) // 64, dtype=np.uint64)
+    v = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint64)
+    nv = lib().oracle_probe_validity(_p(ids, _i64p), len(ids), row_base, None if v is None else _p(v, _u64p),
+                                     _p(out, _u64p) if len(out) else None)
+    return out, int(nv)
+
+
+def sum_nulls(ids, a, valid_a=None, b=None, valid_b=None, row_base=0):
+    """SUM(a) / SUM(a*b) over the rows `ids`, skipping NULL inputs → (int128 sum, rows aggregated, overflow)"""
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    va = None if valid_a is None else np.ascontiguousarray(valid_a, dtype=np.uint64)
+    bb = None if b is None else np.ascontiguousarray(b, dtype=np.int64)
+    vb = None if valid_b is None else np.ascontiguousarray(valid_b, dtype=np.uint64)
+    lo, hi, ovf = C.c_uint64(0), C.c_int64(0), C.c_int(0)
+    rows = lib().oracle_sum_nulls(_p(ids, _i64p), len(ids), row_base, _p(a, _i64p),
+                                  None if va is None else _p(va, _u64p), None if bb is None else _p(bb, _i64p),
+                                  None if vb is None else _p(vb, _u64p), C.byref(lo), C.byref(hi), C.byref(ovf))
+    return int128(lo.value, hi.value), int(rows), bool(ovf.value)
 
 
 def sum_i64(vals):

@@ -82,7 +82,49 @@ static void AppendAfterBuild() {
 	REQUIRE(ids == want);
 }
 
+// NULLs in a projected column: the chunk's vector carries the validity mask of the probed rows
+static void NullsInProjectedColumn() {
+	const idx_t n = 300007;
+	std::vector<int32_t> key(n);
+	std::vector<int64_t> val(n);
+	std::vector<uint64_t> valid((n + 63) / 64, 0);
+	for (idx_t r = 0; r < n; r++) {
+		key[r] = (int32_t)(r % 4);
+		val[r] = (int64_t)r * 3;
+		if (r % 5 != 2) {
+			valid[r / 64] |= 1ull << (r % 64);
+		}
+	}
+	CubitTable table(n, 0);
+	table.AddColumn(0, key.data());
+	table.AddColumn(1, val.data());
+	table.SetValidity(1, valid.data());
+	CubitIndex ix(table, 0, 0, 4);
+	ix.Build();
+	auto bind = CubitScanBind(table, {{&ix, 1, 2}});
+	std::vector<column_t> column_ids = {COLUMN_IDENTIFIER_ROW_ID, 1};
+	auto gstate = CubitScanInitGlobal(*bind, column_ids);
+	DataChunk chunk;
+	chunk.Initialize(CubitScanReturnTypes(*bind, column_ids));
+	idx_t seen = 0, nulls = 0;
+	while (CubitScanGetData(*bind, *gstate, chunk) == SourceResultType::HAVE_MORE_OUTPUT) {
+		for (idx_t i = 0; i < chunk.size(); i++, seen++) {
+			const row_t r = chunk.data[0].GetData<row_t>()[i];
+			REQUIRE(r % 4 == 1 || r % 4 == 2);
+			REQUIRE(chunk.data[0].RowIsValid(i));
+			REQUIRE(chunk.data[1].RowIsValid(i) == (r % 5 != 2));
+			if (chunk.data[1].RowIsValid(i)) {
+				REQUIRE(chunk.data[1].GetData<int64_t>()[i] == r * 3);
+			} else {
+				nulls++;
+			}
+		}
+	}
+	REQUIRE(seen == gstate->row_count && seen == 150004 && nulls > 0);
+}
+
 int main() {
+	NullsInProjectedColumn();
 	AppendAfterBuild();
 	ArtManyMatches(1024);
 	ArtManyMatches(2048);

@@ -18,11 +18,17 @@ void oracle_sum_i64(const int64_t *vals, uint64_t n, uint64_t *sum_lo, int64_t *
 void oracle_build_index(const void *col, uint32_t elem_bytes, uint64_t n_rows, int64_t base_value, uint32_t card,
                         uint64_t *bitvectors, uint64_t n_words);
 
+uint64_t oracle_probe_validity(const int64_t *ids, uint64_t n, int64_t row_base, const uint64_t *valid,
+                               uint64_t *out_words);
+uint64_t oracle_sum_nulls(const int64_t *ids, uint64_t n, int64_t row_base, const int64_t *a, const uint64_t *valid_a,
+                          const int64_t *b, const uint64_t *valid_b, uint64_t *sum_lo, int64_t *sum_hi, int *ovf);
+
 #define MAX_COLS 64
 struct cubit_gpu_table {
 	uint64_t n_rows, n_words;
 	int64_t row_base;
 	int64_t *cols[MAX_COLS];
+	uint64_t *valid[MAX_COLS];
 	uint64_t *bits; /* one index only */
 	uint32_t card;
 };
@@ -31,6 +37,8 @@ struct cubit_gpu_result {
 	uint64_t count;
 	int64_t *ids;
 	int64_t *vals[CUBIT_MAX_PROBE_COLS];
+	uint64_t *vmask[CUBIT_MAX_PROBE_COLS]; /* validity over result positions, NULL = all valid */
+	uint64_t agg_rows;
 	uint32_t n_cols;
 	uint64_t sum_lo;
 	int64_t sum_hi;
@@ -48,7 +56,7 @@ int cubit_gpu_create(int device, uint64_t n_rows, int64_t row_base, uint32_t seg
 }
 int cubit_gpu_destroy(cubit_gpu_table *t) {
 	if (!t) return CUBIT_OK;
-	for (int i = 0; i < MAX_COLS; i++) free(t->cols[i]);
+	for (int i = 0; i < MAX_COLS; i++) { free(t->cols[i]); free(t->valid[i]); }
 	free(t->bits); free(t);
 	return CUBIT_OK;
 }
@@ -56,6 +64,12 @@ int cubit_gpu_upload_column(cubit_gpu_table *t, int32_t col_id, const void *data
 	if (elem_bytes != 8 || col_id < 0 || col_id >= MAX_COLS || n != t->n_rows) { snprintf(g_err, sizeof g_err, "mock: bad column"); return CUBIT_EINVAL; }
 	t->cols[col_id] = malloc(n * 8);
 	memcpy(t->cols[col_id], data, n * 8);
+	return CUBIT_OK;
+}
+int cubit_gpu_upload_column_validity(cubit_gpu_table *t, int32_t col_id, const uint64_t *words, uint64_t n_words) {
+	if (col_id < 0 || col_id >= MAX_COLS || !t->cols[col_id] || (words && n_words != t->n_words)) { snprintf(g_err, sizeof g_err, "mock: bad validity"); return CUBIT_EINVAL; }
+	free(t->valid[col_id]); t->valid[col_id] = NULL;
+	if (words) { t->valid[col_id] = malloc(n_words * 8); memcpy(t->valid[col_id], words, n_words * 8); }
 	return CUBIT_OK;
 }
 int oracle_bitpacking_decode(const uint8_t *seg, uint64_t seg_bytes, uint32_t elem_bytes, uint64_t count, void *out,
@@ -108,20 +122,23 @@ int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_result *
 		for (uint32_t c = 0; c < q->n_cols; c++) {
 			r->vals[c] = malloc((r->count + 1) * 8);
 			oracle_probe(r->ids, r->count, t->row_base, t->cols[q->cols[c]], 8, r->vals[c]);
+			if (t->valid[q->cols[c]]) {
+				r->vmask[c] = calloc((r->count + 63) / 64 + 1, 8);
+				oracle_probe_validity(r->ids, r->count, t->row_base, t->valid[q->cols[c]], r->vmask[c]);
+			}
 		}
 	}
 	if (q->agg_kind == CUBIT_AGG_SUM) {
-		int64_t *tmp = malloc((r->count + 1) * 8);
-		oracle_probe(r->ids, r->count, t->row_base, t->cols[q->agg_col_a], 8, tmp);
-		oracle_sum_i64(tmp, r->count, &r->sum_lo, &r->sum_hi);
-		free(tmp);
+		int ovf = 0;
+		r->agg_rows = oracle_sum_nulls(r->ids, r->count, t->row_base, t->cols[q->agg_col_a], t->valid[q->agg_col_a], NULL,
+		                               NULL, &r->sum_lo, &r->sum_hi, &ovf);
 	}
 	*out = r;
 	return CUBIT_OK;
 }
 int cubit_gpu_result_get(cubit_gpu_result *r, cubit_result_info *info) {
 	memset(info, 0, sizeof(*info));
-	info->count = r->count; info->sum_lo = r->sum_lo; info->sum_hi = r->sum_hi;
+	info->count = r->count; info->sum_lo = r->sum_lo; info->sum_hi = r->sum_hi; info->agg_rows = r->agg_rows;
 	return CUBIT_OK;
 }
 int cubit_gpu_fetch(cubit_gpu_result *r, uint64_t offset, uint64_t n, int64_t *host_rowids, uint32_t n_cols,
@@ -131,10 +148,23 @@ int cubit_gpu_fetch(cubit_gpu_result *r, uint64_t offset, uint64_t n, int64_t *h
 	for (uint32_t c = 0; c < n_cols; c++) memcpy(host_cols[c], r->vals[c] + offset, n * 8);
 	return CUBIT_OK;
 }
+int cubit_gpu_fetch_validity(cubit_gpu_result *r, uint32_t col, uint64_t offset, uint64_t n, uint64_t *host_words,
+                             int *all_valid) {
+	if (offset + n > r->count || col >= r->n_cols) { snprintf(g_err, sizeof g_err, "mock: bad fetch"); return CUBIT_EINVAL; }
+	int all = 1;
+	for (uint64_t w = 0; w < (n + 63) / 64; w++) host_words[w] = 0;
+	for (uint64_t j = 0; j < n; j++) {
+		uint64_t p = offset + j;
+		int bit = r->vmask[col] ? (int)((r->vmask[col][p / 64] >> (p % 64)) & 1) : 1;
+		if (bit) host_words[j / 64] |= 1ull << (j % 64); else all = 0;
+	}
+	if (all_valid) *all_valid = all;
+	return CUBIT_OK;
+}
 int cubit_gpu_free_result(cubit_gpu_result *r) {
 	if (!r) return CUBIT_OK;
 	free(r->ids);
-	for (int c = 0; c < CUBIT_MAX_PROBE_COLS; c++) free(r->vals[c]);
+	for (int c = 0; c < CUBIT_MAX_PROBE_COLS; c++) { free(r->vals[c]); free(r->vmask[c]); }
 	free(r);
 	return CUBIT_OK;
 }

@@ -78,7 +78,7 @@ class AppendColumn(C.Structure):
 
 class DecodeInfo(C.Structure):
     _fields_ = [("h2d_bytes", C.c_uint64), ("n_groups", C.c_uint64), ("mode_groups", C.c_uint64 * 6),
-                ("n_launches", C.c_uint32), ("ms_decode", C.c_float)]
+                ("rle_runs", C.c_uint64), ("n_launches", C.c_uint32), ("ms_decode", C.c_float)]
 
 
 SEG_UNCOMPRESSED, SEG_BITPACKING, SEG_CONSTANT = 0, 1, 2

@@ -795,7 +795,13 @@ extern "C" int cubit_gpu_upload_column_segments(cubit_gpu_table *t, int32_t col_
 	};
 	// ---- plan: validate, lay the segments out in one blob, build the group directory
 	std::vector<BpGroup> groups;
-	std::vector<uint64_t> seg_off(n_segs, 0);
+	std::vector<RleTile> tiles;
+	std::vector<uint64_t> seg_off(n_segs, 0), seg_used(n_segs, 0); // blob offset / bytes staged per segment
+	auto ld16 = [](const uint8_t *p) {
+		uint16_t v;
+		memcpy(&v, p, 2);
+		return v;
+	};
 	cubit_decode_info di;
 	memset(&di, 0, sizeof(di));
 	uint64_t blob_bytes = 0, next_row = 0;
@@ -822,6 +828,46 @@ extern "C" int cubit_gpu_upload_column_segments(cubit_gpu_table *t, int32_t col_
 			groups.push_back(BpGroup {blob_bytes, sg.row_start, (uint32_t)sg.count, BP_CONSTANT});
 			di.mode_groups[BP_CONSTANT]++;
 			blob_bytes += 8;
+			continue;
+		}
+		if (sg.kind == CUBIT_SEG_RLE) {
+			// [u64 offset of the run lengths][values][pad][u16 run lengths] (rle.cpp:190-205).  The run count is not
+			// stored: walk the lengths until the segment's rows are covered (what RLEScanPartialInternal does,
+			// :338-364), cutting tiles of ≤ kRleTileRuns runs / ~128 K rows as we go.
+			if (sg.bytes < 8) {
+				return fail(CUBIT_EINVAL, "segment %u: bad RLE segment size %llu", si, (unsigned long long)sg.bytes);
+			}
+			const uint64_t off = ld64(p);
+			if (off < 8 || (off & 7) || off > sg.bytes) {
+				return fail(CUBIT_EINVAL, "segment %u: RLE run-length offset %llu outside the segment", si,
+				            (unsigned long long)off);
+			}
+			const uint64_t max_runs = (off - 8) / elem_bytes;
+			uint64_t produced = 0, run = 0;
+			RleTile tl {blob_bytes + 8, blob_bytes + off, sg.row_start, 0, 0};
+			while (produced < sg.count) {
+				if (run >= max_runs || off + 2 * (run + 1) > sg.bytes) {
+					return fail(CUBIT_EINVAL, "segment %u: RLE runs end after %llu of %llu rows", si,
+					            (unsigned long long)produced, (unsigned long long)sg.count);
+				}
+				const uint64_t len = ld16(p + off + 2 * run);
+				if (len == 0) {
+					return fail(CUBIT_EINVAL, "segment %u: RLE run %llu has length 0", si, (unsigned long long)run);
+				}
+				const uint64_t take = std::min<uint64_t>(len, sg.count - produced);
+				if (tl.n_runs == (uint32_t)kRleTileRuns || (tl.n_runs && tl.n_rows + take > 131072)) {
+					tiles.push_back(tl);
+					tl = RleTile {blob_bytes + 8 + run * elem_bytes, blob_bytes + off + 2 * run, sg.row_start + produced, 0, 0};
+				}
+				tl.n_runs++;
+				tl.n_rows += (uint32_t)take;
+				produced += take;
+				run++;
+			}
+			tiles.push_back(tl);
+			di.rle_runs += run;
+			seg_used[si] = off + 2 * run;
+			blob_bytes += (seg_used[si] + 7) & ~7ull;
 			continue;
 		}
 		if (sg.kind != CUBIT_SEG_BITPACKING) {
@@ -872,7 +918,7 @@ extern "C" int cubit_gpu_upload_column_segments(cubit_gpu_table *t, int32_t col_
 		return fail(CUBIT_EINVAL, "segments cover %llu rows, table has %llu", (unsigned long long)next_row,
 		            (unsigned long long)t->n_rows);
 	}
-	if (groups.size() > 0x7fffffffull) {
+	if (groups.size() > 0x7fffffffull || tiles.size() > 0x7fffffffull) {
 		return fail(CUBIT_EINVAL, "too many metadata groups");
 	}
 	std::lock_guard<std::mutex> lk(t->mu);
@@ -893,12 +939,16 @@ extern "C" int cubit_gpu_upload_column_segments(cubit_gpu_table *t, int32_t col_
 	// ---- compressed bytes host → device as stored
 	uint8_t *d_blob = nullptr;
 	BpGroup *d_groups = nullptr;
+	RleTile *d_tiles = nullptr;
 	auto cleanup = [&]() {
 		if (d_blob) {
 			cudaFree(d_blob);
 		}
 		if (d_groups) {
 			cudaFree(d_groups);
+		}
+		if (d_tiles) {
+			cudaFree(d_tiles);
 		}
 	};
 #define CU_TRY_CLEAN(expr)                                                                                             \
@@ -912,6 +962,7 @@ extern "C" int cubit_gpu_upload_column_segments(cubit_gpu_table *t, int32_t col_
 	} while (0)
 	CU_TRY_CLEAN(cudaMalloc(&d_blob, blob_bytes + 16)); // + 16: the kernel never reads past a group, this is slack
 	CU_TRY_CLEAN(cudaMalloc(&d_groups, (groups.size() + 1) * sizeof(BpGroup)));
+	CU_TRY_CLEAN(cudaMalloc(&d_tiles, (tiles.size() + 1) * sizeof(RleTile)));
 	// Thousands of sub-megabyte segments: gather them into two pinned staging chunks on the host and move each
 	// chunk with ONE async copy (the next chunk is being filled while the previous one is on the wire).
 	const uint64_t chunk = kStageChunk;
@@ -955,7 +1006,7 @@ extern "C" int cubit_gpu_upload_column_segments(cubit_gpu_table *t, int32_t col_
 			di.h2d_bytes += sg.count * elem_bytes;
 			continue;
 		}
-		const uint64_t nb = sg.kind == CUBIT_SEG_CONSTANT ? elem_bytes : sg.bytes;
+		const uint64_t nb = sg.kind == CUBIT_SEG_CONSTANT ? elem_bytes : (sg.kind == CUBIT_SEG_RLE ? seg_used[si] : sg.bytes);
 		const uint8_t *src = static_cast<const uint8_t *>(sg.data);
 		uint64_t done = 0;
 		while (done < nb && pe == cudaSuccess) { // a segment may straddle chunks
@@ -980,11 +1031,16 @@ extern "C" int cubit_gpu_upload_column_segments(cubit_gpu_table *t, int32_t col_
 	CU_TRY_CLEAN(pe);
 	CU_TRY_CLEAN(cudaMemcpyAsync(d_groups, groups.data(), groups.size() * sizeof(BpGroup), cudaMemcpyHostToDevice,
 	                             t->stream));
+	CU_TRY_CLEAN(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(RleTile), cudaMemcpyHostToDevice,
+	                             t->stream));
 	cudaEvent_t e0 = nullptr, e1 = nullptr;
 	CU_TRY_CLEAN(cudaEventCreate(&e0));
 	CU_TRY_CLEAN(cudaEventCreate(&e1));
 	cudaEventRecord(e0, t->stream);
 	cudaError_t le = launch_bp_decode(d_blob, d_groups, (uint32_t)groups.size(), c.d, elem_bytes, t->stream);
+	if (le == cudaSuccess) {
+		le = launch_rle_decode(d_blob, d_tiles, (uint32_t)tiles.size(), c.d, elem_bytes, t->stream);
+	}
 	cudaEventRecord(e1, t->stream);
 	cudaError_t se = cudaStreamSynchronize(t->stream);
 	if (le == cudaSuccess && se == cudaSuccess) {
@@ -996,10 +1052,8 @@ extern "C" int cubit_gpu_upload_column_segments(cubit_gpu_table *t, int32_t col_
 	CU_TRY_CLEAN(se);
 #undef CU_TRY_CLEAN
 	cleanup();
-	if (!groups.empty()) {
-		t->launches++;
-		di.n_launches = 1;
-	}
+	di.n_launches = (groups.empty() ? 0u : 1u) + (tiles.empty() ? 0u : 1u);
+	t->launches += di.n_launches;
 	di.n_groups = groups.size();
 	if (info) {
 		*info = di;

@@ -51,6 +51,18 @@ struct BpGroup {
 	uint32_t mode;     // BpMode
 };
 
+// one tile of an RLE column segment (src/storage/compression/rle.cpp:190-205: [u64 offset of the run lengths]
+// [T values[n_runs]] pad [u16 run lengths[n_runs]]): ≤ kRleTileRuns consecutive runs producing ≤ ~128 K rows,
+// cut and validated on the host
+constexpr int kRleTileRuns = 1024;
+struct RleTile {
+	uint64_t val_off; // byte offset in the staged blob of the tile's first run value (element aligned)
+	uint64_t cnt_off; // byte offset of the tile's first run length (uint16)
+	uint64_t row0;    // first local row the tile decodes to
+	uint32_t n_runs;
+	uint32_t n_rows;  // rows the tile produces (the segment's last run may be cut by the row count)
+};
+
 // Device-side result header (one per query).
 struct ResultHeader {
 	unsigned long long count;
@@ -159,6 +171,10 @@ cudaError_t launch_pack_blocks(const long long *col, uint64_t n_rows, const Pack
 // one CTA per BpGroup: packed words staged in shared memory, FOR / DELTA_FOR (block-wide running sum) decode
 cudaError_t launch_bp_decode(const uint8_t *blob, const BpGroup *groups, uint32_t n_groups, void *out,
                              uint32_t elem_bytes, cudaStream_t stream);
+// one CTA per RleTile: block scan of the run lengths in shared memory, then every output row finds its run by
+// binary search (coalesced stores)
+cudaError_t launch_rle_decode(const uint8_t *blob, const RleTile *tiles, uint32_t n_tiles, void *out, uint32_t elem_bytes,
+                              cudaStream_t stream);
 // WAH (FastBit ibis::bitvector) → verbatim bitvector; `out` must be zeroed; block_group0[b] = number of 31-bit
 // groups before WAH word b * kWahBlockWords (host-computed while validating)
 constexpr int kWahBlockWords = 1024;

@@ -227,6 +227,10 @@ int cubit_gpu_append_rows(cubit_gpu_table *t, uint64_t n_new, const cubit_append
 #define CUBIT_SEG_UNCOMPRESSED 0 /* plain array of count elements (fixed_size_uncompressed.cpp)             */
 #define CUBIT_SEG_BITPACKING 1   /* BitPacking segment: u64 metadata-end offset, group data, metadata words */
 #define CUBIT_SEG_CONSTANT 2     /* Constant compression: data points to the one value of the segment       */
+#define CUBIT_SEG_RLE 3          /* RLE segment (src/storage/compression/rle.cpp:190-205): u64 offset of the run
+                                    lengths, run values, padding, u16 run lengths.  The format does not store its
+                                    size: `bytes` is an upper bound (e.g. up to the end of the block); the runs
+                                    needed to cover `count` rows are validated against it                    */
 typedef struct cubit_column_segment {
 	uint32_t kind;      /* CUBIT_SEG_*                                          */
 	uint32_t reserved;
@@ -239,6 +243,7 @@ typedef struct cubit_decode_info {
 	uint64_t h2d_bytes;  /* compressed bytes copied host → device                */
 	uint64_t n_groups;   /* metadata groups decoded                               */
 	uint64_t mode_groups[6]; /* groups per BitpackingMode (bitpacking.hpp:15)     */
+	uint64_t rle_runs;   /* runs decoded from RLE segments                        */
 	uint32_t n_launches;
 	float ms_decode;     /* decode kernel, CUDA events                            */
 } cubit_decode_info;

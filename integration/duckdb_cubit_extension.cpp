@@ -108,7 +108,7 @@ static unique_ptr<FunctionData> CubitLoadBind(ClientContext &, TableFunctionBind
 // block is pinned through the buffer manager exactly as BitpackingScanState does (bitpacking.cpp:627-636) and
 // the bytes go to cubit_gpu_upload_column_segments untouched; the GPU decodes them.  Returns false (and the
 // caller falls back to pulling decoded rows through a query) unless EVERY segment of the column is a
-// persistent, un-updated BitPacking or Uncompressed INT64 segment without NULLs.
+// persistent, un-updated BitPacking, RLE or Uncompressed INT64 segment without NULLs.
 static std::atomic<idx_t> cubit_segment_columns {0};
 idx_t CubitSegmentRouteCount() {
 	return cubit_segment_columns.load();
@@ -140,7 +140,8 @@ static bool CubitUploadColumnSegments(ClientContext &context, const string &tabl
 			continue;
 		}
 		if (!info.persistent || info.has_updates || info.block_id < 0 ||
-		    (info.compression_type != "BitPacking" && info.compression_type != "Uncompressed")) {
+		    (info.compression_type != "BitPacking" && info.compression_type != "Uncompressed" &&
+		     info.compression_type != "RLE")) {
 			return false;
 		}
 		mine.push_back(info);
@@ -169,6 +170,11 @@ static bool CubitUploadColumnSegments(ClientContext &context, const string &tabl
 			if (info.block_offset + seg.bytes > block_manager.GetBlockSize()) {
 				return false;
 			}
+		} else if (info.compression_type == "RLE") {
+			seg.kind = CUBIT_SEG_RLE;
+			// an RLE segment does not store its size (rle.cpp:190-205): hand over everything up to the end of
+			// the block, the library validates the runs it needs against that bound
+			seg.bytes = block_manager.GetBlockSize() - info.block_offset;
 		} else {
 			seg.kind = CUBIT_SEG_UNCOMPRESSED;
 			seg.bytes = info.segment_count * sizeof(int64_t);

@@ -23,7 +23,7 @@ _i64p = C.POINTER(C.c_int64)
 _i32p = C.POINTER(C.c_int32)
 
 
-_SOURCES = ["cubit_oracle.c", "bitpacking_oracle.c", "wah_oracle.c"]
+_SOURCES = ["cubit_oracle.c", "bitpacking_oracle.c", "wah_oracle.c", "rle_oracle.c"]
 _REF_DIR = os.path.join(_HERE, "_ref")
 _REF_FASTPFOR = os.path.join(_REF_DIR, "libfastpfor_ref.so")
 _REFERENCE_FASTPFOR_SRC = "/root/reference/third_party/fastpforlib"
@@ -134,6 +134,10 @@ def lib():
         L.oracle_wah_bits.restype = C.c_int64
         L.oracle_wah_decode.argtypes = [u32p, C.c_uint64, C.c_uint32, C.c_uint32, _u64p, C.c_uint64]
         L.oracle_wah_decode.restype = C.c_int64
+        L.oracle_rle_decode.argtypes = [u8p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, _u64p]
+        L.oracle_rle_decode.restype = C.c_int
+        L.oracle_rle_encode.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, u8p, C.c_uint64]
+        L.oracle_rle_encode.restype = C.c_int64
         L.oracle_bp_unpack_group64.argtypes = [u8p, _u64p, C.c_uint32]
         L.oracle_bp_unpack_group64.restype = None
         L.oracle_bp_unpack_group32.argtypes = [u8p, C.POINTER(C.c_uint32), C.c_uint32]
@@ -430,3 +434,27 @@ def wah_decode(wah, active_val, active_nbits, n_words):
     if n < 0:
         raise ValueError("malformed WAH bitvector")
     return out, int(n)
+
+
+def rle_decode(seg, elem_bytes, count):
+    """one RLE column segment (rle.cpp layout) → (values, n_runs); raises ValueError when malformed"""
+    seg = np.ascontiguousarray(seg, dtype=np.uint8)
+    out = np.empty(count, dtype=np.int64 if elem_bytes == 8 else np.int32)
+    runs = C.c_uint64(0)
+    rc = lib().oracle_rle_decode(seg.ctypes.data_as(C.POINTER(C.c_uint8)), len(seg), elem_bytes, count, out.ctypes.data,
+                                 C.byref(runs))
+    if rc != 0:
+        raise ValueError("malformed RLE segment")
+    return out, int(runs.value)
+
+
+def rle_encode(values):
+    """values (int32 / int64) → one RLE segment as the reference writes it (uint8 array)"""
+    values = np.ascontiguousarray(values)
+    assert values.dtype.itemsize in (4, 8)
+    cap = 16 + len(values) * (values.dtype.itemsize + 2) + 8
+    out = np.zeros(cap, dtype=np.uint8)
+    n = lib().oracle_rle_encode(values.ctypes.data, len(values), values.dtype.itemsize,
+                                out.ctypes.data_as(C.POINTER(C.c_uint8)), cap)
+    assert n > 0
+    return out[:n].copy()

@@ -192,6 +192,27 @@ int main(int argc, char **argv) {
 		REQUIRE(CubitSegmentRouteCount() == seg_mid + 3); // price fell back to decoded rows, the others did not
 		auto u1 = Run(fcon, "SELECT sum(price) FROM cubit_scan('ft', 7, 7)");
 		REQUIRE(u1->GetValue(0, 0).GetValue<int64_t>() == v1->GetValue(0, 0).GetValue<int64_t>());
+		{ // RLE-compressed columns take the same route (CUBIT_SEG_RLE)
+			Run(fcon, "PRAGMA force_compression='rle'");
+			Run(fcon, "CREATE TABLE fr AS SELECT ((i // 3) * 7919 % 50 + 1)::BIGINT AS q, ((i // 40) * 104729 % 1000003 - 500000)::BIGINT AS price, "
+			          "(i // 70000)::BIGINT AS big FROM range(300000) r(i)");
+			Run(fcon, "CHECKPOINT");
+			Run(fcon, "PRAGMA force_compression='auto'");
+			auto comp = Run(fcon, "SELECT count(*) FROM pragma_storage_info('fr') WHERE segment_type <> 'VALIDITY' AND compression = 'RLE'");
+			REQUIRE(comp->GetValue(0, 0).GetValue<int64_t>() >= 3);
+			const idx_t seg_rle = CubitSegmentRouteCount();
+			Run(fcon, "CALL cubit_load('fr', 'q', 1, 50)");
+			REQUIRE(CubitSegmentRouteCount() == seg_rle + 3);
+			Run(fcon, "CREATE TABLE fr_plain AS SELECT * FROM fr");
+			for (auto w : wheres) {
+				const string where = w;
+				auto a = Run(fcon, "SELECT count(*), sum(price), sum(big), min(rowid), max(rowid) FROM fr WHERE " + where);
+				auto b = Run(fcon, "SELECT count(*), sum(price), sum(big), min(rowid), max(rowid) FROM fr_plain WHERE " + where);
+				for (idx_t c = 0; c < 5; c++) {
+					REQUIRE(a->GetValue(c, 0).ToString() == b->GetValue(c, 0).ToString());
+				}
+			}
+		}
 		printf("storage route ok\n");
 	}
 	auto err = con.Query("SELECT * FROM cubit_scan('nope', 1, 2)");

@@ -74,6 +74,8 @@ int cubit_gpu_upload_column_validity(cubit_gpu_table *t, int32_t col_id, const u
 }
 int oracle_bitpacking_decode(const uint8_t *seg, uint64_t seg_bytes, uint32_t elem_bytes, uint64_t count, void *out,
                              uint64_t *mode_hist);
+int oracle_rle_decode(const uint8_t *seg, uint64_t seg_bytes, uint32_t elem_bytes, uint64_t count, void *out,
+                      uint64_t *n_runs_out);
 int cubit_gpu_upload_column_segments(cubit_gpu_table *t, int32_t col_id, uint32_t elem_bytes,
                                      const cubit_column_segment *segs, uint32_t n_segs, cubit_decode_info *info) {
 	if (elem_bytes != 8 || col_id < 0 || col_id >= MAX_COLS) { snprintf(g_err, sizeof g_err, "mock: bad column"); return CUBIT_EINVAL; }
@@ -85,6 +87,8 @@ int cubit_gpu_upload_column_segments(cubit_gpu_table *t, int32_t col_id, uint32_
 		if (s->kind == CUBIT_SEG_UNCOMPRESSED) memcpy(col + next, s->data, s->count * 8);
 		else if (s->kind == CUBIT_SEG_BITPACKING) {
 			if (oracle_bitpacking_decode(s->data, s->bytes, 8, s->count, col + next, hist) != 0) { free(col); snprintf(g_err, sizeof g_err, "mock: malformed segment"); return CUBIT_EINVAL; }
+		} else if (s->kind == CUBIT_SEG_RLE) {
+			if (oracle_rle_decode(s->data, s->bytes, 8, s->count, col + next, NULL) != 0) { free(col); snprintf(g_err, sizeof g_err, "mock: malformed RLE segment"); return CUBIT_EINVAL; }
 		} else { free(col); snprintf(g_err, sizeof g_err, "mock: kind"); return CUBIT_EINVAL; }
 		next += s->count;
 	}

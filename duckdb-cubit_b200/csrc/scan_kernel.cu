@@ -68,7 +68,10 @@ struct ScanSmem {
 	BlockPartial red[kConsumerWarps];
 };
 
-template <int WPT, bool HAS_DELTA, int NL>
+// ONEG: the predicate is ONE OR group (a range / IN predicate on one indexed column, the common case): the fold
+// is a plain OR into q, without the per-stream group test and the AND / reset of the group accumulator (23 of the
+// 47 SASS instructions the generic fold spends per stream and warp).
+template <int WPT, bool HAS_DELTA, int NL, bool ONEG>
 __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __grid_constant__ ScanArgs a) {
 	using Smem = ScanSmem<WPT, NL>;
 	constexpr int kStages = Smem::kStages;
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 		uint64_t q[WPT], g[WPT];
 #pragma unroll
 		for (int i = 0; i < WPT; i++) {
-			q[i] = ~0ull;
+			q[i] = ONEG ? 0ull : ~0ull;
 			g[i] = 0;
 		}
 		uint32_t tile = kNoTile;
@@ -297,7 +300,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 					// (XOR in shared memory, then the fold below picks them up): no block-wide barrier.
 					bool wrote = false;
 					for (uint32_t u = 0; u < nb; u++) {
-						const uint32_t st = (stage + u) % kStages;
+						uint32_t st = stage + u;
+						st = st >= (uint32_t)kStages ? st - (uint32_t)kStages : st;
 						const uint32_t dcnt = sm.meta[st].dcnt;
 						for (uint32_t e = lane; e < dcnt; e += 32) {
 							uint4 raw;
@@ -322,7 +326,16 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 #pragma unroll
 					for (int u = 0; u < UB; u++) {
 						if (u < (int)nb) {
-							const uint64_t *src = &sm.stage[(stage + u) % kStages][warp * kSpanWords];
+							uint32_t st = stage + (uint32_t)u;
+							st = st >= (uint32_t)kStages ? st - (uint32_t)kStages : st;
+							const uint64_t *src = &sm.stage[st][warp * kSpanWords];
+							if (ONEG) {
+#pragma unroll
+								for (int i = 0; i < WPT; i++) {
+									q[i] |= src[i * 32 + lane];
+								}
+								continue;
+							}
 #pragma unroll
 							for (int i = 0; i < WPT; i++) {
 								g[i] |= src[i * 32 + lane];
@@ -339,7 +352,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 				}
 				__syncwarp();
 				if (lane < (int)nb) {
-					mbar_arrive(&sm.empty[(stage + lane) % kStages]);
+					uint32_t st = stage + (uint32_t)lane;
+					st = st >= (uint32_t)kStages ? st - (uint32_t)kStages : st;
+					mbar_arrive(&sm.empty[st]);
 				}
 				stage += nb;
 				if (stage >= kStages) {
@@ -368,11 +383,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 						sm.warp_tot[buf][warp] = cnt;
 					}
 					consumer_bar_sync();
-#pragma unroll
-					for (int w = 0; w < kConsumerWarps; w++) {
-						const uint32_t t = sm.warp_tot[buf][w];
-						warp_excl += (w < warp) ? t : 0u;
-						tile_total += t;
+					{ // block scan over the 8 warp totals: one shared-memory load and two redux per warp
+						const uint32_t wt = lane < kConsumerWarps ? sm.warp_tot[buf][lane] : 0u;
+						tile_total = __reduce_add_sync(0xffffffffu, wt);
+						warp_excl = __reduce_add_sync(0xffffffffu, lane < warp ? wt : 0u);
 					}
 					if (threadIdx.x == 0) {
 						blk_count += tile_total;
@@ -596,9 +610,9 @@ cudaError_t launch_probe_bits(const ScanArgs &args, uint32_t seg_words, bool pos
 }
 
 // --------------------------------------------------------------------- launch
-template <int WPT, bool HAS_DELTA, int NL>
-static cudaError_t launch_scan_t(const ScanArgs &args, int sm_count, cudaStream_t stream, int *grid_out) {
-	auto kern = cubit_scan_kernel<WPT, HAS_DELTA, NL>;
+template <int WPT, bool HAS_DELTA, int NL, bool ONEG>
+static cudaError_t launch_scan_g(const ScanArgs &args, int sm_count, cudaStream_t stream, int *grid_out) {
+	auto kern = cubit_scan_kernel<WPT, HAS_DELTA, NL, ONEG>;
 	const size_t smem = sizeof(ScanSmem<WPT, NL>) + 128;
 	// function attributes are per device: configure once per (template instance, device)
 	static int blocks_per_sm_dev[64] = {};
@@ -633,6 +647,16 @@ static cudaError_t launch_scan_t(const ScanArgs &args, int sm_count, cudaStream_
 	largs.ticket_depth = td < 2u ? 2u : (td > 8u ? 8u : td);
 	kern<<<(unsigned)grid, kScanThreads, smem, stream>>>(largs);
 	return cudaGetLastError();
+}
+
+template <int WPT, bool HAS_DELTA, int NL>
+static cudaError_t launch_scan_t(const ScanArgs &args, int sm_count, cudaStream_t stream, int *grid_out) {
+	// one OR group ⇔ only the last stream closes a group (the specialised fold exists for the default, unfused path)
+	const bool one_group = NL == 0 && args.k >= 1 && args.group_end == (1ull << (args.k - 1));
+	if (NL == 0 && one_group) {
+		return launch_scan_g<WPT, HAS_DELTA, NL, NL == 0>(args, sm_count, stream, grid_out);
+	}
+	return launch_scan_g<WPT, HAS_DELTA, NL, false>(args, sm_count, stream, grid_out);
 }
 
 template <int WPT, bool HAS_DELTA>

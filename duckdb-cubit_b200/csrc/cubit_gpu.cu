@@ -1636,6 +1636,11 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 			}
 		}
 	}
+	// Single value bitvector, no pending deltas, aggregate only (the equality-predicate + SUM query of config 1):
+	// the merge is the identity, so the bit-driven probe reads B_v itself — no scan launch, no copy of Q —
+	// and counts the set bits on the way.
+	const bool probe_on_bv = probe_mode == PROBE_BITS && k == 1 && !has_delta && !want_ids && !want_vals && !want_q &&
+	                         !unfused && sa.debug == 0;
 	const bool separate_probe = probe_mode == PROBE_GATHER;
 	const bool need_ids_buf = want_ids || separate_probe || (probe_mode == PROBE_BITS && want_vals);
 	if (!need_ids_buf && !want_vals) {
@@ -1702,7 +1707,7 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 	if (want_q) {
 		Q_TRY(cudaMallocAsync((void **)&r->d_q, t->words_per_bv * 8, st));
 	}
-	if ((unfused || probe_mode == PROBE_BITS) && !want_q) {
+	if ((unfused || probe_mode == PROBE_BITS) && !want_q && !probe_on_bv) {
 		Q_TRY(cudaMallocAsync((void **)&r->d_q_tmp, t->words_per_bv * 8, st));
 	}
 	Q_TRY(cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming));
@@ -1722,7 +1727,10 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 	if (r->timing) {
 		Q_TRY(cudaEventRecord(r->ev[0], st));
 	}
-	if (!unfused) {
+	if (probe_on_bv) {
+		sa.q_out = const_cast<uint64_t *>(sa.bv[0]);
+		r->info.fused = 1;
+	} else if (!unfused) {
 		// one pass: merge (+delta XOR) + decode (+ fused probe / aggregate when eligible)
 		sa.ctrl = ctrl_a;
 		sa.q_out = probe_mode == PROBE_BITS && !want_q ? r->d_q_tmp : r->d_q;
@@ -1788,6 +1796,7 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 		pb.agg_ia = agg_ia;
 		pb.agg_ib = agg_ib;
 		pb.hdr = r->d_hdr;
+		pb.count_rows = probe_on_bv ? 1 : 0;
 		Q_TRY(launch_probe_bits(pb, t->seg_words, want_vals && cap, t->sm_count, st));
 		n_launch++;
 		if (r->timing) {
@@ -1866,7 +1875,8 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 	r->info.n_streams = k;
 	r->info.n_launches = n_launch;
 	r->info.delta_entries = delta_entries;
-	r->info.algo_bytes_scan = (uint64_t)k * t->n_words * 8 + delta_entries * sizeof(DeltaEnt);
+	// (probe_on_bv: the one bitvector is read once, by the probe — accounted in probe_fixed_bytes)
+	r->info.algo_bytes_scan = probe_on_bv ? 0 : (uint64_t)k * t->n_words * 8 + delta_entries * sizeof(DeltaEnt);
 	r->info.d_rowids = want_ids ? reinterpret_cast<const int64_t *>(r->d_ids) : nullptr;
 	r->info.d_bitvector = r->d_q;
 	for (uint32_t c = 0; c < r->n_cols; c++) {

@@ -108,6 +108,7 @@ struct ScanArgs {
 	BlockPartial *partials;             // [gridDim.x]
 	ResultHeader *hdr;
 	int skip_count;                     // 1: do not add this launch's popcounts to hdr->count (decode pass of UNFUSED)
+	int count_rows;                     // bit-driven probe only: 1 = it also counts the set bits into hdr->count (no scan ran)
 	unsigned int debug;                 // timing experiments only (CUBIT_SCAN_DEBUG): results are WRONG when != 0
 };
 

@@ -501,6 +501,7 @@ __global__ void __launch_bounds__(kProbeBitsThreads, 3) cubit_probe_bits_kernel(
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	Agg agg;
 	uint32_t it = 0;
+	unsigned long long my_rows = 0; // set bits seen by this thread (a.count_rows)
 	// software pipeline: the next segment's words are in flight while this one is decoded
 	uint64_t qn[WPT];
 	unsigned long long excl_n = 0;
@@ -525,6 +526,7 @@ __global__ void __launch_bounds__(kProbeBitsThreads, 3) cubit_probe_bits_kernel(
 			q[i] = qn[i];
 			cnt += __popcll(q[i]);
 		}
+		my_rows += cnt;
 		const unsigned long long tile_excl = excl_n;
 		prefetch(tile + gridDim.x);
 		unsigned long long wbase = 0;
@@ -546,6 +548,15 @@ __global__ void __launch_bounds__(kProbeBitsThreads, 3) cubit_probe_bits_kernel(
 	}
 	if (a.agg_kind != 0) {
 		agg_flush_warp(agg, a.hdr, lane);
+	}
+	if (a.count_rows) { // the probe ran directly on a value bitvector (single-bitvector predicate): COUNT comes from here
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1) {
+			my_rows += __shfl_xor_sync(0xffffffffu, my_rows, d);
+		}
+		if (lane == 0 && my_rows) {
+			atomicAdd(&a.hdr->count, my_rows);
+		}
 	}
 }
 

@@ -635,3 +635,28 @@ def test_append_rows_extends_columns_and_indexes(cubit, seg_bits):
     with pytest.raises(cubit.CubitError):
         t.append_rows({0: pay[:10], 1: key[:10].astype(np.int64)})  # wrong width
     t.close()
+
+
+def test_single_bitvector_aggregate_runs_on_the_bitvector_itself(cubit, golden, lineitem):
+    """equality predicate + SUM (config 1's query), no deltas: one launch (the bit-driven probe on B_v), and the
+    same answers as the general path; a pending delta on that bitvector brings the scan kernel back"""
+    g, gids = golden
+    t, ix = make_lineitem_table(cubit, lineitem, 32768)
+    ent = g["tpch_sf001"]["answers"]["q_eq_24"]
+    with t.query(refs(ent, ix), flags=0, agg=cubit.AGG_SUM, agg_a=COL_PRICE) as r:
+        assert r.count == ent["count"] and r.sum == ent["sum_price_cents"] and r.info.n_launches == 1
+    with t.query(refs(ent, ix), flags=0, agg=cubit.AGG_SUM_PROD, agg_a=COL_PRICE, agg_b=COL_DISC) as r:
+        assert r.count == ent["count"] and r.sum == ent["sum_price_x_discount_e4"] and r.info.n_launches == 1
+    with t.query(refs(ent, ix), flags=cubit.Q_ROWIDS, agg=cubit.AGG_SUM, agg_a=COL_PRICE) as r:   # row IDs wanted: general path
+        assert r.count == ent["count"] and r.sum == ent["sum_price_cents"] and r.info.n_launches == 2
+        assert np.array_equal(r.fetch()[0], gids["tpch_sf001/q_eq_24/ids"])
+    # delete one selected row through a pending delta: XOR at query time needs the merge kernel again
+    victim = int(gids["tpch_sf001/q_eq_24/ids"][5])
+    t.set_delta(ix["quantity"], 24 - INDEX_BASE["quantity"], np.array([victim], dtype=np.int64))
+    with t.query(refs(ent, ix), flags=0, agg=cubit.AGG_SUM, agg_a=COL_PRICE) as r:
+        assert r.count == ent["count"] - 1 and r.sum == ent["sum_price_cents"] - int(lineitem["price"][victim])
+        assert r.info.n_launches == 2
+    t.merge_deltas(ix["quantity"])
+    with t.query(refs(ent, ix), flags=0, agg=cubit.AGG_SUM, agg_a=COL_PRICE) as r:
+        assert r.count == ent["count"] - 1 and r.info.n_launches == 1
+    t.close()

@@ -1627,9 +1627,10 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 		} else {
 			if (q->flags & CUBIT_Q_FUSE_PROBE) {
 				probe_mode = PROBE_FUSED;
-			} else if (want_ids && cap <= t->n_rows / 256) {
-				// sparse and the row IDs are materialised anyway: gathering over the short ID list
-				// beats writing + re-reading the N/8-byte bitvector (measured: profiles/)
+			} else if (cap <= t->n_rows / 256 && (want_ids || want_vals || want_q || k > 1 || has_delta)) {
+				// sparse: gathering over the short row-ID list (materialised internally when the caller did
+				// not ask for it: 8 bytes per selected row) beats writing + re-reading the N/8-byte bitvector
+				// (measured: profiles/); a single clean bitvector is probed in place instead (probe_on_bv)
 				probe_mode = PROBE_GATHER;
 			} else {
 				probe_mode = PROBE_BITS;

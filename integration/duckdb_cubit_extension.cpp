@@ -49,14 +49,20 @@
 namespace duckdb {
 
 // ---------------------------------------------------------------- registry of GPU-resident tables
-struct CubitGpuTable {
-	cubit_gpu_table *handle = nullptr;
+// one CUBIT index of a GPU-resident table: value v of `key_table_column` ↔ bitvector v - base_value
+struct CubitGpuIndex {
 	int32_t index_id = -1;
 	int64_t base_value = 0;
 	uint32_t cardinality = 0;
+	idx_t key_table_column = 0; // table column index of the indexed column
+};
+
+struct CubitGpuTable {
+	cubit_gpu_table *handle = nullptr;
+	vector<CubitGpuIndex> indexes; // [0] = the one cubit_scan(table, lo, hi) / cubit_agg address; CALL cubit_load again
+	                               // with another key column to add more (conjunctions across them are rewritten)
 	vector<string> column_names; // uploaded BIGINT columns, column id = position
 	vector<idx_t> table_column;  // table column index of every uploaded column
-	idx_t key_table_column = 0;  // table column index of the indexed column
 	idx_t row_count = 0;
 	~CubitGpuTable() {
 		cubit_gpu_destroy(handle);
@@ -195,6 +201,43 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 	if (bind.done) {
 		return;
 	}
+	{ // the table is already resident (any DML would have dropped it): just index one more of its columns
+		shared_ptr<CubitGpuTable> have;
+		{
+			std::lock_guard<std::mutex> lk(cubit_registry_lock);
+			auto it = cubit_registry.find(bind.table);
+			if (it != cubit_registry.end()) {
+				have = it->second;
+			}
+		}
+		if (have) {
+			idx_t gcol = 0;
+			while (gcol < have->column_names.size() && have->column_names[gcol] != bind.key) {
+				gcol++;
+			}
+			bool known = gcol == have->column_names.size();
+			for (auto &ix : have->indexes) {
+				known |= ix.key_table_column == have->table_column[gcol < have->table_column.size() ? gcol : 0];
+			}
+			if (!known) {
+				CubitGpuIndex ix;
+				ix.base_value = bind.base;
+				ix.cardinality = bind.cardinality;
+				ix.key_table_column = have->table_column[gcol];
+				CubitCheck(cubit_gpu_index_create(have->handle, ix.cardinality, &ix.index_id));
+				CubitCheck(cubit_gpu_index_build(have->handle, ix.index_id, NumericCast<int32_t>(gcol), ix.base_value));
+				{
+					std::lock_guard<std::mutex> lk(cubit_registry_lock);
+					have->indexes.push_back(ix);
+				}
+				output.SetValue(0, 0, Value::BIGINT(NumericCast<int64_t>(have->row_count)));
+				output.SetCardinality(1);
+				bind.done = true;
+				return;
+			}
+			// same key again (or an unknown column): reload from scratch below
+		}
+	}
 	// Pull the key and every BIGINT-castable column in row order through a second connection
 	// (rows come back in insertion order: physical_result_collector.cpp:21-45).
 	Connection con(*context.db);
@@ -248,23 +291,24 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 					}
 					const idx_t row = rows_seen + r;
 					valid[k][row / 64] &= ~(uint64_t(1) << (row % 64));
-					if (k == key_col) {
-						cols[k][row] = NumericLimits<int64_t>::Minimum(); // outside every indexed domain
-					}
+					// NULL rows carry a value outside every indexed domain (the probe never shows it: the
+					// validity mask does), so any column can become an index key later
+					cols[k][row] = NumericLimits<int64_t>::Minimum();
 				}
 			}
 		}
 		rows_seen += chunk.size();
 	}
-	gpu->key_table_column = int_cols[key_col];
+	CubitGpuIndex first;
+	first.key_table_column = int_cols[key_col];
+	first.base_value = bind.base;
+	first.cardinality = bind.cardinality;
 	gpu->row_count = cols.empty() ? 0 : cols[0].size();
-	gpu->base_value = bind.base;
-	gpu->cardinality = bind.cardinality;
 	CubitCheck(cubit_gpu_create(0, gpu->row_count, 0, 65536, &gpu->handle));
 	for (idx_t k = 0; k < cols.size(); k++) {
 		// compressed segments straight from the buffer manager when the column qualifies, decoded rows otherwise
-		// (a key column with NULLs goes the decoded way: its NULL rows must carry an out-of-domain value)
-		const bool null_keys = k == key_col && !valid[k].empty();
+		// (a column with NULLs goes the decoded way: its NULL rows must carry an out-of-domain value)
+		const bool null_keys = !valid[k].empty();
 		if (null_keys || !CubitUploadColumnSegments(context, bind.table, int_cols[k], res->types[int_cols[k]],
 		                                            gpu->handle, NumericCast<int32_t>(k), gpu->row_count)) {
 			CubitCheck(cubit_gpu_upload_column(gpu->handle, NumericCast<int32_t>(k), cols[k].data(), 8, gpu->row_count));
@@ -274,8 +318,9 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 			                                            valid[k].size()));
 		}
 	}
-	CubitCheck(cubit_gpu_index_create(gpu->handle, gpu->cardinality, &gpu->index_id));
-	CubitCheck(cubit_gpu_index_build(gpu->handle, gpu->index_id, NumericCast<int32_t>(key_col), gpu->base_value));
+	CubitCheck(cubit_gpu_index_create(gpu->handle, first.cardinality, &first.index_id));
+	CubitCheck(cubit_gpu_index_build(gpu->handle, first.index_id, NumericCast<int32_t>(key_col), first.base_value));
+	gpu->indexes.push_back(first);
 	{
 		std::lock_guard<std::mutex> lk(cubit_registry_lock);
 		cubit_registry[bind.table] = gpu;
@@ -288,7 +333,12 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 // ---------------------------------------------------------------- cubit_scan(table, lo, hi)
 struct CubitScanBindData : public TableFunctionData {
 	shared_ptr<CubitGpuTable> gpu;
-	int64_t lo = 0, hi = 0;
+	// AND of one range per index: lo <= key <= hi → OR over the value bitvectors in [lo, hi]
+	struct Range {
+		idx_t index_slot;
+		int64_t lo, hi;
+	};
+	vector<Range> ranges;
 	// aggregate push-down (cubit_agg)
 	int32_t agg_col = -1;
 	// set by the optimizer rewrite: column_ids are TABLE column indexes and must be mapped to GPU column ids
@@ -316,8 +366,7 @@ static unique_ptr<FunctionData> CubitScanBind(ClientContext &, TableFunctionBind
                                               vector<LogicalType> &return_types, vector<string> &names) {
 	auto bind = make_uniq<CubitScanBindData>();
 	bind->gpu = CubitLookup(input.inputs[0].GetValue<string>());
-	bind->lo = input.inputs[1].GetValue<int64_t>();
-	bind->hi = input.inputs[2].GetValue<int64_t>();
+	bind->ranges.push_back({0, input.inputs[1].GetValue<int64_t>(), input.inputs[2].GetValue<int64_t>()});
 	for (auto &n : bind->gpu->column_names) {
 		return_types.emplace_back(LogicalType::BIGINT);
 		names.emplace_back(n);
@@ -347,16 +396,21 @@ static unique_ptr<GlobalTableFunctionState> CubitRunQuery(const CubitScanBindDat
 		column_ids.push_back(c);
 	}
 	state->column_ids = column_ids;
-	const int64_t lo = MaxValue<int64_t>(bind.lo, gpu.base_value);
-	const int64_t hi = MinValue<int64_t>(bind.hi, gpu.base_value + gpu.cardinality - 1);
-	if (lo > hi) {
-		return std::move(state);
+	// one OR group per range, AND across the groups (Q = AND_j OR_{v in [lo_j, hi_j]} B_v)
+	vector<vector<cubit_bv_ref>> refs(bind.ranges.size());
+	vector<cubit_pred_group> groups;
+	for (idx_t j = 0; j < bind.ranges.size(); j++) {
+		auto &ix = gpu.indexes[bind.ranges[j].index_slot];
+		const int64_t lo = MaxValue<int64_t>(bind.ranges[j].lo, ix.base_value);
+		const int64_t hi = MinValue<int64_t>(bind.ranges[j].hi, ix.base_value + ix.cardinality - 1);
+		if (lo > hi) {
+			return std::move(state); // an empty range empties the conjunction
+		}
+		for (int64_t v = lo; v <= hi; v++) {
+			refs[j].push_back(cubit_bv_ref {ix.index_id, NumericCast<uint32_t>(v - ix.base_value)});
+		}
+		groups.push_back(cubit_pred_group {NumericCast<uint32_t>(refs[j].size()), refs[j].data()});
 	}
-	vector<cubit_bv_ref> refs;
-	for (int64_t v = lo; v <= hi; v++) {
-		refs.push_back(cubit_bv_ref {gpu.index_id, NumericCast<uint32_t>(v - gpu.base_value)});
-	}
-	cubit_pred_group group {NumericCast<uint32_t>(refs.size()), refs.data()};
 	vector<int32_t> cols;
 	bool want_rowid = false;
 	for (auto c : column_ids) {
@@ -367,8 +421,8 @@ static unique_ptr<GlobalTableFunctionState> CubitRunQuery(const CubitScanBindDat
 		}
 	}
 	cubit_query q {};
-	q.n_groups = 1;
-	q.groups = &group;
+	q.n_groups = NumericCast<uint32_t>(groups.size());
+	q.groups = groups.data();
 	if (bind.agg_col >= 0) {
 		q.agg_kind = CUBIT_AGG_SUM;
 		q.agg_col_a = bind.agg_col;
@@ -436,8 +490,7 @@ static unique_ptr<FunctionData> CubitAggBind(ClientContext &, TableFunctionBindI
                                              vector<LogicalType> &return_types, vector<string> &names) {
 	auto bind = make_uniq<CubitScanBindData>();
 	bind->gpu = CubitLookup(input.inputs[0].GetValue<string>());
-	bind->lo = input.inputs[1].GetValue<int64_t>();
-	bind->hi = input.inputs[2].GetValue<int64_t>();
+	bind->ranges.push_back({0, input.inputs[1].GetValue<int64_t>(), input.inputs[2].GetValue<int64_t>()});
 	auto col = input.inputs[3].GetValue<string>();
 	for (idx_t c = 0; c < bind->gpu->column_names.size(); c++) {
 		if (bind->gpu->column_names[c] == col) {
@@ -535,8 +588,8 @@ static void CubitRewriteGet(LogicalGet &get) {
 	if (get.function.name != "seq_scan") {
 		CUBIT_WHY(get.function.name.c_str());
 	}
-	if (get.table_filters.filters.size() != 1) {
-		CUBIT_WHY("not exactly one filtered column");
+	if (get.table_filters.filters.empty()) {
+		CUBIT_WHY("no pushed-down filter");
 	}
 	auto table = get.GetTable();
 	if (!table) {
@@ -551,15 +604,30 @@ static void CubitRewriteGet(LogicalGet &get) {
 		}
 		gpu = it->second;
 	}
-	// the only pushed-down filter must sit on the indexed column (keys of LogicalGet::table_filters are
-	// table column indexes: filter_combiner.cpp:438-480, plan_get.cpp:15-33)
-	auto &entry = *get.table_filters.filters.begin();
-	if (entry.first != gpu->key_table_column) {
-		CUBIT_WHY("filter is not on the indexed column");
+	// EVERY pushed-down filter must sit on an indexed column (keys of LogicalGet::table_filters are table column
+	// indexes: filter_combiner.cpp:438-480, plan_get.cpp:15-33); each becomes one OR group over the value
+	// bitvectors of its range, the groups are ANDed — the Q6-style conjunction of range predicates
+	vector<CubitScanBindData::Range> ranges;
+	idx_t n_streams = 0;
+	for (auto &entry : get.table_filters.filters) {
+		idx_t slot = 0;
+		while (slot < gpu->indexes.size() && gpu->indexes[slot].key_table_column != entry.first) {
+			slot++;
+		}
+		if (slot == gpu->indexes.size()) {
+			CUBIT_WHY("a filter sits on a column without a GPU index");
+		}
+		int64_t lo = NumericLimits<int64_t>::Minimum() + 1, hi = NumericLimits<int64_t>::Maximum() - 1;
+		if (!CubitBoundsFromFilter(*entry.second, lo, hi)) {
+			CUBIT_WHY("unsupported filter shape");
+		}
+		auto &ix = gpu->indexes[slot];
+		const int64_t clo = MaxValue<int64_t>(lo, ix.base_value), chi = MinValue<int64_t>(hi, ix.base_value + ix.cardinality - 1);
+		n_streams += chi >= clo ? NumericCast<idx_t>(chi - clo + 1) : 0;
+		ranges.push_back({slot, lo, hi});
 	}
-	int64_t lo = NumericLimits<int64_t>::Minimum() + 1, hi = NumericLimits<int64_t>::Maximum() - 1;
-	if (!CubitBoundsFromFilter(*entry.second, lo, hi)) {
-		CUBIT_WHY("unsupported filter shape");
+	if (n_streams > CUBIT_MAX_STREAMS) {
+		CUBIT_WHY("predicate reads more value bitvectors than one scan merges");
 	}
 	// every column that leaves the scan must be GPU resident and physically int64 (BIGINT, DECIMAL(≤18))
 	for (idx_t i = 0; i < (get.projection_ids.empty() ? get.column_ids.size() : get.projection_ids.size()); i++) {
@@ -580,8 +648,7 @@ static void CubitRewriteGet(LogicalGet &get) {
 	}
 	auto bind = make_uniq<CubitScanBindData>();
 	bind->gpu = gpu;
-	bind->lo = lo;
-	bind->hi = hi;
+	bind->ranges = std::move(ranges);
 	bind->table_column_ids = true;
 	get.function = CubitScanTableFunction();
 	get.bind_data = std::move(bind);

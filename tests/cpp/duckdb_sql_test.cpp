@@ -99,6 +99,39 @@ int main(int argc, char **argv) {
 		auto plan = Run(con, "EXPLAIN SELECT sum(price) FROM t WHERE q BETWEEN 10 AND 19");
 		REQUIRE(plan->GetValue(1, 0).ToString().find("CUBIT_SCAN") != string::npos);
 	}
+	{ // a second index on the same table: conjunctions across indexed columns become AND of OR groups
+		auto l2 = Run(con, "CALL cubit_load('t', 'disc', 0, 11)");
+		REQUIRE(l2->GetValue(0, 0).GetValue<int64_t>() == 300000);
+		const char *conj[] = {"q BETWEEN 10 AND 19 AND disc BETWEEN 5 AND 7", "q = 24 AND disc = 3", "q < 24 AND disc >= 9",
+		                      "disc = 0", "q >= 40 AND disc <= 1 AND disc >= 0", "q = 24 AND disc = 30"};
+		for (auto w : conj) {
+			const string where = w;
+			const idx_t before = CubitRewriteCount();
+			auto a = Run(con, "SELECT count(*), sum(price), sum(price * disc), min(rowid), max(rowid) FROM t WHERE " + where);
+			auto b = Run(con, "SELECT count(*), sum(price), sum(price * disc), min(rowid), max(rowid) FROM t_plain WHERE " + where);
+			REQUIRE(CubitRewriteCount() == before + (b->GetValue(0, 0).GetValue<int64_t>() > 0 ? 1 : 0));
+			for (idx_t c = 0; c < 5; c++) {
+				REQUIRE(a->GetValue(c, 0).ToString() == b->GetValue(c, 0).ToString());
+			}
+			auto x = Run(con, "SELECT rowid, q, price, disc FROM t WHERE " + where + " ORDER BY rowid");
+			auto y = Run(con, "SELECT rowid, q, price, disc FROM t_plain WHERE " + where + " ORDER BY rowid");
+			REQUIRE(x->RowCount() == y->RowCount());
+			for (idx_t r = 0; r < x->RowCount(); r += 53) {
+				for (idx_t c = 0; c < 4; c++) {
+					REQUIRE(x->GetValue(c, r) == y->GetValue(c, r));
+				}
+			}
+		}
+		// a range that would read more than CUBIT_MAX_STREAMS bitvectors keeps the vanilla scan
+		Run(con, "CREATE TABLE tw AS SELECT (i % 200)::BIGINT AS k, i::BIGINT AS v FROM range(50000) r(i)");
+		Run(con, "CALL cubit_load('tw', 'k', 0, 200)");
+		const idx_t before = CubitRewriteCount();
+		auto wide = Run(con, "SELECT count(*), sum(v) FROM tw WHERE k BETWEEN 10 AND 120");
+		REQUIRE(CubitRewriteCount() == before && wide->GetValue(0, 0).GetValue<int64_t>() == 111 * 250);
+		auto narrow = Run(con, "SELECT count(*) FROM tw WHERE k BETWEEN 10 AND 70");
+		REQUIRE(CubitRewriteCount() == before + 1 && narrow->GetValue(0, 0).GetValue<int64_t>() == 61 * 250);
+		printf("multi-index conjunctions ok\n");
+	}
 	{ // NULLs: in projected columns (validity masks on the DataChunk vectors), in aggregate inputs (skipped;
 	  // SUM over only-NULL inputs is NULL) and in the key (NULL keys are not indexed)
 		Run(con, "CREATE TABLE tn AS SELECT CASE WHEN i % 13 = 0 THEN NULL ELSE (i * 7919 % 50 + 1) END::BIGINT AS q, "

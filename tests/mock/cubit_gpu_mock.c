@@ -29,8 +29,10 @@ struct cubit_gpu_table {
 	int64_t row_base;
 	int64_t *cols[MAX_COLS];
 	uint64_t *valid[MAX_COLS];
-	uint64_t *bits; /* one index only */
-	uint32_t card;
+#define MAX_INDEXES 8
+	uint64_t *bits[MAX_INDEXES];
+	uint32_t card[MAX_INDEXES];
+	int n_indexes;
 };
 struct cubit_gpu_result {
 	struct cubit_gpu_table *t;
@@ -57,7 +59,8 @@ int cubit_gpu_create(int device, uint64_t n_rows, int64_t row_base, uint32_t seg
 int cubit_gpu_destroy(cubit_gpu_table *t) {
 	if (!t) return CUBIT_OK;
 	for (int i = 0; i < MAX_COLS; i++) { free(t->cols[i]); free(t->valid[i]); }
-	free(t->bits); free(t);
+	for (int i = 0; i < t->n_indexes; i++) free(t->bits[i]);
+	free(t);
 	return CUBIT_OK;
 }
 int cubit_gpu_upload_column(cubit_gpu_table *t, int32_t col_id, const void *data, uint32_t elem_bytes, uint64_t n) {
@@ -99,20 +102,23 @@ int cubit_gpu_upload_column_segments(cubit_gpu_table *t, int32_t col_id, uint32_
 	return CUBIT_OK;
 }
 int cubit_gpu_index_create(cubit_gpu_table *t, uint32_t cardinality, int32_t *index_id) {
-	t->card = cardinality; t->bits = calloc((size_t)cardinality * t->n_words, 8); *index_id = 0;
+	if (t->n_indexes == MAX_INDEXES) { snprintf(g_err, sizeof g_err, "mock: too many indexes"); return CUBIT_EINVAL; }
+	t->card[t->n_indexes] = cardinality; t->bits[t->n_indexes] = calloc((size_t)cardinality * t->n_words, 8);
+	*index_id = t->n_indexes++;
 	return CUBIT_OK;
 }
 int cubit_gpu_index_build(cubit_gpu_table *t, int32_t index_id, int32_t col_id, int64_t base_value) {
-	(void)index_id;
-	oracle_build_index(t->cols[col_id], 8, t->n_rows, base_value, t->card, t->bits, t->n_words);
+	if (index_id < 0 || index_id >= t->n_indexes) { snprintf(g_err, sizeof g_err, "mock: bad index"); return CUBIT_EINVAL; }
+	oracle_build_index(t->cols[col_id], 8, t->n_rows, base_value, t->card[index_id], t->bits[index_id], t->n_words);
 	return CUBIT_OK;
 }
 int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_result **out) {
 	const uint64_t *streams[CUBIT_MAX_STREAMS]; int32_t group_of[CUBIT_MAX_STREAMS]; int k = 0;
 	for (uint32_t g = 0; g < q->n_groups; g++)
 		for (uint32_t i = 0; i < q->groups[g].n_refs; i++) {
-			if (q->groups[g].refs[i].value_id >= t->card) { snprintf(g_err, sizeof g_err, "mock: bad value id"); return CUBIT_EINVAL; }
-			streams[k] = t->bits + (size_t)q->groups[g].refs[i].value_id * t->n_words; group_of[k++] = (int32_t)g;
+			const int32_t ix = q->groups[g].refs[i].index_id;
+			if (ix < 0 || ix >= t->n_indexes || q->groups[g].refs[i].value_id >= t->card[ix] || k >= CUBIT_MAX_STREAMS) { snprintf(g_err, sizeof g_err, "mock: bad bitvector ref"); return CUBIT_EINVAL; }
+			streams[k] = t->bits[ix] + (size_t)q->groups[g].refs[i].value_id * t->n_words; group_of[k++] = (int32_t)g;
 		}
 	uint64_t *qb = malloc(t->n_words * 8);
 	oracle_merge(streams, NULL, group_of, k, t->n_words, qb);

@@ -67,11 +67,28 @@ def cfg1(cubit):
     g = [[(ix, 23)]]
     agg = timed(cubit, t, g, agg=cubit.AGG_SUM, agg_a=0)
     ids = timed(cubit, t, g, flags=cubit.Q_ROWIDS | cubit.Q_VALUES, cols=[0], agg=cubit.AGG_SUM, agg_a=0)
+    # end-to-end latency of the synchronous C-ABI call (host predicate in → COUNT/SUM on the host), wall clock
+    lat = {}
+    for name, kw in (("aggregate_only", dict(agg=cubit.AGG_SUM, agg_a=0)),
+                     ("rowids_values_first_chunk", dict(flags=cubit.Q_ROWIDS | cubit.Q_VALUES, cols=[0], agg=cubit.AGG_SUM, agg_a=0))):
+        plan = cubit.QueryPlan(g, **kw)
+        ids_h, val_h = np.empty(2048, dtype=np.int64), [np.empty(2048, dtype=np.int64)]
+        ts = []
+        for i in range(300):
+            t0 = time.perf_counter()
+            with t.execute(plan) as r:
+                c = r.count
+                if "flags" in kw:
+                    r.fetch(0, min(2048, c), out_ids=ids_h, out_cols=val_h)
+            ts.append(time.perf_counter() - t0)
+        ts = sorted(ts[50:])
+        lat[name] = {"median_us": round(ts[len(ts) // 2] * 1e6, 1), "p10_us": round(ts[len(ts) // 10] * 1e6, 1)}
     qty, price = t.download_column(1), t.download_column(0)
     want = np.flatnonzero(qty == 24)
     assert agg["count"] == ids["count"] == len(want) and agg["sum"] == ids["sum"] == int(price[want].sum())
     t.close()
     return {"n_rows": n, "k": 1, "selected": len(want), "aggregate_only": agg, "rowids_values_sum": ids,
+            "e2e_latency_sync_call": lat,
             "note": "launch-latency dominated (750 KB bitvector): report microseconds, not % roofline",
             "check": "COUNT and SUM equal a host evaluation of the downloaded columns"}
 

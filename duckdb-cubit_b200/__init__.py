@@ -37,6 +37,7 @@ ABI_SYMBOLS = [
     "cubit_gpu_query",
     "cubit_gpu_result_wait", "cubit_gpu_result_get", "cubit_gpu_fetch", "cubit_gpu_fetch_bitvector",
     "cubit_gpu_free_result", "cubit_gpu_probe", "cubit_gpu_upload_column_validity", "cubit_gpu_fetch_validity",
+    "cubit_gpu_index_serialize", "cubit_gpu_index_deserialize", "cubit_gpu_free_image",
 ]
 
 
@@ -137,6 +138,9 @@ def load_library():
         "cubit_gpu_probe": ([vp, i32, vp, u64, vp, P(u64), P(i64)], C.c_int),
         "cubit_gpu_upload_column_validity": ([vp, i32, vp, u64], C.c_int),
         "cubit_gpu_fetch_validity": ([vp, u32, u64, u64, vp, P(C.c_int)], C.c_int),
+        "cubit_gpu_index_serialize": ([vp, i32, P(vp), P(u64)], C.c_int),
+        "cubit_gpu_index_deserialize": ([vp, vp, u64, P(i32)], C.c_int),
+        "cubit_gpu_free_image": ([vp], None),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -329,6 +333,22 @@ class CubitTable:
         out = np.empty(self.n_words, dtype=np.uint64)
         _check(self._L.cubit_gpu_download_bitvector(self._h, index_id, value_id, out.ctypes.data, len(out)))
         return out
+
+    def serialize_index(self, index_id):
+        """→ bytes: the persistent image of one index (bitvectors verbatim / WAH, pending deltas, checksum)"""
+        img, n = C.c_void_p(None), C.c_uint64(0)
+        _check(self._L.cubit_gpu_index_serialize(self._h, index_id, C.byref(img), C.byref(n)))
+        try:
+            return C.string_at(img.value, n.value)
+        finally:
+            self._L.cubit_gpu_free_image(img)
+
+    def deserialize_index(self, image):
+        """recreate an index from serialize_index's image → new index id"""
+        buf = np.frombuffer(image, dtype=np.uint8)
+        ix = C.c_int32(-1)
+        _check(self._L.cubit_gpu_index_deserialize(self._h, buf.ctypes.data, len(buf), C.byref(ix)))
+        return ix.value
 
     def build_index(self, index_id, col_id, base_value=0):
         _check(self._L.cubit_gpu_index_build(self._h, index_id, col_id, base_value))

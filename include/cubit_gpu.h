@@ -175,6 +175,18 @@ int cubit_gpu_set_delta(cubit_gpu_table *t, int32_t index_id, uint32_t value_id,
 /* merge-back: B_v ^= D_v for every bitvector of the index, deltas cleared */
 int cubit_gpu_merge_deltas(cubit_gpu_table *t, int32_t index_id);
 
+/* Persistence of an index: the analog of BoundIndex::GetStorageInfo → IndexStorageInfo
+ * (src/include/duckdb/execution/index/bound_index.hpp:117-118), written at checkpoint and read back when the
+ * table is attached.  cubit_gpu_index_serialize produces a self-describing byte image of ONE index: header,
+ * every value bitvector either verbatim or WAH-compressed (the form cubit_gpu_upload_bitvector_wah expands on
+ * the GPU — whichever is smaller), the pending deltas as flipped-row lists (they stay pending after a reload),
+ * and a checksum.  *image is malloc'ed by the library: release it with cubit_gpu_free_image.
+ * cubit_gpu_index_deserialize validates the image (magic, sizes, row count of THIS table, checksum; CUBIT_EINVAL
+ * before anything is uploaded) and recreates the index: *index_id receives the new id. */
+int cubit_gpu_index_serialize(cubit_gpu_table *t, int32_t index_id, void **image, uint64_t *bytes);
+int cubit_gpu_index_deserialize(cubit_gpu_table *t, const void *image, uint64_t bytes, int32_t *index_id);
+void cubit_gpu_free_image(void *image);
+
 /* ---- columns (decoded, fixed width 4 or 8 bytes, HBM resident) ---------- */
 int cubit_gpu_upload_column(cubit_gpu_table *t, int32_t col_id, const void *data, uint32_t elem_bytes, uint64_t n);
 int cubit_gpu_download_column(cubit_gpu_table *t, int32_t col_id, void *data, uint32_t elem_bytes, uint64_t n);

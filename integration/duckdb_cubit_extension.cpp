@@ -28,6 +28,11 @@
 #include "duckdb/optimizer/optimizer_extension.hpp"
 #include "duckdb/planner/filter/conjunction_filter.hpp"
 #include "duckdb/planner/filter/constant_filter.hpp"
+#include "duckdb/planner/expression/bound_aggregate_expression.hpp"
+#include "duckdb/planner/expression/bound_cast_expression.hpp"
+#include "duckdb/planner/expression/bound_columnref_expression.hpp"
+#include "duckdb/planner/expression/bound_function_expression.hpp"
+#include "duckdb/planner/operator/logical_aggregate.hpp"
 #include "duckdb/planner/operator/logical_delete.hpp"
 #include "duckdb/planner/operator/logical_get.hpp"
 #include "duckdb/planner/operator/logical_insert.hpp"
@@ -354,6 +359,14 @@ struct CubitScanGlobalState : public GlobalTableFunctionState {
 	int64_t sum_hi = 0;
 	uint64_t agg_rows = 0; // non-NULL inputs of the pushed-down SUM
 	bool agg_emitted = false;
+	// host staging window: result rows [win_begin, win_end) fetched with ONE device→host copy per column and
+	// served to the executor 2048 rows at a time (a copy + synchronise per DataChunk costs ~30 us, i.e. more
+	// than the whole scan for a few hundred thousand rows)
+	static constexpr idx_t WINDOW_ROWS = 64 * STANDARD_VECTOR_SIZE;
+	idx_t win_begin = 0, win_end = 0;
+	vector<int64_t> win_rowids;
+	vector<vector<int64_t>> win_cols;       // one per projected value column
+	vector<vector<uint64_t>> win_validity;  // ValidityMask words of the window, empty = no NULL in the window
 	~CubitScanGlobalState() override {
 		cubit_gpu_free_result(result);
 	}
@@ -450,36 +463,59 @@ static void CubitScanFunction(ClientContext &, TableFunctionInput &data_p, DataC
 	if (state.offset >= state.row_count) {
 		return; // chunk.size() == 0 → PhysicalTableScan::GetData returns FINISHED
 	}
-	const idx_t scan_count = MinValue<idx_t>(STANDARD_VECTOR_SIZE, state.row_count - state.offset);
-	int64_t *rowids = nullptr;
-	vector<void *> col_ptrs;
-	for (idx_t i = 0; i < state.column_ids.size(); i++) {
-		auto ptr = FlatVector::GetData<int64_t>(output.data[i]);
-		if (state.column_ids[i] == COLUMN_IDENTIFIER_ROW_ID) {
-			rowids = ptr;
-		} else {
-			col_ptrs.push_back(ptr);
+	if (state.offset >= state.win_end) { // refill the staging window
+		const idx_t n = MinValue<idx_t>(CubitScanGlobalState::WINDOW_ROWS, state.row_count - state.offset);
+		state.win_begin = state.offset;
+		state.win_end = state.offset + n;
+		bool want_rowid = false;
+		idx_t n_value_cols = 0;
+		for (auto c : state.column_ids) {
+			want_rowid |= c == COLUMN_IDENTIFIER_ROW_ID;
+			n_value_cols += c != COLUMN_IDENTIFIER_ROW_ID;
+		}
+		state.win_cols.resize(n_value_cols);
+		state.win_validity.resize(n_value_cols);
+		vector<void *> ptrs;
+		for (auto &col : state.win_cols) {
+			col.resize(n);
+			ptrs.push_back(col.data());
+		}
+		if (want_rowid) {
+			state.win_rowids.resize(n);
+		}
+		CubitCheck(cubit_gpu_fetch(state.result, state.win_begin, n, want_rowid ? state.win_rowids.data() : nullptr,
+		                           NumericCast<uint32_t>(ptrs.size()), ptrs.data()));
+		// NULLs: the validity mask of every projected value (StandardColumnData::FetchRow = validity + data)
+		for (idx_t c = 0; c < n_value_cols; c++) {
+			int all_valid = 1;
+			state.win_validity[c].assign((n + 63) / 64, 0);
+			CubitCheck(cubit_gpu_fetch_validity(state.result, NumericCast<uint32_t>(c), state.win_begin, n,
+			                                    state.win_validity[c].data(), &all_valid));
+			if (all_valid) {
+				state.win_validity[c].clear();
+			}
 		}
 	}
-	CubitCheck(cubit_gpu_fetch(state.result, state.offset, scan_count, rowids, NumericCast<uint32_t>(col_ptrs.size()),
-	                           col_ptrs.data()));
-	// NULLs: the validity mask of every projected value (StandardColumnData::FetchRow = validity + data)
-	uint32_t value_col = 0;
+	const idx_t scan_count = MinValue<idx_t>(STANDARD_VECTOR_SIZE, state.win_end - state.offset);
+	const idx_t rel = state.offset - state.win_begin; // a multiple of 2048: word aligned in the window's masks
+	idx_t value_col = 0;
 	for (idx_t i = 0; i < state.column_ids.size(); i++) {
+		auto dst = FlatVector::GetData<int64_t>(output.data[i]);
 		if (state.column_ids[i] == COLUMN_IDENTIFIER_ROW_ID) {
+			memcpy(dst, state.win_rowids.data() + rel, scan_count * sizeof(int64_t));
 			continue;
 		}
-		uint64_t words[STANDARD_VECTOR_SIZE / 64];
-		int all_valid = 1;
-		CubitCheck(cubit_gpu_fetch_validity(state.result, value_col++, state.offset, scan_count, words, &all_valid));
-		if (!all_valid) {
+		memcpy(dst, state.win_cols[value_col].data() + rel, scan_count * sizeof(int64_t));
+		auto &words = state.win_validity[value_col];
+		if (!words.empty()) {
 			auto &mask = FlatVector::Validity(output.data[i]);
 			for (idx_t r = 0; r < scan_count; r++) {
-				if (!((words[r / 64] >> (r % 64)) & 1)) {
+				if (!((words[(rel + r) / 64] >> ((rel + r) % 64)) & 1)) {
 					mask.SetInvalid(r);
 				}
 			}
 		}
+		value_col++;
 	}
 	output.SetCardinality(scan_count);
 	state.offset += scan_count;
@@ -576,15 +612,17 @@ static bool CubitBoundsFromFilter(const TableFilter &filter, int64_t &lo, int64_
 	}
 }
 
+// Can this seq_scan's pushed-down filters be answered by the table's GPU indexes?  Fills the table and one
+// (index, lo, hi) range per filtered column.  Nothing is modified.
+static bool CubitPlanGet(LogicalGet &get, shared_ptr<CubitGpuTable> &gpu, vector<CubitScanBindData::Range> &ranges) {
+#undef CUBIT_WHY
 #define CUBIT_WHY(msg)                                                                                                  \
 	do {                                                                                                               \
 		if (getenv("CUBIT_DEBUG_REWRITE")) {                                                                           \
 			fprintf(stderr, "cubit rewrite skipped: %s\n", msg);                                                      \
 		}                                                                                                              \
-		return;                                                                                                        \
+		return false;                                                                                                  \
 	} while (0)
-
-static void CubitRewriteGet(LogicalGet &get) {
 	if (get.function.name != "seq_scan") {
 		CUBIT_WHY(get.function.name.c_str());
 	}
@@ -595,7 +633,6 @@ static void CubitRewriteGet(LogicalGet &get) {
 	if (!table) {
 		CUBIT_WHY("no table");
 	}
-	shared_ptr<CubitGpuTable> gpu;
 	{
 		std::lock_guard<std::mutex> lk(cubit_registry_lock);
 		auto it = cubit_registry.find(table->name);
@@ -607,7 +644,6 @@ static void CubitRewriteGet(LogicalGet &get) {
 	// EVERY pushed-down filter must sit on an indexed column (keys of LogicalGet::table_filters are table column
 	// indexes: filter_combiner.cpp:438-480, plan_get.cpp:15-33); each becomes one OR group over the value
 	// bitvectors of its range, the groups are ANDed — the Q6-style conjunction of range predicates
-	vector<CubitScanBindData::Range> ranges;
 	idx_t n_streams = 0;
 	for (auto &entry : get.table_filters.filters) {
 		idx_t slot = 0;
@@ -629,21 +665,40 @@ static void CubitRewriteGet(LogicalGet &get) {
 	if (n_streams > CUBIT_MAX_STREAMS) {
 		CUBIT_WHY("predicate reads more value bitvectors than one scan merges");
 	}
+	return true;
+}
+
+// GPU column id of table column `c` if it is resident and physically INT64 (BIGINT, DECIMAL(≤18)), else -1
+static int32_t CubitResidentColumn(const LogicalGet &get, const CubitGpuTable &gpu, column_t c) {
+	if (c == COLUMN_IDENTIFIER_ROW_ID || c >= get.returned_types.size() ||
+	    get.returned_types[c].InternalType() != PhysicalType::INT64) {
+		return -1;
+	}
+	for (idx_t g = 0; g < gpu.table_column.size(); g++) {
+		if (gpu.table_column[g] == c) {
+			return NumericCast<int32_t>(g);
+		}
+	}
+	return -1;
+}
+
+static void CubitRewriteGet(LogicalGet &get) {
+	shared_ptr<CubitGpuTable> gpu;
+	vector<CubitScanBindData::Range> ranges;
+	if (!CubitPlanGet(get, gpu, ranges)) {
+		return;
+	}
 	// every column that leaves the scan must be GPU resident and physically int64 (BIGINT, DECIMAL(≤18))
 	for (idx_t i = 0; i < (get.projection_ids.empty() ? get.column_ids.size() : get.projection_ids.size()); i++) {
 		const column_t c = get.column_ids[get.projection_ids.empty() ? i : get.projection_ids[i]];
 		if (c == COLUMN_IDENTIFIER_ROW_ID) {
 			continue;
 		}
-		if (c >= get.returned_types.size() || get.returned_types[c].InternalType() != PhysicalType::INT64) {
-			CUBIT_WHY("projected column is not physically INT64");
-		}
-		bool resident = false;
-		for (auto tc : gpu->table_column) {
-			resident |= tc == c;
-		}
-		if (!resident) {
-			CUBIT_WHY("projected column is not GPU resident");
+		if (CubitResidentColumn(get, *gpu, c) < 0) {
+			if (getenv("CUBIT_DEBUG_REWRITE")) {
+				fprintf(stderr, "cubit rewrite skipped: projected column is not a GPU-resident INT64 column\n");
+			}
+			return;
 		}
 	}
 	auto bind = make_uniq<CubitScanBindData>();
@@ -656,12 +711,222 @@ static void CubitRewriteGet(LogicalGet &get) {
 	cubit_rewrite_count++;
 }
 
-static void CubitRewritePlan(LogicalOperator &op) {
-	if (op.type == LogicalOperatorType::LOGICAL_GET) {
-		CubitRewriteGet(op.Cast<LogicalGet>());
+// ---------------------------------------------------------------- aggregate push-down
+// An ungrouped aggregate of COUNT(*) / COUNT(col) / SUM(col) / SUM(a * b) sitting directly on a rewritable scan is
+// answered on the GPU in ONE row: no row ever crosses PCIe.  The aggregate node is replaced by
+// a table function that carries the aggregate's own table index and return types, so every reference above it
+// stays valid.  SUM semantics are the reference's: int64 inputs into a 128-bit sum (sum.cpp:172-199), int64 product
+// with overflow error (arithmetic.cpp:766-795), NULL inputs skipped, NULL over no input.
+struct CubitAggSpec {
+	enum Kind : uint8_t { COUNT_STAR, COUNT_COL, SUM_COL, SUM_PROD } kind;
+	int32_t col_a = -1, col_b = -1;
+};
+
+struct CubitAggMultiBindData : public TableFunctionData {
+	shared_ptr<CubitGpuTable> gpu;
+	vector<CubitScanBindData::Range> ranges;
+	vector<CubitAggSpec> specs;
+	vector<LogicalType> types;
+};
+
+struct CubitAggMultiState : public GlobalTableFunctionState {
+	bool emitted = false;
+};
+
+static std::atomic<idx_t> cubit_agg_pushdown_count {0};
+idx_t CubitAggPushdownCount() {
+	return cubit_agg_pushdown_count.load();
+}
+
+static unique_ptr<GlobalTableFunctionState> CubitAggMultiInit(ClientContext &, TableFunctionInitInput &) {
+	return make_uniq<CubitAggMultiState>();
+}
+
+static void CubitAggMultiFunction(ClientContext &, TableFunctionInput &data_p, DataChunk &output) {
+	auto &state = data_p.global_state->Cast<CubitAggMultiState>();
+	if (state.emitted) {
+		return;
 	}
-	for (auto &child : op.children) {
-		CubitRewritePlan(*child);
+	state.emitted = true;
+	auto &bind = data_p.bind_data->Cast<CubitAggMultiBindData>();
+	auto &gpu = *bind.gpu;
+	vector<vector<cubit_bv_ref>> refs(bind.ranges.size());
+	vector<cubit_pred_group> groups;
+	bool empty = false;
+	for (idx_t j = 0; j < bind.ranges.size(); j++) {
+		auto &ix = gpu.indexes[bind.ranges[j].index_slot];
+		const int64_t lo = MaxValue<int64_t>(bind.ranges[j].lo, ix.base_value);
+		const int64_t hi = MinValue<int64_t>(bind.ranges[j].hi, ix.base_value + ix.cardinality - 1);
+		empty |= lo > hi;
+		for (int64_t v = lo; v <= hi; v++) {
+			refs[j].push_back(cubit_bv_ref {ix.index_id, NumericCast<uint32_t>(v - ix.base_value)});
+		}
+		groups.push_back(cubit_pred_group {NumericCast<uint32_t>(refs[j].size()), refs[j].data()});
+	}
+	// one GPU query per aggregate (merge + bit-driven probe with the fused SUM; a few tens of microseconds each)
+	for (idx_t a = 0; a < bind.specs.size(); a++) {
+		auto &spec = bind.specs[a];
+		cubit_result_info info;
+		memset(&info, 0, sizeof(info));
+		if (!empty) {
+			cubit_query q {};
+			q.n_groups = NumericCast<uint32_t>(groups.size());
+			q.groups = groups.data();
+			if (spec.kind != CubitAggSpec::COUNT_STAR) {
+				q.agg_kind = spec.kind == CubitAggSpec::SUM_PROD ? CUBIT_AGG_SUM_PROD : CUBIT_AGG_SUM;
+				q.agg_col_a = spec.col_a;
+				q.agg_col_b = spec.col_b;
+			}
+			cubit_gpu_result *res = nullptr;
+			CubitCheck(cubit_gpu_query(gpu.handle, &q, &res));
+			const int rc = cubit_gpu_result_get(res, &info);
+			cubit_gpu_free_result(res);
+			CubitCheck(rc);
+		}
+		auto &vec = output.data[a];
+		if (spec.kind == CubitAggSpec::COUNT_STAR || spec.kind == CubitAggSpec::COUNT_COL) {
+			const uint64_t n = spec.kind == CubitAggSpec::COUNT_STAR ? info.count : info.agg_rows;
+			FlatVector::GetData<int64_t>(vec)[0] = NumericCast<int64_t>(n);
+		} else if (info.agg_rows == 0) {
+			FlatVector::SetNull(vec, 0, true); // SUM over no non-NULL input
+		} else if (bind.types[a].InternalType() == PhysicalType::INT128) {
+			hugeint_t sum;
+			sum.lower = info.sum_lo;
+			sum.upper = info.sum_hi;
+			FlatVector::GetData<hugeint_t>(vec)[0] = sum;
+		} else { // an INT64-typed sum (sum_no_overflow's narrow form): the statistics guarantee that it fits
+			if ((info.sum_hi != 0 || (info.sum_lo >> 63)) && (info.sum_hi != -1 || !(info.sum_lo >> 63))) {
+				throw OutOfRangeException("cubit: SUM does not fit the INT64 result type");
+			}
+			FlatVector::GetData<int64_t>(vec)[0] = static_cast<int64_t>(info.sum_lo);
+		}
+	}
+	output.SetCardinality(1);
+}
+
+// the GPU column an aggregate input reads: a column reference of the scan, possibly under casts that keep the
+// stored int64 as it is (DECIMAL(15,2) → DECIMAL(18,2): same scale, same physical type)
+static int32_t CubitAggInputColumn(const Expression &expr, const LogicalGet &get, const CubitGpuTable &gpu) {
+	const Expression *e = &expr;
+	while (e->expression_class == ExpressionClass::BOUND_CAST) {
+		auto &cast = e->Cast<BoundCastExpression>();
+		const LogicalType &from = cast.child->return_type;
+		const LogicalType &to = cast.return_type;
+		const bool same_scale = (from.id() == LogicalTypeId::DECIMAL ? DecimalType::GetScale(from) : 0) ==
+		                        (to.id() == LogicalTypeId::DECIMAL ? DecimalType::GetScale(to) : 0);
+		if (from.InternalType() != PhysicalType::INT64 || to.InternalType() != PhysicalType::INT64 || !same_scale ||
+		    (!from.IsIntegral() && from.id() != LogicalTypeId::DECIMAL) || (!to.IsIntegral() && to.id() != LogicalTypeId::DECIMAL)) {
+			return -1;
+		}
+		e = cast.child.get();
+	}
+	if (e->expression_class != ExpressionClass::BOUND_COLUMN_REF) {
+		return -1;
+	}
+	auto &ref = e->Cast<BoundColumnRefExpression>();
+	if (ref.binding.table_index != get.table_index || ref.depth != 0) {
+		return -1;
+	}
+	// a binding's column_index is a position in column_ids, with or without projection_ids
+	// (LogicalGet::GetColumnBindings, src/planner/operator/logical_get.cpp)
+	if (ref.binding.column_index >= get.column_ids.size()) {
+		return -1;
+	}
+	return CubitResidentColumn(get, gpu, get.column_ids[ref.binding.column_index]);
+}
+
+static bool CubitTryAggregatePushdown(unique_ptr<LogicalOperator> &op) {
+	if (op->type != LogicalOperatorType::LOGICAL_AGGREGATE_AND_GROUP_BY) {
+		return false;
+	}
+	auto &aggr = op->Cast<LogicalAggregate>();
+	if (!aggr.groups.empty() || !aggr.grouping_functions.empty() || aggr.grouping_sets.size() > 1 ||
+	    aggr.children.size() != 1 || aggr.children[0]->type != LogicalOperatorType::LOGICAL_GET || aggr.expressions.empty()) {
+		return false;
+	}
+	auto &get = aggr.children[0]->Cast<LogicalGet>();
+	shared_ptr<CubitGpuTable> gpu;
+	vector<CubitScanBindData::Range> ranges;
+	if (!CubitPlanGet(get, gpu, ranges)) {
+		return false;
+	}
+	auto bind = make_uniq<CubitAggMultiBindData>();
+	vector<string> names;
+	for (auto &expr : aggr.expressions) {
+		if (expr->expression_class != ExpressionClass::BOUND_AGGREGATE) {
+			return false;
+		}
+		auto &a = expr->Cast<BoundAggregateExpression>();
+		if (a.IsDistinct() || a.filter || a.order_bys) {
+			return false;
+		}
+		CubitAggSpec spec;
+		const auto &fn = a.function.name;
+		const auto phys = a.return_type.InternalType();
+		if (fn == "count_star" && a.children.empty()) {
+			spec.kind = CubitAggSpec::COUNT_STAR;
+		} else if (fn == "count" && a.children.size() == 1) {
+			spec.kind = CubitAggSpec::COUNT_COL;
+			spec.col_a = CubitAggInputColumn(*a.children[0], get, *gpu);
+		} else if ((fn == "sum" || fn == "sum_no_overflow") && a.children.size() == 1 &&
+		           (phys == PhysicalType::INT128 || phys == PhysicalType::INT64) &&
+		           (a.return_type.id() == LogicalTypeId::DECIMAL || a.return_type.id() == LogicalTypeId::HUGEINT ||
+		            a.return_type.id() == LogicalTypeId::BIGINT)) {
+			auto &child = *a.children[0];
+			if (child.expression_class == ExpressionClass::BOUND_FUNCTION && child.Cast<BoundFunctionExpression>().function.name == "*" &&
+			    child.Cast<BoundFunctionExpression>().children.size() == 2 && child.return_type.InternalType() == PhysicalType::INT64) {
+				auto &mul = child.Cast<BoundFunctionExpression>();
+				spec.kind = CubitAggSpec::SUM_PROD; // int64 product, overflow is an error on both sides
+				spec.col_a = CubitAggInputColumn(*mul.children[0], get, *gpu);
+				spec.col_b = CubitAggInputColumn(*mul.children[1], get, *gpu);
+				if (spec.col_b < 0) {
+					return false;
+				}
+			} else {
+				spec.kind = CubitAggSpec::SUM_COL;
+				spec.col_a = CubitAggInputColumn(child, get, *gpu);
+			}
+		} else {
+			if (getenv("CUBIT_DEBUG_REWRITE")) {
+				fprintf(stderr, "cubit aggregate push-down skipped: unsupported aggregate %s -> %s\n", a.ToString().c_str(),
+				        a.return_type.ToString().c_str());
+			}
+			return false;
+		}
+		if (spec.kind != CubitAggSpec::COUNT_STAR && spec.col_a < 0) {
+			if (getenv("CUBIT_DEBUG_REWRITE")) {
+				fprintf(stderr, "cubit aggregate push-down skipped: input of %s is not a GPU-resident INT64 column\n",
+				        a.ToString().c_str());
+			}
+			return false;
+		}
+		bind->specs.push_back(spec);
+		bind->types.push_back(a.return_type);
+		names.push_back(a.ToString());
+	}
+	bind->gpu = gpu;
+	bind->ranges = std::move(ranges);
+	TableFunction fn("cubit_agg_pushdown", {}, CubitAggMultiFunction, nullptr, CubitAggMultiInit);
+	auto types = bind->types;
+	auto replacement = make_uniq<LogicalGet>(aggr.aggregate_index, fn, std::move(bind), types, names);
+	for (idx_t i = 0; i < types.size(); i++) {
+		replacement->column_ids.push_back(i);
+	}
+	op = std::move(replacement);
+	cubit_rewrite_count++;
+	cubit_agg_pushdown_count++;
+	return true;
+}
+
+static void CubitRewritePlan(unique_ptr<LogicalOperator> &op) {
+	if (CubitTryAggregatePushdown(op)) {
+		return;
+	}
+	if (op->type == LogicalOperatorType::LOGICAL_GET) {
+		CubitRewriteGet(op->Cast<LogicalGet>());
+	}
+	for (auto &child : op->children) {
+		CubitRewritePlan(child);
 	}
 }
 
@@ -700,7 +965,19 @@ static void CubitOptimize(OptimizerExtensionInput &, unique_ptr<LogicalOperator>
 	if (CubitInvalidateOnDml(*plan)) {
 		return;
 	}
-	CubitRewritePlan(*plan);
+	if (getenv("CUBIT_NO_AGG_PUSHDOWN")) { // (tests: compare the row-returning scan with the pushed-down aggregate)
+		std::function<void(LogicalOperator &)> walk = [&](LogicalOperator &o) {
+			if (o.type == LogicalOperatorType::LOGICAL_GET) {
+				CubitRewriteGet(o.Cast<LogicalGet>());
+			}
+			for (auto &child : o.children) {
+				walk(*child);
+			}
+		};
+		walk(*plan);
+		return;
+	}
+	CubitRewritePlan(plan);
 }
 
 static TableFunction CubitScanTableFunction() {

@@ -112,6 +112,7 @@ int cubit_gpu_index_build(cubit_gpu_table *t, int32_t index_id, int32_t col_id, 
 	oracle_build_index(t->cols[col_id], 8, t->n_rows, base_value, t->card[index_id], t->bits[index_id], t->n_words);
 	return CUBIT_OK;
 }
+int cubit_gpu_free_result(cubit_gpu_result *r);
 int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_result **out) {
 	const uint64_t *streams[CUBIT_MAX_STREAMS]; int32_t group_of[CUBIT_MAX_STREAMS]; int k = 0;
 	for (uint32_t g = 0; g < q->n_groups; g++)
@@ -138,10 +139,13 @@ int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_result *
 			}
 		}
 	}
-	if (q->agg_kind == CUBIT_AGG_SUM) {
+	if (q->agg_kind == CUBIT_AGG_SUM || q->agg_kind == CUBIT_AGG_SUM_PROD) {
 		int ovf = 0;
-		r->agg_rows = oracle_sum_nulls(r->ids, r->count, t->row_base, t->cols[q->agg_col_a], t->valid[q->agg_col_a], NULL,
-		                               NULL, &r->sum_lo, &r->sum_hi, &ovf);
+		const int prod = q->agg_kind == CUBIT_AGG_SUM_PROD;
+		r->agg_rows = oracle_sum_nulls(r->ids, r->count, t->row_base, t->cols[q->agg_col_a], t->valid[q->agg_col_a],
+		                               prod ? t->cols[q->agg_col_b] : NULL, prod ? t->valid[q->agg_col_b] : NULL,
+		                               &r->sum_lo, &r->sum_hi, &ovf);
+		if (ovf) { snprintf(g_err, sizeof g_err, "Overflow in multiplication of INT64 in SUM(a*b)"); cubit_gpu_free_result(r); return CUBIT_EINVAL; }
 	}
 	*out = r;
 	return CUBIT_OK;

@@ -763,12 +763,28 @@ static void CubitAggMultiFunction(ClientContext &, TableFunctionInput &data_p, D
 		}
 		groups.push_back(cubit_pred_group {NumericCast<uint32_t>(refs[j].size()), refs[j].data()});
 	}
-	// one GPU query per aggregate (merge + bit-driven probe with the fused SUM; a few tens of microseconds each)
+	// one GPU query per aggregate (merge + bit-driven probe with the fused SUM; a few tens of microseconds each);
+	// COUNT(*) rides on any of them (every query reports the selection's row count)
+	bool have_count = false;
+	uint64_t row_count = 0;
+	vector<idx_t> order;
 	for (idx_t a = 0; a < bind.specs.size(); a++) {
+		if (bind.specs[a].kind != CubitAggSpec::COUNT_STAR) {
+			order.push_back(a);
+		}
+	}
+	for (idx_t a = 0; a < bind.specs.size(); a++) {
+		if (bind.specs[a].kind == CubitAggSpec::COUNT_STAR) {
+			order.push_back(a);
+		}
+	}
+	for (auto a : order) {
 		auto &spec = bind.specs[a];
 		cubit_result_info info;
 		memset(&info, 0, sizeof(info));
-		if (!empty) {
+		if (spec.kind == CubitAggSpec::COUNT_STAR && have_count) {
+			info.count = row_count;
+		} else if (!empty) {
 			cubit_query q {};
 			q.n_groups = NumericCast<uint32_t>(groups.size());
 			q.groups = groups.data();
@@ -782,6 +798,8 @@ static void CubitAggMultiFunction(ClientContext &, TableFunctionInput &data_p, D
 			const int rc = cubit_gpu_result_get(res, &info);
 			cubit_gpu_free_result(res);
 			CubitCheck(rc);
+			have_count = true;
+			row_count = info.count;
 		}
 		auto &vec = output.data[a];
 		if (spec.kind == CubitAggSpec::COUNT_STAR || spec.kind == CubitAggSpec::COUNT_COL) {

@@ -22,6 +22,7 @@
 #include "duckdb/function/table_function.hpp"
 #include "duckdb/main/extension_util.hpp"
 #include "duckdb/common/types/data_chunk.hpp"
+#include "duckdb/common/types/date.hpp"
 #include "duckdb/common/types/vector.hpp"
 #include "duckdb/catalog/catalog_entry/table_catalog_entry.hpp"
 #include "duckdb/main/config.hpp"
@@ -60,6 +61,10 @@ struct CubitGpuIndex {
 	int64_t base_value = 0;
 	uint32_t cardinality = 0;
 	idx_t key_table_column = 0; // table column index of the indexed column
+	// binned index (cubit_load(..., bin := 'month' | '<width>')): bitvector b covers the key values in
+	// [bin_lo[b], bin_lo[b + 1]) (cardinality + 1 boundaries); a range predicate is answered by it only when both
+	// of its ends fall on boundaries.  Empty = one bitvector per value.
+	vector<int64_t> bin_lo;
 };
 
 struct CubitGpuTable {
@@ -98,6 +103,7 @@ struct CubitLoadBindData : public TableFunctionData {
 	string table, key;
 	int64_t base = 0;
 	uint32_t cardinality = 0;
+	string bin; // "" = one bitvector per value; "month" (DATE keys); or a positive integer bin width
 	bool done = false;
 };
 
@@ -108,6 +114,10 @@ static unique_ptr<FunctionData> CubitLoadBind(ClientContext &, TableFunctionBind
 	bind->key = input.inputs[1].GetValue<string>();
 	bind->base = input.inputs[2].GetValue<int64_t>();
 	bind->cardinality = NumericCast<uint32_t>(input.inputs[3].GetValue<int64_t>());
+	auto bin = input.named_parameters.find("bin");
+	if (bin != input.named_parameters.end()) {
+		bind->bin = bin->second.GetValue<string>();
+	}
 	return_types.emplace_back(LogicalType::BIGINT);
 	names.emplace_back("rows_indexed");
 	return std::move(bind);
@@ -201,6 +211,98 @@ static bool CubitUploadColumnSegments(ClientContext &context, const string &tabl
 	return true;
 }
 
+// Build one index over GPU column `gcol` of a resident table.  The key values come back from the GPU (the
+// uploaded raw int64, NULL rows = INT64_MIN): every non-NULL key must fall into the indexed domain — a key the
+// index does not cover would silently drop rows from rewritten scans — and binned indexes need the bin id of
+// every row (computed here, uploaded as a temporary column, indexed on the GPU, dropped).
+static CubitGpuIndex CubitBuildIndex(CubitGpuTable &gpu, idx_t gcol, const CubitLoadBindData &bind, const LogicalType &key_type) {
+	CubitGpuIndex ix;
+	ix.key_table_column = gpu.table_column[gcol];
+	vector<int64_t> vals(gpu.row_count);
+	if (gpu.row_count) {
+		CubitCheck(cubit_gpu_download_column(gpu.handle, NumericCast<int32_t>(gcol), vals.data(), 8, gpu.row_count));
+	}
+	const int64_t null_key = NumericLimits<int64_t>::Minimum();
+	if (bind.bin.empty()) {
+		ix.base_value = bind.base;
+		ix.cardinality = bind.cardinality;
+		for (auto v : vals) {
+			if (v != null_key && (v < ix.base_value || v >= ix.base_value + ix.cardinality)) {
+				throw InvalidInputException("cubit_load: key %lld of \"%s\" lies outside the indexed domain [%lld, %lld)",
+				                            (long long)v, bind.key, (long long)ix.base_value,
+				                            (long long)(ix.base_value + ix.cardinality));
+			}
+		}
+		CubitCheck(cubit_gpu_index_create(gpu.handle, ix.cardinality, &ix.index_id));
+		CubitCheck(cubit_gpu_index_build(gpu.handle, ix.index_id, NumericCast<int32_t>(gcol), ix.base_value));
+		return ix;
+	}
+	// ---- binned
+	vector<int64_t> bins(vals.size(), null_key);
+	if (bind.bin == "month") {
+		if (key_type.id() != LogicalTypeId::DATE) {
+			throw InvalidInputException("cubit_load: bin := 'month' needs a DATE key column");
+		}
+		int64_t lo = NumericLimits<int64_t>::Maximum(), hi = NumericLimits<int64_t>::Minimum();
+		for (auto v : vals) {
+			if (v != null_key) {
+				lo = MinValue(lo, v);
+				hi = MaxValue(hi, v);
+			}
+		}
+		if (lo > hi) {
+			lo = hi = 0;
+		}
+		int32_t y0, m0, d0, y1, m1, d1;
+		Date::Convert(date_t(NumericCast<int32_t>(lo)), y0, m0, d0);
+		Date::Convert(date_t(NumericCast<int32_t>(hi)), y1, m1, d1);
+		const int32_t n_bins = (y1 - y0) * 12 + (m1 - m0) + 1;
+		for (int32_t b = 0; b <= n_bins; b++) {
+			const int32_t mm = m0 - 1 + b;
+			ix.bin_lo.push_back(Date::FromDate(y0 + mm / 12, mm % 12 + 1, 1).days);
+		}
+		for (idx_t r = 0; r < vals.size(); r++) {
+			if (vals[r] != null_key) {
+				int32_t y, m, d;
+				Date::Convert(date_t(NumericCast<int32_t>(vals[r])), y, m, d);
+				bins[r] = (y - y0) * 12 + (m - m0);
+			}
+		}
+	} else {
+		int64_t width = 0;
+		try {
+			width = std::stoll(bind.bin);
+		} catch (...) {
+			width = 0;
+		}
+		if (width <= 0 || bind.cardinality == 0) {
+			throw InvalidInputException("cubit_load: bin must be 'month' or a positive integer width (with base and cardinality)");
+		}
+		for (uint32_t b = 0; b <= bind.cardinality; b++) {
+			ix.bin_lo.push_back(bind.base + NumericCast<int64_t>(b) * width);
+		}
+		for (idx_t r = 0; r < vals.size(); r++) {
+			if (vals[r] == null_key) {
+				continue;
+			}
+			if (vals[r] < ix.bin_lo.front() || vals[r] >= ix.bin_lo.back()) {
+				throw InvalidInputException("cubit_load: key %lld of \"%s\" lies outside the binned domain [%lld, %lld)",
+				                            (long long)vals[r], bind.key, (long long)ix.bin_lo.front(), (long long)ix.bin_lo.back());
+			}
+			bins[r] = (vals[r] - bind.base) / width;
+		}
+	}
+	ix.base_value = 0;
+	ix.cardinality = NumericCast<uint32_t>(ix.bin_lo.size() - 1);
+	const int32_t tmp_col = NumericCast<int32_t>(gpu.column_names.size()); // first unused GPU column id
+	CubitCheck(cubit_gpu_upload_column(gpu.handle, tmp_col, bins.data(), 8, gpu.row_count));
+	CubitCheck(cubit_gpu_index_create(gpu.handle, ix.cardinality, &ix.index_id));
+	const int rc = cubit_gpu_index_build(gpu.handle, ix.index_id, tmp_col, 0);
+	cubit_gpu_drop_column(gpu.handle, tmp_col);
+	CubitCheck(rc);
+	return ix;
+}
+
 static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p, DataChunk &output) {
 	auto &bind = data_p.bind_data->CastNoConst<CubitLoadBindData>();
 	if (bind.done) {
@@ -225,12 +327,8 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 				known |= ix.key_table_column == have->table_column[gcol < have->table_column.size() ? gcol : 0];
 			}
 			if (!known) {
-				CubitGpuIndex ix;
-				ix.base_value = bind.base;
-				ix.cardinality = bind.cardinality;
-				ix.key_table_column = have->table_column[gcol];
-				CubitCheck(cubit_gpu_index_create(have->handle, ix.cardinality, &ix.index_id));
-				CubitCheck(cubit_gpu_index_build(have->handle, ix.index_id, NumericCast<int32_t>(gcol), ix.base_value));
+				auto &entry = Catalog::GetEntry<TableCatalogEntry>(context, INVALID_CATALOG, DEFAULT_SCHEMA, bind.table);
+				auto ix = CubitBuildIndex(*have, gcol, bind, entry.GetColumns().GetColumn(LogicalIndex(have->table_column[gcol])).Type());
 				{
 					std::lock_guard<std::mutex> lk(cubit_registry_lock);
 					have->indexes.push_back(ix);
@@ -279,6 +377,10 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 			Vector as_bigint(LogicalType::BIGINT);
 			if (vec.GetType().id() == LogicalTypeId::DECIMAL && vec.GetType().InternalType() == PhysicalType::INT64) {
 				as_bigint.Reinterpret(vec);
+			} else if (vec.GetType().id() == LogicalTypeId::DATE) {
+				Vector as_int(LogicalType::INTEGER); // days since 1970-01-01 (date_t)
+				as_int.Reinterpret(vec);
+				VectorOperations::Cast(context, as_int, as_bigint, chunk.size());
 			} else {
 				VectorOperations::Cast(context, vec, as_bigint, chunk.size());
 			}
@@ -304,10 +406,6 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 		}
 		rows_seen += chunk.size();
 	}
-	CubitGpuIndex first;
-	first.key_table_column = int_cols[key_col];
-	first.base_value = bind.base;
-	first.cardinality = bind.cardinality;
 	gpu->row_count = cols.empty() ? 0 : cols[0].size();
 	CubitCheck(cubit_gpu_create(0, gpu->row_count, 0, 65536, &gpu->handle));
 	for (idx_t k = 0; k < cols.size(); k++) {
@@ -323,9 +421,7 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 			                                            valid[k].size()));
 		}
 	}
-	CubitCheck(cubit_gpu_index_create(gpu->handle, first.cardinality, &first.index_id));
-	CubitCheck(cubit_gpu_index_build(gpu->handle, first.index_id, NumericCast<int32_t>(key_col), first.base_value));
-	gpu->indexes.push_back(first);
+	gpu->indexes.push_back(CubitBuildIndex(*gpu, key_col, bind, res->types[int_cols[key_col]]));
 	{
 		std::lock_guard<std::mutex> lk(cubit_registry_lock);
 		cubit_registry[bind.table] = gpu;
@@ -579,11 +675,12 @@ static bool CubitBoundsFromFilter(const TableFilter &filter, int64_t &lo, int64_
 	}
 	case TableFilterType::CONSTANT_COMPARISON: {
 		auto &cf = filter.Cast<ConstantFilter>();
-		if (!cf.constant.type().IsIntegral() && cf.constant.type().id() != LogicalTypeId::DECIMAL) {
-			return false;
-		}
 		int64_t c;
-		if (!Hugeint::TryCast(IntegralValue::Get(cf.constant), c)) { // raw integer (DECIMAL: unscaled cents)
+		if (cf.constant.type().id() == LogicalTypeId::DATE) {
+			c = cf.constant.GetValue<date_t>().days; // DATE keys are indexed as days since 1970-01-01
+		} else if (!cf.constant.type().IsIntegral() && cf.constant.type().id() != LogicalTypeId::DECIMAL) {
+			return false;
+		} else if (!Hugeint::TryCast(IntegralValue::Get(cf.constant), c)) { // raw integer (DECIMAL: unscaled cents)
 			return false;
 		}
 		switch (cf.comparison_type) {
@@ -658,6 +755,37 @@ static bool CubitPlanGet(LogicalGet &get, shared_ptr<CubitGpuTable> &gpu, vector
 			CUBIT_WHY("unsupported filter shape");
 		}
 		auto &ix = gpu->indexes[slot];
+		if (!ix.bin_lo.empty()) {
+			// binned index: exact only when both ends of the range fall on bin boundaries (every key lies inside
+			// the binned domain — checked at load — so a range that starts before / ends after it is aligned too)
+			int64_t first = 0, last = NumericCast<int64_t>(ix.cardinality) - 1;
+			if (lo > ix.bin_lo.front()) {
+				auto it = std::lower_bound(ix.bin_lo.begin(), ix.bin_lo.end(), lo);
+				if (it == ix.bin_lo.end() || *it != lo) {
+					if (lo >= ix.bin_lo.back()) {
+						first = last + 1; // empty
+					} else {
+						CUBIT_WHY("range start is not a bin boundary of the binned index");
+					}
+				} else {
+					first = it - ix.bin_lo.begin();
+				}
+			}
+			if (hi < ix.bin_lo.back() - 1) {
+				auto it = std::lower_bound(ix.bin_lo.begin(), ix.bin_lo.end(), hi + 1);
+				if (it == ix.bin_lo.end() || *it != hi + 1) {
+					if (hi < ix.bin_lo.front()) {
+						last = -1; // empty
+					} else {
+						CUBIT_WHY("range end is not a bin boundary of the binned index");
+					}
+				} else {
+					last = (it - ix.bin_lo.begin()) - 1;
+				}
+			}
+			lo = first; // ranges are kept in the index's key units: bin ids here
+			hi = last;
+		}
 		const int64_t clo = MaxValue<int64_t>(lo, ix.base_value), chi = MinValue<int64_t>(hi, ix.base_value + ix.cardinality - 1);
 		n_streams += chi >= clo ? NumericCast<idx_t>(chi - clo + 1) : 0;
 		ranges.push_back({slot, lo, hi});
@@ -1010,6 +1138,7 @@ static TableFunction CubitScanTableFunction() {
 void RegisterCubitGpuFunctions(DatabaseInstance &db) {
 	TableFunction load("cubit_load", {LogicalType::VARCHAR, LogicalType::VARCHAR, LogicalType::BIGINT, LogicalType::BIGINT},
 	                   CubitLoadFunction, CubitLoadBind);
+	load.named_parameters["bin"] = LogicalType::VARCHAR;
 	ExtensionUtil::RegisterFunction(db, load);
 
 	ExtensionUtil::RegisterFunction(db, CubitScanTableFunction());

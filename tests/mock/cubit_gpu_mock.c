@@ -65,8 +65,19 @@ int cubit_gpu_destroy(cubit_gpu_table *t) {
 }
 int cubit_gpu_upload_column(cubit_gpu_table *t, int32_t col_id, const void *data, uint32_t elem_bytes, uint64_t n) {
 	if (elem_bytes != 8 || col_id < 0 || col_id >= MAX_COLS || n != t->n_rows) { snprintf(g_err, sizeof g_err, "mock: bad column"); return CUBIT_EINVAL; }
-	t->cols[col_id] = malloc(n * 8);
+	free(t->cols[col_id]);
+	t->cols[col_id] = malloc(n * 8 + 8);
 	memcpy(t->cols[col_id], data, n * 8);
+	return CUBIT_OK;
+}
+int cubit_gpu_download_column(cubit_gpu_table *t, int32_t col_id, void *data, uint32_t elem_bytes, uint64_t n) {
+	if (elem_bytes != 8 || col_id < 0 || col_id >= MAX_COLS || !t->cols[col_id] || n != t->n_rows) { snprintf(g_err, sizeof g_err, "mock: bad column"); return CUBIT_EINVAL; }
+	memcpy(data, t->cols[col_id], n * 8);
+	return CUBIT_OK;
+}
+int cubit_gpu_drop_column(cubit_gpu_table *t, int32_t col_id) {
+	if (col_id < 0 || col_id >= MAX_COLS || !t->cols[col_id]) { snprintf(g_err, sizeof g_err, "mock: bad column"); return CUBIT_EINVAL; }
+	free(t->cols[col_id]); t->cols[col_id] = NULL; free(t->valid[col_id]); t->valid[col_id] = NULL;
 	return CUBIT_OK;
 }
 int cubit_gpu_upload_column_validity(cubit_gpu_table *t, int32_t col_id, const uint64_t *words, uint64_t n_words) {

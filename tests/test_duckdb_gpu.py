@@ -21,7 +21,7 @@ def test_sql_through_reference_duckdb_on_the_gpu(tmp_path):
     r = subprocess.run([os.path.join(REF, "duckdb_sql_gpu_test"), "--db", str(tmp_path / "route.db")],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
-    for marker in ("aggregate push-down ok", "multi-index conjunctions ok", "null semantics ok", "storage route ok", "duckdb_sql_test ok"):
+    for marker in ("aggregate push-down ok", "multi-index conjunctions ok", "binned indexes ok", "null semantics ok", "storage route ok", "duckdb_sql_test ok"):
         assert marker in r.stdout, r.stdout
 
 
@@ -34,3 +34,6 @@ def test_config1_on_reference_tpch_data_small_scale():
     g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["tpch_sf01"]["answers"]["q_eq_24"]
     cnt, total = out["answer_q1"].split("|")
     assert int(cnt) == g["count"] and int(total.replace(".", "")) == g["sum_price_cents"]
+    # TPC-H Q6 as written, answered by the GPU through plain SQL, equals the reference's answer for SF0.1
+    # (extension/tpch/dbgen/answers/sf0.1/q06.csv; also recorded in tests/golden/golden.json)
+    assert out["tpch_q6_as_written"]["answer"] == "11803420.2534"

@@ -131,13 +131,37 @@ def cpu_sweep(rows, steps, warmup, threads):
     return len(SELECTIVITIES) * rows / med, med, checks
 
 
+def duckdb_cpu_sweep(rows, checks):
+    """the REFERENCE's own CPU path (unmodified DuckDB built from /root/reference: seq_scan + pushed-down filter) on
+    the same sample, when the bundle of tools/build_ref_bundle.py travelled with the repo (baseline/_ref/); its
+    answers must equal the oracle's on that sample.  None when the bundle is absent."""
+    import subprocess
+    exe = os.path.join(ROOT, "baseline", "_ref", "duckdb_cfg2_baseline")
+    if not os.path.exists(exe):
+        return None
+    try:
+        r = subprocess.run([exe, str(rows), "3"] + [str(threshold(s)) for s in SELECTIVITIES], stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True, timeout=240)
+        if r.returncode != 0:
+            return {"error": r.stderr.strip()[-200:]}
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:  # the baseline is a report, never a reason to lose the bench line
+        return {"error": str(e)[:200]}
+    if checks is not None:
+        assert [tuple(a) for a in d["answers"]] == [(int(c), int(t)) for c, t in checks], "DuckDB and the oracle disagree"
+    return {"value": d["rows_per_s"], "unit": "rows/s", "cores": d["threads"], "kind": "reference",
+            "sample": "reference DuckDB %s, SELECT count(*), sum(payload) FROM t WHERE v BETWEEN 10 AND 19 per sweep point on "
+                      "%d rows per point, all host threads, median of 3; answers equal the oracle's on the same sample"
+                      % (d["version"], rows)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
     rows = args.cpu_rows
-    value, med, _ = cpu_sweep(rows, args.steps, args.warmup, threads)
+    value, med, checks = cpu_sweep(rows, args.steps, args.warmup, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
@@ -149,6 +173,9 @@ def run_reference(args):
                                    "CUBIT source to run" % (rows, args.rows, threads)},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    duck = duckdb_cpu_sweep(min(rows, 1 << 26), checks if rows <= (1 << 26) else None)
+    if duck is not None:
+        line["reference_duckdb_cpu"] = duck  # the vanilla reference's scan of the same sample, beside the CUBIT-style port
     print(json.dumps(line))
     return 0
 
@@ -411,11 +438,14 @@ def run_b200(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        cv, cmed, _ = cpu_sweep(args.cpu_rows, 3, 1, threads)
+        cv, cmed, checks = cpu_sweep(args.cpu_rows, 3, 1, threads)
         line["cpu_baseline"] = {"value": cv, "unit": "rows/s", "cores": threads, "kind": "port",
                                 "sample": "same 6-point sweep on %d rows per point, %d pthreads, median of 3 "
                                           "(oracle/cubit_oracle.c; no reference CUBIT CPU source exists)"
                                           % (args.cpu_rows, threads)}
+        duck = duckdb_cpu_sweep(min(args.cpu_rows, 1 << 26), checks if args.cpu_rows <= (1 << 26) else None)
+        if duck is not None:
+            line["reference_duckdb_cpu"] = duck
     print(json.dumps(line))
     t.close()
     if world > 1:

@@ -6,6 +6,7 @@ baseline/_ref/ (git-ignored, travels with gpurun):
                         reference's libduckdb.so and the REAL libcubit_gpu.so (on the GPU box: SQL through the
                         optimizer rewrite → CUDA kernels → DataChunks, compared with the vanilla scan)
   duckdb_config1        tests/cpp/duckdb_config1.cpp, config 1 on the reference's own TPC-H data
+  duckdb_cfg2_baseline  tests/cpp/duckdb_cfg2_baseline.cpp: the reference's CPU path on a sample of the bench workload
 Nothing here is product code and no reference SOURCE is copied.  Usage: python tools/build_ref_bundle.py"""
 import os
 import shutil
@@ -41,6 +42,18 @@ def main():
                                    "-lcubit_gpu", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../../duckdb-cubit_b200",
                                    "-lpthread", "-ldl"])
             print("built", dst)
+    # the reference's CPU path on the bench workload (bench.py cpu_baseline / --impl reference): no glue, no GPU
+    # library — libduckdb.so + the oracle's table generator
+    src = os.path.join(ROOT, "tests", "cpp", "duckdb_cfg2_baseline.cpp")
+    dst = os.path.join(OUT, "duckdb_cfg2_baseline")
+    sys.path.insert(0, ROOT)
+    import oracle
+    oracle.build()
+    if stale(dst, [src]):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", REF_INC, src, "-o", dst, "-L", OUT, "-lduckdb",
+                               "-L", os.path.join(ROOT, "oracle"), "-lcubit_oracle", "-Wl,-rpath,$ORIGIN",
+                               "-Wl,-rpath,$ORIGIN/../../oracle", "-lpthread", "-ldl"])
+        print("built", dst)
     return 0
 
 

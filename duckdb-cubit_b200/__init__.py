@@ -38,6 +38,7 @@ ABI_SYMBOLS = [
     "cubit_gpu_result_wait", "cubit_gpu_result_get", "cubit_gpu_fetch", "cubit_gpu_fetch_bitvector",
     "cubit_gpu_free_result", "cubit_gpu_probe", "cubit_gpu_upload_column_validity", "cubit_gpu_fetch_validity",
     "cubit_gpu_index_serialize", "cubit_gpu_index_deserialize", "cubit_gpu_free_image",
+    "cubit_gpu_alloc_host", "cubit_gpu_free_host",
 ]
 
 
@@ -141,6 +142,8 @@ def load_library():
         "cubit_gpu_index_serialize": ([vp, i32, P(vp), P(u64)], C.c_int),
         "cubit_gpu_index_deserialize": ([vp, vp, u64, P(i32)], C.c_int),
         "cubit_gpu_free_image": ([vp], None),
+        "cubit_gpu_alloc_host": ([u64, P(vp)], C.c_int),
+        "cubit_gpu_free_host": ([vp], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)

@@ -2280,6 +2280,29 @@ extern "C" int cubit_gpu_fetch_validity(cubit_gpu_result *r, uint32_t col, uint6
 	return CUBIT_OK;
 }
 
+extern "C" int cubit_gpu_alloc_host(uint64_t bytes, void **ptr) {
+	if (!ptr) {
+		return fail(CUBIT_EINVAL, "NULL argument");
+	}
+	*ptr = nullptr;
+	cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable);
+	if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) {
+		return fail(CUBIT_ENODEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+	}
+	if (e != cudaSuccess) {
+		return fail(e == cudaErrorMemoryAllocation ? CUBIT_ENOMEM : CUBIT_ECUDA, "cudaHostAlloc(%llu): %s",
+		            (unsigned long long)bytes, cudaGetErrorString(e));
+	}
+	return CUBIT_OK;
+}
+
+extern "C" int cubit_gpu_free_host(void *ptr) {
+	if (ptr) {
+		cudaFreeHost(ptr);
+	}
+	return CUBIT_OK;
+}
+
 extern "C" int cubit_gpu_fetch_bitvector(cubit_gpu_result *r, uint64_t *host_words, uint64_t n_words) {
 	if (!r || !host_words) {
 		return fail(CUBIT_EINVAL, "NULL argument");

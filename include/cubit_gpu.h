@@ -280,6 +280,10 @@ int cubit_gpu_fetch(cubit_gpu_result *r, uint64_t offset, uint64_t n, int64_t *h
 int cubit_gpu_fetch_validity(cubit_gpu_result *r, uint32_t col, uint64_t offset, uint64_t n, uint64_t *host_words,
                              int *all_valid);
 int cubit_gpu_fetch_bitvector(cubit_gpu_result *r, uint64_t *host_words, uint64_t n_words);
+/* Page-locked host memory for the buffers cubit_gpu_fetch fills (the staging window behind GetData): a copy
+ * into pageable memory runs at a fraction of the PCIe rate.  Plain malloc'ed buffers keep working. */
+int cubit_gpu_alloc_host(uint64_t bytes, void **ptr);
+int cubit_gpu_free_host(void *ptr);
 int cubit_gpu_free_result(cubit_gpu_result *r);
 
 /* Probe a resident column at caller-supplied sorted row IDs (the

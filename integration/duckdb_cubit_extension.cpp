@@ -74,7 +74,35 @@ struct CubitGpuTable {
 	vector<string> column_names; // uploaded BIGINT columns, column id = position
 	vector<idx_t> table_column;  // table column index of every uploaded column
 	idx_t row_count = 0;
+	// page-locked staging buffers (one DataChunk window each) recycled across scans: allocating and freeing
+	// pinned memory costs milliseconds, far more than a scan
+	std::mutex pool_lock;
+	vector<void *> host_pool;
+	void *AcquireWindow(uint64_t bytes) {
+		{
+			std::lock_guard<std::mutex> lk(pool_lock);
+			if (!host_pool.empty()) {
+				void *p = host_pool.back();
+				host_pool.pop_back();
+				return p;
+			}
+		}
+		void *p = nullptr;
+		if (cubit_gpu_alloc_host(bytes, &p) != CUBIT_OK) {
+			throw InvalidInputException("cubit_gpu: %s", cubit_gpu_last_error());
+		}
+		return p;
+	}
+	void ReleaseWindow(void *p) {
+		if (p) {
+			std::lock_guard<std::mutex> lk(pool_lock);
+			host_pool.push_back(p);
+		}
+	}
 	~CubitGpuTable() {
+		for (auto p : host_pool) {
+			cubit_gpu_free_host(p);
+		}
 		cubit_gpu_destroy(handle);
 	}
 };
@@ -460,11 +488,19 @@ struct CubitScanGlobalState : public GlobalTableFunctionState {
 	// than the whole scan for a few hundred thousand rows)
 	static constexpr idx_t WINDOW_ROWS = 64 * STANDARD_VECTOR_SIZE;
 	idx_t win_begin = 0, win_end = 0;
-	vector<int64_t> win_rowids;
-	vector<vector<int64_t>> win_cols;       // one per projected value column
+	// page-locked, WINDOW_ROWS int64 each, borrowed from the table's pool on first use
+	shared_ptr<CubitGpuTable> pool_owner;
+	int64_t *win_rowids = nullptr;
+	vector<int64_t *> win_cols;             // one per projected value column
 	vector<vector<uint64_t>> win_validity;  // ValidityMask words of the window, empty = no NULL in the window
 	~CubitScanGlobalState() override {
 		cubit_gpu_free_result(result);
+		if (pool_owner) {
+			pool_owner->ReleaseWindow(win_rowids);
+			for (auto p : win_cols) {
+				pool_owner->ReleaseWindow(p);
+			}
+		}
 	}
 	idx_t MaxThreads() const override {
 		return 1; // like index_scan (table_scan.cpp:213-225)
@@ -487,6 +523,7 @@ static unique_ptr<GlobalTableFunctionState> CubitRunQuery(const CubitScanBindDat
                                                           const vector<column_t> &column_ids_p,
                                                           const vector<idx_t> &projection_ids) {
 	auto state = make_uniq<CubitScanGlobalState>();
+	state->pool_owner = bind.gpu;
 	auto &gpu = *bind.gpu;
 	// the columns that actually leave the scan (filter-only columns are pruned: projection_ids)
 	vector<column_t> column_ids;
@@ -569,17 +606,16 @@ static void CubitScanFunction(ClientContext &, TableFunctionInput &data_p, DataC
 			want_rowid |= c == COLUMN_IDENTIFIER_ROW_ID;
 			n_value_cols += c != COLUMN_IDENTIFIER_ROW_ID;
 		}
-		state.win_cols.resize(n_value_cols);
 		state.win_validity.resize(n_value_cols);
-		vector<void *> ptrs;
-		for (auto &col : state.win_cols) {
-			col.resize(n);
-			ptrs.push_back(col.data());
+		const uint64_t win_bytes = CubitScanGlobalState::WINDOW_ROWS * sizeof(int64_t);
+		while (state.win_cols.size() < n_value_cols) {
+			state.win_cols.push_back(static_cast<int64_t *>(state.pool_owner->AcquireWindow(win_bytes)));
 		}
-		if (want_rowid) {
-			state.win_rowids.resize(n);
+		if (want_rowid && !state.win_rowids) {
+			state.win_rowids = static_cast<int64_t *>(state.pool_owner->AcquireWindow(win_bytes));
 		}
-		CubitCheck(cubit_gpu_fetch(state.result, state.win_begin, n, want_rowid ? state.win_rowids.data() : nullptr,
+		vector<void *> ptrs(state.win_cols.begin(), state.win_cols.end());
+		CubitCheck(cubit_gpu_fetch(state.result, state.win_begin, n, want_rowid ? state.win_rowids : nullptr,
 		                           NumericCast<uint32_t>(ptrs.size()), ptrs.data()));
 		// NULLs: the validity mask of every projected value (StandardColumnData::FetchRow = validity + data)
 		for (idx_t c = 0; c < n_value_cols; c++) {
@@ -598,10 +634,10 @@ static void CubitScanFunction(ClientContext &, TableFunctionInput &data_p, DataC
 	for (idx_t i = 0; i < state.column_ids.size(); i++) {
 		auto dst = FlatVector::GetData<int64_t>(output.data[i]);
 		if (state.column_ids[i] == COLUMN_IDENTIFIER_ROW_ID) {
-			memcpy(dst, state.win_rowids.data() + rel, scan_count * sizeof(int64_t));
+			memcpy(dst, state.win_rowids + rel, scan_count * sizeof(int64_t));
 			continue;
 		}
-		memcpy(dst, state.win_cols[value_col].data() + rel, scan_count * sizeof(int64_t));
+		memcpy(dst, state.win_cols[value_col] + rel, scan_count * sizeof(int64_t));
 		auto &words = state.win_validity[value_col];
 		if (!words.empty()) {
 			auto &mask = FlatVector::Validity(output.data[i]);

@@ -186,6 +186,8 @@ int cubit_gpu_fetch_validity(cubit_gpu_result *r, uint32_t col, uint64_t offset,
 	if (all_valid) *all_valid = all;
 	return CUBIT_OK;
 }
+int cubit_gpu_alloc_host(uint64_t bytes, void **ptr) { *ptr = malloc(bytes ? bytes : 1); return *ptr ? CUBIT_OK : CUBIT_ENOMEM; }
+int cubit_gpu_free_host(void *ptr) { free(ptr); return CUBIT_OK; }
 int cubit_gpu_free_result(cubit_gpu_result *r) {
 	if (!r) return CUBIT_OK;
 	free(r->ids);

@@ -67,6 +67,17 @@ def test_argument_validation(cubit):
     assert L.cubit_gpu_create(0, 0, 0, 65536, ctypes.byref(h)) == cubit.EINVAL
     assert L.cubit_gpu_create(0, 10, 7, 65536, ctypes.byref(h)) == cubit.EINVAL
     assert L.cubit_gpu_create(0, 10, 0, 65536, None) == cubit.EINVAL
+    # NULL handles / out-pointers are argument errors on every entry point that can be reached without a device
+    n = ctypes.c_uint64(0)
+    ix = ctypes.c_int32(0)
+    img = ctypes.c_void_p()
+    assert L.cubit_gpu_upload_column_validity(None, 0, None, 0) == cubit.EINVAL
+    assert L.cubit_gpu_fetch_validity(None, 0, 0, 0, None, None) == cubit.EINVAL
+    assert L.cubit_gpu_index_serialize(None, 0, ctypes.byref(img), ctypes.byref(n)) == cubit.EINVAL
+    assert L.cubit_gpu_index_deserialize(None, None, 0, ctypes.byref(ix)) == cubit.EINVAL
+    assert L.cubit_gpu_alloc_host(16, None) == cubit.EINVAL
+    assert L.cubit_gpu_free_host(None) == cubit.OK
+    L.cubit_gpu_free_image(None)
 
 
 def test_product_does_not_import_oracle():

@@ -18,6 +18,10 @@ CubitScanGlobalState::~CubitScanGlobalState() {
 	if (result) {
 		cubit_gpu_free_result(result);
 	}
+	cubit_gpu_free_host(win_rowids);
+	for (auto p : win_cols) {
+		cubit_gpu_free_host(p);
+	}
 }
 
 std::unique_ptr<CubitScanBindData> CubitScanBind(CubitTable &table, std::vector<CubitPredicate> predicates,
@@ -114,19 +118,28 @@ static void FillWindow(CubitScanGlobalState &st) {
 	st.win_end = st.offset + n;
 	bool want_rowid = false;
 	std::vector<void *> ptrs;
-	st.win_cols.resize(st.column_ids.size());
+	st.win_cols.resize(st.column_ids.size(), nullptr);
+	auto pinned = [](void *&p) {
+		if (!p) {
+			Check(cubit_gpu_alloc_host(kWindowRows * 8, &p));
+		}
+	};
 	for (size_t i = 0; i < st.column_ids.size(); i++) {
 		if (st.column_ids[i] == COLUMN_IDENTIFIER_ROW_ID) {
 			want_rowid = true;
 		} else {
-			st.win_cols[i].resize(n * (size_t)st.types[i]);
-			ptrs.push_back(st.win_cols[i].data());
+			void *p = st.win_cols[i];
+			pinned(p);
+			st.win_cols[i] = static_cast<uint8_t *>(p);
+			ptrs.push_back(p);
 		}
 	}
 	if (want_rowid) {
-		st.win_rowids.resize(n);
+		void *p = st.win_rowids;
+		pinned(p);
+		st.win_rowids = static_cast<row_t *>(p);
 	}
-	Check(cubit_gpu_fetch(st.result, st.win_begin, n, want_rowid ? st.win_rowids.data() : nullptr, (uint32_t)ptrs.size(),
+	Check(cubit_gpu_fetch(st.result, st.win_begin, n, want_rowid ? st.win_rowids : nullptr, (uint32_t)ptrs.size(),
 	                      ptrs.data()));
 }
 
@@ -167,10 +180,10 @@ void CubitScanFunction(const CubitScanBindData &bind, CubitScanGlobalState &st, 
 	for (size_t i = 0; i < st.column_ids.size(); i++) {
 		output.data[i].all_valid = true;
 		if (st.column_ids[i] == COLUMN_IDENTIFIER_ROW_ID) {
-			memcpy(output.data[i].Raw(), st.win_rowids.data() + rel, scan_count * sizeof(row_t));
+			memcpy(output.data[i].Raw(), st.win_rowids + rel, scan_count * sizeof(row_t));
 		} else {
 			const size_t w = (size_t)st.types[i];
-			memcpy(output.data[i].Raw(), st.win_cols[i].data() + rel * w, scan_count * w);
+			memcpy(output.data[i].Raw(), st.win_cols[i] + rel * w, scan_count * w);
 			// validity of the probed values (StandardColumnData::FetchRow: validity.FetchRow + data)
 			int all = 1;
 			Check(cubit_gpu_fetch_validity(st.result, value_col++, st.offset, scan_count, output.data[i].validity, &all));

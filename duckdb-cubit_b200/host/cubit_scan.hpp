@@ -46,10 +46,11 @@ struct CubitScanGlobalState { // GlobalTableFunctionState
 	hugeint_t sum;        // aggregate push-down result
 	bool aggregate_done = false;
 	bool finished = false;
-	// host staging window: rows [win_begin, win_end) of the result, fetched in one D2H
+	// host staging window: rows [win_begin, win_end) of the result, fetched in one D2H into page-locked buffers
+	// (cubit_gpu_alloc_host; kWindowRows * 8 bytes each, allocated on first use, freed with the state)
 	idx_t win_begin = 0, win_end = 0;
-	std::vector<row_t> win_rowids;
-	std::vector<std::vector<uint8_t>> win_cols;
+	row_t *win_rowids = nullptr;
+	std::vector<uint8_t *> win_cols; // one slot per column_ids entry (nullptr for the rowid slot)
 };
 
 std::unique_ptr<CubitScanBindData> CubitScanBind(CubitTable &table, std::vector<CubitPredicate> predicates,

@@ -371,27 +371,35 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 	}
 	// Pull the key and every BIGINT-castable column in row order through a second connection
 	// (rows come back in insertion order: physical_result_collector.cpp:21-45).
-	Connection con(*context.db);
-	auto res = con.Query("SELECT * FROM " + KeywordHelper::WriteOptionallyQuoted(bind.table));
-	if (res->HasError()) {
-		throw InvalidInputException("cubit_load: %s", res->GetError());
-	}
+	// (only the columns the GPU can hold are selected: integral, DECIMAL and DATE ones)
 	auto gpu = make_shared_ptr<CubitGpuTable>();
-	vector<idx_t> int_cols;
+	vector<idx_t> int_cols; // result column of every uploaded column (= its position in the select list)
+	vector<LogicalType> col_types;
 	idx_t key_col = DConstants::INVALID_INDEX;
-	for (idx_t c = 0; c < res->ColumnCount(); c++) {
-		auto &t = res->types[c];
-		if (t.IsIntegral() || t.id() == LogicalTypeId::DECIMAL || t.id() == LogicalTypeId::DATE) {
-			if (res->names[c] == bind.key) {
-				key_col = int_cols.size();
+	string select_list;
+	{
+		auto &entry = Catalog::GetEntry<TableCatalogEntry>(context, INVALID_CATALOG, DEFAULT_SCHEMA, bind.table);
+		for (auto &col : entry.GetColumns().Logical()) {
+			auto &t = col.Type();
+			if (t.IsIntegral() || t.id() == LogicalTypeId::DECIMAL || t.id() == LogicalTypeId::DATE) {
+				if (col.Name() == bind.key) {
+					key_col = int_cols.size();
+				}
+				select_list += (select_list.empty() ? "" : ", ") + KeywordHelper::WriteOptionallyQuoted(col.Name());
+				int_cols.push_back(int_cols.size());
+				col_types.push_back(t);
+				gpu->column_names.push_back(col.Name());
+				gpu->table_column.push_back(col.Logical().index);
 			}
-			int_cols.push_back(c);
-			gpu->column_names.push_back(res->names[c]);
-			gpu->table_column.push_back(c);
 		}
 	}
 	if (key_col == DConstants::INVALID_INDEX) {
 		throw InvalidInputException("cubit_load: key column \"%s\" not found or not integral", bind.key);
+	}
+	Connection con(*context.db);
+	auto res = con.Query("SELECT " + select_list + " FROM " + KeywordHelper::WriteOptionallyQuoted(bind.table));
+	if (res->HasError()) {
+		throw InvalidInputException("cubit_load: %s", res->GetError());
 	}
 	vector<vector<int64_t>> cols(int_cols.size());
 	// NULLs: one validity mask per column in the reference's own layout (ValidityMask words), built only for
@@ -440,7 +448,7 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 		// compressed segments straight from the buffer manager when the column qualifies, decoded rows otherwise
 		// (a column with NULLs goes the decoded way: its NULL rows must carry an out-of-domain value)
 		const bool null_keys = !valid[k].empty();
-		if (null_keys || !CubitUploadColumnSegments(context, bind.table, int_cols[k], res->types[int_cols[k]],
+		if (null_keys || !CubitUploadColumnSegments(context, bind.table, gpu->table_column[k], col_types[k],
 		                                            gpu->handle, NumericCast<int32_t>(k), gpu->row_count)) {
 			CubitCheck(cubit_gpu_upload_column(gpu->handle, NumericCast<int32_t>(k), cols[k].data(), 8, gpu->row_count));
 		}
@@ -449,7 +457,7 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 			                                            valid[k].size()));
 		}
 	}
-	gpu->indexes.push_back(CubitBuildIndex(*gpu, key_col, bind, res->types[int_cols[key_col]]));
+	gpu->indexes.push_back(CubitBuildIndex(*gpu, key_col, bind, col_types[key_col]));
 	{
 		std::lock_guard<std::mutex> lk(cubit_registry_lock);
 		cubit_registry[bind.table] = gpu;

@@ -12,8 +12,10 @@
 //
 // Shape of the kernel (B200-first, HBM-bound integer work, no tensor cores):
 //   * TWO persistent CTAs per SM (8 consumer warps + 1 producer warp + 1 prefix
-//     warp each); segments are handed out by a ticket counter, so every
-//     predecessor of a segment is already owned by a running CTA.
+//     warp each); segments are handed out by a ticket counter, ONE segment per
+//     ticket, so segments are merged in roughly global order (the look-back relies
+//     on it) and every predecessor of a segment is already owned by a running CTA.
+//     Tickets are drawn 2..8 segments ahead so the atomic never gates a copy.
 //   * the producer warp streams whole segments of every queried bitvector with
 //     1-D bulk async copies (cp.async.bulk → SASS UBLKCP, the TMA engine) into a
 //     72 KiB shared-memory ring guarded by mbarriers; it runs ahead of the
@@ -23,23 +25,28 @@
 //     mbarrier round trip is paid once per four streams, not once per stream.
 //   * consumer warps: apply the (sparse) pending-delta words of the staged
 //     segment (XOR), fold the segment into registers (OR within a group, AND
-//     across groups) with conflict-free ld.shared.
-//   * decode: __popcll, warp __shfl_up scan, block scan over 16 warp totals; the
+//     across groups; a single OR group — the common range predicate — has its own
+//     leaner fold) with conflict-free ld.shared.
+//   * decode: __popcll, warp redux, block scan over the 8 warp totals; the
 //     segment's aggregate is published at once.  The inter-segment prefix is a
 //     single-pass decoupled look-back done by the PREFIX WARP, asynchronously (it
 //     sums the published aggregates between this CTA's previous segment and the
-//     new one — no chains through other CTAs' look-backs):
-//     consumers hand it (segment, count) through shared memory + mbarrier and
-//     pick the answer up two segments later (the emission of a segment is
-//     deferred behind the merge of the next two), so neither the look-back's L2
-//     round trips nor its waits are ever on the consumers' critical path and no
-//     CTA publishes an aggregate late because it is waiting for somebody else.
-//   * emit: every warp compacts the set bits of 2048 consecutive rows into a
-//     private shared-memory staging buffer (16-bit local row numbers; each lane
-//     walks the two 32-bit halves of its word as two independent ctz chains, no
-//     atomics) and then writes row IDs (and gathers/stores column values,
-//     accumulates SUMs) in position order: four consecutive results per lane,
-//     128-bit stores aligned to the 32-byte sector.
+//     new one — no chains through other CTAs' look-backs): consumers hand it
+//     (segment, count) through shared memory + mbarrier and pick the answer up two
+//     segments later.  The prefix warp serves a request one segment-time after it
+//     was posted (when the next request arrives): by then the predecessors have
+//     published and ONE round of status loads suffices — polling for them at once
+//     cost the bulk-copy stream 12-15 % in L2 traffic.
+//   * emit: the oldest pending segment is written out WHILE the current one is
+//     merged (one emission step after every batch of ring stages, the rest after
+//     the current aggregate is published), so the ring keeps draining.  Every warp
+//     compacts the set bits of 2048 consecutive rows (or its whole 8192-row span
+//     when sparse) into a private shared-memory staging buffer (16-bit local row
+//     numbers; each lane walks the two 32-bit halves of its word as two
+//     independent ctz chains with predicated stores, no atomics) and then writes
+//     row IDs (and gathers/stores column values, accumulates SUMs) in position
+//     order: 128 consecutive results per iteration as two contiguous 512-byte
+//     stores.
 #include "scan_common.cuh"
 
 namespace cubit {

@@ -444,6 +444,13 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 			}
 		}
 		const bool finished = draining || tile == kNoTile;
+		if (!need_emit) { // count / bitvector only: nothing is ever pending, skip the queue's register traffic
+			if (finished) {
+				break;
+			}
+			it++;
+			continue;
+		}
 
 		// shift the queue
 		bool any_pending = false;

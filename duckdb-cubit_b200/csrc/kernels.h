@@ -91,6 +91,7 @@ struct ScanArgs {
 	uint64_t group_end;                 // bit i: stream i closes its OR group (then Q &= group)
 	uint32_t k;                         // streams
 	uint32_t n_seg;                     // segments (tiles)
+	uint32_t ticket_depth;              // segment tickets a CTA keeps in flight (set by launch_scan)
 	int64_t row_base;                   // global row ID of local row 0
 	unsigned long long *ctrl;           // control block (see above)
 	uint64_t *q_out;                    // merged bitvector out, or nullptr

@@ -116,21 +116,20 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 		// fetch the delta CSR offsets of the NEXT segment (its ticket is known one segment ahead)
 		// while lane 0 is busy, so those dependent loads never sit in front of a bulk copy.
 		// Tickets (one segment each, so segments are merged in roughly global order, which the look-back
-		// relies on) are drawn kTicketDepth segments ahead, each into its OWN register (the loop below is
-		// unrolled by the depth): the scoreboard tracks registers per warp, so re-using one register for the
-		// ticket in flight and the ticket being consumed — even from different lanes — makes every segment
-		// wait for a full atomic round trip to L2 (≈ 1 µs).
+		// relies on) are drawn `a.ticket_depth` segments ahead: lane j of this warp holds the ticket of
+		// iteration i ≡ j (mod depth) and re-draws right after it was consumed, so the atomic's round trip
+		// to L2 (≈ 1 µs under load) overlaps `depth` segments of bulk copies instead of gating each one —
+		// with few bitvectors per query a segment is only one or two 8 KiB copies.
 		uint32_t stage = 0, phase = 0;
-		// the first rounds are assigned statically (round j: segment j·grid + CTA) — drawing them with
-		// consecutive atomics would hand each CTA kTicketDepth CONSECUTIVE segments, which serialises the
-		// look-back; the counter then continues from kTicketDepth·grid
-		const uint32_t tbase = (uint32_t)kTicketDepth * gridDim.x;
-		uint32_t tk[kTicketDepth];
-#pragma unroll
-		for (int j = 0; j < kTicketDepth; j++) {
-			tk[j] = (uint32_t)j * gridDim.x + blockIdx.x;
-		}
-		uint32_t dlo[2] = {0, 0}, dhi[2] = {0, 0}; // CSR offsets of streams lane and lane+32 for the current tile
+		const uint32_t td = a.ticket_depth; // 2..8
+		// the first `depth` rounds are assigned statically (round j: segment j·grid + CTA) — drawing them
+		// with one warp-wide atomic would hand each CTA `depth` CONSECUTIVE segments, which serialises the
+		// look-back; the counter then continues from depth·grid
+		const uint32_t tbase = td * gridDim.x;
+		uint32_t my_ticket = (uint32_t)lane * gridDim.x + blockIdx.x;
+		uint32_t tslot = 0; // lane holding the current iteration's ticket
+		uint32_t tile = __shfl_sync(0xffffffffu, my_ticket, 0);
+		uint32_t dlo[2] = {0, 0}, dhi[2] = {0, 0}; // CSR offsets of streams lane and lane+32 for `tile`
 		auto load_offsets = [&](uint32_t tl) {
 #pragma unroll
 			for (int h = 0; h < 2; h++) {
@@ -143,19 +142,15 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 			}
 		};
 		if (HAS_DELTA) {
-			load_offsets(tk[0]);
+			load_offsets(tile);
 		}
-		uint32_t tadd = 0; // 0 while the static rounds are consumed, tbase once tk[] holds raw counter values
 		while (true) {
-#pragma unroll
-		for (int j = 0; j < kTicketDepth; j++) {
-			// (the counter value is used as it comes back: adding tbase right after the atomic would wait for it)
-			const uint32_t tile = __shfl_sync(0xffffffffu, tk[j], 0) + tadd; // drawn kTicketDepth steps ago
 			const bool valid = tile < a.n_seg;
-			uint32_t next = kNoTile;
-			if (HAS_DELTA) { // drawn kTicketDepth - 1 steps ago
-				next = __shfl_sync(0xffffffffu, tk[(j + 1) % kTicketDepth], 0) + (j + 1 == kTicketDepth ? tbase : tadd);
+			if (valid && lane == (int)tslot) {
+				my_ticket = tbase + atomicAdd(ticket, 1u); // consumed `depth` iterations from now
 			}
+			tslot = tslot + 1 == td ? 0 : tslot + 1;
+			const uint32_t next = __shfl_sync(0xffffffffu, my_ticket, tslot); // drawn depth-1 iterations ago
 			if (HAS_DELTA) {
 #pragma unroll
 				for (int h = 0; h < 2; h++) {
@@ -207,11 +202,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 			if (!valid) {
 				return;
 			}
-			if (lane == 0) {
-				tk[j] = atomicAdd(ticket, 1u); // consumed kTicketDepth steps from now
-			}
-		}
-			tadd = tbase;
+			tile = next;
 		}
 	}
 
@@ -453,13 +444,6 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 			}
 		}
 		const bool finished = draining || tile == kNoTile;
-		if (!need_emit) { // count / bitvector only: nothing is ever pending, skip the queue's register traffic
-			if (finished) {
-				break;
-			}
-			it++;
-			continue;
-		}
 
 		// shift the queue
 		bool any_pending = false;
@@ -679,7 +663,11 @@ static cudaError_t launch_scan_g(const ScanArgs &args, int sm_count, cudaStream_
 	if (grid_out) {
 		*grid_out = (int)grid;
 	}
-	kern<<<(unsigned)grid, kScanThreads, smem, stream>>>(args);
+	// tickets in flight per CTA: ≈ 16 bulk copies' worth, 2..8 (see the producer warp)
+	ScanArgs largs = args;
+	const uint32_t td = 16u / (args.k ? args.k : 1u);
+	largs.ticket_depth = td < 2u ? 2u : (td > 8u ? 8u : td);
+	kern<<<(unsigned)grid, kScanThreads, smem, stream>>>(largs);
 	return cudaGetLastError();
 }
 

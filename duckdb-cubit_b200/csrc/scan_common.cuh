@@ -57,6 +57,27 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, 
 		__nanosleep(ns);
 	}
 }
+// shared-window addresses computed ONCE per thread (the generic → shared conversion of a dynamic shared-memory
+// pointer costs an S2R + LEA every time the compiler re-derives it)
+__device__ __forceinline__ void mbar_wait_u32(uint32_t addr, uint32_t parity) {
+	uint32_t done;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\t"
+		             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		             "selp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(done)
+		             : "r"(addr), "r"(parity)
+		             : "memory");
+	} while (!done);
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t addr) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ uint64_t lds64(uint32_t addr) {
+	uint64_t v;
+	asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+	return v;
+}
 // 1-D bulk async copy global → shared, completion on an mbarrier (TMA engine; SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -104,6 +125,9 @@ __device__ __forceinline__ void add128(unsigned long long &lo, long long &hi, un
 
 #ifndef CUBIT_PREFIX_DELAY_NS
 #define CUBIT_PREFIX_DELAY_NS 0
+#endif
+#ifndef CUBIT_SMEM_ADDR
+#define CUBIT_SMEM_ADDR 1
 #endif
 #ifndef CUBIT_STAGE_ASM
 #define CUBIT_STAGE_ASM 1

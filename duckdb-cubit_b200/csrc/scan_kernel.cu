@@ -270,6 +270,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 	bool have_p[kDefer] = {};
 	const uint32_t n_batches = (a.k + (uint32_t)UB - 1) / (uint32_t)UB;
 	bool draining = false; // input exhausted: only pending segments are left
+#if CUBIT_SMEM_ADDR
+	const uint32_t full0 = smem_u32(&sm.full[0]), empty0 = smem_u32(&sm.empty[0]);
+	const uint32_t stage0 = smem_u32(&sm.stage[0][0]) + (uint32_t)(warp * kSpanWords + lane) * 8u;
+#endif
 
 	while (true) {
 		uint64_t q[WPT], g[WPT];
@@ -296,7 +300,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 						st -= kStages;
 						ph ^= 1;
 					}
+#if CUBIT_SMEM_ADDR
+					mbar_wait_u32(full0 + st * 8u, ph);
+#else
 					mbar_wait(&sm.full[st], ph);
+#endif
 				}
 				__syncwarp();
 				if (s == 0) {
@@ -335,18 +343,25 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 						if (u < (int)nb) {
 							uint32_t st = stage + (uint32_t)u;
 							st = st >= (uint32_t)kStages ? st - (uint32_t)kStages : st;
+#if CUBIT_SMEM_ADDR
+							const uint32_t src = stage0 + st * (uint32_t)kTileBytes;
+#define CUBIT_LD(i) lds64(src + (uint32_t)(i) * 256u)
+#else
 							const uint64_t *src = &sm.stage[st][warp * kSpanWords];
+#define CUBIT_LD(i) src[(i) * 32 + lane]
+#endif
 							if (ONEG) {
 #pragma unroll
 								for (int i = 0; i < WPT; i++) {
-									q[i] |= src[i * 32 + lane];
+									q[i] |= CUBIT_LD(i);
 								}
 								continue;
 							}
 #pragma unroll
 							for (int i = 0; i < WPT; i++) {
-								g[i] |= src[i * 32 + lane];
+								g[i] |= CUBIT_LD(i);
 							}
+#undef CUBIT_LD
 							if ((a.group_end >> (s + u)) & 1ull) {
 #pragma unroll
 								for (int i = 0; i < WPT; i++) {
@@ -361,7 +376,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 				if (lane < (int)nb) {
 					uint32_t st = stage + (uint32_t)lane;
 					st = st >= (uint32_t)kStages ? st - (uint32_t)kStages : st;
+#if CUBIT_SMEM_ADDR
+					mbar_arrive_u32(empty0 + st * 8u);
+#else
 					mbar_arrive(&sm.empty[st]);
+#endif
 				}
 				stage += nb;
 				if (stage >= kStages) {

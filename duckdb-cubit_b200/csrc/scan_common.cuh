@@ -151,7 +151,10 @@ constexpr int kDefer = CUBIT_DEFER;        // segments merged between a segment'
 #endif
 constexpr int kPrefixLag = CUBIT_PREFIX_LAG; // requests posted after request n before the prefix warp serves n
 static_assert(kPrefixLag >= 0 && kPrefixLag < kDefer && kReqSlots > kDefer, "look-back pipeline depth");
-constexpr int kWaitBatch = 4;      // ring stages consumed per mbarrier round trip
+#ifndef CUBIT_WAIT_BATCH
+#define CUBIT_WAIT_BATCH 4
+#endif
+constexpr int kWaitBatch = CUBIT_WAIT_BATCH; // ring stages consumed per mbarrier round trip
 constexpr int kDeltaStage = 32;    // delta words staged in shared memory per ring stage (the rest is read from L2)
 constexpr int kSlotRows = 32 * 64; // rows one warp compacts at a time (32 lanes × one 64-bit word)
 // per-warp staging buffer (uint16 units): [0, kSlotRows + 8) row numbers, + 32 per-lane dummy slots, then the

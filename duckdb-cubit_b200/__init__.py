@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("CUBIT_GPU_LIB") or os.path.join(_HERE, "libcubit_gpu.
 HOST_LIB_PATH = os.path.join(_HERE, "libcubit_host.so")
 
 # ---- mirror of include/cubit_gpu.h -------------------------------------------------
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5
 MAX_STREAMS = 64
 MAX_PROBE_COLS = 8
@@ -39,6 +39,9 @@ ABI_SYMBOLS = [
     "cubit_gpu_free_result", "cubit_gpu_probe", "cubit_gpu_upload_column_validity", "cubit_gpu_fetch_validity",
     "cubit_gpu_index_serialize", "cubit_gpu_index_deserialize", "cubit_gpu_free_image",
     "cubit_gpu_alloc_host", "cubit_gpu_free_host",
+    "cubit_gpu_create_sharded", "cubit_gpu_shard_count", "cubit_gpu_shard_info", "cubit_gpu_row_count",
+    "cubit_gpu_index_create_compressed", "cubit_gpu_index_info", "cubit_gpu_add_delta", "cubit_gpu_add_delta_pairs",
+    "cubit_gpu_set_merge_threshold", "cubit_gpu_fetch_async", "cubit_gpu_fetch_wait", "cubit_gpu_result_add_limbs",
 ]
 
 
@@ -76,6 +79,11 @@ class WahBitvector(C.Structure):
 
 class AppendColumn(C.Structure):
     _fields_ = [("col_id", C.c_int32), ("elem_bytes", C.c_uint32), ("data", C.c_void_p)]
+
+
+class IndexInfo(C.Structure):
+    _fields_ = [("cardinality", C.c_uint32), ("compressed", C.c_uint32), ("resident_bytes", C.c_uint64),
+                ("verbatim_bytes", C.c_uint64), ("delta_entries", C.c_uint64), ("auto_merges", C.c_uint64)]
 
 
 class DecodeInfo(C.Structure):
@@ -144,6 +152,18 @@ def load_library():
         "cubit_gpu_free_image": ([vp], None),
         "cubit_gpu_alloc_host": ([u64, P(vp)], C.c_int),
         "cubit_gpu_free_host": ([vp], C.c_int),
+        "cubit_gpu_create_sharded": ([P(C.c_int), u32, u64, i64, u32, P(vp)], C.c_int),
+        "cubit_gpu_shard_count": ([vp, P(u32)], C.c_int),
+        "cubit_gpu_shard_info": ([vp, u32, P(C.c_int), P(u64), P(u64)], C.c_int),
+        "cubit_gpu_row_count": ([vp, P(u64)], C.c_int),
+        "cubit_gpu_index_create_compressed": ([vp, u32, P(i32)], C.c_int),
+        "cubit_gpu_index_info": ([vp, i32, P(IndexInfo)], C.c_int),
+        "cubit_gpu_add_delta": ([vp, i32, u32, vp, u64], C.c_int),
+        "cubit_gpu_add_delta_pairs": ([vp, i32, vp, vp, u64], C.c_int),
+        "cubit_gpu_set_merge_threshold": ([vp, i32, C.c_double], C.c_int),
+        "cubit_gpu_fetch_async": ([vp, u64, u64, vp, u32, P(vp), P(vp)], C.c_int),
+        "cubit_gpu_fetch_wait": ([vp], C.c_int),
+        "cubit_gpu_result_add_limbs": ([vp, vp], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -235,6 +255,23 @@ class Result:
                                           len(self._dtypes), ptrs))
         return ids, cols
 
+    def fetch_async(self, offset, n, out_ids=None, out_cols=()):
+        """enqueue the copy of result rows [offset, offset+n) into (page-locked) arrays → ticket for fetch_wait"""
+        ptrs = (C.c_void_p * max(1, len(out_cols)))()
+        for c, a in enumerate(out_cols):
+            ptrs[c] = a.ctypes.data
+        tk = C.c_void_p()
+        _check(self._t._L.cubit_gpu_fetch_async(self._h, offset, n, out_ids.ctypes.data if out_ids is not None else None,
+                                                len(out_cols), ptrs, C.byref(tk)))
+        return tk
+
+    def fetch_wait(self, ticket):
+        _check(self._t._L.cubit_gpu_fetch_wait(ticket))
+
+    def add_limbs(self, device_ptr):
+        """ADD (count, 128-bit sum) as five int64 limbs to device memory, in stream order (multi-process reduce)"""
+        _check(self._t._L.cubit_gpu_result_add_limbs(self._h, C.c_void_p(device_ptr)))
+
     def fetch_validity(self, col, offset=0, n=None):
         """→ (uint64 mask words with bit j = result row offset+j valid, all_valid) for projected column `col`"""
         if n is None:
@@ -274,10 +311,15 @@ class Result:
 class CubitTable:
     """One table shard resident on one B200 (cubit_gpu_table)."""
 
-    def __init__(self, n_rows, row_base=0, seg_bits=65536, device=0):
+    def __init__(self, n_rows, row_base=0, seg_bits=65536, device=0, devices=None):
+        """devices=[d0, d1, ...]: one table sharded by row range over those GPUs (cubit_gpu_create_sharded)"""
         self._L = load_library()
         h = C.c_void_p()
-        _check(self._L.cubit_gpu_create(device, n_rows, row_base, seg_bits, C.byref(h)))
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            _check(self._L.cubit_gpu_create_sharded(arr, len(devices), n_rows, row_base, seg_bits, C.byref(h)))
+        else:
+            _check(self._L.cubit_gpu_create(device, n_rows, row_base, seg_bits, C.byref(h)))
         self._h = h
         self.n_rows, self.row_base, self.seg_bits, self.device = n_rows, row_base, seg_bits, device
         self.n_words = (n_rows + 63) // 64
@@ -310,10 +352,28 @@ class CubitTable:
         return n.value
 
     # ---- index
-    def create_index(self, cardinality):
+    def create_index(self, cardinality, compressed=False):
+        """compressed=True: roaring-style containers in HBM (cubit_gpu_index_create_compressed)"""
         ix = C.c_int32(-1)
-        _check(self._L.cubit_gpu_index_create(self._h, cardinality, C.byref(ix)))
+        fn = self._L.cubit_gpu_index_create_compressed if compressed else self._L.cubit_gpu_index_create
+        _check(fn(self._h, cardinality, C.byref(ix)))
         return ix.value
+
+    def index_info(self, index_id):
+        info = IndexInfo()
+        _check(self._L.cubit_gpu_index_info(self._h, index_id, C.byref(info)))
+        return info
+
+    @property
+    def shard_count(self):
+        n = C.c_uint32(0)
+        _check(self._L.cubit_gpu_shard_count(self._h, C.byref(n)))
+        return n.value
+
+    def shard_info(self, shard):
+        dev, r0, n = C.c_int(0), C.c_uint64(0), C.c_uint64(0)
+        _check(self._L.cubit_gpu_shard_info(self._h, shard, C.byref(dev), C.byref(r0), C.byref(n)))
+        return dev.value, r0.value, n.value
 
     def upload_bitvector(self, index_id, value_id, words):
         words = np.ascontiguousarray(words, dtype=np.uint64)
@@ -325,9 +385,9 @@ class CubitTable:
         bv = WahBitvector(w.ctypes.data if len(w) else None, len(w), active_val, active_nbits)
         _check(self._L.cubit_gpu_upload_bitvector_wah(self._h, index_id, value_id, C.byref(bv)))
 
-    def upload_index(self, bitvectors):
+    def upload_index(self, bitvectors, compressed=False):
         """bitvectors: [card, n_words] uint64 → new index id"""
-        ix = self.create_index(len(bitvectors))
+        ix = self.create_index(len(bitvectors), compressed)
         for v, w in enumerate(bitvectors):
             self.upload_bitvector(ix, v, w)
         return ix
@@ -365,6 +425,23 @@ class CubitTable:
         rows = np.ascontiguousarray(rows, dtype=np.int64)
         _check(self._L.cubit_gpu_set_delta(self._h, index_id, value_id, rows.ctypes.data if len(rows) else None,
                                            len(rows)))
+
+    def add_delta(self, index_id, value_id, rows):
+        """incremental: the rows join the pending delta of (index, value); ingested on the device"""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        _check(self._L.cubit_gpu_add_delta(self._h, index_id, value_id, rows.ctypes.data if len(rows) else None,
+                                           len(rows)))
+
+    def add_delta_pairs(self, index_id, value_ids, rows):
+        """incremental: (value, row) pairs — what one UPDATE / DELETE statement produces"""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        vals = np.ascontiguousarray(value_ids, dtype=np.uint32)
+        assert len(rows) == len(vals)
+        _check(self._L.cubit_gpu_add_delta_pairs(self._h, index_id, vals.ctypes.data if len(rows) else None,
+                                                 rows.ctypes.data if len(rows) else None, len(rows)))
+
+    def set_merge_threshold(self, index_id, fraction):
+        _check(self._L.cubit_gpu_set_merge_threshold(self._h, index_id, float(fraction)))
 
     def merge_deltas(self, index_id):
         _check(self._L.cubit_gpu_merge_deltas(self._h, index_id))

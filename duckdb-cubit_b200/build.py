@@ -45,8 +45,11 @@ def _run(cmd, verbose):
 
 def build_gpu(verbose=False, ptxas_info=False):
     os.makedirs(OBJ, exist_ok=True)
-    hdrs = [os.path.join(CSRC, "kernels.h"), os.path.join(CSRC, "scan_common.cuh"), os.path.join(CSRC, "col_ref.cuh"), os.path.join(ROOT, "include", "cubit_gpu.h")]
-    units = ["scan_kernel.cu", "aux_kernels.cu", "column_decode.cu", "wah_decode.cu", "cubit_gpu.cu"]
+    hdrs = [os.path.join(CSRC, "kernels.h"), os.path.join(CSRC, "scan_common.cuh"), os.path.join(CSRC, "col_ref.cuh"),
+            os.path.join(CSRC, "table.h"), os.path.join(ROOT, "include", "cubit_gpu.h")]
+    units = ["scan_kernel.cu", "aux_kernels.cu", "column_decode.cu", "wah_decode.cu", "delta_kernels.cu",
+             "container_kernels.cu", "cubit_gpu.cu", "cubit_columns.cu", "cubit_delta.cu", "cubit_persist.cu",
+             "cubit_query.cu", "cubit_sharded.cu"]
     objs = []
     jobs = []
     for u in units:
@@ -56,7 +59,7 @@ def build_gpu(verbose=False, ptxas_info=False):
         if _stale(obj, [src] + hdrs):
             cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", src, "-o", obj]
             jobs.append(cmd)
-    with ThreadPoolExecutor(max_workers=4) as ex:
+    with ThreadPoolExecutor(max_workers=8) as ex:
         outs = list(ex.map(lambda c: _run(c, verbose), jobs))
     lib = os.path.join(HERE, "libcubit_gpu.so")
     if jobs or _stale(lib, objs):

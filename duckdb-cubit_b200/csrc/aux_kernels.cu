@@ -241,8 +241,9 @@ constexpr int kBuildSlots = kBuildRows / 32; // u32 slots per value per tile
 
 template <typename T>
 __global__ void __launch_bounds__(kBuildThreads)
-    cubit_index_build_kernel(const T *__restrict__ col, uint64_t row_begin, uint64_t n_rows, int64_t base_value,
-                             uint32_t v_lo, uint32_t v_n, uint64_t *__restrict__ bitvectors, uint64_t words_per_bv) {
+    cubit_index_build_kernel(const T *__restrict__ col, const unsigned long long *__restrict__ valid, uint64_t row_begin,
+                             uint64_t n_rows, int64_t base_value, uint32_t v_lo, uint32_t v_n,
+                             uint64_t *__restrict__ bitvectors, uint64_t words_per_bv) {
 	extern __shared__ uint32_t tile[]; // [v_n][kBuildSlots]
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint64_t n_tiles = (n_rows + kBuildRows - 1) / kBuildRows;
@@ -257,6 +258,12 @@ __global__ void __launch_bounds__(kBuildThreads)
 		for (int it = 0; it < kIters; it++) {
 			const uint64_t r = row0 + (uint64_t)(it * (kBuildThreads / 32) + warp) * 32 + lane;
 			rel[it] = (r >= row_begin && r < n_rows) ? (long long)__ldcs(col + r) - base_value - (long long)v_lo : -1;
+			if (valid && r < n_rows) { // NULL keys are not indexed: one 32-bit slice of the validity mask per warp
+				const uint32_t vm = __ldg(reinterpret_cast<const uint32_t *>(valid) + (r >> 5)); // r >> 5 is warp-uniform
+				if (!((vm >> (r & 31u)) & 1u)) {
+					rel[it] = -1;
+				}
+			}
 		}
 		for (uint32_t i = threadIdx.x; i < v_n * (kBuildSlots / 4); i += kBuildThreads) {
 			reinterpret_cast<uint4 *>(tile)[i] = make_uint4(0, 0, 0, 0);
@@ -299,8 +306,8 @@ __global__ void __launch_bounds__(kBuildThreads)
 	}
 }
 
-cudaError_t launch_index_build(const void *col, uint32_t elem_bytes, uint64_t row_begin, uint64_t n_rows,
-                               int64_t base_value,
+cudaError_t launch_index_build(const void *col, uint32_t elem_bytes, const unsigned long long *valid, uint64_t row_begin,
+                               uint64_t n_rows, int64_t base_value,
                                uint32_t cardinality, uint64_t *bitvectors, uint64_t words_per_bv, int sm_count,
                                cudaStream_t stream, int *n_launches) {
 	// values per pass bounded by shared memory (≤ 200 KiB tile)
@@ -336,10 +343,10 @@ cudaError_t launch_index_build(const void *col, uint32_t elem_bytes, uint64_t ro
 		}
 		if (elem_bytes == 4) {
 			cubit_index_build_kernel<int><<<(unsigned)grid, kBuildThreads, smem, stream>>>(
-			    static_cast<const int *>(col), row_begin, n_rows, base_value, v_lo, v_n, bitvectors, words_per_bv);
+			    static_cast<const int *>(col), valid, row_begin, n_rows, base_value, v_lo, v_n, bitvectors, words_per_bv);
 		} else {
 			cubit_index_build_kernel<long long><<<(unsigned)grid, kBuildThreads, smem, stream>>>(
-			    static_cast<const long long *>(col), row_begin, n_rows, base_value, v_lo, v_n, bitvectors,
+			    static_cast<const long long *>(col), valid, row_begin, n_rows, base_value, v_lo, v_n, bitvectors,
 			    words_per_bv);
 		}
 		launches++;
@@ -399,27 +406,6 @@ cudaError_t launch_popcount(const uint64_t *words, uint64_t n_words, unsigned lo
                             cudaStream_t stream) {
 	(void)sm_count;
 	return launch_popcount_many(words, n_words, 1, out, stream);
-}
-
-// ------------------------------------------------------- delta merge-back
-__global__ void cubit_apply_delta_kernel(uint64_t *__restrict__ bv, const uint32_t *__restrict__ doff,
-                                         const DeltaEnt *__restrict__ dent, uint32_t n_seg, uint32_t seg_words) {
-	for (uint32_t seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
-		const uint32_t d0 = doff[seg], d1 = doff[seg + 1];
-		for (uint32_t e = d0 + threadIdx.x; e < d1; e += blockDim.x) {
-			bv[(uint64_t)seg * seg_words + dent[e].word] ^= dent[e].mask;
-		}
-	}
-}
-
-cudaError_t launch_apply_delta(uint64_t *bv, const uint32_t *doff, const DeltaEnt *dent, uint32_t n_seg,
-                               uint32_t seg_words, cudaStream_t stream) {
-	unsigned grid = n_seg < 4096u ? n_seg : 4096u;
-	if (grid < 1) {
-		grid = 1;
-	}
-	cubit_apply_delta_kernel<<<grid, 64, 0, stream>>>(bv, doff, dent, n_seg, seg_words);
-	return cudaGetLastError();
 }
 
 // ------------------------------------------------------- FOR bit-packing

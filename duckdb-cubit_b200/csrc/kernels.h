@@ -13,13 +13,52 @@ constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kScanThreads = kConsumerThreads + 64; // + one producer warp + one prefix (look-back) warp
 constexpr int kScanRingBytes = 72 * 1024;           // bulk-copy ring per CTA (stages of one segment each); 2 CTAs / SM
 
-// One pending-delta word of one (bitvector, segment): XOR `mask` into word
-// `word` of the staged segment.  Words are unique within a (bitvector, segment).
+// One pending-delta entry of one (bitvector, segment): XOR `mask` into word `word` of the staged segment.
+// Entries of one (bitvector, segment) are contiguous in the index's delta CSR but unordered, and a word may
+// appear more than once (the kernels XOR atomically), so ingestion never sorts or deduplicates.
+// `pad` carries the entry's CSR key (value * n_seg + segment) for the device-side rebuilds (delta_kernels.cu).
 struct DeltaEnt {
 	uint32_t word;
 	uint32_t pad;
 	uint64_t mask;
 };
+
+// one device-side ingestion of pending deltas (delta_kernels.cu): old CSR + n_new (value, row) pairs → new CSR
+struct DeltaIngest {
+	const long long *rows;   // [n_new] local row positions (device)
+	const uint32_t *values;  // [n_new] value ids (device), or nullptr: every pair belongs to `one_value`
+	uint32_t one_value;
+	uint64_t n_new;
+	uint32_t n_seg;
+	uint32_t seg_shift;      // log2(seg_bits)
+	uint64_t n_keys;         // card * n_seg
+	const uint32_t *old_off; // [n_keys + 1] or nullptr (no pending deltas yet)
+	const DeltaEnt *old_ent;
+	uint64_t n_old;
+	uint32_t drop_value;     // entries of this value are NOT carried over (cubit_gpu_set_delta), 0xffffffff = none
+	uint32_t *cnt;           // [n_keys] scratch, zeroed
+	uint32_t *block_sum;     // [ceil(n_keys / 4096)] scratch
+	uint32_t *new_off;       // [n_keys + 1] out
+	DeltaEnt *new_ent;       // [surviving old + n_new] out
+};
+
+// ---- roaring-style containers of a compressed index (container_kernels.cu) -------------------------
+// directory entry of one (value, segment): type (bits 1:0) | set bits of the segment (bits 18:2, 0..65536) | pool
+// offset in 16-byte units (bits 63:19).  EMPTY = all-zero word, so a zeroed directory is an empty index.
+enum ContainerType : uint32_t { CT_EMPTY = 0, CT_FULL = 1, CT_ARRAY = 2, CT_BITMAP = 3 };
+constexpr int kArrayMax = 512; // ARRAY containers hold ≤ 512 sorted 16-bit positions (1 KiB staged per ring stage)
+__host__ __device__ inline uint32_t ct_type(unsigned long long d) {
+	return (uint32_t)(d & 3ull);
+}
+__host__ __device__ inline uint32_t ct_count(unsigned long long d) {
+	return (uint32_t)((d >> 2) & 0x1ffffull);
+}
+__host__ __device__ inline unsigned long long ct_offset(unsigned long long d) {
+	return (d >> 19) << 4; // bytes
+}
+__host__ __device__ inline unsigned long long ct_make(uint32_t type, uint32_t count, unsigned long long byte_off) {
+	return (unsigned long long)type | ((unsigned long long)count << 2) | ((byte_off >> 4) << 19);
+}
 
 // ---- column storage -----------------------------------------------------------------------------
 // An 8-byte column lives in HBM either raw (int64 per row) or FOR-bit-packed: blocks of kPackBlock rows,
@@ -86,8 +125,9 @@ struct BlockPartial {
 //   [1 .. n_seg]   decoupled look-back status word of every segment
 struct ScanArgs {
 	const uint64_t *bv[kMaxStreams];    // value bitvector B_i (padded to whole segments)
-	const uint32_t *doff[kMaxStreams];  // delta CSR offsets [n_seg+1] of D_i, or nullptr
-	const DeltaEnt *dent[kMaxStreams];  // delta entries of D_i
+	const uint32_t *doff[kMaxStreams];  // delta CSR offsets of D_i (the index's CSR at key value*n_seg), or nullptr
+	const DeltaEnt *dent[kMaxStreams];  // delta entries of D_i's index (offsets are absolute)
+	const unsigned long long *cdir[kMaxStreams]; // container directory of B_i (compressed index; bv[i] = its pool), or nullptr
 	uint64_t group_end;                 // bit i: stream i closes its OR group (then Q &= group)
 	uint32_t k;                         // streams
 	uint32_t n_seg;                     // segments (tiles)
@@ -97,7 +137,6 @@ struct ScanArgs {
 	uint64_t *q_out;                    // merged bitvector out, or nullptr
 	unsigned long long *tile_excl;      // per-segment exclusive prefix out (scan) / in (bit-driven probe), or nullptr
 	long long *ids_out;                 // sorted row IDs out, or nullptr
-	unsigned long long ids_cap;         // capacity of ids_out / vals_out in rows
 	// fused probe: the distinct int64 columns read at every selected row
 	int n_load;                           // 0..kMaxFusedCols
 	ColRef lcol[kMaxFusedCols];           // the columns (local row indexed; raw or bit-packed)
@@ -136,8 +175,9 @@ struct ProbeArgs {
 
 // ---- launchers (all asynchronous on `stream`; return cudaGetLastError()) ----
 // seg_words ∈ {512, 1024, 2048} (= 256 consumer threads × 2/4/8 words).  has_delta: any doff[i] != nullptr.
-cudaError_t launch_scan(const ScanArgs &args, uint32_t seg_words, bool has_delta, int sm_count, cudaStream_t stream,
-                        int *grid_out);
+// compressed: any cdir[i] != nullptr (seg_words ≤ 1024, no fused probe).
+cudaError_t launch_scan(const ScanArgs &args, uint32_t seg_words, bool has_delta, bool compressed, int sm_count,
+                        cudaStream_t stream, int *grid_out);
 int scan_max_grid(uint32_t seg_words, int sm_count);
 // Bit-driven probe: re-decodes the merged bitvector args.q_out (input here) with the
 // per-segment prefixes args.tile_excl and gathers / sums the fused-probe columns at full
@@ -154,16 +194,37 @@ cudaError_t launch_validity_gather(const long long *ids, const unsigned long lon
 int probe_grid(int sm_count);
 
 // index build: B_(col[r]-base) |= bit r for rows [row_begin, n_rows); bits of rows < row_begin are kept (append)
-cudaError_t launch_index_build(const void *col, uint32_t elem_bytes, uint64_t row_begin, uint64_t n_rows,
-                               int64_t base_value,
+// valid: the column's validity mask or nullptr — NULL keys are not indexed (plan_create_index.cpp:60-78)
+cudaError_t launch_index_build(const void *col, uint32_t elem_bytes, const unsigned long long *valid, uint64_t row_begin,
+                               uint64_t n_rows, int64_t base_value,
                                uint32_t cardinality, uint64_t *bitvectors, uint64_t words_per_bv, int sm_count,
                                cudaStream_t stream, int *n_launches);
 cudaError_t launch_popcount(const uint64_t *words, uint64_t n_words, unsigned long long *out, int sm_count,
                             cudaStream_t stream);
 cudaError_t launch_popcount_many(const uint64_t *bitvectors, uint64_t words_per_bv, uint32_t n_bv,
                                  unsigned long long *out, cudaStream_t stream);
-cudaError_t launch_apply_delta(uint64_t *bv, const uint32_t *doff, const DeltaEnt *dent, uint32_t n_seg,
-                               uint32_t seg_words, cudaStream_t stream);
+// pending-delta maintenance (delta_kernels.cu)
+cudaError_t launch_delta_ingest(const DeltaIngest &a, int sm_count, cudaStream_t stream, int *n_launches);
+// B ^= D for entries [e0, e1) of the CSR; bits = B_(value_base)'s first word
+cudaError_t launch_delta_apply(const DeltaEnt *ent, uint64_t e0, uint64_t e1, uint32_t n_seg, uint32_t seg_words,
+                               uint64_t *bits, uint64_t words_per_bv, uint32_t value_base, int sm_count,
+                               cudaStream_t stream);
+cudaError_t launch_delta_restride(const uint32_t *old_off, uint32_t *new_off, DeltaEnt *ent, uint64_t n_ent, uint32_t card,
+                                  uint32_t old_n_seg, uint32_t new_n_seg, int sm_count, cudaStream_t stream);
+// compressed indexes (container_kernels.cu)
+// src: [nv][words_per_bv] verbatim → containers appended to the pool at *cursor (cursor[0], bytes; cursor[1]
+// accumulates the bytes of the containers that are replaced), directory rows dir[v * dir_stride + seg]
+cudaError_t launch_container_compress(const uint64_t *src, uint64_t words_per_bv, uint32_t nv, uint32_t n_seg,
+                                      uint32_t seg_words, unsigned long long *dir, uint64_t dir_stride, uint8_t *pool,
+                                      unsigned long long *cursor, cudaStream_t stream);
+// one value: containers → verbatim words (segments [n_seg, n_seg_alloc) are zeroed)
+cudaError_t launch_container_expand(const unsigned long long *dir, const uint8_t *pool, uint64_t n_seg_alloc, uint32_t n_seg,
+                                    uint32_t seg_words, uint64_t *dst, cudaStream_t stream);
+// out[v] = popcount of B_v (the directory stores every container's count)
+cudaError_t launch_compressed_counts(const unsigned long long *dir, uint64_t dir_stride, uint32_t n_seg, uint32_t card,
+                                     const uint8_t *pool, uint32_t seg_words, unsigned long long *out, cudaStream_t stream);
+// (count, 128-bit sum) of a result header → five 32-bit limbs ADDED to dst[0..5) as int64 (multi-process reduce)
+cudaError_t launch_add_limbs(const ResultHeader *hdr, long long *dst, cudaStream_t stream);
 // FOR-bit-packing of an int64 column (see ColRef): pass 1 per-block min/width, pass 2 pack
 cudaError_t launch_pack_widths(const long long *col, uint64_t n_rows, long long *base_out, uint32_t *width_out,
                                cudaStream_t stream);

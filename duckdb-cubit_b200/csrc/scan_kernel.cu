@@ -53,15 +53,19 @@ namespace cubit {
 
 // NL > 0 (probe fused into the scan, not the default path): the per-warp staging rows also hold the pack-block
 // headers of the probed columns; the ring gives up 8 KiB so that two CTAs still fit one SM.
-template <int WPT, int NL>
+// CMP (a queried index keeps roaring-style containers, container_kernels.cu): the ring gives up a quarter of its
+// bytes for the per-stage ARRAY staging buffers (kArrayMax 16-bit positions each).
+template <int WPT, int NL, bool CMP = false>
 struct ScanSmem {
 	static constexpr int kTileWords = kConsumerThreads * WPT;
 	static constexpr int kTileBytes = kTileWords * 8;
-	static constexpr int kStages = (kScanRingBytes - (NL > 0 ? 8192 : 0)) / kTileBytes;
+	static constexpr int kStages = CMP ? (kScanRingBytes * 3 / 4) / kTileBytes : (kScanRingBytes - (NL > 0 ? 8192 : 0)) / kTileBytes;
 	static constexpr int kCompactRow = kCompactHdrOff + NL * kHdrSlots * 8;
 	alignas(128) uint64_t stage[kStages][kTileWords];
 	alignas(16) uint16_t compact[kConsumerWarps][kCompactRow]; // per-warp staging of local row numbers (+ dummy slots)
 	alignas(16) DeltaEnt dbuf[kStages][kDeltaStage];              // pending-delta words staged beside each segment
+	alignas(16) uint16_t abuf[CMP ? kStages : 1][CMP ? kArrayMax : 8]; // ARRAY containers staged beside each segment
+	unsigned long long pdir[CMP ? kMaxStreams : 1];                    // producer: directory entries of the current segment
 	alignas(8) uint64_t full[kStages];
 	uint64_t empty[kStages];
 	uint64_t req_full[kReqSlots];  // consumers → prefix warp
@@ -78,9 +82,9 @@ struct ScanSmem {
 // ONEG: the predicate is ONE OR group (a range / IN predicate on one indexed column, the common case): the fold
 // is a plain OR into q, without the per-stream group test and the AND / reset of the group accumulator (23 of the
 // 47 SASS instructions the generic fold spends per stream and warp).
-template <int WPT, bool HAS_DELTA, int NL, bool ONEG>
+template <int WPT, bool HAS_DELTA, int NL, bool ONEG, bool CMP>
 __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __grid_constant__ ScanArgs a) {
-	using Smem = ScanSmem<WPT, NL>;
+	using Smem = ScanSmem<WPT, NL, CMP>;
 	constexpr int kStages = Smem::kStages;
 	constexpr int kTileWords = Smem::kTileWords;
 	constexpr int kTileBytes = Smem::kTileBytes;
@@ -141,8 +145,24 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 				}
 			}
 		};
+		// compressed streams: the directory entry of (stream, segment) says what to copy; fetched like the delta
+		// offsets, one segment ahead by all lanes, so the dependent load never sits in front of a bulk copy
+		unsigned long long cde[2] = {0, 0};
+		auto load_dirs = [&](uint32_t tl) {
+#pragma unroll
+			for (int h = 0; h < 2; h++) {
+				const uint32_t s = (uint32_t)lane + 32u * h;
+				cde[h] = 0;
+				if (s < a.k && a.cdir[s] && tl < a.n_seg) {
+					cde[h] = __ldg(a.cdir[s] + tl);
+				}
+			}
+		};
 		if (HAS_DELTA) {
 			load_offsets(tile);
+		}
+		if (CMP) {
+			load_dirs(tile);
 		}
 		while (true) {
 			const bool valid = tile < a.n_seg;
@@ -160,6 +180,16 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 				__syncwarp();
 				if (valid) {
 					load_offsets(next); // in flight while lane 0 issues this segment's copies
+				}
+			}
+			if (CMP) {
+#pragma unroll
+				for (int h = 0; h < 2; h++) {
+					sm.pdir[lane + 32 * h] = cde[h];
+				}
+				__syncwarp();
+				if (valid) {
+					load_dirs(next);
 				}
 			}
 			if (lane == 0) {
@@ -185,8 +215,28 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 								dsrc = a.dent[s] + d0;
 							}
 						}
-						mbar_arrive_expect_tx(&sm.full[stage], kTileBytes + dbytes);
-						bulk_g2s(&sm.stage[stage][0], a.bv[s] + (size_t)tile * kTileWords, kTileBytes, &sm.full[stage]);
+						if (CMP && a.cdir[s]) {
+							// container of (stream, segment): BITMAP → the ring stage, ARRAY → its staging buffer,
+							// EMPTY / FULL → nothing crosses HBM at all
+							const unsigned long long de = sm.pdir[s];
+							const uint32_t ctype = ct_type(de), ccnt = ct_count(de);
+							sm.meta[stage].pad = ctype | (ccnt << 2);
+							const uint8_t *csrc = reinterpret_cast<const uint8_t *>(a.bv[s]) + ct_offset(de);
+							const uint32_t cbytes =
+							    ctype == CT_BITMAP ? (uint32_t)kTileBytes : (ctype == CT_ARRAY ? ((ccnt * 2u + 15u) & ~15u) : 0u);
+							mbar_arrive_expect_tx(&sm.full[stage], cbytes + dbytes);
+							if (ctype == CT_BITMAP) {
+								bulk_g2s(&sm.stage[stage][0], csrc, kTileBytes, &sm.full[stage]);
+							} else if (ctype == CT_ARRAY) {
+								bulk_g2s(&sm.abuf[stage][0], csrc, cbytes, &sm.full[stage]);
+							}
+						} else {
+							if (CMP) {
+								sm.meta[stage].pad = CT_BITMAP;
+							}
+							mbar_arrive_expect_tx(&sm.full[stage], kTileBytes + dbytes);
+							bulk_g2s(&sm.stage[stage][0], a.bv[s] + (size_t)tile * kTileWords, kTileBytes, &sm.full[stage]);
+						}
 						if (dbytes) {
 							bulk_g2s(&sm.dbuf[stage][0], dsrc, dbytes, &sm.full[stage]);
 						}
@@ -310,14 +360,45 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 				if (s == 0) {
 					tile = sm.meta[stage].tile;
 				}
-				if (HAS_DELTA && tile != kNoTile) {
-					// Every warp applies the delta words that fall into ITS span of the staged segment
-					// (XOR in shared memory, then the fold below picks them up): no block-wide barrier.
+				uint32_t skip = 0; // bit u: stage u of this batch is an EMPTY container without deltas — nothing to fold
+				if ((HAS_DELTA || CMP) && tile != kNoTile) {
+					// Every warp prepares ITS span of the staged segment — fills it for an EMPTY / FULL / ARRAY container,
+					// then XORs the pending-delta entries that fall into the span — with generic-proxy writes to shared
+					// memory that the fold below picks up: no block-wide barrier.  Delta entries of one (stream, segment)
+					// are unordered and may repeat a word (device-side ingestion never sorts), hence the atomics.
 					bool wrote = false;
 					for (uint32_t u = 0; u < nb; u++) {
 						uint32_t st = stage + u;
 						st = st >= (uint32_t)kStages ? st - (uint32_t)kStages : st;
-						const uint32_t dcnt = sm.meta[st].dcnt;
+						const uint32_t dcnt = HAS_DELTA ? sm.meta[st].dcnt : 0u;
+						if (CMP) {
+							const uint32_t cmeta = sm.meta[st].pad, ctype = cmeta & 3u;
+							if (ctype != CT_BITMAP) {
+								if (ctype == CT_EMPTY && dcnt == 0) {
+									skip |= 1u << u;
+									continue;
+								}
+								const uint64_t fill = ctype == CT_FULL ? ~0ull : 0ull;
+								uint64_t *span = &sm.stage[st][warp * kSpanWords];
+#pragma unroll
+								for (int i = 0; i < WPT; i++) {
+									span[i * 32 + lane] = fill;
+								}
+								wrote = true;
+								if (ctype == CT_ARRAY) {
+									__syncwarp();
+									const uint32_t cnt = cmeta >> 2;
+									for (uint32_t e = lane; e < cnt; e += 32) {
+										const uint32_t p = sm.abuf[st][e];
+										const uint32_t rel = (p >> 6) - (uint32_t)(warp * kSpanWords);
+										if (rel < (uint32_t)kSpanWords) {
+											atomicOr(reinterpret_cast<unsigned long long *>(&sm.stage[st][p >> 6]), 1ull << (p & 63u));
+										}
+									}
+								}
+								__syncwarp();
+							}
+						}
 						for (uint32_t e = lane; e < dcnt; e += 32) {
 							uint4 raw;
 							if (e < (uint32_t)kDeltaStage) {
@@ -326,8 +407,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 								raw = __ldg(reinterpret_cast<const uint4 *>(a.dent[s + u] + sm.meta[st].d0 + e));
 							}
 							const uint32_t rel = raw.x - (uint32_t)(warp * kSpanWords);
-							if (rel < (uint32_t)kSpanWords) { // words are unique per (stream, segment)
-								sm.stage[st][raw.x] ^= ((uint64_t)raw.w << 32) | raw.z;
+							if (rel < (uint32_t)kSpanWords) {
+								atomicXor(reinterpret_cast<unsigned long long *>(&sm.stage[st][raw.x]),
+								          ((unsigned long long)raw.w << 32) | raw.z);
 								wrote = true;
 							}
 						}
@@ -351,15 +433,19 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 #define CUBIT_LD(i) src[(i) * 32 + lane]
 #endif
 							if (ONEG) {
+								if (!CMP || !((skip >> u) & 1u)) {
 #pragma unroll
-								for (int i = 0; i < WPT; i++) {
-									q[i] |= CUBIT_LD(i);
+									for (int i = 0; i < WPT; i++) {
+										q[i] |= CUBIT_LD(i);
+									}
 								}
 								continue;
 							}
+							if (!CMP || !((skip >> u) & 1u)) {
 #pragma unroll
-							for (int i = 0; i < WPT; i++) {
-								g[i] |= CUBIT_LD(i);
+								for (int i = 0; i < WPT; i++) {
+									g[i] |= CUBIT_LD(i);
+								}
 							}
 #undef CUBIT_LD
 							if ((a.group_end >> (s + u)) & 1ull) {
@@ -651,10 +737,10 @@ cudaError_t launch_probe_bits(const ScanArgs &args, uint32_t seg_words, bool pos
 }
 
 // --------------------------------------------------------------------- launch
-template <int WPT, bool HAS_DELTA, int NL, bool ONEG>
+template <int WPT, bool HAS_DELTA, int NL, bool ONEG, bool CMP>
 static cudaError_t launch_scan_g(const ScanArgs &args, int sm_count, cudaStream_t stream, int *grid_out) {
-	auto kern = cubit_scan_kernel<WPT, HAS_DELTA, NL, ONEG>;
-	const size_t smem = sizeof(ScanSmem<WPT, NL>) + 128;
+	auto kern = cubit_scan_kernel<WPT, HAS_DELTA, NL, ONEG, CMP>;
+	const size_t smem = sizeof(ScanSmem<WPT, NL, CMP>) + 128;
 	// function attributes are per device: configure once per (template instance, device)
 	static int blocks_per_sm_dev[64] = {};
 	int dev = 0;
@@ -690,42 +776,48 @@ static cudaError_t launch_scan_g(const ScanArgs &args, int sm_count, cudaStream_
 	return cudaGetLastError();
 }
 
-template <int WPT, bool HAS_DELTA, int NL>
+template <int WPT, bool HAS_DELTA, int NL, bool CMP>
 static cudaError_t launch_scan_t(const ScanArgs &args, int sm_count, cudaStream_t stream, int *grid_out) {
 	// one OR group ⇔ only the last stream closes a group (the specialised fold exists for the default, unfused path)
 	const bool one_group = NL == 0 && args.k >= 1 && args.group_end == (1ull << (args.k - 1));
 	if (NL == 0 && one_group) {
-		return launch_scan_g<WPT, HAS_DELTA, NL, NL == 0>(args, sm_count, stream, grid_out);
+		return launch_scan_g<WPT, HAS_DELTA, NL, NL == 0, CMP>(args, sm_count, stream, grid_out);
 	}
-	return launch_scan_g<WPT, HAS_DELTA, NL, false>(args, sm_count, stream, grid_out);
+	return launch_scan_g<WPT, HAS_DELTA, NL, false, CMP>(args, sm_count, stream, grid_out);
 }
 
 template <int WPT, bool HAS_DELTA>
-static cudaError_t launch_scan_nl(const ScanArgs &args, int sm_count, cudaStream_t stream, int *grid_out) {
+static cudaError_t launch_scan_nl(const ScanArgs &args, bool compressed, int sm_count, cudaStream_t stream, int *grid_out) {
+	if (compressed) { // container streams: segments of ≤ 65536 rows, probe never fused (cubit_query.cu plans accordingly)
+		if (WPT > 4 || args.n_load != 0) {
+			return cudaErrorInvalidValue;
+		}
+		return launch_scan_t<(WPT > 4 ? 4 : WPT), HAS_DELTA, 0, true>(args, sm_count, stream, grid_out);
+	}
 	switch (args.n_load) {
 	case 0:
-		return launch_scan_t<WPT, HAS_DELTA, 0>(args, sm_count, stream, grid_out);
+		return launch_scan_t<WPT, HAS_DELTA, 0, false>(args, sm_count, stream, grid_out);
 	case 1:
-		return launch_scan_t<WPT, HAS_DELTA, 1>(args, sm_count, stream, grid_out);
+		return launch_scan_t<WPT, HAS_DELTA, 1, false>(args, sm_count, stream, grid_out);
 	case 2:
-		return launch_scan_t<WPT, HAS_DELTA, 2>(args, sm_count, stream, grid_out);
+		return launch_scan_t<WPT, HAS_DELTA, 2, false>(args, sm_count, stream, grid_out);
 	default:
 		return cudaErrorInvalidValue;
 	}
 }
 
-cudaError_t launch_scan(const ScanArgs &args, uint32_t seg_words, bool has_delta, int sm_count, cudaStream_t stream,
-                        int *grid_out) {
+cudaError_t launch_scan(const ScanArgs &args, uint32_t seg_words, bool has_delta, bool compressed, int sm_count,
+                        cudaStream_t stream, int *grid_out) {
 	switch (seg_words) {
 	case 512:
-		return has_delta ? launch_scan_nl<2, true>(args, sm_count, stream, grid_out)
-		                 : launch_scan_nl<2, false>(args, sm_count, stream, grid_out);
+		return has_delta ? launch_scan_nl<2, true>(args, compressed, sm_count, stream, grid_out)
+		                 : launch_scan_nl<2, false>(args, compressed, sm_count, stream, grid_out);
 	case 1024:
-		return has_delta ? launch_scan_nl<4, true>(args, sm_count, stream, grid_out)
-		                 : launch_scan_nl<4, false>(args, sm_count, stream, grid_out);
+		return has_delta ? launch_scan_nl<4, true>(args, compressed, sm_count, stream, grid_out)
+		                 : launch_scan_nl<4, false>(args, compressed, sm_count, stream, grid_out);
 	case 2048:
-		return has_delta ? launch_scan_nl<8, true>(args, sm_count, stream, grid_out)
-		                 : launch_scan_nl<8, false>(args, sm_count, stream, grid_out);
+		return has_delta ? launch_scan_nl<8, true>(args, compressed, sm_count, stream, grid_out)
+		                 : launch_scan_nl<8, false>(args, compressed, sm_count, stream, grid_out);
 	default:
 		return cudaErrorInvalidValue;
 	}

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CUBIT_GPU_ABI_VERSION 2
+#define CUBIT_GPU_ABI_VERSION 3
 
 /* error codes */
 #define CUBIT_OK 0
@@ -49,8 +49,9 @@ extern "C" {
 #define CUBIT_MAX_STREAMS 64 /* bitvectors read by one query (Σ group sizes) */
 #define CUBIT_MAX_PROBE_COLS 8
 
-typedef struct cubit_gpu_table cubit_gpu_table;   /* one table shard on one GPU */
+typedef struct cubit_gpu_table cubit_gpu_table;   /* one table shard on one GPU, or a table sharded over several */
 typedef struct cubit_gpu_result cubit_gpu_result; /* one query's result set     */
+typedef struct cubit_gpu_fetch_ticket cubit_gpu_fetch_ticket; /* one asynchronous hand-off copy in flight */
 
 /* (index, value) names one value bitvector B_v of one CUBIT index. */
 typedef struct cubit_bv_ref {
@@ -130,7 +131,21 @@ int cubit_gpu_device_count(int *count);
  * seg_bits  CUBIT segment size in rows: 32768, 65536 or 131072.  One segment
  *           is the unit of the merge kernel and of the pending-delta lists.  */
 int cubit_gpu_create(int device, uint64_t n_rows, int64_t row_base, uint32_t seg_bits, cubit_gpu_table **out);
+/* One table over several GPUs of the box (the reference's parallel unit is the row-group range handed
+ * out by RowGroupCollection::NextParallelScan, src/storage/table/row_group_collection.cpp:174-224, bounded by
+ * TableFunction MaxThreads, src/include/duckdb/function/table_function.hpp:45-67).  Rows are cut into contiguous
+ * ranges of whole segments, shard i on devices[i] (a device may be named more than once; fewer shards are made when
+ * the table has fewer segments than devices).  The returned handle is used with EVERY other entry point: uploads,
+ * synthetic columns, index builds and deltas are cut or routed by row range; cubit_gpu_query runs on all shards at
+ * once; COUNT / SUM are added exactly; cubit_gpu_fetch walks the shards in row order, so row IDs stay globally
+ * sorted.  Per-shard operations (WAH upload, on-disk segment upload, index images, set_stream) report
+ * CUBIT_ESTATE on the parent — address the shard's own data instead.  row_base must be a multiple of seg_bits. */
+int cubit_gpu_create_sharded(const int *devices, uint32_t n_devices, uint64_t n_rows, int64_t row_base,
+                             uint32_t seg_bits, cubit_gpu_table **out);
+int cubit_gpu_shard_count(const cubit_gpu_table *t, uint32_t *n_shards);
+int cubit_gpu_shard_info(const cubit_gpu_table *t, uint32_t shard, int *device, uint64_t *first_row, uint64_t *n_rows);
 int cubit_gpu_destroy(cubit_gpu_table *t);
+int cubit_gpu_row_count(const cubit_gpu_table *t, uint64_t *n_rows);
 /* run this table's kernels on a caller-owned cudaStream_t (NULL = own stream) */
 int cubit_gpu_set_stream(cubit_gpu_table *t, void *cuda_stream);
 int cubit_gpu_words_per_bitvector(const cubit_gpu_table *t, uint64_t *n_words);
@@ -139,6 +154,22 @@ int cubit_gpu_launch_count(const cubit_gpu_table *t, uint64_t *n);
 
 /* ---- CUBIT index: `cardinality` value bitvectors over the shard's rows -- */
 int cubit_gpu_index_create(cubit_gpu_table *t, uint32_t cardinality, int32_t *index_id);
+/* The same index kept COMPRESSED in HBM: one roaring-style container per (value, segment) —
+ * empty, full, a sorted array of ≤ 512 16-bit row positions, or the verbatim segment — which the scan kernel
+ * expands in shared memory, so sparse bitvectors cost neither HBM capacity nor bandwidth (a day-level l_shipdate
+ * index, 2,526 bitvectors, is 190 GB verbatim at SF100).  Every entry point works on it unchanged: uploads
+ * (verbatim or WAH: expanded on the GPU, stored as containers), GPU build from a column, pending deltas (XOR-ed
+ * after the expansion), merge-back, append, images.  Needs seg_bits <= 65536. */
+int cubit_gpu_index_create_compressed(cubit_gpu_table *t, uint32_t cardinality, int32_t *index_id);
+typedef struct cubit_index_info {
+	uint32_t cardinality;
+	uint32_t compressed;     /* 1: containers, 0: verbatim bitvectors                     */
+	uint64_t resident_bytes; /* HBM the bitvectors occupy (pool + directory / verbatim)    */
+	uint64_t verbatim_bytes; /* cardinality * ceil(n_rows / seg_bits) * seg_bits / 8       */
+	uint64_t delta_entries;  /* pending-delta entries (16 bytes each)                      */
+	uint64_t auto_merges;    /* threshold-driven merge-backs so far                        */
+} cubit_index_info;
+int cubit_gpu_index_info(cubit_gpu_table *t, int32_t index_id, cubit_index_info *info);
 /* words: ceil(n_rows/64) host words, bits >= n_rows must be 0 */
 int cubit_gpu_upload_bitvector(cubit_gpu_table *t, int32_t index_id, uint32_t value_id, const uint64_t *words,
                                uint64_t n_words);
@@ -166,14 +197,25 @@ int cubit_gpu_index_build(cubit_gpu_table *t, int32_t index_id, int32_t col_id, 
 /* popcount of B_v as stored (pending deltas not applied) */
 int cubit_gpu_bitvector_count(cubit_gpu_table *t, int32_t index_id, uint32_t value_id, uint64_t *count);
 
-/* Pending update/delete delta D_v of one bitvector: the set of LOCAL row
- * positions whose bit is flipped at query time (B_v XOR D_v).  Replaces any
- * previous pending delta of that bitvector; a row listed twice cancels.
- * UPDATE v→w of row r contributes r to D_v and D_w, DELETE of a row whose
- * value is v contributes r to D_v. */
+/* Pending update/delete deltas (the index side of DML: BoundIndex::Append / Delete / Insert,
+ * src/include/duckdb/execution/index/bound_index.hpp:71-97).  D_v is the set of LOCAL row positions whose bit is
+ * flipped at query time (B_v XOR D_v); a row listed an even number of times cancels.  UPDATE v→w of row r
+ * contributes r to D_v and D_w, DELETE of a row whose value is v contributes r to D_v.
+ *   cubit_gpu_add_delta        adds n flipped rows to D_v — INCREMENTAL: earlier pending rows stay
+ *   cubit_gpu_add_delta_pairs  adds n (value, row) pairs in one call (what one UPDATE / DELETE statement produces)
+ *   cubit_gpu_set_delta        replaces D_v
+ * Ingestion runs ON THE DEVICE, in stream order behind the scans already enqueued (counting sort by
+ * (value, segment): histogram, scan, move, scatter — delta_kernels.cu); the host only copies the pairs across and
+ * never waits.  rows / value_ids may be pageable and are free to reuse on return.
+ * Merge-back (B_v ^= D_v, lists cleared) happens on demand (cubit_gpu_merge_deltas) and AUTOMATICALLY after an
+ * add once the pending entries of a touched value outweigh `fraction` of its bitvector
+ * (cubit_gpu_set_merge_threshold, default 0.25; 0 disables).  Needs cardinality * segments <= 2^30. */
+int cubit_gpu_add_delta(cubit_gpu_table *t, int32_t index_id, uint32_t value_id, const int64_t *rows, uint64_t n);
+int cubit_gpu_add_delta_pairs(cubit_gpu_table *t, int32_t index_id, const uint32_t *value_ids, const int64_t *rows,
+                              uint64_t n);
 int cubit_gpu_set_delta(cubit_gpu_table *t, int32_t index_id, uint32_t value_id, const int64_t *rows, uint64_t n);
-/* merge-back: B_v ^= D_v for every bitvector of the index, deltas cleared */
 int cubit_gpu_merge_deltas(cubit_gpu_table *t, int32_t index_id);
+int cubit_gpu_set_merge_threshold(cubit_gpu_table *t, int32_t index_id, double fraction);
 
 /* Persistence of an index: the analog of BoundIndex::GetStorageInfo → IndexStorageInfo
  * (src/include/duckdb/execution/index/bound_index.hpp:117-118), written at checkpoint and read back when the
@@ -264,7 +306,10 @@ int cubit_gpu_upload_column_segments(cubit_gpu_table *t, int32_t col_id, uint32_
 
 /* ---- query --------------------------------------------------------------
  * Synchronous unless CUBIT_Q_ASYNC: on return info fields are final.
- * Thread-safe per table (calls are serialised on the table's stream).      */
+ * Thread-safe per table: the table's lock is held only while a query is planned and its kernels are enqueued,
+ * never while a caller waits for the GPU or copies rows out, so several host threads keep queries and DataChunk
+ * hand-offs in flight on one table (kernels of one shard run in order on its kernel stream; hand-off copies run
+ * on separate copy streams).                                                */
 int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_result **out);
 int cubit_gpu_result_wait(cubit_gpu_result *r);
 int cubit_gpu_result_get(cubit_gpu_result *r, cubit_result_info *info);
@@ -273,6 +318,18 @@ int cubit_gpu_result_get(cubit_gpu_result *r, cubit_result_info *info);
  * (≤ 2048 rows per GetData call: table_scan.cpp:258-268). */
 int cubit_gpu_fetch(cubit_gpu_result *r, uint64_t offset, uint64_t n, int64_t *host_rowids, uint32_t n_cols,
                     void *const *host_cols);
+/* The same copy without the wait: window i+1 crosses PCIe while the caller consumes window i (ordered parallel
+ * sources keep several in flight, the pattern of src/function/table/table_scan.cpp:179-189).  Buffers should come
+ * from cubit_gpu_alloc_host (a pageable destination makes the copy synchronous) and must stay untouched until
+ * cubit_gpu_fetch_wait, which completes and frees the ticket.  May be called from several threads at once. */
+int cubit_gpu_fetch_async(cubit_gpu_result *r, uint64_t offset, uint64_t n, int64_t *host_rowids, uint32_t n_cols,
+                          void *const *host_cols, cubit_gpu_fetch_ticket **ticket);
+int cubit_gpu_fetch_wait(cubit_gpu_fetch_ticket *ticket);
+/* Multi-process reduce (one rank per GPU): ADD this result's (count, 128-bit sum) to device_dst[0..5)
+ * as five int64 limbs — count, sum bits [0,32), [32,64), [64,96), signed [96,128) — on the device, in stream
+ * order behind the query, so the caller can hand device_dst to one ncclAllReduce(sum) without the aggregates
+ * visiting the host.  The limbs of up to 2^31 results can be accumulated before a carry could be lost. */
+int cubit_gpu_result_add_limbs(cubit_gpu_result *r, int64_t *device_dst);
 /* Validity mask of projected column `col` (index into the query's cols[]) for result rows [offset, offset+n):
  * bit j of host_words = row offset+j, ceil(n/64) words, bits past n zero — the mask the DataChunk vector gets
  * (FlatVector::Validity).  *all_valid (optional) = 1 when no NULL falls into the range, so the caller can skip

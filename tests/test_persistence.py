@@ -11,13 +11,13 @@ import oracle
 
 pytestmark = pytest.mark.gpu
 
-HDR = struct.Struct("<8sQIiq")      # magic, n_rows, card, src_col, src_base
+HDR = struct.Struct("<8sQIiqII")    # magic, n_rows, card, src_col, src_base, flags (1 = compressed), pad
 ENT = struct.Struct("<IIIIQQ")      # encoding, active_val, active_nbits, pad, n_words, n_delta_rows
 
 
 def parse(image):
-    magic, n_rows, card, src_col, src_base = HDR.unpack_from(image, 0)
-    assert magic == b"CUBITIX1"
+    magic, n_rows, card, src_col, src_base, _flags, _pad = HDR.unpack_from(image, 0)
+    assert magic == b"CUBITIX2"
     at, out = HDR.size, []
     for _ in range(card):
         enc, aval, anb, _pad, nw, nd = ENT.unpack_from(image, at)

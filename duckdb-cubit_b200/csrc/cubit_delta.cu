@@ -24,6 +24,12 @@ uint32_t seg_shift_of(const cubit_gpu_table *t) {
 int ingest_locked(cubit_gpu_table *t, Index *ix, const uint32_t *values, uint32_t one_value, const int64_t *rows, uint64_t n,
                   uint32_t drop_value) {
 	DeltaSet &d = ix->delta;
+	{
+		int src = delta_settle_locked(t, ix); // counts of an earlier add_delta_pairs (and its merge-back decision)
+		if (src) {
+			return src;
+		}
+	}
 	const uint64_t n_keys = (uint64_t)ix->card * t->n_seg;
 	if (n_keys > (1ull << 30)) {
 		return fail(CUBIT_ESTATE, "pending deltas need cardinality * segments <= 2^30 (have %llu)", (unsigned long long)n_keys);
@@ -122,17 +128,33 @@ int ingest_locked(cubit_gpu_table *t, Index *ix, const uint32_t *values, uint32_
 	d.n_ent = n_total;
 	d.cap_ent = n_total;
 	d.n_seg = t->n_seg;
+	if (values) { // per-value counts come back from the device (no 10 M-iteration host loop): see delta_settle_locked
+		if (!d.h_voff) {
+			CU_TRY(cudaMallocHost((void **)&d.h_voff, ((size_t)ix->card + 1) * 4));
+			CU_TRY(cudaEventCreateWithFlags(&d.ev_voff, cudaEventDisableTiming));
+		}
+		uint32_t *d_voff = nullptr;
+		CU_TRY(cudaMallocAsync((void **)&d_voff, ((size_t)ix->card + 1) * 4, st));
+		CU_TRY(launch_delta_value_offsets(new_off, t->n_seg, ix->card, d_voff, st));
+		t->launches++;
+		CU_TRY(cudaMemcpyAsync(d.h_voff, d_voff, ((size_t)ix->card + 1) * 4, cudaMemcpyDeviceToHost, st));
+		CU_TRY(cudaEventRecord(d.ev_voff, st));
+		cudaFreeAsync(d_voff, st);
+		d.voff_pending = true;
+	}
 	return CUBIT_OK;
 }
 
 // the merge-back rule ("compaction of D_i into B_i past a threshold"): once the pending entries of
 // any touched value outweigh merge_fraction of its bitvector, scans would read more delta than data — fold them in
 int maybe_auto_merge(cubit_gpu_table *t, Index *ix, const std::vector<uint32_t> &touched) {
-	if (ix->merge_fraction <= 0) {
+	if (ix->merge_fraction <= 0 || ix->delta.n_ent == 0) {
 		return CUBIT_OK;
 	}
 	const double limit = ix->merge_fraction * (double)t->n_words * 8.0;
-	for (uint32_t v : touched) {
+	const uint32_t n_check = touched.empty() ? ix->card : (uint32_t)touched.size();
+	for (uint32_t i = 0; i < n_check; i++) {
+		const uint32_t v = touched.empty() ? i : touched[i];
 		if ((double)ix->delta.rows[v] * sizeof(DeltaEnt) > limit) {
 			bool any = false;
 			int rc = merge_deltas_locked(t, ix, &any);
@@ -196,10 +218,27 @@ int sharded_add(cubit_gpu_table *t, int32_t index_id, const uint32_t *values, ui
 
 namespace cubit {
 
+int delta_settle_locked(cubit_gpu_table *t, Index *ix) {
+	DeltaSet &d = ix->delta;
+	if (!d.voff_pending) {
+		return CUBIT_OK;
+	}
+	CU_TRY(cudaEventSynchronize(d.ev_voff));
+	d.voff_pending = false;
+	for (uint32_t v = 0; v < ix->card; v++) {
+		d.rows[v] = d.h_voff[v + 1] - d.h_voff[v];
+	}
+	return maybe_auto_merge(t, ix, {});
+}
+
 int merge_deltas_locked(cubit_gpu_table *t, Index *ix, bool *any) {
 	DeltaSet &d = ix->delta;
 	if (any) {
 		*any = false;
+	}
+	if (d.voff_pending) { // (the counts are about to be zeroed: only the event has to be retired)
+		CU_TRY(cudaEventSynchronize(d.ev_voff));
+		d.voff_pending = false;
 	}
 	if (!d.d_off || d.n_ent == 0) {
 		return CUBIT_OK;
@@ -260,6 +299,10 @@ int merge_deltas_locked(cubit_gpu_table *t, Index *ix, bool *any) {
 int delta_rows_locked(cubit_gpu_table *t, Index *ix, uint32_t v, std::vector<int64_t> &rows) {
 	rows.clear();
 	DeltaSet &d = ix->delta;
+	int src = delta_settle_locked(t, ix);
+	if (src) {
+		return src;
+	}
 	if (!d.d_off || d.rows[v] == 0) {
 		return CUBIT_OK;
 	}
@@ -382,26 +425,15 @@ extern "C" int cubit_gpu_add_delta_pairs(cubit_gpu_table *t, int32_t index_id, c
 	if (!ix) {
 		return fail(CUBIT_EINVAL, "bad index %d", index_id);
 	}
-	std::vector<uint64_t> per_value(ix->card, 0);
+	uint32_t vmax = 0;
 	for (uint64_t i = 0; i < n; i++) {
-		if (value_ids[i] >= ix->card) {
-			return fail(CUBIT_EINVAL, "pair %llu: value %u outside the index (cardinality %u)", (unsigned long long)i,
-			            value_ids[i], ix->card);
-		}
-		per_value[value_ids[i]]++;
+		vmax = std::max(vmax, value_ids[i]);
 	}
-	rc = ingest_locked(t, ix, value_ids, 0, rows, n, 0xffffffffu);
-	if (rc) {
-		return rc;
+	if (vmax >= ix->card) {
+		return fail(CUBIT_EINVAL, "a pair names value %u outside the index (cardinality %u)", vmax, ix->card);
 	}
-	std::vector<uint32_t> touched;
-	for (uint32_t v = 0; v < ix->card; v++) {
-		if (per_value[v]) {
-			ix->delta.rows[v] += per_value[v];
-			touched.push_back(v);
-		}
-	}
-	return maybe_auto_merge(t, ix, touched);
+	// the per-value counts (planning bounds, merge-back rule) come back from the device: delta_settle_locked
+	return ingest_locked(t, ix, value_ids, 0, rows, n, 0xffffffffu);
 	ABI_END
 }
 
@@ -427,6 +459,10 @@ extern "C" int cubit_gpu_set_delta(cubit_gpu_table *t, int32_t index_id, uint32_
 	Index *ix = get_index(t, index_id);
 	if (!ix || value_id >= ix->card) {
 		return fail(CUBIT_EINVAL, "bad (index %d, value %u)", index_id, value_id);
+	}
+	rc = delta_settle_locked(t, ix);
+	if (rc) {
+		return rc;
 	}
 	if (n == 0 && ix->delta.rows[value_id] == 0) {
 		return CUBIT_OK;

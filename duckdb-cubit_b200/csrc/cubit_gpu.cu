@@ -98,6 +98,10 @@ void free_delta(DeltaSet &d) {
 	d.n_ent = d.cap_ent = 0;
 	d.n_seg = 0;
 	std::fill(d.rows.begin(), d.rows.end(), 0);
+	if (d.ev_voff) {
+		cudaEventSynchronize(d.ev_voff);
+	}
+	d.voff_pending = false;
 }
 
 void free_compressed(CompressedStore &cs) {
@@ -240,6 +244,12 @@ extern "C" int cubit_gpu_destroy(cubit_gpu_table *t) {
 			continue;
 		}
 		free_delta(ix->delta);
+		if (ix->delta.h_voff) {
+			cudaFreeHost(ix->delta.h_voff);
+		}
+		if (ix->delta.ev_voff) {
+			cudaEventDestroy(ix->delta.ev_voff);
+		}
 		free_compressed(ix->cs);
 		if (ix->d_bits) {
 			cudaFree(ix->d_bits);
@@ -739,6 +749,10 @@ extern "C" int cubit_gpu_index_info(cubit_gpu_table *t, int32_t index_id, cubit_
 	Index *ix = get_index(t, index_id);
 	if (!ix) {
 		return fail(CUBIT_EINVAL, "bad index %d", index_id);
+	}
+	int src = delta_settle_locked(t, ix);
+	if (src) {
+		return src;
 	}
 	info->cardinality = ix->card;
 	info->compressed = ix->compressed ? 1u : 0u;

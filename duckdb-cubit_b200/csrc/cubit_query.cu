@@ -167,7 +167,10 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 				return fail(CUBIT_EINVAL, "group %u ref %u: bad (index %d, value %u)", g, i, grp.refs[i].index_id,
 				            grp.refs[i].value_id);
 			}
-			int rc = refresh_counts(t, ix);
+			int rc = delta_settle_locked(t, ix);
+			if (rc == CUBIT_OK) {
+				rc = refresh_counts(t, ix);
+			}
 			if (rc) {
 				return rc;
 			}

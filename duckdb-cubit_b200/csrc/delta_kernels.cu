@@ -231,6 +231,14 @@ __global__ void __launch_bounds__(kThreads) cubit_delta_restride_ent_kernel(Delt
 	}
 }
 
+__global__ void cubit_delta_value_offsets_kernel(const uint32_t *__restrict__ off, uint32_t n_seg, uint32_t card,
+                                                uint32_t *__restrict__ out) {
+	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v <= card) {
+		out[v] = off[(uint64_t)v * n_seg];
+	}
+}
+
 unsigned grid_for(uint64_t n, int sm_count) {
 	uint64_t g = (n + kThreads - 1) / kThreads;
 	const uint64_t cap = (uint64_t)sm_count * 16;
@@ -283,6 +291,11 @@ cudaError_t launch_delta_apply(const DeltaEnt *ent, uint64_t e0, uint64_t e1, ui
 	}
 	cubit_delta_apply_kernel<<<grid_for(e1 - e0, sm_count), kThreads, 0, stream>>>(
 	    ent, e0, e1, n_seg, seg_words, reinterpret_cast<unsigned long long *>(bits), words_per_bv, value_base);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_delta_value_offsets(const uint32_t *off, uint32_t n_seg, uint32_t card, uint32_t *out, cudaStream_t stream) {
+	cubit_delta_value_offsets_kernel<<<(card + 1 + 255) / 256, 256, 0, stream>>>(off, n_seg, card, out);
 	return cudaGetLastError();
 }
 

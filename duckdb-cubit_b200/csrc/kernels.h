@@ -209,6 +209,8 @@ cudaError_t launch_delta_ingest(const DeltaIngest &a, int sm_count, cudaStream_t
 cudaError_t launch_delta_apply(const DeltaEnt *ent, uint64_t e0, uint64_t e1, uint32_t n_seg, uint32_t seg_words,
                                uint64_t *bits, uint64_t words_per_bv, uint32_t value_base, int sm_count,
                                cudaStream_t stream);
+// out[v] = off[v * n_seg] for v in [0, card] — the per-value entry ranges of the CSR
+cudaError_t launch_delta_value_offsets(const uint32_t *off, uint32_t n_seg, uint32_t card, uint32_t *out, cudaStream_t stream);
 cudaError_t launch_delta_restride(const uint32_t *old_off, uint32_t *new_off, DeltaEnt *ent, uint64_t n_ent, uint32_t card,
                                   uint32_t old_n_seg, uint32_t new_n_seg, int sm_count, cudaStream_t stream);
 // compressed indexes (container_kernels.cu)

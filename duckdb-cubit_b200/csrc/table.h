@@ -72,6 +72,11 @@ struct DeltaSet {
 	uint64_t cap_ent = 0;      // entries allocated in d_ent
 	uint32_t n_seg = 0;        // the segment count the keys were computed with
 	std::vector<uint64_t> rows; // [card] pending flipped rows per value (upper bound of the rows they can add)
+	// add_delta_pairs does not count its pairs per value on the host: the per-value entry offsets of the new CSR are
+	// copied back (card + 1 words, page-locked) behind the ingestion and folded into `rows` by delta_settle_locked
+	uint32_t *h_voff = nullptr;
+	cudaEvent_t ev_voff = nullptr;
+	bool voff_pending = false;
 };
 
 // Roaring-style compressed storage of an index: one container per (value, segment) —
@@ -212,6 +217,8 @@ int expand_value_locked(cubit_gpu_table *t, Index *ix, uint32_t v, uint64_t *dst
 int compress_value_locked(cubit_gpu_table *t, Index *ix, uint32_t v0, uint32_t nv, const uint64_t *src);
 // pending-delta rows of one value as a host list (persistence)
 int delta_rows_locked(cubit_gpu_table *t, Index *ix, uint32_t v, std::vector<int64_t> &rows);
+// pending per-value counts of the last add_delta_pairs → rows[], then the automatic merge-back rule (caller holds t->mu)
+int delta_settle_locked(cubit_gpu_table *t, Index *ix);
 // re-key the delta CSR after the segment count changed (append)
 int delta_restride_locked(cubit_gpu_table *t, Index *ix, uint32_t new_n_seg);
 

@@ -7,42 +7,69 @@
 // reproduced, annotated, in INTEGRATION.md.  Nothing here is copied from the reference; it USES its
 // public extension API:
 //   ExtensionUtil::RegisterFunction          src/include/duckdb/main/extension_util.hpp:34
-//   TableFunction{bind, init_global, function} src/include/duckdb/function/table_function.hpp:184-301
-//   DataChunk / FlatVector                   src/include/duckdb/common/types/{data_chunk,vector}.hpp
+//   TableFunction{bind, init_global, init_local, function, get_batch_index}
+//                                            src/include/duckdb/function/table_function.hpp:184-301
+//   IndexTypeSet::RegisterIndexType          src/execution/index/index_type_set.cpp:24-30
+//   BoundIndex (Append / Delete / Insert / CommitDrop / GetStorageInfo)
+//                                            src/include/duckdb/execution/index/bound_index.hpp:67-126
+//   OptimizerExtension                       src/include/duckdb/optimizer/optimizer_extension.hpp:31-43
+//
+// The GPU-resident mirror of a table is a registered INDEX TYPE ("CUBIT"): CALL cubit_load(...) creates an index
+// catalog entry of that type on the table and puts a CubitIndex (a BoundIndex) into the table's own index list, next
+// to its ART indexes.  From then on DuckDB's DML path maintains it like any index —
+//   INSERT            → DataTable::AppendToIndexes → CubitIndex::Append  → cubit_gpu_append_rows
+//   DELETE            → cleanup of the committed delete → DataTable::RemoveFromIndexes → CubitIndex::Delete
+//                       → cubit_gpu_add_delta_pairs (the rows' bits are flipped in the pending deltas D_v)
+//   UPDATE of a resident column → the binder turns it into DELETE + INSERT because an index covers the column
+//                       (BoundIndex::IndexIsUpdated) → both of the above
+//   DROP TABLE / DROP INDEX → CommitDrop → the GPU memory is released
+//   CHECKPOINT        → GetStorageInfo → the index images (cubit_gpu_index_serialize) are written to blocks
+//   ATTACH / restart  → IndexType::create_instance → the images are read back and handed to
+//                       cubit_gpu_index_deserialize when the table is first used
+// — and there is no registry keyed by table name: the accelerator is found through the table's own index list, so
+// dropping, re-creating, altering or shadowing a table can never route a query to another table's rows.
 //
 // SQL surface:
-//   CALL cubit_load('lineitem', 'l_quantity', 1, 50);      -- build the GPU index + upload BIGINT columns
+//   CALL cubit_load('lineitem', 'l_quantity', 1, 50);      -- build the GPU index + upload the GPU-eligible columns
 //   SELECT sum(l_extendedprice) FROM cubit_scan('lineitem', 24, 24);   -- rowid + the uploaded columns
 //   SELECT * FROM cubit_agg('lineitem', 24, 24, 'l_extendedprice');    -- aggregate push-down: one row
-// and, transparently (OptimizerExtension, src/include/duckdb/optimizer/optimizer_extension.hpp:31-43): a plain
+// and, transparently (OptimizerExtension): a plain
 //   SELECT sum(l_extendedprice) FROM lineitem WHERE l_quantity BETWEEN 10 AND 19;
-// whose pushed-down filters touch only the indexed column is re-pointed at the GPU scan, the way
+// whose pushed-down filters touch only indexed columns is re-pointed at the GPU scan, the way
 // TableScanPushdownComplexFilter re-points a seq_scan at ART's index_scan (src/function/table/table_scan.cpp:296-370).
 #include "duckdb.hpp"
-#include "duckdb/function/table_function.hpp"
-#include "duckdb/main/extension_util.hpp"
+#include "duckdb/catalog/catalog_entry/duck_index_entry.hpp"
+#include "duckdb/catalog/catalog_entry/duck_table_entry.hpp"
+#include "duckdb/catalog/catalog_entry/table_catalog_entry.hpp"
 #include "duckdb/common/types/data_chunk.hpp"
 #include "duckdb/common/types/date.hpp"
 #include "duckdb/common/types/vector.hpp"
-#include "duckdb/catalog/catalog_entry/table_catalog_entry.hpp"
+#include "duckdb/execution/index/bound_index.hpp"
+#include "duckdb/execution/index/index_type.hpp"
+#include "duckdb/execution/index/index_type_set.hpp"
+#include "duckdb/function/table_function.hpp"
 #include "duckdb/main/config.hpp"
+#include "duckdb/main/extension_util.hpp"
 #include "duckdb/optimizer/optimizer_extension.hpp"
-#include "duckdb/planner/filter/conjunction_filter.hpp"
-#include "duckdb/planner/filter/constant_filter.hpp"
+#include "duckdb/parser/expression/columnref_expression.hpp"
+#include "duckdb/parser/parsed_data/create_index_info.hpp"
 #include "duckdb/planner/expression/bound_aggregate_expression.hpp"
 #include "duckdb/planner/expression/bound_cast_expression.hpp"
 #include "duckdb/planner/expression/bound_columnref_expression.hpp"
 #include "duckdb/planner/expression/bound_function_expression.hpp"
+#include "duckdb/planner/filter/conjunction_filter.hpp"
+#include "duckdb/planner/filter/constant_filter.hpp"
 #include "duckdb/planner/operator/logical_aggregate.hpp"
-#include "duckdb/planner/operator/logical_delete.hpp"
 #include "duckdb/planner/operator/logical_get.hpp"
-#include "duckdb/planner/operator/logical_insert.hpp"
-#include "duckdb/planner/operator/logical_update.hpp"
 #include "duckdb/storage/block_manager.hpp"
 #include "duckdb/storage/buffer_manager.hpp"
 #include "duckdb/storage/data_table.hpp"
+#include "duckdb/storage/table/data_table_info.hpp"
 #include "duckdb/storage/table_io_manager.hpp"
 #include "duckdb/storage/table_storage_info.hpp"
+#include "duckdb/parser/qualified_name.hpp"
+#include "duckdb/transaction/duck_transaction.hpp"
+#include "duckdb/transaction/meta_transaction.hpp"
 
 #include "cubit_gpu.h"
 
@@ -50,30 +77,101 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
-#include <unordered_map>
 
 namespace duckdb {
 
-// ---------------------------------------------------------------- registry of GPU-resident tables
+static constexpr const char *CUBIT_INDEX_TYPE = "CUBIT";
+
+static void CubitCheck(int rc) {
+	if (rc != CUBIT_OK) {
+		// errors cross the C-ABI as codes; here they become the exceptions DuckDB expects
+		throw InvalidInputException("cubit_gpu: %s", cubit_gpu_last_error());
+	}
+}
+
+// ---------------------------------------------------------------- the GPU-resident mirror of one table
 // one CUBIT index of a GPU-resident table: value v of `key_table_column` ↔ bitvector v - base_value
 struct CubitGpuIndex {
 	int32_t index_id = -1;
 	int64_t base_value = 0;
 	uint32_t cardinality = 0;
 	idx_t key_table_column = 0; // table column index of the indexed column
+	idx_t key_gpu_column = 0;   // ... and its GPU column id
 	// binned index (cubit_load(..., bin := 'month' | '<width>')): bitvector b covers the key values in
 	// [bin_lo[b], bin_lo[b + 1]) (cardinality + 1 boundaries); a range predicate is answered by it only when both
 	// of its ends fall on boundaries.  Empty = one bitvector per value.
 	vector<int64_t> bin_lo;
+	// bitvector of raw key `v`, or -1 when the index does not cover it (NULL keys: INT64_MIN)
+	int64_t ValueId(int64_t v) const {
+		if (bin_lo.empty()) {
+			return v >= base_value && v < base_value + NumericCast<int64_t>(cardinality) ? v - base_value : -1;
+		}
+		if (v < bin_lo.front() || v >= bin_lo.back()) {
+			return -1;
+		}
+		return (std::upper_bound(bin_lo.begin(), bin_lo.end(), v) - bin_lo.begin()) - 1;
+	}
 };
+
+// what CALL cubit_load asked for: kept in the index catalog entry's options, so it survives a restart
+struct CubitIndexSpec {
+	string key;
+	int64_t base = 0;
+	uint32_t cardinality = 0;
+	string bin; // "" = one bitvector per value; "month" (DATE keys); or a positive integer bin width
+};
+
+static string CubitEncodeSpecs(const vector<CubitIndexSpec> &specs) {
+	string out;
+	for (auto &s : specs) {
+		out += s.key + "\x1f" + std::to_string(s.base) + "\x1f" + std::to_string(s.cardinality) + "\x1f" + s.bin + "\x1e";
+	}
+	return out;
+}
+
+static vector<CubitIndexSpec> CubitDecodeSpecs(const string &text) {
+	vector<CubitIndexSpec> out;
+	for (auto &rec : StringUtil::Split(text, '\x1e')) {
+		if (rec.empty()) {
+			continue;
+		}
+		vector<string> f;
+		idx_t at = 0;
+		while (true) { // (StringUtil::Split drops empty fields: the last one — the bin — is often empty)
+			auto next = rec.find('\x1f', at);
+			f.push_back(rec.substr(at, next == string::npos ? string::npos : next - at));
+			if (next == string::npos) {
+				break;
+			}
+			at = next + 1;
+		}
+		if (f.size() != 4) {
+			throw InvalidInputException("cubit: malformed index options");
+		}
+		CubitIndexSpec s;
+		s.key = f[0];
+		s.base = std::stoll(f[1]);
+		s.cardinality = NumericCast<uint32_t>(std::stoll(f[2]));
+		s.bin = f[3];
+		out.push_back(s);
+	}
+	return out;
+}
 
 struct CubitGpuTable {
 	cubit_gpu_table *handle = nullptr;
 	vector<CubitGpuIndex> indexes; // [0] = the one cubit_scan(table, lo, hi) / cubit_agg address; CALL cubit_load again
 	                               // with another key column to add more (conjunctions across them are rewritten)
-	vector<string> column_names; // uploaded BIGINT columns, column id = position
+	vector<string> column_names; // uploaded columns (raw int64 on the GPU), GPU column id = position
 	vector<idx_t> table_column;  // table column index of every uploaded column
-	idx_t row_count = 0;
+	vector<LogicalType> column_types;
+	idx_t row_count = 0; // rows resident on the GPU = the table's row-id high-water mark at that point
+	bool loaded = false;
+	// false once DML produced something the GPU copy cannot represent (a key outside the indexed domain, row ids that
+	// do not continue the table): scans then keep the vanilla path until the next cubit_load
+	bool usable = true;
+	string unusable_reason;
+	std::mutex dml_lock; // DML callbacks and (re)loads
 	// page-locked staging buffers (one DataChunk window each) recycled across scans: allocating and freeing
 	// pinned memory costs milliseconds, far more than a scan
 	std::mutex pool_lock;
@@ -99,56 +197,94 @@ struct CubitGpuTable {
 			host_pool.push_back(p);
 		}
 	}
-	~CubitGpuTable() {
+	void Unload() {
 		for (auto p : host_pool) {
 			cubit_gpu_free_host(p);
 		}
+		host_pool.clear();
 		cubit_gpu_destroy(handle);
+		handle = nullptr;
+		indexes.clear();
+		loaded = false;
+		row_count = 0;
+	}
+	~CubitGpuTable() {
+		Unload();
 	}
 };
 
-static std::mutex cubit_registry_lock;
-static std::unordered_map<string, shared_ptr<CubitGpuTable>> cubit_registry;
+static std::atomic<idx_t> cubit_dml_append_rows {0}, cubit_dml_delta_pairs {0}, cubit_image_loads {0};
+idx_t CubitImageLoads() {
+	return cubit_image_loads.load();
+}
+idx_t CubitDmlAppendedRows() {
+	return cubit_dml_append_rows.load();
+}
+idx_t CubitDmlDeltaPairs() {
+	return cubit_dml_delta_pairs.load();
+}
 
-static void CubitCheck(int rc) {
-	if (rc != CUBIT_OK) {
-		// errors cross the C-ABI as codes; here they become the exceptions DuckDB expects
-		throw InvalidInputException("cubit_gpu: %s", cubit_gpu_last_error());
+// raw int64 of every row of `vec` as the GPU holds it: integers widened, DECIMALs as their unscaled value whatever
+// their physical width (DECIMAL(15,2) is int64 cents, dbgen.cpp:48-50; DECIMAL(4,2) is an int16 — a numeric cast
+// would ROUND 0.05 to 0), DATEs as days since 1970-01-01; NULL rows carry INT64_MIN (outside every indexed domain)
+static void CubitRawInt64(Vector &vec, idx_t count, int64_t *out, uint64_t *valid_words,
+                          idx_t valid_bit0, bool &any_null) {
+	Vector as_bigint(LogicalType::BIGINT);
+	const auto &type = vec.GetType();
+	if (type.id() == LogicalTypeId::DECIMAL) {
+		switch (type.InternalType()) {
+		case PhysicalType::INT64:
+			as_bigint.Reinterpret(vec);
+			break;
+		case PhysicalType::INT32: {
+			Vector as_int(LogicalType::INTEGER);
+			as_int.Reinterpret(vec);
+			VectorOperations::DefaultCast(as_int, as_bigint, count);
+			break;
+		}
+		case PhysicalType::INT16: {
+			Vector as_small(LogicalType::SMALLINT);
+			as_small.Reinterpret(vec);
+			VectorOperations::DefaultCast(as_small, as_bigint, count);
+			break;
+		}
+		default:
+			throw InternalException("cubit: DECIMAL wider than 18 digits is not GPU eligible");
+		}
+	} else if (type.id() == LogicalTypeId::DATE) {
+		Vector as_int(LogicalType::INTEGER); // days since 1970-01-01 (date_t)
+		as_int.Reinterpret(vec);
+		VectorOperations::DefaultCast(as_int, as_bigint, count);
+	} else {
+		VectorOperations::DefaultCast(vec, as_bigint, count);
+	}
+	as_bigint.Flatten(count);
+	auto ptr = FlatVector::GetData<int64_t>(as_bigint);
+	auto &mask = FlatVector::Validity(as_bigint);
+	for (idx_t r = 0; r < count; r++) {
+		if (mask.RowIsValid(r)) {
+			out[r] = ptr[r];
+		} else {
+			out[r] = NumericLimits<int64_t>::Minimum();
+			any_null = true;
+			if (valid_words) {
+				const idx_t bit = valid_bit0 + r;
+				valid_words[bit / 64] &= ~(uint64_t(1) << (bit % 64));
+			}
+		}
 	}
 }
 
-static shared_ptr<CubitGpuTable> CubitLookup(const string &name) {
-	std::lock_guard<std::mutex> lk(cubit_registry_lock);
-	auto it = cubit_registry.find(name);
-	if (it == cubit_registry.end()) {
-		throw InvalidInputException("no CUBIT GPU index loaded for table \"%s\" (CALL cubit_load first)", name);
+static bool CubitEligibleType(const LogicalType &t) {
+	if (t.id() == LogicalTypeId::DECIMAL) {
+		return t.InternalType() == PhysicalType::INT16 || t.InternalType() == PhysicalType::INT32 ||
+		       t.InternalType() == PhysicalType::INT64;
 	}
-	return it->second;
-}
-
-// ---------------------------------------------------------------- cubit_load(table, key, base, cardinality)
-struct CubitLoadBindData : public TableFunctionData {
-	string table, key;
-	int64_t base = 0;
-	uint32_t cardinality = 0;
-	string bin; // "" = one bitvector per value; "month" (DATE keys); or a positive integer bin width
-	bool done = false;
-};
-
-static unique_ptr<FunctionData> CubitLoadBind(ClientContext &, TableFunctionBindInput &input,
-                                              vector<LogicalType> &return_types, vector<string> &names) {
-	auto bind = make_uniq<CubitLoadBindData>();
-	bind->table = input.inputs[0].GetValue<string>();
-	bind->key = input.inputs[1].GetValue<string>();
-	bind->base = input.inputs[2].GetValue<int64_t>();
-	bind->cardinality = NumericCast<uint32_t>(input.inputs[3].GetValue<int64_t>());
-	auto bin = input.named_parameters.find("bin");
-	if (bin != input.named_parameters.end()) {
-		bind->bin = bin->second.GetValue<string>();
+	if (t.id() == LogicalTypeId::DATE) {
+		return true;
 	}
-	return_types.emplace_back(LogicalType::BIGINT);
-	names.emplace_back("rows_indexed");
-	return std::move(bind);
+	return t.IsIntegral() && t.InternalType() != PhysicalType::INT128 && t.InternalType() != PhysicalType::UINT128 &&
+	       t.InternalType() != PhysicalType::UINT64;
 }
 
 // ---- storage route: hand a column's ON-DISK segments to the GPU as they are.
@@ -163,13 +299,9 @@ idx_t CubitSegmentRouteCount() {
 	return cubit_segment_columns.load();
 }
 
-static bool CubitUploadColumnSegments(ClientContext &context, const string &table, idx_t table_column,
+static bool CubitUploadColumnSegments(ClientContext &, TableCatalogEntry &entry, idx_t table_column,
                                       const LogicalType &type, cubit_gpu_table *handle, int32_t gpu_col, idx_t row_count) {
 	if (type.InternalType() != PhysicalType::INT64) {
-		return false;
-	}
-	auto &entry = Catalog::GetEntry<TableCatalogEntry>(context, INVALID_CATALOG, DEFAULT_SCHEMA, table);
-	if (!entry.IsDuckTable()) {
 		return false;
 	}
 	auto &storage = entry.GetStorage();
@@ -243,34 +375,28 @@ static bool CubitUploadColumnSegments(ClientContext &context, const string &tabl
 // uploaded raw int64, NULL rows = INT64_MIN): every non-NULL key must fall into the indexed domain — a key the
 // index does not cover would silently drop rows from rewritten scans — and binned indexes need the bin id of
 // every row (computed here, uploaded as a temporary column, indexed on the GPU, dropped).
-static CubitGpuIndex CubitBuildIndex(CubitGpuTable &gpu, idx_t gcol, const CubitLoadBindData &bind, const LogicalType &key_type) {
+static CubitGpuIndex CubitBuildIndex(CubitGpuTable &gpu, idx_t gcol, const CubitIndexSpec &spec, const LogicalType &key_type,
+                                     const vector<uint8_t> *image) {
 	CubitGpuIndex ix;
 	ix.key_table_column = gpu.table_column[gcol];
-	vector<int64_t> vals(gpu.row_count);
-	if (gpu.row_count) {
-		CubitCheck(cubit_gpu_download_column(gpu.handle, NumericCast<int32_t>(gcol), vals.data(), 8, gpu.row_count));
-	}
+	ix.key_gpu_column = gcol;
 	const int64_t null_key = NumericLimits<int64_t>::Minimum();
-	if (bind.bin.empty()) {
-		ix.base_value = bind.base;
-		ix.cardinality = bind.cardinality;
-		for (auto v : vals) {
-			if (v != null_key && (v < ix.base_value || v >= ix.base_value + ix.cardinality)) {
-				throw InvalidInputException("cubit_load: key %lld of \"%s\" lies outside the indexed domain [%lld, %lld)",
-				                            (long long)v, bind.key, (long long)ix.base_value,
-				                            (long long)(ix.base_value + ix.cardinality));
-			}
+	// ---- the domain (bin boundaries) is a function of the spec alone, except for month bins, which follow the data
+	vector<int64_t> vals;
+	auto fetch_vals = [&]() {
+		if (vals.empty() && gpu.row_count) {
+			vals.resize(gpu.row_count);
+			CubitCheck(cubit_gpu_download_column(gpu.handle, NumericCast<int32_t>(gcol), vals.data(), 8, gpu.row_count));
 		}
-		CubitCheck(cubit_gpu_index_create(gpu.handle, ix.cardinality, &ix.index_id));
-		CubitCheck(cubit_gpu_index_build(gpu.handle, ix.index_id, NumericCast<int32_t>(gcol), ix.base_value));
-		return ix;
-	}
-	// ---- binned
-	vector<int64_t> bins(vals.size(), null_key);
-	if (bind.bin == "month") {
+	};
+	if (spec.bin.empty()) {
+		ix.base_value = spec.base;
+		ix.cardinality = spec.cardinality;
+	} else if (spec.bin == "month") {
 		if (key_type.id() != LogicalTypeId::DATE) {
 			throw InvalidInputException("cubit_load: bin := 'month' needs a DATE key column");
 		}
+		fetch_vals();
 		int64_t lo = NumericLimits<int64_t>::Maximum(), hi = NumericLimits<int64_t>::Minimum();
 		for (auto v : vals) {
 			if (v != null_key) {
@@ -289,46 +415,502 @@ static CubitGpuIndex CubitBuildIndex(CubitGpuTable &gpu, idx_t gcol, const Cubit
 			const int32_t mm = m0 - 1 + b;
 			ix.bin_lo.push_back(Date::FromDate(y0 + mm / 12, mm % 12 + 1, 1).days);
 		}
-		for (idx_t r = 0; r < vals.size(); r++) {
-			if (vals[r] != null_key) {
-				int32_t y, m, d;
-				Date::Convert(date_t(NumericCast<int32_t>(vals[r])), y, m, d);
-				bins[r] = (y - y0) * 12 + (m - m0);
-			}
-		}
+		ix.base_value = 0;
+		ix.cardinality = NumericCast<uint32_t>(ix.bin_lo.size() - 1);
 	} else {
 		int64_t width = 0;
 		try {
-			width = std::stoll(bind.bin);
+			width = std::stoll(spec.bin);
 		} catch (...) {
 			width = 0;
 		}
-		if (width <= 0 || bind.cardinality == 0) {
+		if (width <= 0 || spec.cardinality == 0) {
 			throw InvalidInputException("cubit_load: bin must be 'month' or a positive integer width (with base and cardinality)");
 		}
-		for (uint32_t b = 0; b <= bind.cardinality; b++) {
-			ix.bin_lo.push_back(bind.base + NumericCast<int64_t>(b) * width);
+		for (uint32_t b = 0; b <= spec.cardinality; b++) {
+			ix.bin_lo.push_back(spec.base + NumericCast<int64_t>(b) * width);
 		}
-		for (idx_t r = 0; r < vals.size(); r++) {
-			if (vals[r] == null_key) {
-				continue;
-			}
-			if (vals[r] < ix.bin_lo.front() || vals[r] >= ix.bin_lo.back()) {
-				throw InvalidInputException("cubit_load: key %lld of \"%s\" lies outside the binned domain [%lld, %lld)",
-				                            (long long)vals[r], bind.key, (long long)ix.bin_lo.front(), (long long)ix.bin_lo.back());
-			}
-			bins[r] = (vals[r] - bind.base) / width;
+		ix.base_value = 0;
+		ix.cardinality = spec.cardinality;
+	}
+	// ---- a checkpointed image of this index (GetStorageInfo) replaces the build when it describes this table
+	if (image && !image->empty()) {
+		if (cubit_gpu_index_deserialize(gpu.handle, image->data(), image->size(), &ix.index_id) == CUBIT_OK) {
+			cubit_image_loads++;
+			return ix;
+		}
+		ix.index_id = -1; // stale image (the table changed since the checkpoint): rebuild from the column
+	}
+	fetch_vals();
+	for (auto v : vals) {
+		if (v != null_key && ix.ValueId(v) < 0) {
+			throw InvalidInputException("cubit_load: key %lld of \"%s\" lies outside the indexed domain", (long long)v, spec.key);
 		}
 	}
-	ix.base_value = 0;
-	ix.cardinality = NumericCast<uint32_t>(ix.bin_lo.size() - 1);
+	CubitCheck(cubit_gpu_index_create(gpu.handle, ix.cardinality, &ix.index_id));
+	if (ix.bin_lo.empty()) {
+		CubitCheck(cubit_gpu_index_build(gpu.handle, ix.index_id, NumericCast<int32_t>(gcol), ix.base_value));
+		return ix;
+	}
+	vector<int64_t> bins(vals.size(), null_key);
+	for (idx_t r = 0; r < vals.size(); r++) {
+		if (vals[r] != null_key) {
+			bins[r] = ix.ValueId(vals[r]);
+		}
+	}
 	const int32_t tmp_col = NumericCast<int32_t>(gpu.column_names.size()); // first unused GPU column id
 	CubitCheck(cubit_gpu_upload_column(gpu.handle, tmp_col, bins.data(), 8, gpu.row_count));
-	CubitCheck(cubit_gpu_index_create(gpu.handle, ix.cardinality, &ix.index_id));
 	const int rc = cubit_gpu_index_build(gpu.handle, ix.index_id, tmp_col, 0);
 	cubit_gpu_drop_column(gpu.handle, tmp_col);
 	CubitCheck(rc);
 	return ix;
+}
+
+// ---------------------------------------------------------------- the registered index type
+class CubitIndex : public BoundIndex {
+public:
+	CubitIndex(const string &name, const vector<column_t> &column_ids, TableIOManager &table_io_manager,
+	           const vector<unique_ptr<Expression>> &unbound_expressions, AttachedDatabase &db, vector<CubitIndexSpec> specs_p)
+	    : BoundIndex(name, CUBIT_INDEX_TYPE, IndexConstraintType::NONE, column_ids, table_io_manager, unbound_expressions, db),
+	      gpu(make_shared_ptr<CubitGpuTable>()), specs(std::move(specs_p)) {
+	}
+
+	shared_ptr<CubitGpuTable> gpu;
+	vector<CubitIndexSpec> specs;
+	// index images: read from the database file at attach (consumed by the first load), refreshed at every checkpoint
+	vector<vector<uint8_t>> images;
+	vector<block_id_t> image_blocks; // blocks holding the images of the last checkpoint
+
+	// IndexType::create_instance (index_type.hpp): binding after ATTACH / WAL replay.  The GPU copy is materialised
+	// lazily, at the first statement that can use it (the optimizer hook has a ClientContext; this callback does not).
+	static unique_ptr<BoundIndex> Create(CreateIndexInput &input) {
+		vector<CubitIndexSpec> specs;
+		auto opt = input.options.find("cubit_specs");
+		if (opt != input.options.end()) {
+			specs = CubitDecodeSpecs(opt->second.GetValue<string>());
+		}
+		auto index = make_uniq<CubitIndex>(input.name, input.column_ids, input.table_io_manager, input.unbound_expressions, input.db,
+		                                   std::move(specs));
+		index->ReadImages(input.storage_info); // (also recovers the specs: this version's IndexCatalogEntry::GetInfo
+		                                       // drops `options` at checkpoint, index_catalog_entry.cpp:14-39)
+		return std::move(index);
+	}
+
+	// ---- DML (bound_index.hpp:71-97)
+	// INSERT: rows arrive in the table's column layout with their final row ids (DataTable::AppendToIndexes,
+	// data_table.cpp:1000-1040; for transaction-local appends at commit, LocalStorage::AppendToIndexes)
+	ErrorData Append(IndexLock &, DataChunk &entries, Vector &row_identifiers) override {
+		std::lock_guard<std::mutex> lk(gpu->dml_lock);
+		if (!gpu->loaded || entries.size() == 0) {
+			return ErrorData(); // not resident (yet): the load reads the table as it is then
+		}
+		try {
+			AppendLocked(entries, row_identifiers);
+		} catch (std::exception &ex) {
+			// the GPU copy is an accelerator: it never fails the user's statement, it steps aside
+			gpu->usable = false;
+			gpu->unusable_reason = ErrorData(ex).Message();
+		}
+		return ErrorData();
+	}
+	ErrorData Insert(IndexLock &lock, DataChunk &input, Vector &row_identifiers) override {
+		return Append(lock, input, row_identifiers);
+	}
+	// DELETE (and the delete half of an UPDATE): called when the committed delete is cleaned up
+	// (CleanupState::CleanupDelete → DataTable::RemoveFromIndexes → RowGroupCollection::RemoveFromIndexes,
+	// row_group_collection.cpp:526-589) and when an append is reverted (data_table.cpp:962-980)
+	void Delete(IndexLock &, DataChunk &entries, Vector &row_identifiers) override {
+		std::lock_guard<std::mutex> lk(gpu->dml_lock);
+		if (!gpu->loaded || entries.size() == 0) {
+			return;
+		}
+		try {
+			DeleteLocked(entries, row_identifiers);
+		} catch (std::exception &ex) {
+			gpu->usable = false;
+			gpu->unusable_reason = ErrorData(ex).Message();
+		}
+	}
+	void VerifyAppend(DataChunk &) override {
+	}
+	void VerifyAppend(DataChunk &, ConflictManager &) override {
+	}
+	void CheckConstraintsForChunk(DataChunk &, ConflictManager &) override {
+	}
+	void CommitDrop(IndexLock &) override {
+		std::lock_guard<std::mutex> lk(gpu->dml_lock);
+		gpu->Unload();
+		auto &block_manager = table_io_manager.GetIndexBlockManager();
+		for (auto id : image_blocks) {
+			block_manager.MarkBlockAsModified(id);
+		}
+		image_blocks.clear();
+		images.clear();
+	}
+	bool MergeIndexes(IndexLock &, BoundIndex &) override {
+		return false;
+	}
+	void Vacuum(IndexLock &) override {
+	}
+	idx_t GetInMemorySize(IndexLock &) override {
+		return 0; // device memory, not DuckDB's buffer pool
+	}
+	string VerifyAndToString(IndexLock &, const bool) override {
+		return "CUBIT index (GPU resident)";
+	}
+	string GetConstraintViolationMessage(VerifyExistenceType, idx_t, DataChunk &) override {
+		return "CUBIT indexes carry no constraint";
+	}
+
+	// ---- persistence (bound_index.hpp:117-118, IndexStorageInfo; WAL: write_ahead_log.cpp:260-273, replay
+	// wal_replay.cpp:533-565).  One "allocator" per GPU index; its buffers are the index image
+	// (cubit_gpu_index_serialize) cut into block-sized pieces.  get_buffers = true (WAL): the pieces are handed over
+	// as memory; false (checkpoint): they are written to blocks here and the block pointers recorded.
+	IndexStorageInfo GetStorageInfo(const bool get_buffers) override {
+		std::lock_guard<std::mutex> lk(gpu->dml_lock);
+		RefreshImages();
+		IndexStorageInfo info(name);
+		info.root = 0;
+		auto &block_manager = table_io_manager.GetIndexBlockManager();
+		const idx_t piece = block_manager.GetBlockSize();
+		vector<block_id_t> new_blocks;
+		for (idx_t i = 0; i < MaxValue<idx_t>(1, images.size()); i++) {
+			FixedSizeAllocatorInfo alloc;
+			alloc.segment_size = i < images.size() ? images[i].size() : 0; // image bytes
+			vector<IndexBufferInfo> bufs;
+			for (idx_t at = 0; i < images.size() && at < images[i].size(); at += piece) {
+				const idx_t n = MinValue<idx_t>(piece, images[i].size() - at);
+				alloc.buffer_ids.push_back(alloc.buffer_ids.size());
+				alloc.segment_counts.push_back(1);
+				alloc.allocation_sizes.push_back(n);
+				if (get_buffers || block_manager.InMemory()) {
+					alloc.block_pointers.emplace_back();
+					bufs.emplace_back(images[i].data() + at, n);
+				} else {
+					shared_ptr<BlockHandle> block;
+					auto handle = block_manager.buffer_manager.Allocate(MemoryTag::ART_INDEX, piece, false, &block);
+					memcpy(handle.Ptr(), images[i].data() + at, n);
+					const auto id = block_manager.GetFreeBlockId();
+					block_manager.ConvertToPersistent(id, std::move(block));
+					alloc.block_pointers.emplace_back(id, 0);
+					new_blocks.push_back(id);
+				}
+			}
+			info.allocator_infos.push_back(std::move(alloc));
+			if (get_buffers) {
+				info.buffers.push_back(std::move(bufs));
+			}
+		}
+		if (!get_buffers && !block_manager.InMemory()) {
+			for (auto id : image_blocks) { // the previous checkpoint's image
+				block_manager.MarkBlockAsModified(id);
+			}
+			image_blocks = std::move(new_blocks);
+		}
+		// last "allocator": the specs (key, domain, binning of every GPU index), one character per buffer id
+		FixedSizeAllocatorInfo spec_alloc;
+		spec_alloc.segment_size = SPEC_MAGIC;
+		for (auto ch : CubitEncodeSpecs(specs)) {
+			spec_alloc.buffer_ids.push_back(static_cast<uint8_t>(ch));
+		}
+		info.allocator_infos.push_back(std::move(spec_alloc));
+		if (get_buffers) {
+			info.buffers.emplace_back();
+		}
+		return info;
+	}
+
+private:
+	static constexpr idx_t SPEC_MAGIC = 0xC0B175BEC5ULL;
+
+	void ReadImages(const IndexStorageInfo &info) {
+		auto &block_manager = table_io_manager.GetIndexBlockManager();
+		for (auto &alloc : info.allocator_infos) {
+			if (alloc.segment_size == SPEC_MAGIC) {
+				string text;
+				for (auto ch : alloc.buffer_ids) {
+					text.push_back(static_cast<char>(ch));
+				}
+				if (specs.empty()) {
+					specs = CubitDecodeSpecs(text);
+				}
+				continue;
+			}
+			vector<uint8_t> image;
+			for (idx_t j = 0; j < alloc.block_pointers.size() && j < alloc.allocation_sizes.size(); j++) {
+				if (!alloc.block_pointers[j].IsValid()) {
+					image.clear();
+					break;
+				}
+				auto block = block_manager.RegisterBlock(alloc.block_pointers[j].block_id);
+				auto handle = block_manager.buffer_manager.Pin(block);
+				image.insert(image.end(), handle.Ptr(), handle.Ptr() + alloc.allocation_sizes[j]);
+				image_blocks.push_back(alloc.block_pointers[j].block_id);
+			}
+			if (image.size() != alloc.segment_size) {
+				image.clear();
+			}
+			images.push_back(std::move(image));
+		}
+	}
+
+	// the images of the resident indexes (the checkpoint / WAL write what the GPU holds NOW, pending deltas included)
+	void RefreshImages() {
+		if (!gpu->loaded) {
+			return; // never used since attach: what was read from the file is still current
+		}
+		images.assign(gpu->indexes.size(), {});
+		for (idx_t i = 0; i < gpu->indexes.size(); i++) {
+			void *img = nullptr;
+			uint64_t bytes = 0;
+			if (cubit_gpu_index_serialize(gpu->handle, gpu->indexes[i].index_id, &img, &bytes) == CUBIT_OK) {
+				images[i].assign(static_cast<uint8_t *>(img), static_cast<uint8_t *>(img) + bytes);
+				cubit_gpu_free_image(img);
+			}
+		}
+	}
+
+	void AppendLocked(DataChunk &entries, Vector &row_identifiers) {
+		const idx_t n = entries.size();
+		row_identifiers.Flatten(n);
+		auto row_ids = FlatVector::GetData<row_t>(row_identifiers);
+		if (row_ids[0] != NumericCast<row_t>(gpu->row_count) || row_ids[n - 1] != row_ids[0] + NumericCast<row_t>(n - 1)) {
+			throw InvalidInputException("appended row ids [%lld, %lld] do not continue the %llu resident rows", (long long)row_ids[0],
+			                            (long long)row_ids[n - 1], (unsigned long long)gpu->row_count);
+		}
+		vector<vector<int64_t>> cols(gpu->column_names.size(), vector<int64_t>(n));
+		vector<cubit_append_column> ac;
+		bool any_null = false;
+		for (idx_t g = 0; g < cols.size(); g++) {
+			Vector copy(entries.data[gpu->table_column[g]]);
+			CubitRawInt64(copy, n, cols[g].data(), nullptr, 0, any_null);
+			ac.push_back(cubit_append_column {NumericCast<int32_t>(g), 8, cols[g].data()});
+		}
+		CubitCheck(cubit_gpu_append_rows(gpu->handle, n, ac.data(), NumericCast<uint32_t>(ac.size())));
+		gpu->row_count += n;
+		cubit_dml_append_rows += n;
+		if (any_null) {
+			// NULLs in appended rows: the validity masks would have to grow row by row — rare in append-mostly
+			// fact tables; the GPU copy steps aside until it is reloaded
+			throw InvalidInputException("NULL in appended rows");
+		}
+		// indexes built from a resident column were extended by the library; binned indexes (built from a
+		// temporary bin-id column) get the new rows' bits as pending deltas: 0 XOR 1
+		for (auto &ix : gpu->indexes) {
+			vector<uint32_t> values;
+			vector<int64_t> rows;
+			for (idx_t r = 0; r < n; r++) {
+				const int64_t id = ix.ValueId(cols[ix.key_gpu_column][r]);
+				if (id < 0) {
+					throw InvalidInputException("appended key %lld lies outside the indexed domain", (long long)cols[ix.key_gpu_column][r]);
+				}
+				if (!ix.bin_lo.empty()) {
+					values.push_back(NumericCast<uint32_t>(id));
+					rows.push_back(row_ids[r]);
+				}
+			}
+			if (!rows.empty()) {
+				CubitCheck(cubit_gpu_add_delta_pairs(gpu->handle, ix.index_id, values.data(), rows.data(), rows.size()));
+			}
+		}
+	}
+
+	void DeleteLocked(DataChunk &entries, Vector &row_identifiers) {
+		const idx_t n = entries.size();
+		UnifiedVectorFormat rid;
+		row_identifiers.ToUnifiedFormat(n, rid);
+		auto row_ids = UnifiedVectorFormat::GetData<row_t>(rid);
+		for (auto &ix : gpu->indexes) {
+			Vector copy(entries.data[ix.key_table_column]);
+			vector<int64_t> keys(n);
+			bool any_null = false;
+			CubitRawInt64(copy, n, keys.data(), nullptr, 0, any_null);
+			vector<uint32_t> values;
+			vector<int64_t> rows;
+			for (idx_t r = 0; r < n; r++) {
+				const row_t row = row_ids[rid.sel->get_index(r)];
+				const int64_t id = ix.ValueId(keys[r]);
+				if (id >= 0 && row >= 0 && NumericCast<idx_t>(row) < gpu->row_count) {
+					values.push_back(NumericCast<uint32_t>(id)); // the row's bit in B_v is flipped off at query time
+					rows.push_back(row);
+				}
+			}
+			if (!rows.empty()) {
+				CubitCheck(cubit_gpu_add_delta_pairs(gpu->handle, ix.index_id, values.data(), rows.data(), rows.size()));
+				cubit_dml_delta_pairs += rows.size();
+			}
+		}
+	}
+};
+
+// the table's CUBIT index, bound if necessary (after ATTACH it sits in the index list unbound until someone asks)
+static optional_ptr<CubitIndex> CubitFindIndex(ClientContext &context, TableCatalogEntry &table) {
+	if (!table.IsDuckTable()) {
+		return nullptr;
+	}
+	auto info = table.GetStorage().GetDataTableInfo();
+	bool present = false;
+	info->GetIndexes().Scan([&](Index &index) {
+		present |= index.GetIndexType() == CUBIT_INDEX_TYPE;
+		return present;
+	});
+	if (!present) {
+		return nullptr;
+	}
+	info->InitializeIndexes(context, CUBIT_INDEX_TYPE);
+	optional_ptr<CubitIndex> found;
+	info->GetIndexes().Scan([&](Index &index) {
+		if (index.GetIndexType() == CUBIT_INDEX_TYPE && index.IsBound()) {
+			found = &index.Cast<CubitIndex>();
+		}
+		return found != nullptr;
+	});
+	return found;
+}
+
+static TableCatalogEntry &CubitResolveTable(ClientContext &context, const string &name) {
+	auto qname = QualifiedName::Parse(name);
+	return Catalog::GetEntry<TableCatalogEntry>(context, qname.catalog.empty() ? INVALID_CATALOG : qname.catalog,
+	                                            qname.schema.empty() ? DEFAULT_SCHEMA : qname.schema, qname.name);
+}
+
+static shared_ptr<CubitGpuTable> CubitLookup(ClientContext &context, const string &name) {
+	auto index = CubitFindIndex(context, CubitResolveTable(context, name));
+	if (!index || !index->gpu->loaded) {
+		throw InvalidInputException("no CUBIT GPU index loaded for table \"%s\" (CALL cubit_load first)", name);
+	}
+	return index->gpu;
+}
+
+// ---------------------------------------------------------------- materialise the GPU copy
+// Pulls rowid and every GPU-eligible column through a second connection and places every row at ITS ROW ID: the GPU
+// row position is the table's row id (rowids are dense table positions, row_group.cpp:511-514, stable under
+// DELETE / UPDATE), whatever order the chunks arrive in and whether or not rows were deleted before — positions of
+// deleted rows hold a NULL key and are never selected.
+static void CubitMaterialise(ClientContext &context, TableCatalogEntry &entry, CubitIndex &index) {
+	auto &gpu = *index.gpu;
+	gpu.Unload();
+	gpu.usable = true;
+	gpu.unusable_reason.clear();
+	gpu.column_names.clear();
+	gpu.table_column.clear();
+	gpu.column_types.clear();
+	string select_list = "rowid";
+	for (auto &col : entry.GetColumns().Logical()) {
+		if (!col.Generated() && CubitEligibleType(col.Type())) {
+			select_list += ", " + KeywordHelper::WriteOptionallyQuoted(col.Name());
+			gpu.column_names.push_back(col.Name());
+			gpu.table_column.push_back(col.Logical().index);
+			gpu.column_types.push_back(col.Type());
+		}
+	}
+	auto &storage = entry.GetStorage();
+	const idx_t total = storage.GetTotalRows();
+	if (total == 0) {
+		throw InvalidInputException("cubit_load: table \"%s\" is empty", entry.name);
+	}
+	Connection con(*context.db);
+	auto res = con.Query("SELECT " + select_list + " FROM " + KeywordHelper::WriteOptionallyQuoted(entry.ParentCatalog().GetName()) + "." +
+	                     KeywordHelper::WriteOptionallyQuoted(entry.ParentSchema().name) + "." +
+	                     KeywordHelper::WriteOptionallyQuoted(entry.name));
+	if (res->HasError()) {
+		throw InvalidInputException("cubit_load: %s", res->GetError());
+	}
+	const idx_t n_cols = gpu.column_names.size();
+	const int64_t null_key = NumericLimits<int64_t>::Minimum();
+	vector<vector<int64_t>> cols(n_cols, vector<int64_t>(total, null_key));
+	// NULLs: one validity mask per column in the reference's own layout (ValidityMask words), built only for
+	// columns that hold a NULL; NULL keys are not indexed (plan_create_index.cpp:60-78 filters them out)
+	vector<vector<uint64_t>> valid(n_cols);
+	vector<int64_t> tmp(STANDARD_VECTOR_SIZE);
+	idx_t rows_seen = 0;
+	for (auto &chunk : res->Collection().Chunks()) {
+		const idx_t n = chunk.size();
+		if (n == 0) {
+			continue;
+		}
+		chunk.data[0].Flatten(n);
+		auto rid = FlatVector::GetData<row_t>(chunk.data[0]);
+		const bool dense = rid[n - 1] - rid[0] == NumericCast<row_t>(n - 1);
+		if (rid[0] < 0 || NumericCast<idx_t>(rid[n - 1]) >= total) {
+			throw InvalidInputException("cubit_load: the table changed while it was being read");
+		}
+		for (idx_t k = 0; k < n_cols; k++) {
+			bool any_null = false;
+			int64_t *dst = dense ? cols[k].data() + rid[0] : tmp.data();
+			CubitRawInt64(chunk.data[k + 1], n, dst, nullptr, 0, any_null);
+			if (!dense) {
+				for (idx_t r = 0; r < n; r++) {
+					cols[k][rid[r]] = tmp[r];
+				}
+			}
+			if (any_null) {
+				if (valid[k].empty()) {
+					valid[k].assign((total + 63) / 64, ~uint64_t(0));
+				}
+				chunk.data[k + 1].Flatten(n);
+				auto &mask = FlatVector::Validity(chunk.data[k + 1]);
+				for (idx_t r = 0; r < n; r++) {
+					if (!mask.RowIsValid(r)) {
+						valid[k][rid[r] / 64] &= ~(uint64_t(1) << (rid[r] % 64));
+					}
+				}
+			}
+		}
+		rows_seen += n;
+	}
+	const bool no_deleted_rows = rows_seen == total;
+	gpu.row_count = total;
+	CubitCheck(cubit_gpu_create(0, gpu.row_count, 0, 65536, &gpu.handle));
+	for (idx_t k = 0; k < n_cols; k++) {
+		// compressed segments straight from the buffer manager when the column qualifies (physical position = row
+		// id, so the route needs a table without deleted rows), decoded rows otherwise (a column with NULLs goes
+		// the decoded way: its NULL rows must carry an out-of-domain value)
+		const bool has_nulls = !valid[k].empty();
+		if (has_nulls || !no_deleted_rows ||
+		    !CubitUploadColumnSegments(context, entry, gpu.table_column[k], gpu.column_types[k], gpu.handle, NumericCast<int32_t>(k),
+		                               gpu.row_count)) {
+			CubitCheck(cubit_gpu_upload_column(gpu.handle, NumericCast<int32_t>(k), cols[k].data(), 8, gpu.row_count));
+		}
+		if (has_nulls) {
+			CubitCheck(cubit_gpu_upload_column_validity(gpu.handle, NumericCast<int32_t>(k), valid[k].data(), valid[k].size()));
+		}
+	}
+	for (idx_t i = 0; i < index.specs.size(); i++) {
+		auto &spec = index.specs[i];
+		idx_t gcol = 0;
+		while (gcol < n_cols && gpu.column_names[gcol] != spec.key) {
+			gcol++;
+		}
+		if (gcol == n_cols) {
+			throw InvalidInputException("cubit_load: key column \"%s\" not found or not GPU eligible", spec.key);
+		}
+		gpu.indexes.push_back(CubitBuildIndex(gpu, gcol, spec, gpu.column_types[gcol], i < index.images.size() ? &index.images[i] : nullptr));
+	}
+	gpu.loaded = true;
+}
+
+// ---------------------------------------------------------------- cubit_load(table, key, base, cardinality)
+struct CubitLoadBindData : public TableFunctionData {
+	string table;
+	CubitIndexSpec spec;
+	bool done = false;
+};
+
+static unique_ptr<FunctionData> CubitLoadBind(ClientContext &, TableFunctionBindInput &input,
+                                              vector<LogicalType> &return_types, vector<string> &names) {
+	auto bind = make_uniq<CubitLoadBindData>();
+	bind->table = input.inputs[0].GetValue<string>();
+	bind->spec.key = input.inputs[1].GetValue<string>();
+	bind->spec.base = input.inputs[2].GetValue<int64_t>();
+	bind->spec.cardinality = NumericCast<uint32_t>(input.inputs[3].GetValue<int64_t>());
+	auto bin = input.named_parameters.find("bin");
+	if (bin != input.named_parameters.end()) {
+		bind->spec.bin = bin->second.GetValue<string>();
+	}
+	return_types.emplace_back(LogicalType::BIGINT);
+	names.emplace_back("rows_indexed");
+	return std::move(bind);
 }
 
 static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p, DataChunk &output) {
@@ -336,133 +918,102 @@ static void CubitLoadFunction(ClientContext &context, TableFunctionInput &data_p
 	if (bind.done) {
 		return;
 	}
-	{ // the table is already resident (any DML would have dropped it): just index one more of its columns
-		shared_ptr<CubitGpuTable> have;
-		{
-			std::lock_guard<std::mutex> lk(cubit_registry_lock);
-			auto it = cubit_registry.find(bind.table);
-			if (it != cubit_registry.end()) {
-				have = it->second;
-			}
-		}
-		if (have) {
-			idx_t gcol = 0;
-			while (gcol < have->column_names.size() && have->column_names[gcol] != bind.key) {
-				gcol++;
-			}
-			bool known = gcol == have->column_names.size();
-			for (auto &ix : have->indexes) {
-				known |= ix.key_table_column == have->table_column[gcol < have->table_column.size() ? gcol : 0];
-			}
-			if (!known) {
-				auto &entry = Catalog::GetEntry<TableCatalogEntry>(context, INVALID_CATALOG, DEFAULT_SCHEMA, bind.table);
-				auto ix = CubitBuildIndex(*have, gcol, bind, entry.GetColumns().GetColumn(LogicalIndex(have->table_column[gcol])).Type());
-				{
-					std::lock_guard<std::mutex> lk(cubit_registry_lock);
-					have->indexes.push_back(ix);
-				}
-				output.SetValue(0, 0, Value::BIGINT(NumericCast<int64_t>(have->row_count)));
-				output.SetCardinality(1);
-				bind.done = true;
-				return;
-			}
-			// same key again (or an unknown column): reload from scratch below
-		}
+	auto &entry = CubitResolveTable(context, bind.table);
+	if (!entry.IsDuckTable()) {
+		throw InvalidInputException("cubit_load: \"%s\" is not a DuckDB table", bind.table);
 	}
-	// Pull the key and every BIGINT-castable column in row order through a second connection
-	// (rows come back in insertion order: physical_result_collector.cpp:21-45).
-	// (only the columns the GPU can hold are selected: integral, DECIMAL and DATE ones)
-	auto gpu = make_shared_ptr<CubitGpuTable>();
-	vector<idx_t> int_cols; // result column of every uploaded column (= its position in the select list)
-	vector<LogicalType> col_types;
-	idx_t key_col = DConstants::INVALID_INDEX;
-	string select_list;
-	{
-		auto &entry = Catalog::GetEntry<TableCatalogEntry>(context, INVALID_CATALOG, DEFAULT_SCHEMA, bind.table);
+	auto &storage = entry.GetStorage();
+	auto index = CubitFindIndex(context, entry);
+	optional_ptr<DuckIndexEntry> catalog_entry;
+	const string index_name = "cubit_" + entry.name;
+	if (!index) {
+		// ---- first load of this table: register a CUBIT index on it (catalog entry + BoundIndex in the table's index
+		// list), the way PhysicalCreateARTIndex::Finalize does for ART (physical_create_art_index.cpp:155-189);
+		// CREATE INDEX ... USING CUBIT itself is rejected by the planner for non-ART types (plan_create_index.cpp:33-38)
+		MetaTransaction::Get(context).ModifyDatabase(entry.ParentCatalog().GetAttached());
+		auto info = make_uniq<CreateIndexInfo>();
+		info->catalog = entry.ParentCatalog().GetName();
+		info->schema = entry.ParentSchema().name;
+		info->table = entry.name;
+		info->index_name = index_name;
+		info->index_type = CUBIT_INDEX_TYPE;
+		info->constraint_type = IndexConstraintType::NONE;
+		vector<unique_ptr<Expression>> unbound;
+		vector<column_t> column_ids;
 		for (auto &col : entry.GetColumns().Logical()) {
-			auto &t = col.Type();
-			if (t.IsIntegral() || t.id() == LogicalTypeId::DECIMAL || t.id() == LogicalTypeId::DATE) {
-				if (col.Name() == bind.key) {
-					key_col = int_cols.size();
-				}
-				select_list += (select_list.empty() ? "" : ", ") + KeywordHelper::WriteOptionallyQuoted(col.Name());
-				int_cols.push_back(int_cols.size());
-				col_types.push_back(t);
-				gpu->column_names.push_back(col.Name());
-				gpu->table_column.push_back(col.Logical().index);
+			info->scan_types.push_back(col.Type());
+			info->names.push_back(col.Name());
+			if (col.Generated() || !CubitEligibleType(col.Type())) {
+				continue;
 			}
+			// every GPU-resident column is an index column: DML that touches one of them reaches the index
+			// (an UPDATE of such a column is planned as DELETE + INSERT, BoundIndex::IndexIsUpdated)
+			info->expressions.push_back(make_uniq<ColumnRefExpression>(col.Name(), entry.name));
+			info->parsed_expressions.push_back(make_uniq<ColumnRefExpression>(col.Name(), entry.name));
+			unbound.push_back(make_uniq<BoundColumnRefExpression>(col.Name(), col.Type(), ColumnBinding(0, column_ids.size())));
+			column_ids.push_back(col.StorageOid());
+		}
+		info->scan_types.emplace_back(LogicalType::ROW_TYPE);
+		info->column_ids = column_ids;
+		info->options["cubit_specs"] = Value(CubitEncodeSpecs({bind.spec}));
+		auto &schema = entry.ParentSchema();
+		auto created = schema.CreateIndex(schema.GetCatalogTransaction(context), *info, entry);
+		if (!created) {
+			throw InvalidInputException("cubit_load: could not register the index \"%s\"", index_name);
+		}
+		auto &dentry = created->Cast<DuckIndexEntry>();
+		dentry.initial_index_size = 0;
+		dentry.info = make_shared_ptr<IndexDataTableInfo>(storage.GetDataTableInfo(), dentry.name);
+		for (auto &expr : info->parsed_expressions) {
+			dentry.parsed_expressions.push_back(expr->Copy());
+		}
+		auto bound = make_uniq<CubitIndex>(index_name, column_ids, TableIOManager::Get(storage), unbound, storage.db,
+		                                   vector<CubitIndexSpec> {bind.spec});
+		index = bound.get();
+		storage.AddIndex(std::move(bound));
+	}
+	auto &gpu = *index->gpu;
+	std::lock_guard<std::mutex> lk(gpu.dml_lock);
+	idx_t slot = 0;
+	while (slot < index->specs.size() && index->specs[slot].key != bind.spec.key) {
+		slot++;
+	}
+	const bool new_key = slot == index->specs.size();
+	if (new_key) {
+		index->specs.push_back(bind.spec);
+	} else {
+		index->specs[slot] = bind.spec; // same key again: new domain / binning
+	}
+	{ // the catalog entry carries the specs across restarts
+		auto entry_ptr = entry.ParentSchema().GetEntry(entry.ParentSchema().GetCatalogTransaction(context), CatalogType::INDEX_ENTRY,
+		                                               index_name);
+		if (entry_ptr) {
+			entry_ptr->Cast<IndexCatalogEntry>().options["cubit_specs"] = Value(CubitEncodeSpecs(index->specs));
 		}
 	}
-	if (key_col == DConstants::INVALID_INDEX) {
-		throw InvalidInputException("cubit_load: key column \"%s\" not found or not integral", bind.key);
-	}
-	Connection con(*context.db);
-	auto res = con.Query("SELECT " + select_list + " FROM " + KeywordHelper::WriteOptionallyQuoted(bind.table));
-	if (res->HasError()) {
-		throw InvalidInputException("cubit_load: %s", res->GetError());
-	}
-	vector<vector<int64_t>> cols(int_cols.size());
-	// NULLs: one validity mask per column in the reference's own layout (ValidityMask words), built only for
-	// columns that hold a NULL; NULL keys are not indexed (plan_create_index.cpp:60-78 filters them out)
-	vector<vector<uint64_t>> valid(int_cols.size());
-	idx_t rows_seen = 0;
-	for (auto &chunk : res->Collection().Chunks()) {
-		for (idx_t k = 0; k < int_cols.size(); k++) {
-			auto &vec = chunk.data[int_cols[k]];
-			// DECIMAL(15,2) is stored as int64 cents (dbgen.cpp:48-50); cast everything to the raw BIGINT
-			Vector as_bigint(LogicalType::BIGINT);
-			if (vec.GetType().id() == LogicalTypeId::DECIMAL && vec.GetType().InternalType() == PhysicalType::INT64) {
-				as_bigint.Reinterpret(vec);
-			} else if (vec.GetType().id() == LogicalTypeId::DATE) {
-				Vector as_int(LogicalType::INTEGER); // days since 1970-01-01 (date_t)
-				as_int.Reinterpret(vec);
-				VectorOperations::Cast(context, as_int, as_bigint, chunk.size());
-			} else {
-				VectorOperations::Cast(context, vec, as_bigint, chunk.size());
+	if (gpu.loaded && gpu.usable && new_key && gpu.row_count == storage.GetTotalRows()) {
+		// the table is already resident: just index one more of its columns
+		idx_t gcol = 0;
+		while (gcol < gpu.column_names.size() && gpu.column_names[gcol] != bind.spec.key) {
+			gcol++;
+		}
+		if (gcol == gpu.column_names.size()) {
+			index->specs.pop_back();
+			throw InvalidInputException("cubit_load: key column \"%s\" not found or not GPU eligible", bind.spec.key);
+		}
+		gpu.indexes.push_back(CubitBuildIndex(gpu, gcol, bind.spec, gpu.column_types[gcol], nullptr));
+	} else {
+		index->images.clear(); // an explicit load always rebuilds from the table
+		try {
+			CubitMaterialise(context, entry, *index);
+		} catch (...) {
+			if (new_key) {
+				index->specs.pop_back();
 			}
-			as_bigint.Flatten(chunk.size());
-			auto ptr = FlatVector::GetData<int64_t>(as_bigint);
-			cols[k].insert(cols[k].end(), ptr, ptr + chunk.size());
-			auto &mask = FlatVector::Validity(as_bigint);
-			if (!mask.AllValid()) {
-				for (idx_t r = 0; r < chunk.size(); r++) {
-					if (mask.RowIsValid(r)) {
-						continue;
-					}
-					if (valid[k].empty()) {
-						valid[k].assign((res->RowCount() + 63) / 64, ~uint64_t(0));
-					}
-					const idx_t row = rows_seen + r;
-					valid[k][row / 64] &= ~(uint64_t(1) << (row % 64));
-					// NULL rows carry a value outside every indexed domain (the probe never shows it: the
-					// validity mask does), so any column can become an index key later
-					cols[k][row] = NumericLimits<int64_t>::Minimum();
-				}
-			}
-		}
-		rows_seen += chunk.size();
-	}
-	gpu->row_count = cols.empty() ? 0 : cols[0].size();
-	CubitCheck(cubit_gpu_create(0, gpu->row_count, 0, 65536, &gpu->handle));
-	for (idx_t k = 0; k < cols.size(); k++) {
-		// compressed segments straight from the buffer manager when the column qualifies, decoded rows otherwise
-		// (a column with NULLs goes the decoded way: its NULL rows must carry an out-of-domain value)
-		const bool null_keys = !valid[k].empty();
-		if (null_keys || !CubitUploadColumnSegments(context, bind.table, gpu->table_column[k], col_types[k],
-		                                            gpu->handle, NumericCast<int32_t>(k), gpu->row_count)) {
-			CubitCheck(cubit_gpu_upload_column(gpu->handle, NumericCast<int32_t>(k), cols[k].data(), 8, gpu->row_count));
-		}
-		if (!valid[k].empty()) {
-			CubitCheck(cubit_gpu_upload_column_validity(gpu->handle, NumericCast<int32_t>(k), valid[k].data(),
-			                                            valid[k].size()));
+			throw;
 		}
 	}
-	gpu->indexes.push_back(CubitBuildIndex(*gpu, key_col, bind, col_types[key_col]));
-	{
-		std::lock_guard<std::mutex> lk(cubit_registry_lock);
-		cubit_registry[bind.table] = gpu;
-	}
-	output.SetValue(0, 0, Value::BIGINT(NumericCast<int64_t>(gpu->row_count)));
+	output.SetValue(0, 0, Value::BIGINT(NumericCast<int64_t>(gpu.row_count)));
 	output.SetCardinality(1);
 	bind.done = true;
 }
@@ -482,43 +1033,65 @@ struct CubitScanBindData : public TableFunctionData {
 	bool table_column_ids = false;
 };
 
+// DataChunk hand-off.  The result stays on the GPU; its rows leave in WINDOWS of 64 DataChunks.
+// Up to MaxThreads() workers drain windows in parallel: a worker claims the next window index (the batch index the
+// ordered sinks sort by, the pattern of seq_scan's row-group batches, table_scan.cpp:179-189), and while it serves
+// one window out of its page-locked buffers the copy of the NEXT window it claimed is already in flight
+// (cubit_gpu_fetch_async on the library's copy streams) — two buffer sets per worker, no synchronise per chunk.
 struct CubitScanGlobalState : public GlobalTableFunctionState {
 	cubit_gpu_result *result = nullptr;
 	vector<column_t> column_ids;
-	vector<idx_t> out_slot; // which entry of column_ids every output vector shows (projection_ids applied)
-	idx_t row_count = 0, offset = 0;
+	idx_t row_count = 0;
 	uint64_t sum_lo = 0;
 	int64_t sum_hi = 0;
 	uint64_t agg_rows = 0; // non-NULL inputs of the pushed-down SUM
 	bool agg_emitted = false;
-	// host staging window: result rows [win_begin, win_end) fetched with ONE device→host copy per column and
-	// served to the executor 2048 rows at a time (a copy + synchronise per DataChunk costs ~30 us, i.e. more
-	// than the whole scan for a few hundred thousand rows)
+	bool want_rowid = false;
+	idx_t n_value_cols = 0;
+	vector<bool> col_has_nulls; // per projected value column: the result carries a validity mask for it
 	static constexpr idx_t WINDOW_ROWS = 64 * STANDARD_VECTOR_SIZE;
-	idx_t win_begin = 0, win_end = 0;
-	// page-locked, WINDOW_ROWS int64 each, borrowed from the table's pool on first use
+	std::atomic<idx_t> next_window {0};
+	idx_t n_windows = 0;
 	shared_ptr<CubitGpuTable> pool_owner;
-	int64_t *win_rowids = nullptr;
-	vector<int64_t *> win_cols;             // one per projected value column
-	vector<vector<uint64_t>> win_validity;  // ValidityMask words of the window, empty = no NULL in the window
 	~CubitScanGlobalState() override {
 		cubit_gpu_free_result(result);
-		if (pool_owner) {
-			pool_owner->ReleaseWindow(win_rowids);
-			for (auto p : win_cols) {
-				pool_owner->ReleaseWindow(p);
-			}
-		}
 	}
 	idx_t MaxThreads() const override {
-		return 1; // like index_scan (table_scan.cpp:213-225)
+		// a window is 1-3 MB of PCIe traffic plus 64 memcpy'd DataChunks: worth a worker each, up to a handful
+		return MaxValue<idx_t>(1, MinValue<idx_t>(8, n_windows / 2));
 	}
 };
 
-static unique_ptr<FunctionData> CubitScanBind(ClientContext &, TableFunctionBindInput &input,
+struct CubitScanLocalState : public LocalTableFunctionState {
+	struct Window {
+		idx_t index = DConstants::INVALID_INDEX, begin = 0, end = 0;
+		int64_t *rowids = nullptr;
+		vector<int64_t *> cols;
+		vector<vector<uint64_t>> validity; // ValidityMask words of the window, empty = no NULL in the window
+		cubit_gpu_fetch_ticket *ticket = nullptr;
+	};
+	Window win[2];
+	int cur = 0;          // the window being served
+	idx_t offset = 0;     // next result row to emit (inside win[cur])
+	bool primed = false;
+	shared_ptr<CubitGpuTable> pool_owner;
+	~CubitScanLocalState() override {
+		for (auto &w : win) {
+			cubit_gpu_fetch_wait(w.ticket);
+			if (pool_owner) {
+				pool_owner->ReleaseWindow(w.rowids);
+				for (auto p : w.cols) {
+					pool_owner->ReleaseWindow(p);
+				}
+			}
+		}
+	}
+};
+
+static unique_ptr<FunctionData> CubitScanBind(ClientContext &context, TableFunctionBindInput &input,
                                               vector<LogicalType> &return_types, vector<string> &names) {
 	auto bind = make_uniq<CubitScanBindData>();
-	bind->gpu = CubitLookup(input.inputs[0].GetValue<string>());
+	bind->gpu = CubitLookup(context, input.inputs[0].GetValue<string>());
 	bind->ranges.push_back({0, input.inputs[1].GetValue<int64_t>(), input.inputs[2].GetValue<int64_t>()});
 	for (auto &n : bind->gpu->column_names) {
 		return_types.emplace_back(LogicalType::BIGINT);
@@ -592,6 +1165,15 @@ static unique_ptr<GlobalTableFunctionState> CubitRunQuery(const CubitScanBindDat
 	state->sum_lo = info.sum_lo;
 	state->sum_hi = info.sum_hi;
 	state->agg_rows = info.agg_rows;
+	state->want_rowid = want_rowid;
+	state->n_value_cols = cols.size();
+	for (idx_t c = 0; c < cols.size(); c++) {
+		// (a sharded result has no single device pointer: ask the library per window instead)
+		uint32_t n_shards = 1;
+		cubit_gpu_shard_count(gpu.handle, &n_shards);
+		state->col_has_nulls.push_back(n_shards > 1 || info.d_validity[c] != nullptr);
+	}
+	state->n_windows = (state->row_count + CubitScanGlobalState::WINDOW_ROWS - 1) / CubitScanGlobalState::WINDOW_ROWS;
 	return std::move(state);
 }
 
@@ -599,54 +1181,92 @@ static unique_ptr<GlobalTableFunctionState> CubitScanInitGlobal(ClientContext &,
 	return CubitRunQuery(input.bind_data->Cast<CubitScanBindData>(), input.column_ids, input.projection_ids);
 }
 
+static unique_ptr<LocalTableFunctionState> CubitScanInitLocal(ExecutionContext &, TableFunctionInitInput &,
+                                                             GlobalTableFunctionState *global_state) {
+	auto local = make_uniq<CubitScanLocalState>();
+	local->pool_owner = global_state->Cast<CubitScanGlobalState>().pool_owner;
+	return std::move(local);
+}
+
+// claim the next window of the result and start its device → host copy into `w`'s page-locked buffers
+static void CubitClaimWindow(CubitScanGlobalState &state, CubitScanLocalState &local, CubitScanLocalState::Window &w) {
+	w.index = state.next_window.fetch_add(1);
+	w.ticket = nullptr;
+	if (w.index >= state.n_windows) {
+		w.index = DConstants::INVALID_INDEX;
+		return;
+	}
+	w.begin = w.index * CubitScanGlobalState::WINDOW_ROWS;
+	w.end = MinValue<idx_t>(w.begin + CubitScanGlobalState::WINDOW_ROWS, state.row_count);
+	const uint64_t win_bytes = CubitScanGlobalState::WINDOW_ROWS * sizeof(int64_t);
+	while (w.cols.size() < state.n_value_cols) {
+		w.cols.push_back(static_cast<int64_t *>(local.pool_owner->AcquireWindow(win_bytes)));
+	}
+	if (state.want_rowid && !w.rowids) {
+		w.rowids = static_cast<int64_t *>(local.pool_owner->AcquireWindow(win_bytes));
+	}
+	vector<void *> ptrs(w.cols.begin(), w.cols.end());
+	CubitCheck(cubit_gpu_fetch_async(state.result, w.begin, w.end - w.begin, state.want_rowid ? w.rowids : nullptr,
+	                                 NumericCast<uint32_t>(ptrs.size()), ptrs.data(), &w.ticket));
+	// NULLs: the validity mask of every projected value (StandardColumnData::FetchRow = validity + data) — asked for
+	// only when the query touched a NULL-bearing column at all
+	w.validity.resize(state.n_value_cols);
+	for (idx_t c = 0; c < state.n_value_cols; c++) {
+		w.validity[c].clear();
+		if (!state.col_has_nulls[c]) {
+			continue;
+		}
+		int all_valid = 1;
+		w.validity[c].assign((w.end - w.begin + 63) / 64, 0);
+		CubitCheck(cubit_gpu_fetch_validity(state.result, NumericCast<uint32_t>(c), w.begin, w.end - w.begin,
+		                                    w.validity[c].data(), &all_valid));
+		if (all_valid) {
+			w.validity[c].clear();
+		}
+	}
+}
+
 static void CubitScanFunction(ClientContext &, TableFunctionInput &data_p, DataChunk &output) {
 	auto &state = data_p.global_state->Cast<CubitScanGlobalState>();
-	if (state.offset >= state.row_count) {
+	auto &local = data_p.local_state->Cast<CubitScanLocalState>();
+	if (!local.primed) { // two windows in flight per worker from the start
+		local.primed = true;
+		CubitClaimWindow(state, local, local.win[0]);
+		CubitClaimWindow(state, local, local.win[1]);
+		local.cur = 0;
+		local.offset = local.win[0].begin;
+		if (local.win[0].index != DConstants::INVALID_INDEX) {
+			CubitCheck(cubit_gpu_fetch_wait(local.win[0].ticket));
+			local.win[0].ticket = nullptr;
+		}
+	}
+	auto *w = &local.win[local.cur];
+	if (w->index != DConstants::INVALID_INDEX && local.offset >= w->end) {
+		// this window is served: re-arm its buffers with the next unclaimed window, switch to the other (its copy has
+		// been in flight all along)
+		CubitClaimWindow(state, local, *w);
+		local.cur ^= 1;
+		w = &local.win[local.cur];
+		if (w->index != DConstants::INVALID_INDEX) {
+			CubitCheck(cubit_gpu_fetch_wait(w->ticket));
+			w->ticket = nullptr;
+			local.offset = w->begin;
+		}
+	}
+	if (w->index == DConstants::INVALID_INDEX) {
 		return; // chunk.size() == 0 → PhysicalTableScan::GetData returns FINISHED
 	}
-	if (state.offset >= state.win_end) { // refill the staging window
-		const idx_t n = MinValue<idx_t>(CubitScanGlobalState::WINDOW_ROWS, state.row_count - state.offset);
-		state.win_begin = state.offset;
-		state.win_end = state.offset + n;
-		bool want_rowid = false;
-		idx_t n_value_cols = 0;
-		for (auto c : state.column_ids) {
-			want_rowid |= c == COLUMN_IDENTIFIER_ROW_ID;
-			n_value_cols += c != COLUMN_IDENTIFIER_ROW_ID;
-		}
-		state.win_validity.resize(n_value_cols);
-		const uint64_t win_bytes = CubitScanGlobalState::WINDOW_ROWS * sizeof(int64_t);
-		while (state.win_cols.size() < n_value_cols) {
-			state.win_cols.push_back(static_cast<int64_t *>(state.pool_owner->AcquireWindow(win_bytes)));
-		}
-		if (want_rowid && !state.win_rowids) {
-			state.win_rowids = static_cast<int64_t *>(state.pool_owner->AcquireWindow(win_bytes));
-		}
-		vector<void *> ptrs(state.win_cols.begin(), state.win_cols.end());
-		CubitCheck(cubit_gpu_fetch(state.result, state.win_begin, n, want_rowid ? state.win_rowids : nullptr,
-		                           NumericCast<uint32_t>(ptrs.size()), ptrs.data()));
-		// NULLs: the validity mask of every projected value (StandardColumnData::FetchRow = validity + data)
-		for (idx_t c = 0; c < n_value_cols; c++) {
-			int all_valid = 1;
-			state.win_validity[c].assign((n + 63) / 64, 0);
-			CubitCheck(cubit_gpu_fetch_validity(state.result, NumericCast<uint32_t>(c), state.win_begin, n,
-			                                    state.win_validity[c].data(), &all_valid));
-			if (all_valid) {
-				state.win_validity[c].clear();
-			}
-		}
-	}
-	const idx_t scan_count = MinValue<idx_t>(STANDARD_VECTOR_SIZE, state.win_end - state.offset);
-	const idx_t rel = state.offset - state.win_begin; // a multiple of 2048: word aligned in the window's masks
+	const idx_t scan_count = MinValue<idx_t>(STANDARD_VECTOR_SIZE, w->end - local.offset);
+	const idx_t rel = local.offset - w->begin; // a multiple of 2048: word aligned in the window's masks
 	idx_t value_col = 0;
 	for (idx_t i = 0; i < state.column_ids.size(); i++) {
 		auto dst = FlatVector::GetData<int64_t>(output.data[i]);
 		if (state.column_ids[i] == COLUMN_IDENTIFIER_ROW_ID) {
-			memcpy(dst, state.win_rowids + rel, scan_count * sizeof(int64_t));
+			memcpy(dst, w->rowids + rel, scan_count * sizeof(int64_t));
 			continue;
 		}
-		memcpy(dst, state.win_cols[value_col] + rel, scan_count * sizeof(int64_t));
-		auto &words = state.win_validity[value_col];
+		memcpy(dst, w->cols[value_col] + rel, scan_count * sizeof(int64_t));
+		auto &words = w->validity[value_col];
 		if (!words.empty()) {
 			auto &mask = FlatVector::Validity(output.data[i]);
 			for (idx_t r = 0; r < scan_count; r++) {
@@ -658,14 +1278,22 @@ static void CubitScanFunction(ClientContext &, TableFunctionInput &data_p, DataC
 		value_col++;
 	}
 	output.SetCardinality(scan_count);
-	state.offset += scan_count;
+	local.offset += scan_count;
+}
+
+// ordered sinks (batch collectors, ORDER-preserving inserts) sort the chunks of parallel workers by this
+static idx_t CubitScanGetBatchIndex(ClientContext &, const FunctionData *, LocalTableFunctionState *local_state,
+                                    GlobalTableFunctionState *) {
+	auto &local = local_state->Cast<CubitScanLocalState>();
+	auto &w = local.win[local.cur];
+	return w.index == DConstants::INVALID_INDEX ? 0 : w.index;
 }
 
 // ---------------------------------------------------------------- cubit_agg(table, lo, hi, column) → (count, sum)
-static unique_ptr<FunctionData> CubitAggBind(ClientContext &, TableFunctionBindInput &input,
+static unique_ptr<FunctionData> CubitAggBind(ClientContext &context, TableFunctionBindInput &input,
                                              vector<LogicalType> &return_types, vector<string> &names) {
 	auto bind = make_uniq<CubitScanBindData>();
-	bind->gpu = CubitLookup(input.inputs[0].GetValue<string>());
+	bind->gpu = CubitLookup(context, input.inputs[0].GetValue<string>());
 	bind->ranges.push_back({0, input.inputs[1].GetValue<int64_t>(), input.inputs[2].GetValue<int64_t>()});
 	auto col = input.inputs[3].GetValue<string>();
 	for (idx_t c = 0; c < bind->gpu->column_names.size(); c++) {
@@ -755,7 +1383,8 @@ static bool CubitBoundsFromFilter(const TableFilter &filter, int64_t &lo, int64_
 
 // Can this seq_scan's pushed-down filters be answered by the table's GPU indexes?  Fills the table and one
 // (index, lo, hi) range per filtered column.  Nothing is modified.
-static bool CubitPlanGet(LogicalGet &get, shared_ptr<CubitGpuTable> &gpu, vector<CubitScanBindData::Range> &ranges) {
+static bool CubitPlanGet(ClientContext &context, LogicalGet &get, shared_ptr<CubitGpuTable> &gpu,
+                         vector<CubitScanBindData::Range> &ranges) {
 #undef CUBIT_WHY
 #define CUBIT_WHY(msg)                                                                                                  \
 	do {                                                                                                               \
@@ -774,14 +1403,46 @@ static bool CubitPlanGet(LogicalGet &get, shared_ptr<CubitGpuTable> &gpu, vector
 	if (!table) {
 		CUBIT_WHY("no table");
 	}
-	{
-		std::lock_guard<std::mutex> lk(cubit_registry_lock);
-		auto it = cubit_registry.find(table->name);
-		if (it == cubit_registry.end()) {
-			CUBIT_WHY("table has no GPU index");
-		}
-		gpu = it->second;
+	// the accelerator is the table's own CUBIT index (no name-keyed registry: another table, schema or database with
+	// the same name has its own index list)
+	auto index = CubitFindIndex(context, *table);
+	if (!index) {
+		CUBIT_WHY("table has no GPU index");
 	}
+	auto &storage = table->GetStorage();
+	{
+		std::lock_guard<std::mutex> lk(index->gpu->dml_lock);
+		if (!index->gpu->loaded) {
+			// bound from the catalog after ATTACH / restart: materialise the GPU copy now (index images from the
+			// last checkpoint replace the index builds when they still describe the table)
+			if (index->specs.empty()) {
+				CUBIT_WHY("CUBIT index without specs");
+			}
+			try {
+				CubitMaterialise(context, *table, *index);
+			} catch (std::exception &ex) {
+				index->gpu->usable = false;
+				index->gpu->unusable_reason = ErrorData(ex).Message();
+			}
+		}
+		if (!index->gpu->loaded || !index->gpu->usable) {
+			if (getenv("CUBIT_DEBUG_REWRITE")) {
+				fprintf(stderr, "cubit: GPU copy stepped aside: %s\n", index->gpu->unusable_reason.c_str());
+			}
+			CUBIT_WHY("GPU copy is not usable (reload with cubit_load)");
+		}
+		// the GPU copy must describe exactly the committed table: same row-id high-water mark (appends that bypassed
+		// the index callbacks — none are known — or a reverted append would show here) ...
+		if (index->gpu->row_count != storage.GetTotalRows()) {
+			CUBIT_WHY("GPU copy and table differ in row count");
+		}
+	}
+	// ... and this transaction must not have changes of its own: its uncommitted inserts live in its local storage and
+	// its uncommitted deletes reach the index only at commit, so only the vanilla scan sees them
+	if (DuckTransaction::Get(context, table->ParentCatalog()).ChangesMade()) {
+		CUBIT_WHY("the transaction has uncommitted changes");
+	}
+	gpu = index->gpu;
 	// EVERY pushed-down filter must sit on an indexed column (keys of LogicalGet::table_filters are table column
 	// indexes: filter_combiner.cpp:438-480, plan_get.cpp:15-33); each becomes one OR group over the value
 	// bitvectors of its range, the groups are ANDed — the Q6-style conjunction of range predicates
@@ -854,10 +1515,10 @@ static int32_t CubitResidentColumn(const LogicalGet &get, const CubitGpuTable &g
 	return -1;
 }
 
-static void CubitRewriteGet(LogicalGet &get) {
+static void CubitRewriteGet(ClientContext &context, LogicalGet &get) {
 	shared_ptr<CubitGpuTable> gpu;
 	vector<CubitScanBindData::Range> ranges;
-	if (!CubitPlanGet(get, gpu, ranges)) {
+	if (!CubitPlanGet(context, get, gpu, ranges)) {
 		return;
 	}
 	// every column that leaves the scan must be GPU resident and physically int64 (BIGINT, DECIMAL(≤18))
@@ -1025,7 +1686,7 @@ static int32_t CubitAggInputColumn(const Expression &expr, const LogicalGet &get
 	return CubitResidentColumn(get, gpu, get.column_ids[ref.binding.column_index]);
 }
 
-static bool CubitTryAggregatePushdown(unique_ptr<LogicalOperator> &op) {
+static bool CubitTryAggregatePushdown(ClientContext &context, unique_ptr<LogicalOperator> &op) {
 	if (op->type != LogicalOperatorType::LOGICAL_AGGREGATE_AND_GROUP_BY) {
 		return false;
 	}
@@ -1037,7 +1698,7 @@ static bool CubitTryAggregatePushdown(unique_ptr<LogicalOperator> &op) {
 	auto &get = aggr.children[0]->Cast<LogicalGet>();
 	shared_ptr<CubitGpuTable> gpu;
 	vector<CubitScanBindData::Range> ranges;
-	if (!CubitPlanGet(get, gpu, ranges)) {
+	if (!CubitPlanGet(context, get, gpu, ranges)) {
 		return false;
 	}
 	auto bind = make_uniq<CubitAggMultiBindData>();
@@ -1108,57 +1769,28 @@ static bool CubitTryAggregatePushdown(unique_ptr<LogicalOperator> &op) {
 	return true;
 }
 
-static void CubitRewritePlan(unique_ptr<LogicalOperator> &op) {
-	if (CubitTryAggregatePushdown(op)) {
+static void CubitRewritePlan(ClientContext &context, unique_ptr<LogicalOperator> &op) {
+	if (CubitTryAggregatePushdown(context, op)) {
 		return;
 	}
 	if (op->type == LogicalOperatorType::LOGICAL_GET) {
-		CubitRewriteGet(op->Cast<LogicalGet>());
+		CubitRewriteGet(context, op->Cast<LogicalGet>());
 	}
 	for (auto &child : op->children) {
-		CubitRewritePlan(child);
+		CubitRewritePlan(context, child);
 	}
 }
 
-// DML on an indexed table: this glue does not sit in the index-maintenance path (that needs a registered index
-// type, bound_index.hpp:71-97 → cubit_gpu_set_delta / cubit_gpu_append_rows), so the GPU copy would go stale.
-// The statement itself keeps the vanilla scan, and the table's GPU index is dropped: later scans fall back to
-// the vanilla path until cubit_load is called again.
-static bool CubitInvalidateOnDml(LogicalOperator &op) {
-	bool dml = false;
-	const TableCatalogEntry *target = nullptr;
-	switch (op.type) {
-	case LogicalOperatorType::LOGICAL_UPDATE:
-		target = &op.Cast<LogicalUpdate>().table;
-		break;
-	case LogicalOperatorType::LOGICAL_DELETE:
-		target = &op.Cast<LogicalDelete>().table;
-		break;
-	case LogicalOperatorType::LOGICAL_INSERT:
-		target = &op.Cast<LogicalInsert>().table;
-		break;
-	default:
-		break;
-	}
-	if (target) {
-		dml = true;
-		std::lock_guard<std::mutex> lk(cubit_registry_lock);
-		cubit_registry.erase(target->name);
-	}
-	for (auto &child : op.children) {
-		dml |= CubitInvalidateOnDml(*child);
-	}
-	return dml;
-}
-
-static void CubitOptimize(OptimizerExtensionInput &, unique_ptr<LogicalOperator> &plan) {
-	if (CubitInvalidateOnDml(*plan)) {
+// DML needs nothing here: the table's CUBIT index receives it through BoundIndex::Append / Delete (see CubitIndex).
+// The scan that FEEDS a DELETE / UPDATE may itself be rewritten (it only produces row ids and column values).
+static void CubitOptimize(OptimizerExtensionInput &input, unique_ptr<LogicalOperator> &plan) {
+	if (getenv("CUBIT_DISABLE_REWRITE")) { // (tests: the same statement through the vanilla scan of the same table)
 		return;
 	}
 	if (getenv("CUBIT_NO_AGG_PUSHDOWN")) { // (tests: compare the row-returning scan with the pushed-down aggregate)
 		std::function<void(LogicalOperator &)> walk = [&](LogicalOperator &o) {
 			if (o.type == LogicalOperatorType::LOGICAL_GET) {
-				CubitRewriteGet(o.Cast<LogicalGet>());
+				CubitRewriteGet(input.context, o.Cast<LogicalGet>());
 			}
 			for (auto &child : o.children) {
 				walk(*child);
@@ -1167,12 +1799,13 @@ static void CubitOptimize(OptimizerExtensionInput &, unique_ptr<LogicalOperator>
 		walk(*plan);
 		return;
 	}
-	CubitRewritePlan(plan);
+	CubitRewritePlan(input.context, plan);
 }
 
 static TableFunction CubitScanTableFunction() {
 	TableFunction scan("cubit_scan", {LogicalType::VARCHAR, LogicalType::BIGINT, LogicalType::BIGINT}, CubitScanFunction,
-	                   CubitScanBind, CubitScanInitGlobal);
+	                   CubitScanBind, CubitScanInitGlobal, CubitScanInitLocal);
+	scan.get_batch_index = CubitScanGetBatchIndex; // parallel workers, order kept by the window index
 	scan.projection_pushdown = true; // column_ids tell the GPU which columns to probe
 	scan.filter_prune = true;        // columns used only by the (absorbed) filter are not produced
 	return scan;
@@ -1194,6 +1827,15 @@ void RegisterCubitGpuFunctions(DatabaseInstance &db) {
 	OptimizerExtension rewrite;
 	rewrite.optimize_function = CubitOptimize;
 	DBConfig::GetConfig(db).optimizer_extensions.push_back(rewrite);
+
+	// the index type (index_type_set.cpp:24-30): lets a database file that holds a CUBIT index be attached — the
+	// index is bound through create_instance, maintained by DML and checkpointed like any other
+	if (!DBConfig::GetConfig(db).GetIndexTypes().FindByName(CUBIT_INDEX_TYPE)) {
+		IndexType cubit_type;
+		cubit_type.name = CUBIT_INDEX_TYPE;
+		cubit_type.create_instance = CubitIndex::Create;
+		DBConfig::GetConfig(db).GetIndexTypes().RegisterIndexType(cubit_type);
+	}
 }
 
 } // namespace duckdb

@@ -11,6 +11,9 @@ void RegisterCubitGpuFunctions(DatabaseInstance &db);
 idx_t CubitRewriteCount();
 idx_t CubitSegmentRouteCount();
 idx_t CubitAggPushdownCount();
+idx_t CubitDmlAppendedRows();
+idx_t CubitDmlDeltaPairs();
+idx_t CubitImageLoads();
 }
 using namespace duckdb;
 
@@ -29,6 +32,44 @@ static unique_ptr<MaterializedQueryResult> Run(Connection &con, const string &sq
 		exit(1);
 	}
 	return r;
+}
+
+// the same statement through the vanilla scan of the SAME table (the optimizer rewrite switched off for one query)
+static unique_ptr<MaterializedQueryResult> RunVanilla(Connection &con, const string &sql) {
+	setenv("CUBIT_DISABLE_REWRITE", "1", 1);
+	auto r = Run(con, sql);
+	unsetenv("CUBIT_DISABLE_REWRITE");
+	return r;
+}
+
+// every predicate, through the GPU (rewritten: the rewrite counter moves) and through the vanilla scan of the same
+// table: aggregates, and rows with their row ids
+static void CompareWithVanilla(Connection &con, const string &table, const string &cols, const vector<string> &wheres) {
+	for (auto &where : wheres) {
+		const string agg = "SELECT count(*), sum(price), sum(price * disc), min(rowid), max(rowid) FROM " + table + " WHERE " + where;
+		const idx_t before = CubitRewriteCount();
+		auto a = Run(con, agg);
+		auto b = RunVanilla(con, agg);
+		if (b->GetValue(0, 0).GetValue<int64_t>() > 0) {
+			REQUIRE(CubitRewriteCount() == before + 1);
+		}
+		for (idx_t c = 0; c < 5; c++) {
+			if (a->GetValue(c, 0).ToString() != b->GetValue(c, 0).ToString()) {
+				fprintf(stderr, "mismatch on %s WHERE %s col %llu: gpu %s vanilla %s\n", table.c_str(), where.c_str(),
+				        (unsigned long long)c, a->GetValue(c, 0).ToString().c_str(), b->GetValue(c, 0).ToString().c_str());
+			}
+			REQUIRE(a->GetValue(c, 0).ToString() == b->GetValue(c, 0).ToString());
+		}
+		const string rows = "SELECT rowid, " + cols + " FROM " + table + " WHERE " + where + " ORDER BY rowid";
+		auto x = Run(con, rows);
+		auto y = RunVanilla(con, rows);
+		REQUIRE(x->RowCount() == y->RowCount());
+		for (idx_t r = 0; r < x->RowCount(); r += 41) {
+			for (idx_t c = 0; c < x->ColumnCount(); c++) {
+				REQUIRE(x->GetValue(c, r) == y->GetValue(c, r));
+			}
+		}
+	}
 }
 
 int main(int argc, char **argv) {
@@ -272,6 +313,91 @@ int main(int argc, char **argv) {
 		REQUIRE(z2->GetValue(0, 0).GetValue<int64_t>() == 1000 && z2->GetValue(1, 0).IsNull());
 		printf("null semantics ok\n");
 	}
+	{ // DML reaches the GPU copy through the table's CUBIT index (BoundIndex::Append / Delete, bound_index.hpp:71-97):
+	  // DELETE and UPDATE become pending deltas, INSERT appends, and the SAME SELECTs keep being answered by the GPU
+	  // with the answers of the vanilla scan (SURVEY §8c "delta semantics oracle": rowids are stable, updated rows of
+	  // an indexed column move to the end, new rows take the next row ids)
+		const vector<string> dml_wheres = {"q BETWEEN 10 AND 19", "q = 24", "q < 4", "q >= 48 AND q <= 49", "q = 24 AND disc = 3",
+		                                   "q > 40 AND disc BETWEEN 2 AND 5", "disc = 4"};
+		CompareWithVanilla(con, "t", "q, price, disc", dml_wheres);
+		const idx_t pairs0 = CubitDmlDeltaPairs(), app0 = CubitDmlAppendedRows();
+		auto del = Run(con, "DELETE FROM t WHERE q = 24 AND price % 3 = 0");
+		REQUIRE(del->GetValue(0, 0).GetValue<int64_t>() > 0);
+		REQUIRE(CubitDmlDeltaPairs() >= pairs0 + 2 * NumericCast<idx_t>(del->GetValue(0, 0).GetValue<int64_t>())); // two indexes
+		CompareWithVanilla(con, "t", "q, price, disc", dml_wheres);
+		auto plan = Run(con, "EXPLAIN SELECT price FROM t WHERE q BETWEEN 10 AND 19");
+		REQUIRE(plan->GetValue(1, 0).ToString().find("CUBIT_SCAN") != string::npos); // still the GPU scan
+		// UPDATE of the key column and of a payload column: both are index columns → DELETE + INSERT
+		auto up1 = Run(con, "UPDATE t SET q = q % 50 + 1 WHERE disc = 4 AND price > 0");
+		auto up2 = Run(con, "UPDATE t SET price = price + 7 WHERE q = 11");
+		REQUIRE(up1->GetValue(0, 0).GetValue<int64_t>() > 0 && up2->GetValue(0, 0).GetValue<int64_t>() > 0);
+		REQUIRE(CubitDmlAppendedRows() == app0 + NumericCast<idx_t>(up1->GetValue(0, 0).GetValue<int64_t>() + up2->GetValue(0, 0).GetValue<int64_t>()));
+		CompareWithVanilla(con, "t", "q, price, disc", dml_wheres);
+		// INSERT: past several segment boundaries of the bitvectors
+		Run(con, "INSERT INTO t SELECT (i * 31 % 50 + 1)::BIGINT, (i * 17 - 40000)::BIGINT, (i % 11)::BIGINT FROM range(150000) r(i)");
+		REQUIRE(CubitDmlAppendedRows() >= app0 + 150000);
+		CompareWithVanilla(con, "t", "q, price, disc", dml_wheres);
+		// inside a transaction with uncommitted changes only the vanilla scan can see them: no rewrite, right answers
+		Run(con, "BEGIN");
+		Run(con, "DELETE FROM t WHERE q = 3");
+		const idx_t rw = CubitRewriteCount();
+		auto in_txn = Run(con, "SELECT count(*) FROM t WHERE q < 4");
+		REQUIRE(CubitRewriteCount() == rw);
+		Run(con, "ROLLBACK");
+		auto after = Run(con, "SELECT count(*) FROM t WHERE q < 4");
+		REQUIRE(CubitRewriteCount() == rw + 1);
+		REQUIRE(after->GetValue(0, 0).GetValue<int64_t>() > in_txn->GetValue(0, 0).GetValue<int64_t>()); // the delete was rolled back
+		CompareWithVanilla(con, "t", "q, price, disc", dml_wheres);
+		Run(con, "BEGIN");
+		Run(con, "INSERT INTO t VALUES (24, 123456, 3), (25, -5, 4)");
+		Run(con, "DELETE FROM t WHERE q = 49 AND disc = 0");
+		Run(con, "COMMIT");
+		CompareWithVanilla(con, "t", "q, price, disc", dml_wheres);
+		// binned indexes get appended rows as pending deltas (their bin-id source column is temporary)
+		const vector<string> lq_wheres = {"l_quantity < 24 AND l_discount BETWEEN 0.05 AND 0.07", "l_discount = 0.03",
+		                                  "l_shipdate >= DATE '1994-01-01' AND l_shipdate < DATE '1995-01-01' AND l_quantity >= 10 AND l_quantity < 12"};
+		Run(con, "INSERT INTO lq SELECT CAST((i % 50 + 1) AS DECIMAL(15,2)), CAST(i / 7.0 AS DECIMAL(15,2)), CAST((i % 11) / 100.0 AS DECIMAL(15,2)), "
+		         "DATE '1993-06-15' + CAST((i * 7 % 700) AS INTEGER) FROM range(90000) r(i)");
+		Run(con, "DELETE FROM lq WHERE l_quantity = 11 AND l_discount = 0.06");
+		for (auto &w : lq_wheres) {
+			const string sql = "SELECT count(*), sum(l_extendedprice), sum(l_extendedprice * l_discount), min(rowid), max(rowid) FROM lq WHERE " + w;
+			const idx_t before = CubitRewriteCount();
+			auto a = Run(con, sql);
+			auto b = RunVanilla(con, sql);
+			REQUIRE(CubitRewriteCount() == before + 1);
+			for (idx_t c = 0; c < 5; c++) {
+				REQUIRE(a->GetValue(c, 0).ToString() == b->GetValue(c, 0).ToString());
+			}
+		}
+		// a key outside the indexed domain cannot be represented: the GPU copy steps aside (vanilla answers), reload fixes it
+		Run(con, "INSERT INTO t VALUES (77, 1, 1)");
+		const idx_t rw2 = CubitRewriteCount();
+		auto gone = Run(con, "SELECT count(*) FROM t WHERE q = 24");
+		REQUIRE(CubitRewriteCount() == rw2);
+		Run(con, "DELETE FROM t WHERE q = 77");
+		Run(con, "CALL cubit_load('t', 'q', 1, 50)");
+		auto back = Run(con, "SELECT count(*) FROM t WHERE q = 24");
+		REQUIRE(CubitRewriteCount() == rw2 + 1 && back->GetValue(0, 0) == gone->GetValue(0, 0));
+		CompareWithVanilla(con, "t", "q, price, disc", {"q BETWEEN 10 AND 19", "q = 24"}); // (positions of deleted rows hold no key)
+		// DROP TABLE + CREATE of the same name: a different table, no GPU copy, vanilla answers (no name-keyed registry)
+		Run(con, "CREATE TABLE dropme AS SELECT (i % 5)::BIGINT AS k, i::BIGINT AS v FROM range(10000) r(i)");
+		Run(con, "CALL cubit_load('dropme', 'k', 0, 5)");
+		Run(con, "DROP TABLE dropme");
+		Run(con, "CREATE TABLE dropme AS SELECT (i % 5)::BIGINT AS k, (i * 2)::BIGINT AS v FROM range(20000) r(i)");
+		const idx_t rw3 = CubitRewriteCount();
+		auto fresh = Run(con, "SELECT count(*), sum(v) FROM dropme WHERE k = 2");
+		REQUIRE(CubitRewriteCount() == rw3 && fresh->GetValue(0, 0).GetValue<int64_t>() == 4000);
+		REQUIRE(con.Query("SELECT * FROM cubit_scan('dropme', 1, 2)")->HasError());
+		// DECIMAL keys narrower than 64 bits keep their unscaled value (a numeric cast would round 0.05 to 0)
+		Run(con, "CREATE TABLE dn AS SELECT CAST((i % 11) / 100.0 AS DECIMAL(4,2)) AS d, i::BIGINT AS v FROM range(50000) r(i)");
+		Run(con, "CALL cubit_load('dn', 'd', 0, 11)");
+		const idx_t rw4 = CubitRewriteCount();
+		auto dn = Run(con, "SELECT count(*), sum(v) FROM dn WHERE d BETWEEN 0.05 AND 0.07");
+		auto dv = RunVanilla(con, "SELECT count(*), sum(v) FROM dn WHERE d BETWEEN 0.05 AND 0.07");
+		REQUIRE(CubitRewriteCount() == rw4 + 1 && dn->GetValue(0, 0) == dv->GetValue(0, 0) && dn->GetValue(1, 0).ToString() == dv->GetValue(1, 0).ToString());
+		REQUIRE(dn->GetValue(0, 0).GetValue<int64_t>() > 10000);
+		printf("dml through the index ok\n");
+	}
 	if (argc > 2 && string(argv[1]) == "--db") {
 		// Storage route: a FILE-backed, checkpointed table's columns reach the C-ABI as the compressed segments
 		// the reference wrote (BitPacking), lifted from the buffer manager — not as decoded rows.
@@ -302,24 +428,23 @@ int main(int argc, char **argv) {
 				}
 			}
 		}
-		// an UPDATE leaves un-checkpointed changes on the column: the route must decline and fall back
-		// DML keeps the vanilla scan and drops the (now stale) GPU index; an UPDATE leaves un-checkpointed
-		// changes on the column, so on the next load the segment route must decline for it and fall back
+		// an UPDATE of a resident column reaches the index as DELETE + INSERT: the GPU copy follows it; the rows it
+		// deleted stay in the table's segments, so the next load cannot use the segment route (physical position =
+		// row id only holds for the decoded, rowid-placed rows) and falls back for every column
 		Run(fcon, "SET wal_autocheckpoint='10GB'"); // keep the UPDATE un-checkpointed
-		const idx_t rw_before = CubitRewriteCount();
 		auto upd = Run(fcon, "UPDATE ft SET price = price + 1 WHERE q = 7");
-		REQUIRE(upd->GetValue(0, 0).GetValue<int64_t>() == 8000 && CubitRewriteCount() == rw_before);
-		REQUIRE(fcon.Query("SELECT * FROM cubit_scan('ft', 7, 7)")->HasError()); // index dropped by the DML
-		auto v1 = Run(fcon, "SELECT sum(price) FROM ft WHERE q = 7");            // vanilla scan again
-		REQUIRE(CubitRewriteCount() == rw_before);
+		REQUIRE(upd->GetValue(0, 0).GetValue<int64_t>() == 8000);
+		Run(fcon, "UPDATE ft_plain SET price = price + 1 WHERE q = 7");
+		const idx_t rw_before = CubitRewriteCount();
+		auto v1 = Run(fcon, "SELECT sum(price), count(*) FROM ft WHERE q = 7");
+		REQUIRE(CubitRewriteCount() == rw_before + 1);
 		auto u2 = Run(fcon, "SELECT sum(price), count(*) FROM ft_plain WHERE q = 7");
-		REQUIRE(v1->GetValue(0, 0).GetValue<int64_t>() ==
-		        u2->GetValue(0, 0).GetValue<int64_t>() + u2->GetValue(1, 0).GetValue<int64_t>());
+		REQUIRE(v1->GetValue(0, 0).ToString() == u2->GetValue(0, 0).ToString() && v1->GetValue(1, 0) == u2->GetValue(1, 0));
 		const idx_t seg_mid = CubitSegmentRouteCount();
 		Run(fcon, "CALL cubit_load('ft', 'q', 1, 50)");
-		REQUIRE(CubitSegmentRouteCount() == seg_mid + 3); // price fell back to decoded rows, the others did not
+		REQUIRE(CubitSegmentRouteCount() == seg_mid);
 		auto u1 = Run(fcon, "SELECT sum(price) FROM cubit_scan('ft', 7, 7)");
-		REQUIRE(u1->GetValue(0, 0).GetValue<int64_t>() == v1->GetValue(0, 0).GetValue<int64_t>());
+		REQUIRE(u1->GetValue(0, 0).ToString() == v1->GetValue(0, 0).ToString());
 		{ // RLE-compressed columns take the same route (CUBIT_SEG_RLE)
 			Run(fcon, "PRAGMA force_compression='rle'");
 			Run(fcon, "CREATE TABLE fr AS SELECT ((i // 3) * 7919 % 50 + 1)::BIGINT AS q, ((i // 40) * 104729 % 1000003 - 500000)::BIGINT AS price, "
@@ -342,6 +467,44 @@ int main(int argc, char **argv) {
 			}
 		}
 		printf("storage route ok\n");
+		{ // the CUBIT index is a catalog object of a registered index type: it is checkpointed with the table (its
+		  // images written to blocks by GetStorageInfo), bound again through create_instance when the file is
+		  // re-opened, and the first statement that can use it materialises the GPU copy from the images
+			Run(fcon, "CREATE TABLE pt AS SELECT (i * 7919 % 50 + 1)::BIGINT AS q, (i * 104729 % 1000003 - 500000)::BIGINT AS price, "
+			          "(i % 11)::BIGINT AS disc FROM range(250000) r(i)");
+			Run(fcon, "CALL cubit_load('pt', 'q', 1, 50)");
+			Run(fcon, "CALL cubit_load('pt', 'disc', 0, 11)");
+			Run(fcon, "DELETE FROM pt WHERE q = 24 AND disc = 3"); // pending deltas travel in the image
+			auto want = Run(fcon, "SELECT count(*), sum(price), sum(price * disc) FROM pt WHERE q BETWEEN 20 AND 29 AND disc < 5");
+			auto idx = Run(fcon, "SELECT index_name FROM duckdb_indexes() WHERE table_name = 'pt'");
+			REQUIRE(idx->RowCount() == 1 && idx->GetValue(0, 0).ToString() == "cubit_pt");
+			Run(fcon, "CHECKPOINT");
+		}
+	}
+	if (argc > 2 && string(argv[1]) == "--db") {
+		DuckDB rdb(argv[2]); // (the first instance went out of scope: the file is closed and re-opened)
+		Connection rcon(rdb);
+		RegisterCubitGpuFunctions(*rdb.instance);
+		const idx_t img0 = CubitImageLoads(), rw0 = CubitRewriteCount();
+		auto got = Run(rcon, "SELECT count(*), sum(price), sum(price * disc) FROM pt WHERE q BETWEEN 20 AND 29 AND disc < 5");
+		REQUIRE(CubitRewriteCount() == rw0 + 1);
+		REQUIRE(CubitImageLoads() == img0 + 2); // both indexes came from their checkpointed images
+		auto van = RunVanilla(rcon, "SELECT count(*), sum(price), sum(price * disc) FROM pt WHERE q BETWEEN 20 AND 29 AND disc < 5");
+		for (idx_t c = 0; c < 3; c++) {
+			REQUIRE(got->GetValue(c, 0).ToString() == van->GetValue(c, 0).ToString());
+		}
+		auto d24 = Run(rcon, "SELECT count(*) FROM pt WHERE q = 24 AND disc = 3");
+		REQUIRE(d24->GetValue(0, 0).GetValue<int64_t>() == 0);
+		// DML keeps working on the re-attached index
+		Run(rcon, "INSERT INTO pt VALUES (24, 5, 3), (24, 6, 3)");
+		auto d2 = Run(rcon, "SELECT count(*), sum(price) FROM pt WHERE q = 24 AND disc = 3");
+		if (d2->GetValue(0, 0).GetValue<int64_t>() != 2) {
+			fprintf(stderr, "after re-attach + INSERT: count %s sum %s\n", d2->GetValue(0, 0).ToString().c_str(), d2->GetValue(1, 0).ToString().c_str());
+		}
+		REQUIRE(d2->GetValue(0, 0).GetValue<int64_t>() == 2 && d2->GetValue(1, 0).GetValue<int64_t>() == 11);
+		Run(rcon, "DROP TABLE pt"); // CommitDrop releases the GPU memory and the image blocks
+		Run(rcon, "CHECKPOINT");
+		printf("index persistence ok\n");
 	}
 	auto err = con.Query("SELECT * FROM cubit_scan('nope', 1, 2)");
 	REQUIRE(err->HasError());

@@ -31,8 +31,14 @@ struct cubit_gpu_table {
 	uint64_t *valid[MAX_COLS];
 #define MAX_INDEXES 8
 	uint64_t *bits[MAX_INDEXES];
+	uint64_t *dbits[MAX_INDEXES]; /* pending deltas, dense (the mock has no reason to be sparse), NULL = none */
 	uint32_t card[MAX_INDEXES];
+	int32_t src_col[MAX_INDEXES]; /* column the index was built from (-1: uploaded / source dropped) */
+	int64_t src_base[MAX_INDEXES];
 	int n_indexes;
+};
+struct cubit_gpu_fetch_ticket {
+	int dummy;
 };
 struct cubit_gpu_result {
 	struct cubit_gpu_table *t;
@@ -59,7 +65,7 @@ int cubit_gpu_create(int device, uint64_t n_rows, int64_t row_base, uint32_t seg
 int cubit_gpu_destroy(cubit_gpu_table *t) {
 	if (!t) return CUBIT_OK;
 	for (int i = 0; i < MAX_COLS; i++) { free(t->cols[i]); free(t->valid[i]); }
-	for (int i = 0; i < t->n_indexes; i++) free(t->bits[i]);
+	for (int i = 0; i < t->n_indexes; i++) { free(t->bits[i]); free(t->dbits[i]); }
 	free(t);
 	return CUBIT_OK;
 }
@@ -78,6 +84,7 @@ int cubit_gpu_download_column(cubit_gpu_table *t, int32_t col_id, void *data, ui
 int cubit_gpu_drop_column(cubit_gpu_table *t, int32_t col_id) {
 	if (col_id < 0 || col_id >= MAX_COLS || !t->cols[col_id]) { snprintf(g_err, sizeof g_err, "mock: bad column"); return CUBIT_EINVAL; }
 	free(t->cols[col_id]); t->cols[col_id] = NULL; free(t->valid[col_id]); t->valid[col_id] = NULL;
+	for (int ix = 0; ix < t->n_indexes; ix++) if (t->src_col[ix] == col_id) t->src_col[ix] = -1;
 	return CUBIT_OK;
 }
 int cubit_gpu_upload_column_validity(cubit_gpu_table *t, int32_t col_id, const uint64_t *words, uint64_t n_words) {
@@ -115,25 +122,96 @@ int cubit_gpu_upload_column_segments(cubit_gpu_table *t, int32_t col_id, uint32_
 int cubit_gpu_index_create(cubit_gpu_table *t, uint32_t cardinality, int32_t *index_id) {
 	if (t->n_indexes == MAX_INDEXES) { snprintf(g_err, sizeof g_err, "mock: too many indexes"); return CUBIT_EINVAL; }
 	t->card[t->n_indexes] = cardinality; t->bits[t->n_indexes] = calloc((size_t)cardinality * t->n_words, 8);
+	t->src_col[t->n_indexes] = -1;
 	*index_id = t->n_indexes++;
 	return CUBIT_OK;
 }
 int cubit_gpu_index_build(cubit_gpu_table *t, int32_t index_id, int32_t col_id, int64_t base_value) {
 	if (index_id < 0 || index_id >= t->n_indexes) { snprintf(g_err, sizeof g_err, "mock: bad index"); return CUBIT_EINVAL; }
+	memset(t->bits[index_id], 0, (size_t)t->card[index_id] * t->n_words * 8);
 	oracle_build_index(t->cols[col_id], 8, t->n_rows, base_value, t->card[index_id], t->bits[index_id], t->n_words);
+	t->src_col[index_id] = col_id; t->src_base[index_id] = base_value;
 	return CUBIT_OK;
 }
+int cubit_gpu_add_delta_pairs(cubit_gpu_table *t, int32_t index_id, const uint32_t *value_ids, const int64_t *rows, uint64_t n) {
+	if (index_id < 0 || index_id >= t->n_indexes) { snprintf(g_err, sizeof g_err, "mock: bad index"); return CUBIT_EINVAL; }
+	if (!t->dbits[index_id]) t->dbits[index_id] = calloc((size_t)t->card[index_id] * t->n_words, 8);
+	for (uint64_t i = 0; i < n; i++) {
+		if (value_ids[i] >= t->card[index_id] || rows[i] < 0 || (uint64_t)rows[i] >= t->n_rows) { snprintf(g_err, sizeof g_err, "mock: bad delta pair"); return CUBIT_EINVAL; }
+		t->dbits[index_id][(size_t)value_ids[i] * t->n_words + (uint64_t)rows[i] / 64] ^= 1ull << ((uint64_t)rows[i] % 64);
+	}
+	return CUBIT_OK;
+}
+/* INSERT: columns grow, bitvectors are re-strided (the mock keeps them at exactly n_words), indexes built from a
+ * resident column index the new rows */
+int cubit_gpu_append_rows(cubit_gpu_table *t, uint64_t n_new, const cubit_append_column *cols, uint32_t n_cols) {
+	const uint64_t new_n = t->n_rows + n_new, new_w = (new_n + 63) / 64;
+	for (uint32_t i = 0; i < n_cols; i++) {
+		const int32_t c = cols[i].col_id;
+		if (c < 0 || c >= MAX_COLS || !t->cols[c] || cols[i].elem_bytes != 8) { snprintf(g_err, sizeof g_err, "mock: bad append column"); return CUBIT_EINVAL; }
+		if (t->valid[c]) { snprintf(g_err, sizeof g_err, "mock: append to a column with NULLs"); return CUBIT_ESTATE; }
+		t->cols[c] = realloc(t->cols[c], new_n * 8 + 8);
+		memcpy(t->cols[c] + t->n_rows, cols[i].data, n_new * 8);
+	}
+	for (int ix = 0; ix < t->n_indexes; ix++) {
+		for (int which = 0; which < 2; which++) {
+			uint64_t **pp = which ? &t->dbits[ix] : &t->bits[ix];
+			if (!*pp) continue;
+			uint64_t *nb = calloc((size_t)t->card[ix] * new_w, 8);
+			for (uint32_t v = 0; v < t->card[ix]; v++) memcpy(nb + (size_t)v * new_w, *pp + (size_t)v * t->n_words, t->n_words * 8);
+			free(*pp); *pp = nb;
+		}
+	}
+	const uint64_t old_n = t->n_rows;
+	t->n_rows = new_n; t->n_words = new_w;
+	for (int ix = 0; ix < t->n_indexes; ix++) { /* only the NEW rows are indexed, like the library (row_begin = old_n) */
+		if (t->src_col[ix] >= 0 && t->cols[t->src_col[ix]]) {
+			for (uint64_t r = old_n; r < new_n; r++) {
+				const int64_t v = t->cols[t->src_col[ix]][r] - t->src_base[ix];
+				if (v >= 0 && v < (int64_t)t->card[ix]) t->bits[ix][(size_t)v * new_w + r / 64] |= 1ull << (r % 64);
+			}
+		}
+	}
+	return CUBIT_OK;
+}
+int cubit_gpu_shard_count(const cubit_gpu_table *t, uint32_t *n) { (void)t; *n = 1; return CUBIT_OK; }
+/* index image: {n_rows, card, has_delta} + bits (+ delta bits) — the mock's own format */
+int cubit_gpu_index_serialize(cubit_gpu_table *t, int32_t index_id, void **image, uint64_t *bytes) {
+	if (index_id < 0 || index_id >= t->n_indexes) { snprintf(g_err, sizeof g_err, "mock: bad index"); return CUBIT_EINVAL; }
+	const uint64_t nb = (uint64_t)t->card[index_id] * t->n_words * 8, hd = t->dbits[index_id] ? 1 : 0;
+	uint64_t *img = malloc(40 + nb * (1 + hd));
+	img[0] = t->n_rows; img[1] = t->card[index_id]; img[2] = hd;
+	img[3] = (uint64_t)(int64_t)t->src_col[index_id]; img[4] = (uint64_t)t->src_base[index_id];
+	memcpy(img + 5, t->bits[index_id], nb);
+	if (hd) memcpy((char *)(img + 5) + nb, t->dbits[index_id], nb);
+	*image = img; *bytes = 40 + nb * (1 + hd);
+	return CUBIT_OK;
+}
+int cubit_gpu_index_deserialize(cubit_gpu_table *t, const void *image, uint64_t bytes, int32_t *index_id) {
+	const uint64_t *img = image;
+	if (bytes < 40 || img[0] != t->n_rows) { snprintf(g_err, sizeof g_err, "mock: image describes another table"); return CUBIT_EINVAL; }
+	const uint64_t nb = img[1] * t->n_words * 8;
+	if (bytes != 40 + nb * (1 + img[2])) { snprintf(g_err, sizeof g_err, "mock: bad image"); return CUBIT_EINVAL; }
+	int rc = cubit_gpu_index_create(t, (uint32_t)img[1], index_id);
+	if (rc) return rc;
+	t->src_col[*index_id] = (int32_t)(int64_t)img[3]; t->src_base[*index_id] = (int64_t)img[4];
+	memcpy(t->bits[*index_id], img + 5, nb);
+	if (img[2]) { t->dbits[*index_id] = malloc(nb); memcpy(t->dbits[*index_id], (const char *)(img + 5) + nb, nb); }
+	return CUBIT_OK;
+}
+void cubit_gpu_free_image(void *image) { free(image); }
 int cubit_gpu_free_result(cubit_gpu_result *r);
 int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_result **out) {
-	const uint64_t *streams[CUBIT_MAX_STREAMS]; int32_t group_of[CUBIT_MAX_STREAMS]; int k = 0;
+	const uint64_t *streams[CUBIT_MAX_STREAMS], *deltas[CUBIT_MAX_STREAMS]; int32_t group_of[CUBIT_MAX_STREAMS]; int k = 0;
 	for (uint32_t g = 0; g < q->n_groups; g++)
 		for (uint32_t i = 0; i < q->groups[g].n_refs; i++) {
 			const int32_t ix = q->groups[g].refs[i].index_id;
 			if (ix < 0 || ix >= t->n_indexes || q->groups[g].refs[i].value_id >= t->card[ix] || k >= CUBIT_MAX_STREAMS) { snprintf(g_err, sizeof g_err, "mock: bad bitvector ref"); return CUBIT_EINVAL; }
+			deltas[k] = t->dbits[ix] ? t->dbits[ix] + (size_t)q->groups[g].refs[i].value_id * t->n_words : NULL;
 			streams[k] = t->bits[ix] + (size_t)q->groups[g].refs[i].value_id * t->n_words; group_of[k++] = (int32_t)g;
 		}
 	uint64_t *qb = malloc(t->n_words * 8);
-	oracle_merge(streams, NULL, group_of, k, t->n_words, qb);
+	oracle_merge(streams, deltas, group_of, k, t->n_words, qb);
 	struct cubit_gpu_result *r = calloc(1, sizeof(*r));
 	r->t = t; r->count = oracle_popcount(qb, t->n_words);
 	r->ids = malloc((r->count + 1) * 8);
@@ -164,6 +242,7 @@ int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_result *
 int cubit_gpu_result_get(cubit_gpu_result *r, cubit_result_info *info) {
 	memset(info, 0, sizeof(*info));
 	info->count = r->count; info->sum_lo = r->sum_lo; info->sum_hi = r->sum_hi; info->agg_rows = r->agg_rows;
+	for (uint32_t c = 0; c < r->n_cols; c++) info->d_validity[c] = (const uint32_t *)r->vmask[c];
 	return CUBIT_OK;
 }
 int cubit_gpu_fetch(cubit_gpu_result *r, uint64_t offset, uint64_t n, int64_t *host_rowids, uint32_t n_cols,
@@ -173,6 +252,12 @@ int cubit_gpu_fetch(cubit_gpu_result *r, uint64_t offset, uint64_t n, int64_t *h
 	for (uint32_t c = 0; c < n_cols; c++) memcpy(host_cols[c], r->vals[c] + offset, n * 8);
 	return CUBIT_OK;
 }
+int cubit_gpu_fetch_async(cubit_gpu_result *r, uint64_t offset, uint64_t n, int64_t *host_rowids, uint32_t n_cols,
+                          void *const *host_cols, cubit_gpu_fetch_ticket **ticket) {
+	*ticket = calloc(1, sizeof(**ticket));
+	return cubit_gpu_fetch(r, offset, n, host_rowids, n_cols, host_cols);
+}
+int cubit_gpu_fetch_wait(cubit_gpu_fetch_ticket *ticket) { free(ticket); return CUBIT_OK; }
 int cubit_gpu_fetch_validity(cubit_gpu_result *r, uint32_t col, uint64_t offset, uint64_t n, uint64_t *host_words,
                              int *all_valid) {
 	if (offset + n > r->count || col >= r->n_cols) { snprintf(g_err, sizeof g_err, "mock: bad fetch"); return CUBIT_EINVAL; }

@@ -21,7 +21,8 @@ def test_sql_through_reference_duckdb_on_the_gpu(tmp_path):
     r = subprocess.run([os.path.join(REF, "duckdb_sql_gpu_test"), "--db", str(tmp_path / "route.db")],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
-    for marker in ("aggregate push-down ok", "multi-index conjunctions ok", "binned indexes ok", "null semantics ok", "storage route ok", "duckdb_sql_test ok"):
+    for marker in ("aggregate push-down ok", "multi-index conjunctions ok", "binned indexes ok", "null semantics ok",
+                   "dml through the index ok", "storage route ok", "index persistence ok", "duckdb_sql_test ok"):
         assert marker in r.stdout, r.stdout
 
 

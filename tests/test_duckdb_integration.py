@@ -52,3 +52,7 @@ def test_glue_sql_equals_vanilla_scan_with_oracle_mock(tmp_path):
     assert "duckdb_sql_test ok" in r.stdout
     # columns of a checkpointed, file-backed table reached the C-ABI as the reference's compressed segments
     assert "storage route ok" in r.stdout
+    # UPDATE / DELETE / INSERT reached the C-ABI through the registered CUBIT index type (BoundIndex::Append / Delete)
+    assert "dml through the index ok" in r.stdout
+    # ... and the index came back from its checkpointed image after the database file was re-opened
+    assert "index persistence ok" in r.stdout

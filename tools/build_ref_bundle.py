@@ -42,6 +42,13 @@ def main():
                                    "-lcubit_gpu", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../../duckdb-cubit_b200",
                                    "-lpthread", "-ldl"])
             print("built", dst)
+    # the reference's dbgen as a slice generator (config 3 on real TPC-H data): libduckdb.so only
+    src = os.path.join(ROOT, "tests", "cpp", "tpch_slices.cpp")
+    dst = os.path.join(OUT, "tpch_slices")
+    if stale(dst, [src]):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", REF_INC, src, "-o", dst, "-L", OUT, "-lduckdb",
+                               "-Wl,-rpath,$ORIGIN", "-lpthread", "-ldl"])
+        print("built", dst)
     # the reference's CPU path on the bench workload (bench.py cpu_baseline / --impl reference): no glue, no GPU
     # library — libduckdb.so + the oracle's table generator
     src = os.path.join(ROOT, "tests", "cpp", "duckdb_cfg2_baseline.cpp")

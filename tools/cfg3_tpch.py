@@ -1,0 +1,194 @@
+#!/usr/bin/env python
+"""BASELINE config 3 on REAL TPC-H data: lineitem generated slice by slice by the reference's own dbgen
+(baseline/_ref/tpch_slices = tests/cpp/tpch_slices.cpp linked with the reference's libduckdb.so), appended to ONE GPU
+table through the C-ABI (cubit_gpu_append_rows: the built indexes are extended on the GPU slice by slice, the host
+holds one slice at a time), then the Q6-style conjunctive bitmap predicate
+    (OR of the 12 months of 1994) AND (OR of discount in {0.05, 0.06, 0.07}) AND (OR of quantity in 1..23),  k = 38
+with the probe of l_extendedprice / l_discount and SUM(price * discount).
+
+Oracles: (a) the reference's answer file extension/tpch/dbgen/answers/sf<SF>/q06.csv (SF100: 12330426888.4637,
+SF1: 123141078.2283, SF0.1: 11803420.2534, SF0.01: 1193053.2253); (b) the unmodified reference DuckDB answering
+TPC-H Q6 as written (and the config-1 query l_quantity = 24) on every slice — summed over the slices that is its
+answer on the whole table, COUNT included.
+
+    python tools/cfg3_tpch.py --sf 100 --children 400 [--workers N] [--day-index] [--out profiles/r2_cfg3_sf100.json]
+"""
+import argparse
+import glob
+import importlib
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+from decimal import Decimal
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+SLICER = os.path.join(ROOT, "baseline", "_ref", "tpch_slices")
+ANSWER_FILE_Q6 = {"100": "12330426888.4637", "10": "1230113636.0101", "1": "123141078.2283", "0.1": "11803420.2534",
+                  "0.01": "1193053.2253"}
+COL_PRICE, COL_DISC, COL_QUNIT, COL_MONTH, COL_DAY = 0, 1, 2, 3, 4
+MONTH0 = (1992 - 1970) * 12        # month bin 0 = 1992-01
+DAY0 = 8035                        # 1992-01-01 in days since 1970-01-01 (first possible l_shipdate is 1992-01-02)
+
+
+def read_slice(path):
+    with open(path, "rb") as f:
+        n = int(np.fromfile(f, dtype=np.uint64, count=1)[0])
+        qty = np.fromfile(f, dtype=np.int64, count=n)
+        price = np.fromfile(f, dtype=np.int64, count=n)
+        disc = np.fromfile(f, dtype=np.int64, count=n)
+        ship = np.fromfile(f, dtype=np.int32, count=n)
+    assert len(ship) == n
+    month = (ship.astype("datetime64[D]").astype("datetime64[M]").astype(np.int64) - MONTH0).astype(np.int32)
+    return {COL_PRICE: price, COL_DISC: disc, COL_QUNIT: (qty // 100).astype(np.int32), COL_MONTH: month,
+            COL_DAY: (ship - DAY0).astype(np.int32)}
+
+
+def run(sf, children, workers=None, day_index=False, reps=7, log=print):
+    cubit = importlib.import_module("duckdb-cubit_b200")
+    if not os.path.exists(SLICER):
+        raise RuntimeError("baseline/_ref/tpch_slices not built (tools/build_ref_bundle.py, build container)")
+    workers = workers or max(1, (os.cpu_count() or 2) - 1)
+    workers = min(workers, children)
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > (8 << 30) else None
+    tmp = tempfile.mkdtemp(prefix="cubit_tpch_", dir=shm)
+    procs = [subprocess.Popen([SLICER, str(sf), str(children), str(w), str(workers), tmp]) for w in range(workers)]
+    t = None
+    ix = {}
+    ref = {"rows": 0, "q6_count": 0, "q6_revenue": Decimal(0), "q24_count": 0, "q24_sum_price": Decimal(0)}
+    t_gen0 = time.time()
+    append_s = 0.0
+    try:
+        for step in range(children):
+            path = os.path.join(tmp, "slice_%d.bin" % step)
+            while not os.path.exists(path):
+                for p in procs:
+                    if p.poll() not in (None, 0):
+                        raise RuntimeError("tpch_slices failed (rc %d)" % p.returncode)
+                time.sleep(0.02)
+            cols = read_slice(path)
+            meta = json.load(open(os.path.join(tmp, "slice_%d.json" % step)))
+            os.unlink(path)
+            for k in ("rows", "q6_count", "q24_count"):
+                ref[k] += int(meta[k])
+            ref["q6_revenue"] += Decimal(meta["q6_revenue"])
+            ref["q24_sum_price"] += Decimal(meta["q24_sum_price"])
+            if not day_index:
+                cols.pop(COL_DAY)
+            a0 = time.time()
+            if t is None:
+                t = cubit.CubitTable(len(cols[COL_PRICE]))
+                for c, a in cols.items():
+                    t.upload_column(c, a)
+                # the three CUBIT indexes of SURVEY §8d config 3, built on the GPU from the first slice and EXTENDED
+                # on the GPU by every append (BoundIndex::Append analog)
+                for name, col, base, card in (("quantity", COL_QUNIT, 1, 50), ("discount", COL_DISC, 0, 11),
+                                              ("month", COL_MONTH, 0, 84)):
+                    ix[name] = t.create_index(card)
+                    t.build_index(ix[name], col, base)
+            else:
+                t.append_rows(cols)
+            append_s += time.time() - a0
+            if step % 50 == 0:
+                log("slice %d/%d: %d rows resident, %.0f s" % (step + 1, children, t.n_rows, time.time() - t_gen0))
+        for p in procs:
+            p.wait()
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        shutil.rmtree(tmp, ignore_errors=True)
+    gen_s = time.time() - t_gen0
+    n = t.n_rows
+    assert n == ref["rows"], (n, ref["rows"])
+    out = {"sf": str(sf), "children": children, "workers": workers, "rows": n, "generate_and_ingest_s": gen_s,
+           "append_s": append_s, "reference": {k: str(v) for k, v in ref.items()}}
+    for name, card in (("quantity", 50), ("discount", 11), ("month", 84)):
+        assert sum(t.bitvector_count(ix[name], v) for v in range(card)) == n, name  # every row is in exactly one bitvector
+    groups = [[(ix["month"], m) for m in range(24, 36)], [(ix["discount"], d) for d in (5, 6, 7)],
+              [(ix["quantity"], q - 1) for q in range(1, 24)]]
+
+    def timed(flags, **kw):
+        best = None
+        for _ in range(reps):
+            with t.query(groups, flags=flags | cubit.Q_TIMING, **kw) as r:
+                cur = (r.info.ms_scan + r.info.ms_probe, r.info.ms_scan, r.info.ms_probe, r.count, r.sum,
+                       r.info.algo_bytes_scan, r.info.algo_bytes_probe)
+            if best is None or cur[0] < best[0]:
+                best = cur
+        return best
+
+    # ---- TPC-H Q6 on the GPU: k = 38 bitvectors, SUM(l_extendedprice * l_discount) at DECIMAL(18,4) scale
+    tot, ms_scan, ms_probe, count, rev, by_scan, by_probe = timed(0, agg=cubit.AGG_SUM_PROD, agg_a=COL_PRICE, agg_b=COL_DISC)
+    revenue = Decimal(rev) / Decimal(10000)
+    out["q6"] = {"count": count, "revenue": str(revenue), "k": 38, "ms_scan": ms_scan, "ms_probe": ms_probe,
+                 "scan_algo_GBps": by_scan / (ms_scan * 1e-3) / 1e9 if ms_scan else None,
+                 "rows_per_s": n / (tot * 1e-3)}
+    assert count == ref["q6_count"], (count, ref["q6_count"])
+    assert revenue == ref["q6_revenue"], (revenue, ref["q6_revenue"])
+    if str(sf) in ANSWER_FILE_Q6:
+        assert revenue == Decimal(ANSWER_FILE_Q6[str(sf)]), (revenue, ANSWER_FILE_Q6[str(sf)])
+        out["q6"]["answer_file"] = ANSWER_FILE_Q6[str(sf)]
+    # ---- the same predicate returning rows: sorted row IDs + both probed columns
+    tot, ms_scan, ms_probe, count2, _s, by_scan, by_probe = timed(cubit.Q_ROWIDS | cubit.Q_VALUES, cols=[COL_PRICE, COL_DISC])
+    out["q6_rows"] = {"count": count2, "ms_scan": ms_scan, "ms_probe": ms_probe, "rows_per_s": n / (tot * 1e-3),
+                      "scan_algo_GBps": by_scan / (ms_scan * 1e-3) / 1e9 if ms_scan else None}
+    assert count2 == count
+    with t.query(groups, flags=cubit.Q_ROWIDS | cubit.Q_VALUES, cols=[COL_PRICE, COL_DISC]) as r:
+        acc, prev = 0, -1
+        for off in range(0, r.count, 1 << 24):
+            ids, (pr, di) = r.fetch(off, min(1 << 24, r.count - off))
+            assert ids[0] > prev and (np.diff(ids) > 0).all()
+            assert di.min() >= 5 and di.max() <= 7
+            prev = int(ids[-1])
+            acc += int(np.dot(pr, di))  # exact: |price * discount| < 2^27, 2^24 rows per window
+        assert acc == rev, "Σ price*discount over the fetched rows differs from the fused aggregate"
+    # ---- config 1 at this scale: equality predicate + SUM(l_extendedprice)
+    q24 = [[(ix["quantity"], 23)]]
+    best = None
+    for _ in range(reps):
+        with t.query(q24, flags=cubit.Q_TIMING, agg=cubit.AGG_SUM, agg_a=COL_PRICE) as r:
+            cur = (r.info.ms_total, r.count, r.sum)
+        best = cur if best is None or cur[0] < best[0] else best
+    out["q24"] = {"ms": best[0], "count": best[1], "sum_price": str(Decimal(best[2]) / 100)}
+    assert best[1] == ref["q24_count"] and Decimal(best[2]) / 100 == ref["q24_sum_price"]
+    if day_index:
+        # ---- (f)4 at config-3 scale: the DAY-level l_shipdate index (2,526 bitvectors) kept as containers in HBM
+        dx = t.create_index(2526, compressed=True)
+        t0 = time.time()
+        t.build_index(dx, COL_DAY, 0)
+        info = t.index_info(dx)
+        out["day_index"] = {"build_s": time.time() - t0, "resident_bytes": int(info.resident_bytes),
+                            "verbatim_bytes": int(info.verbatim_bytes)}
+        # one month of days ANDed with the other two groups must select what the month bin selects
+        jan94 = int((np.datetime64("1994-01-01") - np.datetime64("1992-01-01")).astype(int))
+        gd = [[(dx, jan94 + d) for d in range(31)], groups[1], groups[2]]
+        gm = [[(ix["month"], 24)], groups[1], groups[2]]
+        with t.query(gd, flags=cubit.Q_TIMING, agg=cubit.AGG_SUM_PROD, agg_a=COL_PRICE, agg_b=COL_DISC) as r1, \
+                t.query(gm, flags=cubit.Q_TIMING, agg=cubit.AGG_SUM_PROD, agg_a=COL_PRICE, agg_b=COL_DISC) as r2:
+            assert (r1.count, r1.sum) == (r2.count, r2.sum)
+            out["day_index"].update({"jan94_count": r1.count, "ms_scan_31_day_containers": r1.info.ms_scan,
+                                     "ms_scan_1_month_bitvector": r2.info.ms_scan})
+    t.close()
+    return out
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sf", default="1")
+    ap.add_argument("--children", type=int, default=4)
+    ap.add_argument("--workers", type=int, default=None)
+    ap.add_argument("--day-index", action="store_true")
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    res = run(a.sf, a.children, a.workers, a.day_index)
+    print(json.dumps(res))
+    if a.out:
+        json.dump(res, open(a.out, "w"), indent=1)

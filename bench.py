@@ -13,9 +13,11 @@ kernel (gather + SUM).
     value  = table rows covered per second, inputs resident in HBM, device-timed (CUDA events)
     e2e    = the same sweep through the synchronous C-ABI call a DuckDB table function makes
              (host predicate structs in, aggregate row + first 2048-row DataChunk out)
-Multi-GPU (torchrun, one rank per GPU): weak scaling, every rank owns --rows rows of a
-row-range-sharded table (row_base = rank * rows); the only collective is one NCCL
-all-reduce of the six (COUNT, SUM) aggregates per step.
+Multi-GPU (torchrun, one rank per GPU): weak scaling by default — every rank owns --rows rows of a
+row-range-sharded table (row_base = rank * rows); --scaling strong cuts ONE --rows-row table over the ranks
+(config 5: --rows 16000000000 --workload cfg5).  The only collective is one NCCL all-reduce per step of the
+(COUNT, SUM) limbs, which the library accumulates ON THE DEVICE behind each query (cubit_gpu_result_add_limbs): no
+aggregate visits the host inside the timed region.
 
 --impl reference times the CPU restatement of the same path (oracle/, multi-threaded C) on
 this box's host cores: the mounted reference has no CUBIT source to run.
@@ -180,11 +182,20 @@ def run_reference(args):
     return 0
 
 
-def workload_config(rows, gpus):
-    return {"workload": "cfg2: synthetic %d-row table per GPU, cardinality-100 CUBIT index, range predicate OR over "
+def workload_config(rows, gpus, scaling="weak", workload="cfg2"):
+    if workload == "cfg5":
+        return {"workload": "cfg5: ONE synthetic %d-row table row-range sharded over %d GPU(s), 8 predicates (OR over 8 value "
+                            "bitvectors; AND of two OR-of-4 groups), 10 %% of the rows on values 10..19; step = the two "
+                            "queries, each merge+decode→sorted int64 row IDs (+ payload probe and SUM when the payload "
+                            "fits)" % (rows, gpus),
+                "rows_total": rows, "k_bitvectors": 8, "seg_bits": 65536, "scaling": scaling,
+                "l2_policy": "inputs larger than L2", "sharding": "row-range, %d shard(s)" % gpus}
+    return {"workload": "cfg2: synthetic %d-row table %s, cardinality-100 CUBIT index, range predicate OR over "
                         "10 bitvectors (values 10..19), selectivity sweep %s; step = the 6-query sweep, each query "
-                        "merge+decode→sorted int64 row IDs→probe int64 payload→COUNT,SUM" % (rows, ",".join(SELECTIVITIES)),
-            "rows_per_gpu": rows, "cardinality": CARD, "k_bitvectors": HOT_N, "selectivities": SELECTIVITIES,
+                        "merge+decode→sorted int64 row IDs→probe int64 payload→COUNT,SUM"
+                        % (rows, "per GPU" if scaling == "weak" else "sharded over the GPUs", ",".join(SELECTIVITIES)),
+            "rows_per_gpu" if scaling == "weak" else "rows_total": rows, "cardinality": CARD, "k_bitvectors": HOT_N,
+            "selectivities": SELECTIVITIES,
             "seg_bits": 65536, "l2_policy": "inputs larger than L2 (1.25 GB of bitvectors per query vs 126 MB L2)",
             "sharding": "row-range, %d shard(s)" % gpus}
 
@@ -206,51 +217,80 @@ def run_b200(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    rows = args.rows
     seg_bits = 65536
-    rows_pad = (rows + seg_bits - 1) // seg_bits * seg_bits
-    row_base = rank * rows_pad  # weak scaling: every rank owns `rows` rows of a world*rows table
+    strong = args.scaling == "strong"
+    cfg5 = args.workload == "cfg5"
+    if strong:   # ONE table of --rows rows cut into contiguous row ranges of whole segments
+        lo, hi = sharding.shard_ranges(args.rows, world, seg_bits)[rank]
+        rows, row_base = hi - lo, lo
+        total_rows = args.rows
+    else:        # weak scaling: every rank owns --rows rows of a world * rows table
+        rows = args.rows
+        row_base = rank * ((rows + seg_bits - 1) // seg_bits * seg_bits)
+        total_rows = world * rows
 
     t = cubit.CubitTable(rows, row_base=row_base, seg_bits=seg_bits, device=local)
-    stream = torch.cuda.current_stream()
+    # ONE stream for the library's kernels, torch's limb arithmetic and NCCL's ordering: a real (non-default) torch
+    # stream made current — the legacy default stream has handle 0, which the library reads as "use your own stream"
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     t.set_stream(stream.cuda_stream)
     t_build0 = time.time()
-    t.synth_column(COL_PAYLOAD, 0)
-    indexes, expect = [], []
-    for s in SELECTIVITIES:
-        t.synth_column(COL_VALUE, 1, seed=SEED, threshold=threshold(s), card=CARD, hot_lo=HOT_LO, hot_n=HOT_N)
-        ix = t.create_index(CARD)
+    with_payload = rows <= 8_000_000_000  # 8 B/row payload + index + row IDs must fit 180 GB
+    if with_payload:
+        t.synth_column(COL_PAYLOAD, 0)
+    indexes, expect, plans_async, plans_sync, labels = [], [], [], [], []
+    flags = cubit.Q_ROWIDS | (cubit.Q_VALUES if with_payload else 0)
+    kw = dict(cols=[COL_PAYLOAD], agg=cubit.AGG_SUM, agg_a=COL_PAYLOAD) if with_payload else {}
+    if cfg5:
+        t.synth_column(COL_VALUE, 1, seed=SEED, threshold=threshold("0.1"), card=CARD, hot_lo=HOT_LO, hot_n=HOT_N)
+        ix = t.create_index(18)  # only the bitvectors the two queries read are kept (values 0..17)
         t.build_index(ix, COL_VALUE, 0)
-        indexes.append(ix)
-        expect.append(sum(t.bitvector_count(ix, v) for v in range(HOT_LO, HOT_LO + HOT_N)))
+        pop = [t.bitvector_count(ix, v) for v in range(18)]
+        qs = [("or_of_8", [[(ix, v) for v in range(10, 18)]], sum(pop[10:18])),
+              ("and_of_two_or_of_4", [[(ix, v) for v in (10, 11, 12, 13)], [(ix, v) for v in (12, 13, 14, 15)]], pop[12] + pop[13])]
+        for name, groups, want in qs:
+            labels.append(name)
+            expect.append(want)
+            plans_async.append(cubit.QueryPlan(groups, flags | cubit.Q_ASYNC | cubit.Q_TIMING, **kw))
+            plans_sync.append(cubit.QueryPlan(groups, flags, **kw))
+    else:
+        for s in SELECTIVITIES:
+            t.synth_column(COL_VALUE, 1, seed=SEED, threshold=threshold(s), card=CARD, hot_lo=HOT_LO, hot_n=HOT_N)
+            ix = t.create_index(CARD)
+            t.build_index(ix, COL_VALUE, 0)
+            indexes.append(ix)
+            expect.append(sum(t.bitvector_count(ix, v) for v in range(HOT_LO, HOT_LO + HOT_N)))
+            groups = [[(ix, v) for v in range(HOT_LO, HOT_LO + HOT_N)]]
+            labels.append(s)
+            plans_async.append(cubit.QueryPlan(groups, flags | cubit.Q_ASYNC | cubit.Q_TIMING, **kw))
+            plans_sync.append(cubit.QueryPlan(groups, flags, **kw))
     t.drop_column(COL_VALUE)
     build_s = time.time() - t_build0
+    n_q = len(plans_async)
 
-    flags = cubit.Q_ROWIDS | cubit.Q_VALUES
-    mk = lambda ix, extra: cubit.QueryPlan([[(ix, v) for v in range(HOT_LO, HOT_LO + HOT_N)]], flags | extra,  # noqa
-                                           cols=[COL_PAYLOAD], agg=cubit.AGG_SUM, agg_a=COL_PAYLOAD)
-    plans_async = [mk(ix, cubit.Q_ASYNC | cubit.Q_TIMING) for ix in indexes]
-    plans_sync = [mk(ix, 0) for ix in indexes]
-    n_words = t.n_words
+    # (COUNT, SUM) of every query of a step as int64 limbs ON THE DEVICE: the library adds them behind each query
+    # (cubit_gpu_result_add_limbs), one NCCL all-reduce per step sums them over the ranks, a running total keeps the
+    # steps — nothing is read back before the timed region ends
+    step_limbs = torch.zeros(5 * n_q, dtype=torch.int64, device=dev)
+    total_limbs = torch.zeros(5 * n_q, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
 
     def step_device():
+        step_limbs.zero_()
         res = [t.execute(p) for p in plans_async]
+        for i, r in enumerate(res):
+            r.add_limbs(step_limbs.data_ptr() + 40 * i)
+        if world > 1:  # the one collective of the path: exact global COUNT/SUM of the step's queries
+            dist.all_reduce(step_limbs)
+        total_limbs.add_(step_limbs)
         for r in res:
             r.wait()
-        agg = [(r.count, r.sum) for r in res]
-        if world > 1:  # the one collective of the path: exact global COUNT/SUM of the six queries
-            limbs = []
-            for c, sm in agg:
-                limbs += sharding.to_limbs(c, sm)
-            tt = torch.tensor(limbs, dtype=torch.int64, device=dev)
-            dist.all_reduce(tt)
-            fl = tt.tolist()
-            agg = [sharding.from_limbs(fl[i * 5:(i + 1) * 5]) for i in range(len(res))]
         infos = [(r.info.ms_scan, r.info.ms_probe, r.info.algo_bytes_scan, r.info.algo_bytes_probe, r.count,
                   r.info.n_launches, r.info.fused) for r in res]
         for r in res:
             r.free()
-        return agg, infos
+        return infos
 
     def barrier():
         torch.cuda.synchronize()
@@ -259,11 +299,13 @@ def run_b200(args):
             torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        agg, infos = step_device()
-    # correctness of what is being timed: COUNT equals Σ popcount of the (disjoint) value
-    # bitvectors and SUM(payload) equals the closed form only via the global check below
+        infos = step_device()
+    # correctness of what is being timed: COUNT equals Σ popcount of the (disjoint) value bitvectors; SUM(payload)
+    # is checked against the row IDs below and globally through the limbs
     for inf, e in zip(infos, expect):
         assert inf[4] == e, "count %d != expected %d" % (inf[4], e)
+    barrier()
+    total_limbs.zero_()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -276,11 +318,11 @@ def run_b200(args):
     e0.record(stream)
     # per-kernel accumulators: [ms, algorithmic bytes, launches]
     kscan, kprobe = [0.0, 0, 0], [0.0, 0, 0]
-    per_sel = [dict(ms_scan=0.0, ms_probe=0.0, by_scan=0, by_probe=0, cnt=0, fused=0) for _ in SELECTIVITIES]
+    per_q = [dict(ms_scan=0.0, ms_probe=0.0, by_scan=0, by_probe=0, cnt=0, fused=0) for _ in range(n_q)]
     for _ in range(args.steps):
-        agg, infos = step_device()
+        infos = step_device()
         for i, (ms_s, ms_p, by_s, by_p, cnt, _nl, fused) in enumerate(infos):
-            ps = per_sel[i]
+            ps = per_q[i]
             ps["cnt"], ps["fused"] = cnt, fused
             ps["ms_scan"] += ms_s
             ps["ms_probe"] += ms_p
@@ -293,7 +335,7 @@ def run_b200(args):
                 kprobe[0] += ms_p
                 kprobe[1] += by_p
                 kprobe[2] += 1
-            else:               # probe fused into the scan kernel
+            else:               # probe fused into the scan kernel (or no probe)
                 kscan[0] += ms_s
                 kscan[1] += by_s + by_p
                 kscan[2] += 1
@@ -311,75 +353,110 @@ def run_b200(args):
         launches = int(tl.item())
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     ms_per_step = ms / args.steps
-    n_q = len(SELECTIVITIES)
-    value = world * n_q * rows / (ms_per_step * 1e-3)
+    value = total_rows * n_q / (ms_per_step * 1e-3)
+    # the limbs, now that the timed region is over: steps x the global (COUNT, SUM) of every query
+    tl_host = total_limbs.cpu().tolist()
+    global_agg = []
+    for i in range(n_q):
+        c, l0, l1, l2, l3 = tl_host[5 * i:5 * i + 5]
+        assert c % args.steps == 0
+        global_agg.append((c // args.steps, (l0 + (l1 << 32) + (l2 << 64) + (l3 << 96)) // args.steps))
+    if world == 1:
+        for (c, _s), e in zip(global_agg, expect):
+            assert c == e, "COUNT from the device limbs %s != expected %s (limbs %s)" % (
+                [g[0] for g in global_agg], expect, tl_host)
+    else:
+        ge = torch.tensor(expect, dtype=torch.int64, device=dev)
+        dist.all_reduce(ge)
+        assert [c for c, _ in global_agg] == ge.tolist(), "global COUNT differs from the sum of the shards' popcounts"
 
-    # ---- e2e: the synchronous C-ABI call path with host buffers (what the table function does)
+    # ---- e2e: the synchronous C-ABI call path with host buffers (what the table function does when the aggregate is
+    # pushed down): host predicate structs in, COUNT/SUM row + the first DataChunk out.  NOT a row-returning number.
     chunk = 2048
     ids_host = np.empty(chunk, dtype=np.int64)
-    val_host = [np.empty(chunk, dtype=np.int64)]
+    val_host = [np.empty(chunk, dtype=np.int64)] if with_payload else []
     scan_args_bytes = 64 * 8 * 3 + 160  # kernel-parameter block carrying the flattened predicate
 
     def step_e2e():
-        out = []
-        for p in plans_sync:
+        step_limbs.zero_()
+        for i, p in enumerate(plans_sync):
             with t.execute(p) as r:            # blocks until COUNT/SUM are on the host
                 n = min(chunk, r.count)
                 r.fetch(0, n, out_ids=ids_host, out_cols=val_host)   # first DataChunk (GetData call #1)
-                out.append((r.count, r.sum))
+                if world > 1:
+                    r.add_limbs(step_limbs.data_ptr() + 40 * i)
         if world > 1:
-            limbs = []
-            for c, sm in out:
-                limbs += sharding.to_limbs(c, sm)
-            tt = torch.tensor(limbs, dtype=torch.int64, device=dev)
-            dist.all_reduce(tt)
-            fl = tt.tolist()
-            out = [sharding.from_limbs(fl[i * 5:(i + 1) * 5]) for i in range(n_q)]
-        return out
+            dist.all_reduce(step_limbs)
+            return step_limbs.cpu()            # the global aggregate row reaches the host: part of the call
+        return None
 
     for _ in range(max(1, args.warmup)):
-        e2e_out = step_e2e()
+        step_e2e()
     barrier()
     w0 = time.perf_counter()
     for _ in range(args.steps):
-        e2e_out = step_e2e()
+        step_e2e()
     barrier()
     e2e_s = time.perf_counter() - w0
     if world > 1:
         tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
-    e2e_value = world * n_q * rows / (e2e_s / args.steps)
-    # global self-check: payload = global row id, so SUM(payload) must equal SUM(row ids);
-    # verified exactly on rank 0's shard for the smallest query by fetching its row IDs
+    e2e_value = total_rows * n_q / (e2e_s / args.steps)
+    # self-check on this rank's shard for the smallest query: payload = global row id, so the probed values must
+    # equal the row IDs, SUM(payload) their sum, and the IDs must ascend inside the shard's row range
     with t.execute(plans_sync[0]) as r:
-        ids, (vals,) = r.fetch()
-        assert (ids == vals).all() and int(ids.sum()) == r.sum and (np.diff(ids) > 0).all()
-    for (c, _s), e in zip(agg, expect):
-        if world == 1:
-            assert c == e
+        if with_payload:
+            ids, (vals,) = r.fetch()
+            assert (ids == vals).all() and int(ids.sum()) == r.sum
+        else:
+            ids, _ = r.fetch()
+        assert (np.diff(ids) > 0).all() and (len(ids) == 0 or (ids[0] >= row_base and ids[-1] < row_base + rows))
 
-    # ---- full materialisation to host (every row ID + value over PCIe), reported beside e2e
+    # ---- row-returning e2e: EVERY selected row ID + payload value to page-locked host memory, on every rank, through
+    # the asynchronous hand-off (two windows in flight per result: window i+1 crosses PCIe while window i is consumed)
     e2e_full = None
-    if world == 1 and not args.no_materialize:
-        cap = max(expect)
-        pin_ids = torch.empty(cap, dtype=torch.int64, pin_memory=True).numpy()
-        pin_val = [torch.empty(cap, dtype=torch.int64, pin_memory=True).numpy()]
+    if not args.no_materialize:
+        win = 1 << 22
+        ncols = 1 if with_payload else 0
+        bufs = [(torch.empty(win, dtype=torch.int64, pin_memory=True).numpy(),
+                 [torch.empty(win, dtype=torch.int64, pin_memory=True).numpy() for _ in range(ncols)]) for _ in range(2)]
 
         def step_full():
+            moved = 0
             for p in plans_sync:
                 with t.execute(p) as r:
-                    r.fetch(0, r.count, out_ids=pin_ids, out_cols=pin_val)
+                    cnt = r.count
+                    nwin = (cnt + win - 1) // win
+                    tk = [None, None]
+                    if nwin:
+                        tk[0] = r.fetch_async(0, min(win, cnt), bufs[0][0], bufs[0][1])
+                    for w in range(nwin):
+                        if w + 1 < nwin:
+                            o = (w + 1) * win
+                            tk[(w + 1) & 1] = r.fetch_async(o, min(win, cnt - o), bufs[(w + 1) & 1][0], bufs[(w + 1) & 1][1])
+                        r.fetch_wait(tk[w & 1])   # window w is in host memory: the consumer would read it here
+                    moved += cnt * 8 * (1 + ncols)
+            return moved
         step_full()
-        torch.cuda.synchronize()
+        barrier()
         w0 = time.perf_counter()
         reps = max(1, min(2, args.steps))
         for _ in range(reps):
-            step_full()
-        torch.cuda.synchronize()
+            moved = step_full()
+        barrier()
         dt = (time.perf_counter() - w0) / reps
-        e2e_full = {"value": n_q * rows / dt, "unit": "rows/s", "d2h_bytes_per_step": 16 * sum(expect),
-                    "note": "every selected row ID + payload value copied to pinned host memory (PCIe bound)"}
+        if world > 1:
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            tm = torch.tensor([moved], dtype=torch.int64, device=dev)
+            dist.all_reduce(tm)
+            moved = int(tm.item())
+        e2e_full = {"value": total_rows * n_q / dt, "unit": "rows/s", "d2h_bytes_per_step": moved,
+                    "pcie_GBps_all_gpus": moved / dt / 1e9,
+                    "note": "every selected row ID + payload value copied to page-locked host memory on every rank "
+                            "(asynchronous double-buffered hand-off; PCIe bound)"}
 
     if rank != 0:
         t.close()
@@ -400,43 +477,50 @@ def run_b200(args):
         ms, by, n = acc
         ach = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "frac_of_nominal_8TBs": ach / 8000.0, "traffic": traffic.get(tkey), "peak_source": peak_src,
+                "frac_of_nominal_8TBs": ach / 8000.0, "traffic": traffic.get(tkey), "traffic_source": traffic.get("source"),
+                "peak_source": peak_src,
                 "launches": n, "bytes_per_launch_avg": by / n if n else 0, "ms_per_launch_avg": ms / n if n else 0,
                 "share_of_step": ms / (ms_per_step * args.steps) if ms_per_step > 0 else 0, "bytes_formula": formula}
 
-    roof_scan = roof(kscan, "cubit_scan_kernel<4,false,0> (segment merge + bit->row-ID decode, single pass)",
+    roof_scan = roof(kscan, "cubit_scan_kernel<4,false,0,true,false> (segment merge + bit->row-ID decode, single pass)",
                      "cubit_scan_kernel_dram_bytes_per_launch",
                      "k*ceil(N/64)*8 + 8*M  [SURVEY 8d]")
-    roof_probe = roof(kprobe, "cubit_probe_bits_kernel<4,1,true> (bit-driven probe: gather payload + SUM; "
-                      "cubit_probe_kernel over the row-ID list for the two sparsest points)",
+    roof_probe = roof(kprobe, "cubit_probe_bits_kernel<4,1,true,false> (bit-driven probe: gather payload + SUM; "
+                      "cubit_probe_kernel over the row-ID list for the sparsest points)",
                       "cubit_probe_bits_kernel_dram_bytes_per_launch",
                       "8*M payload values read + ceil(N/64)*8 re-read of the merged bitvector  [SURVEY 8d: P]")
     dominant = roof_probe if kprobe[0] > kscan[0] else roof_scan
     sweep = []
-    for s, ps in zip(SELECTIVITIES, per_sel):
+    for s, ps in zip(labels, per_q):
         ms_tot = (ps["ms_scan"] + ps["ms_probe"]) / args.steps
         g_scan = ps["by_scan"] / (ps["ms_scan"] * 1e-3) / 1e9 if ps["ms_scan"] > 0 else 0.0
-        sweep.append({"selectivity": s, "rows_selected": ps["cnt"], "probe_fused": bool(ps["fused"] and ps["ms_probe"] == 0),
+        sweep.append({"query" if cfg5 else "selectivity": s, "rows_selected": ps["cnt"],
+                      "probe_fused": bool(ps["fused"] and ps["ms_probe"] == 0),
                       "scan_ms": ps["ms_scan"] / args.steps, "probe_ms": ps["ms_probe"] / args.steps,
                       "rows_per_s": rows / (ms_tot * 1e-3) if ms_tot > 0 else 0.0,
                       "scan_algo_gbs": g_scan, "scan_frac_of_peak": g_scan / peak})
     kernel_bytes = kscan[1] + kprobe[1]
     line = {
         "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(rows, world),
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args.rows, world, args.scaling, args.workload),
         "hbm_gbs": world * (kernel_bytes / args.steps) / (ms_per_step * 1e-3) / 1e9,
         "roofline": dominant, "roofline_merge_decode": roof_scan, "roofline_probe": roof_probe,
         "sweep": sweep,
+        "aggregate_reduce": "device limbs (cubit_gpu_result_add_limbs) + one NCCL all-reduce per step" if world > 1
+                            else "device limbs (cubit_gpu_result_add_limbs)",
         "e2e": {"value": e2e_value, "unit": "rows/s",
                 "h2d_bytes_per_step": n_q * scan_args_bytes,
-                "d2h_bytes_per_step": n_q * (32 + 2 * 8 * chunk),
+                "d2h_bytes_per_step": n_q * (32 + (1 + len(val_host)) * 8 * chunk),
+                "path": "aggregate push-down + first DataChunk",
                 "note": "synchronous cubit_gpu_query + cubit_gpu_fetch of the first 2048-row DataChunk per query; "
-                        "host predicate structs in, COUNT/SUM row + chunk out"},
+                        "host predicate structs in, COUNT/SUM row + chunk out.  This is the aggregate-push-down path: "
+                        "the row-returning number (every row ID and value over PCIe) is e2e_full_materialize"},
         "e2e_full_materialize": e2e_full,
         "gpu_launches": launches, "clocks": clocks, "index_build_s": build_s,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not cfg5:
         threads = os.cpu_count() or 1
         cv, cmed, checks = cpu_sweep(args.cpu_rows, 3, 1, threads)
         line["cpu_baseline"] = {"value": cv, "unit": "rows/s", "cores": threads, "kind": "port",
@@ -463,6 +547,10 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=1 << 26, help="rows per sweep point of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-materialize", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --rows rows per GPU; strong: ONE table of --rows rows cut over the GPUs")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"],
+                    help="cfg2: the selectivity sweep (the metric's config); cfg5: 8 predicates on a 16e9-row table")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)

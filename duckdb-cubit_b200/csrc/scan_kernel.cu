@@ -222,8 +222,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 							const uint32_t ctype = ct_type(de), ccnt = ct_count(de);
 							sm.meta[stage].pad = ctype | (ccnt << 2);
 							const uint8_t *csrc = reinterpret_cast<const uint8_t *>(a.bv[s]) + ct_offset(de);
-							const uint32_t cbytes =
+							uint32_t cbytes =
 							    ctype == CT_BITMAP ? (uint32_t)kTileBytes : (ctype == CT_ARRAY ? ((ccnt * 2u + 15u) & ~15u) : 0u);
+							if (ctype == CT_ARRAY && (a.debug & 16u)) {
+								cbytes = kArrayMax * 2; // experiment: always copy a whole staging row
+							}
 							mbar_arrive_expect_tx(&sm.full[stage], cbytes + dbytes);
 							if (ctype == CT_BITMAP) {
 								bulk_g2s(&sm.stage[stage][0], csrc, kTileBytes, &sm.full[stage]);
@@ -360,24 +363,34 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 				if (s == 0) {
 					tile = sm.meta[stage].tile;
 				}
-				uint32_t skip = 0; // bit u: stage u of this batch is an EMPTY container without deltas — nothing to fold
+				// CMP: bit u of `skip` = stage u of this batch needs no fold from shared memory — an EMPTY container, or a
+				// FULL / ARRAY container that was accumulated straight into the registers below
+				uint32_t skip = 0;
 				if ((HAS_DELTA || CMP) && tile != kNoTile) {
-					// Every warp prepares ITS span of the staged segment — fills it for an EMPTY / FULL / ARRAY container,
-					// then XORs the pending-delta entries that fall into the span — with generic-proxy writes to shared
-					// memory that the fold below picks up: no block-wide barrier.  Delta entries of one (stream, segment)
-					// are unordered and may repeat a word (device-side ingestion never sorts), hence the atomics.
+					// Pending-delta entries of one (stream, segment) are unordered and may repeat a word (device-side
+					// ingestion never sorts), so every warp XORs the entries that fall into ITS span of the staged segment
+					// with 32-bit shared-memory atomics (native ATOMS.XOR; the 64-bit form is a CAS loop) — no block-wide
+					// barrier — and the fold below picks the words up.
+					// Containers without pending deltas never touch shared memory: FULL ORs all-ones into the
+					// accumulator; ARRAY is decoded by the warp — lane l looks at list entries l, l+32, ..., a ballot finds
+					// the ones inside the warp's span, and each of those (a handful per warp: sparse segments are what
+					// ARRAY containers are for) is broadcast and OR-ed into the register of the lane that owns its word.
 					bool wrote = false;
-					for (uint32_t u = 0; u < nb; u++) {
-						uint32_t st = stage + u;
+#pragma unroll
+					for (int u = 0; u < UB; u++) {
+						if (u >= (int)nb) {
+							continue;
+						}
+						uint32_t st = stage + (uint32_t)u;
 						st = st >= (uint32_t)kStages ? st - (uint32_t)kStages : st;
 						const uint32_t dcnt = HAS_DELTA ? sm.meta[st].dcnt : 0u;
 						if (CMP) {
 							const uint32_t cmeta = sm.meta[st].pad, ctype = cmeta & 3u;
-							if (ctype != CT_BITMAP) {
-								if (ctype == CT_EMPTY && dcnt == 0) {
-									skip |= 1u << u;
-									continue;
-								}
+							if (ctype != CT_BITMAP && dcnt == 0) {
+								skip |= 1u << u; // accumulated into the registers by the fold below, in stream order
+								continue;
+							}
+							if (ctype != CT_BITMAP) { // a container WITH pending deltas: materialise the span, then XOR
 								const uint64_t fill = ctype == CT_FULL ? ~0ull : 0ull;
 								uint64_t *span = &sm.stage[st][warp * kSpanWords];
 #pragma unroll
@@ -392,7 +405,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 										const uint32_t p = sm.abuf[st][e];
 										const uint32_t rel = (p >> 6) - (uint32_t)(warp * kSpanWords);
 										if (rel < (uint32_t)kSpanWords) {
-											atomicOr(reinterpret_cast<unsigned long long *>(&sm.stage[st][p >> 6]), 1ull << (p & 63u));
+											atomicOr(reinterpret_cast<unsigned int *>(&sm.stage[st][0]) + (p >> 5), 1u << (p & 31u));
 										}
 									}
 								}
@@ -408,8 +421,13 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 							}
 							const uint32_t rel = raw.x - (uint32_t)(warp * kSpanWords);
 							if (rel < (uint32_t)kSpanWords) {
-								atomicXor(reinterpret_cast<unsigned long long *>(&sm.stage[st][raw.x]),
-								          ((unsigned long long)raw.w << 32) | raw.z);
+								unsigned int *w32 = reinterpret_cast<unsigned int *>(&sm.stage[st][raw.x]);
+								if (raw.z) {
+									atomicXor(w32, raw.z);
+								}
+								if (raw.w) {
+									atomicXor(w32 + 1, raw.w);
+								}
 								wrote = true;
 							}
 						}
@@ -432,16 +450,60 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 							const uint64_t *src = &sm.stage[st][warp * kSpanWords];
 #define CUBIT_LD(i) src[(i) * 32 + lane]
 #endif
-							if (ONEG) {
-								if (!CMP || !((skip >> u) & 1u)) {
+							if (CMP && ((skip >> u) & 1u)) {
+								// container without pending deltas: straight into the accumulator (q for a single OR
+								// group, g otherwise), nothing read from the ring stage
+								const uint32_t cmeta = sm.meta[st].pad, ctype = cmeta & 3u;
+								if (ctype == CT_FULL) {
 #pragma unroll
 									for (int i = 0; i < WPT; i++) {
-										q[i] |= CUBIT_LD(i);
+										(ONEG ? q[i] : g[i]) = ~0ull;
+									}
+								} else if (ctype == CT_ARRAY && !(a.debug & 32u)) {
+									const uint32_t cnt = cmeta >> 2;
+									for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
+										const uint32_t p = e0 + lane < cnt ? (uint32_t)sm.abuf[st][e0 + lane] : 0xffffffffu;
+										// word of the span = (p >> 6) - warp * kSpanWords; inside the span iff < kSpanWords
+										const uint32_t w = (p >> 6) - (uint32_t)(warp * kSpanWords);
+										// The list is sorted, so the entries inside this warp's span are ONE contiguous run: a ballot
+										// finds it, then every lane reads the run's entries straight from shared memory (uniform
+										// address → broadcast) and compares each word against the four words IT owns.  No shuffles:
+										// a *.sync op inside a loop whose trip count the compiler cannot prove uniform costs a
+										// convergence barrier + branch resolve each (ncu: 42 % of all stall samples), and the
+										// accumulator index stays a compile-time constant (a run-time q[w >> 5] goes to local memory).
+										const uint32_t mine = __ballot_sync(0xffffffffu, p != 0xffffffffu && w < (uint32_t)kSpanWords);
+										if (mine) {
+											const uint32_t first = e0 + (uint32_t)(__ffs(mine) - 1), n_in = (uint32_t)__popc(mine);
+											const uint32_t my0 = (uint32_t)(warp * kSpanWords + lane);
+											for (uint32_t j = 0; j < n_in; j += 4) {
+												uint32_t pj[4];
+#pragma unroll
+												for (int r = 0; r < 4; r++) { // (the staging row is kArrayMax entries: reading ≤ 3 past the run stays inside it)
+													pj[r] = j + r < n_in ? (uint32_t)sm.abuf[st][(first + j + r) & (kArrayMax - 1)] : 0xffffffffu;
+												}
+#pragma unroll
+												for (int r = 0; r < 4; r++) {
+													const uint32_t pw = pj[r] >> 6;
+													const uint64_t bit = 1ull << (pj[r] & 63u);
+#pragma unroll
+													for (int i = 0; i < WPT; i++) {
+														(ONEG ? q[i] : g[i]) |= pw == my0 + (uint32_t)(i * 32) ? bit : 0ull;
+													}
+												}
+											}
+										}
 									}
 								}
+								if (ONEG) {
+									continue;
+								}
+							} else if (ONEG) {
+#pragma unroll
+								for (int i = 0; i < WPT; i++) {
+									q[i] |= CUBIT_LD(i);
+								}
 								continue;
-							}
-							if (!CMP || !((skip >> u) & 1u)) {
+							} else {
 #pragma unroll
 								for (int i = 0; i < WPT; i++) {
 									g[i] |= CUBIT_LD(i);

@@ -86,9 +86,8 @@ void CubitIndex::Build() {
 
 void CubitIndex::Delete(row_t row_id, int64_t current_value) {
 	std::lock_guard<std::mutex> lk(mu);
-	const uint32_t v = ValueId(current_value);
-	pending[v].push_back(row_id - table.RowBase());
-	dirty[v] = true;
+	staged_values.push_back(ValueId(current_value));
+	staged_rows.push_back(row_id - table.RowBase());
 }
 
 void CubitIndex::Update(row_t row_id, int64_t old_value, int64_t new_value) {
@@ -97,38 +96,40 @@ void CubitIndex::Update(row_t row_id, int64_t old_value, int64_t new_value) {
 	}
 	std::lock_guard<std::mutex> lk(mu);
 	const uint32_t a = ValueId(old_value), b = ValueId(new_value);
-	pending[a].push_back(row_id - table.RowBase());
-	pending[b].push_back(row_id - table.RowBase());
-	dirty[a] = dirty[b] = true;
+	staged_values.push_back(a);
+	staged_rows.push_back(row_id - table.RowBase());
+	staged_values.push_back(b);
+	staged_rows.push_back(row_id - table.RowBase());
 }
 
+// INCREMENTAL: only the flips staged since the last commit cross to the GPU, where they are merged into the
+// index's pending-delta lists on the device (cubit_gpu_add_delta_pairs); earlier pending flips stay as they are
 void CubitIndex::CommitDeltas() {
 	std::lock_guard<std::mutex> lk(mu);
-	for (auto &kv : dirty) {
-		if (!kv.second) {
-			continue;
-		}
-		auto &rows = pending[kv.first];
-		Check(cubit_gpu_set_delta(table.Handle(), index_id, kv.first, rows.data(), rows.size()));
-		kv.second = false;
+	if (staged_rows.empty()) {
+		return;
 	}
+	Check(cubit_gpu_add_delta_pairs(table.Handle(), index_id, staged_values.data(), staged_rows.data(), staged_rows.size()));
+	committed += staged_rows.size();
+	staged_values.clear();
+	staged_rows.clear();
 }
 
 void CubitIndex::MergeDeltas() {
 	CommitDeltas();
 	std::lock_guard<std::mutex> lk(mu);
 	Check(cubit_gpu_merge_deltas(table.Handle(), index_id));
-	pending.clear();
-	dirty.clear();
+	committed = 0;
 }
 
 idx_t CubitIndex::PendingDeltaRows() const {
 	std::lock_guard<std::mutex> lk(mu);
-	idx_t n = 0;
-	for (auto &kv : pending) {
-		n += kv.second.size();
+	// (the library may have folded committed flips back on its own: the merge-back threshold)
+	cubit_index_info info;
+	if (cubit_gpu_index_info(table.Handle(), index_id, &info) == CUBIT_OK) {
+		return staged_rows.size() + info.delta_entries;
 	}
-	return n;
+	return staged_rows.size() + committed;
 }
 
 bool CubitIndex::Scan(int64_t lo, int64_t hi, idx_t max_count, std::vector<row_t> &row_ids) {

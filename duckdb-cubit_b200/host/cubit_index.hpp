@@ -93,8 +93,9 @@ private:
 	int64_t base_value;
 	uint32_t cardinality;
 	int32_t index_id = -1;
-	std::map<uint32_t, std::vector<row_t>> pending; // value id → flipped local rows
-	std::map<uint32_t, bool> dirty;
+	std::vector<uint32_t> staged_values; // (value id, local row) flips recorded since the last CommitDeltas
+	std::vector<row_t> staged_rows;
+	idx_t committed = 0;                 // flips handed to the GPU and still pending there
 	mutable std::mutex mu;
 };
 

@@ -6,8 +6,13 @@
 // Exit code 0 = all checks passed.  Needs a B200 (no CPU fallback).
 #include "cubit_scan.hpp"
 
+#include "cubit_gpu.h"
+
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 
 using namespace cubit_host;
 
@@ -49,6 +54,63 @@ static void ArtManyMatches(idx_t reps) {
 	REQUIRE(index.Scan(-5, 100, 1 << 30, ids) && ids.size() == 2 * reps); // i >= 0
 	REQUIRE(!index.Scan(0, 1, reps, ids));                                // more than max_count → false
 	REQUIRE(index.Scan(7, 9, 10, ids) && ids.empty());
+}
+
+// Several host threads on ONE table: the table's lock covers planning and enqueueing only, so the
+// config-1 style query (equality predicate + SUM: ~13 us of kernel inside ~40 us of call) overlaps across threads.
+// Straight through the C-ABI, as a DuckDB worker thread would call it.
+static void ConcurrentQueriesOverlap() {
+	const idx_t n = 6001215; // TPC-H SF1 lineitem rows
+	std::vector<int32_t> key(n);
+	std::vector<int64_t> pay(n);
+	std::vector<int64_t> want_sum(50, 0), want_cnt(50, 0);
+	for (idx_t r = 0; r < n; r++) {
+		key[r] = (int32_t)(Rng() % 50);
+		pay[r] = (int64_t)(Rng() % 10000000) - 5000;
+		want_sum[key[r]] += pay[r];
+		want_cnt[key[r]]++;
+	}
+	CubitTable table(n);
+	table.AddColumn(0, key.data());
+	table.AddColumn(1, pay.data());
+	CubitIndex index(table, 0, 0, 50);
+	index.Build();
+	std::atomic<int> bad {0};
+	auto run = [&](int n_threads, int per_thread) {
+		std::vector<std::thread> th;
+		const auto t0 = std::chrono::steady_clock::now();
+		for (int k = 0; k < n_threads; k++) {
+			th.emplace_back([&, k]() {
+				for (int i = 0; i < per_thread; i++) {
+					const uint32_t v = (uint32_t)((k * 7 + i) % 50);
+					cubit_bv_ref ref {index.Id(), v};
+					cubit_pred_group grp {1, &ref};
+					cubit_query q {};
+					q.n_groups = 1;
+					q.groups = &grp;
+					q.agg_kind = CUBIT_AGG_SUM;
+					q.agg_col_a = 1;
+					cubit_gpu_result *res = nullptr;
+					cubit_result_info info;
+					if (cubit_gpu_query(table.Handle(), &q, &res) != CUBIT_OK || cubit_gpu_result_get(res, &info) != CUBIT_OK ||
+					    (int64_t)info.count != want_cnt[v] || (int64_t)info.sum_lo != want_sum[v]) {
+						bad++;
+					}
+					cubit_gpu_free_result(res);
+				}
+			});
+		}
+		for (auto &t : th) {
+			t.join();
+		}
+		const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		return n_threads * per_thread / s;
+	};
+	run(2, 100);
+	const double one = run(1, 2000), eight = run(8, 2000);
+	printf("concurrent config-1 queries on one table: 1 thread %.0f/s, 8 threads %.0f/s (%.2fx)\n", one, eight, eight / one);
+	REQUIRE(bad.load() == 0);
+	REQUIRE(eight > 2.0 * one);
 }
 
 // INSERT after CREATE INDEX: appended rows take the next row ids and show up in index scans
@@ -236,6 +298,7 @@ int main() {
 		threw = true;
 	}
 	REQUIRE(threw);
+	ConcurrentQueriesOverlap();
 	printf("host_scan_test ok\n");
 	return 0;
 }

@@ -15,7 +15,7 @@ def host_test_binary(tmp_path_factory):
     exe = str(tmp_path_factory.mktemp("hostcpp") / "host_scan_test")
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-I",
                            os.path.join(PKG, "host"), os.path.join(ROOT, "tests", "cpp", "host_scan_test.cpp"), "-o",
-                           exe, "-L", PKG, "-lcubit_host", "-lcubit_gpu", "-Wl,-rpath," + PKG])
+                           exe, "-L", PKG, "-lcubit_host", "-lcubit_gpu", "-Wl,-rpath," + PKG, "-lpthread"])
     return exe
 
 
@@ -33,3 +33,4 @@ def test_host_scan_against_brute_force(host_test_binary):
     r = subprocess.run([host_test_binary], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     assert "host_scan_test ok" in r.stdout
+    print(r.stdout)

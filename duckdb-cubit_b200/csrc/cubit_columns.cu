@@ -29,7 +29,7 @@ extern "C" int cubit_gpu_upload_column(cubit_gpu_table *t, int32_t col_id, const
 		}
 		return CUBIT_OK;
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -79,7 +79,7 @@ extern "C" int cubit_gpu_upload_column_validity(cubit_gpu_table *t, int32_t col_
 		}
 		return CUBIT_OK;
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -270,7 +270,7 @@ extern "C" int cubit_gpu_upload_column_segments(cubit_gpu_table *t, int32_t col_
 	if (groups.size() > 0x7fffffffull || tiles.size() > 0x7fffffffull) {
 		return fail(CUBIT_EINVAL, "too many metadata groups");
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -426,7 +426,7 @@ extern "C" int cubit_gpu_download_column(cubit_gpu_table *t, int32_t col_id, voi
 		}
 		return CUBIT_OK;
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -495,7 +495,7 @@ extern "C" int cubit_gpu_synth_column(cubit_gpu_table *t, int32_t col_id, int32_
 		}
 		return CUBIT_OK;
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -539,7 +539,7 @@ extern "C" int cubit_gpu_pack_column(cubit_gpu_table *t, int32_t col_id, int kee
 		}
 		return CUBIT_OK;
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -634,7 +634,7 @@ extern "C" int cubit_gpu_append_rows(cubit_gpu_table *t, uint64_t n_new, const c
 		t->shard_row0.back() = t->n_rows;
 		return CUBIT_OK;
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -864,7 +864,7 @@ extern "C" int cubit_gpu_drop_column(cubit_gpu_table *t, int32_t col_id) {
 		}
 		return CUBIT_OK;
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}

@@ -384,7 +384,7 @@ extern "C" int cubit_gpu_add_delta(cubit_gpu_table *t, int32_t index_id, uint32_
 	if (rc) {
 		return rc;
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -417,7 +417,7 @@ extern "C" int cubit_gpu_add_delta_pairs(cubit_gpu_table *t, int32_t index_id, c
 	if (rc) {
 		return rc;
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -452,7 +452,7 @@ extern "C" int cubit_gpu_set_delta(cubit_gpu_table *t, int32_t index_id, uint32_
 	if (rc) {
 		return rc;
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -490,7 +490,7 @@ extern "C" int cubit_gpu_merge_deltas(cubit_gpu_table *t, int32_t index_id) {
 		}
 		return CUBIT_OK;
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -516,7 +516,7 @@ extern "C" int cubit_gpu_set_merge_threshold(cubit_gpu_table *t, int32_t index_i
 		}
 		return CUBIT_OK;
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	Index *ix = get_index(t, index_id);
 	if (!ix) {
 		return fail(CUBIT_EINVAL, "bad index %d", index_id);

@@ -40,6 +40,29 @@ const char *last_error_cstr() {
 	return g_last_error.c_str();
 }
 
+TableLock::TableLock(cubit_gpu_table *tp) : t(tp), lk(tp->mu) {
+	if (t->sharded() || !t->stream) {
+		return;
+	}
+	cudaSetDevice(t->device);
+	for (int i = 0; i < kAggStreams; i++) {
+		if (t->agg_used[i]) {
+			cudaStreamWaitEvent(t->stream, t->agg_last[i], 0);
+			t->agg_used[i] = false;
+		}
+	}
+}
+
+TableLock::~TableLock() {
+	if (t->sharded() || !t->mut_event || !t->stream) {
+		return;
+	}
+	cudaSetDevice(t->device);
+	if (cudaEventRecord(t->mut_event, t->stream) == cudaSuccess) {
+		t->mut_recorded = true;
+	}
+}
+
 int use_device(const cubit_gpu_table *t) {
 	CU_TRY(cudaSetDevice(t->device));
 	return CUBIT_OK;
@@ -206,6 +229,15 @@ extern "C" int cubit_gpu_create(int device, uint64_t n_rows, int64_t row_base, u
 	for (int c = 0; c < kCopyStreams && e == cudaSuccess; c++) {
 		e = cudaStreamCreateWithFlags(&t->copy_stream[c], cudaStreamNonBlocking);
 	}
+	for (int c = 0; c < kAggStreams && e == cudaSuccess; c++) {
+		e = cudaStreamCreateWithFlags(&t->agg_stream[c], cudaStreamNonBlocking);
+		if (e == cudaSuccess) {
+			e = cudaEventCreateWithFlags(&t->agg_last[c], cudaEventDisableTiming);
+		}
+	}
+	if (e == cudaSuccess) {
+		e = cudaEventCreateWithFlags(&t->mut_event, cudaEventDisableTiming);
+	}
 	if (e != cudaSuccess) {
 		cubit_gpu_destroy(t);
 		return fail(CUBIT_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
@@ -238,6 +270,21 @@ extern "C" int cubit_gpu_destroy(cubit_gpu_table *t) {
 			cudaStreamSynchronize(cs);
 			cudaStreamDestroy(cs);
 		}
+	}
+	for (int c = 0; c < kAggStreams; c++) {
+		if (t->agg_stream[c]) {
+			cudaStreamSynchronize(t->agg_stream[c]);
+			cudaStreamDestroy(t->agg_stream[c]);
+		}
+		if (t->agg_last[c]) {
+			cudaEventDestroy(t->agg_last[c]);
+		}
+	}
+	if (t->mut_event) {
+		cudaEventDestroy(t->mut_event);
+	}
+	for (auto ev : t->ev_pool) {
+		cudaEventDestroy(ev);
 	}
 	for (Index *ix : t->indexes) {
 		if (!ix) {
@@ -287,7 +334,7 @@ extern "C" int cubit_gpu_set_stream(cubit_gpu_table *t, void *cuda_stream) {
 	if (t->sharded()) {
 		return fail(CUBIT_ESTATE, "a sharded table runs on its shards' own streams");
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -351,7 +398,7 @@ static int index_create(cubit_gpu_table *t, uint32_t cardinality, bool compresse
 	if (compressed && t->seg_bits > 65536) {
 		return fail(CUBIT_EINVAL, "compressed indexes need seg_bits <= 65536 (16-bit positions inside a segment)");
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -442,7 +489,7 @@ extern "C" int cubit_gpu_upload_bitvector(cubit_gpu_table *t, int32_t index_id, 
 		}
 		return CUBIT_OK;
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -509,7 +556,7 @@ extern "C" int cubit_gpu_upload_bitvector_wah(cubit_gpu_table *t, int32_t index_
 		return fail(CUBIT_EINVAL, "WAH bitvector describes %llu bits, table has %llu rows",
 		            (unsigned long long)(groups * 31ull + bv->active_nbits), (unsigned long long)t->n_rows);
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -582,7 +629,7 @@ extern "C" int cubit_gpu_download_bitvector(cubit_gpu_table *t, int32_t index_id
 		}
 		return CUBIT_OK;
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -706,7 +753,7 @@ extern "C" int cubit_gpu_bitvector_count(cubit_gpu_table *t, int32_t index_id, u
 		*count = total;
 		return CUBIT_OK;
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -745,7 +792,7 @@ extern "C" int cubit_gpu_index_info(cubit_gpu_table *t, int32_t index_id, cubit_
 		}
 		return CUBIT_OK;
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	Index *ix = get_index(t, index_id);
 	if (!ix) {
 		return fail(CUBIT_EINVAL, "bad index %d", index_id);
@@ -779,7 +826,7 @@ extern "C" int cubit_gpu_index_build(cubit_gpu_table *t, int32_t index_id, int32
 		}
 		return CUBIT_OK;
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}

@@ -98,7 +98,7 @@ extern "C" int cubit_gpu_index_serialize(cubit_gpu_table *t, int32_t index_id, v
 	if (t->sharded()) {
 		return fail(CUBIT_ESTATE, "index images are per shard: serialize every shard of a sharded table");
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	TableLock lk(t);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -273,7 +273,7 @@ extern "C" int cubit_gpu_index_deserialize(cubit_gpu_table *t, const void *image
 	if (rc != CUBIT_OK) {
 		// drop the half-built index (it is the last one created: nothing else can hold its id yet)
 		const std::string why = last_error_cstr();
-		std::lock_guard<std::mutex> lk(t->mu);
+		TableLock lk(t);
 		if (id >= 0 && (size_t)id + 1 == t->indexes.size()) {
 			Index *ix = t->indexes.back();
 			cudaStreamSynchronize(t->stream);
@@ -288,7 +288,7 @@ extern "C" int cubit_gpu_index_deserialize(cubit_gpu_table *t, const void *image
 		return fail(rc, "%s", why.c_str());
 	}
 	{
-		std::lock_guard<std::mutex> lk(t->mu);
+		TableLock lk(t);
 		Index *ix = get_index(t, id);
 		if (ix) { // remember where the bitvectors came from, so appends keep extending the index on the GPU
 			ix->src_col = h.src_col;

@@ -21,7 +21,7 @@ static cudaError_t run_scan(const ScanArgs &sa, uint32_t seg_words, bool has_del
 	return launch_scan(sa, seg_words, has_delta, compressed, sm_count, st, nullptr);
 }
 
-// caller holds r->t->mu (the pinned header goes back to the table's pool)
+// (the pinned header and the completion event go back to the table's pools)
 static void release_result_locked(cubit_gpu_result *r) {
 	cudaStream_t s = r->stream;
 	if (r->copies_in_flight.load()) { // rows still crossing PCIe: the buffers must outlive the copies
@@ -51,6 +51,7 @@ static void release_result_locked(cubit_gpu_result *r) {
 			cudaFreeAsync(p, s);
 		}
 	}
+	std::lock_guard<std::mutex> ml(r->t->meta_mu);
 	if (r->h_hdr) {
 		r->t->hdr_pool.push_back(r->h_hdr);
 	}
@@ -60,7 +61,7 @@ static void release_result_locked(cubit_gpu_result *r) {
 		}
 	}
 	if (r->ev_done) {
-		cudaEventDestroy(r->ev_done);
+		r->t->ev_pool.push_back(r->ev_done); // (completed or never recorded: safe to record again)
 	}
 	delete r;
 }
@@ -167,9 +168,13 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 				return fail(CUBIT_EINVAL, "group %u ref %u: bad (index %d, value %u)", g, i, grp.refs[i].index_id,
 				            grp.refs[i].value_id);
 			}
-			int rc = delta_settle_locked(t, ix);
-			if (rc == CUBIT_OK) {
-				rc = refresh_counts(t, ix);
+			int rc = CUBIT_OK;
+			if (ix->delta.voff_pending || !ix->counts_valid) { // (rare: right after maintenance)
+				std::lock_guard<std::mutex> ml(t->meta_mu);
+				rc = delta_settle_locked(t, ix);
+				if (rc == CUBIT_OK) {
+					rc = refresh_counts(t, ix);
+				}
 			}
 			if (rc) {
 				return rc;
@@ -340,12 +345,20 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 		return fail(CUBIT_ENOMEM, "host allocation failed");
 	}
 	r->t = t;
-	r->stream = t->stream;
+	// Which stream: queries that produce row positions use the look-back between CTAs (a co-resident, persistent
+	// grid) and stay on the in-order kernel stream; aggregate-only / bitvector-only queries have no inter-CTA
+	// dependency and go to the stream pool, where the small grids of concurrent callers overlap on the GPU.
+	int agg_slot = -1;
+	cudaStream_t st = t->stream;
+	if (t->stream == t->own_stream && !need_ids_buf && !want_vals && !unfused && probe_mode != PROBE_GATHER) {
+		agg_slot = (int)(t->next_agg++ % kAggStreams);
+		st = t->agg_stream[agg_slot];
+	}
+	r->stream = st;
 	r->flags = q->flags;
 	r->agg_kind = q->agg_kind;
 	r->n_cols = want_vals ? q->n_cols : 0;
 	r->timing = (q->flags & CUBIT_Q_TIMING) != 0;
-	cudaStream_t st = t->stream;
 	int rc = CUBIT_OK;
 #define Q_TRY(expr)                                                                                                    \
 	do {                                                                                                               \
@@ -374,10 +387,18 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	unsigned int *probe_done = reinterpret_cast<unsigned int *>(r->d_block + hdr_bytes + 2 * ctrl_pad + part_bytes);
 	unsigned long long *tile_excl =
 	    reinterpret_cast<unsigned long long *>(r->d_block + hdr_bytes + 2 * ctrl_pad + part_bytes + 64);
-	if (!t->hdr_pool.empty()) {
-		r->h_hdr = t->hdr_pool.back();
-		t->hdr_pool.pop_back();
-	} else {
+	{
+		std::lock_guard<std::mutex> ml(t->meta_mu);
+		if (!t->hdr_pool.empty()) {
+			r->h_hdr = t->hdr_pool.back();
+			t->hdr_pool.pop_back();
+		}
+		if (!t->ev_pool.empty()) {
+			r->ev_done = t->ev_pool.back();
+			t->ev_pool.pop_back();
+		}
+	}
+	if (!r->h_hdr) {
 		Q_TRY(cudaHostAlloc((void **)&r->h_hdr, sizeof(ResultHeader), cudaHostAllocDefault));
 	}
 	memset(r->h_hdr, 0, sizeof(ResultHeader));
@@ -396,7 +417,12 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	if ((unfused || probe_mode == PROBE_BITS) && !want_q && !probe_on_bv) {
 		Q_TRY(cudaMallocAsync((void **)&r->d_q_tmp, t->words_per_bv * 8, st));
 	}
-	Q_TRY(cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming));
+	if (!r->ev_done) {
+		Q_TRY(cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming));
+	}
+	if (agg_slot >= 0 && t->mut_recorded) {
+		Q_TRY(cudaStreamWaitEvent(st, t->mut_event, 0)); // behind the last maintenance section of the kernel stream
+	}
 	if (r->timing) {
 		for (auto &e : r->ev) {
 			Q_TRY(cudaEventCreate(&e));
@@ -529,6 +555,11 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	}
 	Q_TRY(cudaMemcpyAsync(r->h_hdr, r->d_hdr, sizeof(ResultHeader), cudaMemcpyDeviceToHost, st));
 	Q_TRY(cudaEventRecord(r->ev_done, st));
+	if (agg_slot >= 0) {
+		std::lock_guard<std::mutex> ml(t->meta_mu); // (two callers may share a pool stream: record + flag together)
+		Q_TRY(cudaEventRecord(t->agg_last[agg_slot], st));
+		t->agg_used[agg_slot] = true;
+	}
 #undef Q_TRY
 	t->launches += n_launch;
 
@@ -591,7 +622,7 @@ extern "C" int cubit_gpu_query(cubit_gpu_table *t, const cubit_query *q, cubit_g
 	cubit_gpu_result *r = nullptr;
 	int rc;
 	{
-		std::lock_guard<std::mutex> lk(t->mu);
+		std::shared_lock<std::shared_mutex> lk(t->mu);
 		rc = plan_and_launch(t, q, &r);
 	}
 	if (rc) {
@@ -647,7 +678,7 @@ extern "C" int cubit_gpu_result_add_limbs(cubit_gpu_result *r, int64_t *device_d
 		return fail(CUBIT_ESTATE, "a sharded result is already reduced by the library");
 	}
 	cubit_gpu_table *t = r->t;
-	std::lock_guard<std::mutex> lk(t->mu);
+	std::shared_lock<std::shared_mutex> lk(t->mu);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}
@@ -918,7 +949,7 @@ extern "C" int cubit_gpu_free_result(cubit_gpu_result *r) {
 		return sharded_free_result(r);
 	}
 	cudaSetDevice(r->t->device);
-	std::lock_guard<std::mutex> lk(r->t->mu);
+	std::shared_lock<std::shared_mutex> lk(r->t->mu);
 	release_result_locked(r);
 	return CUBIT_OK;
 }
@@ -933,7 +964,7 @@ extern "C" int cubit_gpu_probe(cubit_gpu_table *t, int32_t col_id, const int64_t
 	if (t->sharded()) {
 		return sharded_probe(t, col_id, host_rowids, n, host_out, sum_lo, sum_hi);
 	}
-	std::lock_guard<std::mutex> lk(t->mu);
+	std::shared_lock<std::shared_mutex> lk(t->mu);
 	if (use_device(t)) {
 		return CUBIT_ECUDA;
 	}

@@ -303,7 +303,7 @@ int sharded_probe(cubit_gpu_table *t, int32_t col_id, const int64_t *host_rowids
 	uint32_t elem = 0;
 	{
 		cubit_gpu_table *s0 = t->shards[0];
-		std::lock_guard<std::mutex> lk(s0->mu);
+		std::shared_lock<std::shared_mutex> lk(s0->mu);
 		auto it = s0->columns.find(col_id);
 		if (it == s0->columns.end()) {
 			return fail(CUBIT_EINVAL, "no column %d", col_id);

@@ -23,6 +23,7 @@
 #include <atomic>
 #include <map>
 #include <mutex>
+#include <shared_mutex>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -125,6 +126,7 @@ struct Column {
 };
 
 constexpr int kCopyStreams = 2;
+constexpr int kAggStreams = 4; // streams for queries whose kernels have no inter-CTA dependency (see plan_and_launch)
 constexpr uint64_t kStageChunk = 16ull << 20;
 
 } // namespace cubit
@@ -141,9 +143,24 @@ struct cubit_gpu_table {
 	cudaStream_t stream = nullptr; // kernel stream (own_stream unless cubit_gpu_set_stream)
 	cudaStream_t copy_stream[cubit::kCopyStreams] = {};
 	std::atomic<uint32_t> next_copy {0};
+	// Aggregate-only / bitvector-only queries (no row positions → no look-back between CTAs, so their grids need not
+	// be co-resident) run on a small pool of streams and overlap ON THE GPU: the config-1 query is a 92-CTA kernel.
+	// Ordering against maintenance on the kernel stream: a pool stream waits for mut_event (recorded at the end of
+	// every mutating section), and a mutating section first orders the kernel stream behind agg_last[] (TableLock).
+	cudaStream_t agg_stream[cubit::kAggStreams] = {};
+	cudaEvent_t agg_last[cubit::kAggStreams] = {};
+	bool agg_used[cubit::kAggStreams] = {};
+	cudaEvent_t mut_event = nullptr;
+	bool mut_recorded = false;
+	std::atomic<uint32_t> next_agg {0};
+	std::vector<cudaEvent_t> ev_pool; // completion events, recycled across queries
 	std::vector<cubit::Index *> indexes;
 	std::map<int32_t, cubit::Column> columns;
-	std::mutex mu;
+	// queries plan and enqueue under a SHARED lock (several host threads at once: the CUDA runtime is thread-safe and
+	// their work lands on different streams or interleaves harmlessly on one); everything that may change table state
+	// takes it exclusively (TableLock).  meta_mu guards the small host-side pools and the lazily refreshed counts.
+	std::shared_mutex mu;
+	std::mutex meta_mu;
 	std::atomic<uint64_t> launches {0};
 	unsigned long long *d_scratch = nullptr; // popcount scratch
 	uint64_t scratch_n = 0;
@@ -196,6 +213,15 @@ struct cubit_gpu_result {
 };
 
 namespace cubit {
+
+// Exclusive section that may change table state (everything except the query path).  Taking it orders the kernel
+// stream behind every pool-stream query in flight; leaving it records the point pool streams must wait for.
+struct TableLock {
+	cubit_gpu_table *t;
+	std::unique_lock<std::shared_mutex> lk;
+	explicit TableLock(cubit_gpu_table *t);
+	~TableLock();
+};
 
 int use_device(const cubit_gpu_table *t);
 Index *get_index(cubit_gpu_table *t, int32_t index_id);

@@ -110,7 +110,7 @@ static void ConcurrentQueriesOverlap() {
 	const double one = run(1, 2000), eight = run(8, 2000);
 	printf("concurrent config-1 queries on one table: 1 thread %.0f/s, 8 threads %.0f/s (%.2fx)\n", one, eight, eight / one);
 	REQUIRE(bad.load() == 0);
-	REQUIRE(eight > 2.0 * one);
+	REQUIRE(eight > 2.5 * one); // measured 3.3-3.6x on a B200 box with 16 host cores (profiles/r2_concurrency.md)
 }
 
 // INSERT after CREATE INDEX: appended rows take the next row ids and show up in index scans

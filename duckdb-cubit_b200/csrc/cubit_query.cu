@@ -332,6 +332,29 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	// and counts the set bits on the way.
 	const bool probe_on_bv = probe_mode == PROBE_BITS && k == 1 && !has_delta && !has_compressed && !want_ids && !want_vals && !want_q &&
 	                         !unfused && sa.debug == 0;
+	// Dense selections over bit-packed columns (widths <= 32) are STREAMED by the dense probe (probe_dense_kernel.cu):
+	// from a few percent of the rows upward every DRAM line of the packed form is touched anyway, and decoding from
+	// shared-memory stages costs a third of the per-value gather (profiles/r2_probe_dense.md).  Below the density
+	// threshold the bit-driven gather probe keeps the job (and picks raw or packed per column, prefer_raw_form).
+	bool dense_probe = false;
+	DenseProbeArgs dp;
+	memset(&dp, 0, sizeof(dp));
+	if (probe_mode == PROBE_BITS && !probe_on_bv) {
+		uint64_t inv = 48; // selected rows >= n_rows / inv
+		if (const char *e = getenv("CUBIT_DENSE_MIN_INV")) {
+			inv = strtoull(e, nullptr, 10); // 0 disables the dense probe (experiments)
+		}
+		if (inv && sel_bound >= t->n_rows / inv) {
+			uint32_t mw[kMaxFusedCols] = {};
+			dp.n_load = n_dist;
+			for (int d = 0; d < n_dist; d++) {
+				const bool pk_ok = dist_cols[d]->packed() && dist_cols[d]->pack_max_width <= 32;
+				dp.lcol[d] = col_ref(dist_cols[d], !pk_ok);
+				mw[d] = dist_cols[d]->pack_max_width;
+			}
+			dense_probe = dense_probe_plan(dp, mw);
+		}
+	}
 	const bool separate_probe = probe_mode == PROBE_GATHER;
 	const bool need_ids_buf = want_ids || separate_probe || (probe_mode == PROBE_BITS && want_vals);
 	if (!need_ids_buf && !want_vals) {
@@ -378,7 +401,8 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	const size_t part_bytes = (size_t)max_grid * sizeof(BlockPartial);
 	// layout: hdr | ctrl A | ctrl B (decode pass of the unfused path) | partials | probe done | segment prefixes
 	const size_t excl_bytes = probe_mode == PROBE_BITS ? ctrl_pad : 0;
-	const size_t block_bytes = hdr_bytes + 2 * ctrl_pad + part_bytes + 64 + excl_bytes;
+	const size_t span_bytes = dense_probe ? (size_t)t->n_seg * kConsumerWarps * 8 : 0; // per-span prefixes (dense probe)
+	const size_t block_bytes = hdr_bytes + 2 * ctrl_pad + part_bytes + 64 + excl_bytes + span_bytes;
 	Q_TRY(cudaMallocAsync((void **)&r->d_block, block_bytes, st));
 	r->d_hdr = reinterpret_cast<ResultHeader *>(r->d_block);
 	unsigned long long *ctrl_a = reinterpret_cast<unsigned long long *>(r->d_block + hdr_bytes);
@@ -387,6 +411,8 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	unsigned int *probe_done = reinterpret_cast<unsigned int *>(r->d_block + hdr_bytes + 2 * ctrl_pad + part_bytes);
 	unsigned long long *tile_excl =
 	    reinterpret_cast<unsigned long long *>(r->d_block + hdr_bytes + 2 * ctrl_pad + part_bytes + 64);
+	unsigned long long *span_excl = reinterpret_cast<unsigned long long *>(
+	    r->d_block + hdr_bytes + 2 * ctrl_pad + part_bytes + 64 + excl_bytes);
 	{
 		std::lock_guard<std::mutex> ml(t->meta_mu);
 		if (!t->hdr_pool.empty()) {
@@ -446,7 +472,8 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 		sa.ctrl = ctrl_a;
 		sa.q_out = probe_mode == PROBE_BITS && !want_q ? r->d_q_tmp : r->d_q;
 		sa.ids_out = need_ids_buf ? r->d_ids : nullptr;
-		sa.tile_excl = probe_mode == PROBE_BITS && want_vals ? tile_excl : nullptr;
+		sa.tile_excl = probe_mode == PROBE_BITS && want_vals && !dense_probe ? tile_excl : nullptr;
+		sa.span_excl = dense_probe && want_vals && cap ? span_excl : nullptr;
 		if (probe_mode == PROBE_FUSED) {
 			sa.n_load = n_dist;
 			for (int d = 0; d < n_dist; d++) {
@@ -489,7 +516,25 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	if (r->timing) {
 		Q_TRY(cudaEventRecord(r->ev[1], st));
 	}
-	if (probe_mode == PROBE_BITS) {
+	if (dense_probe) {
+		dp.q = sa.q_out;
+		dp.span_excl = sa.span_excl;
+		dp.n_span = t->n_seg * (uint32_t)kConsumerWarps;
+		dp.n_blk = (t->n_rows + kPackBlock - 1) / kPackBlock;
+		for (int d = 0; d < n_dist; d++) {
+			dp.lout[d] = dist_out[d] >= 0 && cap ? static_cast<long long *>(r->d_vals[dist_out[d]]) : nullptr;
+		}
+		dp.agg_kind = q->agg_kind;
+		dp.agg_ia = agg_ia;
+		dp.agg_ib = agg_ib;
+		dp.hdr = r->d_hdr;
+		Q_TRY(launch_probe_dense(dp, t->seg_words, want_vals && cap, t->sm_count, st));
+		n_launch++;
+		if (r->timing) {
+			Q_TRY(cudaEventRecord(r->ev[2], st));
+			r->probe_timed = true;
+		}
+	} else if (probe_mode == PROBE_BITS) {
 		ScanArgs pb;
 		memset(&pb, 0, sizeof(pb));
 		pb.q_out = sa.q_out; // input of the bit-driven probe
@@ -586,6 +631,11 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 		r->probe_fixed_bytes = probe_mode == PROBE_BITS ? t->n_words * 8 : 0; // ... the bit-driven one re-reads Q
 	}
 	r->info.capacity = cap;
+	r->info.probe_path = dense_probe                    ? CUBIT_PROBE_DENSE
+	                     : probe_mode == PROBE_BITS     ? CUBIT_PROBE_BITS
+	                     : probe_mode == PROBE_GATHER   ? CUBIT_PROBE_GATHER
+	                     : probe_mode == PROBE_FUSED    ? CUBIT_PROBE_FUSED
+	                                                    : CUBIT_PROBE_NONE;
 	r->info.n_streams = k;
 	r->info.n_launches = n_launch;
 	r->info.delta_entries = delta_entries;

@@ -188,6 +188,7 @@ int sharded_result_finish(cubit_gpu_result *r) {
 		tot.ms_probe = std::max(tot.ms_probe, pi.ms_probe);
 		tot.ms_total = std::max(tot.ms_total, pi.ms_total);
 		tot.fused = pi.fused;
+		tot.probe_path = pi.probe_path;
 	}
 	r->info = tot; // device pointers stay NULL: the rows live on several devices (cubit_gpu_fetch walks them)
 	r->fin_rc = rc;

@@ -136,6 +136,8 @@ struct ScanArgs {
 	unsigned long long *ctrl;           // control block (see above)
 	uint64_t *q_out;                    // merged bitvector out, or nullptr
 	unsigned long long *tile_excl;      // per-segment exclusive prefix out (scan) / in (bit-driven probe), or nullptr
+	unsigned long long *span_excl;      // scan only: exclusive prefix of every consumer warp's span ([n_seg * kConsumerWarps],
+	                                    // written at emission) for the dense probe (probe_dense_kernel.cu), or nullptr
 	long long *ids_out;                 // sorted row IDs out, or nullptr
 	// fused probe: the distinct int64 columns read at every selected row
 	int n_load;                           // 0..kMaxFusedCols
@@ -149,6 +151,23 @@ struct ScanArgs {
 	int skip_count;                     // 1: do not add this launch's popcounts to hdr->count (decode pass of UNFUSED)
 	int count_rows;                     // bit-driven probe only: 1 = it also counts the set bits into hdr->count (no scan ran)
 	unsigned int debug;                 // timing experiments only (CUBIT_SCAN_DEBUG): results are WRONG when != 0
+};
+
+// Dense probe over bit-packed columns (probe_dense_kernel.cu): streams the pack blocks of every span that has a
+// selected row through per-warp shared-memory stages and decodes there.  A span = one scan-kernel consumer warp's
+// share of a segment = seg_words / 8 words of Q = seg_bits / 8192 pack blocks.
+struct DenseProbeArgs {
+	const uint64_t *q;                   // merged bitvector (whole segments)
+	const unsigned long long *span_excl; // [n_span] output position of every span's first selected row (positions only)
+	uint32_t n_span;                     // n_seg * kConsumerWarps
+	uint64_t n_blk;                      // pack blocks of the columns (ceil(n_rows / kPackBlock))
+	int n_load;                          // 1..kMaxFusedCols distinct columns
+	ColRef lcol[kMaxFusedCols];          // bit-packed (widths <= 32) or raw
+	long long *lout[kMaxFusedCols];      // gathered values out (same positions as the row IDs), or nullptr
+	int agg_kind, agg_ia, agg_ib;        // as in ScanArgs
+	ResultHeader *hdr;                   // sums are ADDED
+	uint32_t stage_bytes[kMaxFusedCols]; // bytes of one shared-memory stage of every column (0: raw) — dense_probe_plan
+	uint32_t warp_bytes;                 // shared memory per warp
 };
 
 struct ProbeArgs {
@@ -184,6 +203,11 @@ int scan_max_grid(uint32_t seg_words, int sm_count);
 // occupancy.  Sums are ADDED to args.hdr (which the scan kernel has already finalised).
 cudaError_t launch_probe_bits(const ScanArgs &args, uint32_t seg_words, bool positions, int sm_count,
                               cudaStream_t stream);
+
+// fills stage_bytes / warp_bytes from the columns' widest blocks; false: not eligible (no packed column, or a width > 32)
+bool dense_probe_plan(DenseProbeArgs &args, const uint32_t *max_width);
+cudaError_t launch_probe_dense(const DenseProbeArgs &args, uint32_t seg_words, bool positions, int sm_count,
+                               cudaStream_t stream);
 
 cudaError_t launch_probe(const ProbeArgs &args, int sm_count, cudaStream_t stream);
 // validity of a probed column at the selected rows (ValidityFetchRow analog, validity_uncompressed.cpp:381):

@@ -1,0 +1,364 @@
+// probe_dense_kernel.cu — the column probe for DENSE selections over FOR-bit-packed columns (sm_100a).
+//
+// What it computes: vals[c] = col_c[rows selected by Q], in row order, at the output
+// positions the scan kernel gave the row IDs, plus SUM / SUM(a*b) over them.  Semantics as everywhere else:
+//   fetch of a row's value   src/storage/compression/bitpacking.cpp:879 (BitpackingFetchRow: FOR base + packed delta)
+//   SUM carry                src/include/duckdb/core_functions/aggregate/sum_helpers.hpp:92-113
+//
+// Why a second probe kernel.  The bit-driven probe of scan_kernel.cu gathers every selected value straight from
+// global memory: two dependent loads, a header look-up and 64-bit address arithmetic per value — 87 thread
+// instructions per value, long-scoreboard bound at 24 warps / SM (profiles/r2_probe_dense.md: 3.6 ms for 5·10^8
+// values of a 24-bit column, DRAM pipe 24 % busy).  From a few percent of the rows upward, however, every DRAM
+// line of a packed column is touched anyway, so this kernel STREAMS the column instead:
+//   * work unit = one pack block (1024 rows: 128·width bytes of payload, one 16-byte header) of one warp's span;
+//     every warp owns a double-buffered shared-memory stage per probed column and lane 0 keeps ONE 1-D bulk async
+//     copy (cp.async.bulk → UBLKCP, the TMA engine) in flight for the warp's next non-empty block while the
+//     current one is decoded — completion on a per-warp mbarrier, no CTA-wide barrier anywhere in the kernel
+//     (the exclusive output prefix of every span comes from the scan kernel, ScanArgs::span_excl).  Blocks
+//     without a selected row are never copied.
+//   * decode from shared memory in OUTPUT-POSITION order: the set bits of the block are compacted to 10-bit row
+//     numbers in a per-warp staging row (two ctz chains per lane, the hand-written step of scan_common.cuh), then
+//     lane l handles positions 2l, 2l+1 (+64 …): index multiply, two ld.shared.b32 of neighbouring words (position
+//     order keeps the lanes' addresses within a few banks of each other — lane order would hit 8-way conflicts at
+//     width 24), one funnel shift, a mask, a 64-bit add of the block's base.  Values leave as contiguous
+//     512-byte st.global.cs.v2 stores, exactly like the row IDs did.
+// Raw (unpacked) columns may ride along (plain gather); widths above 32 bits are left to the gather probe.
+#include "scan_common.cuh"
+
+namespace cubit {
+
+constexpr int kDenseWarps = 8;
+constexpr int kDenseThreads = kDenseWarps * 32;
+constexpr int kDenseRowsBytes = (kPackBlock + 8) * 2 + 16; // 10-bit row numbers of one block (+ pad slot), 16-byte multiple
+constexpr int kDenseWarpFixed = kDenseRowsBytes + 16;      // + the warp's two mbarriers
+
+template <int NL>
+struct BlockHdrs { // headers of the block being decoded, one per probed column (warp-uniform registers)
+	long long base[NL];
+	uint32_t width[NL];
+	uint32_t pk[NL]; // shared-window address of the staged payload
+};
+
+// position-ordered write-out of `count` selected rows of ONE pack block (row numbers staged at cbuf[pad ..))
+template <int NL, bool POS>
+__device__ __forceinline__ void dense_write_out(const DenseProbeArgs &a, const uint16_t *cbuf, uint32_t pad, uint32_t count,
+                                                unsigned long long pos0, long long local0, const BlockHdrs<NL> &bh, int lane,
+                                                Agg &agg) {
+	const unsigned long long obase = pos0 - pad; // output position of staging index 0 (even)
+	const uint32_t end = pad + count;
+	const uint32_t *cb32 = reinterpret_cast<const uint32_t *>(cbuf);
+	uint32_t mask[NL];
+#pragma unroll
+	for (int c = 0; c < NL; c++) {
+		mask[c] = bh.width[c] >= 32u ? 0xffffffffu : (1u << bh.width[c]) - 1u;
+	}
+	for (uint32_t g0 = 0; g0 * 2 < end; g0 += 64) {
+		long long v[2][2][NL];
+		bool ok[2][2];
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const uint32_t g = g0 + h * 32 + lane; // pair index
+			const uint32_t packed = g * 2 < end ? cb32[g] : 0u;
+			// (10-bit row numbers; the mask keeps the decode of a slot past the list — stale staging bytes — inside the stage)
+			const uint32_t r[2] = {packed & (uint32_t)(kPackBlock - 1), (packed >> 16) & (uint32_t)(kPackBlock - 1)};
+			ok[h][0] = g * 2 >= pad && g * 2 < end;
+			ok[h][1] = g * 2 + 1 < end;
+#pragma unroll
+			for (int e = 0; e < 2; e++) {
+#pragma unroll
+				for (int c = 0; c < NL; c++) {
+					if (a.lcol[c].raw) {
+						v[h][e][c] = ok[h][e] ? __ldg(a.lcol[c].raw + local0 + r[e]) : 0;
+					} else { // (a lane without a row decodes some row of the stage: harmless, never used)
+						const uint32_t bit = r[e] * bh.width[c];
+						const uint32_t ad = bh.pk[c] + ((bit >> 5) << 2);
+						uint32_t lo, hi;
+						asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lo) : "r"(ad));
+						asm volatile("ld.shared.b32 %0, [%1+4];" : "=r"(hi) : "r"(ad));
+						v[h][e][c] = bh.base[c] + (long long)(__funnelshift_r(lo, hi, bit & 31u) & mask[c]);
+					}
+				}
+			}
+		}
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const uint32_t g = g0 + h * 32 + lane;
+			if (POS) {
+				if (ok[h][0] && ok[h][1]) {
+#pragma unroll
+					for (int c = 0; c < NL; c++) {
+						if (a.lout[c]) {
+							__stcs(reinterpret_cast<longlong2 *>(a.lout[c] + obase + g * 2),
+							       make_longlong2(v[h][0][c], v[h][1][c]));
+						}
+					}
+				} else {
+#pragma unroll
+					for (int e = 0; e < 2; e++) {
+#pragma unroll
+						for (int c = 0; c < NL; c++) {
+							if (ok[h][e] && a.lout[c]) {
+								__stcs(a.lout[c] + obase + g * 2 + e, v[h][e][c]);
+							}
+						}
+					}
+				}
+			}
+#pragma unroll
+			for (int e = 0; e < 2; e++) {
+				if (ok[h][e] && a.agg_kind != 0) {
+					const long long x = (NL > 1 && a.agg_ia == 1) ? v[h][e][NL - 1] : v[h][e][0];
+					if (a.agg_kind == 1) {
+						add128(agg.lo, agg.hi, x);
+					} else if (a.agg_kind == 2) {
+						const long long y = (NL > 1 && a.agg_ib == 1) ? v[h][e][NL - 1] : v[h][e][0];
+						const long long pr = x * y;
+						if (__mul64hi(x, y) != (pr >> 63)) {
+							agg.overflow = 1;
+						}
+						add128(agg.lo, agg.hi, pr);
+					} else {
+						agg.f += __longlong_as_double(x);
+					}
+				}
+			}
+		}
+	}
+}
+
+// SB: pack blocks per span (a span = one consumer warp's share of a segment in the scan kernel: 2·WPT blocks)
+template <int SB, int NL, bool POS>
+__global__ void __launch_bounds__(kDenseThreads, 2) cubit_probe_dense_kernel(const __grid_constant__ DenseProbeArgs a) {
+	extern __shared__ __align__(128) unsigned char dense_smem[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	unsigned char *wbase = dense_smem + (size_t)warp * a.warp_bytes;
+	uint16_t *cbuf = reinterpret_cast<uint16_t *>(wbase);
+	uint64_t *full = reinterpret_cast<uint64_t *>(wbase + kDenseRowsBytes);
+	uint32_t pk0[NL], pk_stride[NL]; // shared-window address of stage 0 of every column, bytes between its two stages
+	{
+		uint32_t off = kDenseWarpFixed;
+#pragma unroll
+		for (int c = 0; c < NL; c++) {
+			pk0[c] = smem_u32(wbase + off);
+			pk_stride[c] = a.stage_bytes[c];
+			off += 2 * a.stage_bytes[c];
+		}
+	}
+	if (lane == 0) {
+		mbar_init(&full[0], 1);
+		mbar_init(&full[1], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+
+	const uint32_t gw = blockIdx.x * kDenseWarps + warp, nw = gridDim.x * kDenseWarps;
+	// the selection bits of one span as 32-bit pieces: piece (j, lane) = rows [j*1024 + 32*lane, +32) of the span;
+	// lane j also holds the headers of the span's block j
+	auto load_span = [&](uint32_t sp, uint32_t (&w)[SB], uint4 (&h)[NL], unsigned long long &ex) {
+#pragma unroll
+		for (int j = 0; j < SB; j++) {
+			w[j] = 0;
+		}
+		if (sp < a.n_span) {
+			const uint32_t *src = reinterpret_cast<const uint32_t *>(a.q) + (size_t)sp * (SB * 32);
+#pragma unroll
+			for (int j = 0; j < SB; j++) {
+				w[j] = __ldg(src + j * 32 + lane);
+			}
+			if (POS) {
+				ex = __ldg(a.span_excl + sp);
+			}
+			const uint64_t blk = (uint64_t)sp * SB + (uint64_t)lane;
+#pragma unroll
+			for (int c = 0; c < NL; c++) {
+				h[c] = make_uint4(0, 0, 0, 0);
+				if (!a.lcol[c].raw && lane < SB && blk < a.n_blk) {
+					h[c] = __ldg(reinterpret_cast<const uint4 *>(a.lcol[c].hdr + blk));
+				}
+			}
+		}
+	};
+	uint32_t n_iss = 0, n_con = 0; // bulk copies issued / consumed by this warp (warp-uniform)
+	// one bulk copy per packed column of block j of the span whose headers are `h`, into stage (n_iss & 1)
+	auto issue = [&](const uint4 (&h)[NL], uint32_t j) {
+		uint32_t off[NL], bytes[NL], total = 0;
+#pragma unroll
+		for (int c = 0; c < NL; c++) {
+			off[c] = __shfl_sync(0xffffffffu, h[c].z, j);
+			bytes[c] = a.lcol[c].raw ? 0u : __shfl_sync(0xffffffffu, h[c].w, j) * (uint32_t)(kPackBlock / 8);
+			total += bytes[c];
+		}
+		if (lane == 0) {
+			const uint32_t st = n_iss & 1u;
+			mbar_arrive_expect_tx(&full[st], total);
+#pragma unroll
+			for (int c = 0; c < NL; c++) {
+				if (bytes[c]) {
+					asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+					                 pk0[c] + st * pk_stride[c]),
+					             "l"(a.lcol[c].words + off[c]), "r"(bytes[c]), "r"(smem_u32(&full[st]))
+					             : "memory");
+				}
+			}
+		}
+		n_iss++;
+	};
+
+	uint32_t cur[SB], nxt[SB];
+	uint4 hc[NL], hn[NL];
+	unsigned long long exc = 0, exn = 0;
+	load_span(gw, cur, hc, exc);
+	load_span(gw + nw, nxt, hn, exn);
+	Agg agg;
+	bool pend = false; // the copy of this span's first non-empty block was issued while the previous span was decoded
+	for (uint32_t sp = gw; sp < a.n_span; sp += nw) {
+		uint32_t m = 0, mn = 0; // non-empty blocks of this span / of the next one
+#pragma unroll
+		for (int j = 0; j < SB; j++) {
+			m |= (__any_sync(0xffffffffu, cur[j] != 0u) ? 1u : 0u) << j;
+			mn |= (__any_sync(0xffffffffu, nxt[j] != 0u) ? 1u : 0u) << j;
+		}
+		if (m && !pend) {
+			issue(hc, (uint32_t)__ffs(m) - 1u);
+		}
+		pend = false;
+		unsigned long long pos = exc;
+		while (m) {
+			const uint32_t j = (uint32_t)__ffs(m) - 1u;
+			m &= m - 1u;
+			// keep one copy ahead: the next non-empty block of this span, else the first one of the next span
+			if (m) {
+				issue(hc, (uint32_t)__ffs(m) - 1u);
+			} else if (mn) {
+				issue(hn, (uint32_t)__ffs(mn) - 1u);
+				pend = true;
+			}
+			uint32_t w = cur[0];
+#pragma unroll
+			for (int i = 1; i < SB; i++) {
+				w = j == (uint32_t)i ? cur[i] : w;
+			}
+			const uint32_t c = (uint32_t)__popc(w);
+			uint32_t incl = c;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+				if (lane >= d) {
+					incl += n;
+				}
+			}
+			const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+			const uint32_t pad = POS ? (uint32_t)pos & 1u : 0u;
+			stage_word(cbuf, pad + incl - c, w & 0xffffu, w >> 16, (uint32_t)lane * 32u, 0u, 16u);
+			BlockHdrs<NL> bh;
+			const uint32_t st = n_con & 1u;
+#pragma unroll
+			for (int cc = 0; cc < NL; cc++) {
+				const uint32_t blo = __shfl_sync(0xffffffffu, hc[cc].x, j), bhi = __shfl_sync(0xffffffffu, hc[cc].y, j);
+				bh.base[cc] = (long long)(((unsigned long long)bhi << 32) | blo);
+				bh.width[cc] = __shfl_sync(0xffffffffu, hc[cc].w, j);
+				bh.pk[cc] = pk0[cc] + st * pk_stride[cc];
+			}
+			__syncwarp();
+			mbar_wait(&full[st], (n_con >> 1) & 1u);
+			dense_write_out<NL, POS>(a, cbuf, pad, total, pos, ((long long)sp * SB + j) * kPackBlock, bh, lane, agg);
+			__syncwarp(); // every lane is done with the staging row and with stage `st` before either is refilled
+			pos += total;
+			n_con++;
+		}
+#pragma unroll
+		for (int j = 0; j < SB; j++) {
+			cur[j] = nxt[j];
+		}
+#pragma unroll
+		for (int c = 0; c < NL; c++) {
+			hc[c] = hn[c];
+		}
+		exc = exn;
+		load_span(sp + 2 * nw, nxt, hn, exn);
+	}
+	if (a.agg_kind != 0) {
+		agg_flush_warp(agg, a.hdr, lane);
+	}
+}
+
+// ------------------------------------------------------------------------------------------ launch
+template <int SB, int NL, bool POS>
+static cudaError_t launch_dense_t(const DenseProbeArgs &args, int sm_count, cudaStream_t stream) {
+	auto kern = cubit_probe_dense_kernel<SB, NL, POS>;
+	const size_t smem = (size_t)args.warp_bytes * kDenseWarps;
+	int dev = 0;
+	cudaGetDevice(&dev);
+	dev &= 63;
+	static size_t smem_set[64] = {}; // largest dynamic shared memory this instance was configured for, per device
+	if (smem > smem_set[dev]) {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) {
+			return e;
+		}
+		smem_set[dev] = smem;
+	}
+	int b = 0;
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kDenseThreads, smem);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	if (b < 1) {
+		return cudaErrorInvalidConfiguration;
+	}
+	long long grid = (long long)sm_count * b; // resident CTAs; spans strided over all warps of the grid
+	const long long need = ((long long)args.n_span + kDenseWarps - 1) / kDenseWarps;
+	grid = grid > need ? need : grid;
+	grid = grid < 1 ? 1 : grid;
+	kern<<<(unsigned)grid, kDenseThreads, smem, stream>>>(args);
+	return cudaGetLastError();
+}
+
+template <int SB>
+static cudaError_t launch_dense_sb(const DenseProbeArgs &args, bool positions, int sm_count, cudaStream_t stream) {
+	if (args.n_load == 1) {
+		return positions ? launch_dense_t<SB, 1, true>(args, sm_count, stream)
+		                 : launch_dense_t<SB, 1, false>(args, sm_count, stream);
+	}
+	if (args.n_load == 2) {
+		return positions ? launch_dense_t<SB, 2, true>(args, sm_count, stream)
+		                 : launch_dense_t<SB, 2, false>(args, sm_count, stream);
+	}
+	return cudaErrorInvalidValue;
+}
+
+bool dense_probe_plan(DenseProbeArgs &args, const uint32_t *max_width) {
+	uint32_t bytes = kDenseWarpFixed;
+	bool any_packed = false;
+	for (int c = 0; c < args.n_load; c++) {
+		args.stage_bytes[c] = 0;
+		if (args.lcol[c].raw) {
+			continue;
+		}
+		if (max_width[c] > 32u) {
+			return false;
+		}
+		any_packed = true;
+		// one block's payload + 16 spare bytes (the decoder reads one 32-bit word past a value)
+		args.stage_bytes[c] = max_width[c] * (uint32_t)(kPackBlock / 8) + 16u;
+		bytes += 2u * args.stage_bytes[c];
+	}
+	args.warp_bytes = (bytes + 127u) & ~127u;
+	return any_packed && args.n_load >= 1 && args.n_load <= kMaxFusedCols;
+}
+
+cudaError_t launch_probe_dense(const DenseProbeArgs &args, uint32_t seg_words, bool positions, int sm_count,
+                               cudaStream_t stream) {
+	switch (seg_words) {
+	case 512:
+		return launch_dense_sb<4>(args, positions, sm_count, stream);
+	case 1024:
+		return launch_dense_sb<8>(args, positions, sm_count, stream);
+	case 2048:
+		return launch_dense_sb<16>(args, positions, sm_count, stream);
+	default:
+		return cudaErrorInvalidValue;
+	}
+}
+
+} // namespace cubit

@@ -1,4 +1,4 @@
-// scan_common.cuh — device helpers shared by the scan kernels (scan_kernel.cu, scan_kernel_ws.cu):
+// scan_common.cuh — device helpers shared by the scan and probe kernels (scan_kernel.cu, probe_dense_kernel.cu):
 // PTX glue (mbarrier, bulk async copy, relaxed status words), 128-bit accumulation, the prefix
 // warp's chain-free look-back, and the staged, position-ordered emission (stage_word / write_out /
 // emit_span).  See scan_kernel.cu for the algorithm description and the reference citations.
@@ -353,12 +353,13 @@ __device__ __forceinline__ void write_out(const ScanArgs &a, const uint16_t *cbu
 // lane-local compaction of one 64-bit word: its two halves are two independent ctz chains.
 // Branch-free: an exhausted chain keeps "storing" into a per-lane dummy slot behind the
 // staging area, so the loop body is straight-line code (no divergence regions).
+// (hi_off: row distance between the two halves — 32 for the halves of a 64-bit word, 16 when a 32-bit piece is split)
 __device__ __forceinline__ void stage_word(uint16_t *cbuf, uint32_t p0, uint32_t wlo, uint32_t whi, uint32_t bit0,
-                                           uint32_t dummy) {
+                                           uint32_t dummy, uint32_t hi_off = 32u) {
 #if !CUBIT_STAGE_ASM
 	uint32_t p1 = p0 + __popc(wlo);
 	uint32_t w0 = wlo, w1 = whi;
-	const uint32_t b1 = bit0 + 32u;
+	const uint32_t b1 = bit0 + hi_off;
 	while (w0 | w1) {
 		const uint32_t i0 = w0 ? p0 : dummy, i1 = w1 ? p1 : dummy;
 		cbuf[i0] = (uint16_t)(bit0 + (uint32_t)(__ffs(w0) - 1));
@@ -376,7 +377,7 @@ __device__ __forceinline__ void stage_word(uint16_t *cbuf, uint32_t p0, uint32_t
 	uint32_t a0 = smem_u32(cbuf + p0);
 	uint32_t a1 = a0 + 2u * (uint32_t)__popc(wlo);
 	uint32_t w0 = wlo, w1 = whi;
-	const uint32_t b1 = bit0 + 32u;
+	const uint32_t b1 = bit0 + hi_off;
 	while (w0 | w1) {
 		asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b32 f, g, t;\n\t.reg .b16 h;\n\t"
 		             "setp.ne.u32 p, %2, 0;\n\t"

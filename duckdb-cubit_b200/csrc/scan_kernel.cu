@@ -590,6 +590,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 						}
 						__syncwarp();
 						excl = sm.resp_excl[slot];
+						if (a.span_excl && lane == 0) { // where this warp's share of the segment starts in the output
+							a.span_excl[(size_t)ptile[kDefer - 1] * kConsumerWarps + warp] = excl + pwexcl[kDefer - 1];
+						}
 					}
 					if (ptotal[kDefer - 1] > 0 && !(dbg & 2u)) {
 						emit_begin<WPT>(pq[kDefer - 1], excl + pwexcl[kDefer - 1], es);

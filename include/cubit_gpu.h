@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CUBIT_GPU_ABI_VERSION 3
+#define CUBIT_GPU_ABI_VERSION 4
 
 /* error codes */
 #define CUBIT_OK 0
@@ -118,7 +118,16 @@ typedef struct cubit_result_info {
 	                           NULLs); 0 means the SQL SUM is NULL                                          */
 	const uint32_t *d_validity[CUBIT_MAX_PROBE_COLS]; /* device validity bits of the projected values (bit j of
 	                           32-bit word j/32 = result row j), NULL = that column holds no NULLs          */
+	uint32_t probe_path;    /* CUBIT_PROBE_*: which kernel probed the columns                              */
+	uint32_t reserved;
 } cubit_result_info;
+
+/* cubit_result_info.probe_path */
+#define CUBIT_PROBE_NONE 0   /* no column was probed                                                        */
+#define CUBIT_PROBE_FUSED 1  /* inside the scan kernel (CUBIT_Q_FUSE_PROBE)                                  */
+#define CUBIT_PROBE_BITS 2   /* bit-driven gather probe over the merged bitvector                            */
+#define CUBIT_PROBE_GATHER 3 /* gather over the row-ID list (sparse selections, NULL-bearing / 4-byte columns) */
+#define CUBIT_PROBE_DENSE 4  /* dense selections over bit-packed columns: pack blocks streamed through shared memory */
 
 /* ---- library ---------------------------------------------------------- */
 int cubit_gpu_abi_version(void);

@@ -24,10 +24,15 @@ def main():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--pack", action="store_true", help="store the payload column FOR-bit-packed")
     ap.add_argument("--keep-raw", action="store_true", help="with --pack: keep the raw column too (hybrid)")
+    ap.add_argument("--payload-bits", type=int, default=0,
+                    help="0: payload = row id (packs to 10 bits); b > 0: uniform random payload in [90000, 90000 + 2^b)")
     args = ap.parse_args()
     cubit = importlib.import_module("duckdb-cubit_b200")
     t = cubit.CubitTable(args.rows, seg_bits=args.seg_bits)
-    t.synth_column(0, 0)
+    if args.payload_bits:
+        t.synth_column(0, 3, seed=0xFEED, threshold=1 << args.payload_bits, hot_lo=90000)
+    else:
+        t.synth_column(0, 0)
     if args.pack:
         print(json.dumps({"packed_payload_bytes": t.pack_column(0, keep_raw=args.keep_raw)}), flush=True)
     variants = {
@@ -59,11 +64,12 @@ def main():
                         msp.append(r.info.ms_probe)
                     by = r.info.algo_bytes_scan + r.info.algo_bytes_probe
                     cnt = r.count
+                    path = r.info.probe_path
             ms.sort()
             msp.sort()
             m = ms[len(ms) // 2]
             mp = msp[len(msp) // 2]
-            rec = {"sel": s, "variant": name, "count": cnt, "ms_scan": round(m, 4), "ms_probe": round(mp, 4),
+            rec = {"sel": s, "variant": name, "count": cnt, "ms_scan": round(m, 4), "ms_probe": round(mp, 4), "probe_path": path,
                    "algo_GBps": round(by / ((m + mp) * 1e-3) / 1e9, 1), "Grows_per_s": round(args.rows / ((m + mp) * 1e-3) / 1e9, 1)}
             print(json.dumps(rec), flush=True)
             out.append(rec)

@@ -29,84 +29,111 @@ namespace cubit {
 
 constexpr int kDenseWarps = 8;
 constexpr int kDenseThreads = kDenseWarps * 32;
-constexpr int kDenseRowsBytes = (kPackBlock + 8) * 2 + 16; // 10-bit row numbers of one block (+ pad slot), 16-byte multiple
-constexpr int kDenseWarpFixed = kDenseRowsBytes + 16;      // + the warp's two mbarriers
+// staging row of 10-bit row numbers: one block (+ pad slot) and a whole write-out iteration of slack, so that the
+// write-out reads its 128 slots unconditionally
+constexpr int kDenseRowsBytes = (kPackBlock + 128 + 8) * 2;
+constexpr int kDenseWarpFixed = kDenseRowsBytes + 16; // + the warp's two mbarriers
+
+// how the aggregate is accumulated (kernel template parameter, so the write-out loop carries no dispatch):
+//   0  no aggregate
+//   1  SUM over a bit-packed column: per block the lanes add up the 32-bit FOR deltas and count their rows; the
+//      block's base is multiplied in once per block (two instructions per value instead of a 128-bit add)
+//   2  everything else (SUM over a raw column, SUM(a*b) with the overflow check, SUM over DOUBLE): per value
+enum { DENSE_AGG_NONE = 0, DENSE_AGG_DELTA = 1, DENSE_AGG_GENERAL = 2 };
 
 template <int NL>
 struct BlockHdrs { // headers of the block being decoded, one per probed column (warp-uniform registers)
 	long long base[NL];
 	uint32_t width[NL];
+	uint32_t mask[NL];
 	uint32_t pk[NL]; // shared-window address of the staged payload
 };
 
-// position-ordered write-out of `count` selected rows of ONE pack block (row numbers staged at cbuf[pad ..))
-template <int NL, bool POS>
-__device__ __forceinline__ void dense_write_out(const DenseProbeArgs &a, const uint16_t *cbuf, uint32_t pad, uint32_t count,
-                                                unsigned long long pos0, long long local0, const BlockHdrs<NL> &bh, int lane,
-                                                Agg &agg) {
-	const unsigned long long obase = pos0 - pad; // output position of staging index 0 (even)
-	const uint32_t end = pad + count;
-	const uint32_t *cb32 = reinterpret_cast<const uint32_t *>(cbuf);
-	uint32_t mask[NL];
+// FOR delta of row r of a staged block: bits [r*width, (r+1)*width) of the payload
+__device__ __forceinline__ uint32_t dense_delta(uint32_t pk, uint32_t r, uint32_t width, uint32_t mask) {
+	const uint32_t bit = r * width;
+	const uint32_t ad = pk + ((bit >> 5) << 2);
+	uint32_t lo, hi;
+	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lo) : "r"(ad));
+	asm volatile("ld.shared.b32 %0, [%1+4];" : "=r"(hi) : "r"(ad));
+	return __funnelshift_r(lo, hi, bit) & mask; // (the shift amount is taken modulo 32)
+}
+
+struct DenseAcc { // per-lane accumulators of the block being decoded (DENSE_AGG_DELTA)
+	unsigned long long dsum = 0;
+	uint32_t rows = 0;
+};
+
+// One write-out iteration: staged rows [2*g0, 2*g0 + 128) of the block → 128 consecutive output positions; lane l
+// handles pairs g0 + l and g0 + 32 + l.  FULL: every one of the 128 slots holds a selected row (no predicates).
+template <int NL, bool POS, bool RAW, int AGGM, bool FULL>
+__device__ __forceinline__ void dense_iter(const DenseProbeArgs &a, const uint32_t *cb32, uint32_t g0, uint32_t pad,
+                                           uint32_t end, unsigned long long obase, long long local0,
+                                           const BlockHdrs<NL> &bh, int lane, Agg &agg, DenseAcc &acc) {
+	long long v[2][2][NL];
+	uint32_t dl[2][2]; // FOR deltas of the aggregate column (DENSE_AGG_DELTA)
+	bool ok[2][2];
+	constexpr int CA = 0; // DENSE_AGG_DELTA: the aggregate column is column agg_ia; resolved below
 #pragma unroll
-	for (int c = 0; c < NL; c++) {
-		mask[c] = bh.width[c] >= 32u ? 0xffffffffu : (1u << bh.width[c]) - 1u;
+	for (int h = 0; h < 2; h++) {
+		const uint32_t g = g0 + h * 32 + lane; // pair index
+		const uint32_t packed = cb32[g];
+		// (10-bit row numbers: the mask keeps the decode of a slot past the list — stale staging bytes — inside the stage)
+		const uint32_t r[2] = {FULL ? packed & 0xffffu : packed & (uint32_t)(kPackBlock - 1),
+		                       FULL ? packed >> 16 : (packed >> 16) & (uint32_t)(kPackBlock - 1)};
+		ok[h][0] = FULL || (g * 2 >= pad && g * 2 < end);
+		ok[h][1] = FULL || g * 2 + 1 < end;
+#pragma unroll
+		for (int e = 0; e < 2; e++) {
+#pragma unroll
+			for (int c = 0; c < NL; c++) {
+				if (RAW && a.lcol[c].raw) {
+					v[h][e][c] = ok[h][e] ? __ldg(a.lcol[c].raw + local0 + r[e]) : 0;
+				} else {
+					const uint32_t d = dense_delta(bh.pk[c], r[e], bh.width[c], bh.mask[c]);
+					if (AGGM == DENSE_AGG_DELTA && (NL == 1 || c == a.agg_ia)) {
+						dl[h][e] = d;
+					}
+					if (POS || AGGM == DENSE_AGG_GENERAL) {
+						v[h][e][c] = bh.base[c] + (long long)d;
+					}
+				}
+			}
+		}
 	}
-	for (uint32_t g0 = 0; g0 * 2 < end; g0 += 64) {
-		long long v[2][2][NL];
-		bool ok[2][2];
+	(void)CA;
 #pragma unroll
-		for (int h = 0; h < 2; h++) {
-			const uint32_t g = g0 + h * 32 + lane; // pair index
-			const uint32_t packed = g * 2 < end ? cb32[g] : 0u;
-			// (10-bit row numbers; the mask keeps the decode of a slot past the list — stale staging bytes — inside the stage)
-			const uint32_t r[2] = {packed & (uint32_t)(kPackBlock - 1), (packed >> 16) & (uint32_t)(kPackBlock - 1)};
-			ok[h][0] = g * 2 >= pad && g * 2 < end;
-			ok[h][1] = g * 2 + 1 < end;
-#pragma unroll
-			for (int e = 0; e < 2; e++) {
+	for (int h = 0; h < 2; h++) {
+		const uint32_t g = g0 + h * 32 + lane;
+		if (POS) {
+			if (FULL || (ok[h][0] && ok[h][1])) {
 #pragma unroll
 				for (int c = 0; c < NL; c++) {
-					if (a.lcol[c].raw) {
-						v[h][e][c] = ok[h][e] ? __ldg(a.lcol[c].raw + local0 + r[e]) : 0;
-					} else { // (a lane without a row decodes some row of the stage: harmless, never used)
-						const uint32_t bit = r[e] * bh.width[c];
-						const uint32_t ad = bh.pk[c] + ((bit >> 5) << 2);
-						uint32_t lo, hi;
-						asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lo) : "r"(ad));
-						asm volatile("ld.shared.b32 %0, [%1+4];" : "=r"(hi) : "r"(ad));
-						v[h][e][c] = bh.base[c] + (long long)(__funnelshift_r(lo, hi, bit & 31u) & mask[c]);
+					if (a.lout[c]) {
+						__stcs(reinterpret_cast<longlong2 *>(a.lout[c] + obase + g * 2), make_longlong2(v[h][0][c], v[h][1][c]));
+					}
+				}
+			} else {
+#pragma unroll
+				for (int e = 0; e < 2; e++) {
+#pragma unroll
+					for (int c = 0; c < NL; c++) {
+						if (ok[h][e] && a.lout[c]) {
+							__stcs(a.lout[c] + obase + g * 2 + e, v[h][e][c]);
+						}
 					}
 				}
 			}
 		}
 #pragma unroll
-		for (int h = 0; h < 2; h++) {
-			const uint32_t g = g0 + h * 32 + lane;
-			if (POS) {
-				if (ok[h][0] && ok[h][1]) {
-#pragma unroll
-					for (int c = 0; c < NL; c++) {
-						if (a.lout[c]) {
-							__stcs(reinterpret_cast<longlong2 *>(a.lout[c] + obase + g * 2),
-							       make_longlong2(v[h][0][c], v[h][1][c]));
-						}
-					}
-				} else {
-#pragma unroll
-					for (int e = 0; e < 2; e++) {
-#pragma unroll
-						for (int c = 0; c < NL; c++) {
-							if (ok[h][e] && a.lout[c]) {
-								__stcs(a.lout[c] + obase + g * 2 + e, v[h][e][c]);
-							}
-						}
-					}
+		for (int e = 0; e < 2; e++) {
+			if (AGGM == DENSE_AGG_DELTA) {
+				acc.dsum += FULL || ok[h][e] ? dl[h][e] : 0u;
+				if (!FULL) {
+					acc.rows += ok[h][e] ? 1u : 0u;
 				}
-			}
-#pragma unroll
-			for (int e = 0; e < 2; e++) {
-				if (ok[h][e] && a.agg_kind != 0) {
+			} else if (AGGM == DENSE_AGG_GENERAL) {
+				if (FULL || ok[h][e]) {
 					const long long x = (NL > 1 && a.agg_ia == 1) ? v[h][e][NL - 1] : v[h][e][0];
 					if (a.agg_kind == 1) {
 						add128(agg.lo, agg.hi, x);
@@ -124,11 +151,39 @@ __device__ __forceinline__ void dense_write_out(const DenseProbeArgs &a, const u
 			}
 		}
 	}
+	if (AGGM == DENSE_AGG_DELTA && FULL) {
+		acc.rows += 4u;
+	}
+}
+
+// position-ordered write-out of `count` selected rows of ONE pack block (row numbers staged at cbuf[pad ..))
+template <int NL, bool POS, bool RAW, int AGGM>
+__device__ __forceinline__ void dense_write_out(const DenseProbeArgs &a, const uint16_t *cbuf, uint32_t pad, uint32_t count,
+                                                unsigned long long pos0, long long local0, const BlockHdrs<NL> &bh, int lane,
+                                                Agg &agg) {
+	const unsigned long long obase = pos0 - pad; // output position of staging index 0 (even)
+	const uint32_t end = pad + count;
+	const uint32_t *cb32 = reinterpret_cast<const uint32_t *>(cbuf);
+	DenseAcc acc;
+	for (uint32_t g0 = 0; g0 * 2 < end; g0 += 64) {
+		if (g0 * 2 >= pad && g0 * 2 + 128 <= end) { // (warp-uniform)
+			dense_iter<NL, POS, RAW, AGGM, true>(a, cb32, g0, pad, end, obase, local0, bh, lane, agg, acc);
+		} else {
+			dense_iter<NL, POS, RAW, AGGM, false>(a, cb32, g0, pad, end, obase, local0, bh, lane, agg, acc);
+		}
+	}
+	if (AGGM == DENSE_AGG_DELTA) { // Σ (base + delta) over this lane's rows of the block = rows·base + Σ delta
+		const int ca = NL == 1 ? 0 : a.agg_ia;
+		const long long b = NL == 1 ? bh.base[0] : (ca == 1 ? bh.base[NL - 1] : bh.base[0]);
+		add128(agg.lo, agg.hi, (unsigned long long)(b * (long long)acc.rows), __mul64hi(b, (long long)acc.rows));
+		add128(agg.lo, agg.hi, acc.dsum, 0ll);
+	}
 }
 
 // SB: pack blocks per span (a span = one consumer warp's share of a segment in the scan kernel: 2·WPT blocks)
-template <int SB, int NL, bool POS>
-__global__ void __launch_bounds__(kDenseThreads, 2) cubit_probe_dense_kernel(const __grid_constant__ DenseProbeArgs a) {
+// RAW: some probed column is a raw array (gathered); AGGM: DENSE_AGG_*
+template <int SB, int NL, bool POS, bool RAW, int AGGM>
+__global__ void __launch_bounds__(kDenseThreads, 3) cubit_probe_dense_kernel(const __grid_constant__ DenseProbeArgs a) {
 	extern __shared__ __align__(128) unsigned char dense_smem[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	unsigned char *wbase = dense_smem + (size_t)warp * a.warp_bytes;
@@ -152,31 +207,32 @@ __global__ void __launch_bounds__(kDenseThreads, 2) cubit_probe_dense_kernel(con
 	__syncwarp();
 
 	const uint32_t gw = blockIdx.x * kDenseWarps + warp, nw = gridDim.x * kDenseWarps;
-	// the selection bits of one span as 32-bit pieces: piece (j, lane) = rows [j*1024 + 32*lane, +32) of the span;
-	// lane j also holds the headers of the span's block j
-	auto load_span = [&](uint32_t sp, uint32_t (&w)[SB], uint4 (&h)[NL], unsigned long long &ex) {
+	// the selection bits of one span as 32-bit pieces: piece (j, lane) = rows [j*1024 + 32*lane, +32) of the span
+	auto load_bits = [&](uint32_t sp, uint32_t (&w)[SB]) {
+		const uint32_t *src = reinterpret_cast<const uint32_t *>(a.q) + (size_t)sp * (SB * 32);
 #pragma unroll
 		for (int j = 0; j < SB; j++) {
-			w[j] = 0;
+			w[j] = sp < a.n_span ? __ldg(src + j * 32 + lane) : 0u;
 		}
-		if (sp < a.n_span) {
-			const uint32_t *src = reinterpret_cast<const uint32_t *>(a.q) + (size_t)sp * (SB * 32);
+	};
+	// lane j holds the headers of the span's block j
+	auto load_hdrs = [&](uint32_t sp, uint4 (&h)[NL]) {
+		const uint64_t blk = (uint64_t)sp * SB + (uint64_t)lane;
 #pragma unroll
-			for (int j = 0; j < SB; j++) {
-				w[j] = __ldg(src + j * 32 + lane);
-			}
-			if (POS) {
-				ex = __ldg(a.span_excl + sp);
-			}
-			const uint64_t blk = (uint64_t)sp * SB + (uint64_t)lane;
-#pragma unroll
-			for (int c = 0; c < NL; c++) {
-				h[c] = make_uint4(0, 0, 0, 0);
-				if (!a.lcol[c].raw && lane < SB && blk < a.n_blk) {
-					h[c] = __ldg(reinterpret_cast<const uint4 *>(a.lcol[c].hdr + blk));
-				}
+		for (int c = 0; c < NL; c++) {
+			h[c] = make_uint4(0, 0, 0, 0);
+			if (!(RAW && a.lcol[c].raw) && sp < a.n_span && lane < SB && blk < a.n_blk) {
+				h[c] = __ldg(reinterpret_cast<const uint4 *>(a.lcol[c].hdr + blk));
 			}
 		}
+	};
+	auto nonempty = [&](const uint32_t (&w)[SB]) {
+		uint32_t m = 0;
+#pragma unroll
+		for (int j = 0; j < SB; j++) {
+			m |= (__any_sync(0xffffffffu, w[j] != 0u) ? 1u : 0u) << j;
+		}
+		return m;
 	};
 	uint32_t n_iss = 0, n_con = 0; // bulk copies issued / consumed by this warp (warp-uniform)
 	// one bulk copy per packed column of block j of the span whose headers are `h`, into stage (n_iss & 1)
@@ -185,7 +241,7 @@ __global__ void __launch_bounds__(kDenseThreads, 2) cubit_probe_dense_kernel(con
 #pragma unroll
 		for (int c = 0; c < NL; c++) {
 			off[c] = __shfl_sync(0xffffffffu, h[c].z, j);
-			bytes[c] = a.lcol[c].raw ? 0u : __shfl_sync(0xffffffffu, h[c].w, j) * (uint32_t)(kPackBlock / 8);
+			bytes[c] = (RAW && a.lcol[c].raw) ? 0u : __shfl_sync(0xffffffffu, h[c].w, j) * (uint32_t)(kPackBlock / 8);
 			total += bytes[c];
 		}
 		if (lane == 0) {
@@ -204,25 +260,36 @@ __global__ void __launch_bounds__(kDenseThreads, 2) cubit_probe_dense_kernel(con
 		n_iss++;
 	};
 
-	uint32_t cur[SB], nxt[SB];
+	// Only the CURRENT span's bits stay in registers.  The next span's bits are loaded once at the top of a span to
+	// find its first non-empty block (whose copy is issued while this span's last block is decoded) and loaded again
+	// — an L1 / L2 hit by then — when the span becomes current: 8..16 registers per thread for one short stall per span.
+	uint32_t cur[SB];
 	uint4 hc[NL], hn[NL];
-	unsigned long long exc = 0, exn = 0;
-	load_span(gw, cur, hc, exc);
-	load_span(gw + nw, nxt, hn, exn);
 	Agg agg;
 	bool pend = false; // the copy of this span's first non-empty block was issued while the previous span was decoded
+	load_hdrs(gw, hn);
 	for (uint32_t sp = gw; sp < a.n_span; sp += nw) {
-		uint32_t m = 0, mn = 0; // non-empty blocks of this span / of the next one
-#pragma unroll
-		for (int j = 0; j < SB; j++) {
-			m |= (__any_sync(0xffffffffu, cur[j] != 0u) ? 1u : 0u) << j;
-			mn |= (__any_sync(0xffffffffu, nxt[j] != 0u) ? 1u : 0u) << j;
+		load_bits(sp, cur);
+		unsigned long long pos = 0;
+		if (POS) {
+			pos = __ldg(a.span_excl + sp);
 		}
+#pragma unroll
+		for (int c = 0; c < NL; c++) {
+			hc[c] = hn[c];
+		}
+		uint32_t mn; // non-empty blocks of the next span
+		{
+			uint32_t nb[SB];
+			load_bits(sp + nw, nb);
+			load_hdrs(sp + nw, hn);
+			mn = nonempty(nb);
+		}
+		uint32_t m = nonempty(cur);
 		if (m && !pend) {
 			issue(hc, (uint32_t)__ffs(m) - 1u);
 		}
 		pend = false;
-		unsigned long long pos = exc;
 		while (m) {
 			const uint32_t j = (uint32_t)__ffs(m) - 1u;
 			m &= m - 1u;
@@ -257,35 +324,26 @@ __global__ void __launch_bounds__(kDenseThreads, 2) cubit_probe_dense_kernel(con
 				const uint32_t blo = __shfl_sync(0xffffffffu, hc[cc].x, j), bhi = __shfl_sync(0xffffffffu, hc[cc].y, j);
 				bh.base[cc] = (long long)(((unsigned long long)bhi << 32) | blo);
 				bh.width[cc] = __shfl_sync(0xffffffffu, hc[cc].w, j);
+				bh.mask[cc] = bh.width[cc] >= 32u ? 0xffffffffu : (1u << bh.width[cc]) - 1u;
 				bh.pk[cc] = pk0[cc] + st * pk_stride[cc];
 			}
 			__syncwarp();
 			mbar_wait(&full[st], (n_con >> 1) & 1u);
-			dense_write_out<NL, POS>(a, cbuf, pad, total, pos, ((long long)sp * SB + j) * kPackBlock, bh, lane, agg);
+			dense_write_out<NL, POS, RAW, AGGM>(a, cbuf, pad, total, pos, ((long long)sp * SB + j) * kPackBlock, bh, lane, agg);
 			__syncwarp(); // every lane is done with the staging row and with stage `st` before either is refilled
 			pos += total;
 			n_con++;
 		}
-#pragma unroll
-		for (int j = 0; j < SB; j++) {
-			cur[j] = nxt[j];
-		}
-#pragma unroll
-		for (int c = 0; c < NL; c++) {
-			hc[c] = hn[c];
-		}
-		exc = exn;
-		load_span(sp + 2 * nw, nxt, hn, exn);
 	}
-	if (a.agg_kind != 0) {
+	if (AGGM != DENSE_AGG_NONE) {
 		agg_flush_warp(agg, a.hdr, lane);
 	}
 }
 
 // ------------------------------------------------------------------------------------------ launch
-template <int SB, int NL, bool POS>
+template <int SB, int NL, bool POS, bool RAW, int AGGM>
 static cudaError_t launch_dense_t(const DenseProbeArgs &args, int sm_count, cudaStream_t stream) {
-	auto kern = cubit_probe_dense_kernel<SB, NL, POS>;
+	auto kern = cubit_probe_dense_kernel<SB, NL, POS, RAW, AGGM>;
 	const size_t smem = (size_t)args.warp_bytes * kDenseWarps;
 	int dev = 0;
 	cudaGetDevice(&dev);
@@ -314,15 +372,38 @@ static cudaError_t launch_dense_t(const DenseProbeArgs &args, int sm_count, cuda
 	return cudaGetLastError();
 }
 
+template <int SB, int NL, bool POS, bool RAW>
+static cudaError_t launch_dense_agg(const DenseProbeArgs &args, int sm_count, cudaStream_t stream) {
+	if (args.agg_kind == 0) {
+		if (!POS) {
+			return cudaSuccess; // nothing to write, nothing to add
+		}
+		return launch_dense_t<SB, NL, POS, RAW, DENSE_AGG_NONE>(args, sm_count, stream);
+	}
+	const int ca = NL == 1 ? 0 : args.agg_ia;
+	if (args.agg_kind == 1 && !args.lcol[ca].raw) { // SUM over a bit-packed column
+		return launch_dense_t<SB, NL, POS, RAW, DENSE_AGG_DELTA>(args, sm_count, stream);
+	}
+	return launch_dense_t<SB, NL, POS, RAW, DENSE_AGG_GENERAL>(args, sm_count, stream);
+}
+
 template <int SB>
 static cudaError_t launch_dense_sb(const DenseProbeArgs &args, bool positions, int sm_count, cudaStream_t stream) {
-	if (args.n_load == 1) {
-		return positions ? launch_dense_t<SB, 1, true>(args, sm_count, stream)
-		                 : launch_dense_t<SB, 1, false>(args, sm_count, stream);
+	bool raw = false;
+	for (int c = 0; c < args.n_load; c++) {
+		raw |= args.lcol[c].raw != nullptr;
+	}
+	if (args.n_load == 1 && !raw) {
+		return positions ? launch_dense_agg<SB, 1, true, false>(args, sm_count, stream)
+		                 : launch_dense_agg<SB, 1, false, false>(args, sm_count, stream);
 	}
 	if (args.n_load == 2) {
-		return positions ? launch_dense_t<SB, 2, true>(args, sm_count, stream)
-		                 : launch_dense_t<SB, 2, false>(args, sm_count, stream);
+		if (raw) {
+			return positions ? launch_dense_agg<SB, 2, true, true>(args, sm_count, stream)
+			                 : launch_dense_agg<SB, 2, false, true>(args, sm_count, stream);
+		}
+		return positions ? launch_dense_agg<SB, 2, true, false>(args, sm_count, stream)
+		                 : launch_dense_agg<SB, 2, false, false>(args, sm_count, stream);
 	}
 	return cudaErrorInvalidValue;
 }

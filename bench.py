@@ -8,8 +8,12 @@ Workload (BASELINE.json configs[1]), per GPU:
 One STEP = the whole selectivity sweep: six queries
     OR over the 10 value bitvectors 10..19 → sorted int64 row IDs → probe payload at those
     rows (values materialised) → COUNT, SUM(payload)
-each as two sm_100a kernels: the single-pass fused merge+decode kernel, then the bit-driven probe
-kernel (gather + SUM).
+each as two sm_100a kernels: the single-pass fused merge+decode kernel, then a probe kernel (gather + SUM).  The
+payload column is resident raw (int64) AND FOR-bit-packed (the form DuckDB itself stores numeric columns in,
+SURVEY §8f rank 3); the library picks per query: gather over the row-ID list (sparsest points), bit-driven gather,
+or — from ~2 % of the rows upward — the dense probe that streams the packed column through shared memory
+(--payload-form raw|packed|both).  A second, 24-bit uniformly random payload (TPC-H l_extendedprice-like) is
+probed in both forms after the timed region and reported under "payload_24bit".
     value  = table rows covered per second, inputs resident in HBM, device-timed (CUDA events)
     e2e    = the same sweep through the synchronous C-ABI call a DuckDB table function makes
              (host predicate structs in, aggregate row + first 2048-row DataChunk out)
@@ -200,6 +204,62 @@ def workload_config(rows, gpus, scaling="weak", workload="cfg2"):
             "sharding": "row-range, %d shard(s)" % gpus}
 
 
+
+# ------------------------------------------------------------------ DRAM traffic (ncu, same invocation)
+KERNEL_FAMILIES = ("cubit_scan_kernel", "cubit_probe_dense_kernel", "cubit_probe_bits_kernel", "cubit_probe_kernel")
+
+
+def measure_traffic(args):
+    """DRAM bytes per launch of the step's kernels, measured by ncu on ONE step of the same workload in a child
+    process (after the timed region; the parent has released its table).  None when ncu cannot run here."""
+    import shutil
+    import tempfile
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    log = tempfile.NamedTemporaryFile(prefix="cubit_ncu_", suffix=".csv", delete=False).name
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none",
+           "--print-units", "base", "-k", "regex:cubit_(scan|probe)", "--csv", "--log-file", log,
+           sys.executable, os.path.abspath(__file__), "--traffic-child", "--rows", str(args.rows),
+           "--payload-form", args.payload_form]
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        if r.returncode != 0:
+            return None, "ncu child failed: " + (r.stderr.strip() or r.stdout.strip())[-160:]
+        return parse_ncu_traffic(log), None
+    except Exception as e:
+        return None, "ncu child: " + str(e)[:160]
+    finally:
+        try:
+            os.unlink(log)
+        except OSError:
+            pass
+
+
+def parse_ncu_traffic(path):
+    import csv
+    rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 10]
+    hdr = next(r for r in rows if "Kernel Name" in r and "Metric Value" in r)
+    ik, im, iv, ii = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+    per_launch = {}
+    for r in rows:
+        if r is hdr or len(r) <= iv or not r[ii].strip().isdigit():
+            continue
+        fam = next((f for f in KERNEL_FAMILIES if f in r[ik]), None)
+        if fam is None or not r[im].startswith("dram__bytes"):
+            continue
+        per_launch.setdefault((fam, int(r[ii])), 0.0)
+        per_launch[(fam, int(r[ii]))] += float(r[iv].replace(",", ""))
+    out = {}
+    for (fam, _id), b in per_launch.items():
+        d = out.setdefault(fam, {"launches": 0, "dram_bytes": 0.0})
+        d["launches"] += 1
+        d["dram_bytes"] += b
+    for d in out.values():
+        d["dram_bytes_per_launch"] = d["dram_bytes"] / d["launches"]
+    return out
+
+
 # ------------------------------------------------------------------ GPU arm
 def run_b200(args):
     import numpy as np
@@ -237,8 +297,11 @@ def run_b200(args):
     t.set_stream(stream.cuda_stream)
     t_build0 = time.time()
     with_payload = rows <= 8_000_000_000  # 8 B/row payload + index + row IDs must fit 180 GB
+    packed_bytes = None
     if with_payload:
         t.synth_column(COL_PAYLOAD, 0)
+        if args.payload_form != "raw":   # FOR-bit-packed form next to (or instead of) the raw int64 array
+            packed_bytes = t.pack_column(COL_PAYLOAD, keep_raw=(args.payload_form == "both"))
     indexes, expect, plans_async, plans_sync, labels = [], [], [], [], []
     flags = cubit.Q_ROWIDS | (cubit.Q_VALUES if with_payload else 0)
     kw = dict(cols=[COL_PAYLOAD], agg=cubit.AGG_SUM, agg_a=COL_PAYLOAD) if with_payload else {}
@@ -287,7 +350,7 @@ def run_b200(args):
         for r in res:
             r.wait()
         infos = [(r.info.ms_scan, r.info.ms_probe, r.info.algo_bytes_scan, r.info.algo_bytes_probe, r.count,
-                  r.info.n_launches, r.info.fused) for r in res]
+                  r.info.n_launches, r.info.fused, r.info.probe_path) for r in res]
         for r in res:
             r.free()
         return infos
@@ -298,6 +361,11 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    if args.traffic_child:   # under ncu (measure_traffic): exactly one step of the workload, nothing printed
+        step_device()
+        torch.cuda.synchronize()
+        t.close()
+        return 0
     for _ in range(args.warmup):
         infos = step_device()
     # correctness of what is being timed: COUNT equals Σ popcount of the (disjoint) value bitvectors; SUM(payload)
@@ -318,12 +386,18 @@ def run_b200(args):
     e0.record(stream)
     # per-kernel accumulators: [ms, algorithmic bytes, launches]
     kscan, kprobe = [0.0, 0, 0], [0.0, 0, 0]
-    per_q = [dict(ms_scan=0.0, ms_probe=0.0, by_scan=0, by_probe=0, cnt=0, fused=0) for _ in range(n_q)]
+    kpath = {}   # the same per probe kernel (cubit_result_info.probe_path)
+    per_q = [dict(ms_scan=0.0, ms_probe=0.0, by_scan=0, by_probe=0, cnt=0, fused=0, path=0) for _ in range(n_q)]
     for _ in range(args.steps):
         infos = step_device()
-        for i, (ms_s, ms_p, by_s, by_p, cnt, _nl, fused) in enumerate(infos):
+        for i, (ms_s, ms_p, by_s, by_p, cnt, _nl, fused, path) in enumerate(infos):
             ps = per_q[i]
-            ps["cnt"], ps["fused"] = cnt, fused
+            ps["cnt"], ps["fused"], ps["path"] = cnt, fused, path
+            if ms_p > 0:
+                kp = kpath.setdefault(path, [0.0, 0, 0])
+                kp[0] += ms_p
+                kp[1] += by_p
+                kp[2] += 1
             ps["ms_scan"] += ms_s
             ps["ms_probe"] += ms_p
             ps["by_scan"] += by_s
@@ -464,31 +538,90 @@ def run_b200(args):
             dist.destroy_process_group()
         return 0
 
-    peak, peak_src = measured_peak()
-    traffic = {}
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp))
-        except Exception:
-            traffic = {}
+    # ---- a realistically distributed payload in both forms (not part of the step): uniform values of 24 significant
+    # bits over a base, like TPC-H l_extendedprice in cents; column 2 stays raw, column 3 holds the same values packed
+    payload24 = None
+    if world == 1 and with_payload and not cfg5 and not args.no_payload24:
+        COL_P24_RAW, COL_P24_PK = 2, 3
+        t.synth_column(COL_P24_RAW, 3, seed=0xFEED, threshold=1 << 24, hot_lo=90000)
+        t.synth_column(COL_P24_PK, 3, seed=0xFEED, threshold=1 << 24, hot_lo=90000)
+        pk_bytes = t.pack_column(COL_P24_PK, keep_raw=False)
+        payload24 = {"distribution": "uniform int64 in [90000, 90000 + 2^24)", "raw_bytes": rows * 8,
+                     "packed_bytes": pk_bytes, "points": []}
+        names = {0: "none", 1: "fused", 2: "bit-driven gather", 3: "gather over row IDs", 4: "dense (streamed)"}
+        for s_lbl, ix in zip(labels, indexes):
+            groups = [[(ix, v) for v in range(HOT_LO, HOT_LO + HOT_N)]]
+            rec = {"selectivity": s_lbl}
+            sums = []
+            for form, col in (("raw", COL_P24_RAW), ("packed", COL_P24_PK)):
+                plan = cubit.QueryPlan(groups, flags | cubit.Q_TIMING, cols=[col], agg=cubit.AGG_SUM, agg_a=col)
+                best = None
+                for _ in range(4):
+                    with t.execute(plan) as r:
+                        ms_p, path, sm = r.info.ms_probe, r.info.probe_path, r.sum
+                    best = ms_p if best is None or ms_p < best else best
+                rec[form + "_probe_ms"] = best
+                rec[form + "_kernel"] = names.get(path, str(path))
+                sums.append(sm)
+            assert sums[0] == sums[1], "raw and packed forms of the 24-bit payload disagree"
+            payload24["points"].append(rec)
+        t.drop_column(COL_P24_RAW)
+        t.drop_column(COL_P24_PK)
 
-    def roof(acc, kernel, tkey, formula):
+    peak, peak_src = measured_peak()
+    # ---- DRAM traffic of the step's kernels: ncu on one step of this very workload, in a child process, now that
+    # the timed regions are over (the table is released first: two copies do not fit).  Falls back to the committed
+    # capture of the same command when ncu cannot run here.
+    traffic, traffic_src = None, None
+    if world == 1 and not args.no_traffic and not cfg5:
+        t.close()
+        traffic, err = measure_traffic(args)
+        traffic_src = "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum on one step of this workload, child " \
+                      "process of this run" if traffic else None
+        if traffic is None:
+            traffic_src = "unavailable in this run (%s)" % err
+    if traffic is None:
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                static = json.load(open(tp))
+                traffic = {k[:-len("_dram_bytes_per_launch")]: {"dram_bytes_per_launch": v} for k, v in static.items()
+                           if k.endswith("_dram_bytes_per_launch")}
+                traffic_src = (traffic_src + "; " if traffic_src else "") + "static: profiles/" + str(static.get("source"))
+            except Exception:
+                traffic = None
+
+    def roof(acc, kernel, family, formula):
         ms, by, n = acc
         ach = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        fams = family if isinstance(family, (list, tuple)) else [family]
+        tr = None
+        if traffic:   # bytes per launch, averaged over the launches of these kernel families in one step
+            tb = sum(traffic[f].get("dram_bytes", traffic[f]["dram_bytes_per_launch"]) for f in fams if f in traffic)
+            tn = sum(traffic[f].get("launches", 1) for f in fams if f in traffic)
+            tr = tb / tn if tn else None
         return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "frac_of_nominal_8TBs": ach / 8000.0, "traffic": traffic.get(tkey), "traffic_source": traffic.get("source"),
+                "frac_of_nominal_8TBs": ach / 8000.0, "traffic": tr, "traffic_source": traffic_src,
                 "peak_source": peak_src,
                 "launches": n, "bytes_per_launch_avg": by / n if n else 0, "ms_per_launch_avg": ms / n if n else 0,
                 "share_of_step": ms / (ms_per_step * args.steps) if ms_per_step > 0 else 0, "bytes_formula": formula}
 
     roof_scan = roof(kscan, "cubit_scan_kernel<4,false,0,true,false> (segment merge + bit->row-ID decode, single pass)",
-                     "cubit_scan_kernel_dram_bytes_per_launch",
-                     "k*ceil(N/64)*8 + 8*M  [SURVEY 8d]")
-    roof_probe = roof(kprobe, "cubit_probe_bits_kernel<4,1,true,false> (bit-driven probe: gather payload + SUM; "
-                      "cubit_probe_kernel over the row-ID list for the sparsest points)",
-                      "cubit_probe_bits_kernel_dram_bytes_per_launch",
-                      "8*M payload values read + ceil(N/64)*8 re-read of the merged bitvector  [SURVEY 8d: P]")
+                     "cubit_scan_kernel", "k*ceil(N/64)*8 + 8*M  [SURVEY 8d]")
+    path_kernel = {2: ("cubit_probe_bits_kernel", "bit-driven gather probe over the merged bitvector"),
+                   3: ("cubit_probe_kernel", "gather probe over the row-ID list (sparsest points)"),
+                   4: ("cubit_probe_dense_kernel", "dense probe: pack blocks of the bit-packed payload streamed "
+                                                   "through shared memory by bulk async copies")}
+    roof_paths = {}
+    for path, acc in sorted(kpath.items()):
+        fam, what = path_kernel.get(path, ("?", "?"))
+        roof_paths[fam] = roof(acc, "%s (%s)" % (fam, what), fam,
+                               "8*M payload values (+ 8*M row IDs re-read by the gather kernel)  [SURVEY 8d: P]")
+    roof_probe = roof(kprobe, "probe kernels of the step: " + ", ".join(
+                          "%s x%d" % (path_kernel.get(p, ("?",))[0], a[2] // max(1, args.steps)) for p, a in sorted(kpath.items())),
+                      [path_kernel[p][0] for p in kpath if p in path_kernel],
+                      "8*M payload values (+ 8*M row IDs re-read by the gather kernel); the merged bitvector the "
+                      "probe re-reads is intermediate traffic and is not counted  [SURVEY 8d: P]")
     dominant = roof_probe if kprobe[0] > kscan[0] else roof_scan
     sweep = []
     for s, ps in zip(labels, per_q):
@@ -496,6 +629,7 @@ def run_b200(args):
         g_scan = ps["by_scan"] / (ps["ms_scan"] * 1e-3) / 1e9 if ps["ms_scan"] > 0 else 0.0
         sweep.append({"query" if cfg5 else "selectivity": s, "rows_selected": ps["cnt"],
                       "probe_fused": bool(ps["fused"] and ps["ms_probe"] == 0),
+                      "probe_kernel": path_kernel.get(ps["path"], ("none",))[0],
                       "scan_ms": ps["ms_scan"] / args.steps, "probe_ms": ps["ms_probe"] / args.steps,
                       "rows_per_s": rows / (ms_tot * 1e-3) if ms_tot > 0 else 0.0,
                       "scan_algo_gbs": g_scan, "scan_frac_of_peak": g_scan / peak})
@@ -507,6 +641,13 @@ def run_b200(args):
         "config": workload_config(args.rows, world, args.scaling, args.workload),
         "hbm_gbs": world * (kernel_bytes / args.steps) / (ms_per_step * 1e-3) / 1e9,
         "roofline": dominant, "roofline_merge_decode": roof_scan, "roofline_probe": roof_probe,
+        "roofline_probe_kernels": roof_paths,
+        "payload": {"column": "int64 = global row id (SURVEY 8d config 2; self-checking: SUM(payload) = SUM(rowid))",
+                    "forms_resident": args.payload_form, "raw_bytes": rows * 8 if args.payload_form != "packed" else 0,
+                    "packed_bytes": packed_bytes,
+                    "note": "FOR-bit-packed in blocks of 1024 rows (10 bits per value for this column); the library "
+                            "chooses the form per query; see payload_24bit for a column that packs to 24 bits"},
+        "payload_24bit": payload24,
         "sweep": sweep,
         "aggregate_reduce": "device limbs (cubit_gpu_result_add_limbs) + one NCCL all-reduce per step" if world > 1
                             else "device limbs (cubit_gpu_result_add_limbs)",
@@ -547,6 +688,11 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=1 << 26, help="rows per sweep point of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-materialize", action="store_true")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu child that measures DRAM bytes per kernel")
+    ap.add_argument("--no-payload24", action="store_true", help="skip the 24-bit payload raw/packed comparison")
+    ap.add_argument("--payload-form", default="both", choices=["both", "raw", "packed"],
+                    help="forms of the payload column kept in HBM (both: the library picks per query)")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --rows rows per GPU; strong: ONE table of --rows rows cut over the GPUs")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"],

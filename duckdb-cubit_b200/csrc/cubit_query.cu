@@ -628,7 +628,10 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 		if (separate_probe) {
 			r->probe_widths += 8; // the gather kernel re-reads the 8-byte row IDs
 		}
-		r->probe_fixed_bytes = probe_mode == PROBE_BITS ? t->n_words * 8 : 0; // ... the bit-driven one re-reads Q
+		// The merged bitvector the bit-driven / dense probes re-read is intermediate traffic of an unfused design and is
+		// NOT counted; when the probe runs straight on a value bitvector (probe_on_bv) that bitvector is the
+		// query's one input stream and is counted here, since no scan kernel reads it.
+		r->probe_fixed_bytes = probe_on_bv ? t->n_words * 8 : 0;
 	}
 	r->info.capacity = cap;
 	r->info.probe_path = dense_probe                    ? CUBIT_PROBE_DENSE

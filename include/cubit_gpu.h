@@ -105,7 +105,8 @@ typedef struct cubit_result_info {
 	uint32_t n_launches;    /* kernels launched for this query                   */
 	uint64_t delta_entries; /* pending-delta words XOR-ed at query time          */
 	uint64_t algo_bytes_scan;  /* k*ceil(N/64)*8 + delta + 8*count   */
-	uint64_t algo_bytes_probe; /* count*(8 + Σ col widths) for a separate probe  */
+	uint64_t algo_bytes_probe; /* count*Σ col widths (+ 8*count when a gather kernel re-reads the row IDs); the
+	                              re-read of the merged bitvector by the bit-driven / dense probe is not counted */
 	float ms_scan;          /* merge+decode kernel(s), CUDA events (CUBIT_Q_TIMING) */
 	float ms_probe;         /* probe kernel                                      */
 	float ms_total;         /* first launch → last launch of the query           */

@@ -674,8 +674,8 @@ extern "C" int cubit_gpu_append_rows(cubit_gpu_table *t, uint64_t n_new, const c
 		uint64_t cap = 0;
 	};
 	const bool restride = new_n_seg * t->seg_words > t->words_per_bv;
-	const uint64_t cap_seg = restride ? std::max<uint64_t>(new_n_seg, (uint64_t)(t->words_per_bv / t->seg_words) * 3 / 2 + 1)
-	                                  : t->words_per_bv / t->seg_words;
+	const uint64_t cap_seg = restride ? ((std::max<uint64_t>(new_n_seg, (uint64_t)(t->words_per_bv / t->seg_words) * 3 / 2 + 1) + 3) & ~3ull)
+	                                  : t->words_per_bv / t->seg_words; // (a multiple of 4 segments, as at creation)
 	const uint64_t new_stride = cap_seg * t->seg_words;
 	std::vector<NewBuf> nbits(t->indexes.size()), ncol(n_cols), nvalid(n_cols);
 	auto release_new = [&]() {

@@ -212,7 +212,9 @@ extern "C" int cubit_gpu_create(int device, uint64_t n_rows, int64_t row_base, u
 	t->seg_words = seg_bits / 64;
 	t->n_seg = (uint32_t)((n_rows + seg_bits - 1) / seg_bits);
 	t->n_words = (n_rows + 63) / 64;
-	t->words_per_bv = (uint64_t)t->n_seg * t->seg_words;
+	// capacity in whole segments, rounded up to a multiple of 4 (zero-filled like every pad bit): short queries scan
+	// 2 or 4 consecutive segments as one tile (cubit_query.cu, tile_mult), and the last tile must not leave the bitvector
+	t->words_per_bv = (((uint64_t)t->n_seg + 3) & ~3ull) * t->seg_words;
 	cudaDeviceProp prop;
 	e = cudaGetDeviceProperties(&prop, device);
 	if (e != cudaSuccess) {

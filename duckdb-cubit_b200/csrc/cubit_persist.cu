@@ -64,13 +64,17 @@ bool wah_compress(const uint64_t *words, uint64_t n_rows, uint64_t limit, std::v
 	};
 	for (uint64_t g = 0; g < n_groups; g++) {
 		const uint32_t raw = bits_at(g * 31, 31);
-		if (raw == 0 || raw == 0x7fffffffu) {
+		if (raw == 0 || raw == 0x7fffffffu) { // (FastBit's append rule: a lone fill group is a literal, fills start at 2)
 			const uint32_t fill = 0x80000000u | (raw ? 0x40000000u : 0u);
+			if (!out.empty() && out.back() == raw) {
+				out.back() = fill | 2u;
+				continue;
+			}
 			if (!out.empty() && (out.back() & 0xc0000000u) == fill && (out.back() & 0x3fffffffu) < 0x3fffffffu) {
 				out.back()++;
 				continue;
 			}
-			out.push_back(fill | 1u);
+			out.push_back(raw);
 		} else {
 			out.push_back(reverse(raw, 31));
 		}

@@ -16,9 +16,9 @@ using namespace cubit;
 // several host threads keep queries and hand-offs in flight on one table (table.h).
 // -------------------------------------------------------------------- query
 
-static cudaError_t run_scan(const ScanArgs &sa, uint32_t seg_words, bool has_delta, bool compressed, int sm_count,
+static cudaError_t run_scan(const ScanArgs &sa, uint32_t tile_words, bool has_delta, bool compressed, int sm_count,
                             cudaStream_t st) {
-	return launch_scan(sa, seg_words, has_delta, compressed, sm_count, st, nullptr);
+	return launch_scan(sa, tile_words, has_delta, compressed, sm_count, st, nullptr);
 }
 
 // (the pinned header and the completion event go back to the table's pools)
@@ -214,7 +214,33 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	if (const char *dbg = getenv("CUBIT_SCAN_DEBUG")) {
 		sa.debug = (unsigned)atoi(dbg); // kernel timing experiments: skips parts of the kernel, results invalid
 	}
-	sa.n_seg = t->n_seg;
+	// Tile = the unit the scan kernel hands out.  It is the table's segment, except for SHORT queries: every tile costs
+	// a CTA's consumers ≈ 1 µs of dependent latency (ring wait → fold → count → publish → look-back hand-off → emit),
+	// so a tile must carry ≳ 24 KiB for that to hide behind the bulk copies (profiles/r1_ncu_scan_s01.md,
+	// profiles/r2_small_k.md).  With few bitvectors (or 32768-row segments) the kernel therefore treats 2 or 4
+	// CONSECUTIVE segments as one tile — bitvectors are contiguous, so this is the same kernel instantiated for the
+	// larger segment size.  Pending deltas and containers are keyed by the table's own segments and keep them.
+	uint32_t tile_mult = 1;
+	if (!has_delta && !has_compressed && !(q->flags & CUBIT_Q_UNFUSED)) {
+		while (t->seg_words * tile_mult * 2 <= 2048 && (uint64_t)k * t->seg_words * tile_mult * 8 < 24 * 1024 &&
+		       (uint64_t)((t->n_seg + tile_mult * 2 - 1) / (tile_mult * 2)) * (t->seg_words * tile_mult * 2) <= t->words_per_bv) {
+			tile_mult *= 2;
+		}
+		if (t->seg_words == 512 && tile_mult == 1 &&
+		    (uint64_t)((t->n_seg + 1) / 2) * 1024 <= t->words_per_bv) {
+			tile_mult = 2; // 32768-row segments: never below 65536-row tiles (consumer-bound otherwise)
+		}
+		if (const char *e = getenv("CUBIT_TILE_MULT")) { // experiments: 1 disables
+			const uint32_t m = (uint32_t)atoi(e);
+			if ((m == 1 || m == 2 || m == 4) && t->seg_words * m <= 2048 &&
+			    (uint64_t)((t->n_seg + m - 1) / m) * (t->seg_words * m) <= t->words_per_bv) {
+				tile_mult = m;
+			}
+		}
+	}
+	const uint32_t tile_words = t->seg_words * tile_mult;
+	const uint32_t n_tile = (t->n_seg + tile_mult - 1) / tile_mult;
+	sa.n_seg = n_tile;
 	sa.row_base = t->row_base;
 
 	// ---- projected / aggregate columns
@@ -484,7 +510,7 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 			sa.agg_ia = agg_ia;
 			sa.agg_ib = agg_ib;
 		}
-		Q_TRY(run_scan(sa, t->seg_words, has_delta, has_compressed, t->sm_count, st));
+		Q_TRY(run_scan(sa, tile_words, has_delta, has_compressed, t->sm_count, st));
 		n_launch++;
 		r->info.fused = 1;
 	} else {
@@ -519,7 +545,7 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	if (dense_probe) {
 		dp.q = sa.q_out;
 		dp.span_excl = sa.span_excl;
-		dp.n_span = t->n_seg * (uint32_t)kConsumerWarps;
+		dp.n_span = n_tile * (uint32_t)kConsumerWarps;
 		dp.n_blk = (t->n_rows + kPackBlock - 1) / kPackBlock;
 		for (int d = 0; d < n_dist; d++) {
 			dp.lout[d] = dist_out[d] >= 0 && cap ? static_cast<long long *>(r->d_vals[dist_out[d]]) : nullptr;
@@ -528,7 +554,7 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 		dp.agg_ia = agg_ia;
 		dp.agg_ib = agg_ib;
 		dp.hdr = r->d_hdr;
-		Q_TRY(launch_probe_dense(dp, t->seg_words, want_vals && cap, t->sm_count, st));
+		Q_TRY(launch_probe_dense(dp, tile_words, want_vals && cap, t->sm_count, st));
 		n_launch++;
 		if (r->timing) {
 			Q_TRY(cudaEventRecord(r->ev[2], st));
@@ -539,7 +565,7 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 		memset(&pb, 0, sizeof(pb));
 		pb.q_out = sa.q_out; // input of the bit-driven probe
 		pb.tile_excl = sa.tile_excl;
-		pb.n_seg = t->n_seg;
+		pb.n_seg = probe_on_bv ? t->n_seg : n_tile;
 		pb.row_base = t->row_base;
 		pb.n_load = n_dist;
 		for (int d = 0; d < n_dist; d++) {
@@ -551,7 +577,7 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 		pb.agg_ib = agg_ib;
 		pb.hdr = r->d_hdr;
 		pb.count_rows = probe_on_bv ? 1 : 0;
-		Q_TRY(launch_probe_bits(pb, t->seg_words, want_vals && cap, t->sm_count, st));
+		Q_TRY(launch_probe_bits(pb, probe_on_bv ? t->seg_words : tile_words, want_vals && cap, t->sm_count, st));
 		n_launch++;
 		if (r->timing) {
 			Q_TRY(cudaEventRecord(r->ev[2], st));

@@ -137,7 +137,7 @@ int cubit_gpu_device_count(int *count);
 
 /* ---- table shard -------------------------------------------------------
  * n_rows    rows held by this shard (row-range sharding)
- * row_base  global row ID of local row 0 (multiple of seg_bits)
+ * row_base  global row ID of local row 0 (a non-negative multiple of 64; shards of one table use multiples of seg_bits)
  * seg_bits  CUBIT segment size in rows: 32768, 65536 or 131072.  One segment
  *           is the unit of the merge kernel and of the pending-delta lists.  */
 int cubit_gpu_create(int device, uint64_t n_rows, int64_t row_base, uint32_t seg_bits, cubit_gpu_table **out);

@@ -13,8 +13,10 @@
  *   fill word      MSB = 1, bit 30 = the fill bit, low 30 bits = number of 31-bit groups the fill spans
  *   active word    the last (bitmap length mod 31) bits, kept apart: value in the low `nbits` bits, first bit
  *                  most significant of those
- * The one known-answer vector that description carries — the paper's 128-bit example, 1·0^20·1^3·0^79·1^25 →
- * 40000380 80000002 001FFFFF + active 0000000F (4 bits) — is checked in tests/test_wah.py.
+ * The writer follows FastBit's append rule (a lone all-zero / all-one group is written as a literal, fills start at
+ * two groups).  Known answers: the paper's 128-bit example, 1·0^20·1^3·0^79·1^25 → 40000380 80000002 001FFFFF +
+ * active 0000000F (4 bits), and the 40 vectors of tests/golden/wah_vectors.json, written by an independent
+ * pure-Python encoder (tests/golden/make_wah_golden.py) — all checked in tests/test_wah.py.
  */
 #include <stdint.h>
 #include <string.h>
@@ -40,22 +42,24 @@ ORACLE_API int64_t oracle_wah_encode(const uint64_t *words, uint64_t n_bits, uin
 		for (uint32_t b = 0; b < WAH_GROUP; b++) {
 			lit = (lit << 1) | bit_at(words, g * WAH_GROUP + b); /* first bit ends up most significant */
 		}
+		/* append rule of the FastBit writer (ibis::bitvector::append_active, bitvector.h): a single all-zero /
+		 * all-one group goes out as a LITERAL word; a second one in a row turns that literal into a fill of 2;
+		 * further ones increment the fill */
 		if (lit == 0 || lit == WAH_ALLONES) {
 			const uint32_t fill = 0x80000000u | (lit ? 0x40000000u : 0u);
-			if (n_out && (out[n_out - 1] & 0xc0000000u) == fill && (out[n_out - 1] & WAH_MAXCNT) < WAH_MAXCNT) {
-				out[n_out - 1]++; /* extend the running fill */
+			if (n_out && out[n_out - 1] == lit) {
+				out[n_out - 1] = fill | 2u;
 				continue;
 			}
-			if (n_out >= cap) {
-				return -1;
+			if (n_out && (out[n_out - 1] & 0xc0000000u) == fill && (out[n_out - 1] & WAH_MAXCNT) < WAH_MAXCNT) {
+				out[n_out - 1]++;
+				continue;
 			}
-			out[n_out++] = fill | 1u;
-		} else {
-			if (n_out >= cap) {
-				return -1;
-			}
-			out[n_out++] = lit;
 		}
+		if (n_out >= cap) {
+			return -1;
+		}
+		out[n_out++] = lit;
 	}
 	uint32_t av = 0;
 	const uint32_t an = (uint32_t)(n_bits % WAH_GROUP);

@@ -276,7 +276,7 @@ def test_sf1_shape_config1(cubit):
     t.close()
 
 
-@pytest.mark.parametrize("sel", ["1e-4", "0.5"])
+@pytest.mark.parametrize("sel", ["1e-4", "1e-3", "1e-2", "0.1", "0.25", "0.5"])
 def test_full_size_properties_1b_rows(cubit, sel):
     """BASELINE config 2 at full size (10^9 rows): size-independent properties.
     payload = row id, so SUM(payload) == SUM(row ids); the OR of disjoint value bitvectors

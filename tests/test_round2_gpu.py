@@ -422,3 +422,21 @@ def test_result_limbs_accumulate_on_device(cubit):
         assert c == tot[slot][0]
         assert l0 + (l1 << 32) + (l2 << 64) + (l3 << 96) == tot[slot][1]
     t.close()
+
+
+@pytest.mark.skipif("__import__('torch').cuda.device_count() < 2", reason="needs 2 GPUs")
+def test_nccl_sharded_scan_and_rowid_gather():
+    """tools/multi_gpu_check.py as a test: one rank per GPU over NCCL, row-range shards of one synthetic table,
+    exact all-reduce of (COUNT, SUM), row-ID lists gathered to rank 0 with send/recv and checked there (ascending,
+    length == COUNT, Σ ids == SUM(payload))"""
+    import os
+    import subprocess
+    import sys
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    world = min(torch.cuda.device_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(root, "tools", "multi_gpu_check.py"),
+           "50000017"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "multi_gpu_check ok: world=%d" % world in r.stdout, r.stdout[-2000:]

@@ -44,6 +44,39 @@ def test_published_example_vector():
     assert n == 128 and np.array_equal(back, bits_to_words(bits))
 
 
+def golden_vectors():
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wah_vectors.json")
+    for v in json.load(open(path))["vectors"]:
+        bits = np.concatenate([np.full(n, b, dtype=bool) for b, n in v["runs"]])
+        yield (v["name"], bits, np.array([int(w, 16) for w in v["wah"]], dtype=np.uint32), int(v["active_val"], 16),
+               v["active_nbits"])
+
+
+def test_golden_vectors_from_the_independent_encoder():
+    """tests/golden/wah_vectors.json (40 vectors of tests/golden/make_wah_golden.py, a pure-Python encoder that shares
+    no code with the oracle): the oracle writes exactly those words and decodes them back to the same bits"""
+    seen = 0
+    for name, bits, wah, av, an in golden_vectors():
+        w = bits_to_words(bits)
+        got, gav, gan = oracle.wah_encode(w, len(bits))
+        assert [int(x) for x in got] == [int(x) for x in wah] and (gav, gan) == (av, an), name
+        back, n = oracle.wah_decode(wah, av, an, len(w))
+        assert n == len(bits) and np.array_equal(back, w), name
+        seen += 1
+    assert seen == 40
+
+
+def test_reader_accepts_fills_of_one_group():
+    """a fill word spanning ONE group is never written (FastBit appends a literal) but is legal input"""
+    bits = np.array([0] * 31 + [1] * 31 + [1, 0, 1], dtype=bool)
+    back, n = oracle.wah_decode(np.array([0x80000001, 0xC0000001], dtype=np.uint32), 0b101, 3, 2)
+    assert n == 65 and np.array_equal(back, bits_to_words(bits))
+    wah, _, _ = oracle.wah_encode(bits_to_words(bits), 65)
+    assert [int(x) for x in wah] == [0x00000000, 0x7FFFFFFF]
+
+
 @pytest.mark.parametrize("kind", ["sparse", "dense", "runs", "ones", "zeros"])
 def test_oracle_round_trip(kind):
     rng = np.random.default_rng(17)
@@ -55,7 +88,7 @@ def test_oracle_round_trip(kind):
         back, nb = oracle.wah_decode(wah, av, an, len(w))
         assert nb == n and np.array_equal(back, w), (kind, n)
         if kind in ("ones", "zeros") and n >= 31:
-            assert len(wah) == 1                      # one fill word
+            assert len(wah) == 1                      # one fill word (a literal when it is a single group)
     with pytest.raises(ValueError):
         oracle.wah_decode(np.array([0x80000000], dtype=np.uint32), 0, 0, 4)       # zero-length fill
     with pytest.raises(ValueError):
@@ -105,3 +138,18 @@ def test_gpu_expands_wah_bitvectors(cubit, seg_bits):
             with pytest.raises(cubit.CubitError):
                 t.upload_bitvector_wah(ix, 0, *bad)
         assert np.array_equal(t.download_bitvector(ix, 0), maps[0])   # untouched by the rejected uploads
+
+
+@pytest.mark.gpu
+def test_gpu_expands_the_golden_vectors(cubit):
+    """every vector of tests/golden/wah_vectors.json, uploaded in its WAH form, expands on the GPU to the bits the
+    independent encoder started from (shorter than the table → zero padded)"""
+    n = 31 * 70001 + 64
+    with cubit.CubitTable(n, seg_bits=32768) as t:
+        ix = t.create_index(1)
+        for name, bits, wah, av, an in golden_vectors():
+            t.upload_bitvector_wah(ix, 0, wah, av, an)
+            full = np.zeros(n, dtype=bool)
+            full[:len(bits)] = bits
+            assert np.array_equal(t.download_bitvector(ix, 0), bits_to_words(full)), name
+            assert t.bitvector_count(ix, 0) == int(bits.sum()), name

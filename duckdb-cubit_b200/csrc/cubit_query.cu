@@ -211,6 +211,9 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 		cap = std::min(cap, group_bound);
 	}
 	sa.k = k;
+	if (getenv("CUBIT_FORCE_DELTA_KERNEL")) { // timing experiment: the delta-aware kernel instance on clean bitvectors
+		has_delta = true;
+	}
 	if (const char *dbg = getenv("CUBIT_SCAN_DEBUG")) {
 		sa.debug = (unsigned)atoi(dbg); // kernel timing experiments: skips parts of the kernel, results invalid
 	}

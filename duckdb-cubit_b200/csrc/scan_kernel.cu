@@ -206,7 +206,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 						uint32_t dbytes = 0;
 						const DeltaEnt *dsrc = nullptr;
 						if (HAS_DELTA) {
-							const uint32_t d0 = sm.poff[s], d1 = sm.poff[64 + s];
+							uint32_t d0 = sm.poff[s], d1 = sm.poff[64 + s];
+							if (a.debug & 64u) { // timing experiment: pretend there are no pending deltas
+								d1 = d0;
+							}
 							sm.meta[stage].d0 = d0;
 							sm.meta[stage].dcnt = d1 - d0;
 							if (d1 > d0) { // stage the first kDeltaStage delta words next to the segment
@@ -366,7 +369,50 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 				// CMP: bit u of `skip` = stage u of this batch needs no fold from shared memory — an EMPTY container, or a
 				// FULL / ARRAY container that was accumulated straight into the registers below
 				uint32_t skip = 0;
-				if ((HAS_DELTA || CMP) && tile != kNoTile) {
+				if (HAS_DELTA && !CMP && tile != kNoTile) {
+					// Verbatim streams: the pending-delta entries of ALL stages of the batch are handled in one pass —
+					// lane l looks at entry (l mod LPS) of stage (l / LPS), LPS = 32 / UB lanes per stage — instead of
+					// one pass per stage: with a handful of entries per (stream, segment) the per-stage loop machinery,
+					// not the XORs, was what the consumers paid for (≈ 25 instructions per stage and warp, +17 % scan time
+					// at 1 % pending rows; profiles/r2_delta_scan.md).  Entries are unordered and may repeat a word
+					// (device-side ingestion never sorts), so every warp XORs the ones that fall into ITS span of the
+					// staged segment with 32-bit shared-memory atomics — no block-wide barrier — and the fold below
+					// picks the words up.
+					constexpr int LPS = 32 / UB;
+					const int u_l = lane / LPS;
+					const uint32_t j_l = (uint32_t)(lane % LPS);
+					uint32_t st_l = stage + (uint32_t)u_l;
+					st_l = st_l >= (uint32_t)kStages ? st_l - (uint32_t)kStages : st_l;
+					const uint32_t dcnt_l = u_l < (int)nb ? sm.meta[st_l].dcnt : 0u;
+					const uint32_t maxd = __reduce_max_sync(0xffffffffu, dcnt_l);
+					bool wrote = false;
+					for (uint32_t e0 = 0; e0 < maxd; e0 += (uint32_t)LPS) {
+						const uint32_t e = e0 + j_l;
+						if (e < dcnt_l) {
+							uint4 raw;
+							if (e < (uint32_t)kDeltaStage) {
+								raw = *reinterpret_cast<const uint4 *>(&sm.dbuf[st_l][e]);
+							} else {
+								raw = __ldg(reinterpret_cast<const uint4 *>(a.dent[s + (uint32_t)u_l] + sm.meta[st_l].d0 + e));
+							}
+							const uint32_t rel = raw.x - (uint32_t)(warp * kSpanWords);
+							if (rel < (uint32_t)kSpanWords) {
+								unsigned int *w32 = reinterpret_cast<unsigned int *>(&sm.stage[st_l][raw.x]);
+								if (raw.z) {
+									atomicXor(w32, raw.z);
+								}
+								if (raw.w) {
+									atomicXor(w32 + 1, raw.w);
+								}
+								wrote = true;
+							}
+						}
+					}
+					if (wrote) {
+						fence_proxy_async_smem(); // generic-proxy writes before the stage is refilled by the async proxy
+					}
+					__syncwarp();
+				} else if ((HAS_DELTA || CMP) && tile != kNoTile) {
 					// Pending-delta entries of one (stream, segment) are unordered and may repeat a word (device-side
 					// ingestion never sorts), so every warp XORs the entries that fall into ITS span of the staged segment
 					// with 32-bit shared-memory atomics (native ATOMS.XOR; the 64-bit form is a CAS loop) — no block-wide

@@ -1813,6 +1813,11 @@ static TableFunction CubitScanTableFunction() {
 
 // ---------------------------------------------------------------- registration
 void RegisterCubitGpuFunctions(DatabaseInstance &db) {
+	// structs cross the C-ABI by value: a glue compiled against another header version must not run
+	if (cubit_gpu_abi_version() != CUBIT_GPU_ABI_VERSION) {
+		throw InvalidInputException("cubit_gpu: libcubit_gpu.so has ABI %d, this extension was built for ABI %d",
+		                            cubit_gpu_abi_version(), CUBIT_GPU_ABI_VERSION);
+	}
 	TableFunction load("cubit_load", {LogicalType::VARCHAR, LogicalType::VARCHAR, LogicalType::BIGINT, LogicalType::BIGINT},
 	                   CubitLoadFunction, CubitLoadBind);
 	load.named_parameters["bin"] = LogicalType::VARCHAR;

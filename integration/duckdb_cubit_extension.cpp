@@ -304,6 +304,11 @@ static bool CubitUploadColumnSegments(ClientContext &, TableCatalogEntry &entry,
 	if (type.InternalType() != PhysicalType::INT64) {
 		return false;
 	}
+	uint32_t n_shards = 1;
+	cubit_gpu_shard_count(handle, &n_shards);
+	if (n_shards > 1) {
+		return false; // a compressed segment addresses one shard: a table cut over several GPUs takes the decoded rows
+	}
 	auto &storage = entry.GetStorage();
 	auto &block_manager = TableIOManager::Get(storage).GetBlockManagerForRowData();
 	if (block_manager.InMemory()) {
@@ -782,6 +787,55 @@ static shared_ptr<CubitGpuTable> CubitLookup(ClientContext &context, const strin
 	return index->gpu;
 }
 
+// devices named by CUBIT_GPU_DEVICES ("all", a count, or a comma-separated list; a device may repeat); empty = default
+static vector<int> CubitDeviceList() {
+	vector<int> out;
+	const char *env = getenv("CUBIT_GPU_DEVICES");
+	if (!env || !*env) {
+		return out;
+	}
+	int have = 0;
+	if (cubit_gpu_device_count(&have) != CUBIT_OK || have <= 0) {
+		return out;
+	}
+	string spec(env);
+	if (spec == "all") {
+		for (int d = 0; d < have; d++) {
+			out.push_back(d);
+		}
+		return out;
+	}
+	if (spec.find(',') == string::npos) {
+		int n = 0;
+		try {
+			n = std::stoi(spec);
+		} catch (...) {
+			n = 0;
+		}
+		for (int d = 0; d < n && d < have; d++) {
+			out.push_back(d);
+		}
+		return out;
+	}
+	size_t at = 0;
+	while (at <= spec.size()) {
+		const size_t comma = spec.find(',', at);
+		const string tok = spec.substr(at, comma == string::npos ? string::npos : comma - at);
+		try {
+			const int d = std::stoi(tok);
+			if (d >= 0 && d < have) {
+				out.push_back(d);
+			}
+		} catch (...) {
+		}
+		if (comma == string::npos) {
+			break;
+		}
+		at = comma + 1;
+	}
+	return out;
+}
+
 // ---------------------------------------------------------------- materialise the GPU copy
 // Pulls rowid and every GPU-eligible column through a second connection and places every row at ITS ROW ID: the GPU
 // row position is the table's row id (rowids are dense table positions, row_group.cpp:511-514, stable under
@@ -861,7 +915,18 @@ static void CubitMaterialise(ClientContext &context, TableCatalogEntry &entry, C
 	}
 	const bool no_deleted_rows = rows_seen == total;
 	gpu.row_count = total;
-	CubitCheck(cubit_gpu_create(0, gpu.row_count, 0, 65536, &gpu.handle));
+	// One GPU by default; CUBIT_GPU_DEVICES = "all" | a count | "0,1,3" cuts the table into contiguous row ranges of whole
+	// segments over those devices behind ONE handle (cubit_gpu_create_sharded — the reference's parallel unit is the
+	// row-group range of RowGroupCollection::NextParallelScan, row_group_collection.cpp:174-224).  Everything below
+	// and every query / DML callback addresses that handle unchanged; the storage route and index images are per
+	// shard and fall back to decoded rows / a rebuild at attach.
+	auto devices = CubitDeviceList();
+	if (devices.size() > 1) {
+		CubitCheck(cubit_gpu_create_sharded(devices.data(), NumericCast<uint32_t>(devices.size()), gpu.row_count, 0, 65536,
+		                                    &gpu.handle));
+	} else {
+		CubitCheck(cubit_gpu_create(devices.empty() ? 0 : devices[0], gpu.row_count, 0, 65536, &gpu.handle));
+	}
 	for (idx_t k = 0; k < n_cols; k++) {
 		// compressed segments straight from the buffer manager when the column qualifies (physical position = row
 		// id, so the route needs a table without deleted rows), decoded rows otherwise (a column with NULLs goes

@@ -2,7 +2,9 @@
 // reference DuckDB: the same SQL through cubit_scan / cubit_agg and through the vanilla scan must agree.
 // Runs only where the reference build exists (the build container); see tests/test_duckdb_integration.py.
 #include "duckdb.hpp"
+#include "cubit_gpu.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -398,6 +400,14 @@ int main(int argc, char **argv) {
 		REQUIRE(dn->GetValue(0, 0).GetValue<int64_t>() > 10000);
 		printf("dml through the index ok\n");
 	}
+	// CUBIT_GPU_DEVICES with more than one device: every table is cut over several shards behind one handle.  All
+	// answers must stay the same; only the per-shard features (compressed-segment upload, index images) step aside.
+	bool sharded = false;
+	if (const char *devs = getenv("CUBIT_GPU_DEVICES")) {
+		int have = 0;
+		cubit_gpu_device_count(&have);
+		sharded = string(devs).find(',') != string::npos || (string(devs) == "all" ? have : std::min(atoi(devs), have)) > 1;
+	}
 	if (argc > 2 && string(argv[1]) == "--db") {
 		// Storage route: a FILE-backed, checkpointed table's columns reach the C-ABI as the compressed segments
 		// the reference wrote (BitPacking), lifted from the buffer manager — not as decoded rows.
@@ -410,7 +420,7 @@ int main(int argc, char **argv) {
 		const idx_t seg_before = CubitSegmentRouteCount();
 		auto fl = Run(fcon, "CALL cubit_load('ft', 'q', 1, 50)");
 		REQUIRE(fl->GetValue(0, 0).GetValue<int64_t>() == 400000);
-		REQUIRE(CubitSegmentRouteCount() == seg_before + 4); // all four columns went through the segment route
+		REQUIRE(CubitSegmentRouteCount() == seg_before + (sharded ? 0 : 4)); // all four columns went through the segment route
 		Run(fcon, "CREATE TABLE ft_plain AS SELECT * FROM ft");
 		for (auto w : wheres) {
 			const string where = w;
@@ -455,7 +465,7 @@ int main(int argc, char **argv) {
 			REQUIRE(comp->GetValue(0, 0).GetValue<int64_t>() >= 3);
 			const idx_t seg_rle = CubitSegmentRouteCount();
 			Run(fcon, "CALL cubit_load('fr', 'q', 1, 50)");
-			REQUIRE(CubitSegmentRouteCount() == seg_rle + 3);
+			REQUIRE(CubitSegmentRouteCount() == seg_rle + (sharded ? 0 : 3));
 			Run(fcon, "CREATE TABLE fr_plain AS SELECT * FROM fr");
 			for (auto w : wheres) {
 				const string where = w;
@@ -488,7 +498,7 @@ int main(int argc, char **argv) {
 		const idx_t img0 = CubitImageLoads(), rw0 = CubitRewriteCount();
 		auto got = Run(rcon, "SELECT count(*), sum(price), sum(price * disc) FROM pt WHERE q BETWEEN 20 AND 29 AND disc < 5");
 		REQUIRE(CubitRewriteCount() == rw0 + 1);
-		REQUIRE(CubitImageLoads() == img0 + 2); // both indexes came from their checkpointed images
+		REQUIRE(CubitImageLoads() == img0 + (sharded ? 0 : 2)); // both indexes came from their checkpointed images (sharded: rebuilt from the table)
 		auto van = RunVanilla(rcon, "SELECT count(*), sum(price), sum(price * disc) FROM pt WHERE q BETWEEN 20 AND 29 AND disc < 5");
 		for (idx_t c = 0; c < 3; c++) {
 			REQUIRE(got->GetValue(c, 0).ToString() == van->GetValue(c, 0).ToString());
@@ -508,6 +518,6 @@ int main(int argc, char **argv) {
 	}
 	auto err = con.Query("SELECT * FROM cubit_scan('nope', 1, 2)");
 	REQUIRE(err->HasError());
-	printf("duckdb_sql_test ok\n");
+	printf("duckdb_sql_test ok%s\n", sharded ? " (tables sharded behind one handle)" : "");
 	return 0;
 }

@@ -175,6 +175,12 @@ int cubit_gpu_append_rows(cubit_gpu_table *t, uint64_t n_new, const cubit_append
 	return CUBIT_OK;
 }
 int cubit_gpu_shard_count(const cubit_gpu_table *t, uint32_t *n) { (void)t; *n = 1; return CUBIT_OK; }
+int cubit_gpu_device_count(int *count) { *count = 1; return CUBIT_OK; }
+int cubit_gpu_create_sharded(const int *devices, uint32_t n_devices, uint64_t n_rows, int64_t row_base, uint32_t seg_bits,
+                             cubit_gpu_table **out) {
+	(void)devices; (void)n_devices; /* the mock keeps one shard whatever the device list says */
+	return cubit_gpu_create(0, n_rows, row_base, seg_bits, out);
+}
 /* index image: {n_rows, card, has_delta} + bits (+ delta bits) — the mock's own format */
 int cubit_gpu_index_serialize(cubit_gpu_table *t, int32_t index_id, void **image, uint64_t *bytes) {
 	if (index_id < 0 || index_id >= t->n_indexes) { snprintf(g_err, sizeof g_err, "mock: bad index"); return CUBIT_EINVAL; }

@@ -17,8 +17,16 @@ pytestmark = [pytest.mark.gpu,
                                  reason="baseline/_ref bundle not built (tools/build_ref_bundle.py, build container)")]
 
 
-def test_sql_through_reference_duckdb_on_the_gpu(tmp_path):
-    r = subprocess.run([os.path.join(REF, "duckdb_sql_gpu_test"), "--db", str(tmp_path / "route.db")],
+@pytest.mark.parametrize("devices", [None, "0,0,0", "all"])
+def test_sql_through_reference_duckdb_on_the_gpu(tmp_path, devices):
+    """devices = None: one GPU, one shard.  "0,0,0": the glue cuts every table into three row-range shards behind one
+    handle (cubit_gpu_create_sharded; here all on device 0, which exercises the whole fan-out on a one-GPU box).
+    "all": one shard per visible GPU (the same as None on a one-GPU box)."""
+    env = dict(os.environ)
+    env.pop("CUBIT_GPU_DEVICES", None)
+    if devices:
+        env["CUBIT_GPU_DEVICES"] = devices
+    r = subprocess.run([os.path.join(REF, "duckdb_sql_gpu_test"), "--db", str(tmp_path / "route.db")], env=env,
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     for marker in ("aggregate push-down ok", "multi-index conjunctions ok", "binned indexes ok", "null semantics ok",

@@ -1,4 +1,3 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_round2_gpu.py -m gpu -x -q -k "delta or random_tables or merge or dml or compressed" > gpurun_out/r2_t7.log 2>&1
-tail -4 gpurun_out/r2_t7.log
-python tools/delta_one.py > gpurun_out/r2_delta_b.log 2>&1; tail -1 gpurun_out/r2_delta_b.log
+ncu --set full --clock-control none --import-source on -k "regex:cubit_(scan|probe)" --launch-skip 12 --launch-count 12 -o gpurun_out/r2_step python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-materialize --no-traffic --no-payload24 > gpurun_out/r2_ncu_step.log 2>&1
+tail -c 300 gpurun_out/r2_ncu_step.log | tail -2

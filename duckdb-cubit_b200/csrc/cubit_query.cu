@@ -369,7 +369,8 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	DenseProbeArgs dp;
 	memset(&dp, 0, sizeof(dp));
 	if (probe_mode == PROBE_BITS && !probe_on_bv) {
-		uint64_t inv = 48; // selected rows >= n_rows / inv
+		uint64_t inv = 28; // selected rows >= n_rows / inv: below ~3.5 % the per-block bookkeeping of the dense probe
+		                   // (≈ 300 instructions per touched block, a floor of 0.35 ms per 10^9 rows) loses to the gather
 		if (const char *e = getenv("CUBIT_DENSE_MIN_INV")) {
 			inv = strtoull(e, nullptr, 10); // 0 disables the dense probe (experiments)
 		}

@@ -168,6 +168,7 @@ struct DenseProbeArgs {
 	ResultHeader *hdr;                   // sums are ADDED
 	uint32_t stage_bytes[kMaxFusedCols]; // bytes of one shared-memory stage of every column (0: raw) — dense_probe_plan
 	uint32_t warp_bytes;                 // shared memory per warp
+	uint32_t n_stages;                   // ring stages per column (2..4)
 };
 
 struct ProbeArgs {

@@ -32,7 +32,8 @@ constexpr int kDenseThreads = kDenseWarps * 32;
 // staging row of 10-bit row numbers: one block (+ pad slot) and a whole write-out iteration of slack, so that the
 // write-out reads its 128 slots unconditionally
 constexpr int kDenseRowsBytes = (kPackBlock + 128 + 8) * 2;
-constexpr int kDenseWarpFixed = kDenseRowsBytes + 16; // + the warp's two mbarriers
+constexpr int kDenseMaxStages = 4;
+constexpr int kDenseWarpFixed = kDenseRowsBytes + 8 * kDenseMaxStages; // + the warp's mbarriers (one per stage)
 
 // how the aggregate is accumulated (kernel template parameter, so the write-out loop carries no dispatch):
 //   0  no aggregate
@@ -181,27 +182,29 @@ __device__ __forceinline__ void dense_write_out(const DenseProbeArgs &a, const u
 }
 
 // SB: pack blocks per span (a span = one consumer warp's share of a segment in the scan kernel: 2·WPT blocks)
-// RAW: some probed column is a raw array (gathered); AGGM: DENSE_AGG_*
-template <int SB, int NL, bool POS, bool RAW, int AGGM>
+// RAW: some probed column is a raw array (gathered); AGGM: DENSE_AGG_*; NSTG: ring stages per column (2..4)
+template <int SB, int NL, bool POS, bool RAW, int AGGM, int NSTG>
 __global__ void __launch_bounds__(kDenseThreads, 3) cubit_probe_dense_kernel(const __grid_constant__ DenseProbeArgs a) {
 	extern __shared__ __align__(128) unsigned char dense_smem[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	unsigned char *wbase = dense_smem + (size_t)warp * a.warp_bytes;
 	uint16_t *cbuf = reinterpret_cast<uint16_t *>(wbase);
 	uint64_t *full = reinterpret_cast<uint64_t *>(wbase + kDenseRowsBytes);
-	uint32_t pk0[NL], pk_stride[NL]; // shared-window address of stage 0 of every column, bytes between its two stages
+	constexpr uint32_t NST = (uint32_t)NSTG; // stages per column (dense_probe_plan: what shared memory allows)
+	uint32_t pk0[NL], pk_stride[NL]; // shared-window address of stage 0 of every column, bytes between its stages
 	{
 		uint32_t off = kDenseWarpFixed;
 #pragma unroll
 		for (int c = 0; c < NL; c++) {
 			pk0[c] = smem_u32(wbase + off);
 			pk_stride[c] = a.stage_bytes[c];
-			off += 2 * a.stage_bytes[c];
+			off += NST * a.stage_bytes[c];
 		}
 	}
 	if (lane == 0) {
-		mbar_init(&full[0], 1);
-		mbar_init(&full[1], 1);
+		for (uint32_t i = 0; i < (uint32_t)kDenseMaxStages; i++) {
+			mbar_init(&full[i], 1);
+		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncwarp();
@@ -234,8 +237,10 @@ __global__ void __launch_bounds__(kDenseThreads, 3) cubit_probe_dense_kernel(con
 		}
 		return m;
 	};
-	uint32_t n_iss = 0, n_con = 0; // bulk copies issued / consumed by this warp (warp-uniform)
-	// one bulk copy per packed column of block j of the span whose headers are `h`, into stage (n_iss & 1)
+	// ring bookkeeping (warp-uniform): stage the next copy goes to, stage / parity of the next block to decode, copies
+	// issued but not yet decoded
+	uint32_t st_i = 0, st_c = 0, ph_c = 0, inflight = 0;
+	// one bulk copy per packed column of block j of the span whose headers are `h`, into stage st_i
 	auto issue = [&](const uint4 (&h)[NL], uint32_t j) {
 		uint32_t off[NL], bytes[NL], total = 0;
 #pragma unroll
@@ -245,28 +250,36 @@ __global__ void __launch_bounds__(kDenseThreads, 3) cubit_probe_dense_kernel(con
 			total += bytes[c];
 		}
 		if (lane == 0) {
-			const uint32_t st = n_iss & 1u;
-			mbar_arrive_expect_tx(&full[st], total);
+			mbar_arrive_expect_tx(&full[st_i], total);
 #pragma unroll
 			for (int c = 0; c < NL; c++) {
 				if (bytes[c]) {
 					asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-					                 pk0[c] + st * pk_stride[c]),
-					             "l"(a.lcol[c].words + off[c]), "r"(bytes[c]), "r"(smem_u32(&full[st]))
+					                 pk0[c] + st_i * pk_stride[c]),
+					             "l"(a.lcol[c].words + off[c]), "r"(bytes[c]), "r"(smem_u32(&full[st_i]))
 					             : "memory");
 				}
 			}
 		}
-		n_iss++;
+		st_i = st_i + 1 == NST ? 0 : st_i + 1;
+		inflight++;
 	};
 
 	// Only the CURRENT span's bits stay in registers.  The next span's bits are loaded once at the top of a span to
-	// find its first non-empty block (whose copy is issued while this span's last block is decoded) and loaded again
+	// find its non-empty blocks (whose copies are issued while this span's last blocks are decoded) and loaded again
 	// — an L1 / L2 hit by then — when the span becomes current: 8..16 registers per thread for one short stall per span.
+	// Copies run up to NST - 1 blocks ahead of the decode, across the span boundary.  Wide columns (3–4 KiB per block)
+	// gain 10 % from a ring deeper than two stages; narrow ones do not — their blocks wait for the decode, not for the
+	// copy — and keep two (dense_probe_plan; profiles/r2_probe_dense.md).
 	uint32_t cur[SB];
 	uint4 hc[NL], hn[NL];
 	Agg agg;
-	bool pend = false; // the copy of this span's first non-empty block was issued while the previous span was decoded
+	uint32_t mi_next; // blocks of the span about to become current whose copies have not been issued yet
+	{
+		uint32_t nb[SB];
+		load_bits(gw, nb);
+		mi_next = nonempty(nb);
+	}
 	load_hdrs(gw, hn);
 	for (uint32_t sp = gw; sp < a.n_span; sp += nw) {
 		load_bits(sp, cur);
@@ -278,27 +291,31 @@ __global__ void __launch_bounds__(kDenseThreads, 3) cubit_probe_dense_kernel(con
 		for (int c = 0; c < NL; c++) {
 			hc[c] = hn[c];
 		}
-		uint32_t mn; // non-empty blocks of the next span
+		uint32_t mi = mi_next, mni; // not yet issued: of this span / of the next one
 		{
 			uint32_t nb[SB];
 			load_bits(sp + nw, nb);
 			load_hdrs(sp + nw, hn);
-			mn = nonempty(nb);
+			mni = nonempty(nb);
 		}
 		uint32_t m = nonempty(cur);
-		if (m && !pend) {
-			issue(hc, (uint32_t)__ffs(m) - 1u);
-		}
-		pend = false;
 		while (m) {
 			const uint32_t j = (uint32_t)__ffs(m) - 1u;
 			m &= m - 1u;
-			// keep one copy ahead: the next non-empty block of this span, else the first one of the next span
-			if (m) {
-				issue(hc, (uint32_t)__ffs(m) - 1u);
-			} else if (mn) {
-				issue(hn, (uint32_t)__ffs(mn) - 1u);
-				pend = true;
+			// top the ring up: the blocks of this span in order, then those of the next span (block j itself is always
+			// the oldest block not yet decoded, so it is issued first if it was not yet)
+			while (inflight < NST) {
+				if (mi) {
+					const uint32_t ji = (uint32_t)__ffs(mi) - 1u;
+					mi &= mi - 1u;
+					issue(hc, ji);
+				} else if (mni) {
+					const uint32_t ji = (uint32_t)__ffs(mni) - 1u;
+					mni &= mni - 1u;
+					issue(hn, ji);
+				} else {
+					break;
+				}
 			}
 			uint32_t w = cur[0];
 #pragma unroll
@@ -318,22 +335,26 @@ __global__ void __launch_bounds__(kDenseThreads, 3) cubit_probe_dense_kernel(con
 			const uint32_t pad = POS ? (uint32_t)pos & 1u : 0u;
 			stage_word(cbuf, pad + incl - c, w & 0xffffu, w >> 16, (uint32_t)lane * 32u, 0u, 16u);
 			BlockHdrs<NL> bh;
-			const uint32_t st = n_con & 1u;
 #pragma unroll
 			for (int cc = 0; cc < NL; cc++) {
 				const uint32_t blo = __shfl_sync(0xffffffffu, hc[cc].x, j), bhi = __shfl_sync(0xffffffffu, hc[cc].y, j);
 				bh.base[cc] = (long long)(((unsigned long long)bhi << 32) | blo);
 				bh.width[cc] = __shfl_sync(0xffffffffu, hc[cc].w, j);
 				bh.mask[cc] = bh.width[cc] >= 32u ? 0xffffffffu : (1u << bh.width[cc]) - 1u;
-				bh.pk[cc] = pk0[cc] + st * pk_stride[cc];
+				bh.pk[cc] = pk0[cc] + st_c * pk_stride[cc];
 			}
 			__syncwarp();
-			mbar_wait(&full[st], (n_con >> 1) & 1u);
+			mbar_wait(&full[st_c], ph_c);
 			dense_write_out<NL, POS, RAW, AGGM>(a, cbuf, pad, total, pos, ((long long)sp * SB + j) * kPackBlock, bh, lane, agg);
-			__syncwarp(); // every lane is done with the staging row and with stage `st` before either is refilled
+			__syncwarp(); // every lane is done with the staging row and with stage st_c before either is refilled
 			pos += total;
-			n_con++;
+			inflight--;
+			if (++st_c == NST) {
+				st_c = 0;
+				ph_c ^= 1u;
+			}
 		}
+		mi_next = mni;
 	}
 	if (AGGM != DENSE_AGG_NONE) {
 		agg_flush_warp(agg, a.hdr, lane);
@@ -341,9 +362,9 @@ __global__ void __launch_bounds__(kDenseThreads, 3) cubit_probe_dense_kernel(con
 }
 
 // ------------------------------------------------------------------------------------------ launch
-template <int SB, int NL, bool POS, bool RAW, int AGGM>
-static cudaError_t launch_dense_t(const DenseProbeArgs &args, int sm_count, cudaStream_t stream) {
-	auto kern = cubit_probe_dense_kernel<SB, NL, POS, RAW, AGGM>;
+template <int SB, int NL, bool POS, bool RAW, int AGGM, int NSTG>
+static cudaError_t launch_dense_n(const DenseProbeArgs &args, int sm_count, cudaStream_t stream) {
+	auto kern = cubit_probe_dense_kernel<SB, NL, POS, RAW, AGGM, NSTG>;
 	const size_t smem = (size_t)args.warp_bytes * kDenseWarps;
 	int dev = 0;
 	cudaGetDevice(&dev);
@@ -370,6 +391,20 @@ static cudaError_t launch_dense_t(const DenseProbeArgs &args, int sm_count, cuda
 	grid = grid < 1 ? 1 : grid;
 	kern<<<(unsigned)grid, kDenseThreads, smem, stream>>>(args);
 	return cudaGetLastError();
+}
+
+template <int SB, int NL, bool POS, bool RAW, int AGGM>
+static cudaError_t launch_dense_t(const DenseProbeArgs &args, int sm_count, cudaStream_t stream) {
+	switch (args.n_stages) {
+	case 2:
+		return launch_dense_n<SB, NL, POS, RAW, AGGM, 2>(args, sm_count, stream);
+	case 3:
+		return launch_dense_n<SB, NL, POS, RAW, AGGM, 3>(args, sm_count, stream);
+	case 4:
+		return launch_dense_n<SB, NL, POS, RAW, AGGM, 4>(args, sm_count, stream);
+	default:
+		return cudaErrorInvalidValue;
+	}
 }
 
 template <int SB, int NL, bool POS, bool RAW>
@@ -409,7 +444,7 @@ static cudaError_t launch_dense_sb(const DenseProbeArgs &args, bool positions, i
 }
 
 bool dense_probe_plan(DenseProbeArgs &args, const uint32_t *max_width) {
-	uint32_t bytes = kDenseWarpFixed;
+	uint32_t per_stage = 0;
 	bool any_packed = false;
 	for (int c = 0; c < args.n_load; c++) {
 		args.stage_bytes[c] = 0;
@@ -422,9 +457,31 @@ bool dense_probe_plan(DenseProbeArgs &args, const uint32_t *max_width) {
 		any_packed = true;
 		// one block's payload + 16 spare bytes (the decoder reads one 32-bit word past a value)
 		args.stage_bytes[c] = max_width[c] * (uint32_t)(kPackBlock / 8) + 16u;
-		bytes += 2u * args.stage_bytes[c];
+		per_stage += args.stage_bytes[c];
 	}
-	args.warp_bytes = (bytes + 127u) & ~127u;
+	// stages per column: as deep a ring as shared memory allows with 3 CTAs per SM, else with 2 (227 KiB per SM, 1 KiB
+	// reserved per CTA); the copies run stages - 1 blocks ahead of the decode
+	auto warp_bytes = [&](uint32_t nst) { return ((uint32_t)kDenseWarpFixed + nst * per_stage + 127u) & ~127u; };
+	auto fits = [&](uint32_t ctas, uint32_t nst) {
+		return (uint64_t)warp_bytes(nst) * kDenseWarps <= (227u * 1024u - ctas * 1024u) / ctas;
+	};
+	// (narrow columns gain nothing from a deeper ring — their blocks are ≤ 2 KiB and the decode, not the copy, is what
+	// a block waits for: 0.49 / 0.70 / 0.97 ms with 2 stages against 0.51 / 0.73 / 0.99 ms with 4 on the 10-bit payload,
+	// while the 24-bit payload goes from 0.68 / 0.92 / 1.30 to 0.61 / 0.84 / 1.16 ms; profiles/r2_probe_dense.md)
+	uint32_t nst = 2;
+	if (per_stage < 2048u) {
+		nst = 2;
+	} else if (fits(3, 4)) {
+		nst = 4;
+	} else if (fits(3, 3)) {
+		nst = 3;
+	} else if (fits(2, 4)) {
+		nst = 4;
+	} else if (fits(2, 3)) {
+		nst = 3;
+	}
+	args.n_stages = nst;
+	args.warp_bytes = warp_bytes(nst);
 	return any_packed && args.n_load >= 1 && args.n_load <= kMaxFusedCols;
 }
 

@@ -99,7 +99,7 @@ def test_dense_probe_overflow_and_sparse_fallback(cubit):
     t.pack_column(5)
     with pytest.raises(cubit.CubitError, match="Overflow"):
         t.query([[(ix, v) for v in range(11)]], flags=0, agg=cubit.AGG_SUM_PROD, agg_a=5, agg_b=5)
-    # a selection of < 1/48 of the rows: not the dense probe
+    # a selection of < 1/28 of the rows: not the dense probe
     rare = np.zeros(400_000, dtype=np.int32)
     rare[::97] = 1
     t.upload_column(6, rare)

@@ -506,7 +506,7 @@ class CubitTable:
     def pack_column(self, col_id, keep_raw=False):
         """store an int64 column FOR-bit-packed in HBM (lossless) → resident bytes"""
         b = C.c_uint64(0)
-        _check(self._L.cubit_gpu_pack_column(self._h, col_id, 1 if keep_raw else 0, C.byref(b)))
+        _check(self._L.cubit_gpu_pack_column(self._h, col_id, int(keep_raw), C.byref(b)))  # 0 / 1 / 2 (see the header)
         return b.value
 
     def drop_column(self, col_id):

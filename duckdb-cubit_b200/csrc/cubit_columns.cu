@@ -584,6 +584,12 @@ extern "C" int cubit_gpu_pack_column(cubit_gpu_table *t, int32_t col_id, int kee
 		hdr[b].word_off = (uint32_t)off;
 		off += 16ull * width[b];
 	}
+	if (keep_raw == 2 && max_width > 32) { // "both forms if the dense probe can use the packed one": it cannot
+		if (packed_bytes) {
+			*packed_bytes = 0;
+		}
+		return CUBIT_OK;
+	}
 	const uint64_t bytes = (off + 2) * 8; // + spare words: the decoder may read one word past a value
 	CU_TRY(cudaMalloc(&c.d_hdr, (n_blk + 16) * sizeof(PackHdr))); // + 16: load_hdrs reads a whole span's headers
 	CU_TRY(cudaMemsetAsync(c.d_hdr + n_blk, 0, 16 * sizeof(PackHdr), t->stream));
@@ -659,8 +665,9 @@ extern "C" int cubit_gpu_append_rows(cubit_gpu_table *t, uint64_t n_new, const c
 		if (it->second.elem != cols[i].elem_bytes) {
 			return fail(CUBIT_EINVAL, "append: column %d is %u bytes wide", cols[i].col_id, it->second.elem);
 		}
-		if (it->second.packed()) {
-			return fail(CUBIT_ESTATE, "append: column %d is bit-packed; appends need the raw form", cols[i].col_id);
+		if (it->second.packed() && !it->second.d) {
+			return fail(CUBIT_ESTATE, "append: column %d is resident only bit-packed; appends need the raw form",
+			            cols[i].col_id);
 		}
 	}
 	for (Index *ix : t->indexes) {
@@ -761,6 +768,17 @@ extern "C" int cubit_gpu_append_rows(cubit_gpu_table *t, uint64_t n_new, const c
 	}
 	for (uint32_t i = 0; i < n_cols; i++) {
 		Column &c = t->columns[cols[i].col_id];
+		if (c.packed()) {
+			// both forms were resident: the packed one does not cover the new rows — drop it (cudaFree waits for every
+			// kernel that may still read it); cubit_gpu_pack_column brings it back whenever the caller wants
+			cudaFree(c.d_words);
+			cudaFree(c.d_hdr);
+			c.d_words = nullptr;
+			c.d_hdr = nullptr;
+			c.packed_bytes = 0;
+			c.pack_max_width = 0;
+			c.pack_avg_width = 0;
+		}
 		if (ncol[i].p) {
 			cudaFree(c.d);
 			c.d = ncol[i].p;

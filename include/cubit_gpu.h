@@ -263,14 +263,20 @@ int cubit_gpu_synth_column(cubit_gpu_table *t, int32_t col_id, int32_t kind, uin
                            uint32_t card, uint32_t hot_lo, uint32_t hot_n);
 int cubit_gpu_drop_column(cubit_gpu_table *t, int32_t col_id);
 /* Store an 8-byte column FOR-bit-packed in HBM (lossless): blocks of 1024 rows, per block min + bit width of
- * (max - min).  The probe kernels decode in registers, so a dense probe reads width/8 bytes per row instead of
- * 8.  keep_raw = 0 frees the raw array (index builds need it: build first).  *packed_bytes = resident size. */
+ * (max - min) — the resident analog of the reference's BitPacking column storage.  Selections of >= 1/28 of the
+ * rows over columns packed to <= 32 bits are probed by streaming the pack blocks through shared memory (the dense
+ * probe: width/8 bytes per row instead of 128 bytes of DRAM per gathered value); sparser ones gather from whichever
+ * form is cheaper.  keep_raw = 1 keeps both forms (the planner picks per query); keep_raw = 2 does the same but
+ * leaves the column raw (*packed_bytes = 0) when a block needs more than 32 bits, i.e. when the dense probe could
+ * not use the packed form; keep_raw = 0 frees the raw array (index builds and appends need it: build first).
+ * *packed_bytes = resident size of the packed form. */
 int cubit_gpu_pack_column(cubit_gpu_table *t, int32_t col_id, int keep_raw, uint64_t *packed_bytes);
 
 /* Append n_new rows at the end of the shard (INSERT: the new rows take the next row ids — rowids are dense
  * table positions, src/storage/table/row_group.cpp:511-514; index side BoundIndex::Append,
  * src/include/duckdb/execution/index/bound_index.hpp:71-75).  Every resident column must be supplied (raw
- * form; bit-packed columns are rejected with CUBIT_ESTATE).  Indexes built with cubit_gpu_index_build are
+ * form: a column that is resident ONLY bit-packed is rejected with CUBIT_ESTATE; one that keeps both forms loses
+ * its packed form, which no longer covers the table — cubit_gpu_pack_column rebuilds it).  Indexes built with cubit_gpu_index_build are
  * extended from their source column on the GPU (only the new rows are scanned); bitvectors that were uploaded
  * get zero bits for the new rows.  Pending deltas stay pending.  cubit_gpu_words_per_bitvector changes. */
 typedef struct cubit_append_column {

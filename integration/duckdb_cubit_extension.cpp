@@ -952,6 +952,17 @@ static void CubitMaterialise(ClientContext &context, TableCatalogEntry &entry, C
 		}
 		gpu.indexes.push_back(CubitBuildIndex(gpu, gcol, spec, gpu.column_types[gcol], i < index.images.size() ? &index.images[i] : nullptr));
 	}
+	// NULL-free columns that pack to <= 32 bits per value also get a FOR-bit-packed form (the resident analog of the
+	// BitPacking segments the table is stored in): dense selections are then probed by streaming width/8 bytes per row.
+	// The raw form stays (index builds, appends — an append drops the packed form of the columns it extends).
+	if (!getenv("CUBIT_NO_PACK")) {
+		for (idx_t k = 0; k < n_cols; k++) {
+			if (valid[k].empty()) {
+				uint64_t packed_bytes = 0;
+				CubitCheck(cubit_gpu_pack_column(gpu.handle, NumericCast<int32_t>(k), 2, &packed_bytes));
+			}
+		}
+	}
 	gpu.loaded = true;
 }
 

@@ -176,6 +176,11 @@ int cubit_gpu_append_rows(cubit_gpu_table *t, uint64_t n_new, const cubit_append
 }
 int cubit_gpu_shard_count(const cubit_gpu_table *t, uint32_t *n) { (void)t; *n = 1; return CUBIT_OK; }
 int cubit_gpu_device_count(int *count) { *count = 1; return CUBIT_OK; }
+int cubit_gpu_pack_column(cubit_gpu_table *t, int32_t col_id, int keep_raw, uint64_t *packed_bytes) {
+	(void)t; (void)col_id; (void)keep_raw; /* storage form only: the mock answers from its decoded arrays */
+	if (packed_bytes) *packed_bytes = 0;
+	return CUBIT_OK;
+}
 int cubit_gpu_create_sharded(const int *devices, uint32_t n_devices, uint64_t n_rows, int64_t row_base, uint32_t seg_bits,
                              cubit_gpu_table **out) {
 	(void)devices; (void)n_devices; /* the mock keeps one shard whatever the device list says */

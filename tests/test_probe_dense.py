@@ -110,3 +110,41 @@ def test_dense_probe_overflow_and_sparse_fallback(cubit):
         assert r.info.probe_path != cubit.PROBE_DENSE
         assert np.array_equal(ids, np.arange(0, 400_000, 97) + base) and np.array_equal(ga, a[::97])
     t.close()
+
+
+def test_append_drops_the_packed_form_and_queries_stay_exact(cubit):
+    """a column resident in both forms loses its packed form when rows are appended (it no longer covers the table);
+    keep_raw = 2 packs only what the dense probe can use; a packed-only column refuses the append"""
+    n, extra = 300_000, 70_001
+    rng = np.random.default_rng(3)
+    key = rng.integers(0, 4, n + extra).astype(np.int32)
+    a = rng.integers(-5000, 5000, n + extra).astype(np.int64)          # 14 bits
+    wide = rng.integers(-2**40, 2**40, n + extra).astype(np.int64)     # 41 bits: keep_raw = 2 leaves it raw
+    t = cubit.CubitTable(n, seg_bits=32768)
+    t.upload_column(0, a[:n])
+    t.upload_column(1, wide[:n])
+    t.upload_column(9, key[:n])
+    ix = t.create_index(4)
+    t.build_index(ix, 9, 0)
+    assert t.pack_column(0, keep_raw=2) > 0
+    assert t.pack_column(1, keep_raw=2) == 0               # left raw: a block needs more than 32 bits
+    groups = [[(ix, 1), (ix, 2)]]
+    with t.query(groups, flags=cubit.Q_ROWIDS | cubit.Q_VALUES, cols=[0, 1], agg=cubit.AGG_SUM, agg_a=0) as r:
+        ids, (ga, gw) = r.fetch()
+        sel = np.flatnonzero((key[:n] == 1) | (key[:n] == 2))
+        assert r.info.probe_path == cubit.PROBE_DENSE            # column 0 packed, column 1 rides along raw
+        assert np.array_equal(ids, sel) and np.array_equal(ga, a[sel]) and np.array_equal(gw, wide[sel])
+    t.append_rows({0: a[n:], 1: wide[n:], 9: key[n:]})
+    with t.query(groups, flags=cubit.Q_ROWIDS | cubit.Q_VALUES, cols=[0, 1], agg=cubit.AGG_SUM, agg_a=0) as r:
+        ids, (ga, gw) = r.fetch()
+        sel = np.flatnonzero((key == 1) | (key == 2))
+        assert r.info.probe_path != cubit.PROBE_DENSE            # the packed form is gone
+        assert np.array_equal(ids, sel) and np.array_equal(ga, a[sel]) and np.array_equal(gw, wide[sel])
+        assert r.sum == int(a[sel].sum())
+    t.pack_column(0, keep_raw=True)                              # ... and comes back on request
+    with t.query(groups, flags=cubit.Q_VALUES, cols=[0]) as r:
+        assert r.info.probe_path == cubit.PROBE_DENSE and np.array_equal(r.fetch(rowids=False)[1][0], a[sel])
+    t.pack_column(1, keep_raw=False)                             # packed only: appends are refused
+    with pytest.raises(cubit.CubitError):
+        t.append_rows({0: a[:1], 1: wide[:1], 9: key[:1]})
+    t.close()

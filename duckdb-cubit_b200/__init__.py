@@ -25,6 +25,7 @@ MAX_STREAMS = 64
 MAX_PROBE_COLS = 8
 Q_ROWIDS, Q_BITVECTOR, Q_VALUES, Q_TIMING, Q_UNFUSED, Q_ASYNC, Q_FUSE_PROBE = 1, 2, 4, 8, 16, 32, 64
 PROBE_NONE, PROBE_FUSED, PROBE_BITS, PROBE_GATHER, PROBE_DENSE = 0, 1, 2, 3, 4
+SCAN_RING, SCAN_TWO_PASS, SCAN_NONE = 0, 1, 2
 AGG_NONE, AGG_SUM, AGG_SUM_PROD, AGG_SUM_F64 = 0, 1, 2, 3
 
 # every symbol include/cubit_gpu.h declares (tests check the library exports all of them)
@@ -67,7 +68,7 @@ class ResultInfo(C.Structure):
                 ("ms_probe", C.c_float), ("ms_total", C.c_float), ("fused", C.c_uint32),
                 ("d_rowids", C.c_void_p), ("d_bitvector", C.c_void_p), ("d_values", C.c_void_p * MAX_PROBE_COLS),
                 ("sum_f64", C.c_double), ("agg_rows", C.c_uint64), ("d_validity", C.c_void_p * MAX_PROBE_COLS),
-                ("probe_path", C.c_uint32), ("reserved", C.c_uint32)]
+                ("probe_path", C.c_uint32), ("scan_path", C.c_uint32)]
 
 
 class ColumnSegment(C.Structure):

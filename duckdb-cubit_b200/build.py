@@ -48,7 +48,7 @@ def build_gpu(verbose=False, ptxas_info=False):
     hdrs = [os.path.join(CSRC, "kernels.h"), os.path.join(CSRC, "scan_common.cuh"), os.path.join(CSRC, "col_ref.cuh"),
             os.path.join(CSRC, "table.h"), os.path.join(ROOT, "include", "cubit_gpu.h")]
     units = ["scan_kernel.cu", "aux_kernels.cu", "column_decode.cu", "wah_decode.cu", "delta_kernels.cu",
-             "container_kernels.cu", "probe_dense_kernel.cu", "cubit_gpu.cu", "cubit_columns.cu", "cubit_delta.cu", "cubit_persist.cu",
+             "container_kernels.cu", "probe_dense_kernel.cu", "small_scan_kernels.cu", "cubit_gpu.cu", "cubit_columns.cu", "cubit_delta.cu", "cubit_persist.cu",
              "cubit_query.cu", "cubit_sharded.cu"]
     objs = []
     jobs = []

@@ -392,6 +392,23 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	}
 	cap = (cap + 1) & ~1ull; // even: the probe kernel moves row IDs in pairs
 
+	// SHORT queries on large tables run merge + decode as two streaming passes (small_scan_kernels.cu): the ring
+	// kernel's per-tile count → publish → look-back → emit chain costs a CTA 1–2 µs per tile whatever the tile holds,
+	// which with one to four bitvectors per tile IS the run time, while re-reading the ONE merged bitvector is cheap.
+	// Units of 8192 rows; the probes then see 65536-row tiles (8 units) whatever the table's segment size.
+	uint64_t two_pass_min_rows = 16ull << 20;
+	if (const char *e = getenv("CUBIT_TWO_PASS_MIN_ROWS")) { // tests: 0 = every eligible query; huge = never
+		two_pass_min_rows = strtoull(e, nullptr, 10);
+	}
+	const uint32_t n_units = (uint32_t)(((uint64_t)t->n_seg * t->seg_words + 1023) / 1024) * 8u;
+	// measured crossover against the ring kernel at 10^9 rows (profiles/r2_small_k.md): with row positions k <= 2,
+	// count / bitvector / aggregate only k <= 3
+	const bool two_pass = !has_delta && !has_compressed && !unfused && probe_mode != PROBE_FUSED && !probe_on_bv &&
+	                      k <= (need_ids_buf ? 2u : 3u) &&
+	                      t->n_rows >= two_pass_min_rows && (uint64_t)n_units * 128 <= t->words_per_bv && sa.debug == 0;
+	const uint32_t probe_tile_words = two_pass ? 1024u : tile_words;
+	const uint32_t probe_n_tile = two_pass ? n_units / 8u : n_tile;
+
 	// ---- result object
 	cubit_gpu_result *r = new (std::nothrow) cubit_gpu_result();
 	if (!r) {
@@ -426,13 +443,19 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 
 	const int max_grid = std::max(scan_max_grid(t->seg_words, t->sm_count), probe_grid(t->sm_count));
 	const size_t hdr_bytes = 64;
-	const size_t ctrl_bytes = ((size_t)t->n_seg + 1) * 8;
+	const size_t ctrl_bytes = ((size_t)std::max<uint32_t>(t->n_seg, probe_n_tile) + 1) * 8;
 	const size_t ctrl_pad = (ctrl_bytes + 63) & ~(size_t)63;
 	const size_t part_bytes = (size_t)max_grid * sizeof(BlockPartial);
 	// layout: hdr | ctrl A | ctrl B (decode pass of the unfused path) | partials | probe done | segment prefixes
 	const size_t excl_bytes = probe_mode == PROBE_BITS ? ctrl_pad : 0;
-	const size_t span_bytes = dense_probe ? (size_t)t->n_seg * kConsumerWarps * 8 : 0; // per-span prefixes (dense probe)
-	const size_t block_bytes = hdr_bytes + 2 * ctrl_pad + part_bytes + 64 + excl_bytes + span_bytes;
+	const size_t span_bytes = dense_probe ? (size_t)std::max<uint32_t>(t->n_seg * kConsumerWarps, n_units) * 8 : 0; // per-span prefixes (dense probe)
+	SmallScanArgs ss;
+	memset(&ss, 0, sizeof(ss));
+	if (two_pass) {
+		small_scan_plan(ss, n_units, t->sm_count);
+	}
+	const size_t chunk_bytes = two_pass ? ((size_t)ss.n_chunks + 1) * 8 : 0;
+	const size_t block_bytes = hdr_bytes + 2 * ctrl_pad + part_bytes + 64 + excl_bytes + span_bytes + chunk_bytes;
 	Q_TRY(cudaMallocAsync((void **)&r->d_block, block_bytes, st));
 	r->d_hdr = reinterpret_cast<ResultHeader *>(r->d_block);
 	unsigned long long *ctrl_a = reinterpret_cast<unsigned long long *>(r->d_block + hdr_bytes);
@@ -443,6 +466,8 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	    reinterpret_cast<unsigned long long *>(r->d_block + hdr_bytes + 2 * ctrl_pad + part_bytes + 64);
 	unsigned long long *span_excl = reinterpret_cast<unsigned long long *>(
 	    r->d_block + hdr_bytes + 2 * ctrl_pad + part_bytes + 64 + excl_bytes);
+	unsigned long long *chunk_tot = reinterpret_cast<unsigned long long *>(
+	    r->d_block + hdr_bytes + 2 * ctrl_pad + part_bytes + 64 + excl_bytes + span_bytes);
 	{
 		std::lock_guard<std::mutex> ml(t->meta_mu);
 		if (!t->hdr_pool.empty()) {
@@ -470,7 +495,9 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	if (want_q) {
 		Q_TRY(cudaMallocAsync((void **)&r->d_q, t->words_per_bv * 8, st));
 	}
-	if ((unfused || probe_mode == PROBE_BITS) && !want_q && !probe_on_bv) {
+	// (two passes over ONE bitvector: Q is that bitvector itself, nothing is written)
+	if ((((unfused || probe_mode == PROBE_BITS) && !probe_on_bv) || (two_pass && need_ids_buf)) && !want_q &&
+	    !(two_pass && k == 1)) {
 		Q_TRY(cudaMallocAsync((void **)&r->d_q_tmp, t->words_per_bv * 8, st));
 	}
 	if (!r->ev_done) {
@@ -497,6 +524,35 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	if (probe_on_bv) {
 		sa.q_out = const_cast<uint64_t *>(sa.bv[0]);
 		r->info.fused = 1;
+	} else if (two_pass) {
+		for (uint32_t i = 0; i < k; i++) {
+			ss.bv[i] = sa.bv[i];
+		}
+		ss.group_end = sa.group_end;
+		ss.k = k;
+		ss.chunk_tot = chunk_tot;
+		ss.hdr = r->d_hdr;
+		uint64_t *qbuf = want_q ? r->d_q : r->d_q_tmp; // (nullptr when nobody reads a merged bitvector)
+		ss.q_out = (k > 1 || want_q) ? qbuf : nullptr;
+		ss.q_in = ss.q_out ? ss.q_out : sa.bv[0];
+		ss.count_here = need_ids_buf ? 0 : 1;
+		Q_TRY(launch_small_merge_count(ss, st));
+		n_launch++;
+		if (need_ids_buf) {
+			ss.span_excl = dense_probe && want_vals && cap ? span_excl : nullptr;
+			ss.tile_excl = probe_mode == PROBE_BITS && want_vals && !dense_probe ? tile_excl : nullptr;
+			Q_TRY(launch_small_prefix(ss, st));
+			ScanArgs ea;
+			memset(&ea, 0, sizeof(ea));
+			ea.ids_out = (want_ids || separate_probe) && cap ? r->d_ids : nullptr; // positions alone need no row IDs
+			ea.row_base = t->row_base;
+			Q_TRY(launch_small_decode(ss, ea, st));
+			n_launch += 2;
+		}
+		sa.q_out = const_cast<uint64_t *>(ss.q_in); // what the probe kernels re-decode
+		sa.tile_excl = ss.tile_excl;
+		sa.span_excl = ss.span_excl;
+		r->info.fused = 0;
 	} else if (!unfused) {
 		// one pass: merge (+delta XOR) + decode (+ fused probe / aggregate when eligible)
 		sa.ctrl = ctrl_a;
@@ -549,7 +605,7 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	if (dense_probe) {
 		dp.q = sa.q_out;
 		dp.span_excl = sa.span_excl;
-		dp.n_span = n_tile * (uint32_t)kConsumerWarps;
+		dp.n_span = probe_n_tile * (uint32_t)kConsumerWarps;
 		dp.n_blk = (t->n_rows + kPackBlock - 1) / kPackBlock;
 		for (int d = 0; d < n_dist; d++) {
 			dp.lout[d] = dist_out[d] >= 0 && cap ? static_cast<long long *>(r->d_vals[dist_out[d]]) : nullptr;
@@ -558,7 +614,7 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 		dp.agg_ia = agg_ia;
 		dp.agg_ib = agg_ib;
 		dp.hdr = r->d_hdr;
-		Q_TRY(launch_probe_dense(dp, tile_words, want_vals && cap, t->sm_count, st));
+		Q_TRY(launch_probe_dense(dp, probe_tile_words, want_vals && cap, t->sm_count, st));
 		n_launch++;
 		if (r->timing) {
 			Q_TRY(cudaEventRecord(r->ev[2], st));
@@ -569,7 +625,7 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 		memset(&pb, 0, sizeof(pb));
 		pb.q_out = sa.q_out; // input of the bit-driven probe
 		pb.tile_excl = sa.tile_excl;
-		pb.n_seg = probe_on_bv ? t->n_seg : n_tile;
+		pb.n_seg = probe_on_bv ? t->n_seg : probe_n_tile;
 		pb.row_base = t->row_base;
 		pb.n_load = n_dist;
 		for (int d = 0; d < n_dist; d++) {
@@ -581,7 +637,7 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 		pb.agg_ib = agg_ib;
 		pb.hdr = r->d_hdr;
 		pb.count_rows = probe_on_bv ? 1 : 0;
-		Q_TRY(launch_probe_bits(pb, probe_on_bv ? t->seg_words : tile_words, want_vals && cap, t->sm_count, st));
+		Q_TRY(launch_probe_bits(pb, probe_on_bv ? t->seg_words : probe_tile_words, want_vals && cap, t->sm_count, st));
 		n_launch++;
 		if (r->timing) {
 			Q_TRY(cudaEventRecord(r->ev[2], st));
@@ -669,6 +725,7 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	                     : probe_mode == PROBE_GATHER   ? CUBIT_PROBE_GATHER
 	                     : probe_mode == PROBE_FUSED    ? CUBIT_PROBE_FUSED
 	                                                    : CUBIT_PROBE_NONE;
+	r->info.scan_path = probe_on_bv ? CUBIT_SCAN_NONE : (two_pass ? CUBIT_SCAN_TWO_PASS : CUBIT_SCAN_RING);
 	r->info.n_streams = k;
 	r->info.n_launches = n_launch;
 	r->info.delta_entries = delta_entries;

@@ -189,6 +189,7 @@ int sharded_result_finish(cubit_gpu_result *r) {
 		tot.ms_total = std::max(tot.ms_total, pi.ms_total);
 		tot.fused = pi.fused;
 		tot.probe_path = pi.probe_path;
+		tot.scan_path = pi.scan_path;
 	}
 	r->info = tot; // device pointers stay NULL: the rows live on several devices (cubit_gpu_fetch walks them)
 	r->fin_rc = rc;

@@ -171,6 +171,26 @@ struct DenseProbeArgs {
 	uint32_t n_stages;                   // ring stages per column (2..4)
 };
 
+// Short queries as two streaming passes (small_scan_kernels.cu).  Unit = 128 words = 8192 rows; every warp of the
+// grid owns a contiguous chunk of units.
+struct SmallScanArgs {
+	const uint64_t *bv[8];          // value bitvectors (k <= 8 here; the planner uses it for k <= 4)
+	uint64_t group_end;             // bit i: stream i closes its OR group
+	uint32_t k;
+	uint32_t n_units, units_per_chunk, n_chunks; // small_scan_plan
+	uint64_t *q_out;                // pass A: merged bitvector out, or nullptr (k = 1: Q is bv[0] itself)
+	const uint64_t *q_in;           // pass C: the bitvector to decode
+	unsigned long long *chunk_tot;  // [n_chunks + 1]: pass A totals → pass B exclusive prefixes (+ total)
+	unsigned long long *span_excl;  // pass C out: output position of every unit's first row, or nullptr
+	unsigned long long *tile_excl;  // pass C out: the same per 8 units (65536-row tile), or nullptr
+	ResultHeader *hdr;
+	int count_here;                 // 1: pass A adds COUNT to hdr (no pass B / C follows)
+};
+cudaError_t launch_small_merge_count(const SmallScanArgs &s, cudaStream_t stream);
+cudaError_t launch_small_prefix(const SmallScanArgs &s, cudaStream_t stream);
+cudaError_t launch_small_decode(const SmallScanArgs &s, const ScanArgs &a, cudaStream_t stream);
+void small_scan_plan(SmallScanArgs &s, uint32_t n_units, int sm_count);
+
 struct ProbeArgs {
 	const long long *ids;               // sorted global row IDs
 	const unsigned long long *count_ptr; // device count (hdr->count) or nullptr

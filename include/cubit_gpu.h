@@ -120,8 +120,13 @@ typedef struct cubit_result_info {
 	const uint32_t *d_validity[CUBIT_MAX_PROBE_COLS]; /* device validity bits of the projected values (bit j of
 	                           32-bit word j/32 = result row j), NULL = that column holds no NULLs          */
 	uint32_t probe_path;    /* CUBIT_PROBE_*: which kernel probed the columns                              */
-	uint32_t reserved;
+	uint32_t scan_path;     /* CUBIT_SCAN_*: how merge + decode ran                                         */
 } cubit_result_info;
+
+/* cubit_result_info.scan_path */
+#define CUBIT_SCAN_RING 0     /* the single-pass ring kernel (fused merge + decode)                          */
+#define CUBIT_SCAN_TWO_PASS 1 /* short queries on large tables: streaming merge + count, then a decode pass  */
+#define CUBIT_SCAN_NONE 2     /* no scan ran: the probe read the one value bitvector itself                  */
 
 /* cubit_result_info.probe_path */
 #define CUBIT_PROBE_NONE 0   /* no column was probed                                                        */

@@ -27,6 +27,7 @@ namespace cubit {
 constexpr int kUnitWpt = 4;                    // 64-bit words per lane and unit
 constexpr int kUnitWords = 32 * kUnitWpt;      // 128 words = 8192 rows = one scan-kernel span of a 65536-row tile
 constexpr int kSmallThreads = 256;
+constexpr int kDirectMax = 96;                // rows per unit up to which pass C stores row IDs lane by lane
 
 // ---------------------------------------------------------------------------------------------- pass A
 template <bool ONEG>
@@ -201,7 +202,43 @@ __global__ void __launch_bounds__(kSmallThreads) cubit_decode_kernel(const __gri
 			}
 		}
 		if (cnt && a.ids_out) {
-			emit_span<kUnitWpt, 0, true, false>(a, q, compact[warp], pos_end, a.row_base + (int64_t)u * (kUnitWords * 64), lane, agg);
+			const int64_t row0 = a.row_base + (int64_t)u * (kUnitWords * 64);
+			if (cnt <= (uint32_t)kDirectMax) {
+				// a handful of rows in 8192: four interleaved warp scans give every lane the rank of its words, and the
+				// lanes store their row IDs straight to global memory (≈ 90 instructions per unit instead of the ≈ 400
+				// of the staged, coalesced write-out, which pays off only when there is something to coalesce)
+				uint32_t c[kUnitWpt], incl[kUnitWpt];
+#pragma unroll
+				for (int i = 0; i < kUnitWpt; i++) {
+					c[i] = (uint32_t)__popcll(q[i]);
+					incl[i] = c[i];
+				}
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+					for (int i = 0; i < kUnitWpt; i++) {
+						const uint32_t n = __shfl_up_sync(0xffffffffu, incl[i], d);
+						if (lane >= d) {
+							incl[i] += n;
+						}
+					}
+				}
+				unsigned long long base = pos_end;
+#pragma unroll
+				for (int i = 0; i < kUnitWpt; i++) {
+					const uint32_t slot_total = __shfl_sync(0xffffffffu, incl[i], 31);
+					unsigned long long at = base + incl[i] - c[i];
+					uint64_t w = q[i];
+					const int64_t wrow = row0 + (int64_t)(i * 32 + lane) * 64;
+					while (w) {
+						a.ids_out[at++] = wrow + (__ffsll((long long)w) - 1);
+						w &= w - 1;
+					}
+					base += slot_total;
+				}
+			} else {
+				emit_span<kUnitWpt, 0, true, false>(a, q, compact[warp], pos_end, row0, lane, agg);
+			}
 		}
 	}
 }

@@ -107,21 +107,28 @@ __device__ __forceinline__ void dense_iter(const DenseProbeArgs &a, const uint32
 	for (int h = 0; h < 2; h++) {
 		const uint32_t g = g0 + h * 32 + lane;
 		if (POS) {
-			if (FULL || (ok[h][0] && ok[h][1])) {
 #pragma unroll
-				for (int c = 0; c < NL; c++) {
-					if (a.lout[c]) {
-						__stcs(reinterpret_cast<longlong2 *>(a.lout[c] + obase + g * 2), make_longlong2(v[h][0][c], v[h][1][c]));
-					}
-				}
-			} else {
-#pragma unroll
-				for (int e = 0; e < 2; e++) {
-#pragma unroll
-					for (int c = 0; c < NL; c++) {
-						if (ok[h][e] && a.lout[c]) {
-							__stcs(a.lout[c] + obase + g * 2 + e, v[h][e][c]);
-						}
+			for (int c = 0; c < NL; c++) {
+				if (a.lout[c]) {
+					long long *dst = a.lout[c] + obase + g * 2;
+					if (FULL) {
+						__stcs(reinterpret_cast<longlong2 *>(dst), make_longlong2(v[h][0][c], v[h][1][c]));
+					} else {
+						// the pair as one 128-bit store when both slots hold a row, else whichever does — predicated,
+						// no branches (the compiler's if / else cost the partial iteration twice the full one's instructions)
+						asm volatile("{\n\t.reg .pred p, q, b, nb;\n\t"
+						             "setp.ne.u32 p, %3, 0;\n\t"
+						             "setp.ne.u32 q, %4, 0;\n\t"
+						             "and.pred b, p, q;\n\t"
+						             "not.pred nb, b;\n\t"
+						             "and.pred p, p, nb;\n\t"
+						             "and.pred q, q, nb;\n\t"
+						             "@b st.global.cs.v2.s64 [%0], {%1, %2};\n\t"
+						             "@p st.global.cs.s64 [%0], %1;\n\t"
+						             "@q st.global.cs.s64 [%0+8], %2;\n\t}"
+						             :
+						             : "l"(dst), "l"(v[h][0][c]), "l"(v[h][1][c]), "r"((uint32_t)ok[h][0]), "r"((uint32_t)ok[h][1])
+						             : "memory");
 					}
 				}
 			}
@@ -176,7 +183,15 @@ __device__ __forceinline__ void dense_write_out(const DenseProbeArgs &a, const u
 	if (AGGM == DENSE_AGG_DELTA) { // Σ (base + delta) over this lane's rows of the block = rows·base + Σ delta
 		const int ca = NL == 1 ? 0 : a.agg_ia;
 		const long long b = NL == 1 ? bh.base[0] : (ca == 1 ? bh.base[NL - 1] : bh.base[0]);
-		add128(agg.lo, agg.hi, (unsigned long long)(b * (long long)acc.rows), __mul64hi(b, (long long)acc.rows));
+		// rows < 2^11: the 128-bit product from two 32 x 32 → 64-bit multiplies and a sign correction (b = ub − 2^64
+		// for negative b) — a generic signed 64 x 64 → 128 multiply costs 35 instructions per block
+		const unsigned long long ub = (unsigned long long)b;
+		const unsigned long long p0 = (unsigned long long)(uint32_t)ub * acc.rows;
+		const unsigned long long p1 = (unsigned long long)(uint32_t)(ub >> 32) * acc.rows;
+		const unsigned long long plo = p0 + (p1 << 32);
+		long long phi = (long long)((p1 >> 32) + (plo < p0 ? 1ull : 0ull));
+		phi -= b < 0 ? (long long)acc.rows : 0ll;
+		add128(agg.lo, agg.hi, plo, phi);
 		add128(agg.lo, agg.hi, acc.dsum, 0ll);
 	}
 }

@@ -230,11 +230,10 @@ cudaError_t launch_validity_gather(const long long *ids, const unsigned long lon
 
 // ------------------------------------------------------------- index build
 // One CTA converts kBuildRows consecutive rows per iteration.  Each warp reads
-// 32 consecutive rows (coalesced); __match_any_sync gives every lane the mask
-// of lanes holding the same value, which IS the 32-bit slice of that value's
-// bitvector for these rows.  Slices are collected in a shared-memory tile
-// [value][kBuildRows/32] (each slot written by exactly one lane) and flushed as
-// contiguous runs of kBuildRows/8 bytes per value.
+// 32 consecutive rows (coalesced) and every lane ORs its row's bit into the
+// 32-bit slice of its value's bitvector in a shared-memory tile
+// [value][kBuildRows/32] (ATOMS.OR, bank-swizzled by the value), which is then
+// flushed as contiguous runs of kBuildRows/8 bytes per value.
 constexpr int kBuildThreads = 256;
 constexpr int kBuildRows = 4096;
 constexpr int kBuildSlots = kBuildRows / 32; // u32 slots per value per tile
@@ -248,49 +247,103 @@ __global__ void __launch_bounds__(kBuildThreads)
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint64_t n_tiles = (n_rows + kBuildRows - 1) / kBuildRows;
 	constexpr int kIters = kBuildSlots / (kBuildThreads / 32); // 32-row slots per warp per tile
-	// rows below row_begin are already indexed (append path): their bits are kept as they are
-	for (uint64_t t = row_begin / kBuildRows + blockIdx.x; t < n_tiles; t += gridDim.x) {
+	const long long off = base_value + (long long)v_lo;
+	// this thread's kIters column values of tile t as value ids relative to v_lo (0xffffffff: not indexed here)
+	auto load_tile = [&](uint64_t t, uint32_t (&rel)[kIters]) {
 		const uint64_t row0 = t * kBuildRows;
-		// all of this warp's column loads first (kIters independent 128-byte requests in flight),
-		// overlapped with zeroing the tile
-		long long rel[kIters];
+		if (row0 >= row_begin && row0 + kBuildRows <= n_rows && !valid) { // interior tile, no NULLs: no per-row checks
+			const T *src = col + row0 + (uint64_t)warp * 32 + lane;
+			T raw[kIters]; // all loads first, conversions after: kIters independent 128-byte requests per warp in flight
+#pragma unroll
+			for (int it = 0; it < kIters; it++) {
+				raw[it] = __ldcs(src + it * kBuildThreads);
+			}
+#pragma unroll
+			for (int it = 0; it < kIters; it++) {
+				const unsigned long long d = (unsigned long long)((long long)raw[it] - off);
+				rel[it] = d < (unsigned long long)v_n ? (uint32_t)d : 0xffffffffu;
+			}
+			return;
+		}
 #pragma unroll
 		for (int it = 0; it < kIters; it++) {
 			const uint64_t r = row0 + (uint64_t)(it * (kBuildThreads / 32) + warp) * 32 + lane;
-			rel[it] = (r >= row_begin && r < n_rows) ? (long long)__ldcs(col + r) - base_value - (long long)v_lo : -1;
-			if (valid && r < n_rows) { // NULL keys are not indexed: one 32-bit slice of the validity mask per warp
-				const uint32_t vm = __ldg(reinterpret_cast<const uint32_t *>(valid) + (r >> 5)); // r >> 5 is warp-uniform
-				if (!((vm >> (r & 31u)) & 1u)) {
-					rel[it] = -1;
+			// rows below row_begin are already indexed (append path): their bits are kept as they are
+			unsigned long long d = ~0ull;
+			if (r >= row_begin && r < n_rows) {
+				d = (unsigned long long)((long long)__ldcs(col + r) - off);
+				if (valid) { // NULL keys are not indexed: one 32-bit slice of the validity mask per warp
+					const uint32_t vm = __ldg(reinterpret_cast<const uint32_t *>(valid) + (r >> 5)); // r >> 5 is warp-uniform
+					if (!((vm >> (r & 31u)) & 1u)) {
+						d = ~0ull;
+					}
 				}
 			}
+			rel[it] = d < (unsigned long long)v_n ? (uint32_t)d : 0xffffffffu;
 		}
-		for (uint32_t i = threadIdx.x; i < v_n * (kBuildSlots / 4); i += kBuildThreads) {
-			reinterpret_cast<uint4 *>(tile)[i] = make_uint4(0, 0, 0, 0);
+	};
+	uint32_t cur[kIters], nxt[kIters];
+	uint64_t t = row_begin / kBuildRows + blockIdx.x;
+	if (t < n_tiles) {
+		load_tile(t, cur);
+	}
+	// the tile is zeroed once; the flush of every tile leaves it zeroed for the next one
+	for (uint32_t i = threadIdx.x; i < v_n * (kBuildSlots / 4); i += kBuildThreads) {
+		reinterpret_cast<uint4 *>(tile)[i] = make_uint4(0, 0, 0, 0);
+	}
+	__syncthreads();
+	for (; t < n_tiles; t += gridDim.x) {
+		const uint64_t row0 = t * kBuildRows;
+		// the NEXT tile's column values are in flight while this one is scattered and flushed (the loads of a tile
+		// right in front of its scatter were 56 % of the stall samples)
+		if (t + gridDim.x < n_tiles) {
+			load_tile(t + gridDim.x, nxt);
 		}
-		__syncthreads();
+		// every row sets ITS bit with one shared-memory atomic OR (fire and forget: nothing waits for it), instead of a
+		// __match_any_sync per 32 rows whose result the next instruction needs — that dependency was 40 % of the
+		// kernel's stall samples (profiles/r2_index_build.md).  The slot index is warp-uniform, so the tile is swizzled
+		// by the value (the low five bits of the slot XOR the value's): lanes with different values hit different
+		// banks; the flush undoes it (piece index XOR, then a permutation of the piece's four words).
 #pragma unroll
 		for (int it = 0; it < kIters; it++) {
-			const int slot = it * (kBuildThreads / 32) + warp;
-			const bool in = rel[it] >= 0 && rel[it] < (long long)v_n;
-			const unsigned key = in ? (unsigned)rel[it] : 0xffffffffu;
-			const unsigned same = __match_any_sync(0xffffffffu, key);
-			if (in && (__ffs(same) - 1) == lane) {
-				tile[(uint32_t)rel[it] * kBuildSlots + slot] = same;
+			const uint32_t slot = (uint32_t)(it * (kBuildThreads / 32) + warp);
+			const uint32_t v = cur[it];
+			if (v != 0xffffffffu) {
+				atomicOr(&tile[v * kBuildSlots + (slot ^ (v & 31u))], 1u << lane);
 			}
 		}
 		__syncthreads();
-		// flush: per value kBuildSlots u32 = kBuildRows/64 u64 words, contiguous in B_v
+		// flush (and re-zero): per value kBuildSlots u32 = kBuildRows/64 u64 words = 512 contiguous bytes of B_v — one
+		// coalesced 512-byte store per (warp, value): lane l moves the 16-byte piece l
 		const uint64_t word0 = row0 / 64;
-		constexpr int kPairsPerVal = kBuildRows / 128; // 16-byte (two-word) pieces per value
-		for (uint32_t i = threadIdx.x; i < v_n * kPairsPerVal; i += kBuildThreads) {
-			const uint32_t v = i / kPairsPerVal, p = i % kPairsPerVal;
-			if (word0 + 2 * p < words_per_bv) {
-				uint4 x = reinterpret_cast<const uint4 *>(tile)[v * (kBuildSlots / 4) + p];
-				uint4 *dst = reinterpret_cast<uint4 *>(bitvectors + (uint64_t)(v_lo + v) * words_per_bv + word0 + 2 * p);
-				const uint64_t piece_row0 = (word0 + 2 * p) * 64;
-				if (piece_row0 + 128 <= row_begin) {
-					continue; // only rows indexed earlier
+		static_assert(kBuildRows / 128 == 32, "one 16-byte piece per lane");
+		const bool interior = row0 >= row_begin && word0 + kBuildRows / 64 <= words_per_bv;
+		for (uint32_t v = (uint32_t)warp; v < v_n; v += kBuildThreads / 32) {
+			// un-swizzle: logical piece l sits at physical piece l ^ (m >> 2), its four words permuted by m & 3 (m = v mod 32)
+			uint4 *src = reinterpret_cast<uint4 *>(tile) + v * (kBuildSlots / 4) + ((uint32_t)lane ^ ((v & 31u) >> 2));
+			uint4 x = *src;
+			*src = make_uint4(0, 0, 0, 0);
+			if (v & 1u) {
+				uint32_t tmp = x.x;
+				x.x = x.y;
+				x.y = tmp;
+				tmp = x.z;
+				x.z = x.w;
+				x.w = tmp;
+			}
+			if (v & 2u) {
+				uint32_t tmp = x.x;
+				x.x = x.z;
+				x.z = tmp;
+				tmp = x.y;
+				x.y = x.w;
+				x.w = tmp;
+			}
+			uint4 *dst = reinterpret_cast<uint4 *>(bitvectors + (uint64_t)(v_lo + v) * words_per_bv + word0 + 2 * lane);
+			if (!interior) {
+				const uint64_t piece_row0 = (word0 + 2 * lane) * 64;
+				if (word0 + 2 * lane >= words_per_bv || piece_row0 + 128 <= row_begin) {
+					continue; // past the capacity / only rows indexed earlier
 				}
 				if (piece_row0 < row_begin) { // the boundary piece: old rows' bits stay (the tile holds zeros for them)
 					const uint4 old = *dst;
@@ -299,10 +352,14 @@ __global__ void __launch_bounds__(kBuildThreads)
 					x.z |= old.z;
 					x.w |= old.w;
 				}
-				__stcs(dst, x);
 			}
+			__stcs(dst, x);
 		}
 		__syncthreads();
+#pragma unroll
+		for (int it = 0; it < kIters; it++) {
+			cur[it] = nxt[it];
+		}
 	}
 }
 

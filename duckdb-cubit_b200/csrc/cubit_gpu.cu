@@ -855,7 +855,13 @@ extern "C" int cubit_gpu_index_build(cubit_gpu_table *t, int32_t index_id, int32
 	const unsigned long long *valid = c.d_valid;
 	int launches = 0;
 	if (!ix->compressed) {
-		CU_TRY(cudaMemsetAsync(ix->d_bits, 0, (size_t)ix->card * t->words_per_bv * 8, t->stream));
+		// the build kernel writes every word of the 4096-row tiles that hold rows (64 words each); only the capacity
+		// behind the last tile has to be zeroed here — not the whole index (12.5 GB at cardinality 100 and 10^9 rows)
+		const uint64_t built_words = std::min<uint64_t>(t->words_per_bv, (t->n_rows + 4095) / 4096 * 64);
+		if (built_words < t->words_per_bv) {
+			CU_TRY(cudaMemset2DAsync(ix->d_bits + built_words, t->words_per_bv * 8, 0, (t->words_per_bv - built_words) * 8,
+			                         ix->card, t->stream));
+		}
 		CU_TRY(launch_index_build(c.d, c.elem, valid, 0, t->n_rows, base_value, ix->card, ix->d_bits, t->words_per_bv,
 		                          t->sm_count, t->stream, &launches));
 		t->launches += launches;

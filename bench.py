@@ -532,6 +532,37 @@ def run_b200(args):
                     "note": "every selected row ID + payload value copied to page-locked host memory on every rank "
                             "(asynchronous double-buffered hand-off; PCIe bound)"}
 
+    # ---- the result gather (north_star: "per-shard row-ID lists are concatenated with shard offsets, NCCL only for
+    # the final aggregate or result gather"): every rank's sorted row IDs of the s = 1e-2 query to rank 0 over NCCL
+    # send/recv, straight from the library's device buffers; concatenation in rank order is the globally sorted list
+    rowid_gather = None
+    if world > 1 and not cfg5:
+        gi = SELECTIVITIES.index("1e-2")
+        gplan = cubit.QueryPlan([[(indexes[gi], v) for v in range(HOT_LO, HOT_LO + HOT_N)]], cubit.Q_ROWIDS)
+        best = None
+        for _ in range(3):
+            with t.execute(gplan) as r:
+                loc = sharding.result_rowids_tensor(r, dev)
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(stream)
+                full = sharding.gather_sorted(loc, dist, dst=0)
+                g1.record(stream)
+                torch.cuda.synchronize()
+                ms_g = g0.elapsed_time(g1)
+                if rank == 0:
+                    assert bool((full[1:] > full[:-1]).all()), "gathered row IDs are not ascending"
+                    n_full = int(full.numel())
+                del full
+            tg = torch.tensor([ms_g], dtype=torch.float64, device=dev)
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            best = float(tg.item()) if best is None else min(best, float(tg.item()))
+        if rank == 0:
+            rowid_gather = {"query": "s = 1e-2", "rows_gathered": n_full, "ms": best,
+                            "GBps_into_rank0": n_full * 8 * (world - 1) / world / (best * 1e-3) / 1e9,
+                            "note": "NCCL send/recv of the per-shard row-ID lists to rank 0 (zero-copy views of the "
+                                    "library's device buffers); checked strictly ascending"}
+
     if rank != 0:
         t.close()
         if world > 1:
@@ -659,6 +690,7 @@ def run_b200(args):
                         "host predicate structs in, COUNT/SUM row + chunk out.  This is the aggregate-push-down path: "
                         "the row-returning number (every row ID and value over PCIe) is e2e_full_materialize"},
         "e2e_full_materialize": e2e_full,
+        "rowid_gather": rowid_gather,
         "gpu_launches": launches, "clocks": clocks, "index_build_s": build_s,
     }
     if world == 1 and not args.no_cpu_baseline and not cfg5:

@@ -532,6 +532,50 @@ def run_b200(args):
                     "note": "every selected row ID + payload value copied to page-locked host memory on every rank "
                             "(asynchronous double-buffered hand-off; PCIe bound)"}
 
+    # ---- the same hand-off over the NARROW WIRE (include/cubit_gpu_wire.h): per DataChunk and stream the GPU ships a
+    # base + the narrowest deltas straight into page-locked windows; host workers (cubit_gpu_drain) widen ONE DataChunk
+    # at a time into cache-resident vectors and a consumer reads every value (wrapping sums, checked against the
+    # device's own SUM) — every selected row is DELIVERED as int64 DataChunks, which is what GetData hands on.
+    e2e_drain = None
+    if not args.no_materialize:
+        drain_threads = max(1, min(16, (os.cpu_count() or 1) // world))
+        ncols = 1 if with_payload else 0
+
+        def step_drain():
+            wire = wide = 0
+            for p in plans_sync:
+                with t.execute(p) as r:
+                    st = r.drain(rowids=True, n_cols=ncols, threads=drain_threads, window_rows=args.drain_window)
+                    assert st.rows == r.count
+                    if with_payload:  # payload = global row id: both streams must sum to the device's SUM
+                        assert st.sum_rowids == st.sum_cols[0] == r.sum % (1 << 64), "drain checksum != device SUM"
+                    wire += st.wire_bytes
+                    wide += st.wide_bytes
+            return wire, wide
+        step_drain()
+        barrier()
+        w0 = time.perf_counter()
+        reps = max(1, min(3, args.steps))
+        for _ in range(reps):
+            wire_b, wide_b = step_drain()
+        barrier()
+        dt = (time.perf_counter() - w0) / reps
+        if world > 1:
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            tm = torch.tensor([wire_b, wide_b], dtype=torch.int64, device=dev)
+            dist.all_reduce(tm)
+            wire_b, wide_b = int(tm[0].item()), int(tm[1].item())
+        e2e_drain = {"value": total_rows * n_q / dt, "unit": "rows/s", "d2h_bytes_per_step": wire_b,
+                     "wide_bytes_per_step": wide_b, "pcie_GBps_all_gpus": wire_b / dt / 1e9,
+                     "host_threads_per_gpu": drain_threads, "window_rows": args.drain_window or 128 * 2048,
+                     "rows_delivered_per_s": wide_b / (8 * (1 + ncols)) / dt,
+                     "note": "every selected row ID + payload value delivered to host consumers as 2048-row int64 "
+                             "DataChunks: narrow wire (per-chunk base + 1/2/4/8-byte deltas chosen and written by "
+                             "the GPU, zero-copy), widened chunk by chunk in cache by cubit_gpu_drain's workers, every "
+                             "value read (checksums equal the device SUM)"}
+
     # ---- the result gather (north_star: "per-shard row-ID lists are concatenated with shard offsets, NCCL only for
     # the final aggregate or result gather"): every rank's sorted row IDs of the s = 1e-2 query to rank 0 over NCCL
     # send/recv, straight from the library's device buffers; concatenation in rank order is the globally sorted list
@@ -690,6 +734,7 @@ def run_b200(args):
                         "host predicate structs in, COUNT/SUM row + chunk out.  This is the aggregate-push-down path: "
                         "the row-returning number (every row ID and value over PCIe) is e2e_full_materialize"},
         "e2e_full_materialize": e2e_full,
+        "e2e_full_materialize_narrow_wire": e2e_drain,
         "rowid_gather": rowid_gather,
         "gpu_launches": launches, "clocks": clocks, "index_build_s": build_s,
     }
@@ -720,6 +765,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=1 << 26, help="rows per sweep point of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-materialize", action="store_true")
+    ap.add_argument("--drain-window", type=int, default=0, help="rows per narrow-wire window (0 = library default)")
     ap.add_argument("--no-traffic", action="store_true", help="skip the ncu child that measures DRAM bytes per kernel")
     ap.add_argument("--no-payload24", action="store_true", help="skip the 24-bit payload raw/packed comparison")
     ap.add_argument("--payload-form", default="both", choices=["both", "raw", "packed"],

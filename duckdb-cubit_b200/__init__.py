@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("CUBIT_GPU_LIB") or os.path.join(_HERE, "libcubit_gpu.
 HOST_LIB_PATH = os.path.join(_HERE, "libcubit_host.so")
 
 # ---- mirror of include/cubit_gpu.h -------------------------------------------------
-ABI_VERSION = 4
+ABI_VERSION = 5
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5
 MAX_STREAMS = 64
 MAX_PROBE_COLS = 8
@@ -44,6 +44,8 @@ ABI_SYMBOLS = [
     "cubit_gpu_create_sharded", "cubit_gpu_shard_count", "cubit_gpu_shard_info", "cubit_gpu_row_count",
     "cubit_gpu_index_create_compressed", "cubit_gpu_index_info", "cubit_gpu_add_delta", "cubit_gpu_add_delta_pairs",
     "cubit_gpu_set_merge_threshold", "cubit_gpu_fetch_async", "cubit_gpu_fetch_wait", "cubit_gpu_result_add_limbs",
+    "cubit_gpu_fetch_wire_async", "cubit_gpu_wire_bytes", "cubit_gpu_wire_payload_bytes", "cubit_gpu_wire_unpack",
+    "cubit_gpu_drain",
 ]
 
 
@@ -59,6 +61,17 @@ class Query(C.Structure):
     _fields_ = [("n_groups", C.c_uint32), ("groups", C.POINTER(PredGroup)), ("flags", C.c_uint32),
                 ("n_cols", C.c_uint32), ("cols", C.POINTER(C.c_int32)), ("agg_kind", C.c_int32),
                 ("agg_col_a", C.c_int32), ("agg_col_b", C.c_int32)]
+
+
+WIRE_CHUNK = 2048
+CHUNK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_int64),
+                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p))
+
+
+class DrainStats(C.Structure):
+    _fields_ = [("rows", C.c_uint64), ("chunks", C.c_uint64), ("windows", C.c_uint64), ("wire_bytes", C.c_uint64),
+                ("wide_bytes", C.c_uint64), ("sum_rowids", C.c_uint64), ("sum_cols", C.c_uint64 * MAX_PROBE_COLS),
+                ("workers", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class ResultInfo(C.Structure):
@@ -167,6 +180,11 @@ def load_library():
         "cubit_gpu_fetch_async": ([vp, u64, u64, vp, u32, P(vp), P(vp)], C.c_int),
         "cubit_gpu_fetch_wait": ([vp], C.c_int),
         "cubit_gpu_result_add_limbs": ([vp, vp], C.c_int),
+        "cubit_gpu_fetch_wire_async": ([vp, u64, u64, C.c_int, u32, vp, u64, P(vp)], C.c_int),
+        "cubit_gpu_wire_bytes": ([u64, u32], u64),
+        "cubit_gpu_wire_payload_bytes": ([vp], u64),
+        "cubit_gpu_wire_unpack": ([vp, u32, u64, vp, u32], C.c_int),
+        "cubit_gpu_drain": ([vp, C.c_int, u32, u32, u64, vp, vp, P(DrainStats)], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -181,6 +199,40 @@ def load_library():
 def _check(rc):
     if rc != OK:
         raise CubitError(rc, load_library().cubit_gpu_last_error().decode())
+
+
+class HostBuffer:
+    """page-locked host memory from cubit_gpu_alloc_host as a uint8 array (`.array`); free() or context manager"""
+
+    def __init__(self, nbytes):
+        self._p = C.c_void_p()
+        _check(load_library().cubit_gpu_alloc_host(nbytes, C.byref(self._p)))
+        self.array = np.ctypeslib.as_array((C.c_uint8 * max(1, nbytes)).from_address(self._p.value))
+
+    def free(self):
+        if self._p is not None:
+            self.array = None
+            load_library().cubit_gpu_free_host(self._p)
+            self._p = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.free()
+
+
+def wire_bytes(n_rows, n_streams):
+    return int(load_library().cubit_gpu_wire_bytes(n_rows, n_streams))
+
+
+def wire_unpack(wire, stream, chunk, dtype=np.int64):
+    """widen one DataChunk of one stream of a narrow wire (host-only code) → array"""
+    out = np.empty(WIRE_CHUNK, dtype=dtype)
+    n = load_library().cubit_gpu_wire_unpack(wire.ctypes.data, stream, chunk, out.ctypes.data, out.dtype.itemsize)
+    if n < 0:
+        raise CubitError(EINVAL, load_library().cubit_gpu_last_error().decode())
+    return out[:n]
 
 
 def device_count():
@@ -270,6 +322,49 @@ class Result:
 
     def fetch_wait(self, ticket):
         _check(self._t._L.cubit_gpu_fetch_wait(ticket))
+
+    def fetch_wire_async(self, offset, n, wire, rowids=True, n_cols=None):
+        """enqueue the narrow-wire hand-off of result rows [offset, offset+n) into the page-locked uint8 array `wire`
+        (include/cubit_gpu_wire.h) → ticket for fetch_wait"""
+        tk = C.c_void_p()
+        nc = len(self._dtypes) if n_cols is None else n_cols
+        _check(self._t._L.cubit_gpu_fetch_wire_async(self._h, offset, n, 1 if rowids else 0, nc, wire.ctypes.data,
+                                                     wire.nbytes, C.byref(tk)))
+        return tk
+
+    def drain(self, rowids=True, n_cols=None, threads=1, window_rows=0, fn=None, validity=False):
+        """the parallel ordered DataChunk hand-off over the narrow wire (cubit_gpu_drain).  fn(worker, batch_index,
+        row_offset, ids or None, [column arrays]) is called per DataChunk (copies); with validity=True a sixth
+        argument carries, per column, the chunk's ValidityMask words or None.  fn=None = checksum consumer.
+        → DrainStats"""
+        nc = len(self._dtypes) if n_cols is None else n_cols
+        st = DrainStats()
+        cb = None
+        if fn is not None:
+            dts = self._dtypes[:nc]
+
+            def tramp(ctx, worker, batch, row_off, n, ids_p, cols_p, val_p):
+                try:
+                    ids = np.ctypeslib.as_array(ids_p, shape=(n,)).copy() if (rowids and n) else (
+                        np.empty(0, np.int64) if rowids else None)
+                    cols = []
+                    for c, dt in enumerate(dts):
+                        buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(cols_p[c]) if n else b""
+                        cols.append(np.frombuffer(buf, dtype=dt, count=n).copy())
+                    if validity:
+                        vw = [np.ctypeslib.as_array(C.cast(val_p[c], C.POINTER(C.c_uint64)),
+                                                    shape=((n + 63) // 64,)).copy() if val_p[c] else None
+                              for c in range(len(dts))]
+                        return int(bool(fn(worker, batch, row_off, ids, cols, vw)))
+                    return int(bool(fn(worker, batch, row_off, ids, cols)))
+                except Exception:  # an exception must not unwind through the C frames
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            cb = CHUNK_FN(tramp)
+        _check(self._t._L.cubit_gpu_drain(self._h, 1 if rowids else 0, nc, threads, window_rows,
+                                          C.cast(cb, C.c_void_p) if cb is not None else None, None, C.byref(st)))
+        return st
 
     def add_limbs(self, device_ptr):
         """ADD (count, 128-bit sum) as five int64 limbs to device memory, in stream order (multi-process reduce)"""

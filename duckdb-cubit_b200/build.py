@@ -49,7 +49,7 @@ def build_gpu(verbose=False, ptxas_info=False):
             os.path.join(CSRC, "table.h"), os.path.join(ROOT, "include", "cubit_gpu.h")]
     units = ["scan_kernel.cu", "aux_kernels.cu", "column_decode.cu", "wah_decode.cu", "delta_kernels.cu",
              "container_kernels.cu", "probe_dense_kernel.cu", "small_scan_kernels.cu", "cubit_gpu.cu", "cubit_columns.cu", "cubit_delta.cu", "cubit_persist.cu",
-             "cubit_query.cu", "cubit_sharded.cu"]
+             "cubit_query.cu", "cubit_sharded.cu", "cubit_wire.cu"]
     objs = []
     jobs = []
     for u in units:

@@ -267,6 +267,7 @@ extern "C" int cubit_gpu_destroy(cubit_gpu_table *t) {
 	if (t->stream) {
 		cudaStreamSynchronize(t->stream);
 	}
+	wire_pool_free(t);
 	for (auto &cs : t->copy_stream) {
 		if (cs) {
 			cudaStreamSynchronize(cs);

@@ -107,6 +107,7 @@ int sharded_destroy(cubit_gpu_table *t) {
 		cubit_gpu_destroy(s);
 	}
 	t->shards.clear();
+	wire_pool_free(t);
 	delete t;
 	return CUBIT_OK;
 }

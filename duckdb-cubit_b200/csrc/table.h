@@ -165,6 +165,7 @@ struct cubit_gpu_table {
 	unsigned long long *d_scratch = nullptr; // popcount scratch
 	uint64_t scratch_n = 0;
 	std::vector<cubit::ResultHeader *> hdr_pool; // pinned result headers, recycled across queries
+	std::vector<std::pair<void *, uint64_t>> wire_pool; // page-locked narrow-wire windows of cubit_gpu_drain, recycled
 	uint8_t *h_stage[2] = {nullptr, nullptr};     // pinned staging chunks of the segment / delta upload (lazy, kept)
 	cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 	// sharded parent (cubit_gpu_create_sharded): no device state of its own, every call fans out to the children
@@ -247,6 +248,8 @@ int delta_rows_locked(cubit_gpu_table *t, Index *ix, uint32_t v, std::vector<int
 int delta_settle_locked(cubit_gpu_table *t, Index *ix);
 // re-key the delta CSR after the segment count changed (append)
 int delta_restride_locked(cubit_gpu_table *t, Index *ix, uint32_t new_n_seg);
+
+void wire_pool_free(cubit_gpu_table *t); // cubit_wire.cu
 
 // sharded fan-out (cubit_sharded.cu)
 int sharded_destroy(cubit_gpu_table *t);

@@ -1,6 +1,7 @@
 #include "cubit_scan.hpp"
 
 #include "cubit_gpu.h"
+#include "cubit_gpu_wire.h"
 
 #include <algorithm>
 
@@ -18,6 +19,7 @@ CubitScanGlobalState::~CubitScanGlobalState() {
 	if (result) {
 		cubit_gpu_free_result(result);
 	}
+	cubit_gpu_free_host(win_wire);
 	cubit_gpu_free_host(win_rowids);
 	for (auto p : win_cols) {
 		cubit_gpu_free_host(p);
@@ -107,6 +109,11 @@ std::unique_ptr<CubitScanGlobalState> CubitScanInitGlobal(const CubitScanBindDat
 	cubit_result_info info;
 	Check(cubit_gpu_result_get(state->result, &info));
 	state->row_count = info.count;
+	{
+		uint32_t n_shards = 1;
+		cubit_gpu_shard_count(bind.table->Handle(), &n_shards);
+		state->narrow_wire = n_shards == 1 && bind.aggregate == CubitAggregate::NONE && !column_ids.empty();
+	}
 	state->sum.lower = info.sum_lo;
 	state->sum.upper = info.sum_hi;
 	return state;
@@ -118,6 +125,22 @@ static void FillWindow(CubitScanGlobalState &st) {
 	st.win_end = st.offset + n;
 	bool want_rowid = false;
 	std::vector<void *> ptrs;
+	if (st.narrow_wire) {
+		uint32_t n_value_cols = 0;
+		for (auto c : st.column_ids) {
+			want_rowid = want_rowid || c == COLUMN_IDENTIFIER_ROW_ID;
+			n_value_cols += c == COLUMN_IDENTIFIER_ROW_ID ? 0 : 1;
+		}
+		if (!st.win_wire) {
+			st.win_wire_bytes = cubit_wire_bytes(kWindowRows, (want_rowid ? 1u : 0u) + n_value_cols);
+			Check(cubit_gpu_alloc_host(st.win_wire_bytes, &st.win_wire));
+		}
+		cubit_gpu_fetch_ticket *ticket = nullptr;
+		Check(cubit_gpu_fetch_wire_async(st.result, st.win_begin, n, want_rowid ? 1 : 0, n_value_cols, st.win_wire,
+		                                 st.win_wire_bytes, &ticket));
+		Check(cubit_gpu_fetch_wait(ticket));
+		return;
+	}
 	st.win_cols.resize(st.column_ids.size(), nullptr);
 	auto pinned = [](void *&p) {
 		if (!p) {
@@ -177,13 +200,30 @@ void CubitScanFunction(const CubitScanBindData &bind, CubitScanGlobalState &st, 
 	const idx_t scan_count = std::min<idx_t>(STANDARD_VECTOR_SIZE, st.win_end - st.offset);
 	const idx_t rel = st.offset - st.win_begin;
 	uint32_t value_col = 0;
+	bool has_rowid = false;
+	for (auto c : st.column_ids) {
+		has_rowid = has_rowid || c == COLUMN_IDENTIFIER_ROW_ID;
+	}
+	auto unpack = [&](uint32_t stream, void *dst, uint32_t elem) {
+		if (cubit_wire_unpack_chunk(st.win_wire, stream, rel / STANDARD_VECTOR_SIZE, dst, elem) != (int)scan_count) {
+			throw InternalException("malformed wire window");
+		}
+	};
 	for (size_t i = 0; i < st.column_ids.size(); i++) {
 		output.data[i].all_valid = true;
 		if (st.column_ids[i] == COLUMN_IDENTIFIER_ROW_ID) {
-			memcpy(output.data[i].Raw(), st.win_rowids + rel, scan_count * sizeof(row_t));
+			if (st.narrow_wire) {
+				unpack(0, output.data[i].Raw(), 8);
+			} else {
+				memcpy(output.data[i].Raw(), st.win_rowids + rel, scan_count * sizeof(row_t));
+			}
 		} else {
 			const size_t w = (size_t)st.types[i];
-			memcpy(output.data[i].Raw(), st.win_cols[i] + rel * w, scan_count * w);
+			if (st.narrow_wire) {
+				unpack((has_rowid ? 1u : 0u) + value_col, output.data[i].Raw(), (uint32_t)w);
+			} else {
+				memcpy(output.data[i].Raw(), st.win_cols[i] + rel * w, scan_count * w);
+			}
 			// validity of the probed values (StandardColumnData::FetchRow: validity.FetchRow + data)
 			int all = 1;
 			Check(cubit_gpu_fetch_validity(st.result, value_col++, st.offset, scan_count, output.data[i].validity, &all));

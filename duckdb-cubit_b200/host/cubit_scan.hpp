@@ -51,6 +51,12 @@ struct CubitScanGlobalState { // GlobalTableFunctionState
 	idx_t win_begin = 0, win_end = 0;
 	row_t *win_rowids = nullptr;
 	std::vector<uint8_t *> win_cols; // one slot per column_ids entry (nullptr for the rowid slot)
+	// the same window in the narrow wire format (include/cubit_gpu_wire.h): the device writes per-DataChunk frames
+	// of base + 1/2/4/8-byte deltas into it and GetData widens one chunk straight into the output vectors.  Used
+	// whenever the result lives on one device; a sharded result keeps the wide copies above.
+	void *win_wire = nullptr;
+	uint64_t win_wire_bytes = 0;
+	bool narrow_wire = false;
 };
 
 std::unique_ptr<CubitScanBindData> CubitScanBind(CubitTable &table, std::vector<CubitPredicate> predicates,

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CUBIT_GPU_ABI_VERSION 4
+#define CUBIT_GPU_ABI_VERSION 5
 
 /* error codes */
 #define CUBIT_OK 0
@@ -346,6 +346,48 @@ int cubit_gpu_fetch(cubit_gpu_result *r, uint64_t offset, uint64_t n, int64_t *h
 int cubit_gpu_fetch_async(cubit_gpu_result *r, uint64_t offset, uint64_t n, int64_t *host_rowids, uint32_t n_cols,
                           void *const *host_cols, cubit_gpu_fetch_ticket **ticket);
 int cubit_gpu_fetch_wait(cubit_gpu_fetch_ticket *ticket);
+/* ---- narrow-wire hand-off (include/cubit_gpu_wire.h has the format and the inline unpacker) -----------------
+ * Result rows [offset, offset+n) as ONE wire: per DataChunk (2048 rows) and stream an int64 base + deltas of the
+ * narrowest width that holds the chunk's range, written by the GPU straight into `host_wire` (zero-copy stores, so
+ * only the narrowed bytes cross PCIe: 2-6 bytes per row and stream on sorted row IDs and FOR-friendly columns
+ * instead of 8).  with_rowids != 0 puts the row IDs in stream 0; then the first n_cols projected columns follow.
+ * host_wire must be page-locked (cubit_gpu_alloc_host / cudaHostAlloc / cudaHostRegister — CUBIT_EINVAL otherwise:
+ * the device writes it directly) and hold cubit_wire_bytes(n, streams) bytes; it must stay untouched until
+ * cubit_gpu_fetch_wait(ticket).  Thread-safe like cubit_gpu_fetch_async.  A sharded result has no single device to
+ * write from: CUBIT_ESTATE — use cubit_gpu_drain (which walks the shards) or the wide fetch. */
+int cubit_gpu_fetch_wire_async(cubit_gpu_result *r, uint64_t offset, uint64_t n, int with_rowids, uint32_t n_cols,
+                               void *host_wire, uint64_t host_wire_bytes, cubit_gpu_fetch_ticket **ticket);
+/* exported copies of the inline helpers of cubit_gpu_wire.h (for bindings that cannot include C) */
+uint64_t cubit_gpu_wire_bytes(uint64_t n_rows, uint32_t n_streams);
+uint64_t cubit_gpu_wire_payload_bytes(const void *host_wire);
+int cubit_gpu_wire_unpack(const void *host_wire, uint32_t stream, uint64_t chunk, void *out, uint32_t out_elem);
+
+/* The whole parallel ordered hand-off in one call (the source side of PhysicalTableScan::GetData with
+ * MaxThreads() > 1 and get_batch_index, table_function.hpp:45-67, table_scan.cpp:179-189): n_threads workers claim
+ * windows of window_rows result rows (a multiple of 2048; 0 = default), keep two narrow-wire fetches in flight each,
+ * widen one DataChunk at a time into worker-local vectors and hand it to fn together with its batch index (= the
+ * window index: chunks of one window arrive in order on one worker; sort by (batch_index, row_offset) to restore
+ * the global order).  cols[c] points to n values of the c-th projected column (4- or 8-byte elements as the query
+ * returns them), validity[c] is NULL or the ValidityMask words of the chunk; rowids is NULL unless with_rowids.
+ * A non-zero return of fn stops the drain (CUBIT_ESTATE).  fn == NULL is the built-in checksum consumer: every
+ * chunk is widened and summed (wrapping 64-bit sums of the row IDs and of every column's bit patterns widened to
+ * 64 bits) — a consumer that reads every delivered value, for tests and bench.py.  Works on sharded results. */
+typedef int (*cubit_chunk_fn)(void *ctx, uint32_t worker, uint64_t batch_index, uint64_t row_offset, uint32_t n,
+                              const int64_t *rowids, const void *const *cols, const uint64_t *const *validity);
+typedef struct cubit_drain_stats {
+	uint64_t rows;       /* rows delivered                                        */
+	uint64_t chunks;     /* DataChunks delivered                                  */
+	uint64_t windows;
+	uint64_t wire_bytes; /* bytes that crossed PCIe (directories + written slots) */
+	uint64_t wide_bytes; /* what the wide hand-off would have moved               */
+	uint64_t sum_rowids; /* checksum consumer: wrapping sums                      */
+	uint64_t sum_cols[CUBIT_MAX_PROBE_COLS];
+	uint32_t workers;
+	uint32_t reserved;
+} cubit_drain_stats;
+int cubit_gpu_drain(cubit_gpu_result *r, int with_rowids, uint32_t n_cols, uint32_t n_threads, uint64_t window_rows,
+                    cubit_chunk_fn fn, void *ctx, cubit_drain_stats *stats);
+
 /* Multi-process reduce (one rank per GPU): ADD this result's (count, 128-bit sum) to device_dst[0..5)
  * as five int64 limbs — count, sum bits [0,32), [32,64), [64,96), signed [96,128) — on the device, in stream
  * order behind the query, so the caller can hand device_dst to one ncclAllReduce(sum) without the aggregates

@@ -75,6 +75,7 @@
 #include "duckdb/transaction/meta_transaction.hpp"
 
 #include "cubit_gpu.h"
+#include "cubit_gpu_wire.h"
 
 #include <atomic>
 #include <cstdio>
@@ -200,11 +201,41 @@ struct CubitGpuTable {
 			host_pool.push_back(p);
 		}
 	}
+	// narrow-wire windows (their size depends on the number of streams)
+	vector<std::pair<void *, uint64_t>> wire_pool;
+	void *AcquireWire(uint64_t bytes) {
+		{
+			std::lock_guard<std::mutex> lk(pool_lock);
+			for (idx_t i = 0; i < wire_pool.size(); i++) {
+				if (wire_pool[i].second >= bytes) {
+					void *p = wire_pool[i].first;
+					wire_pool[i] = wire_pool.back();
+					wire_pool.pop_back();
+					return p;
+				}
+			}
+		}
+		void *p = nullptr;
+		if (cubit_gpu_alloc_host(bytes, &p) != CUBIT_OK) {
+			throw InvalidInputException("cubit_gpu: %s", cubit_gpu_last_error());
+		}
+		return p;
+	}
+	void ReleaseWire(void *p, uint64_t bytes) {
+		if (p) {
+			std::lock_guard<std::mutex> lk(pool_lock);
+			wire_pool.emplace_back(p, bytes);
+		}
+	}
 	void Unload() {
 		for (auto p : host_pool) {
 			cubit_gpu_free_host(p);
 		}
 		host_pool.clear();
+		for (auto &w : wire_pool) {
+			cubit_gpu_free_host(w.first);
+		}
+		wire_pool.clear();
 		cubit_gpu_destroy(handle);
 		handle = nullptr;
 		indexes.clear();
@@ -1241,6 +1272,7 @@ struct CubitScanBindData : public TableFunctionData {
 // ordered sinks sort by, the pattern of seq_scan's row-group batches, table_scan.cpp:179-189), and while it serves
 // one window out of its page-locked buffers the copy of the NEXT window it claimed is already in flight
 // (cubit_gpu_fetch_async on the library's copy streams) — two buffer sets per worker, no synchronise per chunk.
+static_assert(STANDARD_VECTOR_SIZE == CUBIT_WIRE_CHUNK, "a wire frame is one DataChunk");
 struct CubitScanGlobalState : public GlobalTableFunctionState {
 	cubit_gpu_result *result = nullptr;
 	vector<column_t> column_ids;
@@ -1252,6 +1284,11 @@ struct CubitScanGlobalState : public GlobalTableFunctionState {
 	bool want_rowid = false;
 	idx_t n_value_cols = 0;
 	vector<bool> col_has_nulls; // per projected value column: the result carries a validity mask for it
+	// rows leave the GPU in the narrow wire format (cubit_gpu_wire.h: per DataChunk a base + 1/2/4/8-byte deltas the
+	// device writes straight into the page-locked window; widened into the output vectors one chunk at a time).  A
+	// sharded result has no single device to write a wire from and keeps the wide copies.
+	bool narrow_wire = false;
+	uint64_t wire_bytes = 0;
 	static constexpr idx_t WINDOW_ROWS = 64 * STANDARD_VECTOR_SIZE;
 	std::atomic<idx_t> next_window {0};
 	idx_t n_windows = 0;
@@ -1272,6 +1309,8 @@ struct CubitScanLocalState : public LocalTableFunctionState {
 		vector<int64_t *> cols;
 		vector<vector<uint64_t>> validity; // ValidityMask words of the window, empty = no NULL in the window
 		cubit_gpu_fetch_ticket *ticket = nullptr;
+		void *wire = nullptr; // narrow-wire window (instead of rowids / cols)
+		uint64_t wire_bytes = 0;
 	};
 	Window win[2];
 	int cur = 0;          // the window being served
@@ -1286,6 +1325,7 @@ struct CubitScanLocalState : public LocalTableFunctionState {
 				for (auto p : w.cols) {
 					pool_owner->ReleaseWindow(p);
 				}
+				pool_owner->ReleaseWire(w.wire, w.wire_bytes);
 			}
 		}
 	}
@@ -1377,6 +1417,13 @@ static unique_ptr<GlobalTableFunctionState> CubitRunQuery(const CubitScanBindDat
 		state->col_has_nulls.push_back(n_shards > 1 || info.d_validity[c] != nullptr);
 	}
 	state->n_windows = (state->row_count + CubitScanGlobalState::WINDOW_ROWS - 1) / CubitScanGlobalState::WINDOW_ROWS;
+	{
+		uint32_t n_shards = 1;
+		cubit_gpu_shard_count(gpu.handle, &n_shards);
+		const uint32_t streams = NumericCast<uint32_t>((want_rowid ? 1 : 0) + cols.size());
+		state->narrow_wire = n_shards == 1 && streams > 0 && bind.agg_col < 0 && !getenv("CUBIT_WIDE_HANDOFF");
+		state->wire_bytes = cubit_wire_bytes(CubitScanGlobalState::WINDOW_ROWS, streams);
+	}
 	return std::move(state);
 }
 
@@ -1401,16 +1448,26 @@ static void CubitClaimWindow(CubitScanGlobalState &state, CubitScanLocalState &l
 	}
 	w.begin = w.index * CubitScanGlobalState::WINDOW_ROWS;
 	w.end = MinValue<idx_t>(w.begin + CubitScanGlobalState::WINDOW_ROWS, state.row_count);
-	const uint64_t win_bytes = CubitScanGlobalState::WINDOW_ROWS * sizeof(int64_t);
-	while (w.cols.size() < state.n_value_cols) {
-		w.cols.push_back(static_cast<int64_t *>(local.pool_owner->AcquireWindow(win_bytes)));
+	if (state.narrow_wire) {
+		if (!w.wire) {
+			w.wire = local.pool_owner->AcquireWire(state.wire_bytes);
+			w.wire_bytes = state.wire_bytes;
+		}
+		CubitCheck(cubit_gpu_fetch_wire_async(state.result, w.begin, w.end - w.begin, state.want_rowid ? 1 : 0,
+		                                      NumericCast<uint32_t>(state.n_value_cols), w.wire, w.wire_bytes,
+		                                      &w.ticket));
+	} else {
+		const uint64_t win_bytes = CubitScanGlobalState::WINDOW_ROWS * sizeof(int64_t);
+		while (w.cols.size() < state.n_value_cols) {
+			w.cols.push_back(static_cast<int64_t *>(local.pool_owner->AcquireWindow(win_bytes)));
+		}
+		if (state.want_rowid && !w.rowids) {
+			w.rowids = static_cast<int64_t *>(local.pool_owner->AcquireWindow(win_bytes));
+		}
+		vector<void *> ptrs(w.cols.begin(), w.cols.end());
+		CubitCheck(cubit_gpu_fetch_async(state.result, w.begin, w.end - w.begin, state.want_rowid ? w.rowids : nullptr,
+		                                 NumericCast<uint32_t>(ptrs.size()), ptrs.data(), &w.ticket));
 	}
-	if (state.want_rowid && !w.rowids) {
-		w.rowids = static_cast<int64_t *>(local.pool_owner->AcquireWindow(win_bytes));
-	}
-	vector<void *> ptrs(w.cols.begin(), w.cols.end());
-	CubitCheck(cubit_gpu_fetch_async(state.result, w.begin, w.end - w.begin, state.want_rowid ? w.rowids : nullptr,
-	                                 NumericCast<uint32_t>(ptrs.size()), ptrs.data(), &w.ticket));
 	// NULLs: the validity mask of every projected value (StandardColumnData::FetchRow = validity + data) — asked for
 	// only when the query touched a NULL-bearing column at all
 	w.validity.resize(state.n_value_cols);
@@ -1462,13 +1519,27 @@ static void CubitScanFunction(ClientContext &, TableFunctionInput &data_p, DataC
 	const idx_t scan_count = MinValue<idx_t>(STANDARD_VECTOR_SIZE, w->end - local.offset);
 	const idx_t rel = local.offset - w->begin; // a multiple of 2048: word aligned in the window's masks
 	idx_t value_col = 0;
+	const uint64_t wire_chunk = rel / STANDARD_VECTOR_SIZE; // windows are cut at DataChunk boundaries
 	for (idx_t i = 0; i < state.column_ids.size(); i++) {
 		auto dst = FlatVector::GetData<int64_t>(output.data[i]);
 		if (state.column_ids[i] == COLUMN_IDENTIFIER_ROW_ID) {
-			memcpy(dst, w->rowids + rel, scan_count * sizeof(int64_t));
+			if (state.narrow_wire) { // stream 0: widened straight into the output vector
+				if (cubit_wire_unpack_chunk(w->wire, 0, wire_chunk, dst, 8) != int(scan_count)) {
+					throw InternalException("cubit: malformed wire window");
+				}
+			} else {
+				memcpy(dst, w->rowids + rel, scan_count * sizeof(int64_t));
+			}
 			continue;
 		}
-		memcpy(dst, w->cols[value_col] + rel, scan_count * sizeof(int64_t));
+		if (state.narrow_wire) {
+			const uint32_t stream = NumericCast<uint32_t>((state.want_rowid ? 1 : 0) + value_col);
+			if (cubit_wire_unpack_chunk(w->wire, stream, wire_chunk, dst, 8) != int(scan_count)) {
+				throw InternalException("cubit: malformed wire window");
+			}
+		} else {
+			memcpy(dst, w->cols[value_col] + rel, scan_count * sizeof(int64_t));
+		}
 		auto &words = w->validity[value_col];
 		if (!words.empty()) {
 			auto &mask = FlatVector::Validity(output.data[i]);

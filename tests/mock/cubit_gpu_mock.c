@@ -4,6 +4,7 @@
  * be exercised end-to-end through real reference SQL in the GPU-less build container
  * (tests/test_duckdb_integration.py).  It is never built into, linked with or loaded by the product. */
 #include "cubit_gpu.h"
+#include "cubit_gpu_wire.h"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -269,6 +270,47 @@ int cubit_gpu_fetch_async(cubit_gpu_result *r, uint64_t offset, uint64_t n, int6
 	return cubit_gpu_fetch(r, offset, n, host_rowids, n_cols, host_cols);
 }
 int cubit_gpu_fetch_wait(cubit_gpu_fetch_ticket *ticket) { free(ticket); return CUBIT_OK; }
+/* narrow wire (include/cubit_gpu_wire.h) written on the CPU: per chunk the narrowest width, like the device does */
+static void mock_wire_stream(void *wire, const cubit_wire_header *h, uint32_t stream, const int64_t *v) {
+	cubit_wire_dir *dir = (cubit_wire_dir *)((char *)wire + sizeof(cubit_wire_header));
+	for (uint64_t c = 0; c < h->n_chunks; c++) {
+		const uint64_t r0 = c * CUBIT_WIRE_CHUNK;
+		const uint32_t n = (uint32_t)(h->n_rows - r0 < CUBIT_WIRE_CHUNK ? h->n_rows - r0 : CUBIT_WIRE_CHUNK);
+		int64_t lo = v[r0], hi = v[r0];
+		for (uint32_t i = 1; i < n; i++) { if (v[r0 + i] < lo) lo = v[r0 + i]; if (v[r0 + i] > hi) hi = v[r0 + i]; }
+		const uint64_t range = (uint64_t)hi - (uint64_t)lo;
+		const uint32_t w = range == 0 ? 0 : range < 256 ? 1 : range < 65536 ? 2 : range < (1ull << 32) ? 4 : 8;
+		const uint64_t slot = (uint64_t)stream * h->n_chunks + c;
+		dir[slot].base = lo; dir[slot].width = w; dir[slot].n = n;
+		unsigned char *dst = (unsigned char *)wire + h->data_offset + slot * CUBIT_WIRE_SLOT_BYTES;
+		for (uint32_t i = 0; i < n; i++) {
+			const uint64_t d = (uint64_t)v[r0 + i] - (uint64_t)lo;
+			memcpy(dst + (size_t)i * w, &d, w); /* little endian */
+		}
+	}
+}
+int cubit_gpu_fetch_wire_async(cubit_gpu_result *r, uint64_t offset, uint64_t n, int with_rowids, uint32_t n_cols,
+                               void *host_wire, uint64_t host_wire_bytes, cubit_gpu_fetch_ticket **ticket) {
+	const uint32_t streams = (with_rowids ? 1u : 0u) + n_cols;
+	if (offset + n > r->count || n_cols > r->n_cols || !streams || host_wire_bytes < cubit_wire_bytes(n, streams)) {
+		snprintf(g_err, sizeof g_err, "mock: bad wire fetch"); return CUBIT_EINVAL;
+	}
+	cubit_wire_header *h = (cubit_wire_header *)host_wire;
+	memset(h, 0, sizeof *h);
+	h->magic = CUBIT_WIRE_MAGIC; h->n_streams = streams; h->n_rows = n;
+	h->n_chunks = (n + CUBIT_WIRE_CHUNK - 1) / CUBIT_WIRE_CHUNK;
+	h->data_offset = (sizeof *h + (uint64_t)streams * h->n_chunks * sizeof(cubit_wire_dir) + 255) & ~255ull;
+	uint32_t s = 0;
+	if (with_rowids) { h->elem[s] = 8; mock_wire_stream(host_wire, h, s++, r->ids + offset); }
+	for (uint32_t c = 0; c < n_cols; c++) { h->elem[s] = 8; mock_wire_stream(host_wire, h, s++, r->vals[c] + offset); }
+	*ticket = calloc(1, sizeof(**ticket));
+	return CUBIT_OK;
+}
+uint64_t cubit_gpu_wire_bytes(uint64_t n_rows, uint32_t n_streams) { return cubit_wire_bytes(n_rows, n_streams); }
+uint64_t cubit_gpu_wire_payload_bytes(const void *w) { return cubit_wire_payload_bytes(w); }
+int cubit_gpu_wire_unpack(const void *w, uint32_t stream, uint64_t chunk, void *out, uint32_t out_elem) {
+	return cubit_wire_unpack_chunk(w, stream, chunk, out, out_elem);
+}
 int cubit_gpu_fetch_validity(cubit_gpu_result *r, uint32_t col, uint64_t offset, uint64_t n, uint64_t *host_words,
                              int *all_valid) {
 	if (offset + n > r->count || col >= r->n_cols) { snprintf(g_err, sizeof g_err, "mock: bad fetch"); return CUBIT_EINVAL; }

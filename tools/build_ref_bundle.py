@@ -36,7 +36,7 @@ def main():
     for exe, src in (("duckdb_sql_gpu_test", "duckdb_sql_test.cpp"), ("duckdb_config1", "duckdb_config1.cpp")):
         src = os.path.join(ROOT, "tests", "cpp", src)
         dst = os.path.join(OUT, exe)
-        if stale(dst, [glue, hdr, src]):
+        if stale(dst, [glue, hdr, os.path.join(ROOT, "include", "cubit_gpu_wire.h"), src]):
             subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", REF_INC, "-I", os.path.join(ROOT, "include"), glue, src,
                                    "-o", dst, "-L", OUT, "-lduckdb", "-L", os.path.join(ROOT, "duckdb-cubit_b200"),
                                    "-lcubit_gpu", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../../duckdb-cubit_b200",

@@ -25,7 +25,7 @@ MAX_STREAMS = 64
 MAX_PROBE_COLS = 8
 Q_ROWIDS, Q_BITVECTOR, Q_VALUES, Q_TIMING, Q_UNFUSED, Q_ASYNC, Q_FUSE_PROBE = 1, 2, 4, 8, 16, 32, 64
 PROBE_NONE, PROBE_FUSED, PROBE_BITS, PROBE_GATHER, PROBE_DENSE = 0, 1, 2, 3, 4
-SCAN_RING, SCAN_TWO_PASS, SCAN_NONE = 0, 1, 2
+SCAN_RING, SCAN_TWO_PASS, SCAN_NONE, SCAN_LOOKBACK = 0, 1, 2, 3
 AGG_NONE, AGG_SUM, AGG_SUM_PROD, AGG_SUM_F64 = 0, 1, 2, 3
 
 # every symbol include/cubit_gpu.h declares (tests check the library exports all of them)

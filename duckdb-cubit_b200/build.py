@@ -46,9 +46,10 @@ def _run(cmd, verbose):
 def build_gpu(verbose=False, ptxas_info=False):
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, "kernels.h"), os.path.join(CSRC, "scan_common.cuh"), os.path.join(CSRC, "col_ref.cuh"),
-            os.path.join(CSRC, "table.h"), os.path.join(ROOT, "include", "cubit_gpu.h")]
+            os.path.join(CSRC, "table.h"), os.path.join(ROOT, "include", "cubit_gpu.h"),
+            os.path.join(ROOT, "include", "cubit_gpu_wire.h")]
     units = ["scan_kernel.cu", "aux_kernels.cu", "column_decode.cu", "wah_decode.cu", "delta_kernels.cu",
-             "container_kernels.cu", "probe_dense_kernel.cu", "small_scan_kernels.cu", "cubit_gpu.cu", "cubit_columns.cu", "cubit_delta.cu", "cubit_persist.cu",
+             "container_kernels.cu", "probe_dense_kernel.cu", "small_scan_kernels.cu", "lookback_scan_kernel.cu", "cubit_gpu.cu", "cubit_columns.cu", "cubit_delta.cu", "cubit_persist.cu",
              "cubit_query.cu", "cubit_sharded.cu", "cubit_wire.cu"]
     objs = []
     jobs = []
@@ -74,6 +75,7 @@ def build_host(verbose=False):
         return None
     hdrs = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".hpp")]
     hdrs.append(os.path.join(ROOT, "include", "cubit_gpu.h"))
+    hdrs.append(os.path.join(ROOT, "include", "cubit_gpu_wire.h"))
     lib = os.path.join(HERE, "libcubit_host.so")
     if _stale(lib, srcs + hdrs):
         _run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-I", os.path.join(ROOT, "include"),

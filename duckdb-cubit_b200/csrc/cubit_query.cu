@@ -41,6 +41,9 @@ static void release_result_locked(cubit_gpu_result *r) {
 	if (r->d_q_tmp) {
 		cudaFreeAsync(r->d_q_tmp, s);
 	}
+	if (r->d_wire_stats) {
+		cudaFreeAsync(r->d_wire_stats, s);
+	}
 	for (auto &p : r->d_vals) {
 		if (p) {
 			cudaFreeAsync(p, s);
@@ -518,6 +521,7 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	sa.partials = partials;
 	sa.hdr = r->d_hdr;
 	uint32_t n_launch = 0;
+	bool lookback = false;
 	if (r->timing) {
 		Q_TRY(cudaEventRecord(r->ev[0], st));
 	}
@@ -536,18 +540,33 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 		ss.q_out = (k > 1 || want_q) ? qbuf : nullptr;
 		ss.q_in = ss.q_out ? ss.q_out : sa.bv[0];
 		ss.count_here = need_ids_buf ? 0 : 1;
-		Q_TRY(launch_small_merge_count(ss, st));
-		n_launch++;
-		if (need_ids_buf) {
+		// with row positions: ONE pass with a decoupled look-back (lookback_scan_kernel.cu) instead of merge + count,
+		// chunk prefix and decode (CUBIT_NO_LOOKBACK=1 keeps the three launches: A/B runs in profiles/r2_small_k.md)
+		lookback = need_ids_buf && getenv("CUBIT_NO_LOOKBACK") == nullptr;
+		if (lookback) {
 			ss.span_excl = dense_probe && want_vals && cap ? span_excl : nullptr;
 			ss.tile_excl = probe_mode == PROBE_BITS && want_vals && !dense_probe ? tile_excl : nullptr;
-			Q_TRY(launch_small_prefix(ss, st));
 			ScanArgs ea;
 			memset(&ea, 0, sizeof(ea));
 			ea.ids_out = (want_ids || separate_probe) && cap ? r->d_ids : nullptr; // positions alone need no row IDs
 			ea.row_base = t->row_base;
-			Q_TRY(launch_small_decode(ss, ea, st));
-			n_launch += 2;
+			ea.ctrl = ctrl_a; // ticket counter + one status word per 32-unit tile (zeroed above)
+			Q_TRY(launch_lookback_scan(ss, ea, st));
+			n_launch++;
+		} else {
+			Q_TRY(launch_small_merge_count(ss, st));
+			n_launch++;
+			if (need_ids_buf) {
+				ss.span_excl = dense_probe && want_vals && cap ? span_excl : nullptr;
+				ss.tile_excl = probe_mode == PROBE_BITS && want_vals && !dense_probe ? tile_excl : nullptr;
+				Q_TRY(launch_small_prefix(ss, st));
+				ScanArgs ea;
+				memset(&ea, 0, sizeof(ea));
+				ea.ids_out = (want_ids || separate_probe) && cap ? r->d_ids : nullptr; // positions alone need no row IDs
+				ea.row_base = t->row_base;
+				Q_TRY(launch_small_decode(ss, ea, st));
+				n_launch += 2;
+			}
 		}
 		sa.q_out = const_cast<uint64_t *>(ss.q_in); // what the probe kernels re-decode
 		sa.tile_excl = ss.tile_excl;
@@ -725,7 +744,8 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	                     : probe_mode == PROBE_GATHER   ? CUBIT_PROBE_GATHER
 	                     : probe_mode == PROBE_FUSED    ? CUBIT_PROBE_FUSED
 	                                                    : CUBIT_PROBE_NONE;
-	r->info.scan_path = probe_on_bv ? CUBIT_SCAN_NONE : (two_pass ? CUBIT_SCAN_TWO_PASS : CUBIT_SCAN_RING);
+	r->info.scan_path = probe_on_bv ? CUBIT_SCAN_NONE
+	                                : (lookback ? CUBIT_SCAN_LOOKBACK : (two_pass ? CUBIT_SCAN_TWO_PASS : CUBIT_SCAN_RING));
 	r->info.n_streams = k;
 	r->info.n_launches = n_launch;
 	r->info.delta_entries = delta_entries;

@@ -8,8 +8,10 @@
 // page-locked window (zero-copy: no staging buffer, no second pass, no host round trip to learn a size), and the
 // consumer widens one chunk at a time into its DataChunk — in cache, right before the next operator reads it.
 //
-//   cubit_wire_pack_kernel      one CTA per (chunk, stream): coalesced load of 2048 values, block min / max, width
-//                               choice, deltas staged in shared memory, contiguous 16-byte stores to host memory
+//   cubit_wire_stats_kernel     one CTA per frame (chunk, stream): coalesced load of 2048 values, block min / max → form
+//   cubit_wire_pack_kernel      one CTA per frame: its offset from the forms before it, deltas / bitmap staged in
+//                               shared memory, contiguous 16-byte stores to host memory — frames end up back to back
+//                               in consumption order, so the host reads one sequential stream
 //   cubit_gpu_fetch_wire_async  enqueue it on a copy stream behind the query
 //   cubit_gpu_drain             n worker threads: claim window → two wires in flight → unpack chunk → callback
 #include "table.h"
@@ -17,6 +19,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -25,44 +28,58 @@ using namespace cubit;
 namespace {
 
 constexpr int kPackThreads = 256;
+constexpr uint64_t kWireStatsCap = 1ull << 18; // frames in a result's ring of forms (4 MiB): ≫ the windows in flight
 constexpr int kPerThread = CUBIT_WIRE_CHUNK / kPackThreads; // 8
 
 struct WireArgs {
 	const void *src[CUBIT_MAX_PROBE_COLS + 1]; // first value of the window, per stream
 	uint32_t elem[CUBIT_MAX_PROBE_COLS + 1];   // 4 or 8
+	uint32_t ascending;                        // bit s: stream s is strictly ascending (the row IDs): bitmap frames allowed
+	uint32_t n_streams;
 	uint64_t n_rows;
 	uint64_t n_chunks;
-	cubit_wire_dir *dir; // device-visible address of the wire's directory
-	unsigned char *slots;
+	uint4 *stats;        // device scratch: per frame (base lo, base hi, width field, n), frame = chunk * n_streams + stream
+	cubit_wire_dir *dir; // device-visible address of the wire's directory (host memory)
+	unsigned char *frames; // device-visible address of header.data_offset
 };
 
 __device__ __forceinline__ long long shfl_xor_ll(long long v, int m) {
 	return __shfl_xor_sync(0xffffffffu, v, m);
 }
 
-__global__ void __launch_bounds__(kPackThreads) cubit_wire_pack_kernel(const WireArgs a) {
-	__shared__ __align__(16) unsigned char stage[CUBIT_WIRE_SLOT_BYTES];
-	__shared__ long long s_min[kPackThreads / 32], s_max[kPackThreads / 32];
-	const uint32_t chunk = blockIdx.x, stream = blockIdx.y, t = threadIdx.x;
+__device__ __forceinline__ void load_chunk(const WireArgs &a, uint32_t chunk, uint32_t stream, uint32_t t, uint32_t n,
+                                           long long (&v)[kPerThread]) {
 	const uint64_t row0 = (uint64_t)chunk * CUBIT_WIRE_CHUNK;
-	const uint32_t n = (uint32_t)min((uint64_t)CUBIT_WIRE_CHUNK, a.n_rows - row0);
-	long long v[kPerThread];
-	long long lo = LLONG_MAX, hi = LLONG_MIN;
 	if (a.elem[stream] == 8) {
 		const long long *s = static_cast<const long long *>(a.src[stream]) + row0;
 #pragma unroll
 		for (int j = 0; j < kPerThread; j++) {
 			const uint32_t i = t + j * kPackThreads;
-			v[j] = i < n ? __ldcs(s + i) : 0;
+			v[j] = i < n ? __ldg(s + i) : 0;
 		}
 	} else {
 		const int *s = static_cast<const int *>(a.src[stream]) + row0;
 #pragma unroll
 		for (int j = 0; j < kPerThread; j++) {
 			const uint32_t i = t + j * kPackThreads;
-			v[j] = i < n ? (long long)__ldcs(s + i) : 0;
+			v[j] = i < n ? (long long)__ldg(s + i) : 0;
 		}
 	}
+}
+
+__device__ __forceinline__ uint32_t frame_bytes(uint32_t width, uint32_t n) {
+	const uint32_t b = (width & 255u) == CUBIT_WIRE_BITMAP ? (width >> 8) * 8u : n * width;
+	return (b + 15u) & ~15u;
+}
+
+// pass 1: the form of every frame (one CTA per frame): block min / max → width, or a bitmap for a dense ascending stream
+__global__ void __launch_bounds__(kPackThreads) cubit_wire_stats_kernel(const WireArgs a) {
+	__shared__ long long s_min[kPackThreads / 32], s_max[kPackThreads / 32];
+	const uint32_t chunk = blockIdx.x, stream = blockIdx.y, t = threadIdx.x;
+	const uint32_t n = (uint32_t)min((uint64_t)CUBIT_WIRE_CHUNK, a.n_rows - (uint64_t)chunk * CUBIT_WIRE_CHUNK);
+	long long v[kPerThread];
+	load_chunk(a, chunk, stream, t, n, v);
+	long long lo = LLONG_MAX, hi = LLONG_MIN;
 #pragma unroll
 	for (int j = 0; j < kPerThread; j++) {
 		if (t + j * kPackThreads < n) {
@@ -80,81 +97,140 @@ __global__ void __launch_bounds__(kPackThreads) cubit_wire_pack_kernel(const Wir
 		s_max[t >> 5] = hi;
 	}
 	__syncthreads();
+	if (t == 0) {
 #pragma unroll
-	for (int w = 0; w < kPackThreads / 32; w++) {
-		lo = min(lo, s_min[w]);
-		hi = max(hi, s_max[w]);
+		for (int w = 0; w < kPackThreads / 32; w++) {
+			lo = min(lo, s_min[w]);
+			hi = max(hi, s_max[w]);
+		}
+		const unsigned long long range = (unsigned long long)hi - (unsigned long long)lo; // true difference, < 2^64
+		uint32_t width = range == 0 ? 0 : range < 256ull ? 1 : range < 65536ull ? 2 : range < (1ull << 32) ? 4 : 8;
+		// a strictly ascending stream of a dense selection is cheaper as a bitmap over [lo, hi] (≥ 2x fewer bytes, else
+		// the slower host decode is not worth it)
+		const uint32_t words = (uint32_t)min(range / 64ull + 1ull, 0xffffffull);
+		if (((a.ascending >> stream) & 1u) && (unsigned long long)words * 16ull <= (unsigned long long)n * width) {
+			width = CUBIT_WIRE_BITMAP | (words << 8);
+		}
+		a.stats[(uint64_t)chunk * a.n_streams + stream] =
+		    make_uint4((unsigned int)(unsigned long long)lo, (unsigned int)((unsigned long long)lo >> 32), width, n);
 	}
-	const unsigned long long range = (unsigned long long)hi - (unsigned long long)lo; // true difference, < 2^64
-	const uint32_t width = range == 0 ? 0 : range < 256ull ? 1 : range < 65536ull ? 2 : range < (1ull << 32) ? 4 : 8;
+}
+
+// pass 2: one CTA per frame: its offset = the padded sizes of all frames before it (≤ 1152 per window: summed by the
+// CTA itself, no scan kernel), deltas / bitmap staged in shared memory, contiguous 16-byte stores into host memory
+__global__ void __launch_bounds__(kPackThreads) cubit_wire_pack_kernel(const WireArgs a) {
+	__shared__ __align__(16) unsigned char stage[CUBIT_WIRE_SLOT_BYTES];
+	__shared__ unsigned long long s_off[kPackThreads / 32];
+	const uint32_t chunk = blockIdx.x, stream = blockIdx.y, t = threadIdx.x;
+	const uint64_t frame = (uint64_t)chunk * a.n_streams + stream;
+	unsigned long long off = 0;
+	for (uint64_t f = t; f < frame; f += kPackThreads) {
+		const uint4 e = __ldg(a.stats + f);
+		off += frame_bytes(e.z, e.w);
+	}
 #pragma unroll
-	for (int j = 0; j < kPerThread; j++) {
-		const uint32_t i = t + j * kPackThreads;
-		const unsigned long long d = (unsigned long long)v[j] - (unsigned long long)lo;
-		if (i < n) {
-			switch (width) {
-			case 1:
-				stage[i] = (unsigned char)d;
-				break;
-			case 2:
-				reinterpret_cast<unsigned short *>(stage)[i] = (unsigned short)d;
-				break;
-			case 4:
-				reinterpret_cast<unsigned int *>(stage)[i] = (unsigned int)d;
-				break;
-			case 8:
-				reinterpret_cast<unsigned long long *>(stage)[i] = d;
-				break;
-			default:
-				break;
+	for (int m = 16; m; m >>= 1) {
+		off += __shfl_xor_sync(0xffffffffu, off, m);
+	}
+	if ((t & 31) == 0) {
+		s_off[t >> 5] = off;
+	}
+	const uint4 me = __ldg(a.stats + frame);
+	const uint32_t width = me.z, n = me.w;
+	const unsigned long long lo = (unsigned long long)me.x | ((unsigned long long)me.y << 32);
+	long long v[kPerThread];
+	load_chunk(a, chunk, stream, t, n, v);
+	if ((width & 255u) == CUBIT_WIRE_BITMAP) {
+		unsigned int *bits = reinterpret_cast<unsigned int *>(stage);
+		for (uint32_t w = t; w < (width >> 8) * 2; w += kPackThreads) {
+			bits[w] = 0;
+		}
+		__syncthreads();
+#pragma unroll
+		for (int j = 0; j < kPerThread; j++) {
+			if (t + j * kPackThreads < n) {
+				const unsigned int d = (unsigned int)((unsigned long long)v[j] - lo);
+				atomicOr(bits + (d >> 5), 1u << (d & 31u));
+			}
+		}
+	} else {
+#pragma unroll
+		for (int j = 0; j < kPerThread; j++) {
+			const uint32_t i = t + j * kPackThreads;
+			const unsigned long long d = (unsigned long long)v[j] - lo;
+			if (i < n) {
+				switch (width) {
+				case 1:
+					stage[i] = (unsigned char)d;
+					break;
+				case 2:
+					reinterpret_cast<unsigned short *>(stage)[i] = (unsigned short)d;
+					break;
+				case 4:
+					reinterpret_cast<unsigned int *>(stage)[i] = (unsigned int)d;
+					break;
+				case 8:
+					reinterpret_cast<unsigned long long *>(stage)[i] = d;
+					break;
+				default:
+					break;
+				}
 			}
 		}
 	}
 	__syncthreads();
-	const uint64_t slot = (uint64_t)stream * a.n_chunks + chunk;
-	// contiguous 16-byte stores: a warp writes 512 consecutive bytes of host memory per instruction (the tail of the
-	// last 16-byte unit is shared-memory garbage the unpacker never reads)
-	const uint32_t units = (n * width + 15) / 16;
-	uint4 *dst = reinterpret_cast<uint4 *>(a.slots + slot * CUBIT_WIRE_SLOT_BYTES);
+	off = 0;
+#pragma unroll
+	for (int w = 0; w < kPackThreads / 32; w++) {
+		off += s_off[w];
+	}
+	// contiguous 16-byte stores: a warp writes 512 consecutive bytes of host memory per instruction (the padding of
+	// the last 16-byte unit is shared-memory garbage the unpacker never reads)
+	const uint32_t units = frame_bytes(width, n) / 16;
+	uint4 *dst = reinterpret_cast<uint4 *>(a.frames + off);
 	const uint4 *src16 = reinterpret_cast<const uint4 *>(stage);
 	for (uint32_t u = t; u < units; u += kPackThreads) {
 		dst[u] = src16[u];
 	}
 	if (t == 0) {
-		uint4 e;
-		e.x = (unsigned int)(unsigned long long)lo;
-		e.y = (unsigned int)((unsigned long long)lo >> 32);
-		e.z = width;
-		e.w = n;
-		reinterpret_cast<uint4 *>(a.dir)[slot] = e;
+		unsigned long long *d = reinterpret_cast<unsigned long long *>(a.dir + frame);
+		d[0] = lo;
+		d[1] = off;
+		d[2] = (unsigned long long)width | ((unsigned long long)n << 32);
 	}
 }
 
 // page-locked wire windows recycled across drains (cudaHostAlloc costs milliseconds)
-void *wire_pool_acquire(cubit_gpu_table *t, uint64_t bytes) {
-	{
-		std::lock_guard<std::mutex> ml(t->meta_mu);
-		for (size_t i = 0; i < t->wire_pool.size(); i++) {
-			if (t->wire_pool[i].second >= bytes) {
-				void *p = t->wire_pool[i].first;
-				t->wire_pool[i] = t->wire_pool.back();
-				t->wire_pool.pop_back();
-				return p;
-			}
-		}
-	}
-	void *p = nullptr;
-	if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
-		cudaGetLastError();
-		return nullptr;
-	}
-	return p;
-}
-
 struct PooledWire {
 	void *p = nullptr;
-	uint64_t bytes = 0;
+	uint64_t bytes = 0; // what the buffer really holds (it goes back to the pool with this, whatever was asked for)
 };
+
+PooledWire wire_pool_acquire(cubit_gpu_table *t, uint64_t bytes) {
+	{
+		std::lock_guard<std::mutex> ml(t->meta_mu);
+		size_t best = SIZE_MAX; // smallest buffer that fits
+		for (size_t i = 0; i < t->wire_pool.size(); i++) {
+			if (t->wire_pool[i].second >= bytes && (best == SIZE_MAX || t->wire_pool[i].second < t->wire_pool[best].second)) {
+				best = i;
+			}
+		}
+		if (best != SIZE_MAX) {
+			PooledWire w {t->wire_pool[best].first, t->wire_pool[best].second};
+			t->wire_pool[best] = t->wire_pool.back();
+			t->wire_pool.pop_back();
+			return w;
+		}
+	}
+	PooledWire w;
+	if (cudaHostAlloc(&w.p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+		cudaGetLastError();
+		w.p = nullptr;
+		return w;
+	}
+	w.bytes = bytes;
+	return w;
+}
 
 } // namespace
 
@@ -246,11 +322,13 @@ extern "C" int cubit_gpu_fetch_wire_async(cubit_gpu_result *r, uint64_t offset, 
 	h->n_streams = n_streams;
 	h->n_rows = n;
 	h->n_chunks = (n + CUBIT_WIRE_CHUNK - 1) / CUBIT_WIRE_CHUNK;
-	h->data_offset = (sizeof(cubit_wire_header) + (uint64_t)n_streams * h->n_chunks * sizeof(cubit_wire_dir) + 255) &
-	                 ~255ull;
+	h->data_offset = cubit_wire_data_offset(h->n_chunks, n_streams);
 	WireArgs a {};
 	uint32_t s = 0;
 	if (with_rowids) {
+		// sorted unique row IDs (art.cpp:974-985) may travel as bitmaps.  Opt-in: on a 16-vCPU host the bit-by-bit
+		// decode costs the workers more time than the saved bus bytes buy (profiles/r2_narrow_wire.md)
+		a.ascending = getenv("CUBIT_WIRE_BITMAP") ? 1u : 0u;
 		a.src[s] = r->d_ids + offset;
 		a.elem[s] = 8;
 		h->elem[s++] = 8;
@@ -263,16 +341,58 @@ extern "C" int cubit_gpu_fetch_wire_async(cubit_gpu_result *r, uint64_t offset, 
 	}
 	a.n_rows = n;
 	a.n_chunks = h->n_chunks;
+	a.n_streams = n_streams;
 	a.dir = reinterpret_cast<cubit_wire_dir *>(dev_wire + sizeof(cubit_wire_header));
-	a.slots = dev_wire + h->data_offset;
+	a.frames = dev_wire + h->data_offset;
 	cubit_gpu_fetch_ticket *tk = new cubit_gpu_fetch_ticket();
 	if (n) {
 		r->copies_in_flight.store(1); // free_result drains the copy streams before the buffers go back to the pool
 		cudaStream_t cs = t->copy_stream[t->next_copy.fetch_add(1) % kCopyStreams];
 		cudaError_t e = cudaStreamWaitEvent(cs, r->ev_done, 0);
+		// the frames' forms between the two passes live in a per-result ring (no allocation per window: sixteen
+		// workers calling cudaMallocAsync / cudaFreeAsync per window serialise in the driver)
+		const uint64_t frames = h->n_chunks * n_streams;
+		uint64_t slot = 256;
+		while (slot < frames) {
+			slot <<= 1;
+		}
+		void *scratch = nullptr;
+		bool own_scratch = false;
+		if (e == cudaSuccess && slot <= kWireStatsCap / 8) {
+			if (!r->d_wire_stats) {
+				std::lock_guard<std::mutex> lk(r->fin_mu);
+				if (!r->d_wire_stats) {
+					void *p = nullptr;
+					e = cudaMallocAsync(&p, kWireStatsCap * sizeof(uint4), cs);
+					if (e == cudaSuccess) {
+						e = cudaStreamSynchronize(cs); // the other copy streams use it too: once per result
+					}
+					if (e == cudaSuccess) {
+						r->d_wire_stats = static_cast<uint4 *>(p);
+					}
+				}
+			}
+			if (e == cudaSuccess) {
+				uint64_t pos;
+				do { // a slot never straddles the end of the ring; the ring is far larger than what can be in flight
+					pos = r->wire_stats_cursor.fetch_add(slot) % kWireStatsCap;
+				} while (pos + slot > kWireStatsCap);
+				scratch = r->d_wire_stats + pos;
+			}
+		} else if (e == cudaSuccess) { // a window of more than 32 Ki frames: its own allocation
+			e = cudaMallocAsync(&scratch, frames * sizeof(uint4), cs);
+			own_scratch = e == cudaSuccess;
+		}
 		if (e == cudaSuccess) {
-			cubit_wire_pack_kernel<<<dim3((unsigned)h->n_chunks, n_streams), kPackThreads, 0, cs>>>(a);
+			a.stats = static_cast<uint4 *>(scratch);
+			const dim3 grid((unsigned)h->n_chunks, n_streams);
+			cubit_wire_stats_kernel<<<grid, kPackThreads, 0, cs>>>(a);
+			cubit_wire_pack_kernel<<<grid, kPackThreads, 0, cs>>>(a);
 			e = cudaGetLastError();
+			if (own_scratch) {
+				cudaFreeAsync(scratch, cs);
+			}
+			t->launches += 2;
 		}
 		if (e == cudaSuccess) {
 			e = cudaEventCreateWithFlags(&tk->ev, cudaEventDisableTiming);
@@ -287,7 +407,6 @@ extern "C" int cubit_gpu_fetch_wire_async(cubit_gpu_result *r, uint64_t offset, 
 			delete tk;
 			CU_TRY(e);
 		}
-		t->launches++;
 	}
 	*ticket = tk;
 	return CUBIT_OK;
@@ -324,6 +443,22 @@ struct DrainLocal {
 	uint64_t sum_cols[CUBIT_MAX_PROBE_COLS] = {};
 };
 
+// wrapping sum with four independent chains (a single chain is one add per cycle: 0.46 ns per value)
+inline uint64_t sum_u64(const uint64_t *p, int n) {
+	uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+	int i = 0;
+	for (; i + 4 <= n; i += 4) {
+		a0 += p[i];
+		a1 += p[i + 1];
+		a2 += p[i + 2];
+		a3 += p[i + 3];
+	}
+	for (; i < n; i++) {
+		a0 += p[i];
+	}
+	return a0 + a1 + a2 + a3;
+}
+
 void drain_fail(DrainShared &sh, int rc, const char *why) {
 	std::lock_guard<std::mutex> lk(sh.err_mu);
 	if (sh.rc.load() == CUBIT_OK) {
@@ -335,12 +470,15 @@ void drain_fail(DrainShared &sh, int rc, const char *why) {
 void drain_worker(DrainShared &sh, uint32_t worker, DrainLocal &out) {
 	struct Slot {
 		void *wire = nullptr;
+		uint64_t wire_cap = 0;
 		cubit_gpu_fetch_ticket *ticket = nullptr;
 		uint64_t index = UINT64_MAX;
 		std::vector<std::vector<uint64_t>> validity;
 	} slot[2];
 	for (auto &s : slot) {
-		s.wire = wire_pool_acquire(sh.pool_owner, sh.wire_bytes_cap);
+		const PooledWire pw = wire_pool_acquire(sh.pool_owner, sh.wire_bytes_cap);
+		s.wire = pw.p;
+		s.wire_cap = pw.bytes;
 		if (!s.wire) {
 			drain_fail(sh, CUBIT_ENOMEM, "page-locked wire window");
 		}
@@ -362,8 +500,7 @@ void drain_worker(DrainShared &sh, uint32_t worker, DrainLocal &out) {
 			return;
 		}
 		const DrainWindow &w = sh.windows[s.index];
-		int rc = cubit_gpu_fetch_wire_async(w.part, w.begin, w.n, sh.with_rowids, sh.n_cols, s.wire, sh.wire_bytes_cap,
-		                                    &s.ticket);
+		int rc = cubit_gpu_fetch_wire_async(w.part, w.begin, w.n, sh.with_rowids, sh.n_cols, s.wire, s.wire_cap, &s.ticket);
 		for (uint32_t c = 0; rc == CUBIT_OK && c < sh.n_cols; c++) {
 			s.validity[c].clear();
 			if (!sh.has_nulls[c]) {
@@ -420,19 +557,12 @@ void drain_worker(DrainShared &sh, uint32_t worker, DrainLocal &out) {
 					}
 				} else { // checksum consumer: reads every delivered value
 					if (sh.with_rowids) {
-						uint64_t acc = 0;
-						for (int i = 0; i < n; i++) {
-							acc += (uint64_t)rowids[i];
-						}
-						out.sum_rowids += acc;
+						out.sum_rowids += sum_u64(reinterpret_cast<const uint64_t *>(rowids.data()), n);
 					}
 					for (uint32_t c = 0; c < sh.n_cols; c++) {
 						uint64_t acc = 0;
 						if (sh.elem[c] == 8) {
-							const uint64_t *p = colbuf[c].data();
-							for (int i = 0; i < n; i++) {
-								acc += p[i];
-							}
+							acc = sum_u64(colbuf[c].data(), n);
 						} else {
 							const uint32_t *p = reinterpret_cast<const uint32_t *>(colbuf[c].data());
 							for (int i = 0; i < n; i++) {
@@ -454,7 +584,7 @@ void drain_worker(DrainShared &sh, uint32_t worker, DrainLocal &out) {
 		cubit_gpu_fetch_wait(s.ticket);
 		if (s.wire) {
 			std::lock_guard<std::mutex> ml(sh.pool_owner->meta_mu);
-			sh.pool_owner->wire_pool.emplace_back(s.wire, sh.wire_bytes_cap);
+			sh.pool_owner->wire_pool.emplace_back(s.wire, s.wire_cap);
 		}
 	}
 }
@@ -484,8 +614,12 @@ extern "C" int cubit_gpu_drain(cubit_gpu_result *r, int with_rowids, uint32_t n_
 	if (!with_rowids && n_cols == 0) {
 		return fail(CUBIT_EINVAL, "nothing to drain: no row IDs and no columns requested");
 	}
-	if (window_rows == 0) {
-		window_rows = 128 * CUBIT_WIRE_CHUNK;
+	if (n_threads == 0) {
+		n_threads = 1;
+	}
+	if (window_rows == 0) { // ≈ 4 windows per worker, between 16 and 256 DataChunks each
+		const uint64_t per = info.count / (4ull * n_threads) / CUBIT_WIRE_CHUNK;
+		window_rows = std::min<uint64_t>(256, std::max<uint64_t>(16, per)) * CUBIT_WIRE_CHUNK;
 	}
 	if (window_rows % CUBIT_WIRE_CHUNK) {
 		return fail(CUBIT_EINVAL, "window_rows must be a multiple of %u", CUBIT_WIRE_CHUNK);
@@ -518,9 +652,6 @@ extern "C" int cubit_gpu_drain(cubit_gpu_result *r, int with_rowids, uint32_t n_
 			sh.windows.push_back(DrainWindow {p, b, n, global_row + b});
 		}
 		global_row += pi.count;
-	}
-	if (n_threads == 0) {
-		n_threads = 1;
 	}
 	n_threads = (uint32_t)std::min<uint64_t>(n_threads, std::max<uint64_t>(1, (sh.windows.size() + 1) / 2));
 	std::vector<DrainLocal> locals(n_threads);

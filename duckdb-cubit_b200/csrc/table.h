@@ -125,7 +125,7 @@ struct Column {
 	}
 };
 
-constexpr int kCopyStreams = 2;
+constexpr int kCopyStreams = 4; // hand-off streams: the gaps between one window's kernels / copies are filled by another's
 constexpr int kAggStreams = 4; // streams for queries whose kernels have no inter-CTA dependency (see plan_and_launch)
 constexpr uint64_t kStageChunk = 16ull << 20;
 
@@ -208,6 +208,9 @@ struct cubit_gpu_result {
 	std::string fin_err;
 	cubit_result_info info = {};
 	std::atomic<uint32_t> copies_in_flight {0};
+	// narrow-wire hand-off (cubit_wire.cu): a ring of per-frame forms between its two kernels, allocated on first use
+	uint4 *d_wire_stats = nullptr;
+	std::atomic<uint64_t> wire_stats_cursor {0};
 	// sharded result: one child per shard, in row order; count_prefix[i] = rows of the children before i
 	std::vector<cubit_gpu_result *> parts;
 	std::vector<uint64_t> count_prefix;

@@ -127,6 +127,7 @@ typedef struct cubit_result_info {
 #define CUBIT_SCAN_RING 0     /* the single-pass ring kernel (fused merge + decode)                          */
 #define CUBIT_SCAN_TWO_PASS 1 /* short queries on large tables: streaming merge + count, then a decode pass  */
 #define CUBIT_SCAN_NONE 2     /* no scan ran: the probe read the one value bitvector itself                  */
+#define CUBIT_SCAN_LOOKBACK 3 /* short queries with row positions on large tables: one pass, decoupled look-back */
 
 /* cubit_result_info.probe_path */
 #define CUBIT_PROBE_NONE 0   /* no column was probed                                                        */

@@ -1298,7 +1298,7 @@ struct CubitScanGlobalState : public GlobalTableFunctionState {
 	}
 	idx_t MaxThreads() const override {
 		// a window is 1-3 MB of PCIe traffic plus 64 memcpy'd DataChunks: worth a worker each, up to a handful
-		return MaxValue<idx_t>(1, MinValue<idx_t>(8, n_windows / 2));
+		return MaxValue<idx_t>(1, MinValue<idx_t>(16, n_windows / 2));
 	}
 };
 

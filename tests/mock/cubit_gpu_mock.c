@@ -270,25 +270,8 @@ int cubit_gpu_fetch_async(cubit_gpu_result *r, uint64_t offset, uint64_t n, int6
 	return cubit_gpu_fetch(r, offset, n, host_rowids, n_cols, host_cols);
 }
 int cubit_gpu_fetch_wait(cubit_gpu_fetch_ticket *ticket) { free(ticket); return CUBIT_OK; }
-/* narrow wire (include/cubit_gpu_wire.h) written on the CPU: per chunk the narrowest width, like the device does */
-static void mock_wire_stream(void *wire, const cubit_wire_header *h, uint32_t stream, const int64_t *v) {
-	cubit_wire_dir *dir = (cubit_wire_dir *)((char *)wire + sizeof(cubit_wire_header));
-	for (uint64_t c = 0; c < h->n_chunks; c++) {
-		const uint64_t r0 = c * CUBIT_WIRE_CHUNK;
-		const uint32_t n = (uint32_t)(h->n_rows - r0 < CUBIT_WIRE_CHUNK ? h->n_rows - r0 : CUBIT_WIRE_CHUNK);
-		int64_t lo = v[r0], hi = v[r0];
-		for (uint32_t i = 1; i < n; i++) { if (v[r0 + i] < lo) lo = v[r0 + i]; if (v[r0 + i] > hi) hi = v[r0 + i]; }
-		const uint64_t range = (uint64_t)hi - (uint64_t)lo;
-		const uint32_t w = range == 0 ? 0 : range < 256 ? 1 : range < 65536 ? 2 : range < (1ull << 32) ? 4 : 8;
-		const uint64_t slot = (uint64_t)stream * h->n_chunks + c;
-		dir[slot].base = lo; dir[slot].width = w; dir[slot].n = n;
-		unsigned char *dst = (unsigned char *)wire + h->data_offset + slot * CUBIT_WIRE_SLOT_BYTES;
-		for (uint32_t i = 0; i < n; i++) {
-			const uint64_t d = (uint64_t)v[r0 + i] - (uint64_t)lo;
-			memcpy(dst + (size_t)i * w, &d, w); /* little endian */
-		}
-	}
-}
+/* narrow wire (include/cubit_gpu_wire.h) written on the CPU: per frame the narrowest width, frames back to back in
+ * chunk-major order, like the device writes them (the mock never uses bitmap frames; delta frames are always valid) */
 int cubit_gpu_fetch_wire_async(cubit_gpu_result *r, uint64_t offset, uint64_t n, int with_rowids, uint32_t n_cols,
                                void *host_wire, uint64_t host_wire_bytes, cubit_gpu_fetch_ticket **ticket) {
 	const uint32_t streams = (with_rowids ? 1u : 0u) + n_cols;
@@ -299,10 +282,29 @@ int cubit_gpu_fetch_wire_async(cubit_gpu_result *r, uint64_t offset, uint64_t n,
 	memset(h, 0, sizeof *h);
 	h->magic = CUBIT_WIRE_MAGIC; h->n_streams = streams; h->n_rows = n;
 	h->n_chunks = (n + CUBIT_WIRE_CHUNK - 1) / CUBIT_WIRE_CHUNK;
-	h->data_offset = (sizeof *h + (uint64_t)streams * h->n_chunks * sizeof(cubit_wire_dir) + 255) & ~255ull;
-	uint32_t s = 0;
-	if (with_rowids) { h->elem[s] = 8; mock_wire_stream(host_wire, h, s++, r->ids + offset); }
-	for (uint32_t c = 0; c < n_cols; c++) { h->elem[s] = 8; mock_wire_stream(host_wire, h, s++, r->vals[c] + offset); }
+	h->data_offset = cubit_wire_data_offset(h->n_chunks, streams);
+	cubit_wire_dir *dir = (cubit_wire_dir *)((char *)host_wire + sizeof(cubit_wire_header));
+	uint64_t at = 0;
+	for (uint64_t c = 0; c < h->n_chunks; c++) {
+		for (uint32_t s = 0; s < streams; s++) {
+			h->elem[s] = 8;
+			const int64_t *v = ((with_rowids && s == 0) ? r->ids : r->vals[s - (with_rowids ? 1 : 0)]) + offset;
+			const uint64_t r0 = c * CUBIT_WIRE_CHUNK;
+			const uint32_t cn = (uint32_t)(n - r0 < CUBIT_WIRE_CHUNK ? n - r0 : CUBIT_WIRE_CHUNK);
+			int64_t lo = v[r0], hi = v[r0];
+			for (uint32_t i = 1; i < cn; i++) { if (v[r0 + i] < lo) lo = v[r0 + i]; if (v[r0 + i] > hi) hi = v[r0 + i]; }
+			const uint64_t range = (uint64_t)hi - (uint64_t)lo;
+			const uint32_t w = range == 0 ? 0 : range < 256 ? 1 : range < 65536 ? 2 : range < (1ull << 32) ? 4 : 8;
+			cubit_wire_dir *d = dir + c * streams + s;
+			d->base = lo; d->offset = at; d->width = w; d->n = cn;
+			unsigned char *dst = (unsigned char *)host_wire + h->data_offset + at;
+			for (uint32_t i = 0; i < cn; i++) {
+				const uint64_t delta = (uint64_t)v[r0 + i] - (uint64_t)lo;
+				memcpy(dst + (size_t)i * w, &delta, w); /* little endian */
+			}
+			at += ((uint64_t)cn * w + 15) & ~15ull;
+		}
+	}
 	*ticket = calloc(1, sizeof(**ticket));
 	return CUBIT_OK;
 }

@@ -1,5 +1,6 @@
 """GPU: short queries (k <= 4 bitvectors, no pending deltas) as two streaming passes — merge + count, then decode
-(small_scan_kernels.cu) — against the oracle, through the C-ABI.  The planner takes this path on large tables only;
+(small_scan_kernels.cu) — or, with row positions, as ONE pass with a decoupled look-back (lookback_scan_kernel.cu;
+CUBIT_NO_LOOKBACK=1 keeps the passes), against the oracle, through the C-ABI.  The planner takes this path on large tables only;
 CUBIT_TWO_PASS_MIN_ROWS=0 forces it here at sizes the oracle finishes in seconds.  Bit-exact: COUNT, row IDs, the
 merged bitvector, probed values (gather, bit-driven and dense probes behind it), aggregates."""
 import os
@@ -23,8 +24,12 @@ def force_two_pass():
         os.environ["CUBIT_TWO_PASS_MIN_ROWS"] = old
 
 
-@pytest.mark.parametrize("seg_bits,n", [(65536, 1_300_017), (32768, 900_001), (131072, 700_003), (65536, 5_000)])
-def test_two_pass_scan_matches_oracle(cubit, force_two_pass, seg_bits, n):
+@pytest.mark.parametrize("lookback", [True, False])
+@pytest.mark.parametrize("seg_bits,n", [(65536, 1_300_017), (32768, 900_001), (131072, 700_003), (65536, 5_000),
+                                        (65536, 262_144 * 3), (65536, 262_144 * 3 + 1)])
+def test_two_pass_scan_matches_oracle(cubit, force_two_pass, monkeypatch, seg_bits, n, lookback):
+    if not lookback:
+        monkeypatch.setenv("CUBIT_NO_LOOKBACK", "1")
     rng = np.random.default_rng(n)
     base = seg_bits * 3
     key = rng.integers(0, 12, n).astype(np.int32)
@@ -58,7 +63,7 @@ def test_two_pass_scan_matches_oracle(cubit, force_two_pass, seg_bits, n):
         wp, ws = oracle.probe(want, pay, base), oracle.probe(want, small, base)
         k = sum(len(g) for g in groups)
         # the planner's rule: with row positions k <= 2, count / bitvector / aggregate only k <= 3
-        with_pos = cubit.SCAN_TWO_PASS if k <= 2 else cubit.SCAN_RING
+        with_pos = (cubit.SCAN_LOOKBACK if lookback else cubit.SCAN_TWO_PASS) if k <= 2 else cubit.SCAN_RING
         no_pos = cubit.SCAN_TWO_PASS if k <= 3 else cubit.SCAN_RING
         with t.query(groups, flags=cubit.Q_ROWIDS) as r:
             assert r.info.scan_path == with_pos and r.count == len(want)

@@ -15,37 +15,70 @@ SLOT = 16384
 MAGIC = 0x45524957
 
 
-def _encode_wire(streams, widths=None):
+BITMAP = 255
+
+
+def _frame(part, ascending):
+    """(width field, payload bytes) of one chunk by the documented rule"""
+    lo, hi = int(part.min()), int(part.max())
+    rng = hi - lo
+    w = 0 if rng == 0 else 1 if rng < 256 else 2 if rng < 65536 else 4 if rng < 2**32 else 8
+    words = rng // 64 + 1
+    if ascending and words * 16 <= len(part) * w:
+        return BITMAP | (words << 8), words * 8
+    return w, len(part) * w
+
+
+def _encode_wire(streams, widths=None, ascending=()):
     """independent encoder of the format: streams = list of int64/int32 arrays of equal length"""
     n = len(streams[0])
     c = (n + CHUNK - 1) // CHUNK
     s = len(streams)
-    dir_end = 64 + s * c * 16
-    data_off = (dir_end + 255) & ~255
+    data_off = (64 + s * c * 24 + 255) & ~255
     wire = np.zeros(data_off + s * c * SLOT, dtype=np.uint8)
     hdr = np.zeros(8, dtype=np.uint64)
     hdr[0] = MAGIC | (s << 32)
     hdr[1], hdr[2], hdr[3] = n, c, data_off
     wire[:64] = hdr.view(np.uint8)
-    for si, a in enumerate(streams):
-        wire[32 + si] = a.dtype.itemsize
-        v = a.astype(np.int64)
-        for ci in range(c):
-            part = v[ci * CHUNK:(ci + 1) * CHUNK]
-            lo, hi = int(part.min()), int(part.max())
-            rng = hi - lo
-            w = 0 if rng == 0 else 1 if rng < 256 else 2 if rng < 65536 else 4 if rng < 2**32 else 8
+    at = 0
+    for ci in range(c):
+        for si, a in enumerate(streams):
+            wire[32 + si] = a.dtype.itemsize
+            part = a.astype(np.int64)[ci * CHUNK:(ci + 1) * CHUNK]
+            lo = int(part.min())
+            w, _ = _frame(part, si in ascending and widths is None)
             if widths is not None:
                 w = max(w, widths[si])
-            slot = si * c + ci
-            d = 64 + slot * 16
-            wire[d:d + 8] = np.array([lo], dtype=np.int64).view(np.uint8)
-            wire[d + 8:d + 16] = np.array([w, len(part)], dtype=np.uint32).view(np.uint8)
-            if w:
-                delta = (part.view(np.uint64) - np.uint64(lo & (2**64 - 1))).astype({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[w])
-                o = data_off + slot * SLOT
-                wire[o:o + len(part) * w] = delta.view(np.uint8)
+            d = 64 + (ci * s + si) * 24
+            wire[d:d + 16] = np.array([lo, at], dtype=np.int64).view(np.uint8)
+            wire[d + 16:d + 24] = np.array([w, len(part)], dtype=np.uint32).view(np.uint8)
+            o = data_off + at
+            if w & 255 == BITMAP:
+                bits = np.zeros((w >> 8) * 64, dtype=np.uint8)
+                bits[part - lo] = 1
+                nbytes = (w >> 8) * 8
+                wire[o:o + nbytes] = np.packbits(bits, bitorder="little")
+            else:
+                nbytes = len(part) * w
+                if w:
+                    delta = (part.view(np.uint64) - np.uint64(lo & (2**64 - 1))).astype(
+                        {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[w])
+                    wire[o:o + nbytes] = delta.view(np.uint8)
+            at += (nbytes + 15) & ~15
     return wire
+
+
+def _dir(wire, n_streams, n):
+    """→ base[stream, chunk], width field[stream, chunk], n[stream, chunk]; checks the frames are back to back"""
+    c = (n + CHUNK - 1) // CHUNK
+    d = wire[64:64 + n_streams * c * 24]
+    q = d.view(np.int64).reshape(c, n_streams, 3)
+    wn = d.view(np.uint32).reshape(c, n_streams, 6)
+    width, cnt = wn[:, :, 4], wn[:, :, 5]
+    nbytes = np.where((width & 255) == BITMAP, (width >> 8) * 8, cnt * width)
+    padded = (nbytes.astype(np.int64) + 15) & ~15
+    assert np.array_equal(q[:, :, 1].ravel(), np.concatenate([[0], np.cumsum(padded.ravel())[:-1]]))
+    return q[:, :, 0].T, width.T, cnt.T
 
 
 @pytest.mark.parametrize("n", [1, 2047, 2048, 2049, 10_000])
@@ -64,12 +97,34 @@ def test_unpack_matches_independent_encoder(cubit, n):
         got = np.concatenate([cubit.wire_unpack(wire, si, c, a.dtype) for c in range((n + CHUNK - 1) // CHUNK)])
         assert np.array_equal(got, a), si
     assert len(cubit.wire_unpack(wire, 0, (n + CHUNK - 1) // CHUNK)) == 0  # past the window: empty, not an error
+    # dense ascending streams as bitmap frames (one row in 2 or 4: bitmap; one in 50: deltas)
+    for step in (2, 4, 50):
+        asc = (np.cumsum(rng.integers(1, 2 * step, n)) + 2**40).astype(np.int64)
+        w2 = _encode_wire([asc, small], ascending=(0,))
+        _, width, _ = _dir(w2, 2, n)
+        assert ((width[0] & 255) == BITMAP).any() == (step < 50 and n >= 2047), (step, n)
+        got = np.concatenate([cubit.wire_unpack(w2, 0, c) for c in range((n + CHUNK - 1) // CHUNK)])
+        assert np.array_equal(got, asc)
+        assert np.array_equal(cubit.wire_unpack(w2, 0, 0, np.int32), asc[:CHUNK].astype(np.int32))
+        assert np.array_equal(cubit.wire_unpack(w2, 1, 0), small[:CHUNK])
     # a wider-than-needed width is still a valid wire (what the CPU mock of the ABI writes)
     wide = _encode_wire(streams, widths=[8] * len(streams))
     for si, a in enumerate(streams):
         assert np.array_equal(cubit.wire_unpack(wide, si, 0, a.dtype), a[:CHUNK])
     # int64 stream read as 4-byte values: the low halves (what a narrowing caller would get)
     assert np.array_equal(cubit.wire_unpack(wire, 2, 0, np.int32), small[:CHUNK].astype(np.int32))
+
+
+def test_scalar_widening_path_gives_the_same_answers():
+    """the AVX2 loops are an optimisation of the scalar ones: run the encoder test again with them switched off"""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, CUBIT_WIRE_SCALAR="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
+                        "unpack_matches_independent_encoder"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "5 passed" in r.stdout, r.stdout[-2000:]
 
 
 def test_unpack_rejects_malformed_wires(cubit):
@@ -82,24 +137,28 @@ def test_unpack_rejects_malformed_wires(cubit):
     with pytest.raises(cubit.CubitError):
         cubit.wire_unpack(wire, 1, 0)  # stream out of range
     bad = wire.copy()
-    bad[64 + 8] = 3  # width 3 does not exist
+    bad[64 + 16] = 3  # width 3 does not exist
     with pytest.raises(cubit.CubitError):
         cubit.wire_unpack(bad, 0, 0)
     bad = wire.copy()
-    bad[64 + 12:64 + 16] = np.array([4096], dtype=np.uint32).view(np.uint8)  # more values than a chunk holds
+    bad[64 + 20:64 + 24] = np.array([4096], dtype=np.uint32).view(np.uint8)  # more values than a chunk holds
+    with pytest.raises(cubit.CubitError):
+        cubit.wire_unpack(bad, 0, 0)
+    # a bitmap frame that holds fewer set bits than dir.n, or claims more words than a slot has
+    dense = _encode_wire([np.arange(0, 9000, 3, dtype=np.int64)], ascending=(0,))
+    assert dense[64 + 16] == BITMAP
+    bad = dense.copy()
+    off = int(dense[24:32].view(np.uint64)[0])
+    bad[off] &= 0xfe
+    with pytest.raises(cubit.CubitError):
+        cubit.wire_unpack(bad, 0, 0)
+    bad = dense.copy()
+    bad[64 + 16:64 + 20] = np.array([BITMAP | (4096 << 8)], dtype=np.uint32).view(np.uint8)
     with pytest.raises(cubit.CubitError):
         cubit.wire_unpack(bad, 0, 0)
 
 
 # ---------------------------------------------------------------------------------------------------- GPU
-def _dir(wire, n_streams, n):
-    c = (n + CHUNK - 1) // CHUNK
-    d = wire[64:64 + n_streams * c * 16]
-    base = d.view(np.int64).reshape(-1, 2)[:, 0].reshape(n_streams, c)
-    wn = d.view(np.uint32).reshape(-1, 4)[:, 2:].reshape(n_streams, c, 2)
-    return base, wn[:, :, 0], wn[:, :, 1]
-
-
 def _wire_table(cubit, n, card, seed, devices=None, row_base=0):
     rng = np.random.default_rng(seed)
     key = rng.integers(0, card, n).astype(np.int32)
@@ -122,8 +181,11 @@ def _wire_table(cubit, n, card, seed, devices=None, row_base=0):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,vals", [(300_007, [3]), (1_000_003, [0, 1, 2, 3, 4, 5, 6]), (70_000, [])])
-def test_device_written_wire_equals_wide_fetch(cubit, n, vals):
+def test_device_written_wire_equals_wide_fetch(cubit, n, vals, monkeypatch):
     card = 8
+    bitmaps = len(vals) == 7  # bitmap frames for the row IDs are opt-in: exercised on the dense selection
+    if bitmaps:
+        monkeypatch.setenv("CUBIT_WIRE_BITMAP", "1")
     t, ix, key, cols = _wire_table(cubit, n, card, 11 + n, row_base=65536 * 3)
     order = [0, 2, 3, 4, 5, 6]
     dts = [cols[c].dtype for c in order]
@@ -158,11 +220,11 @@ def test_device_written_wire_equals_wide_fetch(cubit, n, vals):
                         v = a.view(np.int64) if a.dtype.itemsize == 8 else a.astype(np.int64)
                         for ch in range(nch):
                             p = v[ch * CHUNK:(ch + 1) * CHUNK]
-                            rg = int(p.max()) - int(p.min())
-                            w = 0 if rg == 0 else 1 if rg < 256 else 2 if rg < 65536 else 4 if rg < 2**32 else 8
+                            w, _ = _frame(p, si == 0 and bitmaps)  # only the row-ID stream may travel as a bitmap
                             assert width[si, ch] == w and base[si, ch] == int(p.min()), (si, ch)
-                    # stream 5 is the constant column, stream 2 (= row id) packs exactly like the row IDs
-                    assert (width[5] == 0).all() and np.array_equal(width[2], width[0])
+                    # stream 5 is the constant column; a selection of 7 values in 8 ships its row IDs as bitmaps
+                    assert (width[5] == 0).all()
+                    assert ((width[0] & 255) == BITMAP).all() == bitmaps
                     assert cubit.load_library().cubit_gpu_wire_payload_bytes(wire.ctypes.data) < m * 8 * (1 + len(order))
     t.close()
 

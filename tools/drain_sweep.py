@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--rows", type=int, default=500_000_000)
     ap.add_argument("--sels", default="0.5,0.1,1e-2")
     ap.add_argument("--threads", default="2,4,8,16")
-    ap.add_argument("--windows", default="262144")
+    ap.add_argument("--windows", default="0,262144")
     ap.add_argument("--payload-bits", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()

@@ -550,8 +550,9 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 			memset(&ea, 0, sizeof(ea));
 			ea.ids_out = (want_ids || separate_probe) && cap ? r->d_ids : nullptr; // positions alone need no row IDs
 			ea.row_base = t->row_base;
-			ea.ctrl = ctrl_a; // ticket counter + one status word per 32-unit tile (zeroed above)
-			Q_TRY(launch_lookback_scan(ss, ea, st));
+			ea.ctrl = ctrl_a;      // ticket counter + the total of every 32-unit tile (zeroed above)
+			ss.chunk_tot = ctrl_b; // the tiles' inclusive prefixes (zeroed above)
+			Q_TRY(launch_lookback_scan(ss, ea, t->sm_count, st));
 			n_launch++;
 		} else {
 			Q_TRY(launch_small_merge_count(ss, st));

@@ -193,7 +193,7 @@ void small_scan_plan(SmallScanArgs &s, uint32_t n_units, int sm_count);
 // the same merge + decode in ONE pass with a decoupled look-back (lookback_scan_kernel.cu): a.ctrl = 1 + n_tiles zeroed
 // words, a.ids_out / a.row_base as for launch_small_decode; writes hdr->count, span_excl / tile_excl, q_out
 uint32_t lookback_scan_tiles(uint32_t n_units);
-cudaError_t launch_lookback_scan(const SmallScanArgs &s, const ScanArgs &a, cudaStream_t stream);
+cudaError_t launch_lookback_scan(const SmallScanArgs &s, const ScanArgs &a, int sm_count, cudaStream_t stream);
 
 struct ProbeArgs {
 	const long long *ids;               // sorted global row IDs

@@ -10,9 +10,10 @@
 //      out in tile order to CTAs that are running, so a tile never waits for one that has not started,
 //   2. loads its tile ONCE with plain coalesced 64-bit loads (16 per lane and bitvector, all in flight) and keeps the
 //      merged words in registers,
-//   3. counts, publishes the tile's total (status word = flag | value), and warp 0 looks back over the status words of
-//      the tiles before it — 32 at a time — until it meets one whose inclusive prefix is known; totals are published
-//      before any look-back starts, so no tile waits for another tile's LOOK-BACK, only for its count,
+//   3. counts, publishes the tile's total (status word = flag | value) and computes its output position chain-free:
+//      inclusive prefix of tile − 1024 (finished long ago: only ≈ 600 tickets are in flight) + the totals of the tiles
+//      in between, summed by the whole CTA in one L2 round trip; no tile waits for another tile's LOOK-BACK, only for
+//      its count,
 //   4. emits row IDs from the registers at the known position (the lane-by-lane store path for units that hold a
 //      handful of rows, the staged position-ordered write-out of scan_common.cuh otherwise) and leaves the per-unit /
 //      per-tile prefixes the probe kernels want.
@@ -20,6 +21,8 @@
 // Reference conventions as in scan_kernel.cu (bit order validity_mask.hpp:163-168, sorted unique row ids
 // art.cpp:974-985).
 #include "scan_common.cuh"
+
+#include <cstdlib>
 
 namespace cubit {
 
@@ -31,28 +34,41 @@ constexpr int kLbUnitWpt = 4;                  // 64-bit words per lane and unit
 constexpr int kLbUnitWords = 32 * kLbUnitWpt;
 constexpr int kLbUnitsPerWarp = 4;
 constexpr int kLbTileUnits = kLbWarps * kLbUnitsPerWarp; // 32 units = 32 KiB per bitvector
+constexpr int kLbAnchor = 1024;                // look-back: inclusive prefix of tile − 1024 + the totals in between
 constexpr int kLbDirectMax = 96;               // rows per unit up to which row IDs are stored lane by lane
-constexpr unsigned long long kLbFlagAgg = 1ull << 62;  // value = the tile's own total
-constexpr unsigned long long kLbFlagIncl = 2ull << 62; // value = total of all tiles up to and including this one
+constexpr unsigned long long kLbFlag = 1ull << 62;     // status word published
 constexpr unsigned long long kLbValMask = (1ull << 62) - 1;
 
 } // namespace
 
 template <bool ONEG>
 __global__ void __launch_bounds__(kLbThreads, 4) cubit_scan_lookback_kernel(const __grid_constant__ SmallScanArgs s,
-                                                                           const __grid_constant__ ScanArgs a) {
+                                                                           const __grid_constant__ ScanArgs a,
+                                                                           const uint32_t pf_dist) {
 	__shared__ __align__(16) uint16_t compact[kLbWarps][kCompactHdrOff];
 	__shared__ unsigned long long warp_tot[kLbWarps];
-	__shared__ unsigned long long tile_prefix;
+	__shared__ unsigned long long red[kLbWarps];
 	__shared__ uint32_t tile_s;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	unsigned long long *status = a.ctrl + 1; // [n_tiles], zeroed; a.ctrl[0] = the ticket counter
+	unsigned long long *agg_w = a.ctrl + 1;  // [n_tiles], zeroed: flag | the tile's own total; a.ctrl[0] = the ticket counter
+	unsigned long long *incl_w = s.chunk_tot; // [n_tiles], zeroed: flag | total of all tiles up to and including this one
 	if (threadIdx.x == 0) {
 		tile_s = (uint32_t)atomicAdd(a.ctrl, 1ull);
 	}
 	__syncthreads();
 	const uint32_t tile = tile_s;
 	const uint32_t u0 = tile * kLbTileUnits + warp * kLbUnitsPerWarp;
+	// Experiment (CUBIT_LB_PREFETCH = tickets ahead, default off): ask L2 for the tile a later CTA will draw, one
+	// 128-byte line per thread and bitvector.  Measured: no gain (k = 1: 43 → 47 µs, k = 2: 89 → 108 µs) — the kernel is
+	// bound by the per-CTA chain (ticket → load → count → look-back → emit ≈ 6.7 µs × 6.4 waves), not by DRAM latency.
+	if (pf_dist) {
+		const uint64_t w = ((uint64_t)tile + pf_dist) * (kLbTileUnits * kLbUnitWords) + threadIdx.x * 16u;
+		if (w < (uint64_t)s.n_units * kLbUnitWords) {
+			for (uint32_t st = 0; st < s.k; st++) {
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(s.bv[st] + w));
+			}
+		}
+	}
 
 	// ---- load + merge: this warp's four units, every word in flight at once
 	uint64_t q[kLbUnitsPerWarp][kLbUnitWpt];
@@ -142,57 +158,57 @@ __global__ void __launch_bounds__(kLbThreads, 4) cubit_scan_lookback_kernel(cons
 	}
 	__syncthreads();
 
-	// ---- publish the total, look back (warp 0), publish the inclusive prefix
-	if (warp == 0) {
-		unsigned long long total = 0;
+	// ---- publish the total; look back WITHOUT a chain: the tiles in flight are the last ≈ 600 tickets, so tile
+	// (tile − 1024) finished before this CTA started and its inclusive prefix is there; the totals of the ≤ 1023 tiles in
+	// between are summed by the whole CTA (≤ 4 independent loads per thread): one L2 round trip, and the only thing a
+	// tile ever waits for is a predecessor's COUNT.  (The classic "nearest inclusive prefix" walk measured 68 µs per
+	// 125 MB: the nearest one is a whole wave back, and the polling hammers a handful of L2 lines.)
+	unsigned long long total = 0;
 #pragma unroll
-		for (int w = 0; w < kLbWarps; w++) {
-			total += warp_tot[w];
-		}
-		if (lane == 0) {
-			st_relaxed_u64(&status[tile], (tile == 0 ? kLbFlagIncl : kLbFlagAgg) | total);
-		}
-		unsigned long long excl = 0;
-		if (tile > 0) {
-			int64_t hi = (int64_t)tile - 1; // window [hi - 31, hi], lane l reads tile hi - l
-			while (true) {
-				const int64_t idx = hi - lane;
-				unsigned long long v = kLbFlagIncl; // tiles before 0: an inclusive prefix of 0
-				if (idx >= 0) {
-					do {
-						v = ld_relaxed_u64(&status[idx]);
-					} while ((v >> 62) == 0ull); // that tile's CTA is running (tickets) and publishes right after counting
-				}
-				const uint32_t incl_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
-				// nearest tile with a known inclusive prefix = lowest such lane; sum the totals of the lanes before it
-				const int stop = incl_mask ? __ffs((int)incl_mask) - 1 : 32;
-				const unsigned long long part = lane <= stop ? (v & kLbValMask) : 0ull;
-				unsigned long long sum = part;
+	for (int w = 0; w < kLbWarps; w++) {
+		total += warp_tot[w];
+	}
+	if (threadIdx.x == 0) {
+		st_relaxed_u64(&agg_w[tile], kLbFlag | total);
+	}
+	const int64_t anchor = (int64_t)tile - kLbAnchor;
+	unsigned long long part = 0;
+	if (threadIdx.x == 0 && anchor >= 0) {
+		unsigned long long v;
+		do {
+			v = ld_relaxed_u64(&incl_w[anchor]);
+		} while (!(v & kLbFlag));
+		part = v & kLbValMask;
+	}
+	for (int64_t idx = (anchor >= 0 ? anchor + 1 : 0) + threadIdx.x; idx < (int64_t)tile; idx += kLbThreads) {
+		unsigned long long v;
+		do {
+			v = ld_relaxed_u64(&agg_w[idx]);
+		} while (!(v & kLbFlag)); // that tile's CTA is running (tickets) and publishes right after counting
+		part += v & kLbValMask;
+	}
 #pragma unroll
-				for (int d = 16; d > 0; d >>= 1) {
-					sum += __shfl_xor_sync(0xffffffffu, sum, d);
-				}
-				excl += sum;
-				if (incl_mask) {
-					break;
-				}
-				hi -= 32;
-			}
-			if (lane == 0) {
-				st_relaxed_u64(&status[tile], kLbFlagIncl | (excl + total));
-			}
-		}
-		if (lane == 0) {
-			tile_prefix = excl;
-			if ((tile + 1) * (uint32_t)kLbTileUnits >= s.n_units) { // the last tile knows COUNT
-				s.hdr->count = excl + total;
-			}
-		}
+	for (int d = 16; d > 0; d >>= 1) {
+		part += __shfl_xor_sync(0xffffffffu, part, d);
+	}
+	if (lane == 0) {
+		red[warp] = part;
 	}
 	__syncthreads();
+	unsigned long long excl = 0;
+#pragma unroll
+	for (int w = 0; w < kLbWarps; w++) {
+		excl += red[w];
+	}
+	if (threadIdx.x == 0) {
+		st_relaxed_u64(&incl_w[tile], kLbFlag | (excl + total));
+		if ((tile + 1) * (uint32_t)kLbTileUnits >= s.n_units) { // the last tile knows COUNT
+			s.hdr->count = excl + total;
+		}
+	}
 
 	// ---- emit from the registers at the known position
-	unsigned long long pos = tile_prefix;
+	unsigned long long pos = excl;
 	for (int w = 0; w < warp; w++) {
 		pos += warp_tot[w];
 	}
@@ -255,18 +271,24 @@ __global__ void __launch_bounds__(kLbThreads, 4) cubit_scan_lookback_kernel(cons
 }
 
 // ------------------------------------------------------------------------------------------------ launch
-// ctrl: [1 + n_tiles] words, zeroed (ticket counter, then one status word per tile)
+// a.ctrl: [1 + n_tiles] zeroed words (ticket counter, then every tile's total); s.chunk_tot: [n_tiles] zeroed words
+// (every tile's inclusive prefix)
 uint32_t lookback_scan_tiles(uint32_t n_units) {
 	return (n_units + kLbTileUnits - 1) / kLbTileUnits;
 }
 
-cudaError_t launch_lookback_scan(const SmallScanArgs &s, const ScanArgs &a, cudaStream_t stream) {
+cudaError_t launch_lookback_scan(const SmallScanArgs &s, const ScanArgs &a, int sm_count, cudaStream_t stream) {
 	const uint32_t n_tiles = lookback_scan_tiles(s.n_units);
+	(void)sm_count;
+	uint32_t pf_dist = 0;
+	if (const char *e = getenv("CUBIT_LB_PREFETCH")) { // experiment knob (profiles/r2_small_k.md)
+		pf_dist = (uint32_t)strtoul(e, nullptr, 10);
+	}
 	const bool one_group = s.k >= 1 && s.group_end == (1ull << (s.k - 1));
 	if (one_group) {
-		cubit_scan_lookback_kernel<true><<<n_tiles, kLbThreads, 0, stream>>>(s, a);
+		cubit_scan_lookback_kernel<true><<<n_tiles, kLbThreads, 0, stream>>>(s, a, pf_dist);
 	} else {
-		cubit_scan_lookback_kernel<false><<<n_tiles, kLbThreads, 0, stream>>>(s, a);
+		cubit_scan_lookback_kernel<false><<<n_tiles, kLbThreads, 0, stream>>>(s, a, pf_dist);
 	}
 	return cudaGetLastError();
 }

@@ -732,7 +732,8 @@ def run_b200(args):
                 "path": "aggregate push-down + first DataChunk",
                 "note": "synchronous cubit_gpu_query + cubit_gpu_fetch of the first 2048-row DataChunk per query; "
                         "host predicate structs in, COUNT/SUM row + chunk out.  This is the aggregate-push-down path: "
-                        "the row-returning number (every row ID and value over PCIe) is e2e_full_materialize"},
+                        "the row-returning numbers (every row ID and value over PCIe) are e2e_full_materialize "
+                        "(8-byte copies) and e2e_full_materialize_narrow_wire (delivered to host consumers)"},
         "e2e_full_materialize": e2e_full,
         "e2e_full_materialize_narrow_wire": e2e_drain,
         "rowid_gather": rowid_gather,

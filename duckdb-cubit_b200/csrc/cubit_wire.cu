@@ -25,7 +25,7 @@
 
 using namespace cubit;
 
-namespace {
+namespace cubit {
 
 constexpr int kPackThreads = 256;
 constexpr uint64_t kWireStatsCap = 1ull << 18; // frames in a result's ring of forms (4 MiB): ≫ the windows in flight
@@ -231,10 +231,6 @@ PooledWire wire_pool_acquire(cubit_gpu_table *t, uint64_t bytes) {
 	w.bytes = bytes;
 	return w;
 }
-
-} // namespace
-
-namespace cubit {
 
 void wire_pool_free(cubit_gpu_table *t) {
 	std::lock_guard<std::mutex> ml(t->meta_mu);

@@ -276,10 +276,6 @@ extern "C" int cubit_gpu_fetch_wire_async(cubit_gpu_result *r, uint64_t offset, 
 	if (rc) {
 		return rc;
 	}
-	if (!r->parts.empty()) {
-		return fail(CUBIT_ESTATE, "a sharded result has no single device to write a wire from: use cubit_gpu_drain "
-		                          "or cubit_gpu_fetch_async");
-	}
 	if (offset > info.count || n > info.count - offset) {
 		return fail(CUBIT_EINVAL, "fetch range [%llu, +%llu) outside result of %llu rows", (unsigned long long)offset,
 		            (unsigned long long)n, (unsigned long long)info.count);
@@ -289,6 +285,19 @@ extern "C" int cubit_gpu_fetch_wire_async(cubit_gpu_result *r, uint64_t offset, 
 	}
 	if (with_rowids && !(r->flags & CUBIT_Q_ROWIDS)) {
 		return fail(CUBIT_ESTATE, "query did not materialise row IDs (CUBIT_Q_ROWIDS)");
+	}
+	if (!r->parts.empty()) {
+		// a sharded result: the shard that holds the whole window writes the wire; a window that straddles two shards
+		// has no single device to write it from
+		for (size_t i = 0; i < r->parts.size(); i++) {
+			if (offset >= r->count_prefix[i] && offset + n <= r->count_prefix[i + 1] && (n > 0 || i + 1 == r->parts.size() || offset < r->count_prefix[i + 1])) {
+				return cubit_gpu_fetch_wire_async(r->parts[i], offset - r->count_prefix[i], n, with_rowids, n_cols, host_wire,
+				                                  host_wire_bytes, ticket);
+			}
+		}
+		return fail(CUBIT_ESTATE, "rows [%llu, +%llu) straddle two shards of a sharded result: no single device can write "
+		                          "the wire — use cubit_gpu_drain, a window inside one shard, or cubit_gpu_fetch_async",
+		            (unsigned long long)offset, (unsigned long long)n);
 	}
 	const uint32_t n_streams = (with_rowids ? 1u : 0u) + n_cols;
 	if (n_streams == 0) {
@@ -655,8 +664,15 @@ extern "C" int cubit_gpu_drain(cubit_gpu_result *r, int with_rowids, uint32_t n_
 		drain_worker(sh, 0, locals[0]);
 	} else {
 		std::vector<std::thread> th;
-		for (uint32_t i = 0; i < n_threads; i++) {
-			th.emplace_back([&sh, &locals, i]() { drain_worker(sh, i, locals[i]); });
+		th.reserve(n_threads);
+		try {
+			for (uint32_t i = 0; i < n_threads; i++) {
+				th.emplace_back([&sh, &locals, i]() { drain_worker(sh, i, locals[i]); });
+			}
+		} catch (...) { // the system is out of threads: the workers that did start drain everything
+			if (th.empty()) {
+				drain_worker(sh, 0, locals[0]);
+			}
 		}
 		for (auto &x : th) {
 			x.join();

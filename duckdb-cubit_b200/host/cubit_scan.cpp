@@ -112,7 +112,8 @@ std::unique_ptr<CubitScanGlobalState> CubitScanInitGlobal(const CubitScanBindDat
 	{
 		uint32_t n_shards = 1;
 		cubit_gpu_shard_count(bind.table->Handle(), &n_shards);
-		state->narrow_wire = n_shards == 1 && bind.aggregate == CubitAggregate::NONE && !column_ids.empty();
+		(void)n_shards;
+		state->narrow_wire = bind.aggregate == CubitAggregate::NONE && !column_ids.empty();
 	}
 	state->sum.lower = info.sum_lo;
 	state->sum.upper = info.sum_hi;
@@ -136,11 +137,19 @@ static void FillWindow(CubitScanGlobalState &st) {
 			Check(cubit_gpu_alloc_host(st.win_wire_bytes, &st.win_wire));
 		}
 		cubit_gpu_fetch_ticket *ticket = nullptr;
-		Check(cubit_gpu_fetch_wire_async(st.result, st.win_begin, n, want_rowid ? 1 : 0, n_value_cols, st.win_wire,
-		                                 st.win_wire_bytes, &ticket));
-		Check(cubit_gpu_fetch_wait(ticket));
-		return;
+		const int rc = cubit_gpu_fetch_wire_async(st.result, st.win_begin, n, want_rowid ? 1 : 0, n_value_cols, st.win_wire,
+		                                          st.win_wire_bytes, &ticket);
+		if (rc == CUBIT_OK) {
+			Check(cubit_gpu_fetch_wait(ticket));
+			st.win_is_wire = true;
+			return;
+		}
+		if (rc != CUBIT_ESTATE) { // ESTATE: the window straddles two shards of a sharded table → 8-byte copies
+			Check(rc);
+		}
+		want_rowid = false;
 	}
+	st.win_is_wire = false;
 	st.win_cols.resize(st.column_ids.size(), nullptr);
 	auto pinned = [](void *&p) {
 		if (!p) {
@@ -212,14 +221,14 @@ void CubitScanFunction(const CubitScanBindData &bind, CubitScanGlobalState &st, 
 	for (size_t i = 0; i < st.column_ids.size(); i++) {
 		output.data[i].all_valid = true;
 		if (st.column_ids[i] == COLUMN_IDENTIFIER_ROW_ID) {
-			if (st.narrow_wire) {
+			if (st.win_is_wire) {
 				unpack(0, output.data[i].Raw(), 8);
 			} else {
 				memcpy(output.data[i].Raw(), st.win_rowids + rel, scan_count * sizeof(row_t));
 			}
 		} else {
 			const size_t w = (size_t)st.types[i];
-			if (st.narrow_wire) {
+			if (st.win_is_wire) {
 				unpack((has_rowid ? 1u : 0u) + value_col, output.data[i].Raw(), (uint32_t)w);
 			} else {
 				memcpy(output.data[i].Raw(), st.win_cols[i] + rel * w, scan_count * w);

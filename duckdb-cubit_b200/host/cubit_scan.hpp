@@ -52,11 +52,12 @@ struct CubitScanGlobalState { // GlobalTableFunctionState
 	row_t *win_rowids = nullptr;
 	std::vector<uint8_t *> win_cols; // one slot per column_ids entry (nullptr for the rowid slot)
 	// the same window in the narrow wire format (include/cubit_gpu_wire.h): the device writes per-DataChunk frames
-	// of base + 1/2/4/8-byte deltas into it and GetData widens one chunk straight into the output vectors.  Used
-	// whenever the result lives on one device; a sharded result keeps the wide copies above.
+	// of base + 1/2/4/8-byte deltas into it and GetData widens one chunk straight into the output vectors.  On a
+	// sharded table the shard that holds the window writes it; a window that straddles two shards uses the copies above.
 	void *win_wire = nullptr;
 	uint64_t win_wire_bytes = 0;
-	bool narrow_wire = false;
+	bool narrow_wire = false; // try the wire first
+	bool win_is_wire = false; // the current window arrived as a wire (one that straddles two shards does not)
 };
 
 std::unique_ptr<CubitScanBindData> CubitScanBind(CubitTable &table, std::vector<CubitPredicate> predicates,

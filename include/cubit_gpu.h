@@ -354,8 +354,10 @@ int cubit_gpu_fetch_wait(cubit_gpu_fetch_ticket *ticket);
  * instead of 8).  with_rowids != 0 puts the row IDs in stream 0; then the first n_cols projected columns follow.
  * host_wire must be page-locked (cubit_gpu_alloc_host / cudaHostAlloc / cudaHostRegister — CUBIT_EINVAL otherwise:
  * the device writes it directly) and hold cubit_wire_bytes(n, streams) bytes; it must stay untouched until
- * cubit_gpu_fetch_wait(ticket).  Thread-safe like cubit_gpu_fetch_async.  A sharded result has no single device to
- * write from: CUBIT_ESTATE — use cubit_gpu_drain (which walks the shards) or the wide fetch. */
+ * cubit_gpu_fetch_wait(ticket).  Thread-safe like cubit_gpu_fetch_async.  On a sharded result the shard that holds the
+ * whole window writes the wire; a window that straddles two shards has no single device to write it from:
+ * CUBIT_ESTATE — fetch that window with cubit_gpu_fetch_async, or use cubit_gpu_drain (which cuts its windows at the
+ * shard boundaries). */
 int cubit_gpu_fetch_wire_async(cubit_gpu_result *r, uint64_t offset, uint64_t n, int with_rowids, uint32_t n_cols,
                                void *host_wire, uint64_t host_wire_bytes, cubit_gpu_fetch_ticket **ticket);
 /* exported copies of the inline helpers of cubit_gpu_wire.h (for bindings that cannot include C) */

@@ -1285,8 +1285,9 @@ struct CubitScanGlobalState : public GlobalTableFunctionState {
 	idx_t n_value_cols = 0;
 	vector<bool> col_has_nulls; // per projected value column: the result carries a validity mask for it
 	// rows leave the GPU in the narrow wire format (cubit_gpu_wire.h: per DataChunk a base + 1/2/4/8-byte deltas the
-	// device writes straight into the page-locked window; widened into the output vectors one chunk at a time).  A
-	// sharded result has no single device to write a wire from and keeps the wide copies.
+	// device writes straight into the page-locked window; widened into the output vectors one chunk at a time).  On a
+	// sharded table the shard that holds a window writes it; the rare window that straddles two shards keeps the
+	// 8-byte copies.
 	bool narrow_wire = false;
 	uint64_t wire_bytes = 0;
 	static constexpr idx_t WINDOW_ROWS = 64 * STANDARD_VECTOR_SIZE;
@@ -1311,6 +1312,7 @@ struct CubitScanLocalState : public LocalTableFunctionState {
 		cubit_gpu_fetch_ticket *ticket = nullptr;
 		void *wire = nullptr; // narrow-wire window (instead of rowids / cols)
 		uint64_t wire_bytes = 0;
+		bool narrow = false;  // this window arrived as a wire
 	};
 	Window win[2];
 	int cur = 0;          // the window being served
@@ -1421,7 +1423,8 @@ static unique_ptr<GlobalTableFunctionState> CubitRunQuery(const CubitScanBindDat
 		uint32_t n_shards = 1;
 		cubit_gpu_shard_count(gpu.handle, &n_shards);
 		const uint32_t streams = NumericCast<uint32_t>((want_rowid ? 1 : 0) + cols.size());
-		state->narrow_wire = n_shards == 1 && streams > 0 && bind.agg_col < 0 && !getenv("CUBIT_WIDE_HANDOFF");
+		state->narrow_wire = streams > 0 && bind.agg_col < 0 && !getenv("CUBIT_WIDE_HANDOFF");
+		(void)n_shards; // (a window that straddles two shards falls back to the 8-byte copies on its own)
 		state->wire_bytes = cubit_wire_bytes(CubitScanGlobalState::WINDOW_ROWS, streams);
 	}
 	return std::move(state);
@@ -1448,15 +1451,22 @@ static void CubitClaimWindow(CubitScanGlobalState &state, CubitScanLocalState &l
 	}
 	w.begin = w.index * CubitScanGlobalState::WINDOW_ROWS;
 	w.end = MinValue<idx_t>(w.begin + CubitScanGlobalState::WINDOW_ROWS, state.row_count);
+	w.narrow = false;
 	if (state.narrow_wire) {
 		if (!w.wire) {
 			w.wire = local.pool_owner->AcquireWire(state.wire_bytes);
 			w.wire_bytes = state.wire_bytes;
 		}
-		CubitCheck(cubit_gpu_fetch_wire_async(state.result, w.begin, w.end - w.begin, state.want_rowid ? 1 : 0,
-		                                      NumericCast<uint32_t>(state.n_value_cols), w.wire, w.wire_bytes,
-		                                      &w.ticket));
-	} else {
+		const int rc = cubit_gpu_fetch_wire_async(state.result, w.begin, w.end - w.begin, state.want_rowid ? 1 : 0,
+		                                          NumericCast<uint32_t>(state.n_value_cols), w.wire, w.wire_bytes,
+		                                          &w.ticket);
+		if (rc == CUBIT_OK) {
+			w.narrow = true;
+		} else if (rc != CUBIT_ESTATE) { // ESTATE: the window straddles two shards — this one travels as 8-byte copies
+			CubitCheck(rc);
+		}
+	}
+	if (!w.narrow) {
 		const uint64_t win_bytes = CubitScanGlobalState::WINDOW_ROWS * sizeof(int64_t);
 		while (w.cols.size() < state.n_value_cols) {
 			w.cols.push_back(static_cast<int64_t *>(local.pool_owner->AcquireWindow(win_bytes)));
@@ -1523,7 +1533,7 @@ static void CubitScanFunction(ClientContext &, TableFunctionInput &data_p, DataC
 	for (idx_t i = 0; i < state.column_ids.size(); i++) {
 		auto dst = FlatVector::GetData<int64_t>(output.data[i]);
 		if (state.column_ids[i] == COLUMN_IDENTIFIER_ROW_ID) {
-			if (state.narrow_wire) { // stream 0: widened straight into the output vector
+			if (w->narrow) { // stream 0: widened straight into the output vector
 				if (cubit_wire_unpack_chunk(w->wire, 0, wire_chunk, dst, 8) != int(scan_count)) {
 					throw InternalException("cubit: malformed wire window");
 				}
@@ -1532,7 +1542,7 @@ static void CubitScanFunction(ClientContext &, TableFunctionInput &data_p, DataC
 			}
 			continue;
 		}
-		if (state.narrow_wire) {
+		if (w->narrow) {
 			const uint32_t stream = NumericCast<uint32_t>((state.want_rowid ? 1 : 0) + value_col);
 			if (cubit_wire_unpack_chunk(w->wire, stream, wire_chunk, dst, 8) != int(scan_count)) {
 				throw InternalException("cubit: malformed wire window");

@@ -255,6 +255,9 @@ def test_wire_argument_errors(cubit):
     with t.query([[(ix, 1)]], flags=0, agg=cubit.AGG_SUM, agg_a=0) as r:
         with pytest.raises(cubit.CubitError):
             r.drain(rowids=False, n_cols=0)
+    with t.query([[(ix, 1)], [(ix, 2)]], flags=cubit.Q_ROWIDS | cubit.Q_VALUES, cols=[0]) as r:  # empty result
+        st = r.drain(threads=4)
+        assert r.count == 0 and st.rows == 0 and st.chunks == 0 and st.sum_rowids == 0
     t.close()
 
 
@@ -298,9 +301,22 @@ def test_drain_delivers_every_chunk_once_in_batch_order(cubit, shards, threads, 
         with pytest.raises(cubit.CubitError, match="stopped"):
             r.drain(threads=threads, window_rows=window, fn=lambda *a: 1)
         if shards > 1:
-            with cubit.HostBuffer(cubit.wire_bytes(CHUNK, 4)) as hb:
-                with pytest.raises(cubit.CubitError, match="sharded"):
-                    r.fetch_wire_async(0, CHUNK, hb.array)
+            # one wire = one device: a window inside one shard is written by that shard, one that straddles two is refused
+            spans = [t.shard_info(i) for i in range(shards)]
+            per_shard = [int(np.count_nonzero((loc >= r0) & (loc < r0 + nr))) for _, r0, nr in spans]
+            ids_all, cv_all = r.fetch()
+            with cubit.HostBuffer(cubit.wire_bytes(3 * CHUNK, 4)) as hb:
+                off = per_shard[0] + 5                      # inside the second shard
+                m = min(3 * CHUNK, per_shard[1] - 5)
+                r.fetch_wait(r.fetch_wire_async(off, m, hb.array))
+                got = np.concatenate([cubit.wire_unpack(hb.array, 0, c) for c in range((m + CHUNK - 1) // CHUNK)])
+                assert np.array_equal(got, ids_all[off:off + m])
+                g3 = np.concatenate([cubit.wire_unpack(hb.array, 2, c, np.int32) for c in range((m + CHUNK - 1) // CHUNK)])
+                assert np.array_equal(g3, cv_all[1][off:off + m])
+                with pytest.raises(cubit.CubitError, match="straddle"):
+                    r.fetch_wire_async(per_shard[0] - 10, 100, hb.array)
+                with pytest.raises(cubit.CubitError, match="outside result"):
+                    r.fetch_wire_async(len(want) - 10, 100, hb.array)
     t.close()
 
 

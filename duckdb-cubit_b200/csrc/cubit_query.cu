@@ -41,8 +41,8 @@ static void release_result_locked(cubit_gpu_result *r) {
 	if (r->d_q_tmp) {
 		cudaFreeAsync(r->d_q_tmp, s);
 	}
-	if (r->d_wire_stats) {
-		cudaFreeAsync(r->d_wire_stats, s);
+	if (uint4 *ws = r->d_wire_stats.load()) {
+		cudaFreeAsync(ws, s);
 	}
 	for (auto &p : r->d_vals) {
 		if (p) {

@@ -364,16 +364,16 @@ extern "C" int cubit_gpu_fetch_wire_async(cubit_gpu_result *r, uint64_t offset, 
 		void *scratch = nullptr;
 		bool own_scratch = false;
 		if (e == cudaSuccess && slot <= kWireStatsCap / 8) {
-			if (!r->d_wire_stats) {
+			if (!r->d_wire_stats.load(std::memory_order_acquire)) {
 				std::lock_guard<std::mutex> lk(r->fin_mu);
-				if (!r->d_wire_stats) {
+				if (!r->d_wire_stats.load(std::memory_order_relaxed)) {
 					void *p = nullptr;
 					e = cudaMallocAsync(&p, kWireStatsCap * sizeof(uint4), cs);
 					if (e == cudaSuccess) {
 						e = cudaStreamSynchronize(cs); // the other copy streams use it too: once per result
 					}
 					if (e == cudaSuccess) {
-						r->d_wire_stats = static_cast<uint4 *>(p);
+						r->d_wire_stats.store(static_cast<uint4 *>(p), std::memory_order_release);
 					}
 				}
 			}
@@ -382,7 +382,7 @@ extern "C" int cubit_gpu_fetch_wire_async(cubit_gpu_result *r, uint64_t offset, 
 				do { // a slot never straddles the end of the ring; the ring is far larger than what can be in flight
 					pos = r->wire_stats_cursor.fetch_add(slot) % kWireStatsCap;
 				} while (pos + slot > kWireStatsCap);
-				scratch = r->d_wire_stats + pos;
+				scratch = r->d_wire_stats.load(std::memory_order_acquire) + pos;
 			}
 		} else if (e == cudaSuccess) { // a window of more than 32 Ki frames: its own allocation
 			e = cudaMallocAsync(&scratch, frames * sizeof(uint4), cs);

@@ -209,7 +209,7 @@ struct cubit_gpu_result {
 	cubit_result_info info = {};
 	std::atomic<uint32_t> copies_in_flight {0};
 	// narrow-wire hand-off (cubit_wire.cu): a ring of per-frame forms between its two kernels, allocated on first use
-	uint4 *d_wire_stats = nullptr;
+	std::atomic<uint4 *> d_wire_stats {nullptr};
 	std::atomic<uint64_t> wire_stats_cursor {0};
 	// sharded result: one child per shard, in row order; count_prefix[i] = rows of the children before i
 	std::vector<cubit_gpu_result *> parts;

@@ -372,7 +372,8 @@ int cubit_gpu_wire_unpack(const void *host_wire, uint32_t stream, uint64_t chunk
  * window index: chunks of one window arrive in order on one worker; sort by (batch_index, row_offset) to restore
  * the global order).  cols[c] points to n values of the c-th projected column (4- or 8-byte elements as the query
  * returns them), validity[c] is NULL or the ValidityMask words of the chunk; rowids is NULL unless with_rowids.
- * A non-zero return of fn stops the drain (CUBIT_ESTATE).  fn == NULL is the built-in checksum consumer: every
+ * A non-zero return of fn stops the drain (CUBIT_ESTATE); fn runs on the library's worker threads and must not throw
+ * or unwind through them.  fn == NULL is the built-in checksum consumer: every
  * chunk is widened and summed (wrapping 64-bit sums of the row IDs and of every column's bit patterns widened to
  * 64 bits) — a consumer that reads every delivered value, for tests and bench.py.  Works on sharded results. */
 typedef int (*cubit_chunk_fn)(void *ctx, uint32_t worker, uint64_t batch_index, uint64_t row_offset, uint32_t n,

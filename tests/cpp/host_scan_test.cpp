@@ -12,7 +12,10 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <thread>
+#include <vector>
 
 using namespace cubit_host;
 
@@ -144,6 +147,80 @@ static void AppendAfterBuild() {
 	REQUIRE(ids == want);
 }
 
+// cubit_gpu_drain with a C++ consumer on four library worker threads at once: every DataChunk exactly once, the batch
+// index orders them (PhysicalTableScan's ordered parallel source, table_scan.cpp:179-189), values = brute force
+struct DrainSink {
+	std::mutex mu;
+	std::map<std::pair<uint64_t, uint64_t>, std::pair<std::vector<int64_t>, std::vector<int64_t>>> chunks;
+	std::atomic<int> in_flight {0}, max_in_flight {0};
+};
+static int DrainCallback(void *ctx, uint32_t, uint64_t batch, uint64_t row_offset, uint32_t n, const int64_t *rowids,
+                         const void *const *cols, const uint64_t *const *validity) {
+	auto &sink = *static_cast<DrainSink *>(ctx);
+	const int now = ++sink.in_flight;
+	int seen = sink.max_in_flight.load();
+	while (now > seen && !sink.max_in_flight.compare_exchange_weak(seen, now)) {
+	}
+	std::vector<int64_t> ids(rowids, rowids + n), vals(static_cast<const int64_t *>(cols[0]), static_cast<const int64_t *>(cols[0]) + n);
+	REQUIRE(validity[0] == nullptr);
+	{
+		std::lock_guard<std::mutex> lk(sink.mu);
+		REQUIRE(sink.chunks.emplace(std::make_pair(batch, row_offset), std::make_pair(std::move(ids), std::move(vals))).second);
+	}
+	--sink.in_flight;
+	return 0;
+}
+static void ParallelDrain() {
+	const idx_t n = 2000003;
+	const row_t base = 65536 * 2;
+	std::vector<int32_t> key(n);
+	std::vector<int64_t> pay(n);
+	for (idx_t r = 0; r < n; r++) {
+		key[r] = (int32_t)(Rng() % 5);
+		pay[r] = (int64_t)(Rng() % 100000) * 1000 - 7;
+	}
+	CubitTable table(n, base);
+	table.AddColumn(0, key.data());
+	table.AddColumn(1, pay.data());
+	CubitIndex index(table, 0, 0, 5);
+	index.Build();
+	cubit_bv_ref refs[2] = {{index.Id(), 1}, {index.Id(), 3}};
+	cubit_pred_group grp {2, refs};
+	int32_t col = 1;
+	cubit_query q {};
+	q.n_groups = 1;
+	q.groups = &grp;
+	q.flags = CUBIT_Q_ROWIDS | CUBIT_Q_VALUES;
+	q.n_cols = 1;
+	q.cols = &col;
+	cubit_gpu_result *r = nullptr;
+	REQUIRE(cubit_gpu_query(table.Handle(), &q, &r) == CUBIT_OK);
+	DrainSink sink;
+	cubit_drain_stats st;
+	REQUIRE(cubit_gpu_drain(r, 1, 1, 4, 16 * 2048, DrainCallback, &sink, &st) == CUBIT_OK);
+	std::vector<int64_t> want_ids, want_vals;
+	for (idx_t i = 0; i < n; i++) {
+		if (key[i] == 1 || key[i] == 3) {
+			want_ids.push_back(base + (row_t)i);
+			want_vals.push_back(pay[i]);
+		}
+	}
+	REQUIRE(st.rows == want_ids.size() && st.workers == 4 && st.wire_bytes < st.wide_bytes);
+	std::vector<int64_t> got_ids, got_vals;
+	uint64_t next_row = 0;
+	for (auto &kv : sink.chunks) { // (batch, row offset) order = row order
+		REQUIRE(kv.first.second == next_row);
+		next_row += kv.second.first.size();
+		got_ids.insert(got_ids.end(), kv.second.first.begin(), kv.second.first.end());
+		got_vals.insert(got_vals.end(), kv.second.second.begin(), kv.second.second.end());
+	}
+	REQUIRE(got_ids == want_ids && got_vals == want_vals);
+	printf("parallel drain: %llu rows in %llu chunks, %llu wire bytes (%.1f per row, wide %.0f), up to %d consumers at once\n",
+	       (unsigned long long)st.rows, (unsigned long long)st.chunks, (unsigned long long)st.wire_bytes,
+	       (double)st.wire_bytes / (double)st.rows, (double)st.wide_bytes / (double)st.rows, sink.max_in_flight.load());
+	cubit_gpu_free_result(r);
+}
+
 // NULLs in a projected column: the chunk's vector carries the validity mask of the probed rows
 static void NullsInProjectedColumn() {
 	const idx_t n = 300007;
@@ -186,6 +263,7 @@ static void NullsInProjectedColumn() {
 }
 
 int main() {
+	ParallelDrain();
 	NullsInProjectedColumn();
 	AppendAfterBuild();
 	ArtManyMatches(1024);

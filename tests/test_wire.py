@@ -115,6 +115,28 @@ def test_unpack_matches_independent_encoder(cubit, n):
     assert np.array_equal(cubit.wire_unpack(wire, 2, 0, np.int32), small[:CHUNK].astype(np.int32))
 
 
+def test_unpack_property_random_streams(cubit):
+    """hypothesis: any mix of value ranges, signs, chunk counts and ragged tails survives encode → unpack bit for bit"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 3 * CHUNK + 17), st.integers(0, 63), st.integers(-2**62, 2**62), st.integers(0, 2**32 - 1),
+           st.booleans())
+    def run(n, bits, center, seed, ascending):
+        rng = np.random.default_rng(seed)
+        span = 1 << bits
+        a = (center + rng.integers(0, span, n, dtype=np.int64)).astype(np.int64)
+        if ascending:
+            a = np.unique(a)                      # strictly ascending: may travel as bitmap frames
+            n = len(a)
+        b = rng.integers(-2**31, 2**31 - 1, n).astype(np.int32)
+        wire = _encode_wire([a, b], ascending=(0,) if ascending else ())
+        nch = (n + CHUNK - 1) // CHUNK
+        assert np.array_equal(np.concatenate([cubit.wire_unpack(wire, 0, c) for c in range(nch)]), a)
+        assert np.array_equal(np.concatenate([cubit.wire_unpack(wire, 1, c, np.int32) for c in range(nch)]), b)
+    run()
+
+
 def test_scalar_widening_path_gives_the_same_answers():
     """the AVX2 loops are an optimisation of the scalar ones: run the encoder test again with them switched off"""
     import os

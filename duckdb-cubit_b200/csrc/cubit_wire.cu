@@ -29,6 +29,7 @@ namespace cubit {
 
 constexpr int kPackThreads = 256;
 constexpr uint64_t kWireStatsCap = 1ull << 18; // frames in a result's ring of forms (4 MiB): ≫ the windows in flight
+constexpr uint64_t kWireMaxFrames = kWireStatsCap / 8; // frames of ONE wire (32 Ki: e.g. 16 Mi rows of two streams)
 constexpr int kPerThread = CUBIT_WIRE_CHUNK / kPackThreads; // 8
 
 struct WireArgs {
@@ -308,6 +309,11 @@ extern "C" int cubit_gpu_fetch_wire_async(cubit_gpu_result *r, uint64_t offset, 
 		return fail(CUBIT_EINVAL, "wire buffer of %llu bytes, %llu needed (cubit_gpu_wire_bytes)",
 		            (unsigned long long)host_wire_bytes, (unsigned long long)need);
 	}
+	if (((n + CUBIT_WIRE_CHUNK - 1) / CUBIT_WIRE_CHUNK) * n_streams > kWireMaxFrames) {
+		// (every frame's CTA sums the forms of the frames before it: fine for windows, quadratic for whole results)
+		return fail(CUBIT_EINVAL, "a wire holds at most %llu frames (chunks x streams): fetch the result in windows",
+		            (unsigned long long)kWireMaxFrames);
+	}
 	if (reinterpret_cast<uintptr_t>(host_wire) % 16 != 0) {
 		return fail(CUBIT_EINVAL, "wire buffer must be 16-byte aligned");
 	}
@@ -362,8 +368,7 @@ extern "C" int cubit_gpu_fetch_wire_async(cubit_gpu_result *r, uint64_t offset, 
 			slot <<= 1;
 		}
 		void *scratch = nullptr;
-		bool own_scratch = false;
-		if (e == cudaSuccess && slot <= kWireStatsCap / 8) {
+		if (e == cudaSuccess) {
 			if (!r->d_wire_stats.load(std::memory_order_acquire)) {
 				std::lock_guard<std::mutex> lk(r->fin_mu);
 				if (!r->d_wire_stats.load(std::memory_order_relaxed)) {
@@ -384,9 +389,6 @@ extern "C" int cubit_gpu_fetch_wire_async(cubit_gpu_result *r, uint64_t offset, 
 				} while (pos + slot > kWireStatsCap);
 				scratch = r->d_wire_stats.load(std::memory_order_acquire) + pos;
 			}
-		} else if (e == cudaSuccess) { // a window of more than 32 Ki frames: its own allocation
-			e = cudaMallocAsync(&scratch, frames * sizeof(uint4), cs);
-			own_scratch = e == cudaSuccess;
 		}
 		if (e == cudaSuccess) {
 			a.stats = static_cast<uint4 *>(scratch);
@@ -394,9 +396,6 @@ extern "C" int cubit_gpu_fetch_wire_async(cubit_gpu_result *r, uint64_t offset, 
 			cubit_wire_stats_kernel<<<grid, kPackThreads, 0, cs>>>(a);
 			cubit_wire_pack_kernel<<<grid, kPackThreads, 0, cs>>>(a);
 			e = cudaGetLastError();
-			if (own_scratch) {
-				cudaFreeAsync(scratch, cs);
-			}
 			t->launches += 2;
 		}
 		if (e == cudaSuccess) {

@@ -353,7 +353,8 @@ int cubit_gpu_fetch_wait(cubit_gpu_fetch_ticket *ticket);
  * only the narrowed bytes cross PCIe: 2-6 bytes per row and stream on sorted row IDs and FOR-friendly columns
  * instead of 8).  with_rowids != 0 puts the row IDs in stream 0; then the first n_cols projected columns follow.
  * host_wire must be page-locked (cubit_gpu_alloc_host / cudaHostAlloc / cudaHostRegister — CUBIT_EINVAL otherwise:
- * the device writes it directly) and hold cubit_wire_bytes(n, streams) bytes; it must stay untouched until
+ * the device writes it directly) and hold cubit_wire_bytes(n, streams) bytes; one wire holds at most 32768 frames
+ * (chunks x streams: a window, not a whole result — CUBIT_EINVAL beyond); it must stay untouched until
  * cubit_gpu_fetch_wait(ticket).  Thread-safe like cubit_gpu_fetch_async.  On a sharded result the shard that holds the
  * whole window writes the wire; a window that straddles two shards has no single device to write it from:
  * CUBIT_ESTATE — fetch that window with cubit_gpu_fetch_async, or use cubit_gpu_drain (which cuts its windows at the

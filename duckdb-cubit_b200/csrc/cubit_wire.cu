@@ -628,6 +628,10 @@ extern "C" int cubit_gpu_drain(cubit_gpu_result *r, int with_rowids, uint32_t n_
 	if (window_rows % CUBIT_WIRE_CHUNK) {
 		return fail(CUBIT_EINVAL, "window_rows must be a multiple of %u", CUBIT_WIRE_CHUNK);
 	}
+	{ // one wire holds at most kWireMaxFrames frames: larger windows are cut down
+		const uint64_t max_chunks = kWireMaxFrames / ((with_rowids ? 1u : 0u) + n_cols);
+		window_rows = std::min<uint64_t>(window_rows, max_chunks * CUBIT_WIRE_CHUNK);
+	}
 	DrainShared sh;
 	sh.with_rowids = with_rowids ? 1 : 0;
 	sh.n_cols = n_cols;

@@ -377,3 +377,35 @@ def test_drain_with_nulls_passes_validity(cubit):
         assert np.array_equal(np.concatenate([g[4] for g in seen]), valid[want])
         assert np.array_equal(vals[valid[want]], pay[want][valid[want]])  # NULL slots hold unspecified values
     t.close()
+
+
+@pytest.mark.gpu
+def test_concurrent_queries_and_drains_on_one_table(cubit):
+    """four host threads, each running its own queries and draining them (two workers each) on ONE table at the same
+    time — the hand-off's kernels share the table's copy streams and the per-result rings: every checksum must be right"""
+    import threading
+    n, card = 1_500_007, 6
+    t, ix, key, cols = _wire_table(cubit, n, card, 404)
+    errors = []
+
+    def worker(seed):
+        try:
+            rng = np.random.default_rng(seed)
+            for it in range(6):
+                vals = sorted(rng.choice(card, size=int(rng.integers(1, 4)), replace=False).tolist())
+                want = np.flatnonzero(np.isin(key, vals))
+                with t.query([[(ix, v) for v in vals]], flags=cubit.Q_ROWIDS | cubit.Q_VALUES, cols=[0, 3]) as r:
+                    st = r.drain(threads=2, window_rows=int(rng.choice([2048, 16384, 0])))
+                    assert st.rows == len(want) and st.sum_rowids == int(want.sum())
+                    assert st.sum_cols[0] == int(cols[0][want].view(np.uint64).sum(dtype=np.uint64))
+                    assert st.sum_cols[1] == int(cols[3][want].view(np.uint32).sum(dtype=np.uint64))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+    th = [threading.Thread(target=worker, args=(s,)) for s in range(4)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join(timeout=300)
+    assert not any(x.is_alive() for x in th), "a drain is stuck"
+    assert not errors, errors
+    t.close()

@@ -65,6 +65,11 @@ struct ScanSmem {
 	alignas(16) uint16_t compact[kConsumerWarps][kCompactRow]; // per-warp staging of local row numbers (+ dummy slots)
 	alignas(16) DeltaEnt dbuf[kStages][kDeltaStage];              // pending-delta words staged beside each segment
 	alignas(16) uint16_t abuf[CMP ? kStages : 1][CMP ? kArrayMax : 8]; // ARRAY containers staged beside each segment
+	// ARRAY containers without pending deltas are OR-ed into this tile-sized bitmap by ONE consumer warp per stage
+	// (a 32-bit shared-memory atomic per list entry) and folded into the registers once per OR group — instead of all
+	// eight warps filtering every list for their span (2,650 warp instructions per container stage, the whole run time
+	// of a day-level index scan; profiles/r2_compressed_scan.md)
+	alignas(16) uint64_t acc[CMP ? kTileWords : 1];
 	unsigned long long pdir[CMP ? kMaxStreams : 1];                    // producer: directory entries of the current segment
 	alignas(8) uint64_t full[kStages];
 	uint64_t empty[kStages];
@@ -111,6 +116,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 			mbar_init(&sm.resp_full[s], 1);
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (CMP) {
+		for (int w = threadIdx.x; w < kTileWords; w += kScanThreads) {
+			sm.acc[w] = 0;
+		}
 	}
 	__syncthreads();
 
@@ -340,6 +350,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 		}
 		uint32_t tile = kNoTile;
 		uint32_t tile_total = 0, warp_excl = 0;
+		bool acc_dirty = false; // (uniform over the consumer warps) the accumulation tile holds bits of the open OR group
 		bool e_todo = have_p[kDefer - 1] && need_emit; // the oldest pending segment is still to be emitted
 		bool e_open = false;
 		EmitState es;
@@ -505,7 +516,18 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 									for (int i = 0; i < WPT; i++) {
 										(ONEG ? q[i] : g[i]) = ~0ull;
 									}
-								} else if (ctype == CT_ARRAY && !(a.debug & 32u)) {
+								} else if (ctype == CT_ARRAY && !(a.debug & (32u | 128u))) {
+									// one warp per stage ORs the whole list into the accumulation tile
+									if (warp == (int)((s + (uint32_t)u) & (uint32_t)(kConsumerWarps - 1))) {
+										const uint32_t cnt = cmeta >> 2;
+										unsigned int *acc32 = reinterpret_cast<unsigned int *>(&sm.acc[0]);
+										for (uint32_t e = lane; e < cnt; e += 32) {
+											const uint32_t p = sm.abuf[st][e];
+											atomicOr(acc32 + (p >> 5), 1u << (p & 31u));
+										}
+									}
+									acc_dirty = true;
+								} else if (ctype == CT_ARRAY && !(a.debug & 32u)) { // (debug 128: the per-warp filter, for A/B runs)
 									const uint32_t cnt = cmeta >> 2;
 									for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
 										const uint32_t p = e0 + lane < cnt ? (uint32_t)sm.abuf[st][e0 + lane] : 0xffffffffu;
@@ -557,6 +579,17 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 							}
 #undef CUBIT_LD
 							if ((a.group_end >> (s + u)) & 1ull) {
+								if (CMP && acc_dirty) { // the group's ARRAY containers: every warp's atomics, then this warp's span
+									consumer_bar_sync();
+#pragma unroll
+									for (int i = 0; i < WPT; i++) {
+										uint64_t *w = &sm.acc[warp * kSpanWords + i * 32 + lane];
+										g[i] |= *w;
+										*w = 0;
+									}
+									consumer_bar_sync(); // (before the next group's atomics land in a span that is still being read)
+									acc_dirty = false;
+								}
 #pragma unroll
 								for (int i = 0; i < WPT; i++) {
 									q[i] &= g[i];
@@ -583,6 +616,16 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 				}
 			} else if (b == nb_iter && !draining) {
 				if (tile != kNoTile) {
+					if (CMP && ONEG && acc_dirty) { // single OR group: the tile's ARRAY containers, folded once
+						consumer_bar_sync();
+#pragma unroll
+						for (int i = 0; i < WPT; i++) {
+							uint64_t *w = &sm.acc[warp * kSpanWords + i * 32 + lane];
+							q[i] |= *w;
+							*w = 0;
+						}
+						// (the block scan's barrier below separates this from the next tile's atomics)
+					}
 					// ---- merged bitvector out (optional)
 					if (a.q_out) {
 						uint64_t *dst = a.q_out + (size_t)tile * kTileWords + warp * kSpanWords;

@@ -171,11 +171,17 @@ def run(sf, children, workers=None, day_index=False, reps=7, log=print):
         jan94 = int((np.datetime64("1994-01-01") - np.datetime64("1992-01-01")).astype(int))
         gd = [[(dx, jan94 + d) for d in range(31)], groups[1], groups[2]]
         gm = [[(ix["month"], 24)], groups[1], groups[2]]
-        with t.query(gd, flags=cubit.Q_TIMING, agg=cubit.AGG_SUM_PROD, agg_a=COL_PRICE, agg_b=COL_DISC) as r1, \
-                t.query(gm, flags=cubit.Q_TIMING, agg=cubit.AGG_SUM_PROD, agg_a=COL_PRICE, agg_b=COL_DISC) as r2:
-            assert (r1.count, r1.sum) == (r2.count, r2.sum)
-            out["day_index"].update({"jan94_count": r1.count, "ms_scan_31_day_containers": r1.info.ms_scan,
-                                     "ms_scan_1_month_bitvector": r2.info.ms_scan})
+        ms_d, ms_m = [], []
+        for _ in range(max(2, reps)):  # (the first launch of a kernel instance includes its lazy load: best of several)
+            with t.query(gd, flags=cubit.Q_TIMING, agg=cubit.AGG_SUM_PROD, agg_a=COL_PRICE, agg_b=COL_DISC) as r1, \
+                    t.query(gm, flags=cubit.Q_TIMING, agg=cubit.AGG_SUM_PROD, agg_a=COL_PRICE, agg_b=COL_DISC) as r2:
+                assert (r1.count, r1.sum) == (r2.count, r2.sum)
+                ms_d.append(r1.info.ms_scan)
+                ms_m.append(r2.info.ms_scan)
+                out["day_index"]["jan94_count"] = r1.count
+        out["day_index"].update({"ms_scan_31_day_containers": min(ms_d), "ms_scan_31_day_containers_first_launch": ms_d[0],
+                                 "ms_scan_1_month_bitvector": min(ms_m), "k_day_query": 31 + len(groups[1]) + len(groups[2]),
+                                 "k_month_query": 1 + len(groups[1]) + len(groups[2])})
     t.close()
     return out
 

@@ -5,7 +5,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 cubit = importlib.import_module("duckdb-cubit_b200")
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 60
-t = cubit.CubitTable(6_000_000)
+rows = int(sys.argv[2]) if len(sys.argv) > 2 else 6_000_000
+t = cubit.CubitTable(rows)
 t.synth_column(1, 2, seed=99, card=2526, hot_lo=0)
 cx = t.create_index(2526, compressed=True)
 t.build_index(cx, 1, 0)

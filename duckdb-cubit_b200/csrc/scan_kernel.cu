@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) cubit_scan_kernel(const __gri
 	constexpr int kTileWords = Smem::kTileWords;
 	constexpr int kTileBytes = Smem::kTileBytes;
 	constexpr int kSpanWords = WPT * 32; // words of one warp's span
-	constexpr int UB = WPT >= 8 ? 2 : (kWaitBatch < kStages ? kWaitBatch : kStages);
+	constexpr int UB = (WPT >= 8 || CMP) ? 2 : (kWaitBatch < kStages ? kWaitBatch : kStages); // (CMP: container stages are handshake-bound — shorter batches let the producer run further ahead)
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	Smem &sm = *reinterpret_cast<Smem *>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
 

@@ -403,11 +403,15 @@ static int plan_and_launch(cubit_gpu_table *t, const cubit_query *q, cubit_gpu_r
 	if (const char *e = getenv("CUBIT_TWO_PASS_MIN_ROWS")) { // tests: 0 = every eligible query; huge = never
 		two_pass_min_rows = strtoull(e, nullptr, 10);
 	}
+	uint32_t lb_max_k = 3; // with row positions (measured crossover against the ring kernel, profiles/r2_small_k.md)
+	if (const char *e = getenv("CUBIT_LB_MAX_K")) { // experiment knob
+		lb_max_k = (uint32_t)std::min<unsigned long>(8ul, strtoul(e, nullptr, 10));
+	}
 	const uint32_t n_units = (uint32_t)(((uint64_t)t->n_seg * t->seg_words + 1023) / 1024) * 8u;
-	// measured crossover against the ring kernel at 10^9 rows (profiles/r2_small_k.md): with row positions k <= 2,
-	// count / bitvector / aggregate only k <= 3
+	// measured crossover against the ring kernel at 10^9 rows (profiles/r2_small_k.md): k <= 3, with row positions
+	// (the one-pass look-back kernel) as well as count / bitvector / aggregate only
 	const bool two_pass = !has_delta && !has_compressed && !unfused && probe_mode != PROBE_FUSED && !probe_on_bv &&
-	                      k <= (need_ids_buf ? 2u : 3u) &&
+	                      k <= (need_ids_buf ? lb_max_k : 3u) &&
 	                      t->n_rows >= two_pass_min_rows && (uint64_t)n_units * 128 <= t->words_per_bv && sa.debug == 0;
 	const uint32_t probe_tile_words = two_pass ? 1024u : tile_words;
 	const uint32_t probe_n_tile = two_pass ? n_units / 8u : n_tile;

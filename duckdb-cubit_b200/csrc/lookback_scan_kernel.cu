@@ -1,4 +1,4 @@
-// lookback_scan_kernel.cu — merge + decode of SHORT queries (k ≤ 2 value bitvectors, no pending deltas, verbatim
+// lookback_scan_kernel.cu — merge + decode of SHORT queries (k ≤ 3 value bitvectors, no pending deltas, verbatim
 // bitvectors) that want row positions, in ONE pass with a decoupled look-back (sm_100a).
 //
 // What it computes is what scan_kernel.cu computes:

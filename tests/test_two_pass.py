@@ -56,6 +56,8 @@ def test_two_pass_scan_matches_oracle(cubit, force_two_pass, monkeypatch, seg_bi
         ([[(ix, 4), (ix, 5)], [(ix, 5), (ix, 6)]], [[bv[4], bv[5]], [bv[5], bv[6]]]),   # AND of two ORs
         ([[(ix, 7), (ix, 8), (ix, 9)], [(ixr, 0)]], [[bv[7], bv[8], bv[9]], [bvr[0]]]),
         ([[(ix, 11)]], [[bv[11]]]),
+        ([[(ix, 0), (ix, 1), (ix, 2)]], [[bv[0], bv[1], bv[2]]]),          # k = 3, one OR group
+        ([[(ix, 8), (ix, 9)], [(ixr, 0)]], [[bv[8], bv[9]], [bvr[0]]]),     # k = 3, AND of an OR and a single bitvector
         ([[(ix, 1)], [(ixr, 0)]], [[bv[1]], [bvr[0]]]),                  # AND of two single bitvectors (a = 1 AND b = 0)
         ([[(ix, 2)], [(ixr, 1)]], [[bv[2]], [bvr[1]]]),                  # the same, nearly empty
         ([[(ix, 3)], [(ix, 4)]], [[bv[3]], [bv[4]]]),                    # disjoint: empty result
@@ -65,8 +67,8 @@ def test_two_pass_scan_matches_oracle(cubit, force_two_pass, monkeypatch, seg_bi
         want = oracle.decode(q, base)
         wp, ws = oracle.probe(want, pay, base), oracle.probe(want, small, base)
         k = sum(len(g) for g in groups)
-        # the planner's rule: with row positions k <= 2, count / bitvector / aggregate only k <= 3
-        with_pos = (cubit.SCAN_LOOKBACK if lookback else cubit.SCAN_TWO_PASS) if k <= 2 else cubit.SCAN_RING
+        # the planner's rule: k <= 3, with row positions (look-back kernel) and for count / bitvector / aggregate only
+        with_pos = (cubit.SCAN_LOOKBACK if lookback else cubit.SCAN_TWO_PASS) if k <= 3 else cubit.SCAN_RING
         no_pos = cubit.SCAN_TWO_PASS if k <= 3 else cubit.SCAN_RING
         with t.query(groups, flags=cubit.Q_ROWIDS) as r:
             assert r.info.scan_path == with_pos and r.count == len(want)
